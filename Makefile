@@ -1,0 +1,30 @@
+# Builds the sm_100a C-ABI library, the CPU oracle (test infrastructure) and, when /root/reference is mounted,
+# oracle/_ref. `python -c "import __graft_entry__ as g; g.build()"` drives this.
+NVCC      ?= nvcc
+CXX       ?= g++
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v
+CSRC      := hyrise_b200/csrc
+LIB       := hyrise_b200/lib/libhyrise_b200.so
+CU_SRCS   := $(wildcard $(CSRC)/*.cu)
+CU_OBJS   := $(patsubst $(CSRC)/%.cu,build/%.o,$(CU_SRCS))
+HDRS      := $(wildcard $(CSRC)/*.hpp) $(wildcard $(CSRC)/*.cuh) include/hyrise_b200.h
+
+all: $(LIB) oracle
+
+build/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p build
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
+
+$(LIB): $(CU_OBJS)
+	@mkdir -p hyrise_b200/lib
+	$(NVCC) $(ARCH) -shared -o $@ $(CU_OBJS) -cudart shared
+
+oracle:
+	$(MAKE) -C oracle
+
+clean:
+	rm -rf build $(LIB)
+	$(MAKE) -C oracle clean
+
+.PHONY: all oracle clean

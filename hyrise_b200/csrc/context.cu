@@ -1,0 +1,506 @@
+// Context, device column pool (arena + segment upload), handle registry, timing. Host-side only; no kernels here.
+//
+// The pool is the "new src/lib/storage device column pool" of the north star: device copies of the buffers behind
+// ValueSegment (value_segment.hpp:84-85), DictionarySegment (dictionary_segment.hpp:88-90) and
+// FrameOfReferenceSegment (frame_of_reference_segment.hpp:94-97), addressed by (table, chunk, column).
+#include <algorithm>
+#include <cstring>
+
+#include "internal.hpp"
+
+namespace hyb {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& message) { g_last_error = message; }
+
+int fail(int status, const std::string& message) {
+  g_last_error = message;
+  return status;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Arena
+// ---------------------------------------------------------------------------------------------------------------------
+void* Arena::alloc(size_t bytes) {
+  const size_t need = ((bytes + kTailPad + kAlign - 1) / kAlign) * kAlign;
+  if (_slabs.empty() || _slabs.back().offset + need > _slabs.back().size) {
+    // Slabs grow geometrically (64 MB .. 1 GB) so SF100 tables need tens, not thousands, of cudaMalloc calls.
+    size_t slab_size = std::max<size_t>(need, std::min<size_t>(size_t{1} << 30, std::max<size_t>(size_t{64} << 20,
+                                                                                                   _reserved / 2)));
+    slab_size = ((slab_size + kAlign - 1) / kAlign) * kAlign;
+    char* base = nullptr;
+    if (cudaMalloc(&base, slab_size) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    _slabs.push_back({base, slab_size, 0});
+    _reserved += slab_size;
+  }
+  auto& slab = _slabs.back();
+  void* ptr = slab.base + slab.offset;
+  slab.offset += need;
+  _used += need;
+  return ptr;
+}
+
+void Arena::release() {
+  for (auto& slab : _slabs) cudaFree(slab.base);
+  _slabs.clear();
+  _reserved = _used = 0;
+}
+
+Table::~Table() {
+  if (d_segments) cudaFree(d_segments);
+  if (d_chunk_row_start) cudaFree(d_chunk_row_start);
+  for (auto& entry : d_tile_starts) cudaFree(entry.second);
+}
+
+PosList::~PosList() {
+  if (d_row_ids) cudaFreeAsync(d_row_ids, stream);
+  if (d_chunk_end) cudaFreeAsync(d_chunk_end, stream);
+}
+
+JoinResult::~JoinResult() {
+  if (d_build) cudaFreeAsync(d_build, stream);
+  if (d_probe) cudaFreeAsync(d_probe, stream);
+  if (d_partition_offsets) cudaFreeAsync(d_partition_offsets, stream);
+}
+
+Table* find_table(hyb_context* context, hyb_table_t handle) {
+  auto it = context->tables.find(handle);
+  return it == context->tables.end() ? nullptr : it->second.get();
+}
+
+PosList* find_pos_list(hyb_context* context, hyb_pos_list_t handle) {
+  auto it = context->pos_lists.find(handle);
+  return it == context->pos_lists.end() ? nullptr : it->second.get();
+}
+
+int device_alloc(hyb_context* context, size_t bytes, void** out) {
+  *out = nullptr;
+  if (bytes == 0) bytes = 16;
+  HYB_CUDA(cudaMallocAsync(out, bytes, context->stream));
+  return HYB_OK;
+}
+
+void device_free(hyb_context* context, void* ptr) {
+  if (ptr) cudaFreeAsync(ptr, context->stream);
+}
+
+int sync_table_descriptors(hyb_context* context, Table* table) {
+  if (!table->dirty) return HYB_OK;
+  const uint32_t chunk_count = table->chunk_count();
+  if (table->d_chunk_capacity < chunk_count || !table->d_segments) {
+    // Descriptor arrays are read by kernels already queued on the stream: wait before replacing them.
+    HYB_CUDA(cudaStreamSynchronize(context->stream));
+    if (table->d_segments) cudaFree(table->d_segments);
+    if (table->d_chunk_row_start) cudaFree(table->d_chunk_row_start);
+    table->d_chunk_capacity = std::max<uint32_t>(chunk_count, 16);
+    HYB_CUDA(cudaMalloc(&table->d_segments, sizeof(DevSegment) * size_t{table->d_chunk_capacity} * table->column_count));
+    HYB_CUDA(cudaMalloc(&table->d_chunk_row_start, sizeof(uint64_t) * (size_t{table->d_chunk_capacity} + 1)));
+  }
+  // Column-major staging so that one column's descriptors are contiguous for the kernels.
+  std::vector<DevSegment> staged(size_t{chunk_count} * table->column_count);
+  for (uint32_t chunk = 0; chunk < chunk_count; ++chunk) {
+    for (uint32_t column = 0; column < table->column_count; ++column) {
+      staged[size_t{column} * chunk_count + chunk] = table->segments[size_t{chunk} * table->column_count + column];
+    }
+  }
+  if (!staged.empty()) {
+    HYB_CUDA(cudaMemcpyAsync(table->d_segments, staged.data(), staged.size() * sizeof(DevSegment),
+                             cudaMemcpyHostToDevice, context->stream));
+  }
+  HYB_CUDA(cudaMemcpyAsync(table->d_chunk_row_start, table->chunk_row_start.data(),
+                           table->chunk_row_start.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, context->stream));
+  // `staged` is pageable, so the copies above have completed with respect to the host buffer on return.
+  HYB_CUDA(cudaStreamSynchronize(context->stream));
+  for (auto& entry : table->d_tile_starts) cudaFree(entry.second);
+  table->d_tile_starts.clear();
+  table->h_tile_starts.clear();
+  table->dirty = false;
+  return HYB_OK;
+}
+
+int get_tile_starts(hyb_context* context, Table* table, uint32_t tile_rows, const uint32_t** out_device,
+                    uint32_t* out_tile_count) {
+  auto it = table->d_tile_starts.find(tile_rows);
+  if (it == table->d_tile_starts.end()) {
+    const uint32_t chunk_count = table->chunk_count();
+    std::vector<uint32_t> starts(chunk_count + 1);
+    uint32_t running = 0;
+    for (uint32_t chunk = 0; chunk < chunk_count; ++chunk) {
+      starts[chunk] = running;
+      running += (table->chunk_rows[chunk] + tile_rows - 1) / tile_rows;
+    }
+    starts[chunk_count] = running;
+    uint32_t* device = nullptr;
+    HYB_CUDA(cudaMalloc(&device, sizeof(uint32_t) * starts.size()));
+    HYB_CUDA(cudaMemcpy(device, starts.data(), sizeof(uint32_t) * starts.size(), cudaMemcpyHostToDevice));
+    it = table->d_tile_starts.emplace(tile_rows, device).first;
+    table->h_tile_starts.emplace(tile_rows, std::move(starts));
+  }
+  *out_device = it->second;
+  *out_tile_count = table->h_tile_starts[tile_rows].back();
+  return HYB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Timing: CUDA events on the context stream (the stream every kernel of this library is launched on).
+// ---------------------------------------------------------------------------------------------------------------------
+static void ensure_events(hyb_context* context) {
+  auto& timing = context->timing;
+  if (!timing.op_begin) {
+    cudaEventCreate(&timing.op_begin);
+    cudaEventCreate(&timing.op_end);
+    cudaEventCreate(&timing.kernel_begin);
+    cudaEventCreate(&timing.kernel_end);
+    cudaEventCreate(&timing.count_ready);
+    cudaHostAlloc(&timing.h_output_count, sizeof(uint64_t), cudaHostAllocPortable);
+    *timing.h_output_count = 0;
+  }
+}
+
+void timing_begin(hyb_context* context) {
+  ensure_events(context);
+  context->timing.valid = false;
+  cudaEventRecord(context->timing.op_begin, context->stream);
+}
+
+void timing_kernel_begin(hyb_context* context) { cudaEventRecord(context->timing.kernel_begin, context->stream); }
+
+void timing_kernel_end(hyb_context* context) { cudaEventRecord(context->timing.kernel_end, context->stream); }
+
+void timing_end(hyb_context* context, uint32_t launches, uint64_t algorithmic_bytes, uint64_t input_rows,
+                uint64_t output_rows) {
+  auto& timing = context->timing;
+  cudaEventRecord(timing.op_end, context->stream);
+  timing.stats = hyb_operator_stats{};
+  timing.stats.kernel_launches = launches;
+  timing.stats.algorithmic_bytes = algorithmic_bytes;
+  timing.stats.input_rows = input_rows;
+  timing.stats.output_rows = output_rows;
+  timing.d_output_count = nullptr;
+  timing.output_bytes_each = 0;
+  timing.valid = true;
+}
+
+// Operators whose output size is data dependent call this right after timing_end.
+void timing_output_count(hyb_context* context, const uint64_t* d_count, uint32_t bytes_each) {
+  auto& timing = context->timing;
+  timing.d_output_count = d_count;
+  timing.output_bytes_each = bytes_each;
+  cudaMemcpyAsync(timing.h_output_count, d_count, sizeof(uint64_t), cudaMemcpyDeviceToHost, context->stream);
+  cudaEventRecord(timing.count_ready, context->stream);
+}
+
+}  // namespace hyb
+
+using namespace hyb;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// C-ABI: context
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+int hyb_abi_version(void) { return HYB_ABI_VERSION; }
+
+const char* hyb_last_error(void) { return g_last_error.c_str(); }
+
+int hyb_device_count(int* out_count) {
+  HYB_CHECK(out_count, HYB_ERR_INVALID, "out_count is NULL");
+  int count = 0;
+  cudaError_t error = cudaGetDeviceCount(&count);
+  if (error != cudaSuccess) {
+    cudaGetLastError();
+    *out_count = 0;
+    return fail(HYB_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(error));
+  }
+  *out_count = count;
+  return HYB_OK;
+}
+
+int hyb_context_create(int device_index, hyb_context** out_context) {
+  HYB_CHECK(out_context, HYB_ERR_INVALID, "out_context is NULL");
+  *out_context = nullptr;
+  int count = 0;
+  HYB_CUDA(cudaGetDeviceCount(&count));
+  HYB_CHECK(device_index >= 0 && device_index < count, HYB_ERR_INVALID,
+            "device_index " + std::to_string(device_index) + " out of range (" + std::to_string(count) + " devices)");
+  DeviceGuard guard(device_index);
+  cudaDeviceProp prop{};
+  HYB_CUDA(cudaGetDeviceProperties(&prop, device_index));
+  HYB_CHECK(prop.major >= 10, HYB_ERR_UNSUPPORTED,
+            std::string("libhyrise_b200 is built for sm_100a only; device is ") + prop.name + " (sm_" +
+                std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+  auto context = std::make_unique<hyb_context>();
+  context->device = device_index;
+  context->sm_count = prop.multiProcessorCount;
+  HYB_CUDA(cudaStreamCreateWithFlags(&context->stream, cudaStreamNonBlocking));
+  // Keep freed result buffers in the stream-ordered pool: operators allocate their outputs on every call.
+  cudaMemPool_t pool = nullptr;
+  HYB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device_index));
+  uint64_t threshold = UINT64_MAX;
+  HYB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+  *out_context = context.release();
+  return HYB_OK;
+}
+
+int hyb_context_destroy(hyb_context* context) {
+  if (!context) return HYB_OK;
+  {
+    DeviceGuard guard(context->device);
+    cudaStreamSynchronize(context->stream);
+    context->pos_lists.clear();
+    context->join_results.clear();
+    context->aggregate_results.clear();
+    context->tables.clear();
+    if (context->timing.op_begin) {
+      cudaEventDestroy(context->timing.op_begin);
+      cudaEventDestroy(context->timing.op_end);
+      cudaEventDestroy(context->timing.kernel_begin);
+      cudaEventDestroy(context->timing.kernel_end);
+      cudaEventDestroy(context->timing.count_ready);
+      cudaFreeHost(context->timing.h_output_count);
+    }
+    cudaStreamSynchronize(context->stream);
+    cudaStreamDestroy(context->stream);
+  }
+  delete context;
+  return HYB_OK;
+}
+
+int hyb_context_synchronize(hyb_context* context) {
+  HYB_CHECK(context, HYB_ERR_INVALID, "context is NULL");
+  DeviceGuard guard(context->device);
+  HYB_CUDA(cudaStreamSynchronize(context->stream));
+  return HYB_OK;
+}
+
+int hyb_context_stream(hyb_context* context, void** out_stream) {
+  HYB_CHECK(context && out_stream, HYB_ERR_INVALID, "NULL argument");
+  *out_stream = static_cast<void*>(context->stream);
+  return HYB_OK;
+}
+
+int hyb_host_alloc(size_t bytes, void** out_ptr) {
+  HYB_CHECK(out_ptr, HYB_ERR_INVALID, "out_ptr is NULL");
+  *out_ptr = nullptr;
+  HYB_CUDA(cudaHostAlloc(out_ptr, bytes == 0 ? 16 : bytes, cudaHostAllocPortable));
+  return HYB_OK;
+}
+
+int hyb_host_free(void* ptr) {
+  if (ptr) HYB_CUDA(cudaFreeHost(ptr));
+  return HYB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// C-ABI: device column pool
+// ---------------------------------------------------------------------------------------------------------------------
+static int validate_segment(const hyb_segment_desc& desc, uint32_t chunk, uint32_t column) {
+  const std::string where = " (chunk " + std::to_string(chunk) + ", column " + std::to_string(column) + ")";
+  HYB_CHECK(desc.data_type >= HYB_TYPE_INT32 && desc.data_type <= HYB_TYPE_STRING, HYB_ERR_INVALID,
+            "unknown data_type" + where);
+  switch (desc.encoding) {
+    case HYB_ENC_UNENCODED:
+      HYB_CHECK(desc.data_type != HYB_TYPE_STRING, HYB_ERR_UNSUPPORTED,
+                "unencoded string segments stay on the CPU" + where);
+      HYB_CHECK(desc.values || desc.row_count == 0, HYB_ERR_INVALID, "ValueSegment without values" + where);
+      break;
+    case HYB_ENC_DICTIONARY:
+      HYB_CHECK(desc.attribute_vector || desc.row_count == 0, HYB_ERR_INVALID,
+                "DictionarySegment without attribute vector" + where);
+      HYB_CHECK(desc.data_type == HYB_TYPE_STRING || desc.values || desc.dictionary_size == 0, HYB_ERR_INVALID,
+                "numeric DictionarySegment without dictionary" + where);
+      HYB_CHECK(desc.vector_type >= HYB_VEC_FIXED_1B && desc.vector_type <= HYB_VEC_BITPACKED, HYB_ERR_INVALID,
+                "bad vector_type" + where);
+      break;
+    case HYB_ENC_FRAME_OF_REFERENCE:
+      HYB_CHECK(desc.data_type == HYB_TYPE_INT32, HYB_ERR_INVALID, "FrameOfReference is int32 only" + where);
+      HYB_CHECK((desc.values && desc.attribute_vector) || desc.row_count == 0, HYB_ERR_INVALID,
+                "FrameOfReferenceSegment without minima/offsets" + where);
+      HYB_CHECK(desc.vector_type >= HYB_VEC_FIXED_1B && desc.vector_type <= HYB_VEC_BITPACKED, HYB_ERR_INVALID,
+                "bad vector_type" + where);
+      break;
+    default:
+      return fail(HYB_ERR_UNSUPPORTED, "encoding " + std::to_string(desc.encoding) + " is not on the GPU path" + where);
+  }
+  if (desc.vector_type == HYB_VEC_BITPACKED) {
+    HYB_CHECK(desc.bit_width >= 1 && desc.bit_width <= 32, HYB_ERR_INVALID, "bit_width out of range" + where);
+  }
+  return HYB_OK;
+}
+
+static int upload_buffer(hyb_context* context, Table* table, const void* host, size_t bytes, const void** out_device) {
+  *out_device = nullptr;
+  if (host == nullptr) return HYB_OK;
+  void* device = table->arena.alloc(bytes);
+  HYB_CHECK(device, HYB_ERR_OOM, "device column pool: out of memory allocating " + std::to_string(bytes) + " bytes");
+  if (bytes) HYB_CUDA(cudaMemcpyAsync(device, host, bytes, cudaMemcpyHostToDevice, context->stream));
+  *out_device = device;
+  return HYB_OK;
+}
+
+static int append_chunk_locked(hyb_context* context, Table* table, const hyb_segment_desc* segments) {
+  const uint32_t chunk = table->chunk_count();
+  const uint32_t rows = table->column_count ? segments[0].row_count : 0;
+  std::vector<DevSegment> staged(table->column_count);
+  for (uint32_t column = 0; column < table->column_count; ++column) {
+    const auto& desc = segments[column];
+    HYB_TRY(validate_segment(desc, chunk, column));
+    HYB_CHECK(desc.row_count == rows, HYB_ERR_INVALID, "segments of one chunk must have equal row counts");
+    if (chunk == 0) {
+      table->column_types[column] = desc.data_type;
+    } else {
+      HYB_CHECK(table->column_types[column] == desc.data_type, HYB_ERR_INVALID,
+                "column " + std::to_string(column) + " changes data type between chunks");
+    }
+    DevSegment dev{};
+    dev.row_count = rows;
+    dev.dict_size = desc.dictionary_size;
+    dev.encoding = static_cast<uint8_t>(desc.encoding);
+    dev.data_type = static_cast<uint8_t>(desc.data_type);
+    dev.vector_type = static_cast<uint8_t>(desc.encoding == HYB_ENC_UNENCODED ? HYB_VEC_NONE : desc.vector_type);
+    dev.bit_width = static_cast<uint8_t>(desc.vector_type == HYB_VEC_BITPACKED ? desc.bit_width : 0);
+    const size_t element = data_type_size(desc.data_type);
+    switch (desc.encoding) {
+      case HYB_ENC_UNENCODED:
+        HYB_TRY(upload_buffer(context, table, desc.values, element * rows, &dev.values));
+        break;
+      case HYB_ENC_DICTIONARY:
+        if (desc.data_type != HYB_TYPE_STRING) {
+          HYB_TRY(upload_buffer(context, table, desc.values, element * desc.dictionary_size, &dev.values));
+        }
+        HYB_TRY(upload_buffer(context, table, desc.attribute_vector, vector_bytes(desc.vector_type, desc.bit_width, rows),
+                              &dev.av));
+        if (desc.dictionary_codes) {
+          const void* codes = nullptr;
+          HYB_TRY(upload_buffer(context, table, desc.dictionary_codes, sizeof(uint64_t) * desc.dictionary_size, &codes));
+          dev.dict_codes = static_cast<const uint64_t*>(codes);
+        }
+        break;
+      case HYB_ENC_FRAME_OF_REFERENCE: {
+        const size_t blocks = (size_t{rows} + HYB_FOR_BLOCK_SIZE - 1) / HYB_FOR_BLOCK_SIZE;
+        HYB_TRY(upload_buffer(context, table, desc.values, sizeof(int32_t) * blocks, &dev.values));
+        HYB_TRY(upload_buffer(context, table, desc.attribute_vector, vector_bytes(desc.vector_type, desc.bit_width, rows),
+                              &dev.av));
+        break;
+      }
+    }
+    if (desc.nulls && desc.encoding != HYB_ENC_DICTIONARY) {
+      const void* nulls = nullptr;
+      HYB_TRY(upload_buffer(context, table, desc.nulls, rows, &nulls));
+      dev.nulls = static_cast<const uint8_t*>(nulls);
+    }
+    staged[column] = dev;
+  }
+  table->segments.insert(table->segments.end(), staged.begin(), staged.end());
+  if (chunk > 0 && table->chunk_rows.back() != table->chunk_rows.front()) table->uniform_chunks = false;
+  if (chunk > 0 && rows > table->chunk_rows.front()) table->uniform_chunks = false;
+  table->chunk_rows.push_back(rows);
+  table->chunk_row_start.push_back(table->chunk_row_start.back() + rows);
+  table->max_chunk_rows = std::max(table->max_chunk_rows, rows);
+  table->dirty = true;
+  return HYB_OK;
+}
+
+int hyb_table_create(hyb_context* context, uint32_t column_count, hyb_table_t* out_table) {
+  HYB_CHECK(context && out_table, HYB_ERR_INVALID, "NULL argument");
+  HYB_CHECK(column_count > 0, HYB_ERR_INVALID, "a table needs at least one column");
+  std::lock_guard<std::mutex> lock(context->mutex);
+  auto table = std::make_unique<Table>();
+  table->column_count = column_count;
+  table->column_types.assign(column_count, -1);
+  table->chunk_row_start.push_back(0);
+  const auto handle = context->next_handle++;
+  context->tables.emplace(handle, std::move(table));
+  *out_table = handle;
+  return HYB_OK;
+}
+
+int hyb_table_append_chunk(hyb_context* context, hyb_table_t handle, const hyb_segment_desc* segments) {
+  HYB_CHECK(context && segments, HYB_ERR_INVALID, "NULL argument");
+  DeviceGuard guard(context->device);
+  std::lock_guard<std::mutex> lock(context->mutex);
+  auto* table = find_table(context, handle);
+  HYB_CHECK(table, HYB_ERR_NOT_FOUND, "unknown table handle");
+  HYB_TRY(append_chunk_locked(context, table, segments));
+  // The source buffers are borrowed only for the duration of the call.
+  HYB_CUDA(cudaStreamSynchronize(context->stream));
+  return HYB_OK;
+}
+
+int hyb_table_upload(hyb_context* context, const hyb_table_view* view, hyb_table_t* out_table) {
+  HYB_CHECK(context && view && out_table, HYB_ERR_INVALID, "NULL argument");
+  HYB_CHECK(view->column_count > 0, HYB_ERR_INVALID, "a table needs at least one column");
+  HYB_CHECK(view->segments || view->chunk_count == 0, HYB_ERR_INVALID, "view->segments is NULL");
+  HYB_TRY(hyb_table_create(context, view->column_count, out_table));
+  DeviceGuard guard(context->device);
+  std::lock_guard<std::mutex> lock(context->mutex);
+  auto* table = find_table(context, *out_table);
+  int status = HYB_OK;
+  for (uint32_t chunk = 0; chunk < view->chunk_count && status == HYB_OK; ++chunk) {
+    status = append_chunk_locked(context, table, view->segments + size_t{chunk} * view->column_count);
+  }
+  if (status == HYB_OK) {
+    cudaError_t error = cudaStreamSynchronize(context->stream);
+    if (error != cudaSuccess) status = fail(HYB_ERR_CUDA, std::string("upload: ") + cudaGetErrorString(error));
+  }
+  if (status != HYB_OK) {
+    cudaStreamSynchronize(context->stream);
+    context->tables.erase(*out_table);
+    *out_table = 0;
+  }
+  return status;
+}
+
+int hyb_table_drop(hyb_context* context, hyb_table_t handle) {
+  HYB_CHECK(context, HYB_ERR_INVALID, "context is NULL");
+  DeviceGuard guard(context->device);
+  std::lock_guard<std::mutex> lock(context->mutex);
+  auto it = context->tables.find(handle);
+  HYB_CHECK(it != context->tables.end(), HYB_ERR_NOT_FOUND, "unknown table handle");
+  HYB_CUDA(cudaStreamSynchronize(context->stream));
+  context->tables.erase(it);
+  return HYB_OK;
+}
+
+int hyb_table_info(hyb_context* context, hyb_table_t handle, uint32_t* out_chunk_count, uint32_t* out_column_count,
+                   uint64_t* out_row_count, uint64_t* out_device_bytes) {
+  HYB_CHECK(context, HYB_ERR_INVALID, "context is NULL");
+  std::lock_guard<std::mutex> lock(context->mutex);
+  auto* table = find_table(context, handle);
+  HYB_CHECK(table, HYB_ERR_NOT_FOUND, "unknown table handle");
+  if (out_chunk_count) *out_chunk_count = table->chunk_count();
+  if (out_column_count) *out_column_count = table->column_count;
+  if (out_row_count) *out_row_count = table->row_count();
+  if (out_device_bytes) *out_device_bytes = table->arena.bytes_used();
+  return HYB_OK;
+}
+
+int hyb_last_operator_stats(hyb_context* context, hyb_operator_stats* out_stats) {
+  HYB_CHECK(context && out_stats, HYB_ERR_INVALID, "NULL argument");
+  DeviceGuard guard(context->device);
+  std::lock_guard<std::mutex> lock(context->mutex);
+  auto& timing = context->timing;
+  HYB_CHECK(timing.valid, HYB_ERR_INVALID, "no operator has run on this context yet");
+  HYB_CUDA(cudaEventSynchronize(timing.op_end));
+  float op_ms = 0.f, kernel_ms = 0.f;
+  HYB_CUDA(cudaEventElapsedTime(&op_ms, timing.op_begin, timing.op_end));
+  HYB_CUDA(cudaEventElapsedTime(&kernel_ms, timing.kernel_begin, timing.kernel_end));
+  timing.stats.device_ms = op_ms;
+  timing.stats.dominant_kernel_ms = kernel_ms;
+  if (timing.d_output_count) {
+    HYB_CUDA(cudaEventSynchronize(timing.count_ready));
+    uint64_t count = *timing.h_output_count;
+    if (count == ~uint64_t{0}) count = 0;
+    timing.stats.output_rows = count;
+    timing.stats.algorithmic_bytes += count * timing.output_bytes_each;
+    timing.d_output_count = nullptr;
+  }
+  *out_stats = timing.stats;
+  return HYB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,240 @@
+// Internal host-side structures of libhyrise_b200 (not part of the C-ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/hyrise_b200.h"
+
+namespace hyb {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Device-visible segment descriptor. One per (chunk, column); arrays of these are what every kernel indexes, so a single
+// launch covers all chunks of a column (9 157 chunks at SF100) instead of one launch per chunk.
+// ---------------------------------------------------------------------------------------------------------------------
+struct DevSegment {
+  const void* values;           // unencoded values | dictionary | FoR block minima
+  const void* av;               // attribute vector (value-IDs) | FoR offsets, in vector_type layout
+  const uint8_t* nulls;         // 1 byte per row or nullptr
+  const uint64_t* dict_codes;   // chunk-independent group-by codes per dictionary entry or nullptr
+  uint32_t row_count;
+  uint32_t dict_size;           // == NULL value-ID for dictionary segments
+  uint8_t encoding;
+  uint8_t data_type;
+  uint8_t vector_type;
+  uint8_t bit_width;
+  uint32_t pad;
+};
+static_assert(sizeof(DevSegment) == 48, "DevSegment layout");
+
+// Bump allocator over large device slabs: one table = a handful of cudaMalloc calls instead of one per segment.
+class Arena {
+ public:
+  static constexpr size_t kAlign = 256;
+  static constexpr size_t kTailPad = 64;  // kernels may read one 16-byte vector past the last row
+  ~Arena() { release(); }
+  void* alloc(size_t bytes);
+  void release();
+  size_t bytes_reserved() const { return _reserved; }
+  size_t bytes_used() const { return _used; }
+
+ private:
+  struct Slab {
+    char* base;
+    size_t size;
+    size_t offset;
+  };
+  std::vector<Slab> _slabs;
+  size_t _reserved = 0;
+  size_t _used = 0;
+};
+
+struct Table {
+  uint32_t column_count = 0;
+  std::vector<uint32_t> chunk_rows;         // rows per chunk
+  std::vector<uint64_t> chunk_row_start;    // exclusive prefix, chunk_count + 1 entries
+  std::vector<DevSegment> segments;         // host copy, chunk-major: [chunk * column_count + column]
+  std::vector<int32_t> column_types;        // hyb_data_type per column (from the first chunk)
+  Arena arena;
+
+  // Device mirrors, rebuilt lazily when `dirty`.
+  DevSegment* d_segments = nullptr;         // column-major: [column * chunk_count + chunk]
+  uint64_t* d_chunk_row_start = nullptr;    // chunk_count + 1
+  uint32_t d_chunk_capacity = 0;
+  bool dirty = true;
+  std::map<uint32_t, uint32_t*> d_tile_starts;  // tile_rows -> device prefix array (chunk_count + 1)
+  std::map<uint32_t, std::vector<uint32_t>> h_tile_starts;
+
+  uint32_t chunk_count() const { return static_cast<uint32_t>(chunk_rows.size()); }
+  uint64_t row_count() const { return chunk_row_start.empty() ? 0 : chunk_row_start.back(); }
+  // Largest chunk and whether all chunks but the last share one size (lets kernels divide instead of search).
+  uint32_t max_chunk_rows = 0;
+  bool uniform_chunks = true;
+  ~Table();
+};
+
+struct PosList {
+  hyb_table_t table = 0;
+  uint32_t chunk_count = 0;
+  hyb_row_id* d_row_ids = nullptr;      // flat, chunk-major, ascending offsets inside a chunk
+  uint64_t capacity = 0;
+  uint64_t* d_chunk_end = nullptr;      // inclusive prefix per chunk (chunk_count entries) + total at [chunk_count]
+  std::vector<uint64_t> h_chunk_offsets;  // chunk_count + 1, filled on first query
+  bool host_valid = false;
+  cudaStream_t stream = nullptr;
+  ~PosList();
+};
+
+struct JoinResult {
+  int32_t mode = 0;
+  int32_t radix_bits = 0;
+  uint32_t partition_count = 1;
+  hyb_row_id* d_build = nullptr;
+  hyb_row_id* d_probe = nullptr;
+  uint64_t* d_partition_offsets = nullptr;  // partition_count + 1
+  uint64_t capacity = 0;
+  std::vector<uint64_t> h_partition_offsets;
+  bool host_valid = false;
+  cudaStream_t stream = nullptr;
+  ~JoinResult();
+};
+
+struct AggregateColumn {
+  int32_t value_type = 0;             // hyb_data_type of the result
+  std::vector<uint8_t> values;        // group_count * element size
+  std::vector<uint8_t> nulls;         // group_count
+};
+
+struct AggregateResult {
+  uint64_t group_count = 0;
+  int32_t used_immediate_keys = 0;
+  std::vector<hyb_row_id> row_ids;
+  std::vector<AggregateColumn> columns;
+};
+
+struct OperatorTiming {
+  cudaEvent_t op_begin = nullptr, op_end = nullptr, kernel_begin = nullptr, kernel_end = nullptr;
+  cudaEvent_t count_ready = nullptr;
+  bool valid = false;
+  hyb_operator_stats stats{};
+  // Output cardinality is only known on the device when the operator returns: it is copied into this pinned slot.
+  const uint64_t* d_output_count = nullptr;
+  uint64_t* h_output_count = nullptr;
+  uint32_t output_bytes_each = 0;
+};
+
+}  // namespace hyb
+
+struct hyb_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  std::mutex mutex;  // serialises enqueue + registry access; device work itself is asynchronous
+  uint64_t next_handle = 1;
+  std::unordered_map<uint64_t, std::unique_ptr<hyb::Table>> tables;
+  std::unordered_map<uint64_t, std::unique_ptr<hyb::PosList>> pos_lists;
+  std::unordered_map<uint64_t, std::unique_ptr<hyb::JoinResult>> join_results;
+  std::unordered_map<uint64_t, std::unique_ptr<hyb::AggregateResult>> aggregate_results;
+  hyb::OperatorTiming timing;
+};
+
+namespace hyb {
+
+// Error plumbing -------------------------------------------------------------------------------------------------------
+void set_error(const std::string& message);
+int fail(int status, const std::string& message);
+
+#define HYB_CUDA(expr)                                                                                      \
+  do {                                                                                                      \
+    cudaError_t _e = (expr);                                                                                \
+    if (_e != cudaSuccess) {                                                                                \
+      return ::hyb::fail(_e == cudaErrorMemoryAllocation ? HYB_ERR_OOM : HYB_ERR_CUDA,                      \
+                         std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" +       \
+                             std::to_string(__LINE__) + ")");                                               \
+    }                                                                                                       \
+  } while (0)
+
+#define HYB_CHECK(cond, status, message)        \
+  do {                                          \
+    if (!(cond)) {                              \
+      return ::hyb::fail((status), (message));  \
+    }                                           \
+  } while (0)
+
+#define HYB_TRY(expr)            \
+  do {                           \
+    int _s = (expr);             \
+    if (_s != HYB_OK) return _s; \
+  } while (0)
+
+// Helpers implemented in context.cu ---------------------------------------------------------------------------------
+class DeviceGuard {
+ public:
+  explicit DeviceGuard(int device) {
+    cudaGetDevice(&_previous);
+    if (_previous != device) cudaSetDevice(device);
+    _device = device;
+  }
+  ~DeviceGuard() {
+    if (_previous != _device) cudaSetDevice(_previous);
+  }
+
+ private:
+  int _previous = 0, _device = 0;
+};
+
+Table* find_table(hyb_context* context, hyb_table_t handle);
+PosList* find_pos_list(hyb_context* context, hyb_pos_list_t handle);
+// Make the table's device descriptor arrays current (call with context->mutex held).
+int sync_table_descriptors(hyb_context* context, Table* table);
+// Device prefix array: tiles of `tile_rows` rows never straddle a chunk; entry c = number of tiles before chunk c.
+int get_tile_starts(hyb_context* context, Table* table, uint32_t tile_rows, const uint32_t** out_device,
+                    uint32_t* out_tile_count);
+// Stream-ordered scratch/result memory.
+int device_alloc(hyb_context* context, size_t bytes, void** out);
+void device_free(hyb_context* context, void* ptr);
+
+void timing_begin(hyb_context* context);
+void timing_kernel_begin(hyb_context* context);
+void timing_kernel_end(hyb_context* context);
+void timing_end(hyb_context* context, uint32_t launches, uint64_t algorithmic_bytes, uint64_t input_rows,
+                uint64_t output_rows);
+void timing_output_count(hyb_context* context, const uint64_t* d_count, uint32_t bytes_each);
+
+inline size_t data_type_size(int32_t data_type) {
+  switch (data_type) {
+    case HYB_TYPE_INT32:
+    case HYB_TYPE_FLOAT32:
+      return 4;
+    case HYB_TYPE_INT64:
+    case HYB_TYPE_FLOAT64:
+      return 8;
+    default:
+      return 0;
+  }
+}
+
+inline size_t vector_bytes(int32_t vector_type, int32_t bit_width, uint32_t rows) {
+  switch (vector_type) {
+    case HYB_VEC_FIXED_1B:
+      return rows;
+    case HYB_VEC_FIXED_2B:
+      return size_t{rows} * 2;
+    case HYB_VEC_FIXED_4B:
+      return size_t{rows} * 4;
+    case HYB_VEC_BITPACKED:
+      return ((size_t{rows} * bit_width + 63) / 64) * 8;
+    default:
+      return 0;
+  }
+}
+
+}  // namespace hyb

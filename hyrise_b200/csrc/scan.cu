@@ -1,0 +1,788 @@
+// TableScan on the device: predicate evaluation on encoded segments + order-preserving compaction into a RowIDPosList.
+//
+// Replaces the hot loop AbstractTableScanImpl::_scan_with_iterators / _simd_scan_with_iterators
+// (src/lib/operators/table_scan/abstract_table_scan_impl.hpp:56-242) and the per-chunk dispatch of
+// ColumnVsValueTableScanImpl (column_vs_value_table_scan_impl.cpp:43-272), ColumnBetweenTableScanImpl
+// (column_between_table_scan_impl.cpp:42-226) and ColumnIsNullTableScanImpl for Value / Dictionary / FrameOfReference
+// segments. One launch scans every chunk of the column:
+//
+//   scan_prepare_kernel   one thread per chunk: turns the predicate into a per-chunk test. Dictionary segments get the
+//                         value-ID range the reference derives from lower_bound/upper_bound (binary search on the
+//                         device-resident dictionary); "no row can match" chunks are marked so the scan skips their
+//                         bytes (the reference's early-outs, column_vs_value_table_scan_impl.cpp:228-272).
+//   scan_kernel           persistent CTAs claim 4096-row tiles through an atomic ticket. Per tile: 128-bit streaming
+//                         loads of value-IDs / values, in-register decode, 8 predicates per thread -> bit mask, warp
+//                         prefix sums, one decoupled look-back per tile for the global output offset, matches staged in
+//                         shared memory and written as coalesced 8-byte RowIDs. Output order == reference order
+//                         (chunk by chunk, ascending ChunkOffset), in a single pass over the input.
+//
+// HBM traffic per launch = N * (bytes per row of the scanned column) + M * 8 (RowIDs) — the compulsory bytes.
+#include <algorithm>
+#include <cmath>
+#include <limits>
+
+#include "device_utils.cuh"
+#include "internal.hpp"
+#include "predicate.cuh"
+
+namespace hyb {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanWarps = kScanThreads / 32;
+constexpr int kScanIterations = 2;                       // 8 rows per thread per iteration
+constexpr int kScanWarpRows = 32 * 8 * kScanIterations;  // rows owned by one warp in a tile (contiguous)
+constexpr int kScanTileRows = kScanWarps * kScanWarpRows;  // 4096
+
+struct ScanPredicateDevice {
+  int32_t condition;
+  int32_t data_type;
+  hyb_value lower;
+  hyb_value upper;
+  const uint32_t* value_id_bounds;  // device copy or nullptr
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Per-chunk predicate preparation
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ uint32_t device_lower_bound(const T* dictionary, uint32_t size, T value) {
+  uint32_t lo = 0, hi = size;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (dictionary[mid] < value) {
+      lo = mid + 1;
+    } else {
+      hi = mid;
+    }
+  }
+  return lo;
+}
+
+template <typename T>
+__device__ uint32_t device_upper_bound(const T* dictionary, uint32_t size, T value) {
+  uint32_t lo = 0, hi = size;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (!(value < dictionary[mid])) {
+      lo = mid + 1;
+    } else {
+      hi = mid;
+    }
+  }
+  return lo;
+}
+
+__device__ void dictionary_bounds(const DevSegment& segment, hyb_value value, uint32_t& lower, uint32_t& upper) {
+  const uint32_t size = segment.dict_size;
+  switch (segment.data_type) {
+    case HYB_TYPE_INT32:
+      lower = device_lower_bound(static_cast<const int32_t*>(segment.values), size, value.i32);
+      upper = device_upper_bound(static_cast<const int32_t*>(segment.values), size, value.i32);
+      break;
+    case HYB_TYPE_INT64:
+      lower = device_lower_bound(static_cast<const long long*>(segment.values), size, static_cast<long long>(value.i64));
+      upper = device_upper_bound(static_cast<const long long*>(segment.values), size, static_cast<long long>(value.i64));
+      break;
+    case HYB_TYPE_FLOAT32:
+      lower = device_lower_bound(static_cast<const float*>(segment.values), size, value.f32);
+      upper = device_upper_bound(static_cast<const float*>(segment.values), size, value.f32);
+      break;
+    default:
+      lower = device_lower_bound(static_cast<const double*>(segment.values), size, value.f64);
+      upper = device_upper_bound(static_cast<const double*>(segment.values), size, value.f64);
+      break;
+  }
+}
+
+__device__ __forceinline__ bool is_between(int32_t condition) {
+  return condition >= HYB_PRED_BETWEEN_INCLUSIVE && condition <= HYB_PRED_BETWEEN_EXCLUSIVE;
+}
+__device__ __forceinline__ bool lower_inclusive(int32_t condition) {
+  return condition == HYB_PRED_BETWEEN_INCLUSIVE || condition == HYB_PRED_BETWEEN_UPPER_EXCLUSIVE;
+}
+__device__ __forceinline__ bool upper_inclusive(int32_t condition) {
+  return condition == HYB_PRED_BETWEEN_INCLUSIVE || condition == HYB_PRED_BETWEEN_LOWER_EXCLUSIVE;
+}
+
+__device__ long long value_as_int(hyb_value value, int32_t data_type) {
+  return data_type == HYB_TYPE_INT32 ? static_cast<long long>(value.i32) : static_cast<long long>(value.i64);
+}
+__device__ double value_as_float(hyb_value value, int32_t data_type) {
+  return data_type == HYB_TYPE_FLOAT32 ? static_cast<double>(value.f32) : value.f64;
+}
+
+__global__ void scan_prepare_kernel(const DevSegment* __restrict__ segments, uint32_t chunk_count,
+                                    ScanPredicateDevice predicate, ChunkTest* __restrict__ tests) {
+  const uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x;
+  if (chunk >= chunk_count) return;
+  const DevSegment segment = segments[chunk];
+  ChunkTest test{};
+  test.mode = kTestNone;
+  const int32_t condition = predicate.condition;
+
+  if (segment.row_count == 0) {
+    tests[chunk] = test;
+    return;
+  }
+
+  if (segment.encoding == HYB_ENC_DICTIONARY) {
+    // Value-ID range [lo, hi) following column_vs_value_table_scan_impl.cpp:96-110 and
+    // column_between_table_scan_impl.cpp:112-125. INVALID_VALUE_ID ("past the end") is represented as dict_size.
+    const uint32_t size = segment.dict_size;
+    uint32_t lo = 0, hi = 0;
+    bool negate = false;
+    if (condition == HYB_PRED_IS_NULL) {
+      lo = size;
+      hi = size + 1;
+    } else if (condition == HYB_PRED_IS_NOT_NULL) {
+      lo = 0;
+      hi = size;
+    } else if (is_between(condition)) {
+      uint32_t lower_lb, lower_ub, upper_lb, upper_ub;
+      if (predicate.value_id_bounds) {
+        lower_lb = min(predicate.value_id_bounds[4 * chunk + 0], size);
+        lower_ub = min(predicate.value_id_bounds[4 * chunk + 1], size);
+        upper_lb = min(predicate.value_id_bounds[4 * chunk + 2], size);
+        upper_ub = min(predicate.value_id_bounds[4 * chunk + 3], size);
+      } else {
+        dictionary_bounds(segment, predicate.lower, lower_lb, lower_ub);
+        dictionary_bounds(segment, predicate.upper, upper_lb, upper_ub);
+      }
+      lo = lower_inclusive(condition) ? lower_lb : lower_ub;
+      hi = upper_inclusive(condition) ? upper_ub : upper_lb;
+    } else {
+      uint32_t lb, ub;
+      if (predicate.value_id_bounds) {
+        lb = min(predicate.value_id_bounds[2 * chunk + 0], size);
+        ub = min(predicate.value_id_bounds[2 * chunk + 1], size);
+      } else {
+        dictionary_bounds(segment, predicate.lower, lb, ub);
+      }
+      switch (condition) {
+        case HYB_PRED_EQUALS:
+          lo = lb;
+          hi = ub;
+          break;
+        case HYB_PRED_NOT_EQUALS:
+          lo = lb;
+          hi = ub;
+          negate = true;
+          break;
+        case HYB_PRED_LESS_THAN:
+          lo = 0;
+          hi = lb;
+          break;
+        case HYB_PRED_LESS_THAN_EQUALS:
+          lo = 0;
+          hi = ub;
+          break;
+        case HYB_PRED_GREATER_THAN:
+          lo = ub;
+          hi = size;
+          break;
+        default:  // HYB_PRED_GREATER_THAN_EQUALS
+          lo = lb;
+          hi = size;
+          break;
+      }
+    }
+    if (negate && lo >= hi) {
+      // value not in the dictionary: every non-NULL row matches
+      negate = false;
+      lo = 0;
+      hi = size;
+    }
+    if (!negate && lo >= hi) {
+      test.mode = kTestNone;
+    } else {
+      test.mode = kTestIdRange;
+      test.negate = negate;
+      test.id_lo = lo;
+      test.id_span = hi - lo;
+    }
+    tests[chunk] = test;
+    return;
+  }
+
+  // ValueSegment / FrameOfReferenceSegment: typed comparison (type_comparison.hpp:87-180).
+  if (condition == HYB_PRED_IS_NULL || condition == HYB_PRED_IS_NOT_NULL) {
+    if (!segment.nulls) {
+      if (condition == HYB_PRED_IS_NULL) {
+        test.mode = kTestNone;
+      } else {
+        test.mode = kTestNull;  // no null vector: every row matches
+        test.want_null = 0;
+      }
+    } else {
+      test.mode = kTestNull;
+      test.want_null = condition == HYB_PRED_IS_NULL;
+    }
+    tests[chunk] = test;
+    return;
+  }
+
+  const bool integral = segment.data_type == HYB_TYPE_INT32 || segment.data_type == HYB_TYPE_INT64;
+  if (integral) {
+    const long long type_min = segment.data_type == HYB_TYPE_INT32 ? INT_MIN : LLONG_MIN;
+    const long long type_max = segment.data_type == HYB_TYPE_INT32 ? INT_MAX : LLONG_MAX;
+    long long lo = type_min, hi = type_max;
+    bool empty = false, negate = false;
+    const long long a = value_as_int(predicate.lower, segment.data_type);
+    const long long b = value_as_int(predicate.upper, segment.data_type);
+    switch (condition) {
+      case HYB_PRED_EQUALS:
+        lo = hi = a;
+        break;
+      case HYB_PRED_NOT_EQUALS:
+        lo = hi = a;
+        negate = true;
+        break;
+      case HYB_PRED_LESS_THAN:
+        if (a == type_min) empty = true;
+        hi = a - 1;
+        break;
+      case HYB_PRED_LESS_THAN_EQUALS:
+        hi = a;
+        break;
+      case HYB_PRED_GREATER_THAN:
+        if (a == type_max) empty = true;
+        lo = a + 1;
+        break;
+      case HYB_PRED_GREATER_THAN_EQUALS:
+        lo = a;
+        break;
+      default: {  // BETWEEN (column_between_table_scan_impl.cpp:88-97: empty integer ranges produce no output)
+        lo = a;
+        hi = b;
+        if (!lower_inclusive(condition)) {
+          if (a == type_max) empty = true;
+          lo = a + 1;
+        }
+        if (!upper_inclusive(condition)) {
+          if (b == type_min) empty = true;
+          hi = b - 1;
+        }
+        break;
+      }
+    }
+    if (empty || lo > hi) {
+      test.mode = kTestNone;
+    } else {
+      test.mode = kTestInt;
+      test.negate = negate;
+      test.int_lo = lo;
+      test.int_hi = hi;
+    }
+  } else {
+    const double a = value_as_float(predicate.lower, segment.data_type);
+    const double b = value_as_float(predicate.upper, segment.data_type);
+    test.mode = kTestFloat;
+    test.float_lo = -INFINITY;
+    test.float_hi = INFINITY;
+    test.float_lo_inclusive = 1;
+    test.float_hi_inclusive = 1;
+    switch (condition) {
+      case HYB_PRED_EQUALS:
+        test.float_lo = test.float_hi = a;
+        break;
+      case HYB_PRED_NOT_EQUALS:
+        test.float_lo = test.float_hi = a;
+        test.negate = 1;
+        break;
+      case HYB_PRED_LESS_THAN:
+        test.float_hi = a;
+        test.float_hi_inclusive = 0;
+        break;
+      case HYB_PRED_LESS_THAN_EQUALS:
+        test.float_hi = a;
+        break;
+      case HYB_PRED_GREATER_THAN:
+        test.float_lo = a;
+        test.float_lo_inclusive = 0;
+        break;
+      case HYB_PRED_GREATER_THAN_EQUALS:
+        test.float_lo = a;
+        break;
+      default:
+        test.float_lo = a;
+        test.float_hi = b;
+        test.float_lo_inclusive = lower_inclusive(condition);
+        test.float_hi_inclusive = upper_inclusive(condition);
+        break;
+    }
+  }
+  tests[chunk] = test;
+}
+
+struct ScanParams {
+  const DevSegment* segments;     // descriptors of the scanned column, one per chunk
+  const ChunkTest* tests;         // per chunk
+  const uint32_t* tile_starts;    // chunk_count + 1
+  uint32_t chunk_count;
+  uint32_t tile_count;
+  unsigned long long* tile_status;  // tile_count, zero-initialised
+  uint32_t* ticket;               // zero-initialised
+  hyb_row_id* out;                // capacity = table rows
+  unsigned long long* chunk_end;  // [chunk] = inclusive prefix after the chunk's last tile; [chunk_count] = total
+};
+
+__global__ void __launch_bounds__(kScanThreads) scan_kernel(const ScanParams params) {
+  __shared__ uint32_t s_offsets[kScanTileRows];
+  __shared__ uint32_t s_warp_totals[kScanWarps];
+  __shared__ uint32_t s_tile;
+  __shared__ uint32_t s_chunk;
+  __shared__ unsigned long long s_base;
+
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = threadIdx.x >> 5;
+
+  while (true) {
+    if (threadIdx.x == 0) {
+      const uint32_t tile = atomicAdd(params.ticket, 1u);
+      s_tile = tile;
+      if (tile < params.tile_count) s_chunk = find_owner(params.tile_starts, params.chunk_count, tile);
+    }
+    __syncthreads();  // also protects s_offsets / s_base of the previous tile
+    const uint32_t tile = s_tile;
+    if (tile >= params.tile_count) return;
+    const uint32_t chunk = s_chunk;
+    const DevSegment segment = params.segments[chunk];
+    const ChunkTest test = params.tests[chunk];
+    const uint32_t tile_in_chunk = tile - __ldg(params.tile_starts + chunk);
+    const uint32_t tile_row0 = tile_in_chunk * kScanTileRows;
+
+    // 1. predicate masks for this thread's 2 x 8 rows
+    uint32_t masks[kScanIterations];
+    uint32_t packed_counts = 0;  // iteration i's count in bits [16i, 16i+16)
+#pragma unroll
+    for (int it = 0; it < kScanIterations; ++it) {
+      const uint32_t row0 = tile_row0 + warp * kScanWarpRows + it * 256 + lane * 8;
+      masks[it] = (test.mode != kTestNone && row0 < segment.row_count) ? evaluate8(segment, test, row0) : 0u;
+      packed_counts |= static_cast<uint32_t>(__popc(masks[it])) << (16 * it);
+    }
+
+    // 2. warp scan of both iterations at once
+    const uint32_t inclusive = warp_inclusive_scan(packed_counts, lane);
+    const uint32_t warp_sums = __shfl_sync(kFullMask, inclusive, 31);
+    const uint32_t exclusive = inclusive - packed_counts;
+    if (lane == 31) s_warp_totals[warp] = (warp_sums & 0xFFFFu) + (warp_sums >> 16);
+    __syncthreads();
+
+    uint32_t warp_base = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < kScanWarps; ++w) {
+      const uint32_t total = s_warp_totals[w];
+      if (w < static_cast<int>(warp)) warp_base += total;
+      tile_total += total;
+    }
+
+    // 3. warp 0 resolves the global offset while the other warps stage their matches
+    if (warp == 0) {
+      const unsigned long long base = lookback_exclusive_prefix(params.tile_status, tile, tile_total, lane);
+      if (lane == 0) {
+        s_base = base;
+        const bool last_tile_of_chunk = tile + 1 == __ldg(params.tile_starts + chunk + 1);
+        if (last_tile_of_chunk) params.chunk_end[chunk] = base + tile_total;
+        if (tile + 1 == params.tile_count) params.chunk_end[params.chunk_count] = base + tile_total;
+      }
+    }
+    {
+      uint32_t position = warp_base + (exclusive & 0xFFFFu);
+#pragma unroll
+      for (int it = 0; it < kScanIterations; ++it) {
+        const uint32_t row0 = tile_row0 + warp * kScanWarpRows + it * 256 + lane * 8;
+        if (it == 1) position = warp_base + (warp_sums & 0xFFFFu) + (exclusive >> 16);
+        const uint32_t mask = masks[it];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (mask & (1u << j)) s_offsets[position++] = row0 + j;
+        }
+      }
+    }
+    __syncthreads();
+
+    // 4. coalesced RowID write-out
+    hyb_row_id* out = params.out + s_base;
+    for (uint32_t i = threadIdx.x; i < tile_total; i += kScanThreads) {
+      st_stream_v2(out + i, chunk, s_offsets[i]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Position-filtered scan (reference-table input whose pos lists reference a single chunk each — what a previous
+// TableScan on the same table produced; abstract_dereferenced_column_table_scan_impl.cpp:38-46 +
+// table_scan.cpp:150-197): gather the referenced rows, test, and emit the referenced RowIDs in input order.
+// ---------------------------------------------------------------------------------------------------------------------
+struct FilteredScanParams {
+  const DevSegment* segments;
+  const ChunkTest* tests;
+  const hyb_row_id* input;            // flat input pos list
+  unsigned long long input_count;
+  const unsigned long long* input_chunk_end;  // inclusive prefix per chunk of the input list (chunk_count entries)
+  uint32_t chunk_count;
+  uint32_t tile_count;                // ceil(input_count / kScanTileRows)
+  unsigned long long* tile_status;
+  uint32_t* ticket;
+  hyb_row_id* out;
+  unsigned long long* out_total;      // [0] = total matches
+};
+
+__global__ void __launch_bounds__(kScanThreads) filtered_scan_kernel(const FilteredScanParams params) {
+  __shared__ hyb_row_id s_rows[kScanTileRows];
+  __shared__ uint32_t s_warp_totals[kScanWarps];
+  __shared__ uint32_t s_tile;
+  __shared__ unsigned long long s_base;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = threadIdx.x >> 5;
+  constexpr int kPerThread = kScanTileRows / kScanThreads;  // 16 consecutive inputs per thread
+
+  while (true) {
+    if (threadIdx.x == 0) s_tile = atomicAdd(params.ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    if (tile >= params.tile_count) return;
+    const unsigned long long first = static_cast<unsigned long long>(tile) * kScanTileRows +
+                                     static_cast<unsigned long long>(threadIdx.x) * kPerThread;
+    uint32_t mask = 0;
+    hyb_row_id rows[kPerThread];
+#pragma unroll
+    for (int j = 0; j < kPerThread; ++j) {
+      const unsigned long long index = first + j;
+      if (index < params.input_count) {
+        rows[j] = params.input[index];
+        const DevSegment& segment = params.segments[rows[j].chunk_id];
+        const ChunkTest& test = params.tests[rows[j].chunk_id];
+        if (evaluate1(segment, test, rows[j].chunk_offset)) mask |= 1u << j;
+      }
+    }
+    const uint32_t count = __popc(mask);
+    const uint32_t inclusive = warp_inclusive_scan(count, lane);
+    if (lane == 31) s_warp_totals[warp] = inclusive;
+    __syncthreads();
+    uint32_t warp_base = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < kScanWarps; ++w) {
+      const uint32_t total = s_warp_totals[w];
+      if (w < static_cast<int>(warp)) warp_base += total;
+      tile_total += total;
+    }
+    if (warp == 0) {
+      const unsigned long long base = lookback_exclusive_prefix(params.tile_status, tile, tile_total, lane);
+      if (lane == 0) {
+        s_base = base;
+        if (tile + 1 == params.tile_count) params.out_total[0] = base + tile_total;
+      }
+    }
+    uint32_t position = warp_base + inclusive - count;
+#pragma unroll
+    for (int j = 0; j < kPerThread; ++j) {
+      if (mask & (1u << j)) s_rows[position++] = rows[j];
+    }
+    __syncthreads();
+    hyb_row_id* out = params.out + s_base;
+    for (uint32_t i = threadIdx.x; i < tile_total; i += kScanThreads) {
+      st_stream_v2(out + i, s_rows[i].chunk_id, s_rows[i].chunk_offset);
+    }
+  }
+}
+
+// Per-chunk boundaries of a filtered scan's output: the output is ordered by chunk (it is a subsequence of an input that
+// is), so chunk c ends at upper_bound(out, c).
+__global__ void pos_list_chunk_ends_kernel(const hyb_row_id* __restrict__ rows, const unsigned long long* total_ptr,
+                                           uint32_t chunk_count, unsigned long long* __restrict__ chunk_end) {
+  const uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned long long total = *total_ptr;
+  if (chunk > chunk_count) return;
+  if (chunk == chunk_count) {
+    chunk_end[chunk] = total;
+    return;
+  }
+  unsigned long long lo = 0, hi = total;
+  while (lo < hi) {
+    const unsigned long long mid = (lo + hi) >> 1;
+    if (rows[mid].chunk_id <= chunk) {
+      lo = mid + 1;
+    } else {
+      hi = mid;
+    }
+  }
+  chunk_end[chunk] = lo;
+}
+
+static bool supported_condition(int32_t condition) {
+  return (condition >= HYB_PRED_EQUALS && condition <= HYB_PRED_BETWEEN_EXCLUSIVE) || condition == HYB_PRED_IS_NULL ||
+         condition == HYB_PRED_IS_NOT_NULL;
+}
+
+// Shared by hyb_table_scan and the fused predicates of hyb_aggregate_hash: builds the per-chunk tests on the device.
+int prepare_chunk_tests(hyb_context* context, Table* table, const hyb_scan_predicate* predicate, ChunkTest** out_tests,
+                        void** out_bounds_scratch) {
+  *out_tests = nullptr;
+  *out_bounds_scratch = nullptr;
+  HYB_CHECK(predicate->column_id < table->column_count, HYB_ERR_INVALID, "predicate column out of range");
+  HYB_CHECK(supported_condition(predicate->condition), HYB_ERR_UNSUPPORTED,
+            "predicate condition " + std::to_string(predicate->condition) + " is not on the GPU path");
+  const uint32_t chunk_count = table->chunk_count();
+  const int32_t data_type = table->column_types[predicate->column_id];
+  const bool needs_value =
+      predicate->condition != HYB_PRED_IS_NULL && predicate->condition != HYB_PRED_IS_NOT_NULL;
+  if (data_type == HYB_TYPE_STRING && needs_value) {
+    HYB_CHECK(predicate->value_id_bounds, HYB_ERR_INVALID,
+              "string dictionary scans need host-computed value_id_bounds (dictionary_segment.cpp:94-119)");
+  }
+  ScanPredicateDevice device_predicate{};
+  device_predicate.condition = predicate->condition;
+  device_predicate.data_type = data_type;
+  device_predicate.lower = predicate->lower;
+  device_predicate.upper = predicate->upper;
+  if (predicate->value_id_bounds && needs_value && chunk_count) {
+    const bool between = predicate->condition >= HYB_PRED_BETWEEN_INCLUSIVE &&
+                         predicate->condition <= HYB_PRED_BETWEEN_EXCLUSIVE;
+    const size_t bytes = sizeof(uint32_t) * size_t{chunk_count} * (between ? 4 : 2);
+    HYB_TRY(device_alloc(context, bytes, out_bounds_scratch));
+    HYB_CUDA(cudaMemcpyAsync(*out_bounds_scratch, predicate->value_id_bounds, bytes, cudaMemcpyHostToDevice,
+                             context->stream));
+    // value_id_bounds is borrowed pageable memory: the copy is staged before cudaMemcpyAsync returns.
+    device_predicate.value_id_bounds = static_cast<const uint32_t*>(*out_bounds_scratch);
+  }
+  void* tests = nullptr;
+  HYB_TRY(device_alloc(context, sizeof(ChunkTest) * std::max<uint32_t>(chunk_count, 1), &tests));
+  if (chunk_count) {
+    const DevSegment* column_segments = table->d_segments + size_t{predicate->column_id} * chunk_count;
+    scan_prepare_kernel<<<(chunk_count + 127) / 128, 128, 0, context->stream>>>(
+        column_segments, chunk_count, device_predicate, static_cast<ChunkTest*>(tests));
+    HYB_CUDA(cudaGetLastError());
+  }
+  *out_tests = static_cast<ChunkTest*>(tests);
+  return HYB_OK;
+}
+
+static uint64_t column_bytes_per_launch(const Table* table, uint32_t column_id) {
+  uint64_t bytes = 0;
+  for (uint32_t chunk = 0; chunk < table->chunk_count(); ++chunk) {
+    const auto& segment = table->segments[size_t{chunk} * table->column_count + column_id];
+    if (segment.encoding == HYB_ENC_UNENCODED) {
+      bytes += data_type_size(segment.data_type) * segment.row_count;
+    } else {
+      bytes += vector_bytes(segment.vector_type, segment.bit_width, segment.row_count);
+      if (segment.encoding == HYB_ENC_FRAME_OF_REFERENCE) {
+        bytes += sizeof(int32_t) * ((segment.row_count + HYB_FOR_BLOCK_SIZE - 1) / HYB_FOR_BLOCK_SIZE);
+      }
+    }
+    if (segment.nulls) bytes += segment.row_count;
+  }
+  return bytes;
+}
+
+}  // namespace hyb
+
+using namespace hyb;
+
+extern "C" {
+
+int hyb_table_scan(hyb_context* context, hyb_table_t table_handle, const hyb_scan_predicate* predicate,
+                   hyb_pos_list_t input_filter, hyb_pos_list_t* out_pos_list) {
+  HYB_CHECK(context && predicate && out_pos_list, HYB_ERR_INVALID, "NULL argument");
+  *out_pos_list = 0;
+  DeviceGuard guard(context->device);
+  std::lock_guard<std::mutex> lock(context->mutex);
+  auto* table = find_table(context, table_handle);
+  HYB_CHECK(table, HYB_ERR_NOT_FOUND, "unknown table handle");
+  PosList* filter = nullptr;
+  if (input_filter) {
+    filter = find_pos_list(context, input_filter);
+    HYB_CHECK(filter, HYB_ERR_NOT_FOUND, "unknown input_filter handle");
+    HYB_CHECK(filter->table == table_handle, HYB_ERR_INVALID, "input_filter belongs to a different table");
+  }
+  HYB_TRY(sync_table_descriptors(context, table));
+
+  timing_begin(context);
+  ChunkTest* tests = nullptr;
+  void* bounds_scratch = nullptr;
+  HYB_TRY(prepare_chunk_tests(context, table, predicate, &tests, &bounds_scratch));
+
+  const uint32_t chunk_count = table->chunk_count();
+  auto result = std::make_unique<PosList>();
+  result->table = table_handle;
+  result->chunk_count = chunk_count;
+  result->stream = context->stream;
+  const DevSegment* column_segments = table->d_segments + size_t{predicate->column_id} * chunk_count;
+  uint32_t launches = 1;
+  uint64_t input_rows = 0, input_bytes = 0;
+
+  void* chunk_end = nullptr;
+  HYB_TRY(device_alloc(context, sizeof(uint64_t) * (size_t{chunk_count} + 1), &chunk_end));
+  result->d_chunk_end = static_cast<uint64_t*>(chunk_end);
+
+  if (!filter) {
+    const uint32_t* tile_starts = nullptr;
+    uint32_t tile_count = 0;
+    HYB_TRY(get_tile_starts(context, table, kScanTileRows, &tile_starts, &tile_count));
+    input_rows = table->row_count();
+    input_bytes = column_bytes_per_launch(table, predicate->column_id);
+    result->capacity = table->row_count();
+    void* out = nullptr;
+    HYB_TRY(device_alloc(context, sizeof(hyb_row_id) * result->capacity, &out));
+    result->d_row_ids = static_cast<hyb_row_id*>(out);
+    // chunk_end is pre-filled with "unset" so chunks without rows can be patched on the host.
+    HYB_CUDA(cudaMemsetAsync(chunk_end, 0xFF, sizeof(uint64_t) * (size_t{chunk_count} + 1), context->stream));
+    if (tile_count > 0) {
+      void* status = nullptr;
+      HYB_TRY(device_alloc(context, sizeof(uint64_t) * (size_t{tile_count} + 1), &status));
+      HYB_CUDA(cudaMemsetAsync(status, 0, sizeof(uint64_t) * (size_t{tile_count} + 1), context->stream));
+      ScanParams params{};
+      params.segments = column_segments;
+      params.tests = tests;
+      params.tile_starts = tile_starts;
+      params.chunk_count = chunk_count;
+      params.tile_count = tile_count;
+      params.tile_status = static_cast<unsigned long long*>(status);
+      params.ticket = reinterpret_cast<uint32_t*>(static_cast<unsigned long long*>(status) + tile_count);
+      params.out = result->d_row_ids;
+      params.chunk_end = reinterpret_cast<unsigned long long*>(result->d_chunk_end);
+      int blocks_per_sm = 0;
+      HYB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, scan_kernel, kScanThreads, 0));
+      const uint32_t grid = std::min<uint32_t>(tile_count, context->sm_count * std::max(blocks_per_sm, 1));
+      timing_kernel_begin(context);
+      scan_kernel<<<grid, kScanThreads, 0, context->stream>>>(params);
+      timing_kernel_end(context);
+      HYB_CUDA(cudaGetLastError());
+      device_free(context, status);
+      launches = 2;
+    } else {
+      timing_kernel_begin(context);
+      timing_kernel_end(context);
+    }
+  } else {
+    // Input = a previous scan's output on the same table.
+    HYB_CUDA(cudaStreamSynchronize(context->stream));
+    uint64_t input_count = 0;
+    HYB_CUDA(cudaMemcpy(&input_count, filter->d_chunk_end + filter->chunk_count, sizeof(uint64_t),
+                        cudaMemcpyDeviceToHost));
+    if (input_count == ~uint64_t{0}) input_count = 0;
+    input_rows = input_count;
+    input_bytes = input_count * sizeof(hyb_row_id);
+    result->capacity = input_count;
+    void* out = nullptr;
+    HYB_TRY(device_alloc(context, sizeof(hyb_row_id) * std::max<uint64_t>(input_count, 1), &out));
+    result->d_row_ids = static_cast<hyb_row_id*>(out);
+    const uint32_t tile_count = static_cast<uint32_t>((input_count + kScanTileRows - 1) / kScanTileRows);
+    void* status = nullptr;
+    HYB_TRY(device_alloc(context, sizeof(uint64_t) * (size_t{tile_count} + 2), &status));
+    HYB_CUDA(cudaMemsetAsync(status, 0, sizeof(uint64_t) * (size_t{tile_count} + 2), context->stream));
+    auto* total = static_cast<unsigned long long*>(status) + tile_count + 1;
+    timing_kernel_begin(context);
+    if (tile_count > 0) {
+      FilteredScanParams params{};
+      params.segments = column_segments;
+      params.tests = tests;
+      params.input = filter->d_row_ids;
+      params.input_count = input_count;
+      params.chunk_count = chunk_count;
+      params.tile_count = tile_count;
+      params.tile_status = static_cast<unsigned long long*>(status);
+      params.ticket = reinterpret_cast<uint32_t*>(static_cast<unsigned long long*>(status) + tile_count);
+      params.out = result->d_row_ids;
+      params.out_total = total;
+      int blocks_per_sm = 0;
+      HYB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, filtered_scan_kernel, kScanThreads, 0));
+      const uint32_t grid = std::min<uint32_t>(tile_count, context->sm_count * std::max(blocks_per_sm, 1));
+      filtered_scan_kernel<<<grid, kScanThreads, 0, context->stream>>>(params);
+      HYB_CUDA(cudaGetLastError());
+    }
+    timing_kernel_end(context);
+    pos_list_chunk_ends_kernel<<<(chunk_count + 1 + 127) / 128, 128, 0, context->stream>>>(
+        result->d_row_ids, total, chunk_count, reinterpret_cast<unsigned long long*>(result->d_chunk_end));
+    HYB_CUDA(cudaGetLastError());
+    device_free(context, status);
+    launches = 3;
+  }
+  device_free(context, tests);
+  device_free(context, bounds_scratch);
+  timing_end(context, launches, input_bytes, input_rows, 0);
+  timing_output_count(context, result->d_chunk_end + chunk_count, sizeof(hyb_row_id));
+
+  const auto handle = context->next_handle++;
+  context->pos_lists.emplace(handle, std::move(result));
+  *out_pos_list = handle;
+  return HYB_OK;
+}
+
+static int ensure_pos_list_host(hyb_context* context, PosList* list) {
+  if (list->host_valid) return HYB_OK;
+  list->h_chunk_offsets.assign(size_t{list->chunk_count} + 1, 0);
+  std::vector<uint64_t> ends(size_t{list->chunk_count} + 1);
+  HYB_CUDA(cudaMemcpyAsync(ends.data(), list->d_chunk_end, sizeof(uint64_t) * ends.size(), cudaMemcpyDeviceToHost,
+                           context->stream));
+  HYB_CUDA(cudaStreamSynchronize(context->stream));
+  uint64_t running = 0;
+  for (uint32_t chunk = 0; chunk < list->chunk_count; ++chunk) {
+    list->h_chunk_offsets[chunk] = running;
+    if (ends[chunk] != ~uint64_t{0}) running = ends[chunk];
+  }
+  list->h_chunk_offsets[list->chunk_count] = running;
+  list->host_valid = true;
+  return HYB_OK;
+}
+
+int hyb_pos_list_info(hyb_context* context, hyb_pos_list_t handle, uint64_t* out_total, uint32_t* out_chunk_count) {
+  HYB_CHECK(context, HYB_ERR_INVALID, "context is NULL");
+  DeviceGuard guard(context->device);
+  std::lock_guard<std::mutex> lock(context->mutex);
+  auto* list = find_pos_list(context, handle);
+  HYB_CHECK(list, HYB_ERR_NOT_FOUND, "unknown pos list handle");
+  HYB_TRY(ensure_pos_list_host(context, list));
+  if (out_total) *out_total = list->h_chunk_offsets.back();
+  if (out_chunk_count) *out_chunk_count = list->chunk_count;
+  return HYB_OK;
+}
+
+int hyb_pos_list_chunk_offsets(hyb_context* context, hyb_pos_list_t handle, uint64_t* out_chunk_offsets) {
+  HYB_CHECK(context && out_chunk_offsets, HYB_ERR_INVALID, "NULL argument");
+  DeviceGuard guard(context->device);
+  std::lock_guard<std::mutex> lock(context->mutex);
+  auto* list = find_pos_list(context, handle);
+  HYB_CHECK(list, HYB_ERR_NOT_FOUND, "unknown pos list handle");
+  HYB_TRY(ensure_pos_list_host(context, list));
+  std::copy(list->h_chunk_offsets.begin(), list->h_chunk_offsets.end(), out_chunk_offsets);
+  return HYB_OK;
+}
+
+int hyb_pos_list_copy(hyb_context* context, hyb_pos_list_t handle, uint64_t begin, uint64_t count,
+                      hyb_row_id* out_row_ids) {
+  HYB_CHECK(context && (out_row_ids || count == 0), HYB_ERR_INVALID, "NULL argument");
+  DeviceGuard guard(context->device);
+  std::lock_guard<std::mutex> lock(context->mutex);
+  auto* list = find_pos_list(context, handle);
+  HYB_CHECK(list, HYB_ERR_NOT_FOUND, "unknown pos list handle");
+  HYB_TRY(ensure_pos_list_host(context, list));
+  HYB_CHECK(begin + count <= list->h_chunk_offsets.back(), HYB_ERR_INVALID, "range exceeds the pos list");
+  if (count) {
+    HYB_CUDA(cudaMemcpyAsync(out_row_ids, list->d_row_ids + begin, sizeof(hyb_row_id) * count, cudaMemcpyDeviceToHost,
+                             context->stream));
+    HYB_CUDA(cudaStreamSynchronize(context->stream));
+  }
+  return HYB_OK;
+}
+
+int hyb_pos_list_device_ptr(hyb_context* context, hyb_pos_list_t handle, void** out_device_row_ids) {
+  HYB_CHECK(context && out_device_row_ids, HYB_ERR_INVALID, "NULL argument");
+  std::lock_guard<std::mutex> lock(context->mutex);
+  auto* list = find_pos_list(context, handle);
+  HYB_CHECK(list, HYB_ERR_NOT_FOUND, "unknown pos list handle");
+  *out_device_row_ids = list->d_row_ids;
+  return HYB_OK;
+}
+
+int hyb_pos_list_free(hyb_context* context, hyb_pos_list_t handle) {
+  HYB_CHECK(context, HYB_ERR_INVALID, "context is NULL");
+  DeviceGuard guard(context->device);
+  std::lock_guard<std::mutex> lock(context->mutex);
+  auto it = context->pos_lists.find(handle);
+  HYB_CHECK(it != context->pos_lists.end(), HYB_ERR_NOT_FOUND, "unknown pos list handle");
+  context->pos_lists.erase(it);
+  return HYB_OK;
+}
+
+}  // extern "C"

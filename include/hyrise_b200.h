@@ -1,0 +1,385 @@
+/*
+ * hyrise_b200.h — C-ABI of the Blackwell (sm_100a) execution path for Hyrise's three bandwidth-bound operators.
+ *
+ * This header is the drop-in boundary. The reference (hyrise/hyrise @ 2f7bedf3) has no FFI for operators; the seam is
+ * the C++ virtual `AbstractOperator::_on_execute()` (src/lib/operators/abstract_operator.hpp:231). Each entry point
+ * below replaces the body of one reference function and is what a maintainer's shim inside that function would call
+ * (see INTEGRATION.md for the shim code):
+ *
+ *   hyb_table_scan        <-  TableScan::_on_execute                 src/lib/operators/table_scan.cpp:97-240
+ *                             ColumnVsValueTableScanImpl             .../table_scan/column_vs_value_table_scan_impl.cpp:43-272
+ *                             ColumnBetweenTableScanImpl             .../table_scan/column_between_table_scan_impl.cpp:42-226
+ *                             ColumnIsNullTableScanImpl              .../table_scan/column_is_null_table_scan_impl.cpp
+ *                             AbstractTableScanImpl::_scan_with_iterators  .../table_scan/abstract_table_scan_impl.hpp:56-242
+ *   hyb_join_hash         <-  JoinHash::_on_execute / JoinHashImpl   src/lib/operators/join_hash.cpp:116-572
+ *                             materialize_input/partition_by_radix/build/probe/probe_semi_anti
+ *                                                                    src/lib/operators/join_hash/join_hash_steps.hpp:274-922
+ *   hyb_aggregate_hash    <-  AggregateHash::_on_execute/_aggregate  src/lib/operators/aggregate_hash.cpp:950-1372
+ *   hyb_table_* (pool)    <-  new "device column pool": device copies of ValueSegment / DictionarySegment /
+ *                             FrameOfReferenceSegment               src/lib/storage/{value_segment.hpp:84-85,
+ *                             dictionary_segment.hpp:88-90, frame_of_reference_segment.hpp:49,94-97}
+ *
+ * Conventions:
+ *   - plain C: pointers + sizes, no C++/torch types; every function returns hyb_status (0 = OK);
+ *     hyb_last_error() returns a thread-local message. No exception crosses this boundary.
+ *   - every entry point is thread-safe and re-entrant; inputs are borrowed and immutable for the duration of the call.
+ *   - HYB_ERR_UNSUPPORTED means "run the CPU operator" (e.g. LIKE scans, string join keys); anything else is a
+ *     hard failure the shim turns into Fail(hyb_last_error()).
+ *   - results stay device-resident behind handles (so the next operator can consume them without a PCIe round trip)
+ *     and are copied out on request into caller-owned host memory (pinned via hyb_host_alloc for full PCIe speed).
+ */
+#ifndef HYRISE_B200_H
+#define HYRISE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HYB_ABI_VERSION 1
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Status codes
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef enum hyb_status {
+  HYB_OK = 0,
+  HYB_ERR_INVALID = 1,     /* bad argument (maps to reference Assert/Fail -> std::logic_error, utils/assert.hpp:48-82) */
+  HYB_ERR_UNSUPPORTED = 2, /* not on the GPU path: caller runs the CPU operator */
+  HYB_ERR_CUDA = 3,        /* CUDA runtime failure; message holds cudaGetErrorString */
+  HYB_ERR_OOM = 4,
+  HYB_ERR_NOT_FOUND = 5    /* unknown handle */
+} hyb_status;
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Core types — restated from src/lib/types.hpp and src/lib/all_type_variant.hpp:34-39
+ * ---------------------------------------------------------------------------------------------------------------- */
+
+/* RowID {ChunkID, ChunkOffset}, 8 bytes — types.hpp:97-117. NULL_ROW_ID = {0xFFFFFFFF, 0xFFFFFFFF}. */
+typedef struct hyb_row_id {
+  uint32_t chunk_id;
+  uint32_t chunk_offset;
+} hyb_row_id;
+
+#define HYB_INVALID_CHUNK_ID 0xFFFFFFFFu
+#define HYB_INVALID_CHUNK_OFFSET 0xFFFFFFFFu
+#define HYB_INVALID_VALUE_ID 0xFFFFFFFFu /* types.hpp INVALID_VALUE_ID */
+#define HYB_DEFAULT_CHUNK_SIZE 65535u    /* storage/chunk.hpp:52 */
+#define HYB_FOR_BLOCK_SIZE 2048u         /* storage/frame_of_reference_segment.hpp:49 */
+
+typedef enum hyb_data_type { /* all_type_variant.hpp:34-39 (Null excluded) */
+  HYB_TYPE_INT32 = 0,
+  HYB_TYPE_INT64 = 1,
+  HYB_TYPE_FLOAT32 = 2,
+  HYB_TYPE_FLOAT64 = 3,
+  HYB_TYPE_STRING = 4 /* only value-IDs of string dictionaries reach the device */
+} hyb_data_type;
+
+typedef enum hyb_encoding { /* storage/encoding_type.hpp; the three the default TPC-H encoding produces */
+  HYB_ENC_UNENCODED = 0,    /* ValueSegment<T> */
+  HYB_ENC_DICTIONARY = 1,   /* DictionarySegment<T> */
+  HYB_ENC_FRAME_OF_REFERENCE = 2 /* FrameOfReferenceSegment<int32_t> */
+} hyb_encoding;
+
+typedef enum hyb_vector_type { /* storage/vector_compression/compressed_vector_type.hpp */
+  HYB_VEC_NONE = 0,
+  HYB_VEC_FIXED_1B = 1, /* FixedWidthIntegerVector<uint8_t>  */
+  HYB_VEC_FIXED_2B = 2, /* FixedWidthIntegerVector<uint16_t> */
+  HYB_VEC_FIXED_4B = 3, /* FixedWidthIntegerVector<uint32_t> */
+  HYB_VEC_BITPACKED = 4 /* BitPackingVector: LSB-first b-bit fields in uint64 words (compact_iterator.hpp:218-252) */
+} hyb_vector_type;
+
+/* PredicateCondition — same order/values as types.hpp:160-179 so a shim can static_cast. */
+typedef enum hyb_predicate_condition {
+  HYB_PRED_EQUALS = 0,
+  HYB_PRED_NOT_EQUALS = 1,
+  HYB_PRED_LESS_THAN = 2,
+  HYB_PRED_LESS_THAN_EQUALS = 3,
+  HYB_PRED_GREATER_THAN = 4,
+  HYB_PRED_GREATER_THAN_EQUALS = 5,
+  HYB_PRED_BETWEEN_INCLUSIVE = 6,
+  HYB_PRED_BETWEEN_LOWER_EXCLUSIVE = 7,
+  HYB_PRED_BETWEEN_UPPER_EXCLUSIVE = 8,
+  HYB_PRED_BETWEEN_EXCLUSIVE = 9,
+  HYB_PRED_IN = 10,                   /* unsupported */
+  HYB_PRED_NOT_IN = 11,               /* unsupported */
+  HYB_PRED_LIKE = 12,                 /* unsupported */
+  HYB_PRED_NOT_LIKE = 13,             /* unsupported */
+  HYB_PRED_LIKE_INSENSITIVE = 14,     /* unsupported */
+  HYB_PRED_NOT_LIKE_INSENSITIVE = 15, /* unsupported */
+  HYB_PRED_IS_NULL = 16,
+  HYB_PRED_IS_NOT_NULL = 17
+} hyb_predicate_condition;
+
+/* JoinMode — same values as types.hpp:210. */
+typedef enum hyb_join_mode {
+  HYB_JOIN_INNER = 0,
+  HYB_JOIN_LEFT = 1,
+  HYB_JOIN_RIGHT = 2,
+  HYB_JOIN_FULL_OUTER = 3, /* unsupported (as in JoinHash) */
+  HYB_JOIN_CROSS = 4,      /* unsupported */
+  HYB_JOIN_SEMI = 5,
+  HYB_JOIN_ANTI_NULL_AS_TRUE = 6,
+  HYB_JOIN_ANTI_NULL_AS_FALSE = 7
+} hyb_join_mode;
+
+/* WindowFunction subset AggregateHash supports on the device (expression/window_function_expression.hpp). */
+typedef enum hyb_aggregate_function {
+  HYB_AGG_MIN = 0,
+  HYB_AGG_MAX = 1,
+  HYB_AGG_SUM = 2,
+  HYB_AGG_AVG = 3,
+  HYB_AGG_COUNT = 4,      /* COUNT(column): non-NULL rows */
+  HYB_AGG_COUNT_STAR = 5, /* COUNT(*): INVALID_COLUMN_ID argument in the reference */
+  HYB_AGG_COUNT_DISTINCT = 6,     /* unsupported -> CPU */
+  HYB_AGG_STDDEV_SAMP = 7,        /* unsupported -> CPU */
+  HYB_AGG_ANY = 8                 /* pseudo aggregate: handled like a group-by column by the shim */
+} hyb_aggregate_function;
+
+/* A typed scalar, already losslessly cast to the column type by the shim (utils/lossless_predicate_cast.hpp:20-60). */
+typedef union hyb_value {
+  int32_t i32;
+  int64_t i64;
+  float f32;
+  double f64;
+} hyb_value;
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Host-side segment / table views (borrowed pointers into the reference's pmr_vectors)
+ * ---------------------------------------------------------------------------------------------------------------- */
+
+/*
+ * One segment of one chunk. Field use per encoding:
+ *   UNENCODED          values = row_count x T; nulls optional.                         value_segment.hpp:84-85
+ *   DICTIONARY         values = dictionary (dictionary_size x T, sorted, unique; NULL pointer for STRING),
+ *                      attribute_vector = row_count value-IDs in vector_type layout,
+ *                      NULL is encoded as value-ID == dictionary_size.                 dictionary_segment.hpp:88-90
+ *   FRAME_OF_REFERENCE values = block minima (ceil(row_count/2048) x int32),
+ *                      attribute_vector = row_count offsets in vector_type layout, nulls optional.
+ *                                                                                      frame_of_reference_segment.hpp:94-97
+ * nulls: one byte per row (0/1). The reference stores pmr_vector<bool> (bit-packed); the shim expands it once.
+ * dictionary_codes (optional, DICTIONARY only): dictionary_size x uint64 chunk-independent group-by codes for this
+ *   segment's dictionary entries — required to group by a STRING column (the shim computes them once per dictionary
+ *   with the reference's own key scheme, aggregate_hash.cpp:818-925; O(dictionary) host work, not O(rows)).
+ */
+typedef struct hyb_segment_desc {
+  int32_t encoding;    /* hyb_encoding */
+  int32_t data_type;   /* hyb_data_type */
+  int32_t vector_type; /* hyb_vector_type (DICTIONARY / FRAME_OF_REFERENCE) */
+  int32_t bit_width;   /* BITPACKED only: bits per entry (1..32) */
+  uint32_t row_count;
+  uint32_t dictionary_size;
+  const void* values;
+  const uint8_t* nulls;
+  const void* attribute_vector;
+  const uint64_t* dictionary_codes;
+} hyb_segment_desc;
+
+/* A table = chunk_count x column_count segments, row-major by chunk: segments[chunk * column_count + column]. */
+typedef struct hyb_table_view {
+  uint32_t chunk_count;
+  uint32_t column_count;
+  const hyb_segment_desc* segments;
+} hyb_table_view;
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Context and device column pool
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct hyb_context hyb_context; /* one per (process, device); owns streams, scratch and the column pool */
+typedef uint64_t hyb_table_t;           /* device-resident table (handle into the pool) */
+typedef uint64_t hyb_pos_list_t;        /* device-resident RowIDPosList set (one list per input chunk) */
+typedef uint64_t hyb_join_result_t;
+typedef uint64_t hyb_aggregate_result_t;
+
+int hyb_abi_version(void);
+const char* hyb_last_error(void);
+
+/* device_index: CUDA ordinal (one process per GPU: pass LOCAL_RANK). */
+int hyb_context_create(int device_index, hyb_context** out_context);
+int hyb_context_destroy(hyb_context* context);
+int hyb_device_count(int* out_count);
+/* Block until all work queued by this context has finished. */
+int hyb_context_synchronize(hyb_context* context);
+
+/* Pinned host memory for upload sources / result destinations (a pinned MemoryResource in the reference's terms,
+ * cf. src/lib/memory/default_memory_resource.cpp:29-35). */
+int hyb_host_alloc(size_t bytes, void** out_ptr);
+int hyb_host_free(void* ptr);
+
+/* Upload a whole table into the pool (H2D of every buffer the descriptors point to). */
+int hyb_table_upload(hyb_context* context, const hyb_table_view* view, hyb_table_t* out_table);
+/* Incremental variant: create an empty table, then append chunks (column_count segments each). */
+int hyb_table_create(hyb_context* context, uint32_t column_count, hyb_table_t* out_table);
+int hyb_table_append_chunk(hyb_context* context, hyb_table_t table, const hyb_segment_desc* segments);
+int hyb_table_drop(hyb_context* context, hyb_table_t table);
+int hyb_table_info(hyb_context* context, hyb_table_t table, uint32_t* out_chunk_count, uint32_t* out_column_count,
+                   uint64_t* out_row_count, uint64_t* out_device_bytes);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * TableScan
+ * ---------------------------------------------------------------------------------------------------------------- */
+
+/*
+ * column <condition> value / column BETWEEN lower AND upper / column IS [NOT] NULL.
+ * For STRING dictionary columns the device never sees strings: the shim passes, per chunk, the value-ID bounds the
+ * reference computes with DictionarySegment::lower_bound/upper_bound (dictionary_segment.cpp:94-119):
+ *   value_id_bounds[2*chunk+0] = lower_bound(lower), value_id_bounds[2*chunk+1] = upper_bound(lower)        (binary)
+ *   value_id_bounds[4*chunk+0..3] = lower_bound(lower), upper_bound(lower), lower_bound(upper), upper_bound(upper)
+ *                                                                                                           (between)
+ * with HYB_INVALID_VALUE_ID for "past the end". For numeric dictionaries leave it NULL: bounds are computed on the
+ * device from `lower`/`upper`.
+ */
+typedef struct hyb_scan_predicate {
+  uint32_t column_id;
+  int32_t condition; /* hyb_predicate_condition */
+  hyb_value lower;   /* the value for binary conditions; lower bound for BETWEEN */
+  hyb_value upper;   /* upper bound for BETWEEN */
+  const uint32_t* value_id_bounds;
+} hyb_scan_predicate;
+
+/*
+ * Scan `table` and produce, per input chunk, the ascending list of matching RowIDs — what
+ * AbstractTableScanImpl::scan_chunk returns for every chunk (table_scan.cpp:131). `input_filter` (0 = none) restricts
+ * the scan to the positions of a previous scan's result on the same table (reference-table input with single-chunk
+ * pos lists, abstract_dereferenced_column_table_scan_impl.cpp:38-46); the output then holds the referenced RowIDs
+ * (table_scan.cpp:150-197).
+ */
+int hyb_table_scan(hyb_context* context, hyb_table_t table, const hyb_scan_predicate* predicate,
+                   hyb_pos_list_t input_filter, hyb_pos_list_t* out_pos_list);
+
+/* Total matches and per-chunk boundaries: out_chunk_offsets has chunk_count + 1 entries; chunk c's RowIDs are
+ * [out_chunk_offsets[c], out_chunk_offsets[c+1]) of the flat list. Either pointer may be NULL. */
+int hyb_pos_list_info(hyb_context* context, hyb_pos_list_t pos_list, uint64_t* out_total, uint32_t* out_chunk_count);
+int hyb_pos_list_chunk_offsets(hyb_context* context, hyb_pos_list_t pos_list, uint64_t* out_chunk_offsets);
+/* Copy RowIDs [begin, begin+count) of the flat list to host memory. */
+int hyb_pos_list_copy(hyb_context* context, hyb_pos_list_t pos_list, uint64_t begin, uint64_t count,
+                      hyb_row_id* out_row_ids);
+int hyb_pos_list_free(hyb_context* context, hyb_pos_list_t pos_list);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * JoinHash (equi-join on one int32/int64 key column per side)
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct hyb_join_side {
+  hyb_table_t table;
+  uint32_t column_id;
+  hyb_pos_list_t filter; /* 0 = all rows; else join only these positions (reference-table input) */
+} hyb_join_side;
+
+/*
+ * build/probe sides are chosen by the caller exactly as JoinHash::_on_execute does (join_hash.cpp:139-155).
+ * radix_bits: the reference's partition count (calculate_radix_bits, join_hash.cpp:70-114; pass -1 to have it computed
+ * from the input sizes). It only fixes the ORDER and SLICING of the output: pairs are emitted grouped by
+ * hash(key) & (2^radix_bits - 1) (std::hash<int> = identity), inside a partition in probe-row order, for one probe row
+ * in build-row order — identical to probe() over radix-partitioned inputs (join_hash_steps.hpp:624-792).
+ * Semi/Anti modes emit probe RowIDs only (probe_semi_anti, :794-922).
+ */
+int hyb_join_hash(hyb_context* context, const hyb_join_side* build, const hyb_join_side* probe, int32_t mode,
+                  int32_t radix_bits, hyb_join_result_t* out_result);
+
+/* out_pair_count: number of emitted rows; out_partition_count: 2^radix_bits. */
+int hyb_join_result_info(hyb_context* context, hyb_join_result_t result, uint64_t* out_pair_count,
+                         uint32_t* out_partition_count, int32_t* out_radix_bits);
+/* partition_count + 1 offsets into the flat pair list (output of partition p = [off[p], off[p+1])). */
+int hyb_join_result_partition_offsets(hyb_context* context, hyb_join_result_t result, uint64_t* out_offsets);
+/* Copy pairs [begin, begin+count). out_build_row_ids may be NULL (always for Semi/Anti). */
+int hyb_join_result_copy(hyb_context* context, hyb_join_result_t result, uint64_t begin, uint64_t count,
+                         hyb_row_id* out_build_row_ids, hyb_row_id* out_probe_row_ids);
+int hyb_join_result_free(hyb_context* context, hyb_join_result_t result);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * AggregateHash (with optionally fused scan predicates and Projection arithmetic)
+ * ---------------------------------------------------------------------------------------------------------------- */
+
+/* Arithmetic expression over columns in reverse Polish notation, evaluated with the reference's type rules
+ * (expression/expression_utils.cpp:172-205: float∘float→float, int∘float→float, int∘int→int ...). A plain column is
+ * the one-op program {HYB_EXPR_COLUMN}. */
+typedef enum hyb_expr_op {
+  HYB_EXPR_COLUMN = 0,   /* push column `column_id` */
+  HYB_EXPR_LITERAL = 1,  /* push literal (type in literal_type, value in literal) */
+  HYB_EXPR_ADD = 2,
+  HYB_EXPR_SUB = 3,
+  HYB_EXPR_MUL = 4,
+  HYB_EXPR_DIV = 5
+} hyb_expr_op;
+
+typedef struct hyb_expr_node {
+  int32_t op;           /* hyb_expr_op */
+  uint32_t column_id;   /* COLUMN */
+  int32_t literal_type; /* LITERAL: hyb_data_type */
+  hyb_value literal;    /* LITERAL */
+} hyb_expr_node;
+
+#define HYB_MAX_EXPR_NODES 16
+#define HYB_MAX_GROUPBY_COLUMNS 8
+#define HYB_MAX_AGGREGATES 16
+#define HYB_MAX_FUSED_PREDICATES 8
+
+typedef struct hyb_aggregate_def {
+  int32_t function; /* hyb_aggregate_function */
+  uint32_t node_count; /* 0 for COUNT(*) */
+  hyb_expr_node nodes[HYB_MAX_EXPR_NODES];
+} hyb_aggregate_def;
+
+typedef struct hyb_aggregate_query {
+  hyb_table_t table;
+  hyb_pos_list_t filter;           /* 0 = all rows; else aggregate only these positions */
+  uint32_t predicate_count;        /* fused conjunctive ColumnVsValue/Between/IsNull predicates (may be 0) */
+  const hyb_scan_predicate* predicates;
+  uint32_t groupby_count;
+  const uint32_t* groupby_column_ids;
+  uint32_t aggregate_count;
+  const hyb_aggregate_def* aggregates;
+} hyb_aggregate_query;
+
+/*
+ * Groups are reported in the order AggregateHash emits them: first appearance in row order, or — when the reference's
+ * "immediate key" shortcut applies (single int32 group-by column with a dense key range, aggregate_hash.cpp:781-804)
+ * — ascending key order with the NULL group first. Representative RowIDs mirror aggregate_hash.cpp:367,394.
+ */
+int hyb_aggregate_hash(hyb_context* context, const hyb_aggregate_query* query, hyb_aggregate_result_t* out_result);
+
+int hyb_aggregate_result_info(hyb_context* context, hyb_aggregate_result_t result, uint64_t* out_group_count,
+                              int32_t* out_used_immediate_keys);
+/* One representative RowID per group (what write_groupby_output turns into ReferenceSegments, :421-537). */
+int hyb_aggregate_result_row_ids(hyb_context* context, hyb_aggregate_result_t result, hyb_row_id* out_row_ids);
+/*
+ * Values of aggregate `aggregate_index` for all groups. Result type follows WindowFunctionTraits
+ * (aggregate/window_function_traits.hpp:14-77): COUNT* -> int64; SUM(int) -> int64; SUM(float/double) -> double;
+ * AVG -> double; MIN/MAX -> the column type. `out_values` receives group_count elements of that type (8 bytes for
+ * int64/double, 4 for int32/float); out_value_type tells which. out_nulls (optional) gets 1 where the reference writes
+ * NULL (aggregate_count == 0).
+ */
+int hyb_aggregate_result_values(hyb_context* context, hyb_aggregate_result_t result, uint32_t aggregate_index,
+                                void* out_values, uint8_t* out_nulls, int32_t* out_value_type);
+int hyb_aggregate_result_free(hyb_context* context, hyb_aggregate_result_t result);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Instrumentation (fills the reference's performance_data, operators/operator_performance_data.hpp:46-97)
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct hyb_operator_stats {
+  float device_ms;            /* CUDA-event time of the operator's kernels on the context stream */
+  float dominant_kernel_ms;   /* the bandwidth-bound kernel alone (scan / probe / aggregate kernel) */
+  uint32_t kernel_launches;   /* kernels launched by the last operator call */
+  uint32_t reserved;
+  uint64_t algorithmic_bytes; /* compulsory traffic of the dominant kernel */
+  uint64_t input_rows;
+  uint64_t output_rows;
+} hyb_operator_stats;
+
+/* Stats of the last operator call made on this context by the calling thread. */
+int hyb_last_operator_stats(hyb_context* context, hyb_operator_stats* out_stats);
+
+/* Multi-GPU support: raw device pointers of result buffers so the host layer can hand them to NCCL
+ * (torch.distributed) for the radix exchange. Pointers stay valid until the result is freed. */
+int hyb_pos_list_device_ptr(hyb_context* context, hyb_pos_list_t pos_list, void** out_device_row_ids);
+int hyb_join_result_device_ptrs(hyb_context* context, hyb_join_result_t result, void** out_build_row_ids,
+                                void** out_probe_row_ids);
+/* The context's CUDA stream (cudaStream_t as void*), so torch can order its collectives after our kernels. */
+int hyb_context_stream(hyb_context* context, void** out_stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* HYRISE_B200_H */
