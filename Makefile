@@ -10,7 +10,9 @@ CU_SRCS   := $(wildcard $(CSRC)/*.cu)
 CU_OBJS   := $(patsubst $(CSRC)/%.cu,build/%.o,$(CU_SRCS))
 HDRS      := $(wildcard $(CSRC)/*.hpp) $(wildcard $(CSRC)/*.cuh) include/hyrise_b200.h
 
-all: $(LIB) oracle
+TPCH_LIB  := hyrise_b200/lib/libhyb_tpch.so
+
+all: $(LIB) $(TPCH_LIB) oracle
 
 build/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p build
@@ -20,11 +22,15 @@ $(LIB): $(CU_OBJS)
 	@mkdir -p hyrise_b200/lib
 	$(NVCC) $(ARCH) -shared -o $@ $(CU_OBJS) -cudart shared
 
+$(TPCH_LIB): $(CSRC)/tpch_gen.cpp include/hyrise_b200_tpch.h include/hyrise_b200.h
+	@mkdir -p hyrise_b200/lib
+	$(CXX) -O3 -march=x86-64-v3 -std=c++17 -fPIC -Wall -pthread -shared -o $@ $(CSRC)/tpch_gen.cpp
+
 oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -rf build $(LIB)
+	rm -rf build $(LIB) $(TPCH_LIB)
 	$(MAKE) -C oracle clean
 
 .PHONY: all oracle clean

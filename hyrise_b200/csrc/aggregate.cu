@@ -1,20 +1,1825 @@
-// AggregateHash on the device (placeholder until the kernels land in this round).
+// AggregateHash on the device, with the TableScan predicates and the Projection arithmetic that precede it in a TPC-H
+// plan fused into the same pass.
+//
+// Replaces AggregateHash::_on_execute (src/lib/operators/aggregate_hash.cpp:1180-1372): _partition_by_groupby_keys
+// (:661-948), get_or_add_result (:317-403), _aggregate_segment (:605-655) and the output writers (:56-230, :421-537).
+// The reference walks chunks and aggregates sequentially on one thread; here every row is handled once:
+//
+//   aggregate_fast_kernel<W, G, C>   the TPC-H shape: at most G <= 8 groups, SUM / AVG / COUNT over columns and over one
+//       product chain col0 (x) f1(col1) (x) f2(col2) ... (Q1: price, price*(1-disc), price*(1-disc)*(1+tax); Q6:
+//       price*disc). One streaming pass: 128-bit loads of value-IDs, predicates as bit masks (same code as TableScan),
+//       dictionary decode in registers, float arithmetic with the reference's type rules (non-fused __fmul_rn /
+//       __fsub_rn), group lookup in a CTA-shared table of <= G keys, per-thread double / int64 accumulators in
+//       registers, one deterministic tree reduction per CTA, partials merged in CTA order on the host.
+//       HBM traffic = the bytes of the referenced columns (+ their per-chunk dictionaries), each read once.
+//   aggregate_general_kernel         everything else (MIN/MAX, arbitrary arithmetic, many groups, position-filtered
+//       input): one thread per row, RPN interpreter, global open-addressing table keyed by the group-by values,
+//       atomic accumulators. Falls back from the fast kernel when more than G groups show up.
+//
+// Group order and representative rows follow the reference: first appearance in row order — or ascending key with the
+// NULL group first and the LAST row as representative when the immediate-key shortcut applies (:781-804, :367).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <numeric>
+
+#include "device_utils.cuh"
 #include "internal.hpp"
+#include "predicate.cuh"
+
+namespace hyb {
+
+constexpr int kAggThreads = 256;
+constexpr int kAggWarps = kAggThreads / 32;
+constexpr int kAggTileRows = 4096;
+constexpr int kMaxKeyWords = HYB_MAX_GROUPBY_COLUMNS;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Shared device helpers
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+  x ^= x >> 33;
+  x *= 0xFF51AFD7ED558CCDull;
+  x ^= x >> 33;
+  x *= 0xC4CEB9FE1A85EC53ull;
+  x ^= x >> 33;
+  return x;
+}
+
+// One AggregateKeyEntry (aggregate_hash.cpp:737-925). int32 -> value - INT32_MIN + 1, strings -> the per-dictionary
+// codes the shim computed with the reference's scheme, other types -> their bit pattern (only equality matters).
+__device__ __forceinline__ unsigned long long key_entry_from_code(const DevSegment& segment, uint32_t code_or_row,
+                                                                  bool is_dictionary_code, bool& is_null) {
+  is_null = false;
+  if (is_dictionary_code) {
+    const uint32_t value_id = code_or_row;
+    if (value_id >= segment.dict_size) {
+      is_null = true;
+      return 0;
+    }
+    if (segment.dict_codes) return __ldg(segment.dict_codes + value_id);
+    switch (segment.data_type) {
+      case HYB_TYPE_INT32:
+        return static_cast<unsigned long long>(static_cast<long long>(__ldg(static_cast<const int32_t*>(segment.values) + value_id)) + 2147483648ll) + 1ull;
+      case HYB_TYPE_INT64:
+        return static_cast<unsigned long long>(__ldg(static_cast<const long long*>(segment.values) + value_id));
+      case HYB_TYPE_FLOAT32: {
+        const float v = __ldg(static_cast<const float*>(segment.values) + value_id);
+        return __float_as_uint(v == 0.0f ? 0.0f : v);
+      }
+      default: {
+        const double v = __ldg(static_cast<const double*>(segment.values) + value_id);
+        return static_cast<unsigned long long>(__double_as_longlong(v == 0.0 ? 0.0 : v));
+      }
+    }
+  }
+  return 0;
+}
+
+__device__ __forceinline__ unsigned long long key_entry_at(const DevSegment& segment, uint32_t row, bool& is_null) {
+  if (segment.encoding == HYB_ENC_DICTIONARY) {
+    const uint32_t value_id = load_code1(segment.av, segment.vector_type, segment.bit_width, row);
+    return key_entry_from_code(segment, value_id, true, is_null);
+  }
+  is_null = segment.nulls && segment.nulls[row];
+  if (is_null) return 0;
+  if (segment.encoding == HYB_ENC_FRAME_OF_REFERENCE) {
+    const uint32_t code = load_code1(segment.av, segment.vector_type, segment.bit_width, row);
+    const int32_t minimum = __ldg(static_cast<const int32_t*>(segment.values) + row / HYB_FOR_BLOCK_SIZE);
+    const int32_t value = static_cast<int32_t>(static_cast<uint32_t>(minimum) + code);
+    return static_cast<unsigned long long>(static_cast<long long>(value) + 2147483648ll) + 1ull;
+  }
+  switch (segment.data_type) {
+    case HYB_TYPE_INT32:
+      return static_cast<unsigned long long>(static_cast<long long>(__ldg(static_cast<const int32_t*>(segment.values) + row)) + 2147483648ll) + 1ull;
+    case HYB_TYPE_INT64:
+      return static_cast<unsigned long long>(__ldg(static_cast<const long long*>(segment.values) + row));
+    case HYB_TYPE_FLOAT32: {
+      const float v = __ldg(static_cast<const float*>(segment.values) + row);
+      return __float_as_uint(v == 0.0f ? 0.0f : v);
+    }
+    default: {
+      const double v = __ldg(static_cast<const double*>(segment.values) + row);
+      return static_cast<unsigned long long>(__double_as_longlong(v == 0.0 ? 0.0 : v));
+    }
+  }
+}
+
+// A typed scalar on the device (mirror of the reference's AllTypeVariant for the four numeric types).
+struct DevScalar {
+  int32_t type;
+  bool is_null;
+  union {
+    int32_t i32;
+    long long i64;
+    float f32;
+    double f64;
+  };
+};
+
+__device__ __forceinline__ DevScalar scalar_at(const DevSegment& segment, uint32_t row) {
+  DevScalar s;
+  s.type = segment.data_type;
+  s.i64 = 0;
+  uint32_t index = row;
+  if (segment.encoding == HYB_ENC_DICTIONARY) {
+    index = load_code1(segment.av, segment.vector_type, segment.bit_width, row);
+    s.is_null = index >= segment.dict_size;
+    if (s.is_null) return s;
+  } else {
+    s.is_null = segment.nulls && segment.nulls[row];
+    if (s.is_null) return s;
+    if (segment.encoding == HYB_ENC_FRAME_OF_REFERENCE) {
+      const uint32_t code = load_code1(segment.av, segment.vector_type, segment.bit_width, row);
+      const int32_t minimum = __ldg(static_cast<const int32_t*>(segment.values) + row / HYB_FOR_BLOCK_SIZE);
+      s.i32 = static_cast<int32_t>(static_cast<uint32_t>(minimum) + code);
+      return s;
+    }
+  }
+  switch (segment.data_type) {
+    case HYB_TYPE_INT32:
+      s.i32 = __ldg(static_cast<const int32_t*>(segment.values) + index);
+      break;
+    case HYB_TYPE_INT64:
+      s.i64 = __ldg(static_cast<const long long*>(segment.values) + index);
+      break;
+    case HYB_TYPE_FLOAT32:
+      s.f32 = __ldg(static_cast<const float*>(segment.values) + index);
+      break;
+    default:
+      s.f64 = __ldg(static_cast<const double*>(segment.values) + index);
+      break;
+  }
+  return s;
+}
+
+__device__ __forceinline__ double scalar_to_double(const DevScalar& s) {
+  switch (s.type) {
+    case HYB_TYPE_INT32:
+      return static_cast<double>(s.i32);
+    case HYB_TYPE_INT64:
+      return static_cast<double>(s.i64);
+    case HYB_TYPE_FLOAT32:
+      return static_cast<double>(s.f32);
+    default:
+      return s.f64;
+  }
+}
+__device__ __forceinline__ float scalar_to_float(const DevScalar& s) {
+  switch (s.type) {
+    case HYB_TYPE_INT32:
+      return static_cast<float>(s.i32);
+    case HYB_TYPE_INT64:
+      return static_cast<float>(s.i64);
+    case HYB_TYPE_FLOAT32:
+      return s.f32;
+    default:
+      return static_cast<float>(s.f64);
+  }
+}
+__device__ __forceinline__ long long scalar_to_int64(const DevScalar& s) {
+  switch (s.type) {
+    case HYB_TYPE_INT32:
+      return s.i32;
+    case HYB_TYPE_INT64:
+      return s.i64;
+    case HYB_TYPE_FLOAT32:
+      return static_cast<long long>(s.f32);
+    default:
+      return static_cast<long long>(s.f64);
+  }
+}
+
+__host__ __device__ inline int32_t expression_common_type(int32_t lhs, int32_t rhs) {  // expression_utils.cpp:172-205
+  if (lhs == HYB_TYPE_FLOAT64 || rhs == HYB_TYPE_FLOAT64) return HYB_TYPE_FLOAT64;
+  const bool lhs_float = lhs == HYB_TYPE_FLOAT32, rhs_float = rhs == HYB_TYPE_FLOAT32;
+  if (lhs == HYB_TYPE_INT64) return rhs_float ? HYB_TYPE_FLOAT64 : HYB_TYPE_INT64;
+  if (rhs == HYB_TYPE_INT64) return lhs_float ? HYB_TYPE_FLOAT64 : HYB_TYPE_INT64;
+  if (lhs_float || rhs_float) return HYB_TYPE_FLOAT32;
+  return HYB_TYPE_INT32;
+}
+
+// std::common_type_t<A, B> of the two C++ types: the type the reference computes in (expression_functors.hpp:136-145).
+__host__ __device__ inline int32_t cpp_common_type(int32_t a, int32_t b) {
+  if (a == HYB_TYPE_FLOAT64 || b == HYB_TYPE_FLOAT64) return HYB_TYPE_FLOAT64;
+  if (a == HYB_TYPE_FLOAT32 || b == HYB_TYPE_FLOAT32) return HYB_TYPE_FLOAT32;  // int64 (x) float -> float
+  if (a == HYB_TYPE_INT64 || b == HYB_TYPE_INT64) return HYB_TYPE_INT64;
+  return HYB_TYPE_INT32;
+}
+
+__device__ DevScalar apply_arithmetic(int32_t op, const DevScalar& a, const DevScalar& b) {
+  DevScalar result;
+  result.type = expression_common_type(a.type, b.type);
+  result.is_null = a.is_null || b.is_null;
+  result.i64 = 0;
+  if (op == HYB_EXPR_DIV) {  // DivisionEvaluator: NULL on division by zero, computed in the result type
+    if (result.is_null) return result;
+    const bool zero = (b.type == HYB_TYPE_INT32 && b.i32 == 0) || (b.type == HYB_TYPE_INT64 && b.i64 == 0) ||
+                      (b.type == HYB_TYPE_FLOAT32 && b.f32 == 0.0f) || (b.type == HYB_TYPE_FLOAT64 && b.f64 == 0.0);
+    if (zero) {
+      result.is_null = true;
+      return result;
+    }
+    switch (result.type) {
+      case HYB_TYPE_INT32:
+        result.i32 = static_cast<int32_t>(scalar_to_int64(a)) / static_cast<int32_t>(scalar_to_int64(b));
+        break;
+      case HYB_TYPE_INT64:
+        result.i64 = scalar_to_int64(a) / scalar_to_int64(b);
+        break;
+      case HYB_TYPE_FLOAT32:
+        result.f32 = __fdiv_rn(scalar_to_float(a), scalar_to_float(b));
+        break;
+      default:
+        result.f64 = __ddiv_rn(scalar_to_double(a), scalar_to_double(b));
+        break;
+    }
+    return result;
+  }
+  if (result.is_null) return result;
+  const int32_t common = cpp_common_type(a.type, b.type);
+  switch (common) {
+    case HYB_TYPE_INT32: {
+      const int32_t x = a.i32, y = b.i32;
+      const int32_t v = op == HYB_EXPR_ADD ? static_cast<int32_t>(static_cast<uint32_t>(x) + static_cast<uint32_t>(y))
+                        : op == HYB_EXPR_SUB ? static_cast<int32_t>(static_cast<uint32_t>(x) - static_cast<uint32_t>(y))
+                                             : static_cast<int32_t>(static_cast<uint32_t>(x) * static_cast<uint32_t>(y));
+      result.i32 = v;
+      break;
+    }
+    case HYB_TYPE_INT64: {
+      const unsigned long long x = static_cast<unsigned long long>(scalar_to_int64(a));
+      const unsigned long long y = static_cast<unsigned long long>(scalar_to_int64(b));
+      const long long v = static_cast<long long>(op == HYB_EXPR_ADD ? x + y : op == HYB_EXPR_SUB ? x - y : x * y);
+      if (result.type == HYB_TYPE_INT64) {
+        result.i64 = v;
+      } else {
+        result.f64 = static_cast<double>(v);
+      }
+      break;
+    }
+    case HYB_TYPE_FLOAT32: {
+      const float x = scalar_to_float(a), y = scalar_to_float(b);
+      const float v = op == HYB_EXPR_ADD ? __fadd_rn(x, y) : op == HYB_EXPR_SUB ? __fsub_rn(x, y) : __fmul_rn(x, y);
+      if (result.type == HYB_TYPE_FLOAT32) {
+        result.f32 = v;
+      } else {
+        result.f64 = static_cast<double>(v);  // int64 (x) float: computed in float, stored as double
+      }
+      break;
+    }
+    default: {
+      const double x = scalar_to_double(a), y = scalar_to_double(b);
+      result.f64 = op == HYB_EXPR_ADD ? __dadd_rn(x, y) : op == HYB_EXPR_SUB ? __dsub_rn(x, y) : __dmul_rn(x, y);
+      break;
+    }
+  }
+  return result;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Plan (device-resident, read-only)
+// ---------------------------------------------------------------------------------------------------------------------
+struct DevExprNode {
+  int32_t op;
+  uint32_t column;  // index into AggregatePlan::columns
+  int32_t literal_type;
+  hyb_value literal;
+};
+
+struct DevAggregate {
+  int32_t function;
+  uint32_t node_count;
+  int32_t input_type;
+  int32_t result_type;
+  DevExprNode nodes[HYB_MAX_EXPR_NODES];
+};
+
+struct AggregatePlan {
+  // input positions
+  const uint2* tile_map;       // unfiltered
+  const hyb_row_id* filter;    // filtered
+  const unsigned long long* chunk_row_start;
+  unsigned long long position_count;
+  uint32_t tile_count;
+  uint32_t chunk_count;
+  // fused predicates
+  uint32_t predicate_count;
+  const DevSegment* predicate_segments[HYB_MAX_FUSED_PREDICATES];
+  const ChunkTest* predicate_tests[HYB_MAX_FUSED_PREDICATES];
+  // group-by
+  uint32_t groupby_count;
+  const DevSegment* group_segments[HYB_MAX_GROUPBY_COLUMNS];
+  // aggregates
+  uint32_t aggregate_count;
+  uint32_t column_count;
+  const DevSegment* columns[HYB_MAX_AGGREGATES * 4];
+  DevAggregate aggregates[HYB_MAX_AGGREGATES];
+};
+
+__device__ DevScalar evaluate_expression(const AggregatePlan& plan, const DevAggregate& aggregate, uint32_t chunk,
+                                         uint32_t row) {
+  DevScalar stack[HYB_MAX_EXPR_NODES];
+  int top = 0;
+  for (uint32_t n = 0; n < aggregate.node_count; ++n) {
+    const DevExprNode& node = aggregate.nodes[n];
+    if (node.op == HYB_EXPR_COLUMN) {
+      stack[top++] = scalar_at(plan.columns[node.column][chunk], row);
+    } else if (node.op == HYB_EXPR_LITERAL) {
+      DevScalar s;
+      s.type = node.literal_type;
+      s.is_null = false;
+      s.i64 = 0;
+      if (node.literal_type == HYB_TYPE_INT32) s.i32 = node.literal.i32;
+      if (node.literal_type == HYB_TYPE_INT64) s.i64 = node.literal.i64;
+      if (node.literal_type == HYB_TYPE_FLOAT32) s.f32 = node.literal.f32;
+      if (node.literal_type == HYB_TYPE_FLOAT64) s.f64 = node.literal.f64;
+      stack[top++] = s;
+    } else {
+      const DevScalar b = stack[--top];
+      const DevScalar a = stack[--top];
+      stack[top++] = apply_arithmetic(node.op, a, b);
+    }
+  }
+  return stack[0];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// General path
+// ---------------------------------------------------------------------------------------------------------------------
+struct GroupTable {
+  uint32_t capacity_mask;  // capacity - 1 (power of two)
+  uint32_t key_words;      // max(groupby_count, 1)
+  unsigned long long* hashes;    // 0 = empty
+  uint32_t* states;              // 2 = key words published
+  unsigned long long* keys;      // capacity * key_words
+  uint32_t* null_masks;          // capacity
+  unsigned long long* rows;      // capacity: COUNT(*)
+  unsigned long long* min_position;
+  unsigned long long* max_position;
+  unsigned long long* accumulators;  // aggregate_count * capacity (double / int64 / ordered min-max encodings)
+  unsigned long long* counts;        // aggregate_count * capacity (non-NULL inputs)
+  uint32_t* control;                 // [0] groups inserted, [1] overflow
+};
+
+__device__ __forceinline__ unsigned long long ordered_from_double(double value) {
+  const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(value));
+  return (bits >> 63) ? ~bits : (bits | 0x8000000000000000ull);
+}
+__device__ __forceinline__ unsigned long long ordered_from_int64(long long value) {
+  return static_cast<unsigned long long>(value) ^ 0x8000000000000000ull;
+}
+
+__device__ uint32_t find_or_insert_group(const GroupTable& table, const unsigned long long* key, uint32_t null_mask,
+                                         unsigned long long hash) {
+  uint32_t slot = static_cast<uint32_t>(hash >> 17) & table.capacity_mask;
+  for (uint32_t probes = 0; probes <= table.capacity_mask; ++probes) {
+    unsigned long long current = ld_volatile_u64(table.hashes + slot);
+    if (current == 0) {
+      current = atomicCAS(table.hashes + slot, 0ull, hash);
+      if (current == 0) {
+        for (uint32_t w = 0; w < table.key_words; ++w) table.keys[static_cast<size_t>(slot) * table.key_words + w] = key[w];
+        table.null_masks[slot] = null_mask;
+        __threadfence();
+        *reinterpret_cast<volatile uint32_t*>(table.states + slot) = 2;
+        const uint32_t inserted = atomicAdd(table.control, 1u) + 1;
+        if (inserted > (table.capacity_mask >> 1)) table.control[1] = 1;  // load factor > 0.5: ask for a bigger table
+        return slot;
+      }
+    }
+    if (current == hash) {
+      while (*reinterpret_cast<volatile uint32_t*>(table.states + slot) != 2) {
+      }
+      __threadfence();
+      bool equal = *reinterpret_cast<volatile uint32_t*>(table.null_masks + slot) == null_mask;
+      for (uint32_t w = 0; w < table.key_words && equal; ++w) {
+        equal = ld_volatile_u64(table.keys + static_cast<size_t>(slot) * table.key_words + w) == key[w];
+      }
+      if (equal) return slot;
+    }
+    slot = (slot + 1) & table.capacity_mask;
+  }
+  table.control[1] = 1;
+  return 0xFFFFFFFFu;
+}
+
+__global__ void __launch_bounds__(kAggThreads) aggregate_general_kernel(const AggregatePlan* __restrict__ plan_ptr,
+                                                                        const GroupTable table) {
+  const AggregatePlan& plan = *plan_ptr;
+  const uint32_t capacity = table.capacity_mask + 1;
+  for (uint32_t tile = blockIdx.x; tile < plan.tile_count; tile += gridDim.x) {
+    for (uint32_t index = threadIdx.x; index < kAggTileRows; index += kAggThreads) {
+      uint32_t chunk, row;
+      unsigned long long position;
+      if (plan.tile_map) {
+        const uint2 info = __ldg(plan.tile_map + tile);
+        chunk = info.x;
+        row = (info.y & 0x7FFFFFFFu) + index;
+        const DevSegment& first = plan.groupby_count      ? plan.group_segments[0][chunk]
+                                  : plan.column_count     ? plan.columns[0][chunk]
+                                  : plan.predicate_count  ? plan.predicate_segments[0][chunk]
+                                                          : plan.group_segments[0][chunk];
+        if (row >= first.row_count) continue;
+        position = __ldg(plan.chunk_row_start + chunk) + row;
+      } else {
+        position = static_cast<unsigned long long>(tile) * kAggTileRows + index;
+        if (position >= plan.position_count) continue;
+        const hyb_row_id row_id = plan.filter[position];
+        chunk = row_id.chunk_id;
+        row = row_id.chunk_offset;
+      }
+      bool keep = true;
+      for (uint32_t p = 0; p < plan.predicate_count && keep; ++p) {
+        keep = evaluate1(plan.predicate_segments[p][chunk], plan.predicate_tests[p][chunk], row);
+      }
+      if (!keep) continue;
+
+      unsigned long long key[kMaxKeyWords];
+      uint32_t null_mask = 0;
+      unsigned long long hash = 0x9E3779B97F4A7C15ull;
+      for (uint32_t g = 0; g < plan.groupby_count; ++g) {
+        bool is_null;
+        key[g] = key_entry_at(plan.group_segments[g][chunk], row, is_null);
+        if (is_null) null_mask |= 1u << g;
+        hash = mix64(hash ^ key[g]) + (is_null ? 0x51ED270B3Full : 0ull);
+      }
+      if (plan.groupby_count == 0) key[0] = 0;
+      hash = mix64(hash) | 1ull;
+      const uint32_t slot = find_or_insert_group(table, key, null_mask, hash);
+      if (slot == 0xFFFFFFFFu) continue;
+      atomicAdd(table.rows + slot, 1ull);
+      atomicMin(table.min_position + slot, position);
+      atomicMax(table.max_position + slot, position);
+
+      for (uint32_t a = 0; a < plan.aggregate_count; ++a) {
+        const DevAggregate& aggregate = plan.aggregates[a];
+        if (aggregate.function == HYB_AGG_COUNT_STAR) continue;
+        const DevScalar value = evaluate_expression(plan, aggregate, chunk, row);
+        if (value.is_null) continue;
+        unsigned long long* accumulator = table.accumulators + static_cast<size_t>(a) * capacity + slot;
+        atomicAdd(table.counts + static_cast<size_t>(a) * capacity + slot, 1ull);
+        const bool integral = value.type == HYB_TYPE_INT32 || value.type == HYB_TYPE_INT64;
+        switch (aggregate.function) {
+          case HYB_AGG_SUM:
+          case HYB_AGG_AVG:
+            if (integral) {
+              atomicAdd(accumulator, static_cast<unsigned long long>(scalar_to_int64(value)));
+            } else {
+              atomicAdd(reinterpret_cast<double*>(accumulator), scalar_to_double(value));
+            }
+            break;
+          case HYB_AGG_MIN:
+            atomicMin(accumulator, integral ? ordered_from_int64(scalar_to_int64(value))
+                                            : ordered_from_double(scalar_to_double(value)));
+            break;
+          case HYB_AGG_MAX:
+            atomicMax(accumulator, integral ? ordered_from_int64(scalar_to_int64(value))
+                                            : ordered_from_double(scalar_to_double(value)));
+            break;
+          default:
+            break;
+        }
+      }
+    }
+  }
+}
+
+__global__ void gather_row_ids_kernel(const unsigned long long* __restrict__ positions, uint32_t count,
+                                      const hyb_row_id* __restrict__ filter, hyb_row_id* __restrict__ out) {
+  const uint32_t index = blockIdx.x * blockDim.x + threadIdx.x;
+  if (index < count) out[index] = filter[positions[index]];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fast path
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kFastMaxColumns = 4;
+enum AffineKind : int32_t { kIdentity = 0, kLiteralMinusColumn = 1, kLiteralPlusColumn = 2, kColumnMinusLiteral = 3, kColumnPlusLiteral = 4 };
+
+struct FastPlan {
+  const uint2* tile_map;
+  const unsigned long long* chunk_row_start;
+  uint32_t tile_count;
+  uint32_t predicate_count;
+  const DevSegment* predicate_segments[HYB_MAX_FUSED_PREDICATES];
+  const ChunkTest* predicate_tests[HYB_MAX_FUSED_PREDICATES];
+  uint32_t groupby_count;
+  const DevSegment* group_segments[HYB_MAX_GROUPBY_COLUMNS];
+  const DevSegment* value_segments[kFastMaxColumns];
+  int32_t affine_kind[kFastMaxColumns];
+  double literal[kFastMaxColumns];
+  uint32_t need_raw_mask;   // bit i: accumulate column i itself
+  uint32_t need_product_mask;  // bit i: accumulate f0(col0) * ... * fi(coli)
+  // per-CTA partials
+  unsigned long long* partial_hash;      // [cta][G]
+  unsigned long long* partial_keys;      // [cta][G][kMaxKeyWords]
+  uint32_t* partial_null_mask;           // [cta][G]
+  unsigned long long* partial_rows;      // [cta][G]
+  unsigned long long* partial_min_position;
+  unsigned long long* partial_max_position;
+  unsigned long long* partial_raw;       // [cta][G][C] (double or int64 bits)
+  unsigned long long* partial_product;   // [cta][G][C]
+  unsigned long long* partial_raw_nulls;      // [cta][G][C]
+  unsigned long long* partial_product_nulls;  // [cta][G][C]
+  uint32_t* overflow;                    // set when a CTA sees more than G groups
+};
+
+template <int W>
+struct WorkType;
+template <>
+struct WorkType<0> {
+  using Value = float;
+  using Accumulator = double;
+};
+template <>
+struct WorkType<1> {
+  using Value = double;
+  using Accumulator = double;
+};
+template <>
+struct WorkType<2> {
+  using Value = long long;
+  using Accumulator = long long;
+};
+
+template <int W>
+__device__ __forceinline__ typename WorkType<W>::Value typed_load(const void* base, uint8_t data_type, uint32_t index) {
+  if constexpr (W == 0) {
+    return __ldg(static_cast<const float*>(base) + index);
+  } else if constexpr (W == 1) {
+    return __ldg(static_cast<const double*>(base) + index);
+  } else {
+    return data_type == HYB_TYPE_INT32 ? static_cast<long long>(__ldg(static_cast<const int32_t*>(base) + index))
+                                       : __ldg(static_cast<const long long*>(base) + index);
+  }
+}
+
+// Values of 8 consecutive rows of a value column in the working type + NULL bits.
+template <int W>
+__device__ __forceinline__ void load_values8(const DevSegment& segment, uint32_t row0, typename WorkType<W>::Value (&values)[8],
+                                             uint32_t& null_bits) {
+  using Value = typename WorkType<W>::Value;
+  null_bits = 0;
+  if (segment.encoding == HYB_ENC_DICTIONARY) {
+    uint32_t codes[8];
+    load_codes8(segment.av, segment.vector_type, segment.bit_width, row0, segment.row_count, codes);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool is_null = codes[j] >= segment.dict_size;
+      null_bits |= is_null ? (1u << j) : 0u;
+      values[j] = is_null ? Value{} : typed_load<W>(segment.values, segment.data_type, codes[j]);
+    }
+    return;
+  }
+  null_bits = load_nulls8(segment.nulls, row0);
+  if (segment.encoding == HYB_ENC_FRAME_OF_REFERENCE) {
+    if constexpr (W == 2) {
+      uint32_t codes[8];
+      load_codes8(segment.av, segment.vector_type, segment.bit_width, row0, segment.row_count, codes);
+      const int32_t minimum = __ldg(static_cast<const int32_t*>(segment.values) + row0 / HYB_FOR_BLOCK_SIZE);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) values[j] = static_cast<int32_t>(static_cast<uint32_t>(minimum) + codes[j]);
+    }
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    values[j] = (row0 + j < segment.row_count) ? typed_load<W>(segment.values, segment.data_type, row0 + j) : Value{};
+  }
+}
+
+template <int W>
+__device__ __forceinline__ typename WorkType<W>::Value apply_affine(int32_t kind, typename WorkType<W>::Value literal,
+                                                                    typename WorkType<W>::Value value) {
+  if constexpr (W == 0) {
+    switch (kind) {
+      case kLiteralMinusColumn:
+        return __fsub_rn(literal, value);
+      case kLiteralPlusColumn:
+        return __fadd_rn(literal, value);
+      case kColumnMinusLiteral:
+        return __fsub_rn(value, literal);
+      case kColumnPlusLiteral:
+        return __fadd_rn(value, literal);
+      default:
+        return value;
+    }
+  } else if constexpr (W == 1) {
+    switch (kind) {
+      case kLiteralMinusColumn:
+        return __dsub_rn(literal, value);
+      case kLiteralPlusColumn:
+        return __dadd_rn(literal, value);
+      case kColumnMinusLiteral:
+        return __dsub_rn(value, literal);
+      case kColumnPlusLiteral:
+        return __dadd_rn(value, literal);
+      default:
+        return value;
+    }
+  } else {
+    return value;
+  }
+}
+
+template <int W>
+__device__ __forceinline__ typename WorkType<W>::Value multiply(typename WorkType<W>::Value a, typename WorkType<W>::Value b) {
+  if constexpr (W == 0) {
+    return __fmul_rn(a, b);
+  } else if constexpr (W == 1) {
+    return __dmul_rn(a, b);
+  } else {
+    return a * b;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_reduce_add(T value) {
+#pragma unroll
+  for (int delta = 16; delta > 0; delta >>= 1) value += __shfl_xor_sync(kFullMask, value, delta);
+  return value;
+}
+
+template <int W, int G, int C>
+__global__ void __launch_bounds__(kAggThreads, 1) aggregate_fast_kernel(const FastPlan* __restrict__ plan_ptr) {
+  using Value = typename WorkType<W>::Value;
+  using Accumulator = typename WorkType<W>::Accumulator;
+  const FastPlan& plan = *plan_ptr;
+
+  __shared__ unsigned long long s_hash[G];
+  __shared__ unsigned long long s_keys[G][kMaxKeyWords];
+  __shared__ uint32_t s_null_mask[G];
+  __shared__ unsigned long long s_null_counts[2][G][C];  // [raw | product] NULL inputs (rare path)
+  __shared__ Accumulator s_reduce[kAggWarps];
+  __shared__ unsigned long long s_reduce_u64[kAggWarps];
+
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < G) {
+    s_hash[threadIdx.x] = 0;
+    s_null_mask[threadIdx.x] = 0;
+    for (int w = 0; w < kMaxKeyWords; ++w) s_keys[threadIdx.x][w] = 0;
+    for (int c = 0; c < C; ++c) {
+      s_null_counts[0][threadIdx.x][c] = 0;
+      s_null_counts[1][threadIdx.x][c] = 0;
+    }
+  }
+  __syncthreads();
+
+  Accumulator raw_sum[G][C], product_sum[G][C];
+  unsigned long long rows[G], min_position[G], max_position[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    rows[g] = 0;
+    min_position[g] = ~0ull;
+    max_position[g] = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      raw_sum[g][c] = Accumulator{};
+      product_sum[g][c] = Accumulator{};
+    }
+  }
+  Value literals[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) literals[c] = static_cast<Value>(plan.literal[c]);
+
+  // Static tile assignment (tile = blockIdx.x + k * gridDim.x) keeps the summation order reproducible.
+  for (uint32_t tile = blockIdx.x; tile < plan.tile_count; tile += gridDim.x) {
+    const uint2 info = __ldg(plan.tile_map + tile);
+    const uint32_t chunk = info.x;
+    const uint32_t tile_row0 = info.y & 0x7FFFFFFFu;
+    const unsigned long long chunk_first_position = __ldg(plan.chunk_row_start + chunk);
+    const uint32_t chunk_rows = plan.value_segments[0] ? plan.value_segments[0][chunk].row_count
+                                : plan.groupby_count  ? plan.group_segments[0][chunk].row_count
+                                                       : plan.predicate_segments[0][chunk].row_count;
+#pragma unroll 1
+    for (int it = 0; it < kAggTileRows / (kAggThreads * 8); ++it) {
+      const uint32_t row0 = tile_row0 + warp * (kAggTileRows / kAggWarps) + it * 256 + lane * 8;
+      if (row0 >= chunk_rows) continue;
+      uint32_t mask = chunk_rows - row0 >= 8 ? 0xFFu : ((1u << (chunk_rows - row0)) - 1u);
+      for (uint32_t p = 0; p < plan.predicate_count && mask; ++p) {
+        const ChunkTest test = plan.predicate_tests[p][chunk];
+        mask &= test.mode == kTestNone ? 0u : evaluate8(plan.predicate_segments[p][chunk], test, row0);
+      }
+      if (mask == 0) continue;
+
+      // group ids of the 8 rows
+      int32_t group_of[8];
+      if constexpr (G == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) group_of[j] = 0;
+        if (s_hash[0] == 0) s_hash[0] = 1;  // benign race: every writer stores the same value
+      } else {
+        unsigned long long hashes[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hashes[j] = 0x9E3779B97F4A7C15ull;
+        for (uint32_t q = 0; q < plan.groupby_count; ++q) {
+          const DevSegment& segment = plan.group_segments[q][chunk];
+          if (segment.encoding == HYB_ENC_DICTIONARY) {
+            uint32_t codes[8];
+            load_codes8(segment.av, segment.vector_type, segment.bit_width, row0, segment.row_count, codes);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              bool is_null;
+              const unsigned long long entry = key_entry_from_code(segment, codes[j], true, is_null);
+              hashes[j] = mix64(hashes[j] ^ entry) + (is_null ? 0x51ED270B3Full : 0ull);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              bool is_null = false;
+              const unsigned long long entry = (mask >> j) & 1u ? key_entry_at(segment, row0 + j, is_null) : 0ull;
+              hashes[j] = mix64(hashes[j] ^ entry) + (is_null ? 0x51ED270B3Full : 0ull);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          group_of[j] = -1;
+          if (!((mask >> j) & 1u)) continue;
+          const unsigned long long hash = mix64(hashes[j]) | 1ull;
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            if (group_of[j] < 0 && ld_volatile_u64(&s_hash[g]) == hash) group_of[j] = g;
+          }
+          if (group_of[j] < 0) {
+            // First sighting in this CTA: claim the first free slot (all threads probe in the same order).
+            for (int g = 0; g < G && group_of[j] < 0; ++g) {
+              const unsigned long long previous = atomicCAS(&s_hash[g], 0ull, hash);
+              if (previous == 0ull) {
+                uint32_t null_mask = 0;
+                for (uint32_t q = 0; q < plan.groupby_count; ++q) {
+                  bool is_null;
+                  s_keys[g][q] = key_entry_at(plan.group_segments[q][chunk], row0 + j, is_null);
+                  if (is_null) null_mask |= 1u << q;
+                }
+                s_null_mask[g] = null_mask;
+                group_of[j] = g;
+              } else if (previous == hash) {
+                group_of[j] = g;
+              }
+            }
+            if (group_of[j] < 0) {
+              *plan.overflow = 1;  // more than G groups: the host reruns the general kernel
+              mask &= ~(1u << j);
+            }
+          }
+        }
+      }
+
+      // Row counts and first / last position per group (positions ascend within a thread). Written as selects over
+      // ALL groups on purpose: an `if (group == g)` chain is folded by the compiler into an indexed access, which
+      // would move the accumulators from registers to local memory.
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (!((mask >> j) & 1u)) group_of[j] = -1;
+        const unsigned long long position = chunk_first_position + row0 + j;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const bool hit = group_of[j] == g;
+          min_position[g] = (hit && rows[g] == 0) ? position : min_position[g];
+          max_position[g] = hit ? position : max_position[g];
+          rows[g] += hit ? 1ull : 0ull;
+        }
+      }
+
+      // value columns: raw sums and the running product
+      Value product[8];
+      uint32_t product_nulls = 0;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        if (plan.value_segments[c] == nullptr) continue;
+        Value values[8];
+        uint32_t null_bits;
+        load_values8<W>(plan.value_segments[c][chunk], row0, values, null_bits);
+        const bool need_raw = (plan.need_raw_mask >> c) & 1u;
+        const bool need_product = (plan.need_product_mask >> c) & 1u;
+        const bool in_chain = (plan.need_product_mask >> c) != 0;  // some product at or after this column
+        if (in_chain) {
+          product_nulls |= null_bits;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const Value factor = apply_affine<W>(plan.affine_kind[c], literals[c], values[j]);
+            product[j] = c == 0 ? factor : multiply<W>(product[j], factor);
+          }
+        }
+        if (need_raw) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const Accumulator value = ((null_bits >> j) & 1u) ? Accumulator{} : static_cast<Accumulator>(values[j]);
+#pragma unroll
+            for (int g = 0; g < G; ++g) raw_sum[g][c] += group_of[j] == g ? value : Accumulator{};
+          }
+        }
+        if (need_product) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const Accumulator value = ((product_nulls >> j) & 1u) ? Accumulator{} : static_cast<Accumulator>(product[j]);
+#pragma unroll
+            for (int g = 0; g < G; ++g) product_sum[g][c] += group_of[j] == g ? value : Accumulator{};
+          }
+        }
+        if ((need_raw && (null_bits & mask)) || (need_product && (product_nulls & mask))) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (!((mask >> j) & 1u) || group_of[j] < 0) continue;
+            if (need_raw && ((null_bits >> j) & 1u)) atomicAdd(&s_null_counts[0][group_of[j]][c], 1ull);
+            if (need_product && ((product_nulls >> j) & 1u)) atomicAdd(&s_null_counts[1][group_of[j]][c], 1ull);
+          }
+        }
+      }
+    }
+  }
+
+  // CTA reduction in a fixed order: lanes (butterfly), then warps 0..7.
+  __syncthreads();
+  const size_t cta = blockIdx.x;
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const unsigned long long total_rows = warp_reduce_add(rows[g]);
+    unsigned long long low = min_position[g], high = max_position[g];
+#pragma unroll
+    for (int delta = 16; delta > 0; delta >>= 1) {
+      low = min(low, __shfl_xor_sync(kFullMask, low, delta));
+      high = max(high, __shfl_xor_sync(kFullMask, high, delta));
+    }
+    // rows
+    if (lane == 0) s_reduce_u64[warp] = total_rows;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long sum = 0;
+      for (int w = 0; w < kAggWarps; ++w) sum += s_reduce_u64[w];
+      plan.partial_rows[cta * G + g] = sum;
+    }
+    __syncthreads();
+    if (lane == 0) s_reduce_u64[warp] = low;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long value = ~0ull;
+      for (int w = 0; w < kAggWarps; ++w) value = min(value, s_reduce_u64[w]);
+      plan.partial_min_position[cta * G + g] = value;
+    }
+    __syncthreads();
+    if (lane == 0) s_reduce_u64[warp] = high;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long value = 0;
+      for (int w = 0; w < kAggWarps; ++w) value = max(value, s_reduce_u64[w]);
+      plan.partial_max_position[cta * G + g] = value;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        const Accumulator lane_sum = warp_reduce_add(which == 0 ? raw_sum[g][c] : product_sum[g][c]);
+        if (lane == 0) s_reduce[warp] = lane_sum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          Accumulator sum{};
+          for (int w = 0; w < kAggWarps; ++w) sum += s_reduce[w];
+          unsigned long long bits;
+          memcpy(&bits, &sum, sizeof(bits));
+          (which == 0 ? plan.partial_raw : plan.partial_product)[(cta * G + g) * C + c] = bits;
+        }
+        __syncthreads();
+      }
+    }
+  }
+  if (threadIdx.x < G) {
+    const int g = threadIdx.x;
+    plan.partial_hash[cta * G + g] = s_hash[g];
+    plan.partial_null_mask[cta * G + g] = s_null_mask[g];
+    for (int w = 0; w < kMaxKeyWords; ++w) plan.partial_keys[(cta * G + g) * kMaxKeyWords + w] = s_keys[g][w];
+    for (int c = 0; c < C; ++c) {
+      plan.partial_raw_nulls[(cta * G + g) * C + c] = s_null_counts[0][g][c];
+      plan.partial_product_nulls[(cta * G + g) * C + c] = s_null_counts[1][g][c];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------------------------------
+struct HostGroup {
+  std::vector<uint64_t> key;
+  uint32_t null_mask = 0;
+  uint64_t rows = 0;
+  uint64_t min_position = ~uint64_t{0};
+  uint64_t max_position = 0;
+  std::vector<uint64_t> accumulators;  // per aggregate (bits)
+  std::vector<uint64_t> counts;        // per aggregate
+};
+
+static int expression_type(const Table* table, const hyb_aggregate_def& def, int32_t* out_type) {
+  std::vector<int32_t> stack;
+  for (uint32_t n = 0; n < def.node_count; ++n) {
+    const auto& node = def.nodes[n];
+    if (node.op == HYB_EXPR_COLUMN) {
+      HYB_CHECK(node.column_id < table->column_count, HYB_ERR_INVALID, "expression column out of range");
+      const int32_t type = table->column_types[node.column_id];
+      HYB_CHECK(type != HYB_TYPE_STRING, HYB_ERR_UNSUPPORTED, "aggregates over string columns stay on the CPU operator");
+      stack.push_back(type < 0 ? HYB_TYPE_INT32 : type);
+    } else if (node.op == HYB_EXPR_LITERAL) {
+      HYB_CHECK(node.literal_type >= HYB_TYPE_INT32 && node.literal_type <= HYB_TYPE_FLOAT64, HYB_ERR_INVALID,
+                "bad literal type");
+      stack.push_back(node.literal_type);
+    } else {
+      HYB_CHECK(node.op >= HYB_EXPR_ADD && node.op <= HYB_EXPR_DIV, HYB_ERR_INVALID, "bad expression op");
+      HYB_CHECK(stack.size() >= 2, HYB_ERR_INVALID, "malformed expression");
+      const int32_t b = stack.back();
+      stack.pop_back();
+      const int32_t a = stack.back();
+      stack.pop_back();
+      stack.push_back(expression_common_type(a, b));
+    }
+  }
+  HYB_CHECK(stack.size() == 1, HYB_ERR_INVALID, "malformed expression");
+  *out_type = stack[0];
+  return HYB_OK;
+}
+
+static int32_t aggregate_result_type(int32_t function, int32_t input_type) {  // window_function_traits.hpp:14-77
+  const bool integral = input_type == HYB_TYPE_INT32 || input_type == HYB_TYPE_INT64;
+  switch (function) {
+    case HYB_AGG_COUNT:
+    case HYB_AGG_COUNT_STAR:
+      return HYB_TYPE_INT64;
+    case HYB_AGG_SUM:
+      return integral ? HYB_TYPE_INT64 : HYB_TYPE_FLOAT64;
+    case HYB_AGG_AVG:
+      return HYB_TYPE_FLOAT64;
+    default:
+      return input_type;
+  }
+}
+
+// ---- fast-path planning: recognise `col`, and left-nested products of {col, lit (+|-) col, col (+|-) lit} -----------
+struct Factor {
+  uint32_t column;
+  int32_t kind;
+  double literal;
+  bool operator==(const Factor& other) const {
+    return column == other.column && kind == other.kind && (kind == kIdentity || literal == other.literal);
+  }
+};
+
+static double literal_as_double(const hyb_expr_node& node) {
+  switch (node.literal_type) {
+    case HYB_TYPE_INT32:
+      return node.literal.i32;
+    case HYB_TYPE_INT64:
+      return static_cast<double>(node.literal.i64);
+    case HYB_TYPE_FLOAT32:
+      return node.literal.f32;
+    default:
+      return node.literal.f64;
+  }
+}
+
+// Parses the RPN program into a chain of factors; false if it is not of the supported shape.
+static bool parse_product_chain(const hyb_aggregate_def& def, std::vector<Factor>* chain) {
+  struct Item {
+    enum { kLiteral, kFactor, kChain } what;
+    double literal = 0;
+    int32_t literal_type = 0;
+    std::vector<Factor> factors;
+  };
+  std::vector<Item> stack;
+  for (uint32_t n = 0; n < def.node_count; ++n) {
+    const auto& node = def.nodes[n];
+    if (node.op == HYB_EXPR_COLUMN) {
+      Item item;
+      item.what = Item::kFactor;
+      item.factors.push_back(Factor{node.column_id, kIdentity, 0.0});
+      stack.push_back(item);
+    } else if (node.op == HYB_EXPR_LITERAL) {
+      Item item;
+      item.what = Item::kLiteral;
+      item.literal = literal_as_double(node);
+      item.literal_type = node.literal_type;
+      stack.push_back(item);
+    } else {
+      if (stack.size() < 2) return false;
+      Item b = stack.back();
+      stack.pop_back();
+      Item a = stack.back();
+      stack.pop_back();
+      Item result;
+      if (node.op == HYB_EXPR_ADD || node.op == HYB_EXPR_SUB) {
+        const bool plus = node.op == HYB_EXPR_ADD;
+        if (a.what == Item::kLiteral && b.what == Item::kFactor && b.factors[0].kind == kIdentity) {
+          result.what = Item::kFactor;
+          result.factors.push_back(Factor{b.factors[0].column, plus ? kLiteralPlusColumn : kLiteralMinusColumn, a.literal});
+        } else if (b.what == Item::kLiteral && a.what == Item::kFactor && a.factors[0].kind == kIdentity) {
+          result.what = Item::kFactor;
+          result.factors.push_back(Factor{a.factors[0].column, plus ? kColumnPlusLiteral : kColumnMinusLiteral, b.literal});
+        } else {
+          return false;
+        }
+      } else if (node.op == HYB_EXPR_MUL) {
+        if (a.what == Item::kLiteral || b.what == Item::kLiteral) return false;
+        if (b.what != Item::kFactor) return false;  // only left-nested products: (a * b) * c
+        result.what = Item::kChain;
+        result.factors = a.factors;
+        result.factors.push_back(b.factors[0]);
+      } else {
+        return false;
+      }
+      stack.push_back(result);
+    }
+  }
+  if (stack.size() != 1 || stack[0].what == Item::kLiteral) return false;
+  *chain = stack[0].factors;
+  return true;
+}
+
+struct FastMapping {
+  bool is_count_star = false;
+  bool uses_product = false;
+  uint32_t column_slot = 0;  // index into the canonical column list
+};
+
+struct FastPlanHost {
+  bool possible = false;
+  int work_type = 0;  // 0 float, 1 double, 2 int64
+  std::vector<Factor> columns;  // canonical order: the product chain first, then stand-alone columns
+  uint32_t chain_length = 0;
+  uint32_t need_raw_mask = 0, need_product_mask = 0;
+  std::vector<FastMapping> mapping;  // per aggregate
+};
+
+static FastPlanHost plan_fast_path(const Table* table, const hyb_aggregate_query* query) {
+  FastPlanHost plan;
+  if (query->filter) return plan;
+  std::vector<std::vector<Factor>> chains(query->aggregate_count);
+  std::vector<Factor> longest;
+  for (uint32_t a = 0; a < query->aggregate_count; ++a) {
+    const auto& def = query->aggregates[a];
+    if (def.function == HYB_AGG_COUNT_STAR) continue;
+    if (def.function != HYB_AGG_SUM && def.function != HYB_AGG_AVG && def.function != HYB_AGG_COUNT) return plan;
+    if (!parse_product_chain(def, &chains[a])) return plan;
+    const bool is_plain_column = chains[a].size() == 1 && chains[a][0].kind == kIdentity;
+    if (!is_plain_column && chains[a].size() > longest.size()) longest = chains[a];
+  }
+  // every non-trivial chain must be a prefix of the longest one
+  for (uint32_t a = 0; a < query->aggregate_count; ++a) {
+    const auto& chain = chains[a];
+    const bool is_plain_column = chain.size() == 1 && chain[0].kind == kIdentity;
+    if (chain.empty() || is_plain_column) continue;
+    if (chain.size() > longest.size()) return plan;
+    for (size_t i = 0; i < chain.size(); ++i) {
+      if (!(chain[i] == longest[i])) return plan;
+    }
+  }
+  plan.columns = longest;
+  plan.chain_length = static_cast<uint32_t>(longest.size());
+  // a column may appear only once in the chain (keeps the column <-> slot mapping unique)
+  for (size_t i = 0; i < longest.size(); ++i) {
+    for (size_t j = i + 1; j < longest.size(); ++j) {
+      if (longest[i].column == longest[j].column) return plan;
+    }
+  }
+  plan.mapping.resize(query->aggregate_count);
+  for (uint32_t a = 0; a < query->aggregate_count; ++a) {
+    const auto& def = query->aggregates[a];
+    auto& mapping = plan.mapping[a];
+    if (def.function == HYB_AGG_COUNT_STAR) {
+      mapping.is_count_star = true;
+      continue;
+    }
+    const auto& chain = chains[a];
+    const bool is_plain_column = chain.size() == 1 && chain[0].kind == kIdentity;
+    if (is_plain_column) {
+      size_t slot = plan.columns.size();
+      for (size_t i = 0; i < plan.columns.size(); ++i) {
+        if (plan.columns[i].column == chain[0].column) slot = i;
+      }
+      if (slot == plan.columns.size()) plan.columns.push_back(chain[0]);
+      // chain position 0 with identity kind: the product P_1 equals the raw column, either accumulator works
+      mapping.column_slot = static_cast<uint32_t>(slot);
+      plan.need_raw_mask |= 1u << slot;
+    } else {
+      mapping.uses_product = true;
+      mapping.column_slot = static_cast<uint32_t>(chain.size() - 1);
+      plan.need_product_mask |= 1u << (chain.size() - 1);
+    }
+  }
+  if (plan.columns.size() > kFastMaxColumns) return plan;
+  // one working type: all value columns share a type; arithmetic only on float / double columns
+  int32_t type = -1;
+  for (const auto& factor : plan.columns) {
+    const int32_t column_type = table->column_types[factor.column];
+    if (column_type == HYB_TYPE_STRING) return plan;
+    const int32_t normalised = column_type == HYB_TYPE_INT32 ? HYB_TYPE_INT64 : column_type;
+    if (type < 0) type = normalised;
+    if (type != normalised) return plan;
+  }
+  if (type < 0) type = HYB_TYPE_INT64;  // COUNT(*) only
+  if (type == HYB_TYPE_INT64 && plan.chain_length > 0) return plan;
+  if (type == HYB_TYPE_INT64) {
+    // int32 and int64 columns must not be mixed inside one FrameOfReference / value decode path: they are not (checked
+    // per segment at decode time through data_type), nothing to do.
+  }
+  // literals must be representable in the working type exactly as the reference converts them (int literal -> float)
+  plan.work_type = type == HYB_TYPE_FLOAT32 ? 0 : type == HYB_TYPE_FLOAT64 ? 1 : 2;
+  plan.possible = true;
+  return plan;
+}
+
+template <int W, int G>
+static void launch_fast_kernel_c(int columns, uint32_t grid, cudaStream_t stream, const FastPlan* plan) {
+  switch (columns) {
+    case 1:
+      aggregate_fast_kernel<W, G, 1><<<grid, kAggThreads, 0, stream>>>(plan);
+      break;
+    case 2:
+      aggregate_fast_kernel<W, G, 2><<<grid, kAggThreads, 0, stream>>>(plan);
+      break;
+    default:
+      aggregate_fast_kernel<W, G, 4><<<grid, kAggThreads, 0, stream>>>(plan);
+      break;
+  }
+}
+
+template <int W>
+static void launch_fast_kernel_g(int groups, int columns, uint32_t grid, cudaStream_t stream, const FastPlan* plan) {
+  switch (groups) {
+    case 1:
+      launch_fast_kernel_c<W, 1>(columns, grid, stream, plan);
+      break;
+    case 4:
+      launch_fast_kernel_c<W, 4>(columns, grid, stream, plan);
+      break;
+    default:
+      launch_fast_kernel_c<W, 8>(columns, grid, stream, plan);
+      break;
+  }
+}
+
+static void launch_fast_kernel(int work_type, int groups, int columns, uint32_t grid, cudaStream_t stream,
+                               const FastPlan* plan) {
+  switch (work_type) {
+    case 0:
+      launch_fast_kernel_g<0>(groups, columns, grid, stream, plan);
+      break;
+    case 1:
+      launch_fast_kernel_g<1>(groups, columns, grid, stream, plan);
+      break;
+    default:
+      launch_fast_kernel_g<2>(groups, columns, grid, stream, plan);
+      break;
+  }
+}
+
+static hyb_row_id position_to_row_id_host(const Table* table, uint64_t position) {
+  const auto& starts = table->chunk_row_start;
+  const auto it = std::upper_bound(starts.begin(), starts.end(), position);
+  const uint32_t chunk = static_cast<uint32_t>(it - starts.begin()) - 1;
+  return hyb_row_id{chunk, static_cast<uint32_t>(position - starts[chunk])};
+}
+
+static double double_from_ordered(uint64_t ordered) {
+  const uint64_t bits = (ordered >> 63) ? (ordered & 0x7FFFFFFFFFFFFFFFull) : ~ordered;
+  double value;
+  std::memcpy(&value, &bits, sizeof(value));
+  return value;
+}
+
+}  // namespace hyb
+
 using namespace hyb;
+
 extern "C" {
-int hyb_aggregate_hash(hyb_context*, const hyb_aggregate_query*, hyb_aggregate_result_t*) {
-  return fail(HYB_ERR_UNSUPPORTED, "hyb_aggregate_hash: not implemented yet");
+
+int hyb_aggregate_hash(hyb_context* context, const hyb_aggregate_query* query, hyb_aggregate_result_t* out_result) {
+  HYB_CHECK(context && query && out_result, HYB_ERR_INVALID, "NULL argument");
+  *out_result = 0;
+  HYB_CHECK(query->groupby_count <= HYB_MAX_GROUPBY_COLUMNS, HYB_ERR_UNSUPPORTED, "too many group-by columns");
+  HYB_CHECK(query->aggregate_count <= HYB_MAX_AGGREGATES, HYB_ERR_UNSUPPORTED, "too many aggregates");
+  HYB_CHECK(query->predicate_count <= HYB_MAX_FUSED_PREDICATES, HYB_ERR_UNSUPPORTED, "too many fused predicates");
+  HYB_CHECK(query->groupby_count == 0 || query->groupby_column_ids, HYB_ERR_INVALID, "groupby_column_ids is NULL");
+  HYB_CHECK(query->aggregate_count == 0 || query->aggregates, HYB_ERR_INVALID, "aggregates is NULL");
+  HYB_CHECK(query->predicate_count == 0 || query->predicates, HYB_ERR_INVALID, "predicates is NULL");
+  DeviceGuard guard(context->device);
+  std::lock_guard<std::mutex> lock(context->mutex);
+  auto* table = find_table(context, query->table);
+  HYB_CHECK(table, HYB_ERR_NOT_FOUND, "unknown table handle");
+  PosList* filter = nullptr;
+  if (query->filter) {
+    filter = find_pos_list(context, query->filter);
+    HYB_CHECK(filter, HYB_ERR_NOT_FOUND, "unknown filter handle");
+    HYB_CHECK(filter->table == query->table, HYB_ERR_INVALID, "filter belongs to a different table");
+  }
+  HYB_TRY(sync_table_descriptors(context, table));
+  cudaStream_t stream = context->stream;
+  const uint32_t chunk_count = table->chunk_count();
+  const uint32_t aggregate_count = query->aggregate_count;
+
+  // ---- validate + type the aggregates -----------------------------------------------------------------------------
+  std::vector<int32_t> input_types(aggregate_count, HYB_TYPE_INT64), result_types(aggregate_count, HYB_TYPE_INT64);
+  for (uint32_t a = 0; a < aggregate_count; ++a) {
+    const auto& def = query->aggregates[a];
+    HYB_CHECK(def.function >= HYB_AGG_MIN && def.function <= HYB_AGG_COUNT_STAR, HYB_ERR_UNSUPPORTED,
+              "aggregate function " + std::to_string(def.function) + " runs on the CPU operator");
+    if (def.function == HYB_AGG_COUNT_STAR) continue;
+    HYB_CHECK(def.node_count >= 1 && def.node_count <= HYB_MAX_EXPR_NODES, HYB_ERR_INVALID, "bad expression length");
+    HYB_TRY(expression_type(table, def, &input_types[a]));
+    result_types[a] = aggregate_result_type(def.function, input_types[a]);
+  }
+  for (uint32_t g = 0; g < query->groupby_count; ++g) {
+    const uint32_t column = query->groupby_column_ids[g];
+    HYB_CHECK(column < table->column_count, HYB_ERR_INVALID, "group-by column out of range");
+    if (table->column_types[column] == HYB_TYPE_STRING) {
+      for (uint32_t chunk = 0; chunk < chunk_count; ++chunk) {
+        HYB_CHECK(table->segments[size_t{chunk} * table->column_count + column].dict_codes, HYB_ERR_UNSUPPORTED,
+                  "grouping by a string column needs dictionary_codes in its segments");
+      }
+    }
+  }
+
+  timing_begin(context);
+  uint32_t launches = 0;
+
+  // ---- fused predicates -------------------------------------------------------------------------------------------
+  std::vector<ChunkTest*> tests(query->predicate_count, nullptr);
+  std::vector<void*> bounds(query->predicate_count, nullptr);
+  const auto release_tests = [&]() {
+    for (auto* t : tests) device_free(context, t);
+    for (auto* b : bounds) device_free(context, b);
+  };
+  for (uint32_t p = 0; p < query->predicate_count; ++p) {
+    const int status = prepare_chunk_tests(context, table, &query->predicates[p], &tests[p], &bounds[p]);
+    if (status != HYB_OK) {
+      release_tests();
+      return status;
+    }
+    ++launches;
+  }
+
+  uint64_t position_count = table->row_count();
+  if (filter) {
+    HYB_CUDA(cudaStreamSynchronize(stream));
+    HYB_CUDA(cudaMemcpy(&position_count, filter->d_chunk_end + filter->chunk_count, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (position_count == ~uint64_t{0}) position_count = 0;
+  }
+
+  std::vector<HostGroup> groups;
+  bool done = false;
+  uint64_t algorithmic_bytes = 0;
+  {
+    // bytes of every referenced column, each counted once
+    std::vector<uint32_t> referenced;
+    for (uint32_t p = 0; p < query->predicate_count; ++p) referenced.push_back(query->predicates[p].column_id);
+    for (uint32_t g = 0; g < query->groupby_count; ++g) referenced.push_back(query->groupby_column_ids[g]);
+    for (uint32_t a = 0; a < aggregate_count; ++a) {
+      for (uint32_t n = 0; n < query->aggregates[a].node_count; ++n) {
+        if (query->aggregates[a].nodes[n].op == HYB_EXPR_COLUMN) referenced.push_back(query->aggregates[a].nodes[n].column_id);
+      }
+    }
+    std::sort(referenced.begin(), referenced.end());
+    referenced.erase(std::unique(referenced.begin(), referenced.end()), referenced.end());
+    for (const uint32_t column : referenced) {
+      for (uint32_t chunk = 0; chunk < chunk_count; ++chunk) {
+        const auto& segment = table->segments[size_t{chunk} * table->column_count + column];
+        if (segment.encoding == HYB_ENC_UNENCODED) {
+          algorithmic_bytes += data_type_size(segment.data_type) * segment.row_count;
+        } else {
+          algorithmic_bytes += vector_bytes(segment.vector_type, segment.bit_width, segment.row_count);
+          if (segment.encoding == HYB_ENC_DICTIONARY && segment.data_type != HYB_TYPE_STRING) {
+            algorithmic_bytes += data_type_size(segment.data_type) * segment.dict_size;
+          }
+          if (segment.encoding == HYB_ENC_FRAME_OF_REFERENCE) {
+            algorithmic_bytes += sizeof(int32_t) * ((segment.row_count + HYB_FOR_BLOCK_SIZE - 1) / HYB_FOR_BLOCK_SIZE);
+          }
+        }
+        if (segment.nulls) algorithmic_bytes += segment.row_count;
+      }
+    }
+    if (filter) algorithmic_bytes = position_count * sizeof(hyb_row_id);
+  }
+  bool kernel_timed = false;
+
+  // ---- fast path --------------------------------------------------------------------------------------------------
+  const FastPlanHost fast = plan_fast_path(table, query);
+  if (fast.possible && chunk_count > 0) {
+    const int column_template = fast.columns.size() <= 1 ? 1 : fast.columns.size() <= 2 ? 2 : 4;
+    const int group_template = query->groupby_count == 0 ? 1 : 8;  // try 4 first when there are group-by columns
+    std::vector<int> attempts;
+    if (query->groupby_count == 0) {
+      attempts = {1};
+    } else {
+      attempts = {4, 8};
+    }
+    (void)group_template;
+    const uint2* tile_map = nullptr;
+    uint32_t tile_count = 0;
+    HYB_TRY(get_tile_map(context, table, kAggTileRows, &tile_map, &tile_count));
+    for (const int G : attempts) {
+      const int C = column_template;
+      const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(tile_count, context->sm_count * 2));
+      FastPlan host_plan{};
+      host_plan.tile_map = tile_map;
+      host_plan.chunk_row_start = reinterpret_cast<const unsigned long long*>(table->d_chunk_row_start);
+      host_plan.tile_count = tile_count;
+      host_plan.predicate_count = query->predicate_count;
+      for (uint32_t p = 0; p < query->predicate_count; ++p) {
+        host_plan.predicate_segments[p] = table->d_segments + size_t{query->predicates[p].column_id} * chunk_count;
+        host_plan.predicate_tests[p] = tests[p];
+      }
+      host_plan.groupby_count = query->groupby_count;
+      for (uint32_t g = 0; g < query->groupby_count; ++g) {
+        host_plan.group_segments[g] = table->d_segments + size_t{query->groupby_column_ids[g]} * chunk_count;
+      }
+      for (size_t c = 0; c < fast.columns.size(); ++c) {
+        host_plan.value_segments[c] = table->d_segments + size_t{fast.columns[c].column} * chunk_count;
+        host_plan.affine_kind[c] = fast.columns[c].kind;
+        host_plan.literal[c] = fast.columns[c].literal;
+      }
+      if (fast.columns.empty() && query->groupby_count == 0 && query->predicate_count == 0) {
+        // COUNT(*) over the whole table: give the kernel a column to size chunks with
+        host_plan.group_segments[0] = table->d_segments;
+      }
+      host_plan.need_raw_mask = fast.need_raw_mask;
+      host_plan.need_product_mask = fast.need_product_mask;
+      const size_t entries = size_t{grid} * G;
+      const size_t words = entries * (1 + kMaxKeyWords + 3 + 4 * C) + entries;  // generous
+      void* scratch = nullptr;
+      HYB_TRY(device_alloc(context, sizeof(uint64_t) * words + sizeof(FastPlan) + 64, &scratch));
+      HYB_CUDA(cudaMemsetAsync(scratch, 0, sizeof(uint64_t) * words + sizeof(FastPlan) + 64, stream));
+      auto* cursor = static_cast<unsigned long long*>(scratch);
+      host_plan.partial_hash = cursor;
+      cursor += entries;
+      host_plan.partial_keys = cursor;
+      cursor += entries * kMaxKeyWords;
+      host_plan.partial_rows = cursor;
+      cursor += entries;
+      host_plan.partial_min_position = cursor;
+      cursor += entries;
+      host_plan.partial_max_position = cursor;
+      cursor += entries;
+      host_plan.partial_raw = cursor;
+      cursor += entries * C;
+      host_plan.partial_product = cursor;
+      cursor += entries * C;
+      host_plan.partial_raw_nulls = cursor;
+      cursor += entries * C;
+      host_plan.partial_product_nulls = cursor;
+      cursor += entries * C;
+      host_plan.partial_null_mask = reinterpret_cast<uint32_t*>(cursor);
+      cursor += (entries + 1) / 2;
+      host_plan.overflow = reinterpret_cast<uint32_t*>(cursor);
+      cursor += 1;
+      auto* device_plan = reinterpret_cast<FastPlan*>(cursor);
+      // value_segments[0] doubles as the "chunk size" source inside the kernel: make sure something is there
+      if (!host_plan.value_segments[0] && !host_plan.groupby_count && !host_plan.predicate_count) {
+        host_plan.groupby_count = 0;
+      }
+      HYB_CUDA(cudaMemcpyAsync(device_plan, &host_plan, sizeof(FastPlan), cudaMemcpyHostToDevice, stream));
+      timing_kernel_begin(context);
+      launch_fast_kernel(fast.work_type, G, C, grid, stream, device_plan);
+      timing_kernel_end(context);
+      kernel_timed = true;
+      HYB_CUDA(cudaGetLastError());
+      ++launches;
+      std::vector<uint64_t> host(words);
+      HYB_CUDA(cudaMemcpyAsync(host.data(), scratch, sizeof(uint64_t) * words, cudaMemcpyDeviceToHost, stream));
+      HYB_CUDA(cudaStreamSynchronize(stream));
+      device_free(context, scratch);
+      const auto offset_of = [&](const void* pointer) {
+        return static_cast<size_t>(static_cast<const unsigned long long*>(pointer) - static_cast<unsigned long long*>(scratch));
+      };
+      const uint32_t overflow = *reinterpret_cast<const uint32_t*>(&host[offset_of(host_plan.overflow)]);
+      if (overflow) continue;  // more groups than this instantiation holds
+      // merge the per-CTA partials in CTA order (deterministic)
+      const uint64_t* p_hash = &host[offset_of(host_plan.partial_hash)];
+      const uint64_t* p_keys = &host[offset_of(host_plan.partial_keys)];
+      const uint64_t* p_rows = &host[offset_of(host_plan.partial_rows)];
+      const uint64_t* p_min = &host[offset_of(host_plan.partial_min_position)];
+      const uint64_t* p_max = &host[offset_of(host_plan.partial_max_position)];
+      const uint64_t* p_raw = &host[offset_of(host_plan.partial_raw)];
+      const uint64_t* p_product = &host[offset_of(host_plan.partial_product)];
+      const uint64_t* p_raw_nulls = &host[offset_of(host_plan.partial_raw_nulls)];
+      const uint64_t* p_product_nulls = &host[offset_of(host_plan.partial_product_nulls)];
+      const uint32_t* p_null_mask = reinterpret_cast<const uint32_t*>(&host[offset_of(host_plan.partial_null_mask)]);
+      struct Merged {
+        uint64_t hash;
+        std::vector<uint64_t> key;
+        uint32_t null_mask;
+        uint64_t rows = 0, min_position = ~uint64_t{0}, max_position = 0;
+        std::vector<double> raw_f, product_f;
+        std::vector<int64_t> raw_i;
+        std::vector<uint64_t> raw_nulls, product_nulls;
+      };
+      std::vector<Merged> merged;
+      bool consistent = true;
+      for (size_t entry = 0; entry < entries; ++entry) {
+        if (p_hash[entry] == 0 || p_rows[entry] == 0) continue;
+        std::vector<uint64_t> key(p_keys + entry * kMaxKeyWords, p_keys + entry * kMaxKeyWords + std::max<uint32_t>(query->groupby_count, 1));
+        Merged* target = nullptr;
+        for (auto& m : merged) {
+          if (m.hash == p_hash[entry]) {
+            if (m.key != key || m.null_mask != p_null_mask[entry]) consistent = false;  // 64-bit hash collision
+            target = &m;
+          }
+        }
+        if (!target) {
+          merged.emplace_back();
+          target = &merged.back();
+          target->hash = p_hash[entry];
+          target->key = key;
+          target->null_mask = p_null_mask[entry];
+          target->raw_f.assign(C, 0.0);
+          target->product_f.assign(C, 0.0);
+          target->raw_i.assign(C, 0);
+          target->raw_nulls.assign(C, 0);
+          target->product_nulls.assign(C, 0);
+        }
+        target->rows += p_rows[entry];
+        target->min_position = std::min(target->min_position, p_min[entry]);
+        target->max_position = std::max(target->max_position, p_max[entry]);
+        for (int c = 0; c < C; ++c) {
+          if (fast.work_type == 2) {
+            target->raw_i[c] += static_cast<int64_t>(p_raw[entry * C + c]);
+          } else {
+            double raw, product;
+            std::memcpy(&raw, &p_raw[entry * C + c], sizeof(double));
+            std::memcpy(&product, &p_product[entry * C + c], sizeof(double));
+            target->raw_f[c] += raw;
+            target->product_f[c] += product;
+          }
+          target->raw_nulls[c] += p_raw_nulls[entry * C + c];
+          target->product_nulls[c] += p_product_nulls[entry * C + c];
+        }
+      }
+      if (!consistent) break;  // fall through to the general path
+      for (const auto& m : merged) {
+        HostGroup group;
+        group.key = m.key;
+        group.null_mask = m.null_mask;
+        group.rows = m.rows;
+        group.min_position = m.min_position;
+        group.max_position = m.max_position;
+        group.accumulators.assign(aggregate_count, 0);
+        group.counts.assign(aggregate_count, 0);
+        for (uint32_t a = 0; a < aggregate_count; ++a) {
+          const auto& mapping = fast.mapping[a];
+          if (mapping.is_count_star) {
+            group.counts[a] = m.rows;
+            continue;
+          }
+          const uint32_t slot = mapping.column_slot;
+          const uint64_t nulls = mapping.uses_product ? m.product_nulls[slot] : m.raw_nulls[slot];
+          group.counts[a] = m.rows - nulls;
+          if (fast.work_type == 2) {
+            const int64_t sum = m.raw_i[slot];
+            std::memcpy(&group.accumulators[a], &sum, sizeof(sum));
+          } else {
+            const double sum = mapping.uses_product ? m.product_f[slot] : m.raw_f[slot];
+            std::memcpy(&group.accumulators[a], &sum, sizeof(sum));
+          }
+        }
+        groups.push_back(std::move(group));
+      }
+      done = true;
+      break;
+    }
+  }
+
+  // ---- general path -----------------------------------------------------------------------------------------------
+  if (!done) {
+    AggregatePlan host_plan{};
+    const uint2* tile_map = nullptr;
+    if (filter) {
+      host_plan.filter = filter->d_row_ids;
+      host_plan.tile_count = static_cast<uint32_t>((position_count + kAggTileRows - 1) / kAggTileRows);
+    } else {
+      HYB_TRY(get_tile_map(context, table, kAggTileRows, &tile_map, &host_plan.tile_count));
+      host_plan.tile_map = tile_map;
+    }
+    host_plan.chunk_row_start = reinterpret_cast<const unsigned long long*>(table->d_chunk_row_start);
+    host_plan.position_count = position_count;
+    host_plan.chunk_count = chunk_count;
+    host_plan.predicate_count = query->predicate_count;
+    for (uint32_t p = 0; p < query->predicate_count; ++p) {
+      host_plan.predicate_segments[p] = table->d_segments + size_t{query->predicates[p].column_id} * chunk_count;
+      host_plan.predicate_tests[p] = tests[p];
+    }
+    host_plan.groupby_count = query->groupby_count;
+    for (uint32_t g = 0; g < query->groupby_count; ++g) {
+      host_plan.group_segments[g] = table->d_segments + size_t{query->groupby_column_ids[g]} * chunk_count;
+    }
+    if (query->groupby_count == 0) host_plan.group_segments[0] = table->d_segments;  // sizes chunks when nothing else does
+    host_plan.aggregate_count = aggregate_count;
+    std::vector<uint32_t> plan_columns;
+    for (uint32_t a = 0; a < aggregate_count; ++a) {
+      const auto& def = query->aggregates[a];
+      auto& device_aggregate = host_plan.aggregates[a];
+      device_aggregate.function = def.function;
+      device_aggregate.node_count = def.function == HYB_AGG_COUNT_STAR ? 0 : def.node_count;
+      device_aggregate.input_type = input_types[a];
+      device_aggregate.result_type = result_types[a];
+      for (uint32_t n = 0; n < device_aggregate.node_count; ++n) {
+        auto& node = device_aggregate.nodes[n];
+        node.op = def.nodes[n].op;
+        node.literal_type = def.nodes[n].literal_type;
+        node.literal = def.nodes[n].literal;
+        if (node.op == HYB_EXPR_COLUMN) {
+          auto it = std::find(plan_columns.begin(), plan_columns.end(), def.nodes[n].column_id);
+          if (it == plan_columns.end()) {
+            plan_columns.push_back(def.nodes[n].column_id);
+            it = plan_columns.end() - 1;
+          }
+          node.column = static_cast<uint32_t>(it - plan_columns.begin());
+        }
+      }
+    }
+    HYB_CHECK(plan_columns.size() <= HYB_MAX_AGGREGATES * 4, HYB_ERR_UNSUPPORTED, "too many distinct aggregate columns");
+    host_plan.column_count = static_cast<uint32_t>(plan_columns.size());
+    for (size_t c = 0; c < plan_columns.size(); ++c) {
+      host_plan.columns[c] = table->d_segments + size_t{plan_columns[c]} * chunk_count;
+    }
+    void* device_plan = nullptr;
+    HYB_TRY(device_alloc(context, sizeof(AggregatePlan), &device_plan));
+    HYB_CUDA(cudaMemcpyAsync(device_plan, &host_plan, sizeof(AggregatePlan), cudaMemcpyHostToDevice, stream));
+    HYB_CUDA(cudaStreamSynchronize(stream));  // host_plan is on the stack
+
+    uint64_t capacity = 1024;
+    while (capacity < std::min<uint64_t>(position_count * 2, uint64_t{1} << 20)) capacity <<= 1;
+    const uint32_t key_words = std::max<uint32_t>(query->groupby_count, 1);
+    while (!done) {
+      HYB_CHECK(capacity <= (uint64_t{1} << 31), HYB_ERR_OOM, "group table would exceed 2^31 slots");
+      const size_t per_slot_words = 1 + key_words + 3 + 2 * size_t{aggregate_count};
+      const size_t bytes = sizeof(uint64_t) * capacity * per_slot_words + sizeof(uint32_t) * capacity * 2 + 64;
+      void* scratch = nullptr;
+      HYB_TRY(device_alloc(context, bytes, &scratch));
+      HYB_CUDA(cudaMemsetAsync(scratch, 0, bytes, stream));
+      GroupTable group_table{};
+      group_table.capacity_mask = static_cast<uint32_t>(capacity - 1);
+      group_table.key_words = key_words;
+      auto* cursor = static_cast<unsigned long long*>(scratch);
+      group_table.hashes = cursor;
+      cursor += capacity;
+      group_table.keys = cursor;
+      cursor += capacity * key_words;
+      group_table.rows = cursor;
+      cursor += capacity;
+      group_table.min_position = cursor;
+      cursor += capacity;
+      group_table.max_position = cursor;
+      cursor += capacity;
+      group_table.accumulators = cursor;
+      cursor += capacity * aggregate_count;
+      group_table.counts = cursor;
+      cursor += capacity * aggregate_count;
+      group_table.states = reinterpret_cast<uint32_t*>(cursor);
+      group_table.null_masks = group_table.states + capacity;
+      group_table.control = group_table.null_masks + capacity;
+      HYB_CUDA(cudaMemsetAsync(group_table.min_position, 0xFF, sizeof(uint64_t) * capacity, stream));
+      for (uint32_t a = 0; a < aggregate_count; ++a) {
+        if (query->aggregates[a].function == HYB_AGG_MIN) {
+          HYB_CUDA(cudaMemsetAsync(group_table.accumulators + size_t{a} * capacity, 0xFF, sizeof(uint64_t) * capacity, stream));
+        }
+      }
+      const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(host_plan.tile_count, context->sm_count * 8));
+      if (!kernel_timed) timing_kernel_begin(context);
+      if (host_plan.tile_count) {
+        aggregate_general_kernel<<<grid, kAggThreads, 0, stream>>>(static_cast<const AggregatePlan*>(device_plan), group_table);
+        HYB_CUDA(cudaGetLastError());
+        ++launches;
+      }
+      if (!kernel_timed) timing_kernel_end(context);
+      kernel_timed = true;
+      std::vector<uint8_t> host(bytes);
+      HYB_CUDA(cudaMemcpyAsync(host.data(), scratch, bytes, cudaMemcpyDeviceToHost, stream));
+      HYB_CUDA(cudaStreamSynchronize(stream));
+      device_free(context, scratch);
+      const auto* words = reinterpret_cast<const uint64_t*>(host.data());
+      const size_t word_count = capacity * per_slot_words;
+      const auto* tail = reinterpret_cast<const uint32_t*>(words + word_count);
+      const uint32_t overflow = tail[2 * capacity + 1];
+      if (overflow) {
+        capacity <<= 3;
+        continue;
+      }
+      const uint64_t* h_hashes = words;
+      const uint64_t* h_keys = h_hashes + capacity;
+      const uint64_t* h_rows = h_keys + capacity * key_words;
+      const uint64_t* h_min = h_rows + capacity;
+      const uint64_t* h_max = h_min + capacity;
+      const uint64_t* h_acc = h_max + capacity;
+      const uint64_t* h_counts = h_acc + capacity * aggregate_count;
+      const uint32_t* h_null_masks = tail + capacity;
+      for (uint64_t slot = 0; slot < capacity; ++slot) {
+        if (h_hashes[slot] == 0) continue;
+        HostGroup group;
+        group.key.assign(h_keys + slot * key_words, h_keys + (slot + 1) * key_words);
+        group.null_mask = h_null_masks[slot];
+        group.rows = h_rows[slot];
+        group.min_position = h_min[slot];
+        group.max_position = h_max[slot];
+        group.accumulators.resize(aggregate_count);
+        group.counts.resize(aggregate_count);
+        for (uint32_t a = 0; a < aggregate_count; ++a) {
+          group.accumulators[a] = h_acc[size_t{a} * capacity + slot];
+          group.counts[a] = query->aggregates[a].function == HYB_AGG_COUNT_STAR ? group.rows : h_counts[size_t{a} * capacity + slot];
+          // undo the ordered encodings of MIN / MAX
+          const int32_t function = query->aggregates[a].function;
+          if ((function == HYB_AGG_MIN || function == HYB_AGG_MAX) && group.counts[a] > 0) {
+            const bool integral = input_types[a] == HYB_TYPE_INT32 || input_types[a] == HYB_TYPE_INT64;
+            if (integral) {
+              group.accumulators[a] ^= 0x8000000000000000ull;
+            } else {
+              const double value = double_from_ordered(group.accumulators[a]);
+              std::memcpy(&group.accumulators[a], &value, sizeof(value));
+            }
+          }
+        }
+        groups.push_back(std::move(group));
+      }
+      done = true;
+    }
+    device_free(context, device_plan);
+  }
+  release_tests();
+
+  // ---- order the groups like the reference and materialise the result ---------------------------------------------
+  uint64_t input_rows = 0;
+  for (const auto& group : groups) input_rows += group.rows;
+  bool immediate = false;
+  if (query->groupby_count == 1 && table->column_types[query->groupby_column_ids[0]] == HYB_TYPE_INT32) {
+    // immediate key shortcut (aggregate_hash.cpp:781-804)
+    uint64_t min_key = ~uint64_t{0}, max_key = 0;
+    for (const auto& group : groups) {
+      if (group.null_mask) continue;
+      min_key = std::min(min_key, group.key[0]);
+      max_key = std::max(max_key, group.key[0]);
+    }
+    immediate = max_key > 0 && static_cast<double>(max_key - min_key) < static_cast<double>(input_rows) * 1.2;
+  }
+  if (immediate) {
+    std::sort(groups.begin(), groups.end(), [](const HostGroup& a, const HostGroup& b) {
+      if ((a.null_mask != 0) != (b.null_mask != 0)) return a.null_mask != 0;  // NULL group first
+      return a.key[0] < b.key[0];
+    });
+  } else {
+    std::sort(groups.begin(), groups.end(),
+              [](const HostGroup& a, const HostGroup& b) { return a.min_position < b.min_position; });
+  }
+
+  auto result = std::make_unique<AggregateResult>();
+  const bool synthesize_empty_row = query->groupby_count == 0 && aggregate_count > 0 && groups.empty();  // (:1395-1405)
+  const size_t group_count = synthesize_empty_row ? 1 : groups.size();
+  result->group_count = group_count;
+  result->used_immediate_keys = immediate ? 1 : 0;
+  result->row_ids.resize(group_count);
+  if (synthesize_empty_row) {
+    result->row_ids[0] = hyb_row_id{HYB_INVALID_CHUNK_ID, HYB_INVALID_CHUNK_OFFSET};
+  } else if (!groups.empty()) {
+    std::vector<uint64_t> positions(groups.size());
+    for (size_t g = 0; g < groups.size(); ++g) {
+      positions[g] = immediate ? groups[g].max_position : groups[g].min_position;
+      // no group-by + COUNT(*) first: the reference stores RowID{0, 0} (aggregate_hash.cpp:1097-1102); any non-NULL
+      // RowID is equivalent since no group-by column is written.
+    }
+    if (filter) {
+      void* d_positions = nullptr;
+      void* d_rows = nullptr;
+      HYB_TRY(device_alloc(context, sizeof(uint64_t) * positions.size(), &d_positions));
+      HYB_TRY(device_alloc(context, sizeof(hyb_row_id) * positions.size(), &d_rows));
+      HYB_CUDA(cudaMemcpyAsync(d_positions, positions.data(), sizeof(uint64_t) * positions.size(), cudaMemcpyHostToDevice, stream));
+      gather_row_ids_kernel<<<static_cast<uint32_t>((positions.size() + 255) / 256), 256, 0, stream>>>(
+          static_cast<const unsigned long long*>(d_positions), static_cast<uint32_t>(positions.size()), filter->d_row_ids,
+          static_cast<hyb_row_id*>(d_rows));
+      HYB_CUDA(cudaGetLastError());
+      HYB_CUDA(cudaMemcpyAsync(result->row_ids.data(), d_rows, sizeof(hyb_row_id) * positions.size(), cudaMemcpyDeviceToHost, stream));
+      HYB_CUDA(cudaStreamSynchronize(stream));
+      device_free(context, d_positions);
+      device_free(context, d_rows);
+      ++launches;
+    } else {
+      for (size_t g = 0; g < groups.size(); ++g) result->row_ids[g] = position_to_row_id_host(table, positions[g]);
+    }
+  }
+  result->columns.resize(aggregate_count);
+  for (uint32_t a = 0; a < aggregate_count; ++a) {
+    const auto& def = query->aggregates[a];
+    auto& column = result->columns[a];
+    column.value_type = result_types[a];
+    const size_t element = (result_types[a] == HYB_TYPE_INT32 || result_types[a] == HYB_TYPE_FLOAT32) ? 4 : 8;
+    column.values.assign(group_count * element, 0);
+    column.nulls.assign(group_count, 0);
+    const bool integral = input_types[a] == HYB_TYPE_INT32 || input_types[a] == HYB_TYPE_INT64;
+    for (size_t g = 0; g < group_count; ++g) {
+      const uint64_t count = synthesize_empty_row ? 0 : groups[g].counts[a];
+      const uint64_t bits = synthesize_empty_row ? 0 : groups[g].accumulators[a];
+      uint8_t* out = column.values.data() + g * element;
+      if (def.function == HYB_AGG_COUNT || def.function == HYB_AGG_COUNT_STAR) {
+        const int64_t value = static_cast<int64_t>(count);
+        std::memcpy(out, &value, sizeof(value));
+        continue;
+      }
+      if (count == 0) {
+        column.nulls[g] = 1;
+        continue;
+      }
+      switch (def.function) {
+        case HYB_AGG_SUM:
+          std::memcpy(out, &bits, 8);  // int64 sum or double sum, already in the result representation
+          break;
+        case HYB_AGG_AVG: {
+          double sum;
+          if (integral) {
+            int64_t as_int;
+            std::memcpy(&as_int, &bits, sizeof(as_int));
+            sum = static_cast<double>(as_int);
+          } else {
+            std::memcpy(&sum, &bits, sizeof(sum));
+          }
+          const double average = sum / static_cast<double>(count);
+          std::memcpy(out, &average, sizeof(average));
+          break;
+        }
+        default: {  // MIN / MAX in the column type
+          if (result_types[a] == HYB_TYPE_INT32) {
+            const int32_t value = static_cast<int32_t>(static_cast<int64_t>(bits));
+            std::memcpy(out, &value, sizeof(value));
+          } else if (result_types[a] == HYB_TYPE_INT64) {
+            std::memcpy(out, &bits, 8);
+          } else {
+            double as_double;
+            std::memcpy(&as_double, &bits, sizeof(as_double));
+            if (result_types[a] == HYB_TYPE_FLOAT32) {
+              const float value = static_cast<float>(as_double);
+              std::memcpy(out, &value, sizeof(value));
+            } else {
+              std::memcpy(out, &as_double, sizeof(as_double));
+            }
+          }
+          break;
+        }
+      }
+    }
+  }
+  if (!kernel_timed) {
+    timing_kernel_begin(context);
+    timing_kernel_end(context);
+  }
+  timing_end(context, launches, algorithmic_bytes, filter ? position_count : table->row_count(), group_count);
+
+  const auto handle = context->next_handle++;
+  context->aggregate_results.emplace(handle, std::move(result));
+  *out_result = handle;
+  return HYB_OK;
 }
-int hyb_aggregate_result_info(hyb_context*, hyb_aggregate_result_t, uint64_t*, int32_t*) {
-  return fail(HYB_ERR_NOT_FOUND, "unknown aggregate result");
+
+static AggregateResult* find_aggregate_result(hyb_context* context, hyb_aggregate_result_t handle) {
+  auto it = context->aggregate_results.find(handle);
+  return it == context->aggregate_results.end() ? nullptr : it->second.get();
 }
-int hyb_aggregate_result_row_ids(hyb_context*, hyb_aggregate_result_t, hyb_row_id*) {
-  return fail(HYB_ERR_NOT_FOUND, "unknown aggregate result");
+
+int hyb_aggregate_result_info(hyb_context* context, hyb_aggregate_result_t handle, uint64_t* out_group_count,
+                              int32_t* out_used_immediate_keys) {
+  HYB_CHECK(context, HYB_ERR_INVALID, "context is NULL");
+  std::lock_guard<std::mutex> lock(context->mutex);
+  auto* result = find_aggregate_result(context, handle);
+  HYB_CHECK(result, HYB_ERR_NOT_FOUND, "unknown aggregate result handle");
+  if (out_group_count) *out_group_count = result->group_count;
+  if (out_used_immediate_keys) *out_used_immediate_keys = result->used_immediate_keys;
+  return HYB_OK;
 }
-int hyb_aggregate_result_values(hyb_context*, hyb_aggregate_result_t, uint32_t, void*, uint8_t*, int32_t*) {
-  return fail(HYB_ERR_NOT_FOUND, "unknown aggregate result");
+
+int hyb_aggregate_result_row_ids(hyb_context* context, hyb_aggregate_result_t handle, hyb_row_id* out_row_ids) {
+  HYB_CHECK(context, HYB_ERR_INVALID, "context is NULL");
+  std::lock_guard<std::mutex> lock(context->mutex);
+  auto* result = find_aggregate_result(context, handle);
+  HYB_CHECK(result, HYB_ERR_NOT_FOUND, "unknown aggregate result handle");
+  HYB_CHECK(out_row_ids || result->row_ids.empty(), HYB_ERR_INVALID, "out_row_ids is NULL");
+  std::copy(result->row_ids.begin(), result->row_ids.end(), out_row_ids);
+  return HYB_OK;
 }
-int hyb_aggregate_result_free(hyb_context*, hyb_aggregate_result_t) {
-  return fail(HYB_ERR_NOT_FOUND, "unknown aggregate result");
+
+int hyb_aggregate_result_values(hyb_context* context, hyb_aggregate_result_t handle, uint32_t aggregate_index,
+                                void* out_values, uint8_t* out_nulls, int32_t* out_value_type) {
+  HYB_CHECK(context, HYB_ERR_INVALID, "context is NULL");
+  std::lock_guard<std::mutex> lock(context->mutex);
+  auto* result = find_aggregate_result(context, handle);
+  HYB_CHECK(result, HYB_ERR_NOT_FOUND, "unknown aggregate result handle");
+  HYB_CHECK(aggregate_index < result->columns.size(), HYB_ERR_INVALID, "aggregate_index out of range");
+  const auto& column = result->columns[aggregate_index];
+  if (out_values && !column.values.empty()) std::memcpy(out_values, column.values.data(), column.values.size());
+  if (out_nulls && !column.nulls.empty()) std::memcpy(out_nulls, column.nulls.data(), column.nulls.size());
+  if (out_value_type) *out_value_type = column.value_type;
+  return HYB_OK;
 }
+
+int hyb_aggregate_result_free(hyb_context* context, hyb_aggregate_result_t handle) {
+  HYB_CHECK(context, HYB_ERR_INVALID, "context is NULL");
+  std::lock_guard<std::mutex> lock(context->mutex);
+  auto it = context->aggregate_results.find(handle);
+  HYB_CHECK(it != context->aggregate_results.end(), HYB_ERR_NOT_FOUND, "unknown aggregate result handle");
+  context->aggregate_results.erase(it);
+  return HYB_OK;
 }
+
+}  // extern "C"

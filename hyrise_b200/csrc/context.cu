@@ -53,7 +53,7 @@ void Arena::release() {
 Table::~Table() {
   if (d_segments) cudaFree(d_segments);
   if (d_chunk_row_start) cudaFree(d_chunk_row_start);
-  for (auto& entry : d_tile_starts) cudaFree(entry.second);
+  for (auto& entry : d_tile_maps) cudaFree(entry.second.first);
 }
 
 PosList::~PosList() {
@@ -115,33 +115,35 @@ int sync_table_descriptors(hyb_context* context, Table* table) {
                            table->chunk_row_start.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, context->stream));
   // `staged` is pageable, so the copies above have completed with respect to the host buffer on return.
   HYB_CUDA(cudaStreamSynchronize(context->stream));
-  for (auto& entry : table->d_tile_starts) cudaFree(entry.second);
-  table->d_tile_starts.clear();
-  table->h_tile_starts.clear();
+  for (auto& entry : table->d_tile_maps) cudaFree(entry.second.first);
+  table->d_tile_maps.clear();
   table->dirty = false;
   return HYB_OK;
 }
 
-int get_tile_starts(hyb_context* context, Table* table, uint32_t tile_rows, const uint32_t** out_device,
-                    uint32_t* out_tile_count) {
-  auto it = table->d_tile_starts.find(tile_rows);
-  if (it == table->d_tile_starts.end()) {
+int get_tile_map(hyb_context* context, Table* table, uint32_t tile_rows, const uint2** out_device,
+                 uint32_t* out_tile_count) {
+  auto it = table->d_tile_maps.find(tile_rows);
+  if (it == table->d_tile_maps.end()) {
+    // One entry per tile: {chunk, first row | last-tile-of-chunk flag in bit 31}. Tiles never straddle chunks.
+    std::vector<uint2> map;
     const uint32_t chunk_count = table->chunk_count();
-    std::vector<uint32_t> starts(chunk_count + 1);
-    uint32_t running = 0;
     for (uint32_t chunk = 0; chunk < chunk_count; ++chunk) {
-      starts[chunk] = running;
-      running += (table->chunk_rows[chunk] + tile_rows - 1) / tile_rows;
+      const uint32_t rows = table->chunk_rows[chunk];
+      for (uint32_t row0 = 0; row0 < rows; row0 += tile_rows) {
+        const bool last = row0 + tile_rows >= rows;
+        map.push_back(make_uint2(chunk, row0 | (last ? 0x80000000u : 0u)));
+      }
     }
-    starts[chunk_count] = running;
-    uint32_t* device = nullptr;
-    HYB_CUDA(cudaMalloc(&device, sizeof(uint32_t) * starts.size()));
-    HYB_CUDA(cudaMemcpy(device, starts.data(), sizeof(uint32_t) * starts.size(), cudaMemcpyHostToDevice));
-    it = table->d_tile_starts.emplace(tile_rows, device).first;
-    table->h_tile_starts.emplace(tile_rows, std::move(starts));
+    uint2* device = nullptr;
+    HYB_CUDA(cudaMalloc(&device, sizeof(uint2) * std::max<size_t>(map.size(), 1)));
+    if (!map.empty()) {
+      HYB_CUDA(cudaMemcpy(device, map.data(), sizeof(uint2) * map.size(), cudaMemcpyHostToDevice));
+    }
+    it = table->d_tile_maps.emplace(tile_rows, std::make_pair(device, static_cast<uint32_t>(map.size()))).first;
   }
-  *out_device = it->second;
-  *out_tile_count = table->h_tile_starts[tile_rows].back();
+  *out_device = it->second.first;
+  *out_tile_count = it->second.second;
   return HYB_OK;
 }
 

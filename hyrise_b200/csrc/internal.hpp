@@ -70,8 +70,7 @@ struct Table {
   uint64_t* d_chunk_row_start = nullptr;    // chunk_count + 1
   uint32_t d_chunk_capacity = 0;
   bool dirty = true;
-  std::map<uint32_t, uint32_t*> d_tile_starts;  // tile_rows -> device prefix array (chunk_count + 1)
-  std::map<uint32_t, std::vector<uint32_t>> h_tile_starts;
+  std::map<uint32_t, std::pair<uint2*, uint32_t>> d_tile_maps;  // tile_rows -> (device {chunk,row0} per tile, count)
 
   uint32_t chunk_count() const { return static_cast<uint32_t>(chunk_rows.size()); }
   uint64_t row_count() const { return chunk_row_start.empty() ? 0 : chunk_row_start.back(); }
@@ -195,9 +194,9 @@ Table* find_table(hyb_context* context, hyb_table_t handle);
 PosList* find_pos_list(hyb_context* context, hyb_pos_list_t handle);
 // Make the table's device descriptor arrays current (call with context->mutex held).
 int sync_table_descriptors(hyb_context* context, Table* table);
-// Device prefix array: tiles of `tile_rows` rows never straddle a chunk; entry c = number of tiles before chunk c.
-int get_tile_starts(hyb_context* context, Table* table, uint32_t tile_rows, const uint32_t** out_device,
-                    uint32_t* out_tile_count);
+// Device tile map: tiles of `tile_rows` rows never straddle a chunk; entry t = {chunk, first row | last-in-chunk << 31}.
+int get_tile_map(hyb_context* context, Table* table, uint32_t tile_rows, const uint2** out_device,
+                 uint32_t* out_tile_count);
 // Stream-ordered scratch/result memory.
 int device_alloc(hyb_context* context, size_t bytes, void** out);
 void device_free(hyb_context* context, void* ptr);

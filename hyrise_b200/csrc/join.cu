@@ -1,21 +1,938 @@
-// JoinHash on the device (placeholder until the kernels land in this round).
+// JoinHash on the device: equi-join on one int32/int64 key column per side.
+//
+// Replaces JoinHashImpl::_on_execute (src/lib/operators/join_hash.cpp:270-572) and its steps materialize_input /
+// partition_by_radix / build / probe / probe_semi_anti (src/lib/operators/join_hash/join_hash_steps.hpp:274-922).
+// The reference radix-partitions both inputs so that every partition's hash table fits a CPU L2; that buys nothing on a
+// GPU whose L2 is 126 MB, so the device path keeps ONE hash table for the whole build side and never materialises
+// {RowID, value} tuples. What the reference's partitioning does fix is the ORDER of the output — pairs come out grouped
+// by hash(key) & (2^radix_bits - 1) (std::hash<int> is the identity), inside a partition in probe-row order, for one
+// probe row in build-row order — and that order is reproduced exactly by ranking the matches instead of moving tuples:
+//
+//   join_build_kernel      every build row inserts {key, build position} into a bucketised open-addressing table
+//                          (32-byte buckets of four {key:32, value:32} slots; bucket = mix(key >> 2), so four consecutive
+//                          keys — the TPC-H orderkey pattern — share one sector). Duplicate keys keep the smallest
+//                          position and raise a flag; if it is raised the CSR of positions per key is built (count,
+//                          scan, fill, sort) so matches can be emitted in build-row order (PosHashTable, :97-236).
+//   join_probe_count_kernel  per 4096-position tile of the probe side: decode keys, look them up, remember the match
+//                          (4 bytes per probe row) and add the emitted-row counts to a per-(partition, tile) histogram.
+//   exclusive scan         over the histogram laid out partition-major: the start of every (partition, tile) run.
+//   join_probe_write_kernel  stable multi-split: each tile ranks its rows per partition (warp match_any + shared
+//                          counters) and writes (build RowID, probe RowID) pairs straight to their final position.
+//
+// Semi / Anti modes emit probe RowIDs only (probe_semi_anti); Left/Right emit NULL_ROW_ID partners for unmatched or
+// NULL probe keys (probe<keep_null_values = true>). NULL build keys are never inserted (join_hash.cpp:271-286).
+#include <algorithm>
+#include <cmath>
+
+#include "device_utils.cuh"
 #include "internal.hpp"
+
+namespace hyb {
+
+constexpr int kJoinThreads = 256;
+constexpr int kJoinWarps = kJoinThreads / 32;
+constexpr int kJoinTileRows = 4096;
+constexpr int kJoinRowsPerWarp = kJoinTileRows / kJoinWarps;  // 512 contiguous positions per warp
+constexpr uint32_t kNoMatch = 0xFFFFFFFFu;
+constexpr unsigned long long kEmptySlot = ~0ull;
+constexpr int kMaxPartitions = 256;
+
+struct KeySource {
+  const DevSegment* segments;        // key column descriptors, one per chunk
+  const uint2* tile_map;             // unfiltered input: per tile {chunk, row0 | last << 31}
+  const hyb_row_id* filter;          // filtered input: flat pos list (then tile_map == nullptr)
+  const unsigned long long* chunk_row_start;  // chunk_count + 1 (unfiltered)
+  unsigned long long position_count;
+  uint32_t tile_count;
+  uint32_t chunk_count;
+  uint32_t uniform_chunk_rows;       // > 0: all chunks but the last have this many rows
+};
+
+struct KeyAt {
+  long long key;
+  bool valid;
+  bool is_null;
+  hyb_row_id row_id;
+  unsigned long long position;
+};
+
+// Value at one position of an integer key column. NULL positions yield what the reference iterators yield: the stored
+// value for ValueSegments, minimum + offset for FrameOfReference, T{} for dictionaries (dictionary_segment_iterable.hpp
+// :116, frame_of_reference_segment_iterable.hpp:131-139) — it decides the partition a NULL probe row is emitted in.
+__device__ __forceinline__ long long decode_int_key(const DevSegment& segment, uint32_t row, bool& is_null) {
+  switch (segment.encoding) {
+    case HYB_ENC_UNENCODED:
+      is_null = segment.nulls && segment.nulls[row];
+      return segment.data_type == HYB_TYPE_INT32 ? static_cast<long long>(__ldg(static_cast<const int32_t*>(segment.values) + row))
+                                                 : __ldg(static_cast<const long long*>(segment.values) + row);
+    case HYB_ENC_DICTIONARY: {
+      const uint32_t value_id = load_code1(segment.av, segment.vector_type, segment.bit_width, row);
+      is_null = value_id >= segment.dict_size;
+      if (is_null) return 0;
+      return segment.data_type == HYB_TYPE_INT32
+                 ? static_cast<long long>(__ldg(static_cast<const int32_t*>(segment.values) + value_id))
+                 : __ldg(static_cast<const long long*>(segment.values) + value_id);
+    }
+    default: {
+      is_null = segment.nulls && segment.nulls[row];
+      const uint32_t code = load_code1(segment.av, segment.vector_type, segment.bit_width, row);
+      const int32_t minimum = __ldg(static_cast<const int32_t*>(segment.values) + row / HYB_FOR_BLOCK_SIZE);
+      return static_cast<long long>(static_cast<int32_t>(static_cast<uint32_t>(minimum) + code));
+    }
+  }
+}
+
+__device__ __forceinline__ KeyAt key_at(const KeySource& source, uint32_t tile, uint32_t index_in_tile) {
+  KeyAt result{};
+  if (source.tile_map) {
+    const uint2 info = __ldg(source.tile_map + tile);
+    const uint32_t chunk = info.x;
+    const uint32_t row = (info.y & 0x7FFFFFFFu) + index_in_tile;
+    const DevSegment& segment = source.segments[chunk];
+    result.valid = row < segment.row_count;
+    if (result.valid) {
+      result.key = decode_int_key(segment, row, result.is_null);
+      result.row_id = hyb_row_id{chunk, row};
+      result.position = __ldg(source.chunk_row_start + chunk) + row;
+    }
+  } else {
+    const unsigned long long position = static_cast<unsigned long long>(tile) * kJoinTileRows + index_in_tile;
+    result.valid = position < source.position_count;
+    if (result.valid) {
+      result.row_id = source.filter[position];
+      result.key = decode_int_key(source.segments[result.row_id.chunk_id], result.row_id.chunk_offset, result.is_null);
+      result.position = position;
+    }
+  }
+  return result;
+}
+
+__device__ __forceinline__ hyb_row_id position_to_row_id(const KeySource& source, unsigned long long position) {
+  if (source.filter) return source.filter[position];
+  if (source.uniform_chunk_rows) {
+    const uint32_t chunk = static_cast<uint32_t>(position / source.uniform_chunk_rows);
+    return hyb_row_id{chunk, static_cast<uint32_t>(position - static_cast<unsigned long long>(chunk) * source.uniform_chunk_rows)};
+  }
+  uint32_t lo = 0, hi = source.chunk_count;  // chunk_row_start[lo] <= position < chunk_row_start[hi]
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(source.chunk_row_start + mid) <= position) {
+      lo = mid;
+    } else {
+      hi = mid;
+    }
+  }
+  return hyb_row_id{lo, static_cast<uint32_t>(position - __ldg(source.chunk_row_start + lo))};
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Hash table: buckets of four 64-bit slots {key (low 32 bits of the int64 key... see below), value}.
+// Keys are compared as 32-bit patterns when both columns are int32 (kWide == false). For int64 keys (kWide == true) a
+// slot holds the low 32 key bits and the value indexes `wide_keys`, where the full key is verified.
+// ---------------------------------------------------------------------------------------------------------------------
+struct HashTable {
+  unsigned long long* slots;      // bucket_count * 4
+  uint32_t bucket_mask;           // bucket_count - 1 (power of two)
+  const long long* wide_keys;     // per build position (int64 joins only), else nullptr
+};
+
+__device__ __forceinline__ uint32_t mix32(uint32_t h) {
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
+}
+
+__device__ __forceinline__ uint32_t bucket_of(long long key, uint32_t mask) {
+  const unsigned long long bits = static_cast<unsigned long long>(key);
+  return mix32(static_cast<uint32_t>(bits >> 2) ^ static_cast<uint32_t>(bits >> 34) * 0x9E3779B1u) & mask;
+}
+
+__device__ __forceinline__ unsigned long long pack_slot(uint32_t key_bits, uint32_t value) {
+  return (static_cast<unsigned long long>(value) << 32) | key_bits;
+}
+
+// Returns the slot index holding `key`, or kNoMatch. A bucket with a free slot ends the search (no deletions).
+__device__ __forceinline__ uint32_t table_find(const HashTable& table, long long key) {
+  const uint32_t key_bits = static_cast<uint32_t>(key);
+  uint32_t bucket = bucket_of(key, table.bucket_mask);
+  while (true) {
+    const ulonglong2* base = reinterpret_cast<const ulonglong2*>(table.slots + static_cast<size_t>(bucket) * 4);
+    const ulonglong2 a = __ldg(base);
+    const ulonglong2 b = __ldg(base + 1);
+    const unsigned long long slots[4] = {a.x, a.y, b.x, b.y};
+    bool has_empty = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (slots[j] == kEmptySlot) {
+        has_empty = true;
+      } else if (static_cast<uint32_t>(slots[j]) == key_bits) {
+        if (!table.wide_keys || table.wide_keys[static_cast<uint32_t>(slots[j] >> 32)] == key) return bucket * 4 + j;
+      }
+    }
+    if (has_empty) return kNoMatch;
+    bucket = (bucket + 1) & table.bucket_mask;
+  }
+}
+
+struct BuildParams {
+  KeySource source;
+  HashTable table;
+  long long* wide_keys_out;        // int64 joins: full key per build position
+  uint32_t* flags;                 // [0] duplicate keys seen, [1] NULL keys seen, [2] inserted rows
+};
+
+__global__ void __launch_bounds__(kJoinThreads) join_build_kernel(const BuildParams params) {
+  for (uint32_t tile = blockIdx.x; tile < params.source.tile_count; tile += gridDim.x) {
+    for (uint32_t index = threadIdx.x; index < kJoinTileRows; index += kJoinThreads) {
+      const KeyAt row = key_at(params.source, tile, index);
+      if (!row.valid) continue;
+      if (row.is_null) {
+        params.flags[1] = 1;
+        continue;
+      }
+      const uint32_t value = static_cast<uint32_t>(row.position);
+      if (params.wide_keys_out) params.wide_keys_out[value] = row.key;
+      const uint32_t key_bits = static_cast<uint32_t>(row.key);
+      const unsigned long long desired = pack_slot(key_bits, value);
+      uint32_t bucket = bucket_of(row.key, params.table.bucket_mask);
+      bool done = false;
+      while (!done) {
+        unsigned long long* slots = params.table.slots + static_cast<size_t>(bucket) * 4;
+        const uint32_t start = static_cast<uint32_t>(row.key) & 3u;
+#pragma unroll
+        for (int j = 0; j < 4 && !done; ++j) {
+          unsigned long long* slot = slots + ((start + j) & 3u);
+          unsigned long long current = *reinterpret_cast<volatile unsigned long long*>(slot);
+          if (current == kEmptySlot) {
+            current = atomicCAS(slot, kEmptySlot, desired);
+            if (current == kEmptySlot) {
+              done = true;
+              break;
+            }
+          }
+          if (static_cast<uint32_t>(current) == key_bits) {
+            bool same = true;
+            if (params.wide_keys_out) {
+              // The owner of the slot publishes its full key before inserting; positions are unique, so once the slot is
+              // visible wide_keys_out[owner] is either written or about to be: spin until it is.
+              const uint32_t owner = static_cast<uint32_t>(current >> 32);
+              same = *reinterpret_cast<volatile long long*>(params.wide_keys_out + owner) == row.key;
+            }
+            if (same) {
+              // Equal key already present: keep the smallest build position in the slot (deterministic) and flag it.
+              atomicMin(reinterpret_cast<uint32_t*>(slot) + 1, value);
+              params.flags[0] = 1;
+              done = true;
+              break;
+            }
+          }
+        }
+        bucket = (bucket + 1) & params.table.bucket_mask;
+      }
+    }
+  }
+}
+
+// ---- duplicate build keys: CSR of build positions per slot ----------------------------------------------------------
+__global__ void join_count_duplicates_kernel(const KeySource source, const HashTable table, uint32_t* __restrict__ counts) {
+  for (uint32_t tile = blockIdx.x; tile < source.tile_count; tile += gridDim.x) {
+    for (uint32_t index = threadIdx.x; index < kJoinTileRows; index += kJoinThreads) {
+      const KeyAt row = key_at(source, tile, index);
+      if (!row.valid || row.is_null) continue;
+      const uint32_t slot = table_find(table, row.key);
+      if (slot != kNoMatch) atomicAdd(counts + slot, 1u);
+    }
+  }
+}
+
+__global__ void join_fill_positions_kernel(const KeySource source, const HashTable table,
+                                           const unsigned long long* __restrict__ offsets, uint32_t* __restrict__ cursors,
+                                           uint32_t* __restrict__ positions) {
+  for (uint32_t tile = blockIdx.x; tile < source.tile_count; tile += gridDim.x) {
+    for (uint32_t index = threadIdx.x; index < kJoinTileRows; index += kJoinThreads) {
+      const KeyAt row = key_at(source, tile, index);
+      if (!row.valid || row.is_null) continue;
+      const uint32_t slot = table_find(table, row.key);
+      if (slot == kNoMatch) continue;
+      const uint32_t at = atomicAdd(cursors + slot, 1u);
+      positions[offsets[slot] + at] = static_cast<uint32_t>(row.position);
+    }
+  }
+}
+
+// Build-row order inside a key's position list (insertion order of PosHashTable::emplace): heap sort, one thread per key.
+__global__ void join_sort_positions_kernel(const uint32_t* __restrict__ counts, const unsigned long long* __restrict__ offsets,
+                                           uint32_t slot_count, uint32_t* __restrict__ positions) {
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= slot_count) return;
+  const uint32_t n = counts[slot];
+  if (n < 2) return;
+  uint32_t* a = positions + offsets[slot];
+  const auto sift_down = [&](uint32_t start, uint32_t end) {
+    uint32_t root = start;
+    while (2 * root + 1 < end) {
+      uint32_t child = 2 * root + 1;
+      if (child + 1 < end && a[child] < a[child + 1]) ++child;
+      if (a[root] >= a[child]) return;
+      const uint32_t t = a[root];
+      a[root] = a[child];
+      a[child] = t;
+      root = child;
+    }
+  };
+  for (uint32_t start = n / 2; start-- > 0;) sift_down(start, n);
+  for (uint32_t end = n; end-- > 1;) {
+    const uint32_t t = a[0];
+    a[0] = a[end];
+    a[end] = t;
+    sift_down(0, end);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Generic single-pass exclusive scan uint32 -> uint64 (decoupled look-back), used for the (partition, tile) histogram and
+// the duplicate-key CSR.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kJoinThreads * kScanItems;
+
+__global__ void __launch_bounds__(kJoinThreads) exclusive_scan_kernel(const uint32_t* __restrict__ in,
+                                                                      unsigned long long* __restrict__ out,
+                                                                      unsigned long long count, unsigned long long* status,
+                                                                      uint32_t* ticket, unsigned long long* total_out) {
+  __shared__ unsigned long long s_warp[kJoinWarps];
+  __shared__ unsigned long long s_base;
+  __shared__ uint32_t s_tile;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t tile_count = static_cast<uint32_t>((count + kScanTile - 1) / kScanTile);
+  while (true) {
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    if (tile >= tile_count) return;
+    const unsigned long long first = static_cast<unsigned long long>(tile) * kScanTile + threadIdx.x * kScanItems;
+    uint32_t items[kScanItems];
+    unsigned long long sum = 0;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+      items[j] = first + j < count ? in[first + j] : 0u;
+      sum += items[j];
+    }
+    unsigned long long inclusive = sum;
+#pragma unroll
+    for (int delta = 1; delta < 32; delta <<= 1) {
+      const unsigned long long other = __shfl_up_sync(kFullMask, inclusive, delta);
+      if (lane >= static_cast<uint32_t>(delta)) inclusive += other;
+    }
+    if (lane == 31) s_warp[warp] = inclusive;
+    __syncthreads();
+    unsigned long long warp_base = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < kJoinWarps; ++w) {
+      if (w < static_cast<int>(warp)) warp_base += s_warp[w];
+      tile_total += s_warp[w];
+    }
+    if (warp == 0) {
+      const unsigned long long base = lookback_exclusive_prefix(status, tile, tile_total, lane);
+      if (lane == 0) {
+        s_base = base;
+        if (tile + 1 == tile_count && total_out) *total_out = base + tile_total;
+      }
+    }
+    __syncthreads();
+    unsigned long long running = s_base + warp_base + inclusive - sum;
+#pragma unroll
+    for (int j = 0; j < kScanItems; ++j) {
+      if (first + j < count) out[first + j] = running;
+      running += items[j];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Probe
+// ---------------------------------------------------------------------------------------------------------------------
+struct ProbeParams {
+  KeySource probe;
+  KeySource build;                        // for position -> RowID of the build side
+  HashTable table;
+  int32_t mode;
+  uint32_t partition_mask;                // 2^radix_bits - 1
+  uint32_t partition_count;
+  uint32_t unique_build;                  // 1: slot value is the build position; 0: use counts/offsets/positions
+  uint32_t build_is_empty;
+  const uint32_t* dup_counts;             // per slot
+  const unsigned long long* dup_offsets;  // per slot
+  const uint32_t* dup_positions;
+  uint32_t* matches;                      // per probe position: slot value / slot index / kNoMatch
+  uint32_t* emit_counts;                  // per probe position (only when !unique_build)
+  uint32_t* histogram;                    // [partition][tile]
+  const unsigned long long* run_starts;   // exclusive scan of histogram
+  hyb_row_id* out_build;
+  hyb_row_id* out_probe;
+};
+
+// How many output rows one probe row produces, and what to remember about its match.
+__device__ __forceinline__ uint32_t probe_one(const ProbeParams& params, const KeyAt& row, uint32_t& match) {
+  match = kNoMatch;
+  if (!row.valid) return 0;
+  const int32_t mode = params.mode;
+  if (row.is_null) {
+    // Inner/Semi discard NULL probe keys during materialisation; Left/Right and AntiNullAsFalse emit them;
+    // AntiNullAsTrue emits them only when the build table is empty (join_hash_steps.hpp:711-758, 848-913).
+    if (mode == HYB_JOIN_LEFT || mode == HYB_JOIN_RIGHT || mode == HYB_JOIN_ANTI_NULL_AS_FALSE) return 1;
+    if (mode == HYB_JOIN_ANTI_NULL_AS_TRUE) return params.build_is_empty ? 1 : 0;
+    return 0;
+  }
+  const uint32_t slot = params.table.slots ? table_find(params.table, row.key) : kNoMatch;
+  const bool found = slot != kNoMatch;
+  switch (mode) {
+    case HYB_JOIN_SEMI:
+      return found ? 1 : 0;
+    case HYB_JOIN_ANTI_NULL_AS_TRUE:
+    case HYB_JOIN_ANTI_NULL_AS_FALSE:
+      return found ? 0 : 1;
+    default:
+      break;
+  }
+  if (!found) return (mode == HYB_JOIN_LEFT || mode == HYB_JOIN_RIGHT) ? 1 : 0;
+  if (params.unique_build) {
+    match = static_cast<uint32_t>(params.table.slots[slot] >> 32);
+    return 1;
+  }
+  match = slot;
+  return params.dup_counts[slot];
+}
+
+__device__ __forceinline__ uint32_t partition_of(const ProbeParams& params, const KeyAt& row) {
+  // hash(value) & mask with std::hash<int32/int64> = identity (join_hash_steps.hpp:345-395)
+  return static_cast<uint32_t>(static_cast<unsigned long long>(row.key)) & params.partition_mask;
+}
+
+__global__ void __launch_bounds__(kJoinThreads) join_probe_count_kernel(const ProbeParams params) {
+  __shared__ uint32_t s_histogram[kMaxPartitions];
+  for (uint32_t tile = blockIdx.x; tile < params.probe.tile_count; tile += gridDim.x) {
+    for (uint32_t p = threadIdx.x; p < params.partition_count; p += kJoinThreads) s_histogram[p] = 0;
+    __syncthreads();
+    for (uint32_t index = threadIdx.x; index < kJoinTileRows; index += kJoinThreads) {
+      const KeyAt row = key_at(params.probe, tile, index);
+      uint32_t match;
+      const uint32_t emit = probe_one(params, row, match);
+      if (row.valid) {
+        params.matches[row.position] = match;
+        if (!params.unique_build) params.emit_counts[row.position] = emit;
+      }
+      const uint32_t partition = row.valid ? partition_of(params, row) : 0;
+      // one shared-memory atomic per distinct partition in the warp
+      const uint32_t peers = __match_any_sync(kFullMask, partition);
+      uint32_t total = emit;
+      if (params.unique_build) {
+        total = __popc(__ballot_sync(kFullMask, emit != 0) & peers);
+      } else {
+        // sum over the peer group
+        uint32_t sum = 0;
+        uint32_t remaining = peers;
+        while (remaining) {
+          const int source_lane = __ffs(remaining) - 1;
+          sum += __shfl_sync(peers, emit, source_lane);
+          remaining &= remaining - 1;
+        }
+        total = sum;
+      }
+      const uint32_t lane = threadIdx.x & 31;
+      if (lane == static_cast<uint32_t>(__ffs(peers) - 1) && total) atomicAdd(&s_histogram[partition], total);
+    }
+    __syncthreads();
+    for (uint32_t p = threadIdx.x; p < params.partition_count; p += kJoinThreads) {
+      params.histogram[static_cast<size_t>(p) * params.probe.tile_count + tile] = s_histogram[p];
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kJoinThreads) join_probe_write_kernel(const ProbeParams params) {
+  __shared__ uint32_t s_warp_histogram[kJoinWarps][kMaxPartitions];
+  __shared__ unsigned long long s_start[kJoinWarps][kMaxPartitions];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lanes_below = (1u << lane) - 1u;
+  const bool emit_build = params.out_build != nullptr;
+
+  for (uint32_t tile = blockIdx.x; tile < params.probe.tile_count; tile += gridDim.x) {
+    for (uint32_t p = lane; p < params.partition_count; p += 32) s_warp_histogram[warp][p] = 0;
+    __syncwarp();
+    // pass 1: per-warp histogram of emitted rows (each warp owns kJoinRowsPerWarp contiguous positions)
+    for (uint32_t step = 0; step < kJoinRowsPerWarp / 32; ++step) {
+      const uint32_t index = warp * kJoinRowsPerWarp + step * 32 + lane;
+      const KeyAt row = key_at(params.probe, tile, index);
+      uint32_t emit = 0;
+      if (row.valid) {
+        emit = params.unique_build ? 0u : params.emit_counts[row.position];
+        if (params.unique_build) {
+          uint32_t match;
+          // re-derive from the stored match: emitted iff a match exists or the mode emits unmatched rows
+          match = params.matches[row.position];
+          const int32_t mode = params.mode;
+          if (mode == HYB_JOIN_INNER) {
+            emit = match != kNoMatch;
+          } else {
+            KeyAt copy = row;
+            uint32_t ignored;
+            emit = probe_one(params, copy, ignored);
+          }
+        }
+      }
+      const uint32_t partition = row.valid ? partition_of(params, row) : 0;
+      const uint32_t peers = __match_any_sync(kFullMask, partition);
+      uint32_t sum = 0;
+      uint32_t remaining = peers;
+      while (remaining) {
+        const int source_lane = __ffs(remaining) - 1;
+        sum += __shfl_sync(peers, emit, source_lane);
+        remaining &= remaining - 1;
+      }
+      if (lane == static_cast<uint32_t>(__ffs(peers) - 1) && sum) s_warp_histogram[warp][partition] += sum;
+      __syncwarp();
+    }
+    __syncthreads();
+    // start of every (warp, partition) run inside this tile's (partition, tile) run
+    for (uint32_t p = threadIdx.x; p < params.partition_count; p += kJoinThreads) {
+      unsigned long long running = params.run_starts[static_cast<size_t>(p) * params.probe.tile_count + tile];
+#pragma unroll
+      for (int w = 0; w < kJoinWarps; ++w) {
+        s_start[w][p] = running;
+        running += s_warp_histogram[w][p];
+      }
+    }
+    __syncthreads();
+    // pass 2: ranks and writes, in position order inside each warp
+    for (uint32_t step = 0; step < kJoinRowsPerWarp / 32; ++step) {
+      const uint32_t index = warp * kJoinRowsPerWarp + step * 32 + lane;
+      const KeyAt row = key_at(params.probe, tile, index);
+      uint32_t emit = 0, match = kNoMatch;
+      if (row.valid) {
+        match = params.matches[row.position];
+        if (params.unique_build) {
+          if (params.mode == HYB_JOIN_INNER) {
+            emit = match != kNoMatch;
+          } else {
+            uint32_t ignored;
+            emit = probe_one(params, row, ignored);
+          }
+        } else {
+          emit = params.emit_counts[row.position];
+        }
+      }
+      const uint32_t partition = row.valid ? partition_of(params, row) : 0;
+      const uint32_t peers = __match_any_sync(kFullMask, partition);
+      uint32_t before = 0, sum = 0;
+      uint32_t remaining = peers;
+      while (remaining) {
+        const int source_lane = __ffs(remaining) - 1;
+        const uint32_t value = __shfl_sync(peers, emit, source_lane);
+        if (static_cast<uint32_t>(source_lane) < lane) before += value;
+        sum += value;
+        remaining &= remaining - 1;
+      }
+      (void)lanes_below;
+      const unsigned long long base = s_start[warp][partition];
+      __syncwarp();
+      if (lane == static_cast<uint32_t>(__ffs(peers) - 1) && sum) s_start[warp][partition] = base + sum;
+      __syncwarp();
+      if (emit) {
+        unsigned long long at = base + before;
+        if (match == kNoMatch || !emit_build) {
+          // unmatched outer row (NULL partner) or a Semi/Anti row
+          if (emit_build) st_stream_v2(params.out_build + at, HYB_INVALID_CHUNK_ID, HYB_INVALID_CHUNK_OFFSET);
+          st_stream_v2(params.out_probe + at, row.row_id.chunk_id, row.row_id.chunk_offset);
+        } else if (params.unique_build) {
+          const hyb_row_id build_row = position_to_row_id(params.build, match);
+          st_stream_v2(params.out_build + at, build_row.chunk_id, build_row.chunk_offset);
+          st_stream_v2(params.out_probe + at, row.row_id.chunk_id, row.row_id.chunk_offset);
+        } else {
+          const unsigned long long first = params.dup_offsets[match];
+          for (uint32_t j = 0; j < emit; ++j) {
+            const hyb_row_id build_row = position_to_row_id(params.build, params.dup_positions[first + j]);
+            st_stream_v2(params.out_build + at + j, build_row.chunk_id, build_row.chunk_offset);
+            st_stream_v2(params.out_probe + at + j, row.row_id.chunk_id, row.row_id.chunk_offset);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void join_partition_offsets_kernel(const unsigned long long* __restrict__ run_starts,
+                                              const unsigned long long* __restrict__ total, uint32_t partition_count,
+                                              uint32_t tile_count, unsigned long long* __restrict__ out) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p > partition_count) return;
+  out[p] = (p == partition_count || tile_count == 0) ? *total : run_starts[static_cast<size_t>(p) * tile_count];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------------------------------
+// JoinHash::calculate_radix_bits (join_hash.cpp:70-114)
+static int32_t calculate_radix_bits(uint64_t build_side_size) {
+  constexpr double kL2CacheMaxUsable = 1'024'000 * 0.75;
+  const double complete_hash_map_size = static_cast<double>(build_side_size) * static_cast<double>(sizeof(uint32_t)) / 0.8;
+  const double cluster_count = std::max(1.0, complete_hash_map_size / kL2CacheMaxUsable);
+  return static_cast<int32_t>(std::min<size_t>(8, static_cast<size_t>(std::ceil(std::log2(cluster_count)))));
+}
+
+struct SideInfo {
+  Table* table = nullptr;
+  PosList* filter = nullptr;
+  KeySource source{};
+  int32_t data_type = 0;
+  uint64_t positions = 0;
+};
+
+static int prepare_side(hyb_context* context, const hyb_join_side* side, SideInfo* out) {
+  out->table = find_table(context, side->table);
+  HYB_CHECK(out->table, HYB_ERR_NOT_FOUND, "unknown table handle");
+  HYB_CHECK(side->column_id < out->table->column_count, HYB_ERR_INVALID, "join column out of range");
+  out->data_type = out->table->chunk_count() ? out->table->column_types[side->column_id] : HYB_TYPE_INT32;
+  HYB_CHECK(out->data_type == HYB_TYPE_INT32 || out->data_type == HYB_TYPE_INT64, HYB_ERR_UNSUPPORTED,
+            "JoinHash on the device supports int32/int64 key columns; other key types run on the CPU operator");
+  HYB_TRY(sync_table_descriptors(context, out->table));
+  KeySource& source = out->source;
+  const uint32_t chunk_count = out->table->chunk_count();
+  source.segments = out->table->d_segments + size_t{side->column_id} * chunk_count;
+  source.chunk_row_start = reinterpret_cast<const unsigned long long*>(out->table->d_chunk_row_start);
+  source.chunk_count = chunk_count;
+  source.uniform_chunk_rows = (out->table->uniform_chunks && chunk_count) ? out->table->chunk_rows[0] : 0;
+  if (side->filter) {
+    out->filter = find_pos_list(context, side->filter);
+    HYB_CHECK(out->filter, HYB_ERR_NOT_FOUND, "unknown filter handle");
+    HYB_CHECK(out->filter->table == side->table, HYB_ERR_INVALID, "filter belongs to a different table");
+    HYB_CUDA(cudaStreamSynchronize(context->stream));
+    uint64_t count = 0;
+    HYB_CUDA(cudaMemcpy(&count, out->filter->d_chunk_end + out->filter->chunk_count, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (count == ~uint64_t{0}) count = 0;
+    out->positions = count;
+    source.filter = out->filter->d_row_ids;
+    source.tile_map = nullptr;
+    source.tile_count = static_cast<uint32_t>((count + kJoinTileRows - 1) / kJoinTileRows);
+  } else {
+    out->positions = out->table->row_count();
+    HYB_TRY(get_tile_map(context, out->table, kJoinTileRows, &source.tile_map, &source.tile_count));
+  }
+  source.position_count = out->positions;
+  return HYB_OK;
+}
+
+static int run_exclusive_scan(hyb_context* context, const uint32_t* in, unsigned long long* out, uint64_t count,
+                              unsigned long long* total_out) {
+  const uint32_t tile_count = static_cast<uint32_t>((count + kScanTile - 1) / kScanTile);
+  if (tile_count == 0) {
+    if (total_out) HYB_CUDA(cudaMemsetAsync(total_out, 0, sizeof(unsigned long long), context->stream));
+    return HYB_OK;
+  }
+  void* status = nullptr;
+  HYB_TRY(device_alloc(context, sizeof(uint64_t) * (size_t{tile_count} + 1), &status));
+  HYB_CUDA(cudaMemsetAsync(status, 0, sizeof(uint64_t) * (size_t{tile_count} + 1), context->stream));
+  const uint32_t grid = std::min<uint32_t>(tile_count, context->sm_count * 4);
+  exclusive_scan_kernel<<<grid, kJoinThreads, 0, context->stream>>>(
+      in, out, count, static_cast<unsigned long long*>(status),
+      reinterpret_cast<uint32_t*>(static_cast<unsigned long long*>(status) + tile_count), total_out);
+  HYB_CUDA(cudaGetLastError());
+  device_free(context, status);
+  return HYB_OK;
+}
+
+}  // namespace hyb
+
 using namespace hyb;
+
 extern "C" {
-int hyb_join_hash(hyb_context*, const hyb_join_side*, const hyb_join_side*, int32_t, int32_t, hyb_join_result_t*) {
-  return fail(HYB_ERR_UNSUPPORTED, "hyb_join_hash: not implemented yet");
+
+int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const hyb_join_side* probe_side, int32_t mode,
+                  int32_t radix_bits, hyb_join_result_t* out_result) {
+  HYB_CHECK(context && build_side && probe_side && out_result, HYB_ERR_INVALID, "NULL argument");
+  *out_result = 0;
+  HYB_CHECK(mode == HYB_JOIN_INNER || mode == HYB_JOIN_LEFT || mode == HYB_JOIN_RIGHT || mode == HYB_JOIN_SEMI ||
+                mode == HYB_JOIN_ANTI_NULL_AS_TRUE || mode == HYB_JOIN_ANTI_NULL_AS_FALSE,
+            HYB_ERR_UNSUPPORTED, "JoinMode not supported by JoinHash");
+  DeviceGuard guard(context->device);
+  std::lock_guard<std::mutex> lock(context->mutex);
+  SideInfo build, probe;
+  HYB_TRY(prepare_side(context, build_side, &build));
+  HYB_TRY(prepare_side(context, probe_side, &probe));
+  HYB_CHECK(build.positions < 0xFFFFFFFFull && probe.positions < 0xFFFFFFFFull, HYB_ERR_UNSUPPORTED,
+            "more than 2^32 - 1 rows per join side");
+  if (radix_bits < 0) radix_bits = calculate_radix_bits(build.positions);
+  HYB_CHECK(radix_bits <= 8, HYB_ERR_INVALID, "radix_bits must be <= 8 (join_hash.cpp:113)");
+  const uint32_t partition_count = 1u << radix_bits;
+  const bool wide = build.data_type == HYB_TYPE_INT64 || probe.data_type == HYB_TYPE_INT64;
+  const bool semi_or_anti = mode == HYB_JOIN_SEMI || mode == HYB_JOIN_ANTI_NULL_AS_TRUE || mode == HYB_JOIN_ANTI_NULL_AS_FALSE;
+  cudaStream_t stream = context->stream;
+  uint32_t launches = 0;
+
+  timing_begin(context);
+
+  // ---- build -----------------------------------------------------------------------------------------------------
+  uint64_t bucket_count = 1;
+  while (bucket_count * 2 < build.positions) bucket_count <<= 1;  // >= positions / 2 buckets -> load factor <= 0.5
+  HYB_CHECK(bucket_count * 4 < 0xFFFFFFFFull, HYB_ERR_UNSUPPORTED, "build side too large for 32-bit slot indexes");
+  const uint64_t slot_count = bucket_count * 4;
+  void* slots = nullptr;
+  void* wide_keys = nullptr;
+  void* flags = nullptr;
+  HYB_TRY(device_alloc(context, sizeof(uint64_t) * slot_count, &slots));
+  HYB_CUDA(cudaMemsetAsync(slots, 0xFF, sizeof(uint64_t) * slot_count, stream));
+  HYB_TRY(device_alloc(context, sizeof(uint32_t) * 4, &flags));
+  HYB_CUDA(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * 4, stream));
+  if (wide) {
+    HYB_TRY(device_alloc(context, sizeof(long long) * std::max<uint64_t>(build.positions, 1), &wide_keys));
+    // 0x80.. pattern cannot equal a key whose low 32 bits matched a slot unless it is the key itself; positions that
+    // are never written (NULL keys) are never referenced by a slot.
+    HYB_CUDA(cudaMemsetAsync(wide_keys, 0x80, sizeof(long long) * std::max<uint64_t>(build.positions, 1), stream));
+  }
+  HashTable table{};
+  table.slots = static_cast<unsigned long long*>(slots);
+  table.bucket_mask = static_cast<uint32_t>(bucket_count - 1);
+  table.wide_keys = static_cast<const long long*>(wide_keys);
+  const uint32_t build_grid = std::max<uint32_t>(1, std::min<uint32_t>(build.source.tile_count, context->sm_count * 8));
+  if (build.source.tile_count) {
+    BuildParams build_params{};
+    build_params.source = build.source;
+    build_params.table = table;
+    build_params.wide_keys_out = static_cast<long long*>(wide_keys);
+    build_params.flags = static_cast<uint32_t*>(flags);
+    join_build_kernel<<<build_grid, kJoinThreads, 0, stream>>>(build_params);
+    HYB_CUDA(cudaGetLastError());
+    ++launches;
+  }
+  uint32_t host_flags[4] = {0, 0, 0, 0};
+  HYB_CUDA(cudaMemcpyAsync(host_flags, flags, sizeof(host_flags), cudaMemcpyDeviceToHost, stream));
+  HYB_CUDA(cudaStreamSynchronize(stream));
+  const bool has_duplicates = host_flags[0] != 0;
+  const bool build_has_nulls = host_flags[1] != 0;
+
+  void* dup_counts = nullptr;
+  void* dup_offsets = nullptr;
+  void* dup_positions = nullptr;
+  const bool need_positions = has_duplicates && !semi_or_anti;
+  if (need_positions) {
+    HYB_TRY(device_alloc(context, sizeof(uint32_t) * slot_count * 2, &dup_counts));  // counts | cursors
+    HYB_CUDA(cudaMemsetAsync(dup_counts, 0, sizeof(uint32_t) * slot_count * 2, stream));
+    HYB_TRY(device_alloc(context, sizeof(uint64_t) * slot_count, &dup_offsets));
+    HYB_TRY(device_alloc(context, sizeof(uint32_t) * std::max<uint64_t>(build.positions, 1), &dup_positions));
+    join_count_duplicates_kernel<<<build_grid, kJoinThreads, 0, stream>>>(build.source, table, static_cast<uint32_t*>(dup_counts));
+    HYB_CUDA(cudaGetLastError());
+    HYB_TRY(run_exclusive_scan(context, static_cast<uint32_t*>(dup_counts), static_cast<unsigned long long*>(dup_offsets),
+                               slot_count, nullptr));
+    join_fill_positions_kernel<<<build_grid, kJoinThreads, 0, stream>>>(
+        build.source, table, static_cast<unsigned long long*>(dup_offsets), static_cast<uint32_t*>(dup_counts) + slot_count,
+        static_cast<uint32_t*>(dup_positions));
+    HYB_CUDA(cudaGetLastError());
+    join_sort_positions_kernel<<<static_cast<uint32_t>((slot_count + 255) / 256), 256, 0, stream>>>(
+        static_cast<uint32_t*>(dup_counts), static_cast<unsigned long long*>(dup_offsets), static_cast<uint32_t>(slot_count),
+        static_cast<uint32_t*>(dup_positions));
+    HYB_CUDA(cudaGetLastError());
+    launches += 4;
+  }
+
+  // ---- probe -----------------------------------------------------------------------------------------------------
+  auto result = std::make_unique<JoinResult>();
+  result->mode = mode;
+  result->radix_bits = radix_bits;
+  result->partition_count = partition_count;
+  result->stream = stream;
+  void* partition_offsets = nullptr;
+  HYB_TRY(device_alloc(context, sizeof(uint64_t) * (size_t{partition_count} + 2), &partition_offsets));
+  result->d_partition_offsets = static_cast<uint64_t*>(partition_offsets);
+  unsigned long long* total_slot = reinterpret_cast<unsigned long long*>(result->d_partition_offsets) + partition_count + 1;
+
+  // AntiNullAsTrue: a NULL on the build side means no tuple can be emitted (join_hash.cpp:471-483).
+  const bool early_out = mode == HYB_JOIN_ANTI_NULL_AS_TRUE && build_has_nulls;
+  const uint32_t probe_tiles = early_out ? 0 : probe.source.tile_count;
+  uint64_t output_capacity = 0;
+
+  if (probe_tiles == 0) {
+    HYB_CUDA(cudaMemsetAsync(partition_offsets, 0, sizeof(uint64_t) * (size_t{partition_count} + 2), stream));
+    timing_kernel_begin(context);
+    timing_kernel_end(context);
+  } else {
+    void* matches = nullptr;
+    void* emit_counts = nullptr;
+    void* histogram = nullptr;
+    void* run_starts = nullptr;
+    const size_t histogram_entries = size_t{partition_count} * probe_tiles;
+    HYB_TRY(device_alloc(context, sizeof(uint32_t) * std::max<uint64_t>(probe.positions, 1), &matches));
+    if (need_positions) HYB_TRY(device_alloc(context, sizeof(uint32_t) * std::max<uint64_t>(probe.positions, 1), &emit_counts));
+    HYB_TRY(device_alloc(context, sizeof(uint32_t) * histogram_entries, &histogram));
+    HYB_TRY(device_alloc(context, sizeof(uint64_t) * histogram_entries, &run_starts));
+
+    ProbeParams params{};
+    params.probe = probe.source;
+    params.build = build.source;
+    params.table = table;
+    if (build.source.tile_count == 0) params.table.slots = nullptr;
+    params.mode = mode;
+    params.partition_mask = partition_count - 1;
+    params.partition_count = partition_count;
+    params.unique_build = need_positions ? 0 : 1;
+    params.build_is_empty = build.positions == 0;
+    params.dup_counts = static_cast<const uint32_t*>(dup_counts);
+    params.dup_offsets = static_cast<const unsigned long long*>(dup_offsets);
+    params.dup_positions = static_cast<const uint32_t*>(dup_positions);
+    params.matches = static_cast<uint32_t*>(matches);
+    params.emit_counts = static_cast<uint32_t*>(emit_counts);
+    params.histogram = static_cast<uint32_t*>(histogram);
+    params.run_starts = static_cast<const unsigned long long*>(run_starts);
+
+    const uint32_t probe_grid = std::min<uint32_t>(probe_tiles, context->sm_count * 6);
+    timing_kernel_begin(context);
+    join_probe_count_kernel<<<probe_grid, kJoinThreads, 0, stream>>>(params);
+    HYB_CUDA(cudaGetLastError());
+    HYB_TRY(run_exclusive_scan(context, static_cast<uint32_t*>(histogram), static_cast<unsigned long long*>(run_starts),
+                               histogram_entries, total_slot));
+    // The output size is data dependent: read it back to size the PosLists exactly.
+    uint64_t total = 0;
+    HYB_CUDA(cudaMemcpyAsync(&total, total_slot, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+    HYB_CUDA(cudaStreamSynchronize(stream));
+    output_capacity = total;
+    void* out_probe = nullptr;
+    void* out_build = nullptr;
+    HYB_TRY(device_alloc(context, sizeof(hyb_row_id) * std::max<uint64_t>(total, 1), &out_probe));
+    if (!semi_or_anti) HYB_TRY(device_alloc(context, sizeof(hyb_row_id) * std::max<uint64_t>(total, 1), &out_build));
+    result->d_probe = static_cast<hyb_row_id*>(out_probe);
+    result->d_build = static_cast<hyb_row_id*>(out_build);
+    params.out_probe = result->d_probe;
+    params.out_build = result->d_build;
+    join_probe_write_kernel<<<probe_grid, kJoinThreads, 0, stream>>>(params);
+    HYB_CUDA(cudaGetLastError());
+    timing_kernel_end(context);
+    join_partition_offsets_kernel<<<(partition_count + 1 + 127) / 128, 128, 0, stream>>>(
+        static_cast<const unsigned long long*>(run_starts), total_slot, partition_count, probe_tiles,
+        reinterpret_cast<unsigned long long*>(result->d_partition_offsets));
+    HYB_CUDA(cudaGetLastError());
+    launches += 4;
+    device_free(context, matches);
+    device_free(context, emit_counts);
+    device_free(context, histogram);
+    device_free(context, run_starts);
+  }
+  result->capacity = output_capacity;
+  device_free(context, slots);
+  device_free(context, wide_keys);
+  device_free(context, flags);
+  device_free(context, dup_counts);
+  device_free(context, dup_offsets);
+  device_free(context, dup_positions);
+
+  // Compulsory traffic: each key once + each output RowID once.
+  const auto key_bytes = [](const SideInfo& side) -> uint64_t {
+    if (side.filter) return side.positions * (sizeof(hyb_row_id) + data_type_size(side.data_type));
+    uint64_t bytes = 0;
+    const uint32_t column = static_cast<uint32_t>((side.source.segments - side.table->d_segments) / std::max<uint32_t>(side.table->chunk_count(), 1));
+    for (uint32_t chunk = 0; chunk < side.table->chunk_count(); ++chunk) {
+      const auto& segment = side.table->segments[size_t{chunk} * side.table->column_count + column];
+      bytes += segment.encoding == HYB_ENC_UNENCODED ? data_type_size(segment.data_type) * segment.row_count
+                                                     : vector_bytes(segment.vector_type, segment.bit_width, segment.row_count);
+      if (segment.encoding == HYB_ENC_FRAME_OF_REFERENCE) {
+        bytes += sizeof(int32_t) * ((segment.row_count + HYB_FOR_BLOCK_SIZE - 1) / HYB_FOR_BLOCK_SIZE);
+      }
+    }
+    return bytes;
+  };
+  timing_end(context, launches, key_bytes(build) + key_bytes(probe), probe.positions, 0);
+  timing_output_count(context, reinterpret_cast<const uint64_t*>(total_slot), semi_or_anti ? 8 : 16);
+
+  const auto handle = context->next_handle++;
+  context->join_results.emplace(handle, std::move(result));
+  *out_result = handle;
+  return HYB_OK;
 }
-int hyb_join_result_info(hyb_context*, hyb_join_result_t, uint64_t*, uint32_t*, int32_t*) {
-  return fail(HYB_ERR_NOT_FOUND, "unknown join result");
+
+static JoinResult* find_join_result(hyb_context* context, hyb_join_result_t handle) {
+  auto it = context->join_results.find(handle);
+  return it == context->join_results.end() ? nullptr : it->second.get();
 }
-int hyb_join_result_partition_offsets(hyb_context*, hyb_join_result_t, uint64_t*) {
-  return fail(HYB_ERR_NOT_FOUND, "unknown join result");
+
+static int ensure_join_host(hyb_context* context, JoinResult* result) {
+  if (result->host_valid) return HYB_OK;
+  result->h_partition_offsets.assign(size_t{result->partition_count} + 1, 0);
+  HYB_CUDA(cudaMemcpyAsync(result->h_partition_offsets.data(), result->d_partition_offsets,
+                           sizeof(uint64_t) * result->h_partition_offsets.size(), cudaMemcpyDeviceToHost, context->stream));
+  HYB_CUDA(cudaStreamSynchronize(context->stream));
+  result->host_valid = true;
+  return HYB_OK;
 }
-int hyb_join_result_copy(hyb_context*, hyb_join_result_t, uint64_t, uint64_t, hyb_row_id*, hyb_row_id*) {
-  return fail(HYB_ERR_NOT_FOUND, "unknown join result");
+
+int hyb_join_result_info(hyb_context* context, hyb_join_result_t handle, uint64_t* out_pair_count,
+                         uint32_t* out_partition_count, int32_t* out_radix_bits) {
+  HYB_CHECK(context, HYB_ERR_INVALID, "context is NULL");
+  DeviceGuard guard(context->device);
+  std::lock_guard<std::mutex> lock(context->mutex);
+  auto* result = find_join_result(context, handle);
+  HYB_CHECK(result, HYB_ERR_NOT_FOUND, "unknown join result handle");
+  HYB_TRY(ensure_join_host(context, result));
+  if (out_pair_count) *out_pair_count = result->h_partition_offsets.back();
+  if (out_partition_count) *out_partition_count = result->partition_count;
+  if (out_radix_bits) *out_radix_bits = result->radix_bits;
+  return HYB_OK;
 }
-int hyb_join_result_free(hyb_context*, hyb_join_result_t) { return fail(HYB_ERR_NOT_FOUND, "unknown join result"); }
-int hyb_join_result_device_ptrs(hyb_context*, hyb_join_result_t, void**, void**) {
-  return fail(HYB_ERR_NOT_FOUND, "unknown join result");
+
+int hyb_join_result_partition_offsets(hyb_context* context, hyb_join_result_t handle, uint64_t* out_offsets) {
+  HYB_CHECK(context && out_offsets, HYB_ERR_INVALID, "NULL argument");
+  DeviceGuard guard(context->device);
+  std::lock_guard<std::mutex> lock(context->mutex);
+  auto* result = find_join_result(context, handle);
+  HYB_CHECK(result, HYB_ERR_NOT_FOUND, "unknown join result handle");
+  HYB_TRY(ensure_join_host(context, result));
+  std::copy(result->h_partition_offsets.begin(), result->h_partition_offsets.end(), out_offsets);
+  return HYB_OK;
 }
+
+int hyb_join_result_copy(hyb_context* context, hyb_join_result_t handle, uint64_t begin, uint64_t count,
+                         hyb_row_id* out_build_row_ids, hyb_row_id* out_probe_row_ids) {
+  HYB_CHECK(context, HYB_ERR_INVALID, "context is NULL");
+  DeviceGuard guard(context->device);
+  std::lock_guard<std::mutex> lock(context->mutex);
+  auto* result = find_join_result(context, handle);
+  HYB_CHECK(result, HYB_ERR_NOT_FOUND, "unknown join result handle");
+  HYB_TRY(ensure_join_host(context, result));
+  HYB_CHECK(begin + count <= result->h_partition_offsets.back(), HYB_ERR_INVALID, "range exceeds the join result");
+  if (count == 0) return HYB_OK;
+  if (out_build_row_ids) {
+    HYB_CHECK(result->d_build, HYB_ERR_INVALID, "Semi/Anti joins have no build-side PosList");
+    HYB_CUDA(cudaMemcpyAsync(out_build_row_ids, result->d_build + begin, sizeof(hyb_row_id) * count, cudaMemcpyDeviceToHost,
+                             context->stream));
+  }
+  if (out_probe_row_ids) {
+    HYB_CUDA(cudaMemcpyAsync(out_probe_row_ids, result->d_probe + begin, sizeof(hyb_row_id) * count, cudaMemcpyDeviceToHost,
+                             context->stream));
+  }
+  HYB_CUDA(cudaStreamSynchronize(context->stream));
+  return HYB_OK;
 }
+
+int hyb_join_result_device_ptrs(hyb_context* context, hyb_join_result_t handle, void** out_build_row_ids,
+                                void** out_probe_row_ids) {
+  HYB_CHECK(context, HYB_ERR_INVALID, "context is NULL");
+  std::lock_guard<std::mutex> lock(context->mutex);
+  auto* result = find_join_result(context, handle);
+  HYB_CHECK(result, HYB_ERR_NOT_FOUND, "unknown join result handle");
+  if (out_build_row_ids) *out_build_row_ids = result->d_build;
+  if (out_probe_row_ids) *out_probe_row_ids = result->d_probe;
+  return HYB_OK;
+}
+
+int hyb_join_result_free(hyb_context* context, hyb_join_result_t handle) {
+  HYB_CHECK(context, HYB_ERR_INVALID, "context is NULL");
+  DeviceGuard guard(context->device);
+  std::lock_guard<std::mutex> lock(context->mutex);
+  auto it = context->join_results.find(handle);
+  HYB_CHECK(it != context->join_results.end(), HYB_ERR_NOT_FOUND, "unknown join result handle");
+  context->join_results.erase(it);
+  return HYB_OK;
+}
+
+}  // extern "C"

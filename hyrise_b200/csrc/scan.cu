@@ -29,9 +29,10 @@ namespace hyb {
 
 constexpr int kScanThreads = 256;
 constexpr int kScanWarps = kScanThreads / 32;
-constexpr int kScanIterations = 2;                       // 8 rows per thread per iteration
+constexpr int kScanIterations = 4;                       // 8 rows per thread per iteration
 constexpr int kScanWarpRows = 32 * 8 * kScanIterations;  // rows owned by one warp in a tile (contiguous)
-constexpr int kScanTileRows = kScanWarps * kScanWarpRows;  // 4096
+constexpr int kScanTileRows = kScanWarps * kScanWarpRows;  // 8192
+constexpr int kFilteredTileRows = 4096;                  // position-filtered scan: inputs per tile
 
 struct ScanPredicateDevice {
   int32_t condition;
@@ -317,7 +318,7 @@ __global__ void scan_prepare_kernel(const DevSegment* __restrict__ segments, uin
 struct ScanParams {
   const DevSegment* segments;     // descriptors of the scanned column, one per chunk
   const ChunkTest* tests;         // per chunk
-  const uint32_t* tile_starts;    // chunk_count + 1
+  const uint2* tile_map;          // per tile: {chunk, first row | last-tile-of-chunk << 31}
   uint32_t chunk_count;
   uint32_t tile_count;
   unsigned long long* tile_status;  // tile_count, zero-initialised
@@ -326,47 +327,71 @@ struct ScanParams {
   unsigned long long* chunk_end;  // [chunk] = inclusive prefix after the chunk's last tile; [chunk_count] = total
 };
 
+// Per-tile schedule, all of it latency: (1) ticket + tile map entry — prefetched one tile ahead by thread 0;
+// (2) column loads, 4 x 128 bit in flight per thread; (3) barrier A: warp totals; (4) warp 0: look-back for the global
+// offset, other warps: stage matches in shared memory; (5) barrier B; (6) coalesced RowID stores. Two barriers per
+// 8192-row tile; shared-memory reuse across iterations is ordered by those same two barriers (see comments inline).
 __global__ void __launch_bounds__(kScanThreads) scan_kernel(const ScanParams params) {
-  __shared__ uint32_t s_offsets[kScanTileRows];
+  __shared__ uint16_t s_offsets[kScanTileRows];  // tile-relative offsets of the matches, in row order
   __shared__ uint32_t s_warp_totals[kScanWarps];
-  __shared__ uint32_t s_tile;
-  __shared__ uint32_t s_chunk;
+  __shared__ uint32_t s_next[2][3];              // double-buffered {tile, chunk, row0|last}
   __shared__ unsigned long long s_base;
 
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp = threadIdx.x >> 5;
 
-  while (true) {
-    if (threadIdx.x == 0) {
-      const uint32_t tile = atomicAdd(params.ticket, 1u);
-      s_tile = tile;
-      if (tile < params.tile_count) s_chunk = find_owner(params.tile_starts, params.chunk_count, tile);
-    }
-    __syncthreads();  // also protects s_offsets / s_base of the previous tile
-    const uint32_t tile = s_tile;
+  if (threadIdx.x == 0) {
+    const uint32_t tile = atomicAdd(params.ticket, 1u);
+    const uint2 info = tile < params.tile_count ? __ldg(params.tile_map + tile) : make_uint2(0, 0);
+    s_next[0][0] = tile;
+    s_next[0][1] = info.x;
+    s_next[0][2] = info.y;
+  }
+  __syncthreads();
+
+  for (uint32_t iteration = 0;; ++iteration) {
+    const uint32_t slot = iteration & 1;
+    const uint32_t tile = s_next[slot][0];
     if (tile >= params.tile_count) return;
-    const uint32_t chunk = s_chunk;
+    const uint32_t chunk = s_next[slot][1];
+    const uint32_t tile_row0 = s_next[slot][2] & 0x7FFFFFFFu;
+    const bool last_tile_of_chunk = (s_next[slot][2] >> 31) != 0;
+
+    // Claim the next tile now; the answer is only needed after barrier B.
+    uint32_t next_tile = 0;
+    uint2 next_info = make_uint2(0, 0);
+    if (threadIdx.x == 0) {
+      next_tile = atomicAdd(params.ticket, 1u);
+      if (next_tile < params.tile_count) next_info = __ldg(params.tile_map + next_tile);
+    }
+
     const DevSegment segment = params.segments[chunk];
     const ChunkTest test = params.tests[chunk];
-    const uint32_t tile_in_chunk = tile - __ldg(params.tile_starts + chunk);
-    const uint32_t tile_row0 = tile_in_chunk * kScanTileRows;
 
-    // 1. predicate masks for this thread's 2 x 8 rows
+    // 1. predicate masks for this thread's kScanIterations x 8 rows (the warp owns kScanWarpRows contiguous rows)
     uint32_t masks[kScanIterations];
-    uint32_t packed_counts = 0;  // iteration i's count in bits [16i, 16i+16)
+    unsigned long long packed_counts = 0;  // iteration i's count in bits [16i, 16i+16)
 #pragma unroll
     for (int it = 0; it < kScanIterations; ++it) {
       const uint32_t row0 = tile_row0 + warp * kScanWarpRows + it * 256 + lane * 8;
       masks[it] = (test.mode != kTestNone && row0 < segment.row_count) ? evaluate8(segment, test, row0) : 0u;
-      packed_counts |= static_cast<uint32_t>(__popc(masks[it])) << (16 * it);
+      packed_counts |= static_cast<unsigned long long>(__popc(masks[it])) << (16 * it);
     }
 
-    // 2. warp scan of both iterations at once
-    const uint32_t inclusive = warp_inclusive_scan(packed_counts, lane);
-    const uint32_t warp_sums = __shfl_sync(kFullMask, inclusive, 31);
-    const uint32_t exclusive = inclusive - packed_counts;
-    if (lane == 31) s_warp_totals[warp] = (warp_sums & 0xFFFFu) + (warp_sums >> 16);
-    __syncthreads();
+    // 2. warp scan of all iterations at once (each field <= 256 fits 16 bits)
+    unsigned long long inclusive = packed_counts;
+#pragma unroll
+    for (int delta = 1; delta < 32; delta <<= 1) {
+      const unsigned long long other = __shfl_up_sync(kFullMask, inclusive, delta);
+      if (lane >= static_cast<uint32_t>(delta)) inclusive += other;
+    }
+    const unsigned long long warp_sums = __shfl_sync(kFullMask, inclusive, 31);
+    const unsigned long long exclusive = inclusive - packed_counts;
+    uint32_t warp_total = 0;
+#pragma unroll
+    for (int it = 0; it < kScanIterations; ++it) warp_total += static_cast<uint32_t>((warp_sums >> (16 * it)) & 0xFFFFu);
+    if (lane == 31) s_warp_totals[warp] = warp_total;
+    __syncthreads();  // barrier A. (s_warp_totals of the previous tile was last read before its barrier B.)
 
     uint32_t warp_base = 0, tile_total = 0;
 #pragma unroll
@@ -376,35 +401,40 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(const ScanParams par
       tile_total += total;
     }
 
-    // 3. warp 0 resolves the global offset while the other warps stage their matches
+    // 3. warp 0 resolves the global offset while the other warps stage their matches. s_offsets / s_base of the
+    //    previous tile are free: every warp finished its write-out before arriving at barrier A.
     if (warp == 0) {
       const unsigned long long base = lookback_exclusive_prefix(params.tile_status, tile, tile_total, lane);
       if (lane == 0) {
         s_base = base;
-        const bool last_tile_of_chunk = tile + 1 == __ldg(params.tile_starts + chunk + 1);
         if (last_tile_of_chunk) params.chunk_end[chunk] = base + tile_total;
         if (tile + 1 == params.tile_count) params.chunk_end[params.chunk_count] = base + tile_total;
+        s_next[slot ^ 1][0] = next_tile;
+        s_next[slot ^ 1][1] = next_info.x;
+        s_next[slot ^ 1][2] = next_info.y;
       }
     }
     {
-      uint32_t position = warp_base + (exclusive & 0xFFFFu);
+      uint32_t position = warp_base;
 #pragma unroll
       for (int it = 0; it < kScanIterations; ++it) {
-        const uint32_t row0 = tile_row0 + warp * kScanWarpRows + it * 256 + lane * 8;
-        if (it == 1) position = warp_base + (warp_sums & 0xFFFFu) + (exclusive >> 16);
+        // rows of iteration `it` come after all rows of earlier iterations of this warp
+        uint32_t at = position + static_cast<uint32_t>((exclusive >> (16 * it)) & 0xFFFFu);
+        const uint32_t relative = warp * kScanWarpRows + it * 256 + lane * 8;
         const uint32_t mask = masks[it];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          if (mask & (1u << j)) s_offsets[position++] = row0 + j;
+          if (mask & (1u << j)) s_offsets[at++] = static_cast<uint16_t>(relative + j);
         }
+        position += static_cast<uint32_t>((warp_sums >> (16 * it)) & 0xFFFFu);
       }
     }
-    __syncthreads();
+    __syncthreads();  // barrier B: staging, s_base and s_next[slot ^ 1] are visible
 
     // 4. coalesced RowID write-out
     hyb_row_id* out = params.out + s_base;
     for (uint32_t i = threadIdx.x; i < tile_total; i += kScanThreads) {
-      st_stream_v2(out + i, chunk, s_offsets[i]);
+      st_stream_v2(out + i, chunk, tile_row0 + s_offsets[i]);
     }
   }
 }
@@ -421,7 +451,7 @@ struct FilteredScanParams {
   unsigned long long input_count;
   const unsigned long long* input_chunk_end;  // inclusive prefix per chunk of the input list (chunk_count entries)
   uint32_t chunk_count;
-  uint32_t tile_count;                // ceil(input_count / kScanTileRows)
+  uint32_t tile_count;                // ceil(input_count / kFilteredTileRows)
   unsigned long long* tile_status;
   uint32_t* ticket;
   hyb_row_id* out;
@@ -429,20 +459,20 @@ struct FilteredScanParams {
 };
 
 __global__ void __launch_bounds__(kScanThreads) filtered_scan_kernel(const FilteredScanParams params) {
-  __shared__ hyb_row_id s_rows[kScanTileRows];
+  __shared__ hyb_row_id s_rows[kFilteredTileRows];
   __shared__ uint32_t s_warp_totals[kScanWarps];
   __shared__ uint32_t s_tile;
   __shared__ unsigned long long s_base;
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warp = threadIdx.x >> 5;
-  constexpr int kPerThread = kScanTileRows / kScanThreads;  // 16 consecutive inputs per thread
+  constexpr int kPerThread = kFilteredTileRows / kScanThreads;  // 16 consecutive inputs per thread
 
   while (true) {
     if (threadIdx.x == 0) s_tile = atomicAdd(params.ticket, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
     if (tile >= params.tile_count) return;
-    const unsigned long long first = static_cast<unsigned long long>(tile) * kScanTileRows +
+    const unsigned long long first = static_cast<unsigned long long>(tile) * kFilteredTileRows +
                                      static_cast<unsigned long long>(threadIdx.x) * kPerThread;
     uint32_t mask = 0;
     hyb_row_id rows[kPerThread];
@@ -616,9 +646,9 @@ int hyb_table_scan(hyb_context* context, hyb_table_t table_handle, const hyb_sca
   result->d_chunk_end = static_cast<uint64_t*>(chunk_end);
 
   if (!filter) {
-    const uint32_t* tile_starts = nullptr;
+    const uint2* tile_map = nullptr;
     uint32_t tile_count = 0;
-    HYB_TRY(get_tile_starts(context, table, kScanTileRows, &tile_starts, &tile_count));
+    HYB_TRY(get_tile_map(context, table, kScanTileRows, &tile_map, &tile_count));
     input_rows = table->row_count();
     input_bytes = column_bytes_per_launch(table, predicate->column_id);
     result->capacity = table->row_count();
@@ -634,7 +664,7 @@ int hyb_table_scan(hyb_context* context, hyb_table_t table_handle, const hyb_sca
       ScanParams params{};
       params.segments = column_segments;
       params.tests = tests;
-      params.tile_starts = tile_starts;
+      params.tile_map = tile_map;
       params.chunk_count = chunk_count;
       params.tile_count = tile_count;
       params.tile_status = static_cast<unsigned long long*>(status);
@@ -667,7 +697,7 @@ int hyb_table_scan(hyb_context* context, hyb_table_t table_handle, const hyb_sca
     void* out = nullptr;
     HYB_TRY(device_alloc(context, sizeof(hyb_row_id) * std::max<uint64_t>(input_count, 1), &out));
     result->d_row_ids = static_cast<hyb_row_id*>(out);
-    const uint32_t tile_count = static_cast<uint32_t>((input_count + kScanTileRows - 1) / kScanTileRows);
+    const uint32_t tile_count = static_cast<uint32_t>((input_count + kFilteredTileRows - 1) / kFilteredTileRows);
     void* status = nullptr;
     HYB_TRY(device_alloc(context, sizeof(uint64_t) * (size_t{tile_count} + 2), &status));
     HYB_CUDA(cudaMemsetAsync(status, 0, sizeof(uint64_t) * (size_t{tile_count} + 2), context->stream));

@@ -43,23 +43,6 @@ def _set_value(target: capi.Value, data_type: int, value) -> None:
         target.f64 = float(value)
 
 
-def string_value_id_bounds(table: Table, predicate: Predicate) -> np.ndarray:
-    """Per-chunk DictionarySegment::lower_bound / upper_bound (dictionary_segment.cpp:94-119) on the host-resident
-    string dictionaries; INVALID_VALUE_ID when past the end."""
-    between = capi.PRED_BETWEEN_INCLUSIVE <= predicate.condition <= capi.PRED_BETWEEN_EXCLUSIVE
-    width = 4 if between else 2
-    bounds = np.empty((table.chunk_count, width), dtype=np.uint32)
-    values = [predicate.lower, predicate.upper] if between else [predicate.lower]
-    for chunk_id, chunk in enumerate(table.chunks):
-        dictionary = chunk.segments[predicate.column_id].string_dictionary
-        for index, value in enumerate(values):
-            needle = np.array([value if isinstance(value, bytes) else str(value).encode()], dtype="S")
-            for offset, side in enumerate(("left", "right")):
-                position = int(np.searchsorted(dictionary, needle, side=side)[0]) if len(dictionary) else 0
-                bounds[chunk_id, 2 * index + offset] = capi.INVALID_VALUE_ID if position >= len(dictionary) else position
-    return bounds
-
-
 def build_scan_predicate(table: Table, predicate: Predicate) -> tuple[capi.ScanPredicate, object]:
     """Returns the C struct plus an object that must stay alive while the struct is in use."""
     data_type = table.column_definitions[predicate.column_id].data_type
@@ -70,7 +53,7 @@ def build_scan_predicate(table: Table, predicate: Predicate) -> tuple[capi.ScanP
     needs_value = predicate.condition not in (capi.PRED_IS_NULL, capi.PRED_IS_NOT_NULL)
     if data_type == capi.TYPE_STRING:
         if needs_value:
-            keepalive = np.ascontiguousarray(string_value_id_bounds(table, predicate))
+            keepalive = np.ascontiguousarray(table.string_value_id_bounds(predicate), dtype=np.uint32)
             struct.value_id_bounds = keepalive.ctypes.data
     else:
         _set_value(struct.lower, data_type, predicate.lower)
@@ -233,7 +216,8 @@ class DeviceContext:
         check(self.lib.hyb_context_synchronize(self.ptr))
 
     # device column pool ------------------------------------------------------------------------------------------
-    def upload(self, table: Table) -> DeviceTable:
+    def upload(self, table) -> DeviceTable:
+        """`table`: storage.Table or tpch.GeneratedTable (anything with view() / column_definitions)."""
         holder = table.view()
         handle = C.c_uint64()
         check(self.lib.hyb_table_upload(self.ptr, holder.pointer(), C.byref(handle)))

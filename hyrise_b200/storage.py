@@ -344,6 +344,24 @@ class Table:
     def view(self) -> "TableViewHolder":
         return TableViewHolder(self)
 
+    def string_value_id_bounds(self, predicate) -> np.ndarray:
+        """Per-chunk DictionarySegment::lower_bound / upper_bound (dictionary_segment.cpp:94-119) on the host-resident
+        string dictionaries; INVALID_VALUE_ID when past the end. Layout: [chunk][lb, ub] or, for BETWEEN,
+        [chunk][lb(lower), ub(lower), lb(upper), ub(upper)]."""
+        between = capi.PRED_BETWEEN_INCLUSIVE <= predicate.condition <= capi.PRED_BETWEEN_EXCLUSIVE
+        width = 4 if between else 2
+        bounds = np.empty((self.chunk_count, width), dtype=np.uint32)
+        values = [predicate.lower, predicate.upper] if between else [predicate.lower]
+        for chunk_id, chunk in enumerate(self.chunks):
+            dictionary = chunk.segments[predicate.column_id].string_dictionary
+            for index, value in enumerate(values):
+                needle = np.array([value if isinstance(value, bytes) else str(value).encode()], dtype="S")
+                for offset, side in enumerate(("left", "right")):
+                    position = int(np.searchsorted(dictionary, needle, side=side)[0]) if len(dictionary) else 0
+                    bounds[chunk_id, 2 * index + offset] = capi.INVALID_VALUE_ID if position >= len(dictionary) \
+                        else position
+        return bounds
+
     def column_values(self, column_id: int) -> tuple[np.ndarray, np.ndarray]:
         """Decoded values and null mask of a whole column (host side)."""
         if not self.chunks:

@@ -91,14 +91,14 @@ inline bool segment_is_null(const hyb_segment_desc& segment, uint32_t offset) {
   return segment.nulls && segment.nulls[offset];
 }
 
-// Value at `offset`. For NULL positions the reference iterators yield T{} (e.g. value_segment_iterable.hpp,
-// dictionary_segment_iterable.hpp: SegmentPosition{T{}, true, offset}); FrameOfReference yields minimum + offset
-// (frame_of_reference_segment_iterable.hpp) but is_null() is what callers test first.
+// Value at `offset`. For NULL positions the reference iterators yield: the stored value for ValueSegments
+// (value_segment_iterable.hpp; load_table stores T{} for NULL), T{} for dictionaries
+// (dictionary_segment_iterable.hpp:116), minimum + offset for FrameOfReference
+// (frame_of_reference_segment_iterable.hpp:131-139). JoinHash hashes that value for NULL probe rows it keeps.
 template <typename T>
 inline T segment_value(const hyb_segment_desc& segment, uint32_t offset) {
   switch (segment.encoding) {
     case HYB_ENC_UNENCODED:
-      if (segment.nulls && segment.nulls[offset]) return T{};
       return static_cast<const T*>(segment.values)[offset];
     case HYB_ENC_DICTIONARY: {
       const uint32_t value_id = vector_get(segment.attribute_vector, segment.vector_type, segment.bit_width, offset);
@@ -106,7 +106,6 @@ inline T segment_value(const hyb_segment_desc& segment, uint32_t offset) {
       return static_cast<const T*>(segment.values)[value_id];
     }
     default: {  // frame_of_reference_segment.hpp:65-73
-      if (segment.nulls && segment.nulls[offset]) return T{};
       if constexpr (std::is_same_v<T, int32_t>) {
         const int32_t minimum = static_cast<const int32_t*>(segment.values)[offset / HYB_FOR_BLOCK_SIZE];
         return static_cast<int32_t>(static_cast<uint32_t>(minimum) +
@@ -561,6 +560,20 @@ RadixContainer<T> materialize_input(const hyb_table_view* table, uint32_t column
     std::lock_guard<std::mutex> lock(bloom_mutex);
     for (uint32_t slot = 0; slot < BLOOM_FILTER_SIZE; ++slot) output_bloom_filter[slot] |= local_bloom[slot];
   });
+  if (filter) {
+    // A reference-table input only has the chunks its producer emitted: TableScan drops chunks without matches
+    // (table_scan.cpp:132-134), so they do not exist as partitions here either (matters for build(): an input with
+    // zero chunks yields no hash table at all, join_hash_steps.hpp:433-435).
+    RadixContainer<T> compacted;
+    std::vector<std::vector<size_t>> compacted_histograms;
+    for (uint32_t chunk = 0; chunk < chunk_count; ++chunk) {
+      if (filter->chunk_offsets[chunk + 1] == filter->chunk_offsets[chunk]) continue;
+      compacted.push_back(std::move(radix_container[chunk]));
+      compacted_histograms.push_back(std::move(histograms[chunk]));
+    }
+    radix_container = std::move(compacted);
+    histograms = std::move(compacted_histograms);
+  }
   return radix_container;
 }
 
@@ -1345,6 +1358,45 @@ int orc_join_hash(const hyb_table_view* build_table, uint32_t build_column, cons
   }
   return join_hash_impl<int64_t, int64_t>(build_table, build_column, build_filter, probe_table, probe_column,
                                           probe_filter, mode, bits, threads, out);
+}
+
+// Test hook for the KATs of src/test/lib/operators/join_hash/join_hash_steps_test.cpp:169-263: runs materialize_input
+// <int32, int32> and reports elements (in container order), per-chunk histograms and the output Bloom filter slots.
+int orc_debug_materialize(const hyb_table_view* table, uint32_t column, int32_t keep_nulls, int32_t radix_bits,
+                          const uint32_t* input_bloom_slots, uint32_t input_bloom_slot_count, int32_t* out_values,
+                          hyb_row_id* out_row_ids, uint8_t* out_nulls, uint64_t* out_count, uint64_t* out_histograms,
+                          uint32_t* out_bloom_slots, uint32_t* out_bloom_slot_count) {
+  std::vector<std::vector<size_t>> histograms;
+  BloomFilter output_bloom, input_bloom;
+  const BloomFilter* input = nullptr;
+  if (input_bloom_slots) {
+    input_bloom.assign(BLOOM_FILTER_SIZE, 0);
+    for (uint32_t i = 0; i < input_bloom_slot_count; ++i) input_bloom[input_bloom_slots[i]] = 1;
+    input = &input_bloom;
+  }
+  RadixContainer<int32_t> container =
+      keep_nulls ? materialize_input<int32_t, int32_t, true>(table, column, nullptr, histograms, radix_bits, output_bloom, input, 1)
+                 : materialize_input<int32_t, int32_t, false>(table, column, nullptr, histograms, radix_bits, output_bloom, input, 1);
+  uint64_t count = 0;
+  for (const auto& partition : container) {
+    for (size_t i = 0; i < partition.elements.size(); ++i) {
+      out_values[count] = partition.elements[i].value;
+      out_row_ids[count] = partition.elements[i].row_id;
+      out_nulls[count] = keep_nulls ? partition.null_values[i] : 0;
+      ++count;
+    }
+  }
+  *out_count = count;
+  const size_t partitions = size_t{1} << radix_bits;
+  for (size_t chunk = 0; chunk < histograms.size(); ++chunk) {
+    for (size_t p = 0; p < partitions; ++p) out_histograms[chunk * partitions + p] = histograms[chunk][p];
+  }
+  uint32_t slots = 0;
+  for (uint32_t slot = 0; slot < BLOOM_FILTER_SIZE; ++slot) {
+    if (output_bloom[slot] && slots < 4096) out_bloom_slots[slots++] = slot;
+  }
+  *out_bloom_slot_count = slots;
+  return HYB_OK;
 }
 
 void orc_join_result_free(orc_join_result* result) {

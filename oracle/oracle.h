@@ -72,6 +72,11 @@ int orc_join_hash(const hyb_table_view* build_table, uint32_t build_column, cons
                   const hyb_table_view* probe_table, uint32_t probe_column, const orc_pos_list* probe_filter,
                   int32_t mode, int32_t radix_bits, int32_t threads, orc_join_result* out);
 void orc_join_result_free(orc_join_result* result);
+/* Test hook: materialize_input<int32,int32> internals (elements, per-chunk radix histograms, Bloom filter slots). */
+int orc_debug_materialize(const hyb_table_view* table, uint32_t column, int32_t keep_nulls, int32_t radix_bits,
+                          const uint32_t* input_bloom_slots, uint32_t input_bloom_slot_count, int32_t* out_values,
+                          hyb_row_id* out_row_ids, uint8_t* out_nulls, uint64_t* out_count, uint64_t* out_histograms,
+                          uint32_t* out_bloom_slots, uint32_t* out_bloom_slot_count);
 int32_t orc_calculate_radix_bits(uint64_t build_side_size, uint64_t probe_side_size);
 
 typedef struct orc_aggregate_column {

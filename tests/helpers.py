@@ -64,3 +64,168 @@ def random_table(rng: np.random.Generator, rows: int, chunk_size: int, with_null
     ]
     nulls = [(rng.random(rows) < 0.1) if (with_nulls and d.nullable) else None for d in definitions]
     return Table.from_columns(definitions, columns, nulls, chunk_size)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# JoinVerification (src/lib/operators/join_verification.cpp:50-213): nested-loop semantics, used unordered.
+# ---------------------------------------------------------------------------------------------------------------------
+def rows_with_keys(table: Table, column_id: int, filter_list=None):
+    """[(RowID tuple, key or None)] in table order (or filter order)."""
+    out = []
+    if filter_list is not None:
+        cache = {}
+        for row in filter_list.row_ids:
+            chunk_id, offset = int(row["chunk_id"]), int(row["chunk_offset"])
+            if chunk_id not in cache:
+                segment = table.chunks[chunk_id].segments[column_id]
+                cache[chunk_id] = (segment.decode(), segment.null_mask())
+            values, nulls = cache[chunk_id]
+            out.append(((chunk_id, offset), None if nulls[offset] else values[offset].item()))
+        return out
+    for chunk_id, chunk in enumerate(table.chunks):
+        segment = chunk.segments[column_id]
+        values, nulls = segment.decode(), segment.null_mask()
+        for offset in range(segment.row_count):
+            out.append(((chunk_id, offset), None if nulls[offset] else values[offset].item()))
+    return out
+
+
+NULL_ROW = (0xFFFFFFFF, 0xFFFFFFFF)
+
+
+def verification_join(build_rows, probe_rows, mode):
+    """Multiset of output rows: (build RowID, probe RowID) pairs, or probe RowIDs for Semi/Anti."""
+    out = []
+    build_has_null = any(key is None for _, key in build_rows)
+    build_keys = {}
+    for row_id, key in build_rows:
+        if key is not None:
+            build_keys.setdefault(key, []).append(row_id)
+    for probe_id, key in probe_rows:
+        matches = build_keys.get(key, []) if key is not None else []
+        if mode == capi.JOIN_INNER:
+            out.extend((b, probe_id) for b in matches)
+        elif mode in (capi.JOIN_LEFT, capi.JOIN_RIGHT):
+            if matches:
+                out.extend((b, probe_id) for b in matches)
+            else:
+                out.append((NULL_ROW, probe_id))
+        elif mode == capi.JOIN_SEMI:
+            if matches:
+                out.append(probe_id)
+        elif mode == capi.JOIN_ANTI_NULL_AS_FALSE:
+            if not matches:
+                out.append(probe_id)
+        elif mode == capi.JOIN_ANTI_NULL_AS_TRUE:
+            if not build_rows:
+                out.append(probe_id)
+            elif key is not None and not matches and not build_has_null:
+                out.append(probe_id)
+    return out
+
+
+def reference_join_order(build_rows, probe_rows, mode, radix_bits):
+    """The exact output sequence of JoinHashImpl (join_hash_steps.hpp:509-922): grouped by key & (2^bits - 1) (std::hash
+    of an int is the identity; NULL probe rows hash their placeholder value), inside a partition in probe order, for
+    one probe row in build order."""
+    mask = (1 << radix_bits) - 1
+    build_has_null = any(key is None for _, key in build_rows)
+    if mode == capi.JOIN_ANTI_NULL_AS_TRUE and build_has_null:
+        return []
+    build_keys = {}
+    for row_id, key in build_rows:
+        if key is not None:
+            build_keys.setdefault(key, []).append(row_id)
+    partitions = [[] for _ in range(mask + 1)]
+    for probe_id, key, null_placeholder in probe_rows:
+        value = null_placeholder if key is None else key
+        partitions[value & mask].append((probe_id, key))
+    out = []
+    for rows in partitions:
+        for probe_id, key in rows:
+            matches = build_keys.get(key, []) if key is not None else []
+            if mode == capi.JOIN_INNER:
+                out.extend((b, probe_id) for b in matches)
+            elif mode in (capi.JOIN_LEFT, capi.JOIN_RIGHT):
+                out.extend((b, probe_id) for b in matches) if matches else out.append((NULL_ROW, probe_id))
+            elif mode == capi.JOIN_SEMI:
+                if matches:
+                    out.append(probe_id)
+            elif mode == capi.JOIN_ANTI_NULL_AS_FALSE:
+                if not matches:
+                    out.append(probe_id)
+            elif mode == capi.JOIN_ANTI_NULL_AS_TRUE:
+                if (not build_rows) or (key is not None and not matches):
+                    out.append(probe_id)
+    return out
+
+
+def join_result_rows(build_rows_array, probe_rows_array):
+    probe = [(int(r["chunk_id"]), int(r["chunk_offset"])) for r in probe_rows_array]
+    if build_rows_array is None:
+        return probe
+    build = [(int(r["chunk_id"]), int(r["chunk_offset"])) for r in build_rows_array]
+    return list(zip(build, probe))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Aggregate result comparison (check_table_equal.cpp:34,109-116: unordered rows, relative float tolerance)
+# ---------------------------------------------------------------------------------------------------------------------
+def aggregate_rows(table: Table, groupby_column_ids, output) -> list[tuple]:
+    """Result rows (group-by values dereferenced through the representative RowIDs, then the aggregate values)."""
+    rows = []
+    group_values = [column_values_at(table, column_id, output.row_ids) if output.group_count else []
+                    for column_id in groupby_column_ids]
+    for g in range(output.group_count):
+        row = [values[g] for values in group_values]
+        for values, nulls in zip(output.values, output.nulls):
+            row.append(None if nulls[g] else values[g].item())
+        rows.append(tuple(row))
+    return rows
+
+
+def expected_rows(table: Table) -> list[tuple]:
+    columns = []
+    for column_id in range(table.column_count):
+        values, nulls = table.column_values(column_id)
+        columns.append([None if null else (bytes(v) if isinstance(v, bytes) else v.item())
+                        for v, null in zip(values, nulls)])
+    return list(zip(*columns)) if columns and len(columns[0]) else []
+
+
+def _cell_close(a, b, rel=1e-6) -> bool:
+    if a is None or b is None:
+        return a is None and b is None
+    if isinstance(a, bytes) or isinstance(b, bytes):
+        return a == b
+    if isinstance(a, float) or isinstance(b, float):
+        return abs(float(a) - float(b)) <= rel * max(1.0, abs(float(a)), abs(float(b)))
+    return a == b
+
+
+def assert_rows_match_unordered(got: list[tuple], want: list[tuple], rel=1e-6) -> None:
+    assert len(got) == len(want), f"row count {len(got)} != {len(want)}\n got {got}\nwant {want}"
+    remaining = list(want)
+    for row in got:
+        for index, candidate in enumerate(remaining):
+            if len(candidate) == len(row) and all(_cell_close(a, b, rel) for a, b in zip(row, candidate)):
+                remaining.pop(index)
+                break
+        else:
+            raise AssertionError(f"row {row} not expected; remaining {remaining}")
+
+
+def assert_aggregate_outputs_equal(device_output, oracle_output, rel=1e-6) -> None:
+    """Device vs oracle: same groups in the same order, same representative rows, integers exact, floats within rel."""
+    assert device_output.group_count == oracle_output.group_count
+    assert device_output.used_immediate_keys == oracle_output.used_immediate_keys
+    assert row_ids_equal(device_output.row_ids, oracle_output.row_ids), \
+        f"representative RowIDs differ:\n{device_output.row_ids}\n{oracle_output.row_ids}"
+    assert device_output.value_types == oracle_output.value_types
+    for index, (got, want) in enumerate(zip(device_output.values, oracle_output.values)):
+        assert np.array_equal(device_output.nulls[index], oracle_output.nulls[index]), f"aggregate {index}: NULLs differ"
+        valid = ~oracle_output.nulls[index]
+        if got.dtype.kind in "iu":
+            assert np.array_equal(got[valid], want[valid]), f"aggregate {index}: {got} != {want}"
+        else:
+            assert np.allclose(got[valid], want[valid], rtol=rel, atol=0.0), f"aggregate {index}: {got} != {want}"

@@ -265,3 +265,28 @@ def decode_segment(segment) -> tuple[np.ndarray, np.ndarray]:
     nulls = np.zeros(max(segment.row_count, 1), dtype=np.uint8)
     _check(lib.orc_decode_segment(C.byref(desc), values.ctypes.data, nulls.ctypes.data))
     return values[: segment.row_count], nulls[: segment.row_count].astype(bool)
+
+
+def debug_materialize(table: Table, column: int, keep_nulls: bool, radix_bits: int, input_bloom_slots=None):
+    """materialize_input<int,int> internals for the KATs of join_hash_steps_test.cpp:169-263."""
+    lib = load()
+    holder = table.view()
+    rows = table.row_count
+    values = np.zeros(max(rows, 1), dtype=np.int32)
+    row_ids = np.zeros(max(rows, 1), dtype=ROW_ID_DTYPE)
+    nulls = np.zeros(max(rows, 1), dtype=np.uint8)
+    histograms = np.zeros(max(table.chunk_count, 1) * (1 << radix_bits), dtype=np.uint64)
+    bloom = np.zeros(4096, dtype=np.uint32)
+    count, bloom_count = C.c_uint64(), C.c_uint32()
+    slots = None if input_bloom_slots is None else np.ascontiguousarray(input_bloom_slots, dtype=np.uint32)
+    lib.orc_debug_materialize.argtypes = [C.POINTER(capi.TableView), C.c_uint32, C.c_int32, C.c_int32, C.c_void_p,
+                                          C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64),
+                                          C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
+    _check(lib.orc_debug_materialize(holder.pointer(), column, int(keep_nulls), radix_bits,
+                                     None if slots is None else slots.ctypes.data, 0 if slots is None else len(slots),
+                                     values.ctypes.data, row_ids.ctypes.data, nulls.ctypes.data, C.byref(count),
+                                     histograms.ctypes.data, bloom.ctypes.data, C.byref(bloom_count)))
+    n = count.value
+    return (values[:n], row_ids[:n], nulls[:n].astype(bool),
+            histograms.reshape(max(table.chunk_count, 1), 1 << radix_bits)[: table.chunk_count],
+            bloom[: bloom_count.value])

@@ -1,0 +1,162 @@
+"""JoinHash parity: the CUDA path (through the C-ABI) against the oracle — PosList pairs bit-exact, in reference order."""
+import numpy as np
+import pytest
+
+import oracle_lib as orc
+from helpers import ENCODINGS, random_table, row_ids_equal, tbl
+from hyrise_b200 import capi
+from hyrise_b200.device import Predicate
+from hyrise_b200.storage import ColumnDefinition, Table
+
+pytestmark = pytest.mark.gpu
+
+MODES = [capi.JOIN_INNER, capi.JOIN_LEFT, capi.JOIN_SEMI, capi.JOIN_ANTI_NULL_AS_TRUE, capi.JOIN_ANTI_NULL_AS_FALSE]
+
+
+def check_join(device, build, build_dev, build_column, probe, probe_dev, probe_column, mode, radix_bits,
+               build_filter=None, probe_filter=None):
+    """build_filter / probe_filter: (DevicePosList, HostPosList) pairs."""
+    expected = orc.join_hash(build, build_column, probe, probe_column, mode, radix_bits,
+                             build_filter=build_filter[1] if build_filter else None,
+                             probe_filter=probe_filter[1] if probe_filter else None)
+    result = device.join_hash(build_dev, build_column, probe_dev, probe_column, mode, radix_bits,
+                              build_filter=build_filter[0] if build_filter else None,
+                              probe_filter=probe_filter[0] if probe_filter else None)
+    try:
+        pairs, partitions, bits = result.info()
+        context = (mode, radix_bits, build_column, probe_column)
+        assert pairs == expected.pair_count, context
+        assert bits == expected.radix_bits, context
+        assert np.array_equal(result.partition_offsets(), expected.partition_offsets), context
+        got_build, got_probe = result.to_host()
+        assert row_ids_equal(got_probe, expected.probe), context
+        if expected.build is not None:
+            assert row_ids_equal(got_build, expected.build), context
+    finally:
+        result.free()
+    return expected
+
+
+@pytest.mark.parametrize("encoding", ENCODINGS)
+@pytest.mark.parametrize("chunk_size", [10, 3])
+def test_join_test_runner_inputs(device, encoding, chunk_size):
+    # join_test_runner.cpp:184-543: modes x radix bits x table sizes x key columns (int / int_null / long / long_null)
+    tables = {}
+    for side in ("left", "right"):
+        for size in (0, 10, 15):
+            table = tbl(f"join_test_runner/input_table_{side}_{size}.tbl", chunk_size).encode(encoding)
+            tables[(side, size)] = (table, device.upload(table) if table.chunk_count else None)
+    pairs = [(0, 0), (1, 1), (0, 1), (6, 6), (7, 7), (0, 6), (7, 1)]
+    for mode in MODES:
+        for radix_bits in (0, 1, 2, 5):
+            for left_size, right_size in [(10, 15), (15, 10), (15, 15)]:
+                left, left_dev = tables[("left", left_size)]
+                right, right_dev = tables[("right", right_size)]
+                for left_column, right_column in pairs:
+                    if mode == capi.JOIN_INNER and left.row_count <= right.row_count:
+                        check_join(device, left, left_dev, left_column, right, right_dev, right_column, mode, radix_bits)
+                    else:
+                        check_join(device, right, right_dev, right_column, left, left_dev, left_column, mode, radix_bits)
+    for table, device_table in tables.values():
+        if device_table:
+            device_table.drop()
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_empty_sides(device, mode):
+    # an empty build side (no chunks at all is not uploadable: use a one-row table filtered to nothing)
+    left = tbl("join_test_runner/input_table_left_10.tbl", 4)
+    right = tbl("join_test_runner/input_table_right_15.tbl", 4)
+    left_dev, right_dev = device.upload(left), device.upload(right)
+    nothing = Predicate(0, capi.PRED_GREATER_THAN, 10 ** 9)
+    left_none = (device.table_scan(left_dev, nothing), orc.table_scan(left, nothing))
+    right_none = (device.table_scan(right_dev, nothing), orc.table_scan(right, nothing))
+    for radix_bits in (0, 2):
+        check_join(device, right, right_dev, 1, left, left_dev, 1, mode, radix_bits, build_filter=right_none)
+        check_join(device, right, right_dev, 1, left, left_dev, 1, mode, radix_bits, probe_filter=left_none)
+        check_join(device, right, right_dev, 1, left, left_dev, 1, mode, radix_bits, build_filter=right_none,
+                   probe_filter=left_none)
+    left_dev.drop()
+    right_dev.drop()
+
+
+@pytest.mark.parametrize("encoding", ENCODINGS)
+@pytest.mark.parametrize("mode", MODES)
+def test_random_duplicates_and_nulls(device, encoding, mode):
+    # many-to-many keys (duplicate build keys -> position lists in build-row order), NULLs on both sides, negative keys
+    rng = np.random.default_rng(2024 + mode)
+    build = random_table(rng, 6_000, 1_000).encode(encoding)
+    probe = random_table(rng, 20_000, 2_047).encode(encoding)
+    build_dev, probe_dev = device.upload(build), device.upload(probe)
+    for radix_bits in (0, 3, 8):
+        check_join(device, build, build_dev, 4, probe, probe_dev, 4, mode, radix_bits)   # non-nullable, ~20 dups/key
+        check_join(device, build, build_dev, 0, probe, probe_dev, 0, mode, radix_bits)   # nullable int32, negatives
+    check_join(device, build, build_dev, 1, probe, probe_dev, 1, mode, 2)                # int64 keys
+    check_join(device, build, build_dev, 4, probe, probe_dev, 1, mode, 2)                # int32 build, int64 probe
+    build_dev.drop()
+    probe_dev.drop()
+
+
+def test_filtered_inputs(device):
+    # reference-table inputs: both sides pre-filtered by a TableScan (join_hash_test.cpp:52-66 uses scanned inputs)
+    rng = np.random.default_rng(5)
+    build = random_table(rng, 5_000, 512).encode("Dictionary")
+    probe = random_table(rng, 30_000, 4_096).encode("FrameOfReference")
+    build_dev, probe_dev = device.upload(build), device.upload(probe)
+    build_predicate = Predicate(4, capi.PRED_LESS_THAN, 150)
+    probe_predicate = Predicate(0, capi.PRED_GREATER_THAN_EQUALS, -200)
+    build_filter = (device.table_scan(build_dev, build_predicate), orc.table_scan(build, build_predicate))
+    probe_filter = (device.table_scan(probe_dev, probe_predicate), orc.table_scan(probe, probe_predicate))
+    for mode in MODES:
+        check_join(device, build, build_dev, 4, probe, probe_dev, 4, mode, 4, build_filter, probe_filter)
+        check_join(device, build, build_dev, 4, probe, probe_dev, 4, mode, 0, None, probe_filter)
+    build_dev.drop()
+    probe_dev.drop()
+
+
+def test_tpch_sf001_orders_lineitem(device):
+    # join_hash_test.cpp:26-46 shape on real dbgen data (sf-0.01: 15 000 orders x 60 175 lineitems), reference encodings
+    lineitem = np.load("tests/golden/tpch/sf-0.01_lineitem.npz")
+    orders = np.load("tests/golden/tpch/sf-0.01_orders.npz")
+    orders_table = Table.from_columns([ColumnDefinition("o_orderkey", capi.TYPE_INT32)], [orders["o_orderkey"]],
+                                      chunk_size=4_000).encode("Unencoded")
+    lineitem_table = Table.from_columns([ColumnDefinition("l_orderkey", capi.TYPE_INT32)], [lineitem["l_orderkey"]],
+                                        chunk_size=16_000).encode("FrameOfReference")
+    orders_dev, lineitem_dev = device.upload(orders_table), device.upload(lineitem_table)
+    for radix_bits in (-1, 0, 7):
+        expected = check_join(device, orders_table, orders_dev, 0, lineitem_table, lineitem_dev, 0, capi.JOIN_INNER,
+                              radix_bits)
+        assert expected.pair_count == len(lineitem["l_orderkey"])
+    check_join(device, orders_table, orders_dev, 0, lineitem_table, lineitem_dev, 0, capi.JOIN_SEMI, 7)
+    # the other direction: lineitem as build side -> duplicate build keys
+    check_join(device, lineitem_table, lineitem_dev, 0, orders_table, orders_dev, 0, capi.JOIN_INNER, 3)
+    orders_dev.drop()
+    lineitem_dev.drop()
+
+
+def test_generated_sf1_properties(device):
+    """orders x lineitem at SF 1 (6 M probe rows, 65 535-row chunks, FoR keys): size-independent properties."""
+    from hyrise_b200.tpch import TpchTables, L_ORDERKEY, O_ORDERKEY
+
+    tables = TpchTables(1.0, seed=42)
+    orders_dev, lineitem_dev = device.upload(tables.orders), device.upload(tables.lineitem)
+    result = device.join_hash(orders_dev, O_ORDERKEY, lineitem_dev, L_ORDERKEY, capi.JOIN_INNER, -1)
+    pairs, partitions, bits = result.info()
+    assert bits == 4 and partitions == 16             # calculate_radix_bits(1.5 M) = 4
+    assert pairs == tables.lineitem.row_count           # PK-FK: every lineitem finds exactly one order
+    build_rows, probe_rows = result.to_host()
+    probe_index = probe_rows["chunk_id"].astype(np.int64) * capi.DEFAULT_CHUNK_SIZE + probe_rows["chunk_offset"]
+    build_index = build_rows["chunk_id"].astype(np.int64) * capi.DEFAULT_CHUNK_SIZE + build_rows["chunk_offset"]
+    assert np.array_equal(np.sort(probe_index), np.arange(pairs))      # a permutation of the probe rows
+    order_keys = ((build_index + 1) >> 3 << 5) | ((build_index + 1) & 7)  # dbgen sparse key of order index + 1
+    offsets = result.partition_offsets()
+    for partition in range(partitions):
+        begin, end = int(offsets[partition]), int(offsets[partition + 1])
+        assert (order_keys[begin:end] & (partitions - 1) == partition).all()
+        assert (np.diff(probe_index[begin:end]) > 0).all()             # probe order inside the partition
+    # the matched order really is the lineitem's order: lineitem rows are generated order by order
+    assert (np.diff(build_index[np.argsort(probe_index)]) >= 0).all()
+    result.free()
+    orders_dev.drop()
+    lineitem_dev.drop()
+    tables.close()
