@@ -498,6 +498,7 @@ constexpr int kFastMaxColumns = 4;
 enum AffineKind : int32_t { kIdentity = 0, kLiteralMinusColumn = 1, kLiteralPlusColumn = 2, kColumnMinusLiteral = 3, kColumnPlusLiteral = 4 };
 
 struct FastPlan {
+  const DevSegment* size_segments;  // any column of the table: row count per chunk
   const uint2* tile_map;
   const unsigned long long* chunk_row_start;
   uint32_t tile_count;
@@ -689,9 +690,7 @@ __global__ void __launch_bounds__(kAggThreads, 1) aggregate_fast_kernel(const Fa
     const uint32_t chunk = info.x;
     const uint32_t tile_row0 = info.y & 0x7FFFFFFFu;
     const unsigned long long chunk_first_position = __ldg(plan.chunk_row_start + chunk);
-    const uint32_t chunk_rows = plan.value_segments[0] ? plan.value_segments[0][chunk].row_count
-                                : plan.groupby_count  ? plan.group_segments[0][chunk].row_count
-                                                       : plan.predicate_segments[0][chunk].row_count;
+    const uint32_t chunk_rows = plan.size_segments[chunk].row_count;
 #pragma unroll 1
     for (int it = 0; it < kAggTileRows / (kAggThreads * 8); ++it) {
       const uint32_t row0 = tile_row0 + warp * (kAggTileRows / kAggWarps) + it * 256 + lane * 8;
@@ -740,7 +739,7 @@ __global__ void __launch_bounds__(kAggThreads, 1) aggregate_fast_kernel(const Fa
           const unsigned long long hash = mix64(hashes[j]) | 1ull;
 #pragma unroll
           for (int g = 0; g < G; ++g) {
-            if (group_of[j] < 0 && ld_volatile_u64(&s_hash[g]) == hash) group_of[j] = g;
+            if (group_of[j] < 0 && *reinterpret_cast<volatile unsigned long long*>(&s_hash[g]) == hash) group_of[j] = g;
           }
           if (group_of[j] < 0) {
             // First sighting in this CTA: claim the first free slot (all threads probe in the same order).
@@ -1319,6 +1318,7 @@ int hyb_aggregate_hash(hyb_context* context, const hyb_aggregate_query* query, h
       const int C = column_template;
       const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(tile_count, context->sm_count * 2));
       FastPlan host_plan{};
+      host_plan.size_segments = table->d_segments;
       host_plan.tile_map = tile_map;
       host_plan.chunk_row_start = reinterpret_cast<const unsigned long long*>(table->d_chunk_row_start);
       host_plan.tile_count = tile_count;
@@ -1335,10 +1335,6 @@ int hyb_aggregate_hash(hyb_context* context, const hyb_aggregate_query* query, h
         host_plan.value_segments[c] = table->d_segments + size_t{fast.columns[c].column} * chunk_count;
         host_plan.affine_kind[c] = fast.columns[c].kind;
         host_plan.literal[c] = fast.columns[c].literal;
-      }
-      if (fast.columns.empty() && query->groupby_count == 0 && query->predicate_count == 0) {
-        // COUNT(*) over the whole table: give the kernel a column to size chunks with
-        host_plan.group_segments[0] = table->d_segments;
       }
       host_plan.need_raw_mask = fast.need_raw_mask;
       host_plan.need_product_mask = fast.need_product_mask;
@@ -1371,10 +1367,6 @@ int hyb_aggregate_hash(hyb_context* context, const hyb_aggregate_query* query, h
       host_plan.overflow = reinterpret_cast<uint32_t*>(cursor);
       cursor += 1;
       auto* device_plan = reinterpret_cast<FastPlan*>(cursor);
-      // value_segments[0] doubles as the "chunk size" source inside the kernel: make sure something is there
-      if (!host_plan.value_segments[0] && !host_plan.groupby_count && !host_plan.predicate_count) {
-        host_plan.groupby_count = 0;
-      }
       HYB_CUDA(cudaMemcpyAsync(device_plan, &host_plan, sizeof(FastPlan), cudaMemcpyHostToDevice, stream));
       timing_kernel_begin(context);
       launch_fast_kernel(fast.work_type, G, C, grid, stream, device_plan);
