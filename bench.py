@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py — the hot path of BASELINE.json on synthetic TPC-H-shaped tables.
+
+One *step* = one pass of the three operators over the resident lineitem / orders tables of scale factor --sf:
+  1. TableScan   l_shipdate < '1995-01-01' on lineitem (DictionarySegment<string>, u16 value-IDs)  -> RowIDPosList
+  2. JoinHash    orders (ValueSegment<int32>) x lineitem (FrameOfReference u16) on orderkey, Inner -> two PosLists
+  3. AggregateHash  TPC-H Q1: l_shipdate <= '1998-09-02' fused, GROUP BY l_returnflag, l_linestatus, 4 SUM 3 AVG COUNT(*)
+`value` = rows processed per second = (rows scanned + probe rows joined + rows aggregated) / step time, all ranks.
+
+    python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU under torchrun for N > 1)
+    python bench.py --impl reference ...                     the CPU arm: the oracle restatement of the reference's
+                                                             operators on the host cores, on a bounded sample
+
+Prints ONE JSON line (see DESIGN.md "Measurement" for every field).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+from hyrise_b200 import capi  # noqa: E402
+from hyrise_b200.device import Aggregate, DeviceContext, Expression, Predicate, ROW_ID_DTYPE  # noqa: E402
+from hyrise_b200.tpch import (L_DISCOUNT, L_EXTENDEDPRICE, L_LINESTATUS, L_ORDERKEY, L_QUANTITY, L_RETURNFLAG,  # noqa: E402
+                              L_SHIPDATE, L_TAX, O_ORDERKEY, TpchTables)
+
+SCAN_PREDICATE = Predicate(L_SHIPDATE, capi.PRED_LESS_THAN, "1995-01-01")
+Q1_PREDICATES = [Predicate(L_SHIPDATE, capi.PRED_LESS_THAN_EQUALS, "1998-09-02")]
+_ONE = ("lit", capi.TYPE_INT32, 1)
+Q1_AGGREGATES = [
+    Aggregate(capi.AGG_SUM, Expression.column(L_QUANTITY)),
+    Aggregate(capi.AGG_SUM, Expression.column(L_EXTENDEDPRICE)),
+    Aggregate(capi.AGG_SUM, Expression([("col", L_EXTENDEDPRICE), _ONE, ("col", L_DISCOUNT), "-", "*"])),
+    Aggregate(capi.AGG_SUM, Expression([("col", L_EXTENDEDPRICE), _ONE, ("col", L_DISCOUNT), "-", "*", _ONE,
+                                        ("col", L_TAX), "+", "*"])),
+    Aggregate(capi.AGG_AVG, Expression.column(L_QUANTITY)),
+    Aggregate(capi.AGG_AVG, Expression.column(L_EXTENDEDPRICE)),
+    Aggregate(capi.AGG_AVG, Expression.column(L_DISCOUNT)),
+    Aggregate(capi.AGG_COUNT_STAR),
+]
+Q1_GROUPBY = [L_RETURNFLAG, L_LINESTATUS]
+
+
+def measured_peak_gbs() -> tuple[float, str]:
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as handle:
+            return float(json.load(handle)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.device_index = device_index
+        self.samples: list[list[str]] = []
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self) -> None:
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.device_index}", f"--query-gpu={self.QUERY}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                fields = [field.strip() for field in out.strip().split(",")]
+                if len(fields) >= 6:
+                    self.samples.append(fields)
+            except Exception:  # noqa: BLE001 - best effort
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        self._thread.join(timeout=5)
+
+    def summary(self) -> dict:
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        clocks = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        maxima = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [name for index, name in enumerate(names) if any(s[2 + index].lower() == "active" for s in self.samples)]
+        return {"sm_mhz": clocks[len(clocks) // 2] if clocks else None, "sm_max_mhz": max(maxima) if maxima else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+class SlicedTable:
+    """The first `chunks` chunks of a generated table (shares the segment buffers): the bounded CPU sample."""
+
+    def __init__(self, table, chunks: int):
+        self._table = table
+        self.chunk_count = min(chunks, table.chunk_count)
+        self.column_count = table.column_count
+        self.column_definitions = table.column_definitions
+        self._view = capi.TableView(self.chunk_count, table.column_count, table._view.segments)
+        self.row_count = sum(table.segment_desc(chunk, 0).row_count for chunk in range(self.chunk_count))
+
+    def view(self):
+        from hyrise_b200.tpch import _ViewHolder
+        return _ViewHolder(self._view)
+
+    def string_value_id_bounds(self, predicate):
+        return self._table.string_value_id_bounds(predicate)[: self.chunk_count]
+
+
+def cpu_arm(tables: TpchTables, sample_lineitem_chunks: int, steps: int, warmup: int) -> dict:
+    """The reference's operators on the host cores: the oracle restatement (oracle/liboracle.so), chunk-parallel where the
+    reference spawns JobTasks, sequential where the reference is (AggregateHash's aggregation phase)."""
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import oracle_lib as orc
+
+    cores = os.cpu_count() or 1
+    lineitem = SlicedTable(tables.lineitem, sample_lineitem_chunks)
+    # the orders that own those lineitem rows (1..7 lines per order, mean 4) plus slack
+    orders_chunks = max(1, min(tables.orders.chunk_count, int(np.ceil(lineitem.row_count / 3.9 / capi.DEFAULT_CHUNK_SIZE)) + 1))
+    orders = SlicedTable(tables.orders, orders_chunks)
+    times = []
+    detail = {}
+    for step in range(warmup + steps):
+        begin = time.perf_counter()
+        t0 = time.perf_counter()
+        scan = orc.table_scan(lineitem, SCAN_PREDICATE, threads=cores)
+        t1 = time.perf_counter()
+        join = orc.join_hash(orders, O_ORDERKEY, lineitem, L_ORDERKEY, capi.JOIN_INNER, -1, threads=cores)
+        t2 = time.perf_counter()
+        aggregate = orc.aggregate_hash(lineitem, Q1_GROUPBY, Q1_AGGREGATES, predicates=Q1_PREDICATES, threads=cores)
+        t3 = time.perf_counter()
+        if step >= warmup:
+            times.append(t3 - begin)
+            detail = {"scan_ms": (t1 - t0) * 1e3, "join_ms": (t2 - t1) * 1e3, "aggregate_ms": (t3 - t2) * 1e3,
+                      "scan_matches": int(len(scan.row_ids)), "join_pairs": int(join.pair_count),
+                      "groups": int(aggregate.group_count)}
+    rows_per_step = 3 * lineitem.row_count
+    seconds = float(np.mean(times))
+    return {"value": rows_per_step / seconds, "ms_per_step": seconds * 1e3, "cores": cores, "rows_per_step": rows_per_step,
+            "sample": f"first {lineitem.chunk_count} lineitem chunks ({lineitem.row_count} rows) + first {orders.chunk_count} "
+                      f"orders chunks of the same generated tables", "detail": detail}
+
+
+def main() -> None:
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--gpus", type=int, default=1)
+    parser.add_argument("--steps", type=int, default=10)
+    parser.add_argument("--warmup", type=int, default=3)
+    parser.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    parser.add_argument("--sf", type=float, default=10.0, help="TPC-H scale factor per GPU")
+    parser.add_argument("--cpu-sample-chunks", type=int, default=92, help="lineitem chunks of the CPU sample (92 = SF 1)")
+    parser.add_argument("--no-cpu-baseline", action="store_true")
+    parser.add_argument("--no-e2e", action="store_true")
+    args = parser.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
+    metric = "TPC-H rows/sec scan+join+agg (TableScan l_shipdate + JoinHash orders x lineitem + Q1 AggregateHash)"
+    workload = f"tpch-sf{args.sf:g}-per-gpu scan(config 2)+join(config 3)+Q1 aggregate(config 4 query)"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        tables = TpchTables(min(args.sf, 1.2), seed=42)  # only the sample is needed
+        result = cpu_arm(tables, args.cpu_sample_chunks, max(args.steps, 1), warmup)
+        line = {
+            "impl": "reference", "metric": metric, "value": result["value"], "unit": "rows/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": result["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32 keys / u16 value-IDs / f32->f64 sums", "data": "synthetic",
+            "config": {"workload": workload, "cpu_sample": result["sample"]},
+            "cpu_baseline": {"value": result["value"], "unit": "rows/s", "cores": result["cores"], "kind": "port",
+                             "sample": result["sample"]},
+            "e2e": {"value": result["value"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "detail": result["detail"],
+        }
+        print(json.dumps(line))
+        return
+
+    import torch  # device selection / distributed plumbing only
+
+    distributed = world > 1
+    if distributed:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+
+    # ---- data: every rank owns its own SF-sized shard (weak scaling); different seeds = different orders ------------
+    tables = TpchTables(args.sf, seed=42 + rank, pinned=not args.no_e2e)
+    device = DeviceContext(local_rank)
+    lineitem = device.upload(tables.lineitem)
+    orders = device.upload(tables.orders)
+    device.synchronize()
+    rows = tables.lineitem.row_count
+    rows_per_step = 3 * rows
+
+    # L2 flush buffer: 256 MB > 126 MB L2, written before every operator inside the timed region
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
+    stream_ptr = capi.C.c_void_p()
+    capi.check(device.lib.hyb_context_stream(device.ptr, capi.C.byref(stream_ptr)))
+    hyb_stream = torch.cuda.ExternalStream(stream_ptr.value, device=f"cuda:{local_rank}")
+
+    def flush_l2():
+        with torch.cuda.stream(hyb_stream):
+            flush.fill_(1)
+
+    operators = {"scan": [], "join": [], "aggregate": []}
+    launches = [0]
+
+    def run_step(record: bool):
+        flush_l2()
+        scan = device.table_scan(lineitem, SCAN_PREDICATE)
+        scan_stats = device.last_stats()
+        flush_l2()
+        join = device.join_hash(orders, O_ORDERKEY, lineitem, L_ORDERKEY, capi.JOIN_INNER, -1)
+        join_stats = device.last_stats()
+        flush_l2()
+        aggregate = device.aggregate_hash(lineitem, Q1_GROUPBY, Q1_AGGREGATES, predicates=Q1_PREDICATES)
+        aggregate_stats = device.last_stats()
+        if record:
+            for name, stats in (("scan", scan_stats), ("join", join_stats), ("aggregate", aggregate_stats)):
+                operators[name].append((stats.dominant_kernel_ms, stats.device_ms, stats.algorithmic_bytes, stats.output_rows))
+                launches[0] += stats.kernel_launches
+        result = (scan.info()[0], join.info()[0], aggregate.group_count)
+        scan.free()
+        join.free()
+        return result
+
+    for _ in range(warmup):
+        run_step(False)
+    device.synchronize()
+    torch.cuda.synchronize()
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        begin = time.perf_counter()
+        for _ in range(args.steps):
+            outputs = run_step(True)
+        device.synchronize()
+        torch.cuda.synchronize()
+        elapsed = time.perf_counter() - begin
+    barrier()
+    if distributed:
+        tensor = torch.tensor([elapsed], device=f"cuda:{local_rank}", dtype=torch.float64)
+        dist.all_reduce(tensor, op=dist.ReduceOp.MAX)
+        elapsed = float(tensor.item())
+    ms_per_step = elapsed / args.steps * 1e3
+    value = rows_per_step * world / (elapsed / args.steps)
+
+    # ---- end to end: host buffers in, host buffers out, every step ---------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        scan_out = device.pinned_empty(rows, ROW_ID_DTYPE)
+        join_build_out = device.pinned_empty(rows, ROW_ID_DTYPE)
+        join_probe_out = device.pinned_empty(rows, ROW_ID_DTYPE)
+        h2d = tables.lineitem.host_bytes + tables.orders.host_bytes
+        d2h = 0
+
+        def e2e_step():
+            nonlocal d2h
+            table_l = device.upload(tables.lineitem)
+            table_o = device.upload(tables.orders)
+            scan = device.table_scan(table_l, SCAN_PREDICATE)
+            matched = scan.to_host(scan_out)
+            join = device.join_hash(table_o, O_ORDERKEY, table_l, L_ORDERKEY, capi.JOIN_INNER, -1)
+            pairs = join.to_host(join_build_out, join_probe_out)
+            aggregate = device.aggregate_hash(table_l, Q1_GROUPBY, Q1_AGGREGATES, predicates=Q1_PREDICATES)
+            d2h = len(matched) * 8 + len(pairs[1]) * 16 + aggregate.group_count * (8 + 8 * len(Q1_AGGREGATES))
+            scan.free()
+            join.free()
+            table_l.drop()
+            table_o.drop()
+
+        e2e_steps = max(2, min(args.steps, 5))
+        e2e_step()
+        device.synchronize()
+        barrier()
+        begin = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        device.synchronize()
+        e2e_elapsed = time.perf_counter() - begin
+        barrier()
+        if distributed:
+            tensor = torch.tensor([e2e_elapsed], device=f"cuda:{local_rank}", dtype=torch.float64)
+            dist.all_reduce(tensor, op=dist.ReduceOp.MAX)
+            e2e_elapsed = float(tensor.item())
+        e2e = {"value": rows_per_step * world / (e2e_elapsed / e2e_steps), "unit": "rows/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_elapsed / e2e_steps * 1e3, "steps": e2e_steps}
+
+    # ---- roofline of the dominant kernel + per-operator breakdown ---------------------------------------------------
+    peak, peak_source = measured_peak_gbs()
+    breakdown = {}
+    for name, samples in operators.items():
+        kernel_ms = float(np.mean([s[0] for s in samples]))
+        op_ms = float(np.mean([s[1] for s in samples]))
+        algorithmic = float(samples[-1][2])
+        breakdown[name] = {"kernel_ms": kernel_ms, "operator_ms": op_ms, "algorithmic_bytes": algorithmic,
+                           "achieved_gbs": algorithmic / kernel_ms / 1e6, "frac": algorithmic / kernel_ms / 1e6 / peak,
+                           "output_rows": int(samples[-1][3])}
+    dominant = max(breakdown, key=lambda name: breakdown[name]["kernel_ms"])
+    kernel_names = {"scan": "scan_kernel", "join": "join_probe_count_kernel + scan + join_probe_write_kernel",
+                    "aggregate": "aggregate_fast_kernel<f32, 4 groups, 4 columns>"}
+    roofline = {"bound": "hbm", "kernel": kernel_names[dominant], "achieved": breakdown[dominant]["achieved_gbs"],
+                "peak": peak, "peak_source": peak_source, "unit": "GB/s", "frac": breakdown[dominant]["frac"],
+                "traffic": None, "algorithmic_bytes_per_launch": breakdown[dominant]["algorithmic_bytes"],
+                "kernel_ms": breakdown[dominant]["kernel_ms"]}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        result = cpu_arm(tables, args.cpu_sample_chunks, 1, 0)
+        cpu_baseline = {"value": result["value"], "unit": "rows/s", "cores": result["cores"], "kind": "port",
+                        "sample": result["sample"], "detail": result["detail"]}
+
+    if rank == 0:
+        line = {
+            "metric": metric, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32 keys / u16 value-IDs / f32 arithmetic, f64 sums", "data": "synthetic",
+            "config": {"workload": workload, "lineitem_rows_per_gpu": rows, "orders_rows_per_gpu": tables.orders.row_count,
+                       "chunk_size": capi.DEFAULT_CHUNK_SIZE, "l2": "256 MB memset before every operator, inside the timed region",
+                       "parallelism": f"{world} x independent shard (chunk-partitioned scan; join/aggregate per shard)",
+                       "outputs_per_step": {"scan_matches": int(outputs[0]), "join_pairs": int(outputs[1]), "groups": int(outputs[2])}},
+            "roofline": roofline, "operators": breakdown, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "gpu_launches": launches[0], "clocks": clocks.summary(),
+        }
+        print(json.dumps(line))
+    device.close()
+    if distributed:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

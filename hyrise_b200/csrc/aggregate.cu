@@ -590,35 +590,15 @@ __device__ __forceinline__ void load_values8(const DevSegment& segment, uint32_t
   }
 }
 
+// Factor of the product chain as a + b * value with b = +-1: one FMA, and bit-identical to the reference's separate
+// subtraction / addition because b * value is exact (lit - col == fma(-1, col, lit), col - lit == fma(1, col, -lit)).
 template <int W>
-__device__ __forceinline__ typename WorkType<W>::Value apply_affine(int32_t kind, typename WorkType<W>::Value literal,
+__device__ __forceinline__ typename WorkType<W>::Value apply_affine(typename WorkType<W>::Value a, typename WorkType<W>::Value b,
                                                                     typename WorkType<W>::Value value) {
   if constexpr (W == 0) {
-    switch (kind) {
-      case kLiteralMinusColumn:
-        return __fsub_rn(literal, value);
-      case kLiteralPlusColumn:
-        return __fadd_rn(literal, value);
-      case kColumnMinusLiteral:
-        return __fsub_rn(value, literal);
-      case kColumnPlusLiteral:
-        return __fadd_rn(value, literal);
-      default:
-        return value;
-    }
+    return __fmaf_rn(b, value, a);
   } else if constexpr (W == 1) {
-    switch (kind) {
-      case kLiteralMinusColumn:
-        return __dsub_rn(literal, value);
-      case kLiteralPlusColumn:
-        return __dadd_rn(literal, value);
-      case kColumnMinusLiteral:
-        return __dsub_rn(value, literal);
-      case kColumnPlusLiteral:
-        return __dadd_rn(value, literal);
-      default:
-        return value;
-    }
+    return __fma_rn(b, value, a);
   } else {
     return value;
   }
@@ -642,18 +622,50 @@ __device__ __forceinline__ T warp_reduce_add(T value) {
   return value;
 }
 
+constexpr int kFastThreads = 128;
+constexpr int kFastWarps = kFastThreads / 32;
+constexpr int kFastRowsPerWarp = kAggTileRows / kFastWarps;   // 1024 contiguous rows per warp and tile
+constexpr int kFastIterations = kFastRowsPerWarp / 256;       // 8 rows per thread per iteration
+constexpr int kStagedDictionary = 256;                        // dictionaries up to this size are staged in shared memory
+constexpr int kMaxCombos = 256;                              // product of (dictionary size + 1) over the group-by columns
+constexpr uint8_t kComboUnresolved = 0xFF;
+constexpr uint8_t kComboOverflow = 0xFE;
+
+// acc += value where the row's group equals g. A predicated add on purpose: written as `if (group == g) acc[g] += v`
+// the compiler folds the chain into an indexed access and moves the accumulators from registers to local memory; as a
+// select (group == g ? v : 0) every add costs two extra SEL instructions.
+__device__ __forceinline__ void add_where(double& accumulator, double value, int group, int g) {
+  asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %2, %3;\n\t@p add.rn.f64 %0, %0, %1;\n\t}"
+      : "+d"(accumulator)
+      : "d"(value), "r"(group), "r"(g));
+}
+__device__ __forceinline__ void add_where(long long& accumulator, long long value, int group, int g) {
+  asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %2, %3;\n\t@p add.s64 %0, %0, %1;\n\t}"
+      : "+l"(accumulator)
+      : "l"(value), "r"(group), "r"(g));
+}
+
 template <int W, int G, int C>
-__global__ void __launch_bounds__(kAggThreads, 1) aggregate_fast_kernel(const FastPlan* __restrict__ plan_ptr) {
+__global__ void __launch_bounds__(kFastThreads, 2) aggregate_fast_kernel(const FastPlan* __restrict__ plan_ptr) {
   using Value = typename WorkType<W>::Value;
   using Accumulator = typename WorkType<W>::Accumulator;
   const FastPlan& plan = *plan_ptr;
 
+  // CTA-wide group table (<= G distinct keys), filled on first sight
   __shared__ unsigned long long s_hash[G];
   __shared__ unsigned long long s_keys[G][kMaxKeyWords];
   __shared__ uint32_t s_null_mask[G];
   __shared__ unsigned long long s_null_counts[2][G][C];  // [raw | product] NULL inputs (rare path)
-  __shared__ Accumulator s_reduce[kAggWarps];
-  __shared__ unsigned long long s_reduce_u64[kAggWarps];
+  // per-tile staging
+  __shared__ DevSegment s_value_segment[C];
+  __shared__ DevSegment s_group_segment[G == 1 ? 1 : HYB_MAX_GROUPBY_COLUMNS];
+  __shared__ Value s_dictionary[C][kStagedDictionary];
+  __shared__ uint8_t s_dictionary_staged[C];
+  __shared__ uint8_t s_combo_group[G == 1 ? 4 : kMaxCombos];
+  __shared__ uint32_t s_combo_stride[G == 1 ? 1 : HYB_MAX_GROUPBY_COLUMNS];
+  __shared__ uint32_t s_use_combos;
+  __shared__ Accumulator s_reduce[kFastWarps];
+  __shared__ unsigned long long s_reduce_u64[kFastWarps];
 
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x < G) {
@@ -665,24 +677,33 @@ __global__ void __launch_bounds__(kAggThreads, 1) aggregate_fast_kernel(const Fa
       s_null_counts[1][threadIdx.x][c] = 0;
     }
   }
-  __syncthreads();
 
   Accumulator raw_sum[G][C], product_sum[G][C];
-  unsigned long long rows[G], min_position[G], max_position[G];
+  uint32_t rows[G];                 // a thread sees far fewer than 2^32 rows
+  unsigned long long first_position[G], last_position[G];
 #pragma unroll
   for (int g = 0; g < G; ++g) {
     rows[g] = 0;
-    min_position[g] = ~0ull;
-    max_position[g] = 0;
+    first_position[g] = ~0ull;
+    last_position[g] = 0;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       raw_sum[g][c] = Accumulator{};
       product_sum[g][c] = Accumulator{};
     }
   }
-  Value literals[C];
+  Value affine_a[C], affine_b[C];
 #pragma unroll
-  for (int c = 0; c < C; ++c) literals[c] = static_cast<Value>(plan.literal[c]);
+  for (int c = 0; c < C; ++c) {
+    const Value literal = static_cast<Value>(plan.literal[c]);
+    const int32_t kind = plan.affine_kind[c];
+    affine_a[c] = (kind == kLiteralMinusColumn || kind == kLiteralPlusColumn || kind == kColumnPlusLiteral) ? literal
+                  : kind == kColumnMinusLiteral                                                             ? -literal
+                                                                                                            : Value{};
+    affine_b[c] = kind == kLiteralMinusColumn ? Value(-1) : Value(1);
+  }
+  const uint32_t need_raw_mask = plan.need_raw_mask, need_product_mask = plan.need_product_mask;
+  const uint32_t groupby_count = plan.groupby_count;
 
   // Static tile assignment (tile = blockIdx.x + k * gridDim.x) keeps the summation order reproducible.
   for (uint32_t tile = blockIdx.x; tile < plan.tile_count; tile += gridDim.x) {
@@ -691,135 +712,233 @@ __global__ void __launch_bounds__(kAggThreads, 1) aggregate_fast_kernel(const Fa
     const uint32_t tile_row0 = info.y & 0x7FFFFFFFu;
     const unsigned long long chunk_first_position = __ldg(plan.chunk_row_start + chunk);
     const uint32_t chunk_rows = plan.size_segments[chunk].row_count;
+
+    // ---- per-tile staging: segment descriptors, small dictionaries, the combo -> group table -----------------------
+    __syncthreads();  // previous tile done with the staged data
+    if (threadIdx.x < C && plan.value_segments[threadIdx.x]) {
+      s_value_segment[threadIdx.x] = plan.value_segments[threadIdx.x][chunk];
+    }
+    if (G > 1 && threadIdx.x >= 32 && threadIdx.x < 32 + groupby_count) {
+      s_group_segment[threadIdx.x - 32] = plan.group_segments[threadIdx.x - 32][chunk];
+    }
+    __syncthreads();
+    if constexpr (G > 1) {
+      if (threadIdx.x == 0) {
+        uint32_t combos = 1;
+        bool usable = true;
+        for (uint32_t q = 0; q < groupby_count; ++q) {
+          const DevSegment& segment = s_group_segment[q];
+          usable = usable && segment.encoding == HYB_ENC_DICTIONARY && segment.vector_type == HYB_VEC_FIXED_1B;
+          s_combo_stride[q] = combos;
+          combos = usable ? combos * (segment.dict_size + 1) : combos;
+          usable = usable && combos <= kMaxCombos;
+        }
+        s_use_combos = usable ? combos : 0;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      if (plan.value_segments[c] == nullptr) continue;
+      const DevSegment& segment = s_value_segment[c];
+      const bool staged = segment.encoding == HYB_ENC_DICTIONARY && segment.dict_size <= kStagedDictionary;
+      if (threadIdx.x == 0) s_dictionary_staged[c] = staged;
+      if (staged) {
+        for (uint32_t i = threadIdx.x; i < segment.dict_size; i += kFastThreads) {
+          s_dictionary[c][i] = typed_load<W>(segment.values, segment.data_type, i);
+        }
+      }
+    }
+    __syncthreads();
+    if constexpr (G > 1) {
+      // Resolve every value-ID combination of this chunk against the groups the CTA already knows (lookup only: a
+      // combination that never occurs must not claim a slot). After the first tiles all real groups are known, so
+      // rows take the per-row slow path only on first sightings.
+      for (uint32_t combination = threadIdx.x; combination < s_use_combos; combination += kFastThreads) {
+        unsigned long long hash = 0x9E3779B97F4A7C15ull;
+        uint32_t rest = combination;
+        for (uint32_t q = 0; q < groupby_count; ++q) {
+          const DevSegment& segment = s_group_segment[q];
+          const uint32_t value_id = rest % (segment.dict_size + 1);
+          rest /= segment.dict_size + 1;
+          bool is_null;
+          const unsigned long long entry = key_entry_from_code(segment, value_id, true, is_null);
+          hash = mix64(hash ^ entry) + (is_null ? 0x51ED270B3Full : 0ull);
+        }
+        hash = mix64(hash) | 1ull;
+        uint8_t group = kComboUnresolved;
+        for (int g = 0; g < G; ++g) {
+          if (*reinterpret_cast<volatile unsigned long long*>(&s_hash[g]) == hash) group = static_cast<uint8_t>(g);
+        }
+        s_combo_group[combination] = group;
+      }
+      __syncthreads();
+    }
+    const bool use_combos = G > 1 && s_use_combos != 0;
+
 #pragma unroll 1
-    for (int it = 0; it < kAggTileRows / (kAggThreads * 8); ++it) {
-      const uint32_t row0 = tile_row0 + warp * (kAggTileRows / kAggWarps) + it * 256 + lane * 8;
+    for (int it = 0; it < kFastIterations; ++it) {
+      const uint32_t row0 = tile_row0 + warp * kFastRowsPerWarp + it * 256 + lane * 8;
       if (row0 >= chunk_rows) continue;
       uint32_t mask = chunk_rows - row0 >= 8 ? 0xFFu : ((1u << (chunk_rows - row0)) - 1u);
       for (uint32_t p = 0; p < plan.predicate_count && mask; ++p) {
-        const ChunkTest test = plan.predicate_tests[p][chunk];
+        const ChunkTest& test = plan.predicate_tests[p][chunk];
         mask &= test.mode == kTestNone ? 0u : evaluate8(plan.predicate_segments[p][chunk], test, row0);
       }
       if (mask == 0) continue;
 
-      // group ids of the 8 rows
+      // ---- group of each row ----------------------------------------------------------------------------------------
       int32_t group_of[8];
       if constexpr (G == 1) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) group_of[j] = 0;
+        for (int j = 0; j < 8; ++j) group_of[j] = ((mask >> j) & 1u) ? 0 : -1;
         if (s_hash[0] == 0) s_hash[0] = 1;  // benign race: every writer stores the same value
       } else {
-        unsigned long long hashes[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) hashes[j] = 0x9E3779B97F4A7C15ull;
-        for (uint32_t q = 0; q < plan.groupby_count; ++q) {
-          const DevSegment& segment = plan.group_segments[q][chunk];
-          if (segment.encoding == HYB_ENC_DICTIONARY) {
-            uint32_t codes[8];
-            load_codes8(segment.av, segment.vector_type, segment.bit_width, row0, segment.row_count, codes);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              bool is_null;
-              const unsigned long long entry = key_entry_from_code(segment, codes[j], true, is_null);
-              hashes[j] = mix64(hashes[j] ^ entry) + (is_null ? 0x51ED270B3Full : 0ull);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              bool is_null = false;
-              const unsigned long long entry = (mask >> j) & 1u ? key_entry_at(segment, row0 + j, is_null) : 0ull;
-              hashes[j] = mix64(hashes[j] ^ entry) + (is_null ? 0x51ED270B3Full : 0ull);
-            }
-          }
-        }
+        uint32_t combo[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
+          combo[j] = 0;
           group_of[j] = -1;
-          if (!((mask >> j) & 1u)) continue;
-          const unsigned long long hash = mix64(hashes[j]) | 1ull;
+        }
+        if (use_combos) {
+          for (uint32_t q = 0; q < groupby_count; ++q) {
+            const uint2 packed = ld_stream_v2(static_cast<const uint8_t*>(s_group_segment[q].av) + row0);
+            const uint32_t stride = s_combo_stride[q];
 #pragma unroll
-          for (int g = 0; g < G; ++g) {
-            if (group_of[j] < 0 && *reinterpret_cast<volatile unsigned long long*>(&s_hash[g]) == hash) group_of[j] = g;
-          }
-          if (group_of[j] < 0) {
-            // First sighting in this CTA: claim the first free slot (all threads probe in the same order).
-            for (int g = 0; g < G && group_of[j] < 0; ++g) {
-              const unsigned long long previous = atomicCAS(&s_hash[g], 0ull, hash);
-              if (previous == 0ull) {
-                uint32_t null_mask = 0;
-                for (uint32_t q = 0; q < plan.groupby_count; ++q) {
-                  bool is_null;
-                  s_keys[g][q] = key_entry_at(plan.group_segments[q][chunk], row0 + j, is_null);
-                  if (is_null) null_mask |= 1u << q;
-                }
-                s_null_mask[g] = null_mask;
-                group_of[j] = g;
-              } else if (previous == hash) {
-                group_of[j] = g;
-              }
+            for (int j = 0; j < 4; ++j) {
+              combo[j] += ((packed.x >> (8 * j)) & 0xFFu) * stride;
+              combo[4 + j] += ((packed.y >> (8 * j)) & 0xFFu) * stride;
             }
-            if (group_of[j] < 0) {
-              *plan.overflow = 1;  // more than G groups: the host reruns the general kernel
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if ((mask >> j) & 1u) group_of[j] = s_combo_group[combo[j]];
+          }
+        }
+        // slow path: rows whose combination has not been seen in this tile (or every row when combos are unusable)
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {
+          if (!((mask >> j) & 1u)) continue;
+          if (use_combos && group_of[j] != kComboUnresolved) {
+            if (group_of[j] == kComboOverflow) {
+              group_of[j] = -1;
               mask &= ~(1u << j);
             }
+            continue;
+          }
+          unsigned long long entries[kMaxKeyWords];
+          uint32_t null_mask = 0;
+          unsigned long long hash = 0x9E3779B97F4A7C15ull;
+          for (uint32_t q = 0; q < groupby_count; ++q) {
+            bool is_null;
+            entries[q] = key_entry_at(s_group_segment[q], row0 + j, is_null);
+            if (is_null) null_mask |= 1u << q;
+            hash = mix64(hash ^ entries[q]) + (is_null ? 0x51ED270B3Full : 0ull);
+          }
+          hash = mix64(hash) | 1ull;
+          int32_t found = -1;
+          for (int g = 0; g < G && found < 0; ++g) {
+            unsigned long long current = *reinterpret_cast<volatile unsigned long long*>(&s_hash[g]);
+            if (current == 0ull) {
+              current = atomicCAS(&s_hash[g], 0ull, hash);
+              if (current == 0ull) {
+                for (uint32_t q = 0; q < groupby_count; ++q) s_keys[g][q] = entries[q];
+                s_null_mask[g] = null_mask;
+                found = g;
+              }
+            }
+            if (current == hash) found = g;
+          }
+          if (found < 0) {
+            *plan.overflow = 1;  // more than G groups: the host reruns with a bigger G or the general kernel
+            mask &= ~(1u << j);
+            if (use_combos) s_combo_group[combo[j]] = kComboOverflow;
+          } else if (use_combos) {
+            s_combo_group[combo[j]] = static_cast<uint8_t>(found);
+          }
+          group_of[j] = found;
+        }
+      }
+
+      // ---- rows / first / last position per group, once per iteration through hit masks ---------------------------
+      {
+        const unsigned long long base_position = chunk_first_position + row0;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          uint32_t hits = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) hits |= (group_of[j] == g) ? (1u << j) : 0u;
+          if (hits) {
+            if (rows[g] == 0) first_position[g] = base_position + (__ffs(hits) - 1);
+            last_position[g] = base_position + (31 - __clz(hits));
+            rows[g] += __popc(hits);
           }
         }
       }
 
-      // Row counts and first / last position per group (positions ascend within a thread). Written as selects over
-      // ALL groups on purpose: an `if (group == g)` chain is folded by the compiler into an indexed access, which
-      // would move the accumulators from registers to local memory.
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (!((mask >> j) & 1u)) group_of[j] = -1;
-        const unsigned long long position = chunk_first_position + row0 + j;
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const bool hit = group_of[j] == g;
-          min_position[g] = (hit && rows[g] == 0) ? position : min_position[g];
-          max_position[g] = hit ? position : max_position[g];
-          rows[g] += hit ? 1ull : 0ull;
-        }
-      }
-
-      // value columns: raw sums and the running product
+      // ---- value columns: raw sums and the running product ------------------------------------------------------------
       Value product[8];
       uint32_t product_nulls = 0;
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         if (plan.value_segments[c] == nullptr) continue;
+        const DevSegment& segment = s_value_segment[c];
         Value values[8];
-        uint32_t null_bits;
-        load_values8<W>(plan.value_segments[c][chunk], row0, values, null_bits);
-        const bool need_raw = (plan.need_raw_mask >> c) & 1u;
-        const bool need_product = (plan.need_product_mask >> c) & 1u;
-        const bool in_chain = (plan.need_product_mask >> c) != 0;  // some product at or after this column
+        uint32_t null_bits = 0;
+        if (segment.encoding == HYB_ENC_DICTIONARY) {
+          uint32_t codes[8];
+          load_codes8(segment.av, segment.vector_type, segment.bit_width, row0, segment.row_count, codes);
+          if (segment.pad & kSegmentMayContainNulls) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const bool is_null = codes[j] >= segment.dict_size;
+              null_bits |= is_null ? (1u << j) : 0u;
+              codes[j] = is_null ? 0u : codes[j];
+            }
+          } else if (row0 + 8 > segment.row_count) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) codes[j] = row0 + j < segment.row_count ? codes[j] : 0u;
+          }
+          if (s_dictionary_staged[c]) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) values[j] = s_dictionary[c][codes[j]];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) values[j] = typed_load<W>(segment.values, segment.data_type, codes[j]);
+          }
+        } else {
+          load_values8<W>(segment, row0, values, null_bits);
+        }
+        const bool need_raw = (need_raw_mask >> c) & 1u;
+        const bool need_product = (need_product_mask >> c) & 1u;
+        const bool in_chain = (need_product_mask >> c) != 0;  // some product at or after this column
         if (in_chain) {
           product_nulls |= null_bits;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const Value factor = apply_affine<W>(plan.affine_kind[c], literals[c], values[j]);
+            const Value factor = apply_affine<W>(affine_a[c], affine_b[c], values[j]);
             product[j] = c == 0 ? factor : multiply<W>(product[j], factor);
           }
         }
         if (need_raw) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const Accumulator value = ((null_bits >> j) & 1u) ? Accumulator{} : static_cast<Accumulator>(values[j]);
+            const int32_t group = ((null_bits >> j) & 1u) ? -1 : group_of[j];
+            const Accumulator value = static_cast<Accumulator>(values[j]);
 #pragma unroll
-            for (int g = 0; g < G; ++g) raw_sum[g][c] += group_of[j] == g ? value : Accumulator{};
+            for (int g = 0; g < G; ++g) add_where(raw_sum[g][c], value, group, g);
           }
         }
         if (need_product) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const Accumulator value = ((product_nulls >> j) & 1u) ? Accumulator{} : static_cast<Accumulator>(product[j]);
+            const int32_t group = ((product_nulls >> j) & 1u) ? -1 : group_of[j];
+            const Accumulator value = static_cast<Accumulator>(product[j]);
 #pragma unroll
-            for (int g = 0; g < G; ++g) product_sum[g][c] += group_of[j] == g ? value : Accumulator{};
+            for (int g = 0; g < G; ++g) add_where(product_sum[g][c], value, group, g);
           }
         }
         if ((need_raw && (null_bits & mask)) || (need_product && (product_nulls & mask))) {
-#pragma unroll
+#pragma unroll 1
           for (int j = 0; j < 8; ++j) {
             if (!((mask >> j) & 1u) || group_of[j] < 0) continue;
             if (need_raw && ((null_bits >> j) & 1u)) atomicAdd(&s_null_counts[0][group_of[j]][c], 1ull);
@@ -830,24 +949,23 @@ __global__ void __launch_bounds__(kAggThreads, 1) aggregate_fast_kernel(const Fa
     }
   }
 
-  // CTA reduction in a fixed order: lanes (butterfly), then warps 0..7.
+  // CTA reduction in a fixed order: lanes (butterfly), then warps.
   __syncthreads();
   const size_t cta = blockIdx.x;
 #pragma unroll
   for (int g = 0; g < G; ++g) {
-    const unsigned long long total_rows = warp_reduce_add(rows[g]);
-    unsigned long long low = min_position[g], high = max_position[g];
+    const unsigned long long total_rows = warp_reduce_add(static_cast<unsigned long long>(rows[g]));
+    unsigned long long low = first_position[g], high = last_position[g];
 #pragma unroll
     for (int delta = 16; delta > 0; delta >>= 1) {
       low = min(low, __shfl_xor_sync(kFullMask, low, delta));
       high = max(high, __shfl_xor_sync(kFullMask, high, delta));
     }
-    // rows
     if (lane == 0) s_reduce_u64[warp] = total_rows;
     __syncthreads();
     if (threadIdx.x == 0) {
       unsigned long long sum = 0;
-      for (int w = 0; w < kAggWarps; ++w) sum += s_reduce_u64[w];
+      for (int w = 0; w < kFastWarps; ++w) sum += s_reduce_u64[w];
       plan.partial_rows[cta * G + g] = sum;
     }
     __syncthreads();
@@ -855,7 +973,7 @@ __global__ void __launch_bounds__(kAggThreads, 1) aggregate_fast_kernel(const Fa
     __syncthreads();
     if (threadIdx.x == 0) {
       unsigned long long value = ~0ull;
-      for (int w = 0; w < kAggWarps; ++w) value = min(value, s_reduce_u64[w]);
+      for (int w = 0; w < kFastWarps; ++w) value = min(value, s_reduce_u64[w]);
       plan.partial_min_position[cta * G + g] = value;
     }
     __syncthreads();
@@ -863,7 +981,7 @@ __global__ void __launch_bounds__(kAggThreads, 1) aggregate_fast_kernel(const Fa
     __syncthreads();
     if (threadIdx.x == 0) {
       unsigned long long value = 0;
-      for (int w = 0; w < kAggWarps; ++w) value = max(value, s_reduce_u64[w]);
+      for (int w = 0; w < kFastWarps; ++w) value = max(value, s_reduce_u64[w]);
       plan.partial_max_position[cta * G + g] = value;
     }
     __syncthreads();
@@ -876,7 +994,7 @@ __global__ void __launch_bounds__(kAggThreads, 1) aggregate_fast_kernel(const Fa
         __syncthreads();
         if (threadIdx.x == 0) {
           Accumulator sum{};
-          for (int w = 0; w < kAggWarps; ++w) sum += s_reduce[w];
+          for (int w = 0; w < kFastWarps; ++w) sum += s_reduce[w];
           unsigned long long bits;
           memcpy(&bits, &sum, sizeof(bits));
           (which == 0 ? plan.partial_raw : plan.partial_product)[(cta * G + g) * C + c] = bits;
@@ -894,6 +1012,43 @@ __global__ void __launch_bounds__(kAggThreads, 1) aggregate_fast_kernel(const Fa
       plan.partial_raw_nulls[(cta * G + g) * C + c] = s_null_counts[0][g][c];
       plan.partial_product_nulls[(cta * G + g) * C + c] = s_null_counts[1][g][c];
     }
+  }
+}
+
+using FastKernel = void (*)(const FastPlan*);
+
+template <int W, int G>
+static FastKernel fast_kernel_for_columns(int columns) {
+  switch (columns) {
+    case 1:
+      return aggregate_fast_kernel<W, G, 1>;
+    case 2:
+      return aggregate_fast_kernel<W, G, 2>;
+    default:
+      return aggregate_fast_kernel<W, G, 4>;
+  }
+}
+
+template <int W>
+static FastKernel fast_kernel_for_groups(int groups, int columns) {
+  switch (groups) {
+    case 1:
+      return fast_kernel_for_columns<W, 1>(columns);
+    case 4:
+      return fast_kernel_for_columns<W, 4>(columns);
+    default:
+      return fast_kernel_for_columns<W, 8>(columns);
+  }
+}
+
+static FastKernel fast_kernel(int work_type, int groups, int columns) {
+  switch (work_type) {
+    case 0:
+      return fast_kernel_for_groups<0>(groups, columns);
+    case 1:
+      return fast_kernel_for_groups<1>(groups, columns);
+    default:
+      return fast_kernel_for_groups<2>(groups, columns);
   }
 }
 
@@ -1126,51 +1281,6 @@ static FastPlanHost plan_fast_path(const Table* table, const hyb_aggregate_query
   return plan;
 }
 
-template <int W, int G>
-static void launch_fast_kernel_c(int columns, uint32_t grid, cudaStream_t stream, const FastPlan* plan) {
-  switch (columns) {
-    case 1:
-      aggregate_fast_kernel<W, G, 1><<<grid, kAggThreads, 0, stream>>>(plan);
-      break;
-    case 2:
-      aggregate_fast_kernel<W, G, 2><<<grid, kAggThreads, 0, stream>>>(plan);
-      break;
-    default:
-      aggregate_fast_kernel<W, G, 4><<<grid, kAggThreads, 0, stream>>>(plan);
-      break;
-  }
-}
-
-template <int W>
-static void launch_fast_kernel_g(int groups, int columns, uint32_t grid, cudaStream_t stream, const FastPlan* plan) {
-  switch (groups) {
-    case 1:
-      launch_fast_kernel_c<W, 1>(columns, grid, stream, plan);
-      break;
-    case 4:
-      launch_fast_kernel_c<W, 4>(columns, grid, stream, plan);
-      break;
-    default:
-      launch_fast_kernel_c<W, 8>(columns, grid, stream, plan);
-      break;
-  }
-}
-
-static void launch_fast_kernel(int work_type, int groups, int columns, uint32_t grid, cudaStream_t stream,
-                               const FastPlan* plan) {
-  switch (work_type) {
-    case 0:
-      launch_fast_kernel_g<0>(groups, columns, grid, stream, plan);
-      break;
-    case 1:
-      launch_fast_kernel_g<1>(groups, columns, grid, stream, plan);
-      break;
-    default:
-      launch_fast_kernel_g<2>(groups, columns, grid, stream, plan);
-      break;
-  }
-}
-
 static hyb_row_id position_to_row_id_host(const Table* table, uint64_t position) {
   const auto& starts = table->chunk_row_start;
   const auto it = std::upper_bound(starts.begin(), starts.end(), position);
@@ -1316,7 +1426,11 @@ int hyb_aggregate_hash(hyb_context* context, const hyb_aggregate_query* query, h
     HYB_TRY(get_tile_map(context, table, kAggTileRows, &tile_map, &tile_count));
     for (const int G : attempts) {
       const int C = column_template;
-      const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(tile_count, context->sm_count * 2));
+      const FastKernel kernel = fast_kernel(fast.work_type, G, C);
+      int blocks_per_sm = 1;
+      HYB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kFastThreads, 0));
+      // one wave of resident CTAs: the static tile striding must not queue CTAs behind each other
+      const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(tile_count, context->sm_count * std::max(blocks_per_sm, 1)));
       FastPlan host_plan{};
       host_plan.size_segments = table->d_segments;
       host_plan.tile_map = tile_map;
@@ -1369,7 +1483,7 @@ int hyb_aggregate_hash(hyb_context* context, const hyb_aggregate_query* query, h
       auto* device_plan = reinterpret_cast<FastPlan*>(cursor);
       HYB_CUDA(cudaMemcpyAsync(device_plan, &host_plan, sizeof(FastPlan), cudaMemcpyHostToDevice, stream));
       timing_kernel_begin(context);
-      launch_fast_kernel(fast.work_type, G, C, grid, stream, device_plan);
+      kernel<<<grid, kFastThreads, 0, stream>>>(device_plan);
       timing_kernel_end(context);
       kernel_timed = true;
       HYB_CUDA(cudaGetLastError());

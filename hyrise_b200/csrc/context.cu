@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstring>
 
+#include "device_utils.cuh"
 #include "internal.hpp"
 
 namespace hyb {
@@ -194,6 +195,56 @@ void timing_output_count(hyb_context* context, const uint64_t* d_count, uint32_t
   timing.output_bytes_each = bytes_each;
   cudaMemcpyAsync(timing.h_output_count, d_count, sizeof(uint64_t), cudaMemcpyDeviceToHost, context->stream);
   cudaEventRecord(timing.count_ready, context->stream);
+}
+
+// One CTA per dictionary segment: does any row carry the NULL value-ID (== dictionary size)? Lets kernels skip NULL
+// handling for segments without NULLs (the reference knows this from the column definition, `_column_is_nullable`).
+__global__ void probe_null_value_ids_kernel(const DevSegment* __restrict__ segments, uint32_t count,
+                                            uint32_t* __restrict__ flags) {
+  const uint32_t index = blockIdx.x;
+  if (index >= count) return;
+  const DevSegment segment = segments[index];
+  bool found = false;
+  for (uint32_t row = threadIdx.x; row < segment.row_count; row += blockDim.x) {
+    found = found || load_code1(segment.av, segment.vector_type, segment.bit_width, row) >= segment.dict_size;
+  }
+  if (__syncthreads_or(found) && threadIdx.x == 0) flags[index] = 1;
+}
+
+// Fills DevSegment::pad for the segments [first_segment, end) of the host copy (call with the stream idle or ordered).
+int probe_null_flags(hyb_context* context, Table* table, size_t first_segment) {
+  std::vector<size_t> dictionary_segments;
+  for (size_t index = first_segment; index < table->segments.size(); ++index) {
+    auto& segment = table->segments[index];
+    segment.pad = 0;
+    if (segment.encoding == HYB_ENC_DICTIONARY) {
+      if (segment.row_count) dictionary_segments.push_back(index);
+    } else if (segment.nulls) {
+      segment.pad = kSegmentMayContainNulls;
+    }
+  }
+  if (dictionary_segments.empty()) return HYB_OK;
+  std::vector<DevSegment> staged;
+  staged.reserve(dictionary_segments.size());
+  for (const size_t index : dictionary_segments) staged.push_back(table->segments[index]);
+  void* d_segments = nullptr;
+  void* d_flags = nullptr;
+  HYB_TRY(device_alloc(context, sizeof(DevSegment) * staged.size(), &d_segments));
+  HYB_TRY(device_alloc(context, sizeof(uint32_t) * staged.size(), &d_flags));
+  HYB_CUDA(cudaMemcpyAsync(d_segments, staged.data(), sizeof(DevSegment) * staged.size(), cudaMemcpyHostToDevice, context->stream));
+  HYB_CUDA(cudaMemsetAsync(d_flags, 0, sizeof(uint32_t) * staged.size(), context->stream));
+  probe_null_value_ids_kernel<<<static_cast<uint32_t>(staged.size()), 256, 0, context->stream>>>(
+      static_cast<const DevSegment*>(d_segments), static_cast<uint32_t>(staged.size()), static_cast<uint32_t*>(d_flags));
+  HYB_CUDA(cudaGetLastError());
+  std::vector<uint32_t> flags(staged.size());
+  HYB_CUDA(cudaMemcpyAsync(flags.data(), d_flags, sizeof(uint32_t) * flags.size(), cudaMemcpyDeviceToHost, context->stream));
+  HYB_CUDA(cudaStreamSynchronize(context->stream));
+  device_free(context, d_segments);
+  device_free(context, d_flags);
+  for (size_t i = 0; i < dictionary_segments.size(); ++i) {
+    if (flags[i]) table->segments[dictionary_segments[i]].pad = kSegmentMayContainNulls;
+  }
+  return HYB_OK;
 }
 
 }  // namespace hyb
@@ -427,8 +478,10 @@ int hyb_table_append_chunk(hyb_context* context, hyb_table_t handle, const hyb_s
   std::lock_guard<std::mutex> lock(context->mutex);
   auto* table = find_table(context, handle);
   HYB_CHECK(table, HYB_ERR_NOT_FOUND, "unknown table handle");
+  const size_t first_segment = table->segments.size();
   HYB_TRY(append_chunk_locked(context, table, segments));
-  // The source buffers are borrowed only for the duration of the call.
+  // The source buffers are borrowed only for the duration of the call (probe_null_flags synchronises the stream).
+  HYB_TRY(probe_null_flags(context, table, first_segment));
   HYB_CUDA(cudaStreamSynchronize(context->stream));
   return HYB_OK;
 }
@@ -445,6 +498,7 @@ int hyb_table_upload(hyb_context* context, const hyb_table_view* view, hyb_table
   for (uint32_t chunk = 0; chunk < view->chunk_count && status == HYB_OK; ++chunk) {
     status = append_chunk_locked(context, table, view->segments + size_t{chunk} * view->column_count);
   }
+  if (status == HYB_OK) status = probe_null_flags(context, table, 0);
   if (status == HYB_OK) {
     cudaError_t error = cudaStreamSynchronize(context->stream);
     if (error != cudaSuccess) status = fail(HYB_ERR_CUDA, std::string("upload: ") + cudaGetErrorString(error));

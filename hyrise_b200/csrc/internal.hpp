@@ -31,8 +31,9 @@ struct DevSegment {
   uint8_t data_type;
   uint8_t vector_type;
   uint8_t bit_width;
-  uint32_t pad;
+  uint32_t pad;                 // flags: kSegmentMayContainNulls
 };
+constexpr uint32_t kSegmentMayContainNulls = 1u;  // set at upload (null vector present / NULL value-ID found)
 static_assert(sizeof(DevSegment) == 48, "DevSegment layout");
 
 // Bump allocator over large device slabs: one table = a handful of cudaMalloc calls instead of one per segment.
