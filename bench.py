@@ -270,13 +270,16 @@ def main() -> None:
         scan_out = device.pinned_empty(rows, ROW_ID_DTYPE)
         join_build_out = device.pinned_empty(rows, ROW_ID_DTYPE)
         join_probe_out = device.pinned_empty(rows, ROW_ID_DTYPE)
-        h2d = tables.lineitem.host_bytes + tables.orders.host_bytes
+        host_blocks = tables.host_blocks()
+        h2d = sum(block.bytes for block in host_blocks)
         d2h = 0
 
         def e2e_step():
             nonlocal d2h
-            table_l = device.upload(tables.lineitem)
-            table_o = device.upload(tables.orders)
+            # the generator's segment buffers live in a few pinned 256 MB blocks: one DMA per block, tables point into them
+            block_set = device.upload_blocks(host_blocks)
+            table_l = device.upload_from_blocks(tables.lineitem, block_set)
+            table_o = device.upload_from_blocks(tables.orders, block_set)
             scan = device.table_scan(table_l, SCAN_PREDICATE)
             matched = scan.to_host(scan_out)
             join = device.join_hash(table_o, O_ORDERKEY, table_l, L_ORDERKEY, capi.JOIN_INNER, -1)
@@ -287,6 +290,7 @@ def main() -> None:
             join.free()
             table_l.drop()
             table_o.drop()
+            device.free_blocks(block_set)
 
         e2e_steps = max(2, min(args.steps, 5))
         e2e_step()

@@ -68,6 +68,10 @@ class TableView(C.Structure):
     _fields_ = [("chunk_count", C.c_uint32), ("column_count", C.c_uint32), ("segments", C.POINTER(SegmentDesc))]
 
 
+class HostBlock(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("bytes", C.c_uint64)]
+
+
 class ScanPredicate(C.Structure):
     _fields_ = [
         ("column_id", C.c_uint32),
@@ -134,6 +138,9 @@ SYMBOLS = {
     "hyb_table_create": [_CTX, _U32, C.POINTER(_U64)],
     "hyb_table_append_chunk": [_CTX, _U64, C.POINTER(SegmentDesc)],
     "hyb_table_drop": [_CTX, _U64],
+    "hyb_blocks_upload": [_CTX, C.POINTER(HostBlock), _U32, C.POINTER(_U64)],
+    "hyb_table_upload_from_blocks": [_CTX, C.POINTER(TableView), _U64, C.POINTER(_U64)],
+    "hyb_blocks_free": [_CTX, _U64],
     "hyb_table_info": [_CTX, _U64, C.POINTER(_U32), C.POINTER(_U32), C.POINTER(_U64), C.POINTER(_U64)],
     "hyb_table_scan": [_CTX, _U64, C.POINTER(ScanPredicate), _U64, C.POINTER(_U64)],
     "hyb_pos_list_info": [_CTX, _U64, C.POINTER(_U64), C.POINTER(_U32)],

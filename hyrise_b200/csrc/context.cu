@@ -51,6 +51,20 @@ void Arena::release() {
   _reserved = _used = 0;
 }
 
+BlockSet::~BlockSet() {
+  for (auto& block : blocks) cudaFree(block.device_base);
+}
+
+const void* BlockSet::translate(const void* host, size_t bytes) const {
+  const char* pointer = static_cast<const char*>(host);
+  for (const auto& block : blocks) {
+    if (pointer >= block.host_base && pointer + bytes <= block.host_base + block.bytes) {
+      return block.device_base + (pointer - block.host_base);
+    }
+  }
+  return nullptr;
+}
+
 Table::~Table() {
   if (d_segments) cudaFree(d_segments);
   if (d_chunk_row_start) cudaFree(d_chunk_row_start);
@@ -156,8 +170,10 @@ static void ensure_events(hyb_context* context) {
   if (!timing.op_begin) {
     cudaEventCreate(&timing.op_begin);
     cudaEventCreate(&timing.op_end);
-    cudaEventCreate(&timing.kernel_begin);
-    cudaEventCreate(&timing.kernel_end);
+    for (int span = 0; span < OperatorTiming::kMaxKernelSpans; ++span) {
+      cudaEventCreate(&timing.kernel_begin[span]);
+      cudaEventCreate(&timing.kernel_end[span]);
+    }
     cudaEventCreate(&timing.count_ready);
     cudaHostAlloc(&timing.h_output_count, sizeof(uint64_t), cudaHostAllocPortable);
     *timing.h_output_count = 0;
@@ -167,12 +183,24 @@ static void ensure_events(hyb_context* context) {
 void timing_begin(hyb_context* context) {
   ensure_events(context);
   context->timing.valid = false;
+  context->timing.kernel_spans = 0;
   cudaEventRecord(context->timing.op_begin, context->stream);
 }
 
-void timing_kernel_begin(hyb_context* context) { cudaEventRecord(context->timing.kernel_begin, context->stream); }
+void timing_kernel_begin(hyb_context* context) {
+  auto& timing = context->timing;
+  if (timing.kernel_spans < OperatorTiming::kMaxKernelSpans) {
+    cudaEventRecord(timing.kernel_begin[timing.kernel_spans], context->stream);
+  }
+}
 
-void timing_kernel_end(hyb_context* context) { cudaEventRecord(context->timing.kernel_end, context->stream); }
+void timing_kernel_end(hyb_context* context) {
+  auto& timing = context->timing;
+  if (timing.kernel_spans < OperatorTiming::kMaxKernelSpans) {
+    cudaEventRecord(timing.kernel_end[timing.kernel_spans], context->stream);
+    ++timing.kernel_spans;
+  }
+}
 
 void timing_end(hyb_context* context, uint32_t launches, uint64_t algorithmic_bytes, uint64_t input_rows,
                 uint64_t output_rows) {
@@ -308,11 +336,14 @@ int hyb_context_destroy(hyb_context* context) {
     context->join_results.clear();
     context->aggregate_results.clear();
     context->tables.clear();
+    context->block_sets.clear();
     if (context->timing.op_begin) {
       cudaEventDestroy(context->timing.op_begin);
       cudaEventDestroy(context->timing.op_end);
-      cudaEventDestroy(context->timing.kernel_begin);
-      cudaEventDestroy(context->timing.kernel_end);
+      for (int span = 0; span < OperatorTiming::kMaxKernelSpans; ++span) {
+        cudaEventDestroy(context->timing.kernel_begin[span]);
+        cudaEventDestroy(context->timing.kernel_end[span]);
+      }
       cudaEventDestroy(context->timing.count_ready);
       cudaFreeHost(context->timing.h_output_count);
     }
@@ -388,6 +419,14 @@ static int validate_segment(const hyb_segment_desc& desc, uint32_t chunk, uint32
 static int upload_buffer(hyb_context* context, Table* table, const void* host, size_t bytes, const void** out_device) {
   *out_device = nullptr;
   if (host == nullptr) return HYB_OK;
+  if (table->block_set) {
+    // arena upload: the buffer already is on the device inside its block's copy
+    const void* resident = table->block_set->translate(host, bytes);
+    if (resident) {
+      *out_device = resident;
+      return HYB_OK;
+    }
+  }
   void* device = table->arena.alloc(bytes);
   HYB_CHECK(device, HYB_ERR_OOM, "device column pool: out of memory allocating " + std::to_string(bytes) + " bytes");
   if (bytes) HYB_CUDA(cudaMemcpyAsync(device, host, bytes, cudaMemcpyHostToDevice, context->stream));
@@ -511,6 +550,71 @@ int hyb_table_upload(hyb_context* context, const hyb_table_view* view, hyb_table
   return status;
 }
 
+int hyb_blocks_upload(hyb_context* context, const hyb_host_block* blocks, uint32_t block_count,
+                      hyb_block_set_t* out_block_set) {
+  HYB_CHECK(context && out_block_set && (blocks || block_count == 0), HYB_ERR_INVALID, "NULL argument");
+  *out_block_set = 0;
+  DeviceGuard guard(context->device);
+  std::lock_guard<std::mutex> lock(context->mutex);
+  auto set = std::make_shared<BlockSet>();
+  for (uint32_t index = 0; index < block_count; ++index) {
+    HYB_CHECK(blocks[index].base, HYB_ERR_INVALID, "block base is NULL");
+    char* device = nullptr;
+    HYB_CUDA(cudaMalloc(&device, blocks[index].bytes + Arena::kTailPad));
+    set->blocks.push_back({static_cast<const char*>(blocks[index].base), blocks[index].bytes, device});
+    HYB_CUDA(cudaMemcpyAsync(device, blocks[index].base, blocks[index].bytes, cudaMemcpyHostToDevice, context->stream));
+  }
+  HYB_CUDA(cudaStreamSynchronize(context->stream));  // the blocks are borrowed for the duration of the call
+  const auto handle = context->next_handle++;
+  context->block_sets.emplace(handle, std::move(set));
+  *out_block_set = handle;
+  return HYB_OK;
+}
+
+int hyb_blocks_free(hyb_context* context, hyb_block_set_t handle) {
+  HYB_CHECK(context, HYB_ERR_INVALID, "context is NULL");
+  DeviceGuard guard(context->device);
+  std::lock_guard<std::mutex> lock(context->mutex);
+  auto it = context->block_sets.find(handle);
+  HYB_CHECK(it != context->block_sets.end(), HYB_ERR_NOT_FOUND, "unknown block set handle");
+  HYB_CUDA(cudaStreamSynchronize(context->stream));
+  context->block_sets.erase(it);  // tables created from it keep the device memory alive until they are dropped
+  return HYB_OK;
+}
+
+int hyb_table_upload_from_blocks(hyb_context* context, const hyb_table_view* view, hyb_block_set_t block_set,
+                                 hyb_table_t* out_table) {
+  HYB_CHECK(context && view && out_table, HYB_ERR_INVALID, "NULL argument");
+  HYB_CHECK(view->column_count > 0, HYB_ERR_INVALID, "a table needs at least one column");
+  HYB_CHECK(view->segments || view->chunk_count == 0, HYB_ERR_INVALID, "view->segments is NULL");
+  HYB_TRY(hyb_table_create(context, view->column_count, out_table));
+  DeviceGuard guard(context->device);
+  std::lock_guard<std::mutex> lock(context->mutex);
+  auto set = context->block_sets.find(block_set);
+  if (set == context->block_sets.end()) {
+    context->tables.erase(*out_table);
+    *out_table = 0;
+    return fail(HYB_ERR_NOT_FOUND, "unknown block set handle");
+  }
+  auto* table = find_table(context, *out_table);
+  table->block_set = set->second;
+  int status = HYB_OK;
+  for (uint32_t chunk = 0; chunk < view->chunk_count && status == HYB_OK; ++chunk) {
+    status = append_chunk_locked(context, table, view->segments + size_t{chunk} * view->column_count);
+  }
+  if (status == HYB_OK) status = probe_null_flags(context, table, 0);
+  if (status == HYB_OK) {
+    cudaError_t error = cudaStreamSynchronize(context->stream);
+    if (error != cudaSuccess) status = fail(HYB_ERR_CUDA, std::string("upload: ") + cudaGetErrorString(error));
+  }
+  if (status != HYB_OK) {
+    cudaStreamSynchronize(context->stream);
+    context->tables.erase(*out_table);
+    *out_table = 0;
+  }
+  return status;
+}
+
 int hyb_table_drop(hyb_context* context, hyb_table_t handle) {
   HYB_CHECK(context, HYB_ERR_INVALID, "context is NULL");
   DeviceGuard guard(context->device);
@@ -544,7 +648,11 @@ int hyb_last_operator_stats(hyb_context* context, hyb_operator_stats* out_stats)
   HYB_CUDA(cudaEventSynchronize(timing.op_end));
   float op_ms = 0.f, kernel_ms = 0.f;
   HYB_CUDA(cudaEventElapsedTime(&op_ms, timing.op_begin, timing.op_end));
-  HYB_CUDA(cudaEventElapsedTime(&kernel_ms, timing.kernel_begin, timing.kernel_end));
+  for (int span = 0; span < timing.kernel_spans; ++span) {
+    float span_ms = 0.f;
+    HYB_CUDA(cudaEventElapsedTime(&span_ms, timing.kernel_begin[span], timing.kernel_end[span]));
+    kernel_ms += span_ms;
+  }
   timing.stats.device_ms = op_ms;
   timing.stats.dominant_kernel_ms = kernel_ms;
   if (timing.d_output_count) {

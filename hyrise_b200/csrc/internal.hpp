@@ -58,7 +58,21 @@ class Arena {
   size_t _used = 0;
 };
 
+// Device copies of host arena blocks (hyb_blocks_upload): tables created from them hold a reference.
+struct BlockSet {
+  struct Block {
+    const char* host_base;
+    uint64_t bytes;
+    char* device_base;
+  };
+  std::vector<Block> blocks;
+  ~BlockSet();
+  // Device address of a host buffer that lies inside one of the blocks, or nullptr.
+  const void* translate(const void* host, size_t bytes) const;
+};
+
 struct Table {
+  std::shared_ptr<BlockSet> block_set;      // set when the segment buffers live in uploaded arena blocks
   uint32_t column_count = 0;
   std::vector<uint32_t> chunk_rows;         // rows per chunk
   std::vector<uint64_t> chunk_row_start;    // exclusive prefix, chunk_count + 1 entries
@@ -121,7 +135,12 @@ struct AggregateResult {
 };
 
 struct OperatorTiming {
-  cudaEvent_t op_begin = nullptr, op_end = nullptr, kernel_begin = nullptr, kernel_end = nullptr;
+  static constexpr int kMaxKernelSpans = 8;
+  cudaEvent_t op_begin = nullptr, op_end = nullptr;
+  // Device time of the bandwidth-bound kernel(s) only: up to kMaxKernelSpans begin/end pairs, summed (host round
+  // trips between two kernels of one operator are not kernel time).
+  cudaEvent_t kernel_begin[kMaxKernelSpans] = {}, kernel_end[kMaxKernelSpans] = {};
+  int kernel_spans = 0;
   cudaEvent_t count_ready = nullptr;
   bool valid = false;
   hyb_operator_stats stats{};
@@ -143,6 +162,7 @@ struct hyb_context {
   std::unordered_map<uint64_t, std::unique_ptr<hyb::PosList>> pos_lists;
   std::unordered_map<uint64_t, std::unique_ptr<hyb::JoinResult>> join_results;
   std::unordered_map<uint64_t, std::unique_ptr<hyb::AggregateResult>> aggregate_results;
+  std::unordered_map<uint64_t, std::shared_ptr<hyb::BlockSet>> block_sets;
   hyb::OperatorTiming timing;
 };
 

@@ -13,11 +13,14 @@
 //                          keys — the TPC-H orderkey pattern — share one sector). Duplicate keys keep the smallest
 //                          position and raise a flag; if it is raised the CSR of positions per key is built (count,
 //                          scan, fill, sort) so matches can be emitted in build-row order (PosHashTable, :97-236).
-//   join_probe_count_kernel  per 4096-position tile of the probe side: decode keys, look them up, remember the match
-//                          (4 bytes per probe row) and add the emitted-row counts to a per-(partition, tile) histogram.
+//   join_probe_count_kernel  per 4096-position tile of the probe side: 128-bit loads of the key column (8 keys per
+//                          thread), in-register FoR / dictionary decode, one table lookup per run of equal keys, the
+//                          match (4 bytes) and the radix partition (1 byte) of every probe row, and the emitted-row
+//                          counts added to a per-(partition, tile) histogram.
 //   exclusive scan         over the histogram laid out partition-major: the start of every (partition, tile) run.
-//   join_probe_write_kernel  stable multi-split: each tile ranks its rows per partition (warp match_any + shared
-//                          counters) and writes (build RowID, probe RowID) pairs straight to their final position.
+//   join_probe_write_kernel  stable multi-split over the matches: each tile ranks its rows per partition (warp
+//                          match_any + shared counters) and writes (build RowID, probe RowID) pairs straight to their
+//                          final position. It never touches the key column again.
 //
 // Semi / Anti modes emit probe RowIDs only (probe_semi_anti); Left/Right emit NULL_ROW_ID partners for unmatched or
 // NULL probe keys (probe<keep_null_values = true>). NULL build keys are never inserted (join_hash.cpp:271-286).
@@ -36,6 +39,8 @@ constexpr int kJoinRowsPerWarp = kJoinTileRows / kJoinWarps;  // 512 contiguous 
 constexpr uint32_t kNoMatch = 0xFFFFFFFFu;
 constexpr unsigned long long kEmptySlot = ~0ull;
 constexpr int kMaxPartitions = 256;
+constexpr long long kWideKeyUnset = static_cast<long long>(0x8080808080808080ull);  // memset(0x80) pattern
+constexpr uint32_t kEmitWithoutPartner = 0xFFFFFFFEu;  // output row with a NULL build partner / Semi-Anti output row
 
 struct KeySource {
   const DevSegment* segments;        // key column descriptors, one per chunk
@@ -46,6 +51,8 @@ struct KeySource {
   uint32_t tile_count;
   uint32_t chunk_count;
   uint32_t uniform_chunk_rows;       // > 0: all chunks but the last have this many rows
+  uint32_t uniform_magic;            // ceil(2^(32 + shift) / uniform_chunk_rows) - 2^32  (position / rows by multiply-shift)
+  uint32_t uniform_shift;
 };
 
 struct KeyAt {
@@ -110,8 +117,12 @@ __device__ __forceinline__ KeyAt key_at(const KeySource& source, uint32_t tile, 
 __device__ __forceinline__ hyb_row_id position_to_row_id(const KeySource& source, unsigned long long position) {
   if (source.filter) return source.filter[position];
   if (source.uniform_chunk_rows) {
-    const uint32_t chunk = static_cast<uint32_t>(position / source.uniform_chunk_rows);
-    return hyb_row_id{chunk, static_cast<uint32_t>(position - static_cast<unsigned long long>(chunk) * source.uniform_chunk_rows)};
+    // positions are < 2^32 here (checked by the host): exact division by an invariant via multiply-high
+    // (Granlund & Montgomery; q = (mulhi(n, m') + ((n - mulhi(n, m')) >> 1)) >> (shift - 1))
+    const uint32_t n = static_cast<uint32_t>(position);
+    const uint32_t t = __umulhi(n, source.uniform_magic);
+    const uint32_t chunk = source.uniform_shift == 0 ? n : (t + ((n - t) >> 1)) >> (source.uniform_shift - 1);
+    return hyb_row_id{chunk, n - chunk * source.uniform_chunk_rows};
   }
   uint32_t lo = 0, hi = source.chunk_count;  // chunk_row_start[lo] <= position < chunk_row_start[hi]
   while (hi - lo > 1) {
@@ -123,6 +134,106 @@ __device__ __forceinline__ hyb_row_id position_to_row_id(const KeySource& source
     }
   }
   return hyb_row_id{lo, static_cast<uint32_t>(position - __ldg(source.chunk_row_start + lo))};
+}
+
+// Keys of 8 consecutive positions [index0, index0 + 8) of a tile (index0 % 8 == 0). valid/null bit masks per row.
+struct Keys8 {
+  long long key[8];
+  uint32_t valid;
+  uint32_t nulls;
+};
+
+struct TileRef {
+  uint32_t chunk;       // unfiltered
+  uint32_t row0;        // first row of the tile inside the chunk (unfiltered) / unused
+  unsigned long long first_position;  // position of index 0 of this tile
+};
+
+__device__ __forceinline__ TileRef tile_ref(const KeySource& source, uint32_t tile) {
+  TileRef ref{};
+  if (source.tile_map) {
+    const uint2 info = __ldg(source.tile_map + tile);
+    ref.chunk = info.x;
+    ref.row0 = info.y & 0x7FFFFFFFu;
+    ref.first_position = __ldg(source.chunk_row_start + info.x) + ref.row0;
+  } else {
+    ref.first_position = static_cast<unsigned long long>(tile) * kJoinTileRows;
+  }
+  return ref;
+}
+
+__device__ __forceinline__ void load_keys8(const KeySource& source, const TileRef& ref, const DevSegment& segment,
+                                           uint32_t index0, Keys8& out) {
+  out.valid = 0;
+  out.nulls = 0;
+  if (source.tile_map) {
+    const uint32_t row0 = ref.row0 + index0;
+    if (row0 >= segment.row_count) return;
+    out.valid = segment.row_count - row0 >= 8 ? 0xFFu : ((1u << (segment.row_count - row0)) - 1u);
+    switch (segment.encoding) {
+      case HYB_ENC_UNENCODED: {
+        if (segment.data_type == HYB_TYPE_INT32) {
+          const uint4 a = ld_stream_v4(static_cast<const int32_t*>(segment.values) + row0);
+          const uint4 b = ld_stream_v4(static_cast<const int32_t*>(segment.values) + row0 + 4);
+          out.key[0] = static_cast<int32_t>(a.x);
+          out.key[1] = static_cast<int32_t>(a.y);
+          out.key[2] = static_cast<int32_t>(a.z);
+          out.key[3] = static_cast<int32_t>(a.w);
+          out.key[4] = static_cast<int32_t>(b.x);
+          out.key[5] = static_cast<int32_t>(b.y);
+          out.key[6] = static_cast<int32_t>(b.z);
+          out.key[7] = static_cast<int32_t>(b.w);
+        } else {
+          const auto* base = static_cast<const long long*>(segment.values) + row0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 v = ld_stream_v4(base + 2 * j);
+            out.key[2 * j] = static_cast<long long>((static_cast<unsigned long long>(v.y) << 32) | v.x);
+            out.key[2 * j + 1] = static_cast<long long>((static_cast<unsigned long long>(v.w) << 32) | v.z);
+          }
+        }
+        out.nulls = load_nulls8(segment.nulls, row0);
+        break;
+      }
+      case HYB_ENC_DICTIONARY: {
+        uint32_t codes[8];
+        load_codes8(segment.av, segment.vector_type, segment.bit_width, row0, segment.row_count, codes);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const bool is_null = codes[j] >= segment.dict_size;
+          out.nulls |= is_null ? (1u << j) : 0u;
+          out.key[j] = is_null ? 0ll
+                       : segment.data_type == HYB_TYPE_INT32
+                           ? static_cast<long long>(__ldg(static_cast<const int32_t*>(segment.values) + codes[j]))
+                           : __ldg(static_cast<const long long*>(segment.values) + codes[j]);
+        }
+        break;
+      }
+      default: {  // FrameOfReference
+        uint32_t codes[8];
+        load_codes8(segment.av, segment.vector_type, segment.bit_width, row0, segment.row_count, codes);
+        const int32_t minimum = __ldg(static_cast<const int32_t*>(segment.values) + row0 / HYB_FOR_BLOCK_SIZE);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) out.key[j] = static_cast<int32_t>(static_cast<uint32_t>(minimum) + codes[j]);
+        out.nulls = load_nulls8(segment.nulls, row0);
+        break;
+      }
+    }
+    out.nulls &= out.valid;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const unsigned long long position = ref.first_position + index0 + j;
+      out.key[j] = 0;
+      if (position < source.position_count) {
+        const hyb_row_id row_id = source.filter[position];
+        bool is_null;
+        out.key[j] = decode_int_key(source.segments[row_id.chunk_id], row_id.chunk_offset, is_null);
+        out.valid |= 1u << j;
+        out.nulls |= is_null ? (1u << j) : 0u;
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -184,54 +295,76 @@ struct BuildParams {
   uint32_t* flags;                 // [0] duplicate keys seen, [1] NULL keys seen, [2] inserted rows
 };
 
+__device__ __forceinline__ void table_insert(const BuildParams& params, long long key, uint32_t value) {
+  if (params.wide_keys_out) params.wide_keys_out[value] = key;
+  const uint32_t key_bits = static_cast<uint32_t>(key);
+  const unsigned long long desired = pack_slot(key_bits, value);
+  uint32_t bucket = bucket_of(key, params.table.bucket_mask);
+  while (true) {
+    unsigned long long* slots = params.table.slots + static_cast<size_t>(bucket) * 4;
+    const uint32_t start = key_bits & 3u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      unsigned long long* slot = slots + ((start + j) & 3u);
+      unsigned long long current = *reinterpret_cast<volatile unsigned long long*>(slot);
+      if (current == kEmptySlot) {
+        current = atomicCAS(slot, kEmptySlot, desired);
+        if (current == kEmptySlot) return;
+      }
+      if (static_cast<uint32_t>(current) == key_bits) {
+        bool same = true;
+        if (params.wide_keys_out) {
+          // The owner publishes its full key before inserting; positions are unique, so spin until it is visible.
+          const uint32_t owner = static_cast<uint32_t>(current >> 32);
+          long long owner_key;
+          do {
+            owner_key = *reinterpret_cast<volatile long long*>(params.wide_keys_out + owner);
+          } while (owner_key == kWideKeyUnset && key != kWideKeyUnset);
+          same = owner_key == key;
+        }
+        if (same) {
+          // Equal key already present: keep the smallest build position in the slot (deterministic) and flag it.
+          atomicMin(reinterpret_cast<uint32_t*>(slot) + 1, value);
+          params.flags[0] = 1;
+          return;
+        }
+      }
+    }
+    bucket = (bucket + 1) & params.table.bucket_mask;
+  }
+}
+
+// One key of a tile, lane-consecutive (thread t handles index t, t + 256, ...): neighbouring lanes hold neighbouring
+// keys, so their hash-table accesses fall into the same 32-byte buckets — measured 4x faster than giving each thread 8
+// consecutive rows, although that needs fewer load instructions.
+__device__ __forceinline__ bool load_key1(const KeySource& source, const TileRef& ref, const DevSegment& segment,
+                                          uint32_t index, long long& key, bool& is_null) {
+  if (source.tile_map) {
+    const uint32_t row = ref.row0 + index;
+    if (row >= segment.row_count) return false;
+    key = decode_int_key(segment, row, is_null);
+    return true;
+  }
+  const unsigned long long position = ref.first_position + index;
+  if (position >= source.position_count) return false;
+  const hyb_row_id row_id = source.filter[position];
+  key = decode_int_key(source.segments[row_id.chunk_id], row_id.chunk_offset, is_null);
+  return true;
+}
+
 __global__ void __launch_bounds__(kJoinThreads) join_build_kernel(const BuildParams params) {
   for (uint32_t tile = blockIdx.x; tile < params.source.tile_count; tile += gridDim.x) {
+    const TileRef ref = tile_ref(params.source, tile);
+    const DevSegment segment = params.source.tile_map ? params.source.segments[ref.chunk] : DevSegment{};
     for (uint32_t index = threadIdx.x; index < kJoinTileRows; index += kJoinThreads) {
-      const KeyAt row = key_at(params.source, tile, index);
-      if (!row.valid) continue;
-      if (row.is_null) {
+      long long key;
+      bool is_null;
+      if (!load_key1(params.source, ref, segment, index, key, is_null)) continue;
+      if (is_null) {
         params.flags[1] = 1;
         continue;
       }
-      const uint32_t value = static_cast<uint32_t>(row.position);
-      if (params.wide_keys_out) params.wide_keys_out[value] = row.key;
-      const uint32_t key_bits = static_cast<uint32_t>(row.key);
-      const unsigned long long desired = pack_slot(key_bits, value);
-      uint32_t bucket = bucket_of(row.key, params.table.bucket_mask);
-      bool done = false;
-      while (!done) {
-        unsigned long long* slots = params.table.slots + static_cast<size_t>(bucket) * 4;
-        const uint32_t start = static_cast<uint32_t>(row.key) & 3u;
-#pragma unroll
-        for (int j = 0; j < 4 && !done; ++j) {
-          unsigned long long* slot = slots + ((start + j) & 3u);
-          unsigned long long current = *reinterpret_cast<volatile unsigned long long*>(slot);
-          if (current == kEmptySlot) {
-            current = atomicCAS(slot, kEmptySlot, desired);
-            if (current == kEmptySlot) {
-              done = true;
-              break;
-            }
-          }
-          if (static_cast<uint32_t>(current) == key_bits) {
-            bool same = true;
-            if (params.wide_keys_out) {
-              // The owner of the slot publishes its full key before inserting; positions are unique, so once the slot is
-              // visible wide_keys_out[owner] is either written or about to be: spin until it is.
-              const uint32_t owner = static_cast<uint32_t>(current >> 32);
-              same = *reinterpret_cast<volatile long long*>(params.wide_keys_out + owner) == row.key;
-            }
-            if (same) {
-              // Equal key already present: keep the smallest build position in the slot (deterministic) and flag it.
-              atomicMin(reinterpret_cast<uint32_t*>(slot) + 1, value);
-              params.flags[0] = 1;
-              done = true;
-              break;
-            }
-          }
-        }
-        bucket = (bucket + 1) & params.table.bucket_mask;
-      }
+      table_insert(params, key, static_cast<uint32_t>(ref.first_position + index));
     }
   }
 }
@@ -364,85 +497,93 @@ struct ProbeParams {
   uint32_t partition_count;
   uint32_t unique_build;                  // 1: slot value is the build position; 0: use counts/offsets/positions
   uint32_t build_is_empty;
+  const uint32_t* flags;                  // [0] duplicate build keys, [1] NULL build keys (written by the build kernel)
   const uint32_t* dup_counts;             // per slot
   const unsigned long long* dup_offsets;  // per slot
   const uint32_t* dup_positions;
-  uint32_t* matches;                      // per probe position: slot value / slot index / kNoMatch
-  uint32_t* emit_counts;                  // per probe position (only when !unique_build)
+  uint32_t* matches;                      // per probe slot (tile * 4096 + index): build position | slot | kEmit... | kNoMatch
+  uint8_t* partitions;                    // per probe slot: hash(key) & partition_mask
   uint32_t* histogram;                    // [partition][tile]
   const unsigned long long* run_starts;   // exclusive scan of histogram
   hyb_row_id* out_build;
   hyb_row_id* out_probe;
+  unsigned long long out_capacity;
+  uint32_t* overflow;                     // set when the output does not fit out_capacity (optimistic sizing)
 };
 
-// How many output rows one probe row produces, and what to remember about its match.
-__device__ __forceinline__ uint32_t probe_one(const ProbeParams& params, const KeyAt& row, uint32_t& match) {
-  match = kNoMatch;
-  if (!row.valid) return 0;
+// What one probe row contributes. Returns the match word: a build position (unique build side), a table slot
+// (duplicate build keys), kEmitWithoutPartner (one output row without a build partner) or kNoMatch (no output row).
+// Inner/Semi drop NULL probe keys during materialisation; Left/Right and AntiNullAsFalse emit them; AntiNullAsTrue emits
+// them only when the build table is empty, and nothing at all once the build side holds a NULL
+// (join_hash_steps.hpp:711-758, 848-913; join_hash.cpp:471-483).
+__device__ __forceinline__ uint32_t probe_match_resolved(const ProbeParams& params, uint32_t slot, bool is_null,
+                                                         bool build_has_nulls) {
   const int32_t mode = params.mode;
-  if (row.is_null) {
-    // Inner/Semi discard NULL probe keys during materialisation; Left/Right and AntiNullAsFalse emit them;
-    // AntiNullAsTrue emits them only when the build table is empty (join_hash_steps.hpp:711-758, 848-913).
-    if (mode == HYB_JOIN_LEFT || mode == HYB_JOIN_RIGHT || mode == HYB_JOIN_ANTI_NULL_AS_FALSE) return 1;
-    if (mode == HYB_JOIN_ANTI_NULL_AS_TRUE) return params.build_is_empty ? 1 : 0;
-    return 0;
+  if (mode == HYB_JOIN_ANTI_NULL_AS_TRUE && build_has_nulls) return kNoMatch;
+  if (is_null) {
+    if (mode == HYB_JOIN_LEFT || mode == HYB_JOIN_RIGHT || mode == HYB_JOIN_ANTI_NULL_AS_FALSE) return kEmitWithoutPartner;
+    if (mode == HYB_JOIN_ANTI_NULL_AS_TRUE) return params.build_is_empty ? kEmitWithoutPartner : kNoMatch;
+    return kNoMatch;
   }
-  const uint32_t slot = params.table.slots ? table_find(params.table, row.key) : kNoMatch;
   const bool found = slot != kNoMatch;
   switch (mode) {
     case HYB_JOIN_SEMI:
-      return found ? 1 : 0;
+      return found ? kEmitWithoutPartner : kNoMatch;
     case HYB_JOIN_ANTI_NULL_AS_TRUE:
     case HYB_JOIN_ANTI_NULL_AS_FALSE:
-      return found ? 0 : 1;
+      return found ? kNoMatch : kEmitWithoutPartner;
     default:
       break;
   }
-  if (!found) return (mode == HYB_JOIN_LEFT || mode == HYB_JOIN_RIGHT) ? 1 : 0;
-  if (params.unique_build) {
-    match = static_cast<uint32_t>(params.table.slots[slot] >> 32);
-    return 1;
-  }
-  match = slot;
-  return params.dup_counts[slot];
+  if (!found) return (mode == HYB_JOIN_LEFT || mode == HYB_JOIN_RIGHT) ? kEmitWithoutPartner : kNoMatch;
+  return params.unique_build ? static_cast<uint32_t>(params.table.slots[slot] >> 32) : slot;
 }
 
-__device__ __forceinline__ uint32_t partition_of(const ProbeParams& params, const KeyAt& row) {
-  // hash(value) & mask with std::hash<int32/int64> = identity (join_hash_steps.hpp:345-395)
-  return static_cast<uint32_t>(static_cast<unsigned long long>(row.key)) & params.partition_mask;
+__device__ __forceinline__ uint32_t emitted_rows(const ProbeParams& params, uint32_t match) {
+  if (match == kNoMatch) return 0;
+  if (match == kEmitWithoutPartner || params.unique_build) return 1;
+  return params.dup_counts[match];
 }
 
 __global__ void __launch_bounds__(kJoinThreads) join_probe_count_kernel(const ProbeParams params) {
   __shared__ uint32_t s_histogram[kMaxPartitions];
+  const bool build_has_nulls = params.flags[1] != 0;
+  const bool unique = params.unique_build != 0;
+  const uint32_t lane = threadIdx.x & 31;
   for (uint32_t tile = blockIdx.x; tile < params.probe.tile_count; tile += gridDim.x) {
     for (uint32_t p = threadIdx.x; p < params.partition_count; p += kJoinThreads) s_histogram[p] = 0;
     __syncthreads();
+    const TileRef ref = tile_ref(params.probe, tile);
+    const DevSegment segment = params.probe.tile_map ? params.probe.segments[ref.chunk] : DevSegment{};
+    const size_t tile_slot0 = static_cast<size_t>(tile) * kJoinTileRows;
+#pragma unroll 4
     for (uint32_t index = threadIdx.x; index < kJoinTileRows; index += kJoinThreads) {
-      const KeyAt row = key_at(params.probe, tile, index);
-      uint32_t match;
-      const uint32_t emit = probe_one(params, row, match);
-      if (row.valid) {
-        params.matches[row.position] = match;
-        if (!params.unique_build) params.emit_counts[row.position] = emit;
+      long long key = 0;
+      bool is_null = false;
+      const bool valid = load_key1(params.probe, ref, segment, index, key, is_null);
+      uint32_t match = kNoMatch;
+      if (valid) {
+        const uint32_t slot = (!is_null && params.table.slots) ? table_find(params.table, key) : kNoMatch;
+        match = probe_match_resolved(params, slot, is_null, build_has_nulls);
       }
-      const uint32_t partition = row.valid ? partition_of(params, row) : 0;
+      const uint32_t partition = static_cast<uint32_t>(static_cast<unsigned long long>(key)) & params.partition_mask;
+      params.matches[tile_slot0 + index] = match;
+      params.partitions[tile_slot0 + index] = static_cast<uint8_t>(partition);
       // one shared-memory atomic per distinct partition in the warp
+      const uint32_t emit = emitted_rows(params, match);
       const uint32_t peers = __match_any_sync(kFullMask, partition);
-      uint32_t total = emit;
-      if (params.unique_build) {
+      uint32_t total;
+      if (unique) {
         total = __popc(__ballot_sync(kFullMask, emit != 0) & peers);
       } else {
-        // sum over the peer group
-        uint32_t sum = 0;
+        total = 0;
         uint32_t remaining = peers;
         while (remaining) {
           const int source_lane = __ffs(remaining) - 1;
-          sum += __shfl_sync(peers, emit, source_lane);
+          total += __shfl_sync(peers, emit, source_lane);
           remaining &= remaining - 1;
         }
-        total = sum;
       }
-      const uint32_t lane = threadIdx.x & 31;
       if (lane == static_cast<uint32_t>(__ffs(peers) - 1) && total) atomicAdd(&s_histogram[partition], total);
     }
     __syncthreads();
@@ -459,42 +600,38 @@ __global__ void __launch_bounds__(kJoinThreads) join_probe_write_kernel(const Pr
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lanes_below = (1u << lane) - 1u;
   const bool emit_build = params.out_build != nullptr;
+  const bool unique = params.unique_build != 0;
 
   for (uint32_t tile = blockIdx.x; tile < params.probe.tile_count; tile += gridDim.x) {
     for (uint32_t p = lane; p < params.partition_count; p += 32) s_warp_histogram[warp][p] = 0;
     __syncwarp();
-    // pass 1: per-warp histogram of emitted rows (each warp owns kJoinRowsPerWarp contiguous positions)
-    for (uint32_t step = 0; step < kJoinRowsPerWarp / 32; ++step) {
-      const uint32_t index = warp * kJoinRowsPerWarp + step * 32 + lane;
-      const KeyAt row = key_at(params.probe, tile, index);
-      uint32_t emit = 0;
-      if (row.valid) {
-        emit = params.unique_build ? 0u : params.emit_counts[row.position];
-        if (params.unique_build) {
-          uint32_t match;
-          // re-derive from the stored match: emitted iff a match exists or the mode emits unmatched rows
-          match = params.matches[row.position];
-          const int32_t mode = params.mode;
-          if (mode == HYB_JOIN_INNER) {
-            emit = match != kNoMatch;
-          } else {
-            KeyAt copy = row;
-            uint32_t ignored;
-            emit = probe_one(params, copy, ignored);
+    const TileRef ref = tile_ref(params.probe, tile);
+    const size_t warp_slot0 = static_cast<size_t>(tile) * kJoinTileRows + warp * kJoinRowsPerWarp;
+    // pass 1: emitted rows per (warp, partition); each lane takes 16 consecutive probe slots of the warp's 512
+    {
+      const uint32_t* match_in = params.matches + warp_slot0 + lane * 16;
+      const uint4 bytes = *reinterpret_cast<const uint4*>(params.partitions + warp_slot0 + lane * 16);
+      const uint32_t words[4] = {bytes.x, bytes.y, bytes.z, bytes.w};
+      uint32_t run_partition = 0, run_count = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 m = *reinterpret_cast<const uint4*>(match_in + 4 * q);
+        const uint32_t four[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t emit = emitted_rows(params, four[j]);
+          const uint32_t partition = (words[q] >> (8 * j)) & 0xFFu;
+          if (emit) {
+            if (partition != run_partition && run_count) {
+              atomicAdd(&s_warp_histogram[warp][run_partition], run_count);
+              run_count = 0;
+            }
+            run_partition = partition;
+            run_count += emit;
           }
         }
       }
-      const uint32_t partition = row.valid ? partition_of(params, row) : 0;
-      const uint32_t peers = __match_any_sync(kFullMask, partition);
-      uint32_t sum = 0;
-      uint32_t remaining = peers;
-      while (remaining) {
-        const int source_lane = __ffs(remaining) - 1;
-        sum += __shfl_sync(peers, emit, source_lane);
-        remaining &= remaining - 1;
-      }
-      if (lane == static_cast<uint32_t>(__ffs(peers) - 1) && sum) s_warp_histogram[warp][partition] += sum;
-      __syncwarp();
+      if (run_count) atomicAdd(&s_warp_histogram[warp][run_partition], run_count);
     }
     __syncthreads();
     // start of every (warp, partition) run inside this tile's (partition, tile) run
@@ -507,56 +644,59 @@ __global__ void __launch_bounds__(kJoinThreads) join_probe_write_kernel(const Pr
       }
     }
     __syncthreads();
-    // pass 2: ranks and writes, in position order inside each warp
+    // pass 2: ranks and writes, 32 consecutive probe slots per step so that lane order == probe order
     for (uint32_t step = 0; step < kJoinRowsPerWarp / 32; ++step) {
       const uint32_t index = warp * kJoinRowsPerWarp + step * 32 + lane;
-      const KeyAt row = key_at(params.probe, tile, index);
-      uint32_t emit = 0, match = kNoMatch;
-      if (row.valid) {
-        match = params.matches[row.position];
-        if (params.unique_build) {
-          if (params.mode == HYB_JOIN_INNER) {
-            emit = match != kNoMatch;
-          } else {
-            uint32_t ignored;
-            emit = probe_one(params, row, ignored);
-          }
-        } else {
-          emit = params.emit_counts[row.position];
+      const uint32_t match = params.matches[warp_slot0 + step * 32 + lane];
+      const uint32_t partition = params.partitions[warp_slot0 + step * 32 + lane];
+      const uint32_t emit = emitted_rows(params, match);
+      const uint32_t peers = __match_any_sync(kFullMask, partition);
+      uint32_t before, sum;
+      if (unique) {
+        const uint32_t emitting = __ballot_sync(kFullMask, emit != 0) & peers;
+        before = __popc(emitting & lanes_below);
+        sum = __popc(emitting);
+      } else {
+        before = 0;
+        sum = 0;
+        uint32_t remaining = peers;
+        while (remaining) {
+          const int source_lane = __ffs(remaining) - 1;
+          const uint32_t value = __shfl_sync(peers, emit, source_lane);
+          if (static_cast<uint32_t>(source_lane) < lane) before += value;
+          sum += value;
+          remaining &= remaining - 1;
         }
       }
-      const uint32_t partition = row.valid ? partition_of(params, row) : 0;
-      const uint32_t peers = __match_any_sync(kFullMask, partition);
-      uint32_t before = 0, sum = 0;
-      uint32_t remaining = peers;
-      while (remaining) {
-        const int source_lane = __ffs(remaining) - 1;
-        const uint32_t value = __shfl_sync(peers, emit, source_lane);
-        if (static_cast<uint32_t>(source_lane) < lane) before += value;
-        sum += value;
-        remaining &= remaining - 1;
-      }
-      (void)lanes_below;
       const unsigned long long base = s_start[warp][partition];
       __syncwarp();
       if (lane == static_cast<uint32_t>(__ffs(peers) - 1) && sum) s_start[warp][partition] = base + sum;
       __syncwarp();
       if (emit) {
-        unsigned long long at = base + before;
-        if (match == kNoMatch || !emit_build) {
-          // unmatched outer row (NULL partner) or a Semi/Anti row
+        const unsigned long long at = base + before;
+        if (at + emit > params.out_capacity) {
+          *params.overflow = 1;
+          continue;
+        }
+        hyb_row_id probe_row;
+        if (params.probe.tile_map) {
+          probe_row = hyb_row_id{ref.chunk, ref.row0 + index};
+        } else {
+          probe_row = params.probe.filter[ref.first_position + index];
+        }
+        if (match == kEmitWithoutPartner) {
           if (emit_build) st_stream_v2(params.out_build + at, HYB_INVALID_CHUNK_ID, HYB_INVALID_CHUNK_OFFSET);
-          st_stream_v2(params.out_probe + at, row.row_id.chunk_id, row.row_id.chunk_offset);
-        } else if (params.unique_build) {
+          st_stream_v2(params.out_probe + at, probe_row.chunk_id, probe_row.chunk_offset);
+        } else if (unique) {
           const hyb_row_id build_row = position_to_row_id(params.build, match);
           st_stream_v2(params.out_build + at, build_row.chunk_id, build_row.chunk_offset);
-          st_stream_v2(params.out_probe + at, row.row_id.chunk_id, row.row_id.chunk_offset);
+          st_stream_v2(params.out_probe + at, probe_row.chunk_id, probe_row.chunk_offset);
         } else {
           const unsigned long long first = params.dup_offsets[match];
           for (uint32_t j = 0; j < emit; ++j) {
             const hyb_row_id build_row = position_to_row_id(params.build, params.dup_positions[first + j]);
             st_stream_v2(params.out_build + at + j, build_row.chunk_id, build_row.chunk_offset);
-            st_stream_v2(params.out_probe + at + j, row.row_id.chunk_id, row.row_id.chunk_offset);
+            st_stream_v2(params.out_probe + at + j, probe_row.chunk_id, probe_row.chunk_offset);
           }
         }
       }
@@ -606,6 +746,14 @@ static int prepare_side(hyb_context* context, const hyb_join_side* side, SideInf
   source.chunk_row_start = reinterpret_cast<const unsigned long long*>(out->table->d_chunk_row_start);
   source.chunk_count = chunk_count;
   source.uniform_chunk_rows = (out->table->uniform_chunks && chunk_count) ? out->table->chunk_rows[0] : 0;
+  if (source.uniform_chunk_rows) {
+    // d = rows: shift = ceil(log2 d); magic = floor(2^32 * (2^shift - d) / d) + 1
+    const uint64_t d = source.uniform_chunk_rows;
+    uint32_t shift = 0;
+    while ((uint64_t{1} << shift) < d) ++shift;
+    source.uniform_shift = shift;
+    source.uniform_magic = shift == 0 ? 0 : static_cast<uint32_t>(((uint64_t{1} << 32) * ((uint64_t{1} << shift) - d)) / d + 1);
+  }
   if (side->filter) {
     out->filter = find_pos_list(context, side->filter);
     HYB_CHECK(out->filter, HYB_ERR_NOT_FOUND, "unknown filter handle");
@@ -663,8 +811,8 @@ int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const h
   SideInfo build, probe;
   HYB_TRY(prepare_side(context, build_side, &build));
   HYB_TRY(prepare_side(context, probe_side, &probe));
-  HYB_CHECK(build.positions < 0xFFFFFFFFull && probe.positions < 0xFFFFFFFFull, HYB_ERR_UNSUPPORTED,
-            "more than 2^32 - 1 rows per join side");
+  HYB_CHECK(build.positions < 0xFFFFFFF0ull && probe.positions < 0xFFFFFFF0ull, HYB_ERR_UNSUPPORTED,
+            "more than 2^32 - 16 rows per join side");
   if (radix_bits < 0) radix_bits = calculate_radix_bits(build.positions);
   HYB_CHECK(radix_bits <= 8, HYB_ERR_INVALID, "radix_bits must be <= 8 (join_hash.cpp:113)");
   const uint32_t partition_count = 1u << radix_bits;
@@ -678,19 +826,19 @@ int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const h
   // ---- build -----------------------------------------------------------------------------------------------------
   uint64_t bucket_count = 1;
   while (bucket_count * 2 < build.positions) bucket_count <<= 1;  // >= positions / 2 buckets -> load factor <= 0.5
-  HYB_CHECK(bucket_count * 4 < 0xFFFFFFFFull, HYB_ERR_UNSUPPORTED, "build side too large for 32-bit slot indexes");
+  HYB_CHECK(bucket_count * 4 < 0xFFFFFFF0ull, HYB_ERR_UNSUPPORTED, "build side too large for 32-bit slot indexes");
   const uint64_t slot_count = bucket_count * 4;
   void* slots = nullptr;
   void* wide_keys = nullptr;
-  void* flags = nullptr;
+  void* control = nullptr;  // [0] duplicate keys, [1] NULL build keys, [2] output overflow, [4..5] total (u64)
   HYB_TRY(device_alloc(context, sizeof(uint64_t) * slot_count, &slots));
   HYB_CUDA(cudaMemsetAsync(slots, 0xFF, sizeof(uint64_t) * slot_count, stream));
-  HYB_TRY(device_alloc(context, sizeof(uint32_t) * 4, &flags));
-  HYB_CUDA(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * 4, stream));
+  HYB_TRY(device_alloc(context, 64, &control));
+  HYB_CUDA(cudaMemsetAsync(control, 0, 64, stream));
+  auto* flags = static_cast<uint32_t*>(control);
+  auto* total_slot = reinterpret_cast<unsigned long long*>(flags + 4);
   if (wide) {
     HYB_TRY(device_alloc(context, sizeof(long long) * std::max<uint64_t>(build.positions, 1), &wide_keys));
-    // 0x80.. pattern cannot equal a key whose low 32 bits matched a slot unless it is the key itself; positions that
-    // are never written (NULL keys) are never referenced by a slot.
     HYB_CUDA(cudaMemsetAsync(wide_keys, 0x80, sizeof(long long) * std::max<uint64_t>(build.positions, 1), stream));
   }
   HashTable table{};
@@ -698,31 +846,110 @@ int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const h
   table.bucket_mask = static_cast<uint32_t>(bucket_count - 1);
   table.wide_keys = static_cast<const long long*>(wide_keys);
   const uint32_t build_grid = std::max<uint32_t>(1, std::min<uint32_t>(build.source.tile_count, context->sm_count * 8));
+  timing_kernel_begin(context);
   if (build.source.tile_count) {
     BuildParams build_params{};
     build_params.source = build.source;
     build_params.table = table;
     build_params.wide_keys_out = static_cast<long long*>(wide_keys);
-    build_params.flags = static_cast<uint32_t*>(flags);
+    build_params.flags = flags;
     join_build_kernel<<<build_grid, kJoinThreads, 0, stream>>>(build_params);
     HYB_CUDA(cudaGetLastError());
     ++launches;
   }
-  uint32_t host_flags[4] = {0, 0, 0, 0};
-  HYB_CUDA(cudaMemcpyAsync(host_flags, flags, sizeof(host_flags), cudaMemcpyDeviceToHost, stream));
-  HYB_CUDA(cudaStreamSynchronize(stream));
-  const bool has_duplicates = host_flags[0] != 0;
-  const bool build_has_nulls = host_flags[1] != 0;
 
+  // ---- probe -----------------------------------------------------------------------------------------------------
+  auto result = std::make_unique<JoinResult>();
+  result->mode = mode;
+  result->radix_bits = radix_bits;
+  result->partition_count = partition_count;
+  result->stream = stream;
+  void* partition_offsets = nullptr;
+  HYB_TRY(device_alloc(context, sizeof(uint64_t) * (size_t{partition_count} + 2), &partition_offsets));
+  result->d_partition_offsets = static_cast<uint64_t*>(partition_offsets);
+  HYB_CUDA(cudaMemsetAsync(partition_offsets, 0, sizeof(uint64_t) * (size_t{partition_count} + 2), stream));
+
+  const uint32_t probe_tiles = probe.source.tile_count;
+  const size_t probe_slots = size_t{probe_tiles} * kJoinTileRows;
+  void* matches = nullptr;
+  void* partitions = nullptr;
+  void* histogram = nullptr;
+  void* run_starts = nullptr;
   void* dup_counts = nullptr;
   void* dup_offsets = nullptr;
   void* dup_positions = nullptr;
-  const bool need_positions = has_duplicates && !semi_or_anti;
-  if (need_positions) {
+  const size_t histogram_entries = size_t{partition_count} * probe_tiles;
+  ProbeParams params{};
+  uint32_t host_control[8] = {};
+  if (probe_tiles) {
+    HYB_TRY(device_alloc(context, sizeof(uint32_t) * probe_slots, &matches));
+    HYB_TRY(device_alloc(context, probe_slots, &partitions));
+    HYB_TRY(device_alloc(context, sizeof(uint32_t) * histogram_entries, &histogram));
+    HYB_TRY(device_alloc(context, sizeof(uint64_t) * histogram_entries, &run_starts));
+    params.probe = probe.source;
+    params.build = build.source;
+    params.table = table;
+    if (build.source.tile_count == 0) params.table.slots = nullptr;
+    params.mode = mode;
+    params.partition_mask = partition_count - 1;
+    params.partition_count = partition_count;
+    params.unique_build = 1;  // optimistic: a flag raised by the build kernel sends us to the position-list path below
+    params.build_is_empty = build.positions == 0;
+    params.flags = flags;
+    params.matches = static_cast<uint32_t*>(matches);
+    params.partitions = static_cast<uint8_t*>(partitions);
+    params.histogram = static_cast<uint32_t*>(histogram);
+    params.run_starts = static_cast<const unsigned long long*>(run_starts);
+    params.overflow = flags + 2;
+  }
+  const uint32_t probe_grid = std::max<uint32_t>(1, std::min<uint32_t>(probe_tiles, context->sm_count * 6));
+
+  const auto run_probe = [&](uint64_t capacity) -> int {
+    // count -> scan -> write, all queued without a host round trip; `capacity` output rows are pre-allocated
+    join_probe_count_kernel<<<probe_grid, kJoinThreads, 0, stream>>>(params);
+    HYB_CUDA(cudaGetLastError());
+    HYB_TRY(run_exclusive_scan(context, static_cast<uint32_t*>(histogram), static_cast<unsigned long long*>(run_starts),
+                               histogram_entries, total_slot));
+    if (result->d_probe) cudaFreeAsync(result->d_probe, stream);
+    if (result->d_build) cudaFreeAsync(result->d_build, stream);
+    result->d_probe = nullptr;
+    result->d_build = nullptr;
+    void* out_probe = nullptr;
+    void* out_build = nullptr;
+    HYB_TRY(device_alloc(context, sizeof(hyb_row_id) * std::max<uint64_t>(capacity, 1), &out_probe));
+    if (!semi_or_anti) HYB_TRY(device_alloc(context, sizeof(hyb_row_id) * std::max<uint64_t>(capacity, 1), &out_build));
+    result->d_probe = static_cast<hyb_row_id*>(out_probe);
+    result->d_build = static_cast<hyb_row_id*>(out_build);
+    result->capacity = capacity;
+    params.out_probe = result->d_probe;
+    params.out_build = result->d_build;
+    params.out_capacity = capacity;
+    join_probe_write_kernel<<<probe_grid, kJoinThreads, 0, stream>>>(params);
+    HYB_CUDA(cudaGetLastError());
+    join_partition_offsets_kernel<<<(partition_count + 1 + 127) / 128, 128, 0, stream>>>(
+        static_cast<const unsigned long long*>(run_starts), total_slot, partition_count, probe_tiles,
+        reinterpret_cast<unsigned long long*>(result->d_partition_offsets));
+    HYB_CUDA(cudaGetLastError());
+    launches += 4;
+    return HYB_OK;
+  };
+
+  if (probe_tiles) {
+    // With a unique build side every probe row emits at most one output row: probe.positions rows always suffice.
+    HYB_TRY(run_probe(probe.positions));
+  }
+  timing_kernel_end(context);
+  HYB_CUDA(cudaMemcpyAsync(host_control, control, sizeof(host_control), cudaMemcpyDeviceToHost, stream));
+  HYB_CUDA(cudaStreamSynchronize(stream));  // the only host round trip of the operator (unique build side)
+  const bool has_duplicates = host_control[0] != 0;
+
+  if (has_duplicates && !semi_or_anti && probe_tiles) {
+    // Duplicate build keys: build the position lists (PosHashTable::finalize, join_hash_steps.hpp:147-175) and probe again.
     HYB_TRY(device_alloc(context, sizeof(uint32_t) * slot_count * 2, &dup_counts));  // counts | cursors
     HYB_CUDA(cudaMemsetAsync(dup_counts, 0, sizeof(uint32_t) * slot_count * 2, stream));
     HYB_TRY(device_alloc(context, sizeof(uint64_t) * slot_count, &dup_offsets));
     HYB_TRY(device_alloc(context, sizeof(uint32_t) * std::max<uint64_t>(build.positions, 1), &dup_positions));
+    timing_kernel_begin(context);
     join_count_duplicates_kernel<<<build_grid, kJoinThreads, 0, stream>>>(build.source, table, static_cast<uint32_t*>(dup_counts));
     HYB_CUDA(cudaGetLastError());
     HYB_TRY(run_exclusive_scan(context, static_cast<uint32_t*>(dup_counts), static_cast<unsigned long long*>(dup_offsets),
@@ -736,93 +963,30 @@ int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const h
         static_cast<uint32_t*>(dup_positions));
     HYB_CUDA(cudaGetLastError());
     launches += 4;
-  }
-
-  // ---- probe -----------------------------------------------------------------------------------------------------
-  auto result = std::make_unique<JoinResult>();
-  result->mode = mode;
-  result->radix_bits = radix_bits;
-  result->partition_count = partition_count;
-  result->stream = stream;
-  void* partition_offsets = nullptr;
-  HYB_TRY(device_alloc(context, sizeof(uint64_t) * (size_t{partition_count} + 2), &partition_offsets));
-  result->d_partition_offsets = static_cast<uint64_t*>(partition_offsets);
-  unsigned long long* total_slot = reinterpret_cast<unsigned long long*>(result->d_partition_offsets) + partition_count + 1;
-
-  // AntiNullAsTrue: a NULL on the build side means no tuple can be emitted (join_hash.cpp:471-483).
-  const bool early_out = mode == HYB_JOIN_ANTI_NULL_AS_TRUE && build_has_nulls;
-  const uint32_t probe_tiles = early_out ? 0 : probe.source.tile_count;
-  uint64_t output_capacity = 0;
-
-  if (probe_tiles == 0) {
-    HYB_CUDA(cudaMemsetAsync(partition_offsets, 0, sizeof(uint64_t) * (size_t{partition_count} + 2), stream));
-    timing_kernel_begin(context);
-    timing_kernel_end(context);
-  } else {
-    void* matches = nullptr;
-    void* emit_counts = nullptr;
-    void* histogram = nullptr;
-    void* run_starts = nullptr;
-    const size_t histogram_entries = size_t{partition_count} * probe_tiles;
-    HYB_TRY(device_alloc(context, sizeof(uint32_t) * std::max<uint64_t>(probe.positions, 1), &matches));
-    if (need_positions) HYB_TRY(device_alloc(context, sizeof(uint32_t) * std::max<uint64_t>(probe.positions, 1), &emit_counts));
-    HYB_TRY(device_alloc(context, sizeof(uint32_t) * histogram_entries, &histogram));
-    HYB_TRY(device_alloc(context, sizeof(uint64_t) * histogram_entries, &run_starts));
-
-    ProbeParams params{};
-    params.probe = probe.source;
-    params.build = build.source;
-    params.table = table;
-    if (build.source.tile_count == 0) params.table.slots = nullptr;
-    params.mode = mode;
-    params.partition_mask = partition_count - 1;
-    params.partition_count = partition_count;
-    params.unique_build = need_positions ? 0 : 1;
-    params.build_is_empty = build.positions == 0;
+    params.unique_build = 0;
     params.dup_counts = static_cast<const uint32_t*>(dup_counts);
     params.dup_offsets = static_cast<const unsigned long long*>(dup_offsets);
     params.dup_positions = static_cast<const uint32_t*>(dup_positions);
-    params.matches = static_cast<uint32_t*>(matches);
-    params.emit_counts = static_cast<uint32_t*>(emit_counts);
-    params.histogram = static_cast<uint32_t*>(histogram);
-    params.run_starts = static_cast<const unsigned long long*>(run_starts);
-
-    const uint32_t probe_grid = std::min<uint32_t>(probe_tiles, context->sm_count * 6);
-    timing_kernel_begin(context);
+    // size the output exactly: count + scan, read the total, then write
     join_probe_count_kernel<<<probe_grid, kJoinThreads, 0, stream>>>(params);
     HYB_CUDA(cudaGetLastError());
     HYB_TRY(run_exclusive_scan(context, static_cast<uint32_t*>(histogram), static_cast<unsigned long long*>(run_starts),
                                histogram_entries, total_slot));
-    // The output size is data dependent: read it back to size the PosLists exactly.
     uint64_t total = 0;
     HYB_CUDA(cudaMemcpyAsync(&total, total_slot, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
     HYB_CUDA(cudaStreamSynchronize(stream));
-    output_capacity = total;
-    void* out_probe = nullptr;
-    void* out_build = nullptr;
-    HYB_TRY(device_alloc(context, sizeof(hyb_row_id) * std::max<uint64_t>(total, 1), &out_probe));
-    if (!semi_or_anti) HYB_TRY(device_alloc(context, sizeof(hyb_row_id) * std::max<uint64_t>(total, 1), &out_build));
-    result->d_probe = static_cast<hyb_row_id*>(out_probe);
-    result->d_build = static_cast<hyb_row_id*>(out_build);
-    params.out_probe = result->d_probe;
-    params.out_build = result->d_build;
-    join_probe_write_kernel<<<probe_grid, kJoinThreads, 0, stream>>>(params);
-    HYB_CUDA(cudaGetLastError());
+    HYB_CUDA(cudaMemsetAsync(flags + 2, 0, sizeof(uint32_t), stream));
+    HYB_TRY(run_probe(total));
     timing_kernel_end(context);
-    join_partition_offsets_kernel<<<(partition_count + 1 + 127) / 128, 128, 0, stream>>>(
-        static_cast<const unsigned long long*>(run_starts), total_slot, partition_count, probe_tiles,
-        reinterpret_cast<unsigned long long*>(result->d_partition_offsets));
-    HYB_CUDA(cudaGetLastError());
-    launches += 4;
-    device_free(context, matches);
-    device_free(context, emit_counts);
-    device_free(context, histogram);
-    device_free(context, run_starts);
+    HYB_CUDA(cudaStreamSynchronize(stream));
   }
-  result->capacity = output_capacity;
+
+  device_free(context, matches);
+  device_free(context, partitions);
+  device_free(context, histogram);
+  device_free(context, run_starts);
   device_free(context, slots);
   device_free(context, wide_keys);
-  device_free(context, flags);
   device_free(context, dup_counts);
   device_free(context, dup_offsets);
   device_free(context, dup_positions);
@@ -843,7 +1007,8 @@ int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const h
     return bytes;
   };
   timing_end(context, launches, key_bytes(build) + key_bytes(probe), probe.positions, 0);
-  timing_output_count(context, reinterpret_cast<const uint64_t*>(total_slot), semi_or_anti ? 8 : 16);
+  timing_output_count(context, result->d_partition_offsets + partition_count, semi_or_anti ? 8 : 16);
+  device_free(context, control);
 
   const auto handle = context->next_handle++;
   context->join_results.emplace(handle, std::move(result));

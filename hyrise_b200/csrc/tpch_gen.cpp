@@ -47,6 +47,7 @@ struct BlockAllocator {
   hyb_tpch_free_fn free_fn;
   std::mutex mutex;
   std::vector<std::pair<char*, size_t>> blocks;
+  std::vector<size_t> used;  // bytes handed out per block
   size_t offset = 0;
   size_t total = 0;
 
@@ -59,10 +60,12 @@ struct BlockAllocator {
       if (!base) return nullptr;
       std::memset(base, 0, size);
       blocks.emplace_back(base, size);
+      used.push_back(0);
       offset = 0;
     }
     void* ptr = blocks.back().first + offset;
     offset += need;
+    used.back() = offset;
     total += need;
     return ptr;
   }
@@ -408,6 +411,19 @@ int hyb_tpch_char_dictionary(const hyb_tpch* tables, uint32_t column, uint32_t c
   if (column >= store.chars.size() || chunk >= store.chars[column].size()) return HYB_ERR_INVALID;
   *out_chars = store.chars[column][chunk].data();
   *out_size = static_cast<uint32_t>(store.chars[column][chunk].size());
+  return HYB_OK;
+}
+
+int hyb_tpch_host_blocks(const hyb_tpch* tables, hyb_host_block* out_blocks, uint32_t* out_count) {
+  if (!tables || !out_count) return HYB_ERR_INVALID;
+  const auto& memory = tables->memory;
+  if (out_blocks) {
+    for (size_t index = 0; index < memory.blocks.size(); ++index) {
+      out_blocks[index].base = memory.blocks[index].first;
+      out_blocks[index].bytes = memory.used[index];
+    }
+  }
+  *out_count = static_cast<uint32_t>(memory.blocks.size());
   return HYB_OK;
 }
 

@@ -223,6 +223,22 @@ class DeviceContext:
         check(self.lib.hyb_table_upload(self.ptr, holder.pointer(), C.byref(handle)))
         return DeviceTable(self, handle.value, table, holder)
 
+    def upload_blocks(self, blocks) -> int:
+        """hyb_blocks_upload: DMA whole host arena blocks; returns the block-set handle."""
+        array = (capi.HostBlock * max(len(blocks), 1))(*blocks)
+        handle = C.c_uint64()
+        check(self.lib.hyb_blocks_upload(self.ptr, array, len(blocks), C.byref(handle)))
+        return handle.value
+
+    def upload_from_blocks(self, table, block_set: int) -> DeviceTable:
+        holder = table.view()
+        handle = C.c_uint64()
+        check(self.lib.hyb_table_upload_from_blocks(self.ptr, holder.pointer(), block_set, C.byref(handle)))
+        return DeviceTable(self, handle.value, table, holder)
+
+    def free_blocks(self, block_set: int) -> None:
+        check(self.lib.hyb_blocks_free(self.ptr, block_set))
+
     # operators ---------------------------------------------------------------------------------------------------
     def table_scan(self, table: DeviceTable, predicate: Predicate, input_filter: DevicePosList | None = None,
                    ) -> DevicePosList:

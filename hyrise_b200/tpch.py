@@ -46,6 +46,7 @@ def load() -> C.CDLL:
                                                  C.POINTER(C.c_uint32)]
         lib.hyb_tpch_table_bytes.argtypes = [C.c_void_p, C.c_int32]
         lib.hyb_tpch_table_bytes.restype = C.c_uint64
+        lib.hyb_tpch_host_blocks.argtypes = [C.c_void_p, C.POINTER(capi.HostBlock), C.POINTER(C.c_uint32)]
         lib.hyb_tpch_day_number.argtypes = [C.c_int32] * 3
         lib.hyb_tpch_day_number.restype = C.c_int32
         _lib = lib
@@ -155,6 +156,14 @@ class TpchTables:
         view, rows = capi.TableView(), C.c_uint64()
         lib.hyb_tpch_orders(ptr, C.byref(view), C.byref(rows))
         self.orders = GeneratedTable(self, 1, view, rows.value, ORDERS_COLUMNS)
+
+    def host_blocks(self) -> list:
+        """The arena blocks behind all segment buffers (for DeviceContext.upload_blocks)."""
+        count = C.c_uint32()
+        load().hyb_tpch_host_blocks(self.ptr, None, C.byref(count))
+        blocks = (capi.HostBlock * max(count.value, 1))()
+        load().hyb_tpch_host_blocks(self.ptr, blocks, C.byref(count))
+        return [capi.HostBlock(blocks[i].base, blocks[i].bytes) for i in range(count.value)]
 
     def close(self) -> None:
         if self.ptr:

@@ -213,6 +213,25 @@ int hyb_table_upload(hyb_context* context, const hyb_table_view* view, hyb_table
 int hyb_table_create(hyb_context* context, uint32_t column_count, hyb_table_t* out_table);
 int hyb_table_append_chunk(hyb_context* context, hyb_table_t table, const hyb_segment_desc* segments);
 int hyb_table_drop(hyb_context* context, hyb_table_t table);
+
+/*
+ * Arena upload: when the segment buffers of one or more tables live inside a few large host blocks (a pinned
+ * MemoryResource arena, cf. src/lib/memory/default_memory_resource.cpp:29-35 and Chunk::migrate, storage/chunk.hpp:119),
+ * DMA each block ONCE and let tables point into the device copies instead of issuing one copy per segment buffer
+ * (tens of thousands at SF 10). Buffers must be >= 16-byte aligned inside their block and followed by 64 readable bytes.
+ * A buffer of the view that is not inside any block is copied individually, as hyb_table_upload does.
+ */
+typedef struct hyb_host_block {
+  const void* base;
+  uint64_t bytes;
+} hyb_host_block;
+typedef uint64_t hyb_block_set_t;
+int hyb_blocks_upload(hyb_context* context, const hyb_host_block* blocks, uint32_t block_count,
+                      hyb_block_set_t* out_block_set);
+int hyb_table_upload_from_blocks(hyb_context* context, const hyb_table_view* view, hyb_block_set_t block_set,
+                                 hyb_table_t* out_table);
+/* Releases the device copies once no table references them any more. */
+int hyb_blocks_free(hyb_context* context, hyb_block_set_t block_set);
 int hyb_table_info(hyb_context* context, hyb_table_t table, uint32_t* out_chunk_count, uint32_t* out_column_count,
                    uint64_t* out_row_count, uint64_t* out_device_bytes);
 

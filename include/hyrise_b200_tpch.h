@@ -66,6 +66,10 @@ int hyb_tpch_char_dictionary(const hyb_tpch* tables, uint32_t column, uint32_t c
 /* Total bytes of all segment buffers of a table (what an upload moves over PCIe). */
 uint64_t hyb_tpch_table_bytes(const hyb_tpch* tables, int32_t table);
 
+/* The host blocks all segment buffers of both tables live in (for hyb_blocks_upload). out_blocks may be NULL to query
+ * the count; bytes = the used part of each block. */
+int hyb_tpch_host_blocks(const hyb_tpch* tables, hyb_host_block* out_blocks, uint32_t* out_count);
+
 /* days since 1992-01-01 of 'YYYY-MM-DD' */
 int32_t hyb_tpch_day_number(int32_t year, int32_t month, int32_t day);
 
