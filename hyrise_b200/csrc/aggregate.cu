@@ -646,7 +646,7 @@ __device__ __forceinline__ void add_where(long long& accumulator, long long valu
 }
 
 template <int W, int G, int C>
-__global__ void __launch_bounds__(kFastThreads, 2) aggregate_fast_kernel(const FastPlan* __restrict__ plan_ptr) {
+__global__ void __launch_bounds__(kFastThreads, 3) aggregate_fast_kernel(const FastPlan* __restrict__ plan_ptr) {
   using Value = typename WorkType<W>::Value;
   using Accumulator = typename WorkType<W>::Accumulator;
   const FastPlan& plan = *plan_ptr;
@@ -815,6 +815,10 @@ __global__ void __launch_bounds__(kFastThreads, 2) aggregate_fast_kernel(const F
           }
         }
         // slow path: rows whose combination has not been seen in this tile (or every row when combos are unusable)
+        bool any_unresolved = !use_combos;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) any_unresolved = any_unresolved || group_of[j] >= static_cast<int32_t>(kComboOverflow);
+        if (any_unresolved)
 #pragma unroll 1
         for (int j = 0; j < 8; ++j) {
           if (!((mask >> j) & 1u)) continue;
@@ -920,21 +924,39 @@ __global__ void __launch_bounds__(kFastThreads, 2) aggregate_fast_kernel(const F
           }
         }
         if (need_raw) {
+          if (null_bits == 0) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int32_t group = ((null_bits >> j) & 1u) ? -1 : group_of[j];
-            const Accumulator value = static_cast<Accumulator>(values[j]);
+            for (int j = 0; j < 8; ++j) {
+              const Accumulator value = static_cast<Accumulator>(values[j]);
 #pragma unroll
-            for (int g = 0; g < G; ++g) add_where(raw_sum[g][c], value, group, g);
+              for (int g = 0; g < G; ++g) add_where(raw_sum[g][c], value, group_of[j], g);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int32_t group = ((null_bits >> j) & 1u) ? -1 : group_of[j];
+              const Accumulator value = static_cast<Accumulator>(values[j]);
+#pragma unroll
+              for (int g = 0; g < G; ++g) add_where(raw_sum[g][c], value, group, g);
+            }
           }
         }
         if (need_product) {
+          if (product_nulls == 0) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int32_t group = ((product_nulls >> j) & 1u) ? -1 : group_of[j];
-            const Accumulator value = static_cast<Accumulator>(product[j]);
+            for (int j = 0; j < 8; ++j) {
+              const Accumulator value = static_cast<Accumulator>(product[j]);
 #pragma unroll
-            for (int g = 0; g < G; ++g) add_where(product_sum[g][c], value, group, g);
+              for (int g = 0; g < G; ++g) add_where(product_sum[g][c], value, group_of[j], g);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int32_t group = ((product_nulls >> j) & 1u) ? -1 : group_of[j];
+              const Accumulator value = static_cast<Accumulator>(product[j]);
+#pragma unroll
+              for (int g = 0; g < G; ++g) add_where(product_sum[g][c], value, group, g);
+            }
           }
         }
         if ((need_raw && (null_bits & mask)) || (need_product && (product_nulls & mask))) {

@@ -265,27 +265,34 @@ __device__ __forceinline__ unsigned long long pack_slot(uint32_t key_bits, uint3
   return (static_cast<unsigned long long>(value) << 32) | key_bits;
 }
 
-// Returns the slot index holding `key`, or kNoMatch. A bucket with a free slot ends the search (no deletions).
-__device__ __forceinline__ uint32_t table_find(const HashTable& table, long long key) {
+// Looks `key` up. Returns the slot index (kNoMatch if absent) and the slot's value. A bucket with a free slot ends the
+// search (there are no deletions). Written for few instructions: the probe kernel is issue-bound, not bandwidth-bound.
+__device__ __forceinline__ uint32_t table_find(const HashTable& table, long long key, uint32_t& value) {
   const uint32_t key_bits = static_cast<uint32_t>(key);
   uint32_t bucket = bucket_of(key, table.bucket_mask);
   while (true) {
-    const ulonglong2* base = reinterpret_cast<const ulonglong2*>(table.slots + static_cast<size_t>(bucket) * 4);
-    const ulonglong2 a = __ldg(base);
-    const ulonglong2 b = __ldg(base + 1);
-    const unsigned long long slots[4] = {a.x, a.y, b.x, b.y};
-    bool has_empty = false;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (slots[j] == kEmptySlot) {
-        has_empty = true;
-      } else if (static_cast<uint32_t>(slots[j]) == key_bits) {
-        if (!table.wide_keys || table.wide_keys[static_cast<uint32_t>(slots[j] >> 32)] == key) return bucket * 4 + j;
-      }
+    const uint4* base = reinterpret_cast<const uint4*>(table.slots + static_cast<size_t>(bucket) * 4);
+    const uint4 a = __ldg(base);      // {key0, value0, key1, value1}
+    const uint4 b = __ldg(base + 1);  // {key2, value2, key3, value3}
+    // an empty slot has value 0xFFFFFFFF (no entry ever does): 1 bit per slot
+    const uint32_t empty = (a.y == 0xFFFFFFFFu ? 1u : 0u) | (a.w == 0xFFFFFFFFu ? 2u : 0u) | (b.y == 0xFFFFFFFFu ? 4u : 0u) |
+                           (b.w == 0xFFFFFFFFu ? 8u : 0u);
+    uint32_t hits = ((a.x == key_bits ? 1u : 0u) | (a.z == key_bits ? 2u : 0u) | (b.x == key_bits ? 4u : 0u) |
+                     (b.z == key_bits ? 8u : 0u)) & ~empty;
+    while (hits) {
+      const uint32_t e = __ffs(hits) - 1;
+      hits &= hits - 1;
+      value = e == 0 ? a.y : e == 1 ? a.w : e == 2 ? b.y : b.w;
+      if (!table.wide_keys || table.wide_keys[value] == key) return bucket * 4 + e;
     }
-    if (has_empty) return kNoMatch;
+    if (empty) return kNoMatch;
     bucket = (bucket + 1) & table.bucket_mask;
   }
+}
+
+__device__ __forceinline__ uint32_t table_find(const HashTable& table, long long key) {
+  uint32_t value;
+  return table_find(table, key, value);
 }
 
 struct BuildParams {
@@ -516,9 +523,12 @@ struct ProbeParams {
 // Inner/Semi drop NULL probe keys during materialisation; Left/Right and AntiNullAsFalse emit them; AntiNullAsTrue emits
 // them only when the build table is empty, and nothing at all once the build side holds a NULL
 // (join_hash_steps.hpp:711-758, 848-913; join_hash.cpp:471-483).
-__device__ __forceinline__ uint32_t probe_match_resolved(const ProbeParams& params, uint32_t slot, bool is_null,
-                                                         bool build_has_nulls) {
+__device__ __forceinline__ uint32_t probe_match_resolved(const ProbeParams& params, uint32_t slot, uint32_t value,
+                                                         bool is_null, bool build_has_nulls) {
   const int32_t mode = params.mode;
+  if (mode == HYB_JOIN_INNER) {  // the common case first: NULL probe keys were never looked up (slot == kNoMatch)
+    return slot == kNoMatch ? kNoMatch : (params.unique_build ? value : slot);
+  }
   if (mode == HYB_JOIN_ANTI_NULL_AS_TRUE && build_has_nulls) return kNoMatch;
   if (is_null) {
     if (mode == HYB_JOIN_LEFT || mode == HYB_JOIN_RIGHT || mode == HYB_JOIN_ANTI_NULL_AS_FALSE) return kEmitWithoutPartner;
@@ -536,7 +546,7 @@ __device__ __forceinline__ uint32_t probe_match_resolved(const ProbeParams& para
       break;
   }
   if (!found) return (mode == HYB_JOIN_LEFT || mode == HYB_JOIN_RIGHT) ? kEmitWithoutPartner : kNoMatch;
-  return params.unique_build ? static_cast<uint32_t>(params.table.slots[slot] >> 32) : slot;
+  return params.unique_build ? value : slot;
 }
 
 __device__ __forceinline__ uint32_t emitted_rows(const ProbeParams& params, uint32_t match) {
@@ -563,8 +573,9 @@ __global__ void __launch_bounds__(kJoinThreads) join_probe_count_kernel(const Pr
       const bool valid = load_key1(params.probe, ref, segment, index, key, is_null);
       uint32_t match = kNoMatch;
       if (valid) {
-        const uint32_t slot = (!is_null && params.table.slots) ? table_find(params.table, key) : kNoMatch;
-        match = probe_match_resolved(params, slot, is_null, build_has_nulls);
+        uint32_t value = 0;
+        const uint32_t slot = (!is_null && params.table.slots) ? table_find(params.table, key, value) : kNoMatch;
+        match = probe_match_resolved(params, slot, value, is_null, build_has_nulls);
       }
       const uint32_t partition = static_cast<uint32_t>(static_cast<unsigned long long>(key)) & params.partition_mask;
       params.matches[tile_slot0 + index] = match;
@@ -644,11 +655,20 @@ __global__ void __launch_bounds__(kJoinThreads) join_probe_write_kernel(const Pr
       }
     }
     __syncthreads();
-    // pass 2: ranks and writes, 32 consecutive probe slots per step so that lane order == probe order
-    for (uint32_t step = 0; step < kJoinRowsPerWarp / 32; ++step) {
+    // pass 2: ranks and writes, 32 consecutive probe slots per step so that lane order == probe order. All 16 steps'
+    // matches / partitions are fetched up front (independent loads) instead of one dependent round trip per step.
+    constexpr int kSteps = kJoinRowsPerWarp / 32;
+    uint32_t step_match[kSteps], step_partition[kSteps];
+#pragma unroll
+    for (int step = 0; step < kSteps; ++step) {
+      step_match[step] = __ldg(params.matches + warp_slot0 + step * 32 + lane);
+      step_partition[step] = __ldg(params.partitions + warp_slot0 + step * 32 + lane);
+    }
+#pragma unroll
+    for (int step = 0; step < kSteps; ++step) {
       const uint32_t index = warp * kJoinRowsPerWarp + step * 32 + lane;
-      const uint32_t match = params.matches[warp_slot0 + step * 32 + lane];
-      const uint32_t partition = params.partitions[warp_slot0 + step * 32 + lane];
+      const uint32_t match = step_match[step];
+      const uint32_t partition = step_partition[step];
       const uint32_t emit = emitted_rows(params, match);
       const uint32_t peers = __match_any_sync(kFullMask, partition);
       uint32_t before, sum;

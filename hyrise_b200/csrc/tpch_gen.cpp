@@ -404,6 +404,25 @@ int hyb_tpch_date_dictionary(const hyb_tpch* tables, int32_t table, uint32_t col
   return HYB_OK;
 }
 
+int hyb_tpch_value_id_bounds(const hyb_tpch* tables, int32_t table, uint32_t column, const int32_t* day_numbers,
+                             uint32_t value_count, uint32_t* out_bounds) {
+  if (!tables || !day_numbers || !out_bounds) return HYB_ERR_INVALID;
+  const auto& store = table == 0 ? tables->lineitem : tables->orders;
+  if (column >= store.dates.size() || store.dates[column].empty()) return HYB_ERR_INVALID;
+  const auto& dictionaries = store.dates[column];
+  for (size_t chunk = 0; chunk < dictionaries.size(); ++chunk) {
+    const auto& dictionary = dictionaries[chunk];
+    for (uint32_t v = 0; v < value_count; ++v) {
+      const auto lower = std::lower_bound(dictionary.begin(), dictionary.end(), day_numbers[v]);
+      const auto upper = std::upper_bound(dictionary.begin(), dictionary.end(), day_numbers[v]);
+      uint32_t* out = out_bounds + (chunk * value_count + v) * 2;
+      out[0] = lower == dictionary.end() ? HYB_INVALID_VALUE_ID : static_cast<uint32_t>(lower - dictionary.begin());
+      out[1] = upper == dictionary.end() ? HYB_INVALID_VALUE_ID : static_cast<uint32_t>(upper - dictionary.begin());
+    }
+  }
+  return HYB_OK;
+}
+
 int hyb_tpch_char_dictionary(const hyb_tpch* tables, uint32_t column, uint32_t chunk, const char** out_chars,
                              uint32_t* out_size) {
   if (!tables || !out_chars || !out_size) return HYB_ERR_INVALID;

@@ -46,6 +46,8 @@ def load() -> C.CDLL:
                                                  C.POINTER(C.c_uint32)]
         lib.hyb_tpch_table_bytes.argtypes = [C.c_void_p, C.c_int32]
         lib.hyb_tpch_table_bytes.restype = C.c_uint64
+        lib.hyb_tpch_value_id_bounds.argtypes = [C.c_void_p, C.c_int32, C.c_uint32, C.POINTER(C.c_int32), C.c_uint32,
+                                                 C.c_void_p]
         lib.hyb_tpch_host_blocks.argtypes = [C.c_void_p, C.POINTER(capi.HostBlock), C.POINTER(C.c_uint32)]
         lib.hyb_tpch_day_number.argtypes = [C.c_int32] * 3
         lib.hyb_tpch_day_number.restype = C.c_int32
@@ -115,15 +117,13 @@ class GeneratedTable:
         day numbers order like the ISO strings."""
         between = capi.PRED_BETWEEN_INCLUSIVE <= predicate.condition <= capi.PRED_BETWEEN_EXCLUSIVE
         values = [predicate.lower, predicate.upper] if between else [predicate.lower]
-        needles = [day_number(value) if isinstance(value, (str, bytes)) else int(value) for value in values]
-        bounds = np.empty((self.chunk_count, 2 * len(needles)), dtype=np.uint32)
-        for chunk_id in range(self.chunk_count):
-            dictionary = self.date_dictionary(predicate.column_id, chunk_id)
-            for index, needle in enumerate(needles):
-                for offset, side in enumerate(("left", "right")):
-                    position = int(np.searchsorted(dictionary, needle, side=side))
-                    bounds[chunk_id, 2 * index + offset] = capi.INVALID_VALUE_ID if position >= len(dictionary) \
-                        else position
+        needles = (C.c_int32 * len(values))(*[day_number(value) if isinstance(value, (str, bytes)) else int(value)
+                                             for value in values])
+        bounds = np.empty((self.chunk_count, 2 * len(values)), dtype=np.uint32)
+        status = load().hyb_tpch_value_id_bounds(self.owner.ptr, self.table_index, predicate.column_id, needles,
+                                                 len(values), bounds.ctypes.data)
+        if status != 0:
+            raise ValueError("not a date column")
         return bounds
 
 

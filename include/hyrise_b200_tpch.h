@@ -60,6 +60,12 @@ int hyb_tpch_orders(const hyb_tpch* tables, hyb_table_view* out_view, uint64_t* 
 /* Sorted day numbers of the date dictionary of (table, column, chunk): table 0 = lineitem, 1 = orders. */
 int hyb_tpch_date_dictionary(const hyb_tpch* tables, int32_t table, uint32_t column, uint32_t chunk,
                              const int32_t** out_days, uint32_t* out_size);
+/* What the operator shim computes per query for a string column: DictionarySegment::lower_bound / upper_bound
+ * (dictionary_segment.cpp:94-119) of `value_count` date values on every chunk's dictionary. out_bounds receives
+ * chunk_count * 2 * value_count entries laid out [chunk][value][lower, upper] (HYB_INVALID_VALUE_ID past the end) — the
+ * layout hyb_scan_predicate::value_id_bounds expects for value_count 1 (binary) and 2 (between). */
+int hyb_tpch_value_id_bounds(const hyb_tpch* tables, int32_t table, uint32_t column, const int32_t* day_numbers,
+                             uint32_t value_count, uint32_t* out_bounds);
 /* Characters of a one-char string dictionary (l_returnflag / l_linestatus). */
 int hyb_tpch_char_dictionary(const hyb_tpch* tables, uint32_t column, uint32_t chunk, const char** out_chars,
                              uint32_t* out_size);
