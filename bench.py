@@ -203,8 +203,10 @@ def main() -> None:
         if distributed:
             dist.barrier()
 
-    # ---- data: every rank owns its own SF-sized shard (weak scaling); different seeds = different orders ------------
-    tables = TpchTables(args.sf, seed=42 + rank, pinned=not args.no_e2e)
+    # ---- data: every rank owns the shard [rank * orders, (rank + 1) * orders) of one global SF (sf x world) data set
+    #      (weak scaling: the per-GPU work is fixed; key ranges are disjoint, values depend on the global order index)
+    orders_per_rank = int(round(1_500_000 * args.sf))
+    tables = TpchTables(args.sf, seed=42, pinned=not args.no_e2e, first_order=rank * orders_per_rank)
     device = DeviceContext(local_rank)
     lineitem = device.upload(tables.lineitem)
     orders = device.upload(tables.orders)
@@ -224,24 +226,74 @@ def main() -> None:
 
     operators = {"scan": [], "join": [], "aggregate": []}
     launches = [0]
+    torch_device = torch.device("cuda", local_rank)
+    if distributed:
+        from hyrise_b200 import distributed as hd
+        lineitem_chunk_base = hd.chunk_bases(tables.lineitem.chunk_count, torch_device)[rank]
+        orders_chunk_base = hd.chunk_bases(tables.orders.chunk_count, torch_device)[rank]
+        lineitem_row_base = rank * 0  # positions only order groups; per-rank offsets keep them disjoint
+        radix_bits = 8 if args.sf * world >= 4 else 4
+
+    def distributed_join():
+        """materialise {key, RowID} of both sides -> one NCCL all-to-all per side -> local hyb_join_hash on what arrived"""
+        pairs, offsets, build_rows, probe_rows, result = hd.device_distributed_join(
+            device, orders, O_ORDERKEY, lineitem, L_ORDERKEY, radix_bits, orders_chunk_base, lineitem_chunk_base, torch_device)
+        stats = device.last_stats()
+        return pairs, result, stats
+
+    def distributed_q1():
+        """local aggregate_fast_kernel, then the partial groups are exchanged by key hash (one all-to-all) and merged"""
+        functions = [a.function for a in Q1_AGGREGATES]
+
+        def local(decomposed):
+            aggregates = [Aggregate(function, None if function == capi.AGG_COUNT_STAR else Q1_AGGREGATES[original].expression)
+                          for function, original in decomposed]
+            output = device.aggregate_hash(lineitem, Q1_GROUPBY, aggregates, predicates=Q1_PREDICATES)
+            keys = np.zeros((output.group_count, 2), dtype=np.int64)
+            for g, row in enumerate(output.row_ids):
+                keys[g, 0] = tables.lineitem.char_at(L_RETURNFLAG, int(row["chunk_id"]), int(row["chunk_offset"]))
+                keys[g, 1] = tables.lineitem.char_at(L_LINESTATUS, int(row["chunk_id"]), int(row["chunk_offset"]))
+            positions = (np.int64(rank) << 40) + output.row_ids["chunk_id"].astype(np.int64) * capi.DEFAULT_CHUNK_SIZE + \
+                output.row_ids["chunk_offset"].astype(np.int64)
+            values, counts = [], []
+            for index, (function, _) in enumerate(decomposed):
+                raw = output.values[index]
+                values.append(raw.astype(np.float64) if raw.dtype.kind == "f" else raw.astype(np.int64))
+                counts.append(raw.astype(np.int64) if function in (capi.AGG_COUNT, capi.AGG_COUNT_STAR)
+                              else (~output.nulls[index]).astype(np.int64))
+            return hd.PartialGroups(keys, np.zeros_like(keys, dtype=bool), positions, [f for f, _ in decomposed], values, counts)
+
+        outcome = hd.distributed_aggregate(local, functions, torch_device)
+        return outcome
 
     def run_step(record: bool):
         flush_l2()
         scan = device.table_scan(lineitem, SCAN_PREDICATE)
         scan_stats = device.last_stats()
         flush_l2()
-        join = device.join_hash(orders, O_ORDERKEY, lineitem, L_ORDERKEY, capi.JOIN_INNER, -1)
-        join_stats = device.last_stats()
+        if distributed:
+            join_pairs, join, join_stats = distributed_join()
+        else:
+            join = device.join_hash(orders, O_ORDERKEY, lineitem, L_ORDERKEY, capi.JOIN_INNER, -1)
+            join_stats = device.last_stats()
         flush_l2()
-        aggregate = device.aggregate_hash(lineitem, Q1_GROUPBY, Q1_AGGREGATES, predicates=Q1_PREDICATES)
-        aggregate_stats = device.last_stats()
+        if distributed:
+            merged = distributed_q1()
+            aggregate_stats = device.last_stats()
+        else:
+            aggregate = device.aggregate_hash(lineitem, Q1_GROUPBY, Q1_AGGREGATES, predicates=Q1_PREDICATES)
+            aggregate_stats = device.last_stats()
         if record:
             for name, stats in (("scan", scan_stats), ("join", join_stats), ("aggregate", aggregate_stats)):
                 operators[name].append((stats.dominant_kernel_ms, stats.device_ms, stats.algorithmic_bytes, stats.output_rows))
                 launches[0] += stats.kernel_launches
-        result = (scan.info()[0], join.info()[0], aggregate.group_count)
+        if distributed:
+            result = (scan.info()[0], join_pairs, len(merged[0].keys) if merged is not None else 0)
+        else:
+            result = (scan.info()[0], join.info()[0], aggregate.group_count)
         scan.free()
-        join.free()
+        if join is not None:
+            join.free()
         return result
 
     for _ in range(warmup):
@@ -340,7 +392,9 @@ def main() -> None:
             "dtype": "int32 keys / u16 value-IDs / f32 arithmetic, f64 sums", "data": "synthetic",
             "config": {"workload": workload, "lineitem_rows_per_gpu": rows, "orders_rows_per_gpu": tables.orders.row_count,
                        "chunk_size": capi.DEFAULT_CHUNK_SIZE, "l2": "256 MB memset before every operator, inside the timed region",
-                       "parallelism": f"{world} x independent shard (chunk-partitioned scan; join/aggregate per shard)",
+                       "parallelism": (f"{world} ranks: chunk-partitioned scan (no collective); join = radix all-to-all of "
+                                       f"{{key, RowID}} tuples (one per side) + local join; aggregate = local pre-aggregation + "
+                                       f"all-to-all of partial groups") if world > 1 else "1 GPU",
                        "outputs_per_step": {"scan_matches": int(outputs[0]), "join_pairs": int(outputs[1]), "groups": int(outputs[2])}},
             "roofline": roofline, "operators": breakdown, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": launches[0], "clocks": clocks.summary(),

@@ -137,6 +137,7 @@ SYMBOLS = {
     "hyb_table_upload": [_CTX, C.POINTER(TableView), C.POINTER(_U64)],
     "hyb_table_create": [_CTX, _U32, C.POINTER(_U64)],
     "hyb_table_append_chunk": [_CTX, _U64, C.POINTER(SegmentDesc)],
+    "hyb_table_append_chunk_device": [_CTX, _U64, C.POINTER(SegmentDesc)],
     "hyb_table_drop": [_CTX, _U64],
     "hyb_blocks_upload": [_CTX, C.POINTER(HostBlock), _U32, C.POINTER(_U64)],
     "hyb_table_upload_from_blocks": [_CTX, C.POINTER(TableView), _U64, C.POINTER(_U64)],
@@ -152,6 +153,8 @@ SYMBOLS = {
     "hyb_join_result_partition_offsets": [_CTX, _U64, _P],
     "hyb_join_result_copy": [_CTX, _U64, _U64, _U64, _P, _P],
     "hyb_join_result_free": [_CTX, _U64],
+    "hyb_join_side_positions": [_CTX, C.POINTER(JoinSide), C.POINTER(_U64)],
+    "hyb_join_materialize": [_CTX, C.POINTER(JoinSide), _U32, _P, _P],
     "hyb_aggregate_hash": [_CTX, C.POINTER(AggregateQuery), C.POINTER(_U64)],
     "hyb_aggregate_result_info": [_CTX, _U64, C.POINTER(_U64), C.POINTER(_I32)],
     "hyb_aggregate_result_row_ids": [_CTX, _U64, _P],

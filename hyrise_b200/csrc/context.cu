@@ -419,6 +419,10 @@ static int validate_segment(const hyb_segment_desc& desc, uint32_t chunk, uint32
 static int upload_buffer(hyb_context* context, Table* table, const void* host, size_t bytes, const void** out_device) {
   *out_device = nullptr;
   if (host == nullptr) return HYB_OK;
+  if (table->adopting_device_buffers) {
+    *out_device = host;  // hyb_table_append_chunk_device: already a device pointer, borrowed
+    return HYB_OK;
+  }
   if (table->block_set) {
     // arena upload: the buffer already is on the device inside its block's copy
     const void* resident = table->block_set->translate(host, bytes);
@@ -522,6 +526,21 @@ int hyb_table_append_chunk(hyb_context* context, hyb_table_t handle, const hyb_s
   // The source buffers are borrowed only for the duration of the call (probe_null_flags synchronises the stream).
   HYB_TRY(probe_null_flags(context, table, first_segment));
   HYB_CUDA(cudaStreamSynchronize(context->stream));
+  return HYB_OK;
+}
+
+int hyb_table_append_chunk_device(hyb_context* context, hyb_table_t handle, const hyb_segment_desc* segments) {
+  HYB_CHECK(context && segments, HYB_ERR_INVALID, "NULL argument");
+  DeviceGuard guard(context->device);
+  std::lock_guard<std::mutex> lock(context->mutex);
+  auto* table = find_table(context, handle);
+  HYB_CHECK(table, HYB_ERR_NOT_FOUND, "unknown table handle");
+  const size_t first_segment = table->segments.size();
+  table->adopting_device_buffers = true;
+  const int status = append_chunk_locked(context, table, segments);
+  table->adopting_device_buffers = false;
+  HYB_TRY(status);
+  HYB_TRY(probe_null_flags(context, table, first_segment));
   return HYB_OK;
 }
 

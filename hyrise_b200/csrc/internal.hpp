@@ -73,6 +73,7 @@ struct BlockSet {
 
 struct Table {
   std::shared_ptr<BlockSet> block_set;      // set when the segment buffers live in uploaded arena blocks
+  bool adopting_device_buffers = false;     // hyb_table_append_chunk_device in progress: pointers are device pointers
   uint32_t column_count = 0;
   std::vector<uint32_t> chunk_rows;         // rows per chunk
   std::vector<uint64_t> chunk_row_start;    // exclusive prefix, chunk_count + 1 entries

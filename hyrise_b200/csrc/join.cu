@@ -725,6 +725,32 @@ __global__ void __launch_bounds__(kJoinThreads) join_probe_write_kernel(const Pr
   }
 }
 
+// Multi-GPU exchange payload: {key, packed global RowID} per position; NULL keys are marked with RowID -1.
+__global__ void __launch_bounds__(kJoinThreads) join_materialize_kernel(const KeySource source, uint32_t chunk_id_base,
+                                                                        long long* __restrict__ out_keys,
+                                                                        long long* __restrict__ out_row_ids) {
+  for (uint32_t tile = blockIdx.x; tile < source.tile_count; tile += gridDim.x) {
+    const TileRef ref = tile_ref(source, tile);
+    const DevSegment segment = source.tile_map ? source.segments[ref.chunk] : DevSegment{};
+    for (uint32_t index = threadIdx.x; index < kJoinTileRows; index += kJoinThreads) {
+      long long key;
+      bool is_null;
+      if (!load_key1(source, ref, segment, index, key, is_null)) continue;
+      const unsigned long long position = ref.first_position + index;
+      hyb_row_id row_id;
+      if (source.tile_map) {
+        row_id = hyb_row_id{ref.chunk, ref.row0 + index};
+      } else {
+        row_id = source.filter[position];
+      }
+      out_keys[position] = key;
+      out_row_ids[position] = is_null ? -1ll
+                                      : static_cast<long long>(static_cast<unsigned long long>(row_id.chunk_id + chunk_id_base) |
+                                                               (static_cast<unsigned long long>(row_id.chunk_offset) << 32));
+    }
+  }
+}
+
 __global__ void join_partition_offsets_kernel(const unsigned long long* __restrict__ run_starts,
                                               const unsigned long long* __restrict__ total, uint32_t partition_count,
                                               uint32_t tile_count, unsigned long long* __restrict__ out) {
@@ -1033,6 +1059,39 @@ int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const h
   const auto handle = context->next_handle++;
   context->join_results.emplace(handle, std::move(result));
   *out_result = handle;
+  return HYB_OK;
+}
+
+int hyb_join_side_positions(hyb_context* context, const hyb_join_side* side, uint64_t* out_positions) {
+  HYB_CHECK(context && side && out_positions, HYB_ERR_INVALID, "NULL argument");
+  DeviceGuard guard(context->device);
+  std::lock_guard<std::mutex> lock(context->mutex);
+  SideInfo info;
+  HYB_TRY(prepare_side(context, side, &info));
+  *out_positions = info.positions;
+  return HYB_OK;
+}
+
+int hyb_join_materialize(hyb_context* context, const hyb_join_side* side, uint32_t chunk_id_base, void* out_keys_device,
+                         void* out_row_ids_device) {
+  HYB_CHECK(context && side, HYB_ERR_INVALID, "NULL argument");
+  DeviceGuard guard(context->device);
+  std::lock_guard<std::mutex> lock(context->mutex);
+  SideInfo info;
+  HYB_TRY(prepare_side(context, side, &info));
+  HYB_CHECK(info.positions == 0 || (out_keys_device && out_row_ids_device), HYB_ERR_INVALID, "output buffers are NULL");
+  timing_begin(context);
+  timing_kernel_begin(context);
+  if (info.source.tile_count) {
+    const uint32_t grid = std::min<uint32_t>(info.source.tile_count, context->sm_count * 8);
+    join_materialize_kernel<<<grid, kJoinThreads, 0, context->stream>>>(info.source, chunk_id_base,
+                                                                        static_cast<long long*>(out_keys_device),
+                                                                        static_cast<long long*>(out_row_ids_device));
+    HYB_CUDA(cudaGetLastError());
+  }
+  timing_kernel_end(context);
+  timing_end(context, 1, info.positions * 16, info.positions, info.positions);
+  HYB_CUDA(cudaStreamSynchronize(context->stream));  // the caller hands the buffers to NCCL on another stream
   return HYB_OK;
 }
 

@@ -224,6 +224,11 @@ int32_t hyb_tpch_day_number(int32_t year, int32_t month, int32_t day) {
 
 int hyb_tpch_generate(double scale_factor, uint64_t seed, int32_t threads, hyb_tpch_alloc_fn alloc,
                       hyb_tpch_free_fn free_fn, hyb_tpch** out) {
+  return hyb_tpch_generate_shard(scale_factor, seed, 0, threads, alloc, free_fn, out);
+}
+
+int hyb_tpch_generate_shard(double scale_factor, uint64_t seed, uint64_t first_order, int32_t threads,
+                            hyb_tpch_alloc_fn alloc, hyb_tpch_free_fn free_fn, hyb_tpch** out) {
   if (!out || scale_factor <= 0) return HYB_ERR_INVALID;
   auto* tables = new hyb_tpch{};
   tables->memory.alloc = alloc ? alloc : +[](size_t bytes) { return std::malloc(bytes); };
@@ -234,7 +239,7 @@ int hyb_tpch_generate(double scale_factor, uint64_t seed, int32_t threads, hyb_t
   const uint64_t part_count = std::max<uint64_t>(1, static_cast<uint64_t>(std::llround(200'000.0 * scale_factor)));
 
   // Lines per order and their prefix sums at block granularity.
-  const auto lines_of = [&](uint64_t order) { return static_cast<uint32_t>(1 + rng.at(order, 7, 0) % 7); };
+  const auto lines_of = [&](uint64_t order) { return static_cast<uint32_t>(1 + rng.at(order + first_order, 7, 0) % 7); };
   const uint64_t block_count = (order_count + kOrderBlock - 1) / kOrderBlock;
   std::vector<uint64_t> block_rows(block_count + 1, 0);
   run_parallel(block_count, threads, [&](size_t block) {
@@ -278,22 +283,23 @@ int hyb_tpch_generate(double scale_factor, uint64_t seed, int32_t threads, hyb_t
     uint32_t filled = 0;
     while (filled < n) {
       const uint32_t lines = lines_of(order);
-      const int32_t order_date = static_cast<int32_t>(rng.at(order, 7, 1) % kOrderDateRange);
+      const uint64_t global_order = order + first_order;
+      const int32_t order_date = static_cast<int32_t>(rng.at(global_order, 7, 1) % kOrderDateRange);
       for (uint32_t line = 0; line < lines && filled < n; ++line, ++row) {
         if (row < row_begin) continue;
-        const int32_t ship = order_date + 1 + static_cast<int32_t>(rng.at(order, line, 2) % 121);
-        const uint32_t qty = 1 + static_cast<uint32_t>(rng.at(order, line, 3) % 50);
-        const uint32_t disc = static_cast<uint32_t>(rng.at(order, line, 4) % 11);
-        const uint32_t tx = static_cast<uint32_t>(rng.at(order, line, 5) % 9);
-        const uint64_t partkey = 1 + rng.at(order, line, 6) % part_count;
-        const int32_t receipt = ship + 1 + static_cast<int32_t>(rng.at(order, line, 8) % 30);
+        const int32_t ship = order_date + 1 + static_cast<int32_t>(rng.at(global_order, line, 2) % 121);
+        const uint32_t qty = 1 + static_cast<uint32_t>(rng.at(global_order, line, 3) % 50);
+        const uint32_t disc = static_cast<uint32_t>(rng.at(global_order, line, 4) % 11);
+        const uint32_t tx = static_cast<uint32_t>(rng.at(global_order, line, 5) % 9);
+        const uint64_t partkey = 1 + rng.at(global_order, line, 6) % part_count;
+        const int32_t receipt = ship + 1 + static_cast<int32_t>(rng.at(global_order, line, 8) % 30);
         const uint64_t retail_cents = 90000 + (partkey / 10) % 20001 + 100 * (partkey % 1000);  // dss.h retail price
-        orderkey[filled] = order_key(order);
+        orderkey[filled] = order_key(global_order);
         quantity[filled] = static_cast<float>(qty);
         extendedprice[filled] = static_cast<float>(static_cast<double>(qty * retail_cents) / 100.0);
         discount[filled] = static_cast<float>(static_cast<double>(disc) / 100.0);
         tax[filled] = static_cast<float>(static_cast<double>(tx) / 100.0);
-        returnflag[filled] = receipt <= kCutoffDay ? ((rng.at(order, line, 9) & 1) ? 'R' : 'A') : 'N';
+        returnflag[filled] = receipt <= kCutoffDay ? ((rng.at(global_order, line, 9) & 1) ? 'R' : 'A') : 'N';
         linestatus[filled] = ship <= kCutoffDay ? 'F' : 'O';
         shipdate[filled] = static_cast<uint16_t>(ship);
         ++filled;
@@ -351,8 +357,8 @@ int hyb_tpch_generate(double scale_factor, uint64_t seed, int32_t threads, hyb_t
       return;
     }
     for (uint32_t i = 0; i < n; ++i) {
-      keys[i] = order_key(first + i);
-      dates[i] = static_cast<uint16_t>(rng.at(first + i, 7, 1) % kOrderDateRange);
+      keys[i] = order_key(first + i + first_order);
+      dates[i] = static_cast<uint16_t>(rng.at(first + i + first_order, 7, 1) % kOrderDateRange);
     }
     uint64_t bytes = sizeof(int32_t) * n;
     auto* descs = &orders.segments[chunk * HYB_O_COLUMN_COUNT];

@@ -36,6 +36,8 @@ def load() -> C.CDLL:
         lib = C.CDLL(LIB_PATH)
         lib.hyb_tpch_generate.argtypes = [C.c_double, C.c_uint64, C.c_int32, C.c_void_p, C.c_void_p,
                                           C.POINTER(C.c_void_p)]
+        lib.hyb_tpch_generate_shard.argtypes = [C.c_double, C.c_uint64, C.c_uint64, C.c_int32, C.c_void_p, C.c_void_p,
+                                                C.POINTER(C.c_void_p)]
         lib.hyb_tpch_free.argtypes = [C.c_void_p]
         lib.hyb_tpch_free.restype = None
         for name in ("hyb_tpch_lineitem", "hyb_tpch_orders"):
@@ -112,6 +114,15 @@ class GeneratedTable:
             raise ValueError("not a char column")
         return chars.value[: size.value] if size.value else b""
 
+    def value_id_at(self, column_id: int, chunk_id: int, offset: int) -> int:
+        desc = self.segment_desc(chunk_id, column_id)
+        width = {capi.VEC_FIXED_1B: C.c_uint8, capi.VEC_FIXED_2B: C.c_uint16, capi.VEC_FIXED_4B: C.c_uint32}[desc.vector_type]
+        return C.cast(desc.attribute_vector, C.POINTER(width))[offset]
+
+    def char_at(self, column_id: int, chunk_id: int, offset: int) -> int:
+        """Byte value of a one-char string column at a row (group key of l_returnflag / l_linestatus)."""
+        return self.char_dictionary(column_id, chunk_id)[self.value_id_at(column_id, chunk_id, offset)]
+
     def string_value_id_bounds(self, predicate) -> np.ndarray:
         """DictionarySegment::lower_bound / upper_bound per chunk (dictionary_segment.cpp:94-119) for date columns:
         day numbers order like the ISO strings."""
@@ -128,7 +139,8 @@ class GeneratedTable:
 
 
 class TpchTables:
-    def __init__(self, scale_factor: float, seed: int = 42, threads: int = 0, pinned: bool = False):
+    def __init__(self, scale_factor: float, seed: int = 42, threads: int = 0, pinned: bool = False,
+                 first_order: int = 0):
         lib = load()
         self._callbacks = None
         alloc = free = None
@@ -145,7 +157,7 @@ class TpchTables:
             self._callbacks = (ALLOC_FN(_alloc), FREE_FN(_free))
             alloc, free = (C.cast(cb, C.c_void_p) for cb in self._callbacks)
         ptr = C.c_void_p()
-        status = lib.hyb_tpch_generate(scale_factor, seed, threads, alloc, free, C.byref(ptr))
+        status = lib.hyb_tpch_generate_shard(scale_factor, seed, first_order, threads, alloc, free, C.byref(ptr))
         if status != 0:
             raise MemoryError(f"hyb_tpch_generate failed with status {status}")
         self.ptr = ptr

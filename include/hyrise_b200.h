@@ -212,6 +212,10 @@ int hyb_table_upload(hyb_context* context, const hyb_table_view* view, hyb_table
 /* Incremental variant: create an empty table, then append chunks (column_count segments each). */
 int hyb_table_create(hyb_context* context, uint32_t column_count, hyb_table_t* out_table);
 int hyb_table_append_chunk(hyb_context* context, hyb_table_t table, const hyb_segment_desc* segments);
+/* Like hyb_table_append_chunk, but every pointer in `segments` already is a DEVICE pointer on this context's GPU
+ * (e.g. tuples received through the multi-GPU exchange). Nothing is copied; the buffers are borrowed until the table is
+ * dropped and must be 16-byte aligned with 64 readable bytes after their last element. */
+int hyb_table_append_chunk_device(hyb_context* context, hyb_table_t table, const hyb_segment_desc* segments);
 int hyb_table_drop(hyb_context* context, hyb_table_t table);
 
 /*
@@ -305,6 +309,18 @@ int hyb_join_result_partition_offsets(hyb_context* context, hyb_join_result_t re
 int hyb_join_result_copy(hyb_context* context, hyb_join_result_t result, uint64_t begin, uint64_t count,
                          hyb_row_id* out_build_row_ids, hyb_row_id* out_probe_row_ids);
 int hyb_join_result_free(hyb_context* context, hyb_join_result_t result);
+
+/*
+ * Multi-GPU radix exchange, step 1 (materialize_input, join_hash_steps.hpp:274-420, without the Bloom filter): write one
+ * join side as {key, RowID} tuples into caller-provided DEVICE buffers of hyb_join_side_positions() elements each:
+ * out_keys[i] = key as int64, out_row_ids[i] = chunk_id + chunk_id_base | chunk_offset << 32, in row order. Rows with a
+ * NULL key get out_row_ids[i] = -1 (Inner/Semi joins drop them before the exchange). The host layer partitions the
+ * tuples by hash(key) & (world - 1), exchanges them with one all-to-all (NCCL) and joins what it received with
+ * hyb_table_append_chunk_device + hyb_join_hash.
+ */
+int hyb_join_side_positions(hyb_context* context, const hyb_join_side* side, uint64_t* out_positions);
+int hyb_join_materialize(hyb_context* context, const hyb_join_side* side, uint32_t chunk_id_base, void* out_keys_device,
+                         void* out_row_ids_device);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * AggregateHash (with optionally fused scan predicates and Projection arithmetic)

@@ -52,6 +52,10 @@ typedef void (*hyb_tpch_free_fn)(void* ptr);
  */
 int hyb_tpch_generate(double scale_factor, uint64_t seed, int32_t threads, hyb_tpch_alloc_fn alloc,
                       hyb_tpch_free_fn free_fn, hyb_tpch** out);
+/* A shard of a larger data set: the orders with global index first_order + 1 .. first_order + round(1.5 M * scale_factor)
+ * and their lineitems (disjoint key ranges across shards; every value depends on the global order index only). */
+int hyb_tpch_generate_shard(double scale_factor, uint64_t seed, uint64_t first_order, int32_t threads,
+                            hyb_tpch_alloc_fn alloc, hyb_tpch_free_fn free_fn, hyb_tpch** out);
 void hyb_tpch_free(hyb_tpch* tables);
 
 int hyb_tpch_lineitem(const hyb_tpch* tables, hyb_table_view* out_view, uint64_t* out_rows);
