@@ -130,7 +130,7 @@ def main():
             else:
                 assert np.array_equal(values[index].astype(np.int64), expected.values[index].astype(np.int64)), index
         print(f"distributed OK on {world} GPUs: scan {sum(len(g) for g in gathered)} tuples gathered, join pairs "
-              f"{len(expected.probe)}, Q1 groups {len(merged.keys)}")
+              f"{sum(len(p) for p in probe_parts)}, Q1 groups {len(merged.keys)}")
     dist.barrier()
     device.close()
     dist.destroy_process_group()

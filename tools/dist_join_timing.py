@@ -1,0 +1,26 @@
+import os, sys, time
+sys.path.insert(0, ".")
+import numpy as np, torch, torch.distributed as dist
+from hyrise_b200 import capi, distributed as hd
+from hyrise_b200.device import DeviceContext
+from hyrise_b200.tpch import TpchTables, L_ORDERKEY, O_ORDERKEY
+rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr); dist.init_process_group("nccl", device_id=torch.device("cuda", lr)); td = torch.device("cuda", lr)
+sf = float(sys.argv[1]) if len(sys.argv) > 1 else 10.0
+tables = TpchTables(sf, first_order=rank * int(1_500_000 * sf))
+device = DeviceContext(lr)
+lineitem = device.upload(tables.lineitem); orders = device.upload(tables.orders)
+lb = hd.chunk_bases(tables.lineitem.chunk_count, td)[rank]; ob = hd.chunk_bases(tables.orders.chunk_count, td)[rank]
+def sync(): device.synchronize(); torch.cuda.synchronize()
+for i in range(6):
+    sync(); t0 = time.time()
+    bk, br = hd.device_materialize_side(device, orders, O_ORDERKEY, ob, td)
+    pk, pr = hd.device_materialize_side(device, lineitem, L_ORDERKEY, lb, td); sync(); t1 = time.time()
+    bk, br = hd.exchange_tuples_masked(bk, br); pk, pr = hd.exchange_tuples_masked(pk, pr); sync(); t2 = time.time()
+    build = hd.DeviceTupleTable(device, bk, br); probe = hd.DeviceTupleTable(device, pk, pr); sync(); t3 = time.time()
+    result = device.join_hash(build.table, 0, probe.table, 0, capi.JOIN_INNER, 8); st = device.last_stats(); sync(); t4 = time.time()
+    if rank == 0:
+        print(f"materialize {1e3*(t1-t0):.1f} exchange {1e3*(t2-t1):.1f} tables {1e3*(t3-t2):.1f} join wall {1e3*(t4-t3):.1f} "
+              f"kernel {st.dominant_kernel_ms:.2f} op {st.device_ms:.2f} pairs {result.info()[0]} build {build.count} probe {probe.count}", flush=True)
+    result.free(); build.drop(); probe.drop()
+dist.destroy_process_group()
