@@ -132,6 +132,7 @@ int sync_table_descriptors(hyb_context* context, Table* table) {
   HYB_CUDA(cudaStreamSynchronize(context->stream));
   for (auto& entry : table->d_tile_maps) cudaFree(entry.second.first);
   table->d_tile_maps.clear();
+  table->key_bounds.clear();
   table->dirty = false;
   return HYB_OK;
 }

@@ -87,6 +87,13 @@ struct Table {
   uint32_t d_chunk_capacity = 0;
   bool dirty = true;
   std::map<uint32_t, std::pair<uint2*, uint32_t>> d_tile_maps;  // tile_rows -> (device {chunk,row0} per tile, count)
+  // Integer key bounds per column {min, max, has_values}, computed on first use by JoinHash (the device-side analogue of
+  // the MinMaxFilter pruning statistics, statistics/generate_pruning_statistics.cpp); cleared when chunks are appended.
+  struct KeyBounds {
+    long long min = 0, max = 0;
+    bool has_values = false;
+  };
+  std::map<uint32_t, KeyBounds> key_bounds;
 
   uint32_t chunk_count() const { return static_cast<uint32_t>(chunk_rows.size()); }
   uint64_t row_count() const { return chunk_row_start.empty() ? 0 : chunk_row_start.back(); }

@@ -26,6 +26,7 @@
 // NULL probe keys (probe<keep_null_values = true>). NULL build keys are never inserted (join_hash.cpp:271-286).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "device_utils.cuh"
 #include "internal.hpp"
@@ -245,6 +246,12 @@ struct HashTable {
   unsigned long long* slots;      // bucket_count * 4
   uint32_t bucket_mask;           // bucket_count - 1 (power of two)
   const long long* wide_keys;     // per build position (int64 joins only), else nullptr
+  // Direct-address mode (dense key domains): direct[key - direct_min] = smallest build position with that key, or
+  // kNoMatch. std::hash<int> is the identity in the reference (join_hash_steps.hpp:52-60), so "hashing" a dense domain is
+  // an array index; neighbouring keys share sectors and sorted inputs probe the table sequentially.
+  uint32_t* direct;
+  long long direct_min;
+  unsigned long long direct_range;
 };
 
 __device__ __forceinline__ uint32_t mix32(uint32_t h) {
@@ -268,6 +275,12 @@ __device__ __forceinline__ unsigned long long pack_slot(uint32_t key_bits, uint3
 // Looks `key` up. Returns the slot index (kNoMatch if absent) and the slot's value. A bucket with a free slot ends the
 // search (there are no deletions). Written for few instructions: the probe kernel is issue-bound, not bandwidth-bound.
 __device__ __forceinline__ uint32_t table_find(const HashTable& table, long long key, uint32_t& value) {
+  if (table.direct) {
+    const unsigned long long index = static_cast<unsigned long long>(key) - static_cast<unsigned long long>(table.direct_min);
+    if (index >= table.direct_range) return kNoMatch;
+    value = __ldg(table.direct + index);
+    return value == kNoMatch ? kNoMatch : static_cast<uint32_t>(index);
+  }
   const uint32_t key_bits = static_cast<uint32_t>(key);
   uint32_t bucket = bucket_of(key, table.bucket_mask);
   while (true) {
@@ -303,6 +316,12 @@ struct BuildParams {
 };
 
 __device__ __forceinline__ void table_insert(const BuildParams& params, long long key, uint32_t value) {
+  if (params.table.direct) {
+    // every key lies inside [direct_min, direct_min + direct_range): the bounds cover the whole column
+    const unsigned long long index = static_cast<unsigned long long>(key) - static_cast<unsigned long long>(params.table.direct_min);
+    if (atomicMin(params.table.direct + index, value) != kNoMatch) params.flags[0] = 1;
+    return;
+  }
   if (params.wide_keys_out) params.wide_keys_out[value] = key;
   const uint32_t key_bits = static_cast<uint32_t>(key);
   const unsigned long long desired = pack_slot(key_bits, value);
@@ -373,6 +392,37 @@ __global__ void __launch_bounds__(kJoinThreads) join_build_kernel(const BuildPar
       }
       table_insert(params, key, static_cast<uint32_t>(ref.first_position + index));
     }
+  }
+}
+
+// Smallest / largest non-NULL key of a column: out = {min, max, count of non-NULL rows}. Decides direct-address mode.
+__global__ void __launch_bounds__(kJoinThreads) join_key_bounds_kernel(const KeySource source, long long* __restrict__ out) {
+  long long low = 0x7FFFFFFFFFFFFFFFll, high = -0x7FFFFFFFFFFFFFFFll - 1;
+  unsigned long long count = 0;
+  for (uint32_t tile = blockIdx.x; tile < source.tile_count; tile += gridDim.x) {
+    const TileRef ref = tile_ref(source, tile);
+    const DevSegment segment = source.tile_map ? source.segments[ref.chunk] : DevSegment{};
+    for (uint32_t index = threadIdx.x; index < kJoinTileRows; index += kJoinThreads) {
+      long long key;
+      bool is_null;
+      if (!load_key1(source, ref, segment, index, key, is_null) || is_null) continue;
+      low = key < low ? key : low;
+      high = key > high ? key : high;
+      ++count;
+    }
+  }
+#pragma unroll
+  for (int delta = 16; delta > 0; delta >>= 1) {
+    const long long other_low = __shfl_xor_sync(kFullMask, low, delta);
+    const long long other_high = __shfl_xor_sync(kFullMask, high, delta);
+    low = other_low < low ? other_low : low;
+    high = other_high > high ? other_high : high;
+    count += __shfl_xor_sync(kFullMask, count, delta);
+  }
+  if ((threadIdx.x & 31) == 0 && count) {
+    atomicMin(out, low);
+    atomicMax(out + 1, high);
+    atomicAdd(reinterpret_cast<unsigned long long*>(out + 2), count);
   }
 }
 
@@ -820,6 +870,43 @@ static int prepare_side(hyb_context* context, const hyb_join_side* side, SideInf
   return HYB_OK;
 }
 
+// Key bounds of the (whole) key column of a join side, cached on the table. A filtered side uses the same bounds: they
+// cover a superset of its keys.
+static int column_key_bounds(hyb_context* context, const SideInfo& side, uint32_t column_id, Table::KeyBounds* out,
+                             uint32_t* launches) {
+  Table* table = side.table;
+  const auto cached = table->key_bounds.find(column_id);
+  if (cached != table->key_bounds.end()) {
+    *out = cached->second;
+    return HYB_OK;
+  }
+  Table::KeyBounds bounds{};
+  if (table->row_count()) {
+    KeySource whole = side.source;
+    whole.filter = nullptr;
+    HYB_TRY(get_tile_map(context, table, kJoinTileRows, &whole.tile_map, &whole.tile_count));
+    whole.position_count = table->row_count();
+    void* device_bounds = nullptr;
+    HYB_TRY(device_alloc(context, 3 * sizeof(long long), &device_bounds));
+    const long long initial[3] = {0x7FFFFFFFFFFFFFFFll, -0x7FFFFFFFFFFFFFFFll - 1, 0};
+    HYB_CUDA(cudaMemcpyAsync(device_bounds, initial, sizeof(initial), cudaMemcpyHostToDevice, context->stream));
+    const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(whole.tile_count, context->sm_count * 8));
+    join_key_bounds_kernel<<<grid, kJoinThreads, 0, context->stream>>>(whole, static_cast<long long*>(device_bounds));
+    HYB_CUDA(cudaGetLastError());
+    ++*launches;
+    long long host_bounds[3] = {};
+    HYB_CUDA(cudaMemcpyAsync(host_bounds, device_bounds, sizeof(host_bounds), cudaMemcpyDeviceToHost, context->stream));
+    HYB_CUDA(cudaStreamSynchronize(context->stream));
+    device_free(context, device_bounds);
+    bounds.has_values = host_bounds[2] != 0;
+    bounds.min = host_bounds[0];
+    bounds.max = host_bounds[1];
+  }
+  table->key_bounds.emplace(column_id, bounds);
+  *out = bounds;
+  return HYB_OK;
+}
+
 static int run_exclusive_scan(hyb_context* context, const uint32_t* in, unsigned long long* out, uint64_t count,
                               unsigned long long* total_out) {
   const uint32_t tile_count = static_cast<uint32_t>((count + kScanTile - 1) / kScanTile);
@@ -870,27 +957,44 @@ int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const h
   timing_begin(context);
 
   // ---- build -----------------------------------------------------------------------------------------------------
+  // Dense key domain (range of the build column <= 8x its rows): direct-address table, one uint32 per key value.
+  // Otherwise: bucketised open addressing at load factor <= 0.5.
+  Table::KeyBounds bounds{};
+  HYB_TRY(column_key_bounds(context, build, build_side->column_id, &bounds, &launches));
+  const unsigned long long key_span = static_cast<unsigned long long>(bounds.max) - static_cast<unsigned long long>(bounds.min);
+  // HYB_JOIN_TABLE=hash|direct overrides the choice (the parity tests run every case in both modes).
+  const char* forced = std::getenv("HYB_JOIN_TABLE");
+  const bool force_hash = forced && forced[0] == 'h';
+  const bool force_direct = forced && forced[0] == 'd';
+  const bool direct = bounds.has_values && build.positions > 0 && key_span < 0xFFFFFFE0ull && !force_hash &&
+                      (key_span < 8 * build.positions + 65'536 || (force_direct && key_span < (1ull << 28)));
   uint64_t bucket_count = 1;
   while (bucket_count * 2 < build.positions) bucket_count <<= 1;  // >= positions / 2 buckets -> load factor <= 0.5
   HYB_CHECK(bucket_count * 4 < 0xFFFFFFF0ull, HYB_ERR_UNSUPPORTED, "build side too large for 32-bit slot indexes");
-  const uint64_t slot_count = bucket_count * 4;
+  const uint64_t slot_count = direct ? key_span + 1 : bucket_count * 4;
+  const size_t slot_bytes = direct ? sizeof(uint32_t) : sizeof(uint64_t);
   void* slots = nullptr;
   void* wide_keys = nullptr;
   void* control = nullptr;  // [0] duplicate keys, [1] NULL build keys, [2] output overflow, [4..5] total (u64)
-  HYB_TRY(device_alloc(context, sizeof(uint64_t) * slot_count, &slots));
-  HYB_CUDA(cudaMemsetAsync(slots, 0xFF, sizeof(uint64_t) * slot_count, stream));
+  HYB_TRY(device_alloc(context, slot_bytes * slot_count, &slots));
+  HYB_CUDA(cudaMemsetAsync(slots, 0xFF, slot_bytes * slot_count, stream));
   HYB_TRY(device_alloc(context, 64, &control));
   HYB_CUDA(cudaMemsetAsync(control, 0, 64, stream));
   auto* flags = static_cast<uint32_t*>(control);
   auto* total_slot = reinterpret_cast<unsigned long long*>(flags + 4);
-  if (wide) {
+  if (wide && !direct) {
     HYB_TRY(device_alloc(context, sizeof(long long) * std::max<uint64_t>(build.positions, 1), &wide_keys));
     HYB_CUDA(cudaMemsetAsync(wide_keys, 0x80, sizeof(long long) * std::max<uint64_t>(build.positions, 1), stream));
   }
   HashTable table{};
-  table.slots = static_cast<unsigned long long*>(slots);
+  table.slots = static_cast<unsigned long long*>(slots);  // non-NULL also in direct mode: "a table exists"
   table.bucket_mask = static_cast<uint32_t>(bucket_count - 1);
   table.wide_keys = static_cast<const long long*>(wide_keys);
+  if (direct) {
+    table.direct = static_cast<uint32_t*>(slots);
+    table.direct_min = bounds.min;
+    table.direct_range = key_span + 1;
+  }
   const uint32_t build_grid = std::max<uint32_t>(1, std::min<uint32_t>(build.source.tile_count, context->sm_count * 8));
   timing_kernel_begin(context);
   if (build.source.tile_count) {

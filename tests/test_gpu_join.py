@@ -10,6 +10,19 @@ from hyrise_b200.storage import ColumnDefinition, Table
 
 pytestmark = pytest.mark.gpu
 
+
+
+@pytest.fixture(autouse=True, params=["auto", "hash", "direct"])
+def join_table_kind(request, monkeypatch):
+    """Every case runs with the library's own choice, with the open-addressing table forced and with the direct-address
+    table forced (HYB_JOIN_TABLE, read per call by hyb_join_hash): all three must reproduce the reference order."""
+    if request.param == "auto":
+        monkeypatch.delenv("HYB_JOIN_TABLE", raising=False)
+    else:
+        monkeypatch.setenv("HYB_JOIN_TABLE", request.param)
+    return request.param
+
+
 MODES = [capi.JOIN_INNER, capi.JOIN_LEFT, capi.JOIN_SEMI, capi.JOIN_ANTI_NULL_AS_TRUE, capi.JOIN_ANTI_NULL_AS_FALSE]
 
 
