@@ -155,6 +155,7 @@ SYMBOLS = {
     "hyb_join_result_free": [_CTX, _U64],
     "hyb_join_side_positions": [_CTX, C.POINTER(JoinSide), C.POINTER(_U64)],
     "hyb_join_materialize": [_CTX, C.POINTER(JoinSide), _U32, _P, _P],
+    "hyb_join_partition": [_CTX, C.POINTER(JoinSide), _U32, _U32, _P, _P, C.POINTER(_U64)],
     "hyb_aggregate_hash": [_CTX, C.POINTER(AggregateQuery), C.POINTER(_U64)],
     "hyb_aggregate_result_info": [_CTX, _U64, C.POINTER(_U64), C.POINTER(_I32)],
     "hyb_aggregate_result_row_ids": [_CTX, _U64, _P],

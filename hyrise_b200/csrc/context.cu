@@ -72,14 +72,14 @@ Table::~Table() {
 }
 
 PosList::~PosList() {
-  if (d_row_ids) cudaFreeAsync(d_row_ids, stream);
-  if (d_chunk_end) cudaFreeAsync(d_chunk_end, stream);
+  device_free(owner, d_row_ids);
+  device_free(owner, d_chunk_end);
 }
 
 JoinResult::~JoinResult() {
-  if (d_build) cudaFreeAsync(d_build, stream);
-  if (d_probe) cudaFreeAsync(d_probe, stream);
-  if (d_partition_offsets) cudaFreeAsync(d_partition_offsets, stream);
+  device_free(owner, d_build);
+  device_free(owner, d_probe);
+  device_free(owner, d_partition_offsets);
 }
 
 Table* find_table(hyb_context* context, hyb_table_t handle) {
@@ -92,15 +92,68 @@ PosList* find_pos_list(hyb_context* context, hyb_pos_list_t handle) {
   return it == context->pos_lists.end() ? nullptr : it->second.get();
 }
 
+static size_t cache_rounded_size(size_t bytes) {
+  if (bytes <= 512) return 512;
+  if (bytes >= (size_t{1} << 20)) return (bytes + (size_t{1} << 20) - 1) & ~((size_t{1} << 20) - 1);  // 1 MiB steps
+  size_t size = 512;
+  while (size < bytes) size <<= 1;
+  return size;
+}
+
+static void cache_release_free_blocks(hyb_context* context) {
+  auto& cache = context->cache;
+  if (cache.free_blocks.empty()) return;
+  cudaStreamSynchronize(context->stream);  // queued kernels may still use blocks that were returned after launch
+  for (auto& entry : cache.free_blocks) {
+    cudaFree(entry.second);
+    cache.block_size.erase(entry.second);
+  }
+  cache.free_blocks.clear();
+  cache.free_bytes = 0;
+}
+
 int device_alloc(hyb_context* context, size_t bytes, void** out) {
   *out = nullptr;
-  if (bytes == 0) bytes = 16;
-  HYB_CUDA(cudaMallocAsync(out, bytes, context->stream));
+  auto& cache = context->cache;
+  const size_t size = cache_rounded_size(bytes);
+  // best fit, wasting at most 1/8 of the block (large blocks are kept for large requests)
+  const auto it = cache.free_blocks.lower_bound(size);
+  if (it != cache.free_blocks.end() && it->first <= size + std::max<size_t>(size / 8, size_t{1} << 20)) {
+    *out = it->second;
+    cache.free_bytes -= it->first;
+    cache.free_blocks.erase(it);
+    return HYB_OK;
+  }
+  void* block = nullptr;
+  cudaError_t error = cudaMalloc(&block, size);
+  if (error == cudaErrorMemoryAllocation) {
+    cudaGetLastError();
+    cache_release_free_blocks(context);
+    error = cudaMalloc(&block, size);
+  }
+  HYB_CUDA(error);
+  cache.block_size.emplace(block, size);
+  *out = block;
   return HYB_OK;
 }
 
 void device_free(hyb_context* context, void* ptr) {
-  if (ptr) cudaFreeAsync(ptr, context->stream);
+  if (!ptr || !context) return;
+  auto& cache = context->cache;
+  const auto it = cache.block_size.find(ptr);
+  if (it == cache.block_size.end()) return;  // not ours (adopted caller buffer)
+  cache.free_blocks.emplace(it->second, ptr);
+  cache.free_bytes += it->second;
+  // Bound what an idle context holds on to: beyond 64 GiB of unused blocks, give everything back to the driver.
+  if (cache.free_bytes > (size_t{64} << 30)) cache_release_free_blocks(context);
+}
+
+void device_cache_destroy(hyb_context* context) {
+  cudaStreamSynchronize(context->stream);
+  for (auto& entry : context->cache.block_size) cudaFree(entry.first);
+  context->cache.block_size.clear();
+  context->cache.free_blocks.clear();
+  context->cache.free_bytes = 0;
 }
 
 int sync_table_descriptors(hyb_context* context, Table* table) {
@@ -319,11 +372,6 @@ int hyb_context_create(int device_index, hyb_context** out_context) {
   context->device = device_index;
   context->sm_count = prop.multiProcessorCount;
   HYB_CUDA(cudaStreamCreateWithFlags(&context->stream, cudaStreamNonBlocking));
-  // Keep freed result buffers in the stream-ordered pool: operators allocate their outputs on every call.
-  cudaMemPool_t pool = nullptr;
-  HYB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device_index));
-  uint64_t threshold = UINT64_MAX;
-  HYB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
   *out_context = context.release();
   return HYB_OK;
 }
@@ -338,6 +386,7 @@ int hyb_context_destroy(hyb_context* context) {
     context->aggregate_results.clear();
     context->tables.clear();
     context->block_sets.clear();
+    device_cache_destroy(context);
     if (context->timing.op_begin) {
       cudaEventDestroy(context->timing.op_begin);
       cudaEventDestroy(context->timing.op_end);

@@ -42,6 +42,7 @@ constexpr unsigned long long kEmptySlot = ~0ull;
 constexpr int kMaxPartitions = 256;
 constexpr long long kWideKeyUnset = static_cast<long long>(0x8080808080808080ull);  // memset(0x80) pattern
 constexpr uint32_t kEmitWithoutPartner = 0xFFFFFFFEu;  // output row with a NULL build partner / Semi-Anti output row
+constexpr int32_t kModePartition = 100;  // not a JoinMode: hyb_join_partition's stable split of {key, RowID} tuples by owner
 
 struct KeySource {
   const DevSegment* segments;        // key column descriptors, one per chunk
@@ -137,13 +138,6 @@ __device__ __forceinline__ hyb_row_id position_to_row_id(const KeySource& source
   return hyb_row_id{lo, static_cast<uint32_t>(position - __ldg(source.chunk_row_start + lo))};
 }
 
-// Keys of 8 consecutive positions [index0, index0 + 8) of a tile (index0 % 8 == 0). valid/null bit masks per row.
-struct Keys8 {
-  long long key[8];
-  uint32_t valid;
-  uint32_t nulls;
-};
-
 struct TileRef {
   uint32_t chunk;       // unfiltered
   uint32_t row0;        // first row of the tile inside the chunk (unfiltered) / unused
@@ -163,80 +157,6 @@ __device__ __forceinline__ TileRef tile_ref(const KeySource& source, uint32_t ti
   return ref;
 }
 
-__device__ __forceinline__ void load_keys8(const KeySource& source, const TileRef& ref, const DevSegment& segment,
-                                           uint32_t index0, Keys8& out) {
-  out.valid = 0;
-  out.nulls = 0;
-  if (source.tile_map) {
-    const uint32_t row0 = ref.row0 + index0;
-    if (row0 >= segment.row_count) return;
-    out.valid = segment.row_count - row0 >= 8 ? 0xFFu : ((1u << (segment.row_count - row0)) - 1u);
-    switch (segment.encoding) {
-      case HYB_ENC_UNENCODED: {
-        if (segment.data_type == HYB_TYPE_INT32) {
-          const uint4 a = ld_stream_v4(static_cast<const int32_t*>(segment.values) + row0);
-          const uint4 b = ld_stream_v4(static_cast<const int32_t*>(segment.values) + row0 + 4);
-          out.key[0] = static_cast<int32_t>(a.x);
-          out.key[1] = static_cast<int32_t>(a.y);
-          out.key[2] = static_cast<int32_t>(a.z);
-          out.key[3] = static_cast<int32_t>(a.w);
-          out.key[4] = static_cast<int32_t>(b.x);
-          out.key[5] = static_cast<int32_t>(b.y);
-          out.key[6] = static_cast<int32_t>(b.z);
-          out.key[7] = static_cast<int32_t>(b.w);
-        } else {
-          const auto* base = static_cast<const long long*>(segment.values) + row0;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 v = ld_stream_v4(base + 2 * j);
-            out.key[2 * j] = static_cast<long long>((static_cast<unsigned long long>(v.y) << 32) | v.x);
-            out.key[2 * j + 1] = static_cast<long long>((static_cast<unsigned long long>(v.w) << 32) | v.z);
-          }
-        }
-        out.nulls = load_nulls8(segment.nulls, row0);
-        break;
-      }
-      case HYB_ENC_DICTIONARY: {
-        uint32_t codes[8];
-        load_codes8(segment.av, segment.vector_type, segment.bit_width, row0, segment.row_count, codes);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const bool is_null = codes[j] >= segment.dict_size;
-          out.nulls |= is_null ? (1u << j) : 0u;
-          out.key[j] = is_null ? 0ll
-                       : segment.data_type == HYB_TYPE_INT32
-                           ? static_cast<long long>(__ldg(static_cast<const int32_t*>(segment.values) + codes[j]))
-                           : __ldg(static_cast<const long long*>(segment.values) + codes[j]);
-        }
-        break;
-      }
-      default: {  // FrameOfReference
-        uint32_t codes[8];
-        load_codes8(segment.av, segment.vector_type, segment.bit_width, row0, segment.row_count, codes);
-        const int32_t minimum = __ldg(static_cast<const int32_t*>(segment.values) + row0 / HYB_FOR_BLOCK_SIZE);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) out.key[j] = static_cast<int32_t>(static_cast<uint32_t>(minimum) + codes[j]);
-        out.nulls = load_nulls8(segment.nulls, row0);
-        break;
-      }
-    }
-    out.nulls &= out.valid;
-  } else {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const unsigned long long position = ref.first_position + index0 + j;
-      out.key[j] = 0;
-      if (position < source.position_count) {
-        const hyb_row_id row_id = source.filter[position];
-        bool is_null;
-        out.key[j] = decode_int_key(source.segments[row_id.chunk_id], row_id.chunk_offset, is_null);
-        out.valid |= 1u << j;
-        out.nulls |= is_null ? (1u << j) : 0u;
-      }
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------------------
 // Hash table: buckets of four 64-bit slots {key (low 32 bits of the int64 key... see below), value}.
 // Keys are compared as 32-bit patterns when both columns are int32 (kWide == false). For int64 keys (kWide == true) a
@@ -249,9 +169,12 @@ struct HashTable {
   // Direct-address mode (dense key domains): direct[key - direct_min] = smallest build position with that key, or
   // kNoMatch. std::hash<int> is the identity in the reference (join_hash_steps.hpp:52-60), so "hashing" a dense domain is
   // an array index; neighbouring keys share sectors and sorted inputs probe the table sequentially.
+  // When all build keys agree in their `direct_shift` low bits (keys received by one rank of a radix exchange do), the
+  // table is indexed by (key - direct_min) >> direct_shift and keys with other low bits cannot match.
   uint32_t* direct;
   long long direct_min;
   unsigned long long direct_range;
+  uint32_t direct_shift;
 };
 
 __device__ __forceinline__ uint32_t mix32(uint32_t h) {
@@ -276,8 +199,9 @@ __device__ __forceinline__ unsigned long long pack_slot(uint32_t key_bits, uint3
 // search (there are no deletions). Written for few instructions: the probe kernel is issue-bound, not bandwidth-bound.
 __device__ __forceinline__ uint32_t table_find(const HashTable& table, long long key, uint32_t& value) {
   if (table.direct) {
-    const unsigned long long index = static_cast<unsigned long long>(key) - static_cast<unsigned long long>(table.direct_min);
-    if (index >= table.direct_range) return kNoMatch;
+    const unsigned long long offset = static_cast<unsigned long long>(key) - static_cast<unsigned long long>(table.direct_min);
+    const unsigned long long index = offset >> table.direct_shift;
+    if (index >= table.direct_range || (offset & ((1ull << table.direct_shift) - 1ull))) return kNoMatch;
     value = __ldg(table.direct + index);
     return value == kNoMatch ? kNoMatch : static_cast<uint32_t>(index);
   }
@@ -318,7 +242,8 @@ struct BuildParams {
 __device__ __forceinline__ void table_insert(const BuildParams& params, long long key, uint32_t value) {
   if (params.table.direct) {
     // every key lies inside [direct_min, direct_min + direct_range): the bounds cover the whole column
-    const unsigned long long index = static_cast<unsigned long long>(key) - static_cast<unsigned long long>(params.table.direct_min);
+    const unsigned long long index =
+        (static_cast<unsigned long long>(key) - static_cast<unsigned long long>(params.table.direct_min)) >> params.table.direct_shift;
     if (atomicMin(params.table.direct + index, value) != kNoMatch) params.flags[0] = 1;
     return;
   }
@@ -395,10 +320,11 @@ __global__ void __launch_bounds__(kJoinThreads) join_build_kernel(const BuildPar
   }
 }
 
-// Smallest / largest non-NULL key of a column: out = {min, max, count of non-NULL rows}. Decides direct-address mode.
+// Smallest / largest non-NULL key of a column: out = {min, max, count of non-NULL rows, AND of keys, OR of keys}. Decides
+// direct-address mode; bits where AND == OR are the same in every key.
 __global__ void __launch_bounds__(kJoinThreads) join_key_bounds_kernel(const KeySource source, long long* __restrict__ out) {
   long long low = 0x7FFFFFFFFFFFFFFFll, high = -0x7FFFFFFFFFFFFFFFll - 1;
-  unsigned long long count = 0;
+  unsigned long long count = 0, all_and = ~0ull, all_or = 0ull;
   for (uint32_t tile = blockIdx.x; tile < source.tile_count; tile += gridDim.x) {
     const TileRef ref = tile_ref(source, tile);
     const DevSegment segment = source.tile_map ? source.segments[ref.chunk] : DevSegment{};
@@ -408,6 +334,8 @@ __global__ void __launch_bounds__(kJoinThreads) join_key_bounds_kernel(const Key
       if (!load_key1(source, ref, segment, index, key, is_null) || is_null) continue;
       low = key < low ? key : low;
       high = key > high ? key : high;
+      all_and &= static_cast<unsigned long long>(key);
+      all_or |= static_cast<unsigned long long>(key);
       ++count;
     }
   }
@@ -418,11 +346,15 @@ __global__ void __launch_bounds__(kJoinThreads) join_key_bounds_kernel(const Key
     low = other_low < low ? other_low : low;
     high = other_high > high ? other_high : high;
     count += __shfl_xor_sync(kFullMask, count, delta);
+    all_and &= __shfl_xor_sync(kFullMask, all_and, delta);
+    all_or |= __shfl_xor_sync(kFullMask, all_or, delta);
   }
   if ((threadIdx.x & 31) == 0 && count) {
     atomicMin(out, low);
     atomicMax(out + 1, high);
     atomicAdd(reinterpret_cast<unsigned long long*>(out + 2), count);
+    atomicAnd(reinterpret_cast<unsigned long long*>(out + 3), all_and);
+    atomicOr(reinterpret_cast<unsigned long long*>(out + 4), all_or);
   }
 }
 
@@ -566,6 +498,7 @@ struct ProbeParams {
   hyb_row_id* out_probe;
   unsigned long long out_capacity;
   uint32_t* overflow;                     // set when the output does not fit out_capacity (optimistic sizing)
+  uint32_t chunk_id_base;                 // kModePartition: added to chunk ids (RowIDs of the global table)
 };
 
 // What one probe row contributes. Returns the match word: a build position (unique build side), a table slot
@@ -579,6 +512,7 @@ __device__ __forceinline__ uint32_t probe_match_resolved(const ProbeParams& para
   if (mode == HYB_JOIN_INNER) {  // the common case first: NULL probe keys were never looked up (slot == kNoMatch)
     return slot == kNoMatch ? kNoMatch : (params.unique_build ? value : slot);
   }
+  if (mode == kModePartition) return is_null ? kNoMatch : kEmitWithoutPartner;
   if (mode == HYB_JOIN_ANTI_NULL_AS_TRUE && build_has_nulls) return kNoMatch;
   if (is_null) {
     if (mode == HYB_JOIN_LEFT || mode == HYB_JOIN_RIGHT || mode == HYB_JOIN_ANTI_NULL_AS_FALSE) return kEmitWithoutPartner;
@@ -605,48 +539,165 @@ __device__ __forceinline__ uint32_t emitted_rows(const ProbeParams& params, uint
   return params.dup_counts[match];
 }
 
-__global__ void __launch_bounds__(kJoinThreads) join_probe_count_kernel(const ProbeParams params) {
+// ---- per-tile key codecs ---------------------------------------------------------------------------------------------
+// The inner loops are specialised for the layouts that dominate (plain int32/int64 values, FrameOfReference offsets in a
+// FixedWidthIntegerVector, no NULL vector); everything else — dictionaries, bit-packed vectors, nullable segments, PosList
+// inputs — takes the generic decoder. The choice is uniform per tile (tiles never straddle chunks).
+enum : uint32_t { kCodecGeneric = 0, kCodecPlain32, kCodecPlain64, kCodecFor8, kCodecFor16, kCodecFor32 };
+
+__device__ __forceinline__ uint32_t tile_codec(const KeySource& source, const DevSegment& segment) {
+  if (!source.tile_map || segment.nulls) return kCodecGeneric;
+  if (segment.encoding == HYB_ENC_UNENCODED) return segment.data_type == HYB_TYPE_INT32 ? kCodecPlain32 : kCodecPlain64;
+  if (segment.encoding == HYB_ENC_FRAME_OF_REFERENCE) {
+    if (segment.vector_type == HYB_VEC_FIXED_1B) return kCodecFor8;
+    if (segment.vector_type == HYB_VEC_FIXED_2B) return kCodecFor16;
+    if (segment.vector_type == HYB_VEC_FIXED_4B) return kCodecFor32;
+  }
+  return kCodecGeneric;
+}
+
+template <uint32_t kCodec>
+__device__ __forceinline__ bool codec_key(const KeySource& source, const TileRef& ref, const DevSegment& segment, uint32_t index,
+                                          uint32_t for_minimum, long long& key, bool& is_null) {
+  if constexpr (kCodec == kCodecGeneric) {
+    return load_key1(source, ref, segment, index, key, is_null);
+  } else {
+    const uint32_t row = ref.row0 + index;
+    is_null = false;
+    if (row >= segment.row_count) return false;
+    if constexpr (kCodec == kCodecPlain32) {
+      key = static_cast<int32_t>(ld_stream_u32(static_cast<const uint32_t*>(segment.values) + row));
+    } else if constexpr (kCodec == kCodecPlain64) {
+      key = __ldg(static_cast<const long long*>(segment.values) + row);
+    } else if constexpr (kCodec == kCodecFor8) {
+      key = static_cast<int32_t>(for_minimum + __ldg(static_cast<const uint8_t*>(segment.av) + row));
+    } else if constexpr (kCodec == kCodecFor16) {
+      key = static_cast<int32_t>(for_minimum + __ldg(static_cast<const uint16_t*>(segment.av) + row));
+    } else {
+      key = static_cast<int32_t>(for_minimum + ld_stream_u32(static_cast<const uint32_t*>(segment.av) + row));
+    }
+    return true;
+  }
+}
+
+constexpr int kProbeSteps = kJoinRowsPerWarp / 32;  // 16 rows per lane, lane-consecutive: step s, lane l -> chunk0 + 32 s + l
+
+// The rows of one warp chunk (512 consecutive tile indexes) held in registers between the two passes of the write kernel.
+struct ChunkRows {
+  uint32_t match[kProbeSteps];
+  uint32_t rank[kProbeSteps];            // output row of this probe row, relative to its (warp chunk, partition) run
+  uint32_t partitions[kProbeSteps / 4];  // one byte per step
+};
+
+// Pass 1 over one warp chunk: key -> table lookup -> match word and radix partition of every row, emitted-row counts
+// added to histogram[partition] (one shared-memory atomic per distinct partition and step). With kRank the value the
+// histogram held before the add — the number of rows this warp chunk emitted into the partition in earlier steps — plus
+// the emitting peers in lower lanes is the row's rank: lane order is probe order, so ranks reproduce the reference order.
+// kSource: 0 = decode + look up, storing nothing; 1 = decode + look up and store match/partition per probe slot (hash
+// tables: the write kernel must not repeat the random accesses); 2 = load what mode 1 stored.
+template <bool kRank, int kSource, uint32_t kCodec>
+__device__ __forceinline__ void probe_chunk(const ProbeParams& params, const TileRef& ref, const DevSegment& segment,
+                                            uint32_t chunk0, size_t tile_slot0, uint32_t lane, bool build_has_nulls,
+                                            uint32_t* histogram, ChunkRows& rows) {
+  const bool unique = params.unique_build != 0;
+  const uint32_t lanes_below = (1u << lane) - 1u;
+  uint32_t for_minimum = 0;
+  if constexpr (kSource != 2 && kCodec >= kCodecFor8) {
+    // chunk0 is a multiple of 512 and tiles start at multiples of 4096 rows: the warp chunk lies inside one 2048-row block
+    const uint32_t first_row = ref.row0 + chunk0;
+    if (first_row < segment.row_count) {
+      for_minimum = static_cast<uint32_t>(__ldg(static_cast<const int32_t*>(segment.values) + first_row / HYB_FOR_BLOCK_SIZE));
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < kProbeSteps / 4; ++q) rows.partitions[q] = 0;
+#pragma unroll
+  for (int step = 0; step < kProbeSteps; ++step) {
+    const uint32_t index = chunk0 + step * 32 + lane;
+    uint32_t match, partition;
+    if constexpr (kSource == 2) {
+      match = __ldg(params.matches + tile_slot0 + index);
+      partition = __ldg(params.partitions + tile_slot0 + index);
+    } else {
+      long long key = 0;
+      bool is_null = false;
+      const bool valid = codec_key<kCodec>(params.probe, ref, segment, index, for_minimum, key, is_null);
+      match = kNoMatch;
+      if (valid) {
+        uint32_t value = 0;
+        const uint32_t slot = (!is_null && params.table.slots) ? table_find(params.table, key, value) : kNoMatch;
+        match = probe_match_resolved(params, slot, value, is_null, build_has_nulls);
+      }
+      partition = static_cast<uint32_t>(static_cast<unsigned long long>(key)) & params.partition_mask;
+      if constexpr (kSource == 1) {
+        params.matches[tile_slot0 + index] = match;
+        params.partitions[tile_slot0 + index] = static_cast<uint8_t>(partition);
+      }
+    }
+    const uint32_t emit = emitted_rows(params, match);
+    const uint32_t peers = __match_any_sync(kFullMask, partition);
+    uint32_t before = 0, total = 0;
+    if (unique) {
+      const uint32_t emitting = __ballot_sync(kFullMask, emit != 0) & peers;
+      total = __popc(emitting);
+      if constexpr (kRank) before = __popc(emitting & lanes_below);
+    } else {
+      uint32_t remaining = peers;
+      while (remaining) {
+        const int source_lane = __ffs(remaining) - 1;
+        const uint32_t value = __shfl_sync(peers, emit, source_lane);
+        if (static_cast<uint32_t>(source_lane) < lane) before += value;
+        total += value;
+        remaining &= remaining - 1;
+      }
+    }
+    const int leader = __ffs(peers) - 1;
+    uint32_t earlier = 0;
+    if (lane == static_cast<uint32_t>(leader) && total) earlier = atomicAdd(histogram + partition, total);
+    if constexpr (kRank) {
+      earlier = __shfl_sync(kFullMask, earlier, leader);
+      rows.match[step] = match;
+      rows.rank[step] = earlier + before;
+      rows.partitions[step >> 2] |= partition << (8 * (step & 3));
+    }
+  }
+}
+
+template <bool kRank, int kSource>
+__device__ __forceinline__ void probe_chunk_any_codec(const ProbeParams& params, const TileRef& ref, const DevSegment& segment,
+                                                      uint32_t codec, uint32_t chunk0, size_t tile_slot0, uint32_t lane,
+                                                      bool build_has_nulls, uint32_t* histogram, ChunkRows& rows) {
+  switch (codec) {
+    case kCodecPlain32:
+      return probe_chunk<kRank, kSource, kCodecPlain32>(params, ref, segment, chunk0, tile_slot0, lane, build_has_nulls, histogram, rows);
+    case kCodecPlain64:
+      return probe_chunk<kRank, kSource, kCodecPlain64>(params, ref, segment, chunk0, tile_slot0, lane, build_has_nulls, histogram, rows);
+    case kCodecFor8:
+      return probe_chunk<kRank, kSource, kCodecFor8>(params, ref, segment, chunk0, tile_slot0, lane, build_has_nulls, histogram, rows);
+    case kCodecFor16:
+      return probe_chunk<kRank, kSource, kCodecFor16>(params, ref, segment, chunk0, tile_slot0, lane, build_has_nulls, histogram, rows);
+    case kCodecFor32:
+      return probe_chunk<kRank, kSource, kCodecFor32>(params, ref, segment, chunk0, tile_slot0, lane, build_has_nulls, histogram, rows);
+    default:
+      return probe_chunk<kRank, kSource, kCodecGeneric>(params, ref, segment, chunk0, tile_slot0, lane, build_has_nulls, histogram, rows);
+  }
+}
+
+// Emitted rows per (partition, tile). kStore: also keep match/partition per probe slot for the write kernel.
+template <bool kStore>
+__global__ void __launch_bounds__(kJoinThreads, 4) join_probe_count_kernel(const ProbeParams params) {
   __shared__ uint32_t s_histogram[kMaxPartitions];
   const bool build_has_nulls = params.flags[1] != 0;
-  const bool unique = params.unique_build != 0;
-  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (uint32_t tile = blockIdx.x; tile < params.probe.tile_count; tile += gridDim.x) {
     for (uint32_t p = threadIdx.x; p < params.partition_count; p += kJoinThreads) s_histogram[p] = 0;
     __syncthreads();
     const TileRef ref = tile_ref(params.probe, tile);
     const DevSegment segment = params.probe.tile_map ? params.probe.segments[ref.chunk] : DevSegment{};
     const size_t tile_slot0 = static_cast<size_t>(tile) * kJoinTileRows;
-#pragma unroll 4
-    for (uint32_t index = threadIdx.x; index < kJoinTileRows; index += kJoinThreads) {
-      long long key = 0;
-      bool is_null = false;
-      const bool valid = load_key1(params.probe, ref, segment, index, key, is_null);
-      uint32_t match = kNoMatch;
-      if (valid) {
-        uint32_t value = 0;
-        const uint32_t slot = (!is_null && params.table.slots) ? table_find(params.table, key, value) : kNoMatch;
-        match = probe_match_resolved(params, slot, value, is_null, build_has_nulls);
-      }
-      const uint32_t partition = static_cast<uint32_t>(static_cast<unsigned long long>(key)) & params.partition_mask;
-      params.matches[tile_slot0 + index] = match;
-      params.partitions[tile_slot0 + index] = static_cast<uint8_t>(partition);
-      // one shared-memory atomic per distinct partition in the warp
-      const uint32_t emit = emitted_rows(params, match);
-      const uint32_t peers = __match_any_sync(kFullMask, partition);
-      uint32_t total;
-      if (unique) {
-        total = __popc(__ballot_sync(kFullMask, emit != 0) & peers);
-      } else {
-        total = 0;
-        uint32_t remaining = peers;
-        while (remaining) {
-          const int source_lane = __ffs(remaining) - 1;
-          total += __shfl_sync(peers, emit, source_lane);
-          remaining &= remaining - 1;
-        }
-      }
-      if (lane == static_cast<uint32_t>(__ffs(peers) - 1) && total) atomicAdd(&s_histogram[partition], total);
-    }
+    ChunkRows rows;
+    probe_chunk_any_codec<false, kStore ? 1 : 0>(params, ref, segment, tile_codec(params.probe, segment), warp * kJoinRowsPerWarp,
+                                                 tile_slot0, lane, build_has_nulls, s_histogram, rows);
     __syncthreads();
     for (uint32_t p = threadIdx.x; p < params.partition_count; p += kJoinThreads) {
       params.histogram[static_cast<size_t>(p) * params.probe.tile_count + tile] = s_histogram[p];
@@ -655,47 +706,28 @@ __global__ void __launch_bounds__(kJoinThreads) join_probe_count_kernel(const Pr
   }
 }
 
-__global__ void __launch_bounds__(kJoinThreads) join_probe_write_kernel(const ProbeParams params) {
+// Stable multi-split: every probe row's output position = start of its (partition, tile) run (exclusive scan of the
+// histogram) + rows of lower warp chunks of the tile in that partition + its rank inside the warp chunk.
+template <bool kStored>
+__global__ void __launch_bounds__(kJoinThreads, 3) join_probe_write_kernel(const ProbeParams params) {
   __shared__ uint32_t s_warp_histogram[kJoinWarps][kMaxPartitions];
   __shared__ unsigned long long s_start[kJoinWarps][kMaxPartitions];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t lanes_below = (1u << lane) - 1u;
   const bool emit_build = params.out_build != nullptr;
   const bool unique = params.unique_build != 0;
+  const bool build_has_nulls = params.flags[1] != 0;
 
   for (uint32_t tile = blockIdx.x; tile < params.probe.tile_count; tile += gridDim.x) {
     for (uint32_t p = lane; p < params.partition_count; p += 32) s_warp_histogram[warp][p] = 0;
     __syncwarp();
     const TileRef ref = tile_ref(params.probe, tile);
-    const size_t warp_slot0 = static_cast<size_t>(tile) * kJoinTileRows + warp * kJoinRowsPerWarp;
-    // pass 1: emitted rows per (warp, partition); each lane takes 16 consecutive probe slots of the warp's 512
-    {
-      const uint32_t* match_in = params.matches + warp_slot0 + lane * 16;
-      const uint4 bytes = *reinterpret_cast<const uint4*>(params.partitions + warp_slot0 + lane * 16);
-      const uint32_t words[4] = {bytes.x, bytes.y, bytes.z, bytes.w};
-      uint32_t run_partition = 0, run_count = 0;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint4 m = *reinterpret_cast<const uint4*>(match_in + 4 * q);
-        const uint32_t four[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t emit = emitted_rows(params, four[j]);
-          const uint32_t partition = (words[q] >> (8 * j)) & 0xFFu;
-          if (emit) {
-            if (partition != run_partition && run_count) {
-              atomicAdd(&s_warp_histogram[warp][run_partition], run_count);
-              run_count = 0;
-            }
-            run_partition = partition;
-            run_count += emit;
-          }
-        }
-      }
-      if (run_count) atomicAdd(&s_warp_histogram[warp][run_partition], run_count);
-    }
+    const DevSegment segment = params.probe.tile_map ? params.probe.segments[ref.chunk] : DevSegment{};
+    const size_t tile_slot0 = static_cast<size_t>(tile) * kJoinTileRows;
+    ChunkRows rows;
+    probe_chunk_any_codec<true, kStored ? 2 : 0>(params, ref, segment, kStored ? kCodecGeneric : tile_codec(params.probe, segment),
+                                                 warp * kJoinRowsPerWarp, tile_slot0, lane, build_has_nulls,
+                                                 s_warp_histogram[warp], rows);
     __syncthreads();
-    // start of every (warp, partition) run inside this tile's (partition, tile) run
     for (uint32_t p = threadIdx.x; p < params.partition_count; p += kJoinThreads) {
       unsigned long long running = params.run_starts[static_cast<size_t>(p) * params.probe.tile_count + tile];
 #pragma unroll
@@ -705,69 +737,45 @@ __global__ void __launch_bounds__(kJoinThreads) join_probe_write_kernel(const Pr
       }
     }
     __syncthreads();
-    // pass 2: ranks and writes, 32 consecutive probe slots per step so that lane order == probe order. All 16 steps'
-    // matches / partitions are fetched up front (independent loads) instead of one dependent round trip per step.
-    constexpr int kSteps = kJoinRowsPerWarp / 32;
-    uint32_t step_match[kSteps], step_partition[kSteps];
 #pragma unroll
-    for (int step = 0; step < kSteps; ++step) {
-      step_match[step] = __ldg(params.matches + warp_slot0 + step * 32 + lane);
-      step_partition[step] = __ldg(params.partitions + warp_slot0 + step * 32 + lane);
-    }
-#pragma unroll
-    for (int step = 0; step < kSteps; ++step) {
-      const uint32_t index = warp * kJoinRowsPerWarp + step * 32 + lane;
-      const uint32_t match = step_match[step];
-      const uint32_t partition = step_partition[step];
+    for (int step = 0; step < kProbeSteps; ++step) {
+      const uint32_t match = rows.match[step];
       const uint32_t emit = emitted_rows(params, match);
-      const uint32_t peers = __match_any_sync(kFullMask, partition);
-      uint32_t before, sum;
-      if (unique) {
-        const uint32_t emitting = __ballot_sync(kFullMask, emit != 0) & peers;
-        before = __popc(emitting & lanes_below);
-        sum = __popc(emitting);
-      } else {
-        before = 0;
-        sum = 0;
-        uint32_t remaining = peers;
-        while (remaining) {
-          const int source_lane = __ffs(remaining) - 1;
-          const uint32_t value = __shfl_sync(peers, emit, source_lane);
-          if (static_cast<uint32_t>(source_lane) < lane) before += value;
-          sum += value;
-          remaining &= remaining - 1;
-        }
+      if (emit == 0) continue;
+      const uint32_t index = warp * kJoinRowsPerWarp + step * 32 + lane;
+      const uint32_t partition = (rows.partitions[step >> 2] >> (8 * (step & 3))) & 0xFFu;
+      const unsigned long long at = s_start[warp][partition] + rows.rank[step];
+      if (at + emit > params.out_capacity) {
+        *params.overflow = 1;
+        continue;
       }
-      const unsigned long long base = s_start[warp][partition];
-      __syncwarp();
-      if (lane == static_cast<uint32_t>(__ffs(peers) - 1) && sum) s_start[warp][partition] = base + sum;
-      __syncwarp();
-      if (emit) {
-        const unsigned long long at = base + before;
-        if (at + emit > params.out_capacity) {
-          *params.overflow = 1;
-          continue;
-        }
-        hyb_row_id probe_row;
-        if (params.probe.tile_map) {
-          probe_row = hyb_row_id{ref.chunk, ref.row0 + index};
-        } else {
-          probe_row = params.probe.filter[ref.first_position + index];
-        }
-        if (match == kEmitWithoutPartner) {
-          if (emit_build) st_stream_v2(params.out_build + at, HYB_INVALID_CHUNK_ID, HYB_INVALID_CHUNK_OFFSET);
-          st_stream_v2(params.out_probe + at, probe_row.chunk_id, probe_row.chunk_offset);
-        } else if (unique) {
-          const hyb_row_id build_row = position_to_row_id(params.build, match);
-          st_stream_v2(params.out_build + at, build_row.chunk_id, build_row.chunk_offset);
-          st_stream_v2(params.out_probe + at, probe_row.chunk_id, probe_row.chunk_offset);
-        } else {
-          const unsigned long long first = params.dup_offsets[match];
-          for (uint32_t j = 0; j < emit; ++j) {
-            const hyb_row_id build_row = position_to_row_id(params.build, params.dup_positions[first + j]);
-            st_stream_v2(params.out_build + at + j, build_row.chunk_id, build_row.chunk_offset);
-            st_stream_v2(params.out_probe + at + j, probe_row.chunk_id, probe_row.chunk_offset);
-          }
+      hyb_row_id probe_row;
+      if (params.probe.tile_map) {
+        probe_row = hyb_row_id{ref.chunk, ref.row0 + index};
+      } else {
+        probe_row = params.probe.filter[ref.first_position + index];
+      }
+      if (params.mode == kModePartition) {
+        // exchange payload: the key (as the 8 bytes of out_build[at]) and the RowID in the global table
+        long long key = 0;
+        bool is_null = false;
+        load_key1(params.probe, ref, segment, index, key, is_null);
+        st_stream_v2(params.out_build + at, static_cast<uint32_t>(static_cast<unsigned long long>(key)),
+                     static_cast<uint32_t>(static_cast<unsigned long long>(key) >> 32));
+        st_stream_v2(params.out_probe + at, probe_row.chunk_id + params.chunk_id_base, probe_row.chunk_offset);
+      } else if (match == kEmitWithoutPartner) {
+        if (emit_build) st_stream_v2(params.out_build + at, HYB_INVALID_CHUNK_ID, HYB_INVALID_CHUNK_OFFSET);
+        st_stream_v2(params.out_probe + at, probe_row.chunk_id, probe_row.chunk_offset);
+      } else if (unique) {
+        const hyb_row_id build_row = position_to_row_id(params.build, match);
+        st_stream_v2(params.out_build + at, build_row.chunk_id, build_row.chunk_offset);
+        st_stream_v2(params.out_probe + at, probe_row.chunk_id, probe_row.chunk_offset);
+      } else {
+        const unsigned long long first = params.dup_offsets[match];
+        for (uint32_t j = 0; j < emit; ++j) {
+          const hyb_row_id build_row = position_to_row_id(params.build, params.dup_positions[first + j]);
+          st_stream_v2(params.out_build + at + j, build_row.chunk_id, build_row.chunk_offset);
+          st_stream_v2(params.out_probe + at + j, probe_row.chunk_id, probe_row.chunk_offset);
         }
       }
     }
@@ -887,20 +895,24 @@ static int column_key_bounds(hyb_context* context, const SideInfo& side, uint32_
     HYB_TRY(get_tile_map(context, table, kJoinTileRows, &whole.tile_map, &whole.tile_count));
     whole.position_count = table->row_count();
     void* device_bounds = nullptr;
-    HYB_TRY(device_alloc(context, 3 * sizeof(long long), &device_bounds));
-    const long long initial[3] = {0x7FFFFFFFFFFFFFFFll, -0x7FFFFFFFFFFFFFFFll - 1, 0};
+    HYB_TRY(device_alloc(context, 5 * sizeof(long long), &device_bounds));
+    const long long initial[5] = {0x7FFFFFFFFFFFFFFFll, -0x7FFFFFFFFFFFFFFFll - 1, 0, -1ll, 0};
     HYB_CUDA(cudaMemcpyAsync(device_bounds, initial, sizeof(initial), cudaMemcpyHostToDevice, context->stream));
     const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(whole.tile_count, context->sm_count * 8));
     join_key_bounds_kernel<<<grid, kJoinThreads, 0, context->stream>>>(whole, static_cast<long long*>(device_bounds));
     HYB_CUDA(cudaGetLastError());
     ++*launches;
-    long long host_bounds[3] = {};
+    long long host_bounds[5] = {};
     HYB_CUDA(cudaMemcpyAsync(host_bounds, device_bounds, sizeof(host_bounds), cudaMemcpyDeviceToHost, context->stream));
     HYB_CUDA(cudaStreamSynchronize(context->stream));
     device_free(context, device_bounds);
     bounds.has_values = host_bounds[2] != 0;
     bounds.min = host_bounds[0];
     bounds.max = host_bounds[1];
+    if (bounds.has_values) {
+      const unsigned long long varying = static_cast<unsigned long long>(host_bounds[3]) ^ static_cast<unsigned long long>(host_bounds[4]);
+      while (bounds.constant_low_bits < 16 && !((varying >> bounds.constant_low_bits) & 1ull)) ++bounds.constant_low_bits;
+    }
   }
   table->key_bounds.emplace(column_id, bounds);
   *out = bounds;
@@ -966,12 +978,14 @@ int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const h
   const char* forced = std::getenv("HYB_JOIN_TABLE");
   const bool force_hash = forced && forced[0] == 'h';
   const bool force_direct = forced && forced[0] == 'd';
-  const bool direct = bounds.has_values && build.positions > 0 && key_span < 0xFFFFFFE0ull && !force_hash &&
-                      (key_span < 8 * build.positions + 65'536 || (force_direct && key_span < (1ull << 28)));
+  const uint32_t direct_shift = bounds.constant_low_bits;  // keys agree in these low bits (one rank's share of an exchange)
+  const unsigned long long direct_span = key_span >> direct_shift;
+  const bool direct = bounds.has_values && build.positions > 0 && direct_span < 0xFFFFFFE0ull && !force_hash &&
+                      (direct_span < 8 * build.positions + 65'536 || (force_direct && direct_span < (1ull << 28)));
   uint64_t bucket_count = 1;
   while (bucket_count * 2 < build.positions) bucket_count <<= 1;  // >= positions / 2 buckets -> load factor <= 0.5
   HYB_CHECK(bucket_count * 4 < 0xFFFFFFF0ull, HYB_ERR_UNSUPPORTED, "build side too large for 32-bit slot indexes");
-  const uint64_t slot_count = direct ? key_span + 1 : bucket_count * 4;
+  const uint64_t slot_count = direct ? direct_span + 1 : bucket_count * 4;
   const size_t slot_bytes = direct ? sizeof(uint32_t) : sizeof(uint64_t);
   void* slots = nullptr;
   void* wide_keys = nullptr;
@@ -993,7 +1007,8 @@ int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const h
   if (direct) {
     table.direct = static_cast<uint32_t*>(slots);
     table.direct_min = bounds.min;
-    table.direct_range = key_span + 1;
+    table.direct_range = direct_span + 1;
+    table.direct_shift = direct_shift;
   }
   const uint32_t build_grid = std::max<uint32_t>(1, std::min<uint32_t>(build.source.tile_count, context->sm_count * 8));
   timing_kernel_begin(context);
@@ -1014,12 +1029,23 @@ int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const h
   result->radix_bits = radix_bits;
   result->partition_count = partition_count;
   result->stream = stream;
+  result->owner = context;
   void* partition_offsets = nullptr;
   HYB_TRY(device_alloc(context, sizeof(uint64_t) * (size_t{partition_count} + 2), &partition_offsets));
   result->d_partition_offsets = static_cast<uint64_t*>(partition_offsets);
   HYB_CUDA(cudaMemsetAsync(partition_offsets, 0, sizeof(uint64_t) * (size_t{partition_count} + 2), stream));
 
   const uint32_t probe_tiles = probe.source.tile_count;
+  // Hash tables: the count kernel keeps match + partition per probe slot so that the write kernel does not repeat the
+  // random table accesses. Direct-address tables are probed sequentially; looking up twice is cheaper than 10 bytes/row.
+  const bool store_matches = !direct;
+  const auto count_kernel = store_matches ? join_probe_count_kernel<true> : join_probe_count_kernel<false>;
+  const auto write_kernel = store_matches ? join_probe_write_kernel<true> : join_probe_write_kernel<false>;
+  int count_blocks = 1, write_blocks = 1;
+  HYB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&count_blocks, count_kernel, kJoinThreads, 0));
+  HYB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&write_blocks, write_kernel, kJoinThreads, 0));
+  const uint32_t count_grid = std::max<uint32_t>(1, std::min<uint32_t>(probe_tiles, context->sm_count * std::max(count_blocks, 1)));
+  const uint32_t write_grid = std::max<uint32_t>(1, std::min<uint32_t>(probe_tiles, context->sm_count * std::max(write_blocks, 1)));
   const size_t probe_slots = size_t{probe_tiles} * kJoinTileRows;
   void* matches = nullptr;
   void* partitions = nullptr;
@@ -1032,8 +1058,10 @@ int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const h
   ProbeParams params{};
   uint32_t host_control[8] = {};
   if (probe_tiles) {
-    HYB_TRY(device_alloc(context, sizeof(uint32_t) * probe_slots, &matches));
-    HYB_TRY(device_alloc(context, probe_slots, &partitions));
+    if (store_matches) {
+      HYB_TRY(device_alloc(context, sizeof(uint32_t) * probe_slots, &matches));
+      HYB_TRY(device_alloc(context, probe_slots, &partitions));
+    }
     HYB_TRY(device_alloc(context, sizeof(uint32_t) * histogram_entries, &histogram));
     HYB_TRY(device_alloc(context, sizeof(uint64_t) * histogram_entries, &run_starts));
     params.probe = probe.source;
@@ -1052,16 +1080,15 @@ int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const h
     params.run_starts = static_cast<const unsigned long long*>(run_starts);
     params.overflow = flags + 2;
   }
-  const uint32_t probe_grid = std::max<uint32_t>(1, std::min<uint32_t>(probe_tiles, context->sm_count * 6));
 
   const auto run_probe = [&](uint64_t capacity) -> int {
     // count -> scan -> write, all queued without a host round trip; `capacity` output rows are pre-allocated
-    join_probe_count_kernel<<<probe_grid, kJoinThreads, 0, stream>>>(params);
+    count_kernel<<<count_grid, kJoinThreads, 0, stream>>>(params);
     HYB_CUDA(cudaGetLastError());
     HYB_TRY(run_exclusive_scan(context, static_cast<uint32_t*>(histogram), static_cast<unsigned long long*>(run_starts),
                                histogram_entries, total_slot));
-    if (result->d_probe) cudaFreeAsync(result->d_probe, stream);
-    if (result->d_build) cudaFreeAsync(result->d_build, stream);
+    device_free(context, result->d_probe);
+    device_free(context, result->d_build);
     result->d_probe = nullptr;
     result->d_build = nullptr;
     void* out_probe = nullptr;
@@ -1074,7 +1101,7 @@ int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const h
     params.out_probe = result->d_probe;
     params.out_build = result->d_build;
     params.out_capacity = capacity;
-    join_probe_write_kernel<<<probe_grid, kJoinThreads, 0, stream>>>(params);
+    write_kernel<<<write_grid, kJoinThreads, 0, stream>>>(params);
     HYB_CUDA(cudaGetLastError());
     join_partition_offsets_kernel<<<(partition_count + 1 + 127) / 128, 128, 0, stream>>>(
         static_cast<const unsigned long long*>(run_starts), total_slot, partition_count, probe_tiles,
@@ -1118,7 +1145,7 @@ int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const h
     params.dup_offsets = static_cast<const unsigned long long*>(dup_offsets);
     params.dup_positions = static_cast<const uint32_t*>(dup_positions);
     // size the output exactly: count + scan, read the total, then write
-    join_probe_count_kernel<<<probe_grid, kJoinThreads, 0, stream>>>(params);
+    count_kernel<<<count_grid, kJoinThreads, 0, stream>>>(params);
     HYB_CUDA(cudaGetLastError());
     HYB_TRY(run_exclusive_scan(context, static_cast<uint32_t*>(histogram), static_cast<unsigned long long*>(run_starts),
                                histogram_entries, total_slot));
@@ -1196,6 +1223,81 @@ int hyb_join_materialize(hyb_context* context, const hyb_join_side* side, uint32
   timing_kernel_end(context);
   timing_end(context, 1, info.positions * 16, info.positions, info.positions);
   HYB_CUDA(cudaStreamSynchronize(context->stream));  // the caller hands the buffers to NCCL on another stream
+  return HYB_OK;
+}
+
+int hyb_join_partition(hyb_context* context, const hyb_join_side* side, uint32_t partition_count, uint32_t chunk_id_base,
+                       void* out_keys_device, void* out_row_ids_device, uint64_t* out_partition_offsets) {
+  HYB_CHECK(context && side && out_partition_offsets, HYB_ERR_INVALID, "NULL argument");
+  HYB_CHECK(partition_count >= 1 && partition_count <= kMaxPartitions && (partition_count & (partition_count - 1)) == 0,
+            HYB_ERR_INVALID, "partition_count must be a power of two <= 256");
+  DeviceGuard guard(context->device);
+  std::lock_guard<std::mutex> lock(context->mutex);
+  SideInfo info;
+  HYB_TRY(prepare_side(context, side, &info));
+  HYB_CHECK(info.positions == 0 || (out_keys_device && out_row_ids_device), HYB_ERR_INVALID, "output buffers are NULL");
+  HYB_CHECK(info.positions < 0xFFFFFFF0ull, HYB_ERR_UNSUPPORTED, "more than 2^32 - 16 rows per join side");
+  cudaStream_t stream = context->stream;
+  for (uint32_t p = 0; p <= partition_count; ++p) out_partition_offsets[p] = 0;
+  timing_begin(context);
+  const uint32_t tiles = info.source.tile_count;
+  if (tiles == 0) {
+    timing_kernel_begin(context);
+    timing_kernel_end(context);
+    timing_end(context, 0, 0, 0, 0);
+    return HYB_OK;
+  }
+  // Same machinery as the probe: count per (partition, tile) -> exclusive scan -> ranked write. No table, no lookups.
+  const size_t histogram_entries = size_t{partition_count} * tiles;
+  void* histogram = nullptr;
+  void* run_starts = nullptr;
+  void* control = nullptr;
+  void* offsets = nullptr;
+  HYB_TRY(device_alloc(context, sizeof(uint32_t) * histogram_entries, &histogram));
+  HYB_TRY(device_alloc(context, sizeof(uint64_t) * histogram_entries, &run_starts));
+  HYB_TRY(device_alloc(context, 64, &control));
+  HYB_TRY(device_alloc(context, sizeof(uint64_t) * (size_t{partition_count} + 1), &offsets));
+  HYB_CUDA(cudaMemsetAsync(control, 0, 64, stream));
+  auto* flags = static_cast<uint32_t*>(control);
+  auto* total_slot = reinterpret_cast<unsigned long long*>(flags + 4);
+  ProbeParams params{};
+  params.probe = info.source;
+  params.build = info.source;
+  params.mode = kModePartition;
+  params.partition_mask = partition_count - 1;
+  params.partition_count = partition_count;
+  params.unique_build = 1;
+  params.flags = flags;
+  params.histogram = static_cast<uint32_t*>(histogram);
+  params.run_starts = static_cast<const unsigned long long*>(run_starts);
+  params.overflow = flags + 2;
+  params.out_build = static_cast<hyb_row_id*>(out_keys_device);
+  params.out_probe = static_cast<hyb_row_id*>(out_row_ids_device);
+  params.out_capacity = info.positions;
+  params.chunk_id_base = chunk_id_base;
+  int count_blocks = 1, write_blocks = 1;
+  HYB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&count_blocks, join_probe_count_kernel<false>, kJoinThreads, 0));
+  HYB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&write_blocks, join_probe_write_kernel<false>, kJoinThreads, 0));
+  timing_kernel_begin(context);
+  join_probe_count_kernel<false><<<std::min<uint32_t>(tiles, context->sm_count * std::max(count_blocks, 1)), kJoinThreads, 0, stream>>>(params);
+  HYB_CUDA(cudaGetLastError());
+  HYB_TRY(run_exclusive_scan(context, static_cast<uint32_t*>(histogram), static_cast<unsigned long long*>(run_starts),
+                             histogram_entries, total_slot));
+  join_probe_write_kernel<false><<<std::min<uint32_t>(tiles, context->sm_count * std::max(write_blocks, 1)), kJoinThreads, 0, stream>>>(params);
+  HYB_CUDA(cudaGetLastError());
+  join_partition_offsets_kernel<<<(partition_count + 1 + 127) / 128, 128, 0, stream>>>(
+      static_cast<const unsigned long long*>(run_starts), total_slot, partition_count, tiles,
+      static_cast<unsigned long long*>(offsets));
+  HYB_CUDA(cudaGetLastError());
+  timing_kernel_end(context);
+  HYB_CUDA(cudaMemcpyAsync(out_partition_offsets, offsets, sizeof(uint64_t) * (size_t{partition_count} + 1),
+                           cudaMemcpyDeviceToHost, stream));
+  timing_end(context, 4, info.positions * 16, info.positions, 0);
+  HYB_CUDA(cudaStreamSynchronize(stream));  // the caller hands the buffers to NCCL on another stream
+  device_free(context, histogram);
+  device_free(context, run_starts);
+  device_free(context, control);
+  device_free(context, offsets);
   return HYB_OK;
 }
 

@@ -637,6 +637,7 @@ int hyb_table_scan(hyb_context* context, hyb_table_t table_handle, const hyb_sca
   result->table = table_handle;
   result->chunk_count = chunk_count;
   result->stream = context->stream;
+  result->owner = context;
   const DevSegment* column_segments = table->d_segments + size_t{predicate->column_id} * chunk_count;
   uint32_t launches = 1;
   uint64_t input_rows = 0, input_bytes = 0;

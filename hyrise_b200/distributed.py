@@ -312,29 +312,75 @@ def exchange_tuples_masked(keys: torch.Tensor, row_ids: torch.Tensor) -> tuple[t
     return received[:, 0].contiguous(), received[:, 1].contiguous()
 
 
-class DeviceTupleTable:
-    """Received {key, RowID} tuples as a one-chunk device table (ValueSegment<int64> of keys) for hyb_join_hash."""
+def device_partition_side(device_context, table, column_id: int, chunk_id_base: int, world: int, torch_device: torch.device,
+                          filter_handle: int = 0):
+    """hyb_join_partition: the side's non-NULL {key, global RowID} tuples grouped by owner rank (key & (world - 1)), stable.
+    Returns (keys, packed RowIDs, offsets) — device tensors and world + 1 host offsets; group d is [offsets[d], offsets[d+1])."""
+    import ctypes as C
 
-    def __init__(self, device_context, keys: torch.Tensor, row_ids: torch.Tensor):
+    side = capi.JoinSide(table.handle, column_id, filter_handle)
+    positions = C.c_uint64()
+    capi.check(device_context.lib.hyb_join_side_positions(device_context.ptr, C.byref(side), C.byref(positions)))
+    n = positions.value
+    keys = torch.empty(n + 8, dtype=torch.int64, device=torch_device)
+    row_ids = torch.empty(n + 8, dtype=torch.int64, device=torch_device)
+    torch.cuda.current_stream(torch_device).synchronize()  # the buffers' previous users ran on torch's stream
+    offsets = (C.c_uint64 * (world + 1))()
+    capi.check(device_context.lib.hyb_join_partition(device_context.ptr, C.byref(side), world, chunk_id_base, keys.data_ptr(),
+                                                     row_ids.data_ptr(), offsets))
+    return keys, row_ids, [int(v) for v in offsets]
+
+
+def exchange_partitioned(sides: Sequence[tuple[torch.Tensor, torch.Tensor, list[int]]]):
+    """The exchange step of the radix join: for every side (keys, RowIDs, offsets) group d goes to rank d. ONE count
+    all-to-all for all sides, then one payload all-to-all per array, written straight into buffers that
+    hyb_table_append_chunk_device can adopt (8 spare elements after the last key). Returns [(keys, RowIDs, count)]."""
+    rank, world = _world()
+    device = sides[0][0].device
+    send_counts = [[offsets[d + 1] - offsets[d] for d in range(world)] for _, _, offsets in sides]
+    if world == 1:
+        return [(keys, row_ids, offsets[-1]) for keys, row_ids, offsets in sides]
+    send = torch.tensor(send_counts, dtype=torch.int64, device=device).t().contiguous()  # [destination][side]
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send)
+    recv_counts = recv.t().tolist()  # [side][source]
+    out = []
+    for index, (keys, row_ids, offsets) in enumerate(sides):
+        total = sum(recv_counts[index])
+        recv_keys = torch.empty(total + 8, dtype=torch.int64, device=device)
+        recv_rows = torch.empty(total + 8, dtype=torch.int64, device=device)
+        dist.all_to_all_single(recv_keys[:total], keys[:offsets[-1]], recv_counts[index], send_counts[index])
+        dist.all_to_all_single(recv_rows[:total], row_ids[:offsets[-1]], recv_counts[index], send_counts[index])
+        out.append((recv_keys, recv_rows, total))
+    return out
+
+
+class DeviceTupleTable:
+    """Received {key, RowID} tuples as a one-chunk device table (ValueSegment<int64> of keys) for hyb_join_hash. `keys`
+    must have 8 spare elements after the first `count` (Arena::kTailPad contract of hyb_table_append_chunk_device)."""
+
+    def __init__(self, device_context, keys: torch.Tensor, row_ids: torch.Tensor, count: int | None = None):
         import ctypes as C
         from .device import DeviceTable
 
         self.device_context = device_context
-        n = int(keys.shape[0])
-        # 64 readable bytes after the last element (Arena::kTailPad contract of hyb_table_append_chunk_device)
-        self.keys = torch.empty(n + 8, dtype=torch.int64, device=keys.device)
-        self.keys[:n] = keys
-        self.row_ids = row_ids
-        self.count = n
+        if count is None:  # unpadded input: copy into a padded buffer
+            count = int(keys.shape[0])
+            padded = torch.empty(count + 8, dtype=torch.int64, device=keys.device)
+            padded[:count] = keys
+            keys = padded
+        self.keys = keys
+        self.row_ids = row_ids[:count]
+        self.count = count
         handle = C.c_uint64()
         capi.check(device_context.lib.hyb_table_create(device_context.ptr, 1, C.byref(handle)))
-        if n:
+        if count:
             desc = capi.SegmentDesc()
             desc.encoding = capi.ENC_UNENCODED
             desc.data_type = capi.TYPE_INT64
-            desc.row_count = n
+            desc.row_count = count
             desc.values = self.keys.data_ptr()
-            torch.cuda.synchronize(keys.device)
+            torch.cuda.current_stream(keys.device).synchronize()  # NCCL wrote the buffer on torch's stream
             capi.check(device_context.lib.hyb_table_append_chunk_device(device_context.ptr, handle.value, C.byref(desc)))
         self.table = DeviceTable(device_context, handle.value, None, None)
 
@@ -347,12 +393,13 @@ def device_distributed_join(device_context, build_table, build_column: int, prob
     """Inner JoinHash across ranks: materialise both sides, ONE all-to-all per side, join the received tuples locally.
     Returns (pair count on this rank, partition offsets, build RowIDs, probe RowIDs) with GLOBAL RowIDs, the rank's part
     of the reference-ordered result (partitions p with p % world == rank)."""
-    build_keys, build_rows = device_materialize_side(device_context, build_table, build_column, build_chunk_base, torch_device)
-    probe_keys, probe_rows = device_materialize_side(device_context, probe_table, probe_column, probe_chunk_base, torch_device)
-    build_keys, build_rows = exchange_tuples_masked(build_keys, build_rows)
-    probe_keys, probe_rows = exchange_tuples_masked(probe_keys, probe_rows)
-    build = DeviceTupleTable(device_context, build_keys, build_rows)
-    probe = DeviceTupleTable(device_context, probe_keys, probe_rows)
+    _, world = _world()
+    assert world & (world - 1) == 0, "the radix exchange needs a power-of-two world size"
+    sides = [device_partition_side(device_context, build_table, build_column, build_chunk_base, world, torch_device),
+             device_partition_side(device_context, probe_table, probe_column, probe_chunk_base, world, torch_device)]
+    (build_keys, build_rows, build_count), (probe_keys, probe_rows, probe_count) = exchange_partitioned(sides)
+    build = DeviceTupleTable(device_context, build_keys, build_rows, build_count)
+    probe = DeviceTupleTable(device_context, probe_keys, probe_rows, probe_count)
     try:
         if probe.count == 0 or build.count == 0:
             empty = np.zeros(0, dtype=np.int64)

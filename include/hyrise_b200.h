@@ -322,6 +322,19 @@ int hyb_join_side_positions(hyb_context* context, const hyb_join_side* side, uin
 int hyb_join_materialize(hyb_context* context, const hyb_join_side* side, uint32_t chunk_id_base, void* out_keys_device,
                          void* out_row_ids_device);
 
+/*
+ * Multi-GPU radix exchange, sender side in one step (materialize_input + partition_by_radix, join_hash_steps.hpp:274-420
+ * and :422-560, with the RANK that owns a radix partition as the partition): writes the side's non-NULL {key, RowID}
+ * tuples into caller-provided DEVICE buffers of hyb_join_side_positions() elements each, grouped by
+ * key & (partition_count - 1) and in row order inside a group (a stable split, so that the receiving rank sees the rows
+ * of every source rank in their original order). out_keys[i] = key as int64, out_row_ids[i] = {chunk_id + chunk_id_base,
+ * chunk_offset}. out_partition_offsets (HOST, partition_count + 1 entries): group p occupies [offsets[p], offsets[p + 1]).
+ * The host layer sends group p to rank p with one all-to-all (NCCL) and joins what it received with
+ * hyb_table_append_chunk_device + hyb_join_hash. partition_count: power of two <= 256.
+ */
+int hyb_join_partition(hyb_context* context, const hyb_join_side* side, uint32_t partition_count, uint32_t chunk_id_base,
+                       void* out_keys_device, void* out_row_ids_device, uint64_t* out_partition_offsets);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * AggregateHash (with optionally fused scan predicates and Projection arithmetic)
  * ---------------------------------------------------------------------------------------------------------------- */

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as orc
-from helpers import ENCODINGS, random_table, row_ids_equal, tbl
+from helpers import ENCODINGS, random_table, row_ids_equal, rows_with_keys, tbl
 from hyrise_b200 import capi
 from hyrise_b200.device import Predicate
 from hyrise_b200.storage import ColumnDefinition, Table
@@ -173,3 +173,42 @@ def test_generated_sf1_properties(device):
     orders_dev.drop()
     lineitem_dev.drop()
     tables.close()
+
+
+@pytest.mark.parametrize("partition_count", [1, 2, 8])
+def test_partition_for_exchange(device, partition_count):
+    """hyb_join_partition: stable split of the non-NULL {key, RowID} tuples by key & (partition_count - 1)."""
+    import ctypes as C
+
+    import torch
+    rng = np.random.default_rng(11)
+    table = random_table(rng, 30_000, 4_099).encode("Automatic")
+    device_table = device.upload(table)
+    torch_device = torch.device("cuda", 0)
+    for column, filtered in ((0, False), (1, False), (4, True)):
+        scan = device.table_scan(device_table, Predicate(4, capi.PRED_LESS_THAN, 200)) if filtered else None
+        host_filter = orc.table_scan(table, Predicate(4, capi.PRED_LESS_THAN, 200)) if filtered else None
+        side = capi.JoinSide(device_table.handle, column, scan.handle if scan else 0)
+        positions = C.c_uint64()
+        capi.check(device.lib.hyb_join_side_positions(device.ptr, C.byref(side), C.byref(positions)))
+        keys = torch.zeros(positions.value + 8, dtype=torch.int64, device=torch_device)
+        row_ids = torch.zeros(positions.value + 8, dtype=torch.int64, device=torch_device)
+        torch.cuda.synchronize()
+        offsets = (C.c_uint64 * (partition_count + 1))()
+        capi.check(device.lib.hyb_join_partition(device.ptr, C.byref(side), partition_count, 1000, keys.data_ptr(),
+                                                 row_ids.data_ptr(), offsets))
+        offsets = np.array(offsets[:], dtype=np.int64)
+        # expectation from the host copy of the table: rows in order, NULL keys dropped, stable split by the low key bits
+        rows = rows_with_keys(table, column, host_filter)
+        want_keys = np.array([key for _, key in rows if key is not None], dtype=np.int64)
+        want_rows = np.array([(chunk_id + 1000) | (offset << 32) for (chunk_id, offset), key in rows if key is not None],
+                             dtype=np.int64)
+        owner = want_keys & (partition_count - 1)
+        order = np.argsort(owner, kind="stable")
+        assert offsets[-1] == len(want_keys)
+        assert np.array_equal(np.diff(offsets), np.bincount(owner, minlength=partition_count))
+        assert np.array_equal(keys[:offsets[-1]].cpu().numpy(), want_keys[order])
+        assert np.array_equal(row_ids[:offsets[-1]].cpu().numpy(), want_rows[order])
+        if scan:
+            scan.free()
+    device_table.drop()

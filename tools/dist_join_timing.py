@@ -14,13 +14,13 @@ lb = hd.chunk_bases(tables.lineitem.chunk_count, td)[rank]; ob = hd.chunk_bases(
 def sync(): device.synchronize(); torch.cuda.synchronize()
 for i in range(6):
     sync(); t0 = time.time()
-    bk, br = hd.device_materialize_side(device, orders, O_ORDERKEY, ob, td)
-    pk, pr = hd.device_materialize_side(device, lineitem, L_ORDERKEY, lb, td); sync(); t1 = time.time()
-    bk, br = hd.exchange_tuples_masked(bk, br); pk, pr = hd.exchange_tuples_masked(pk, pr); sync(); t2 = time.time()
-    build = hd.DeviceTupleTable(device, bk, br); probe = hd.DeviceTupleTable(device, pk, pr); sync(); t3 = time.time()
+    sides = [hd.device_partition_side(device, orders, O_ORDERKEY, ob, world, td),
+             hd.device_partition_side(device, lineitem, L_ORDERKEY, lb, world, td)]; sync(); t1 = time.time()
+    (bk, br, bn), (pk, pr, pn) = hd.exchange_partitioned(sides); sync(); t2 = time.time()
+    build = hd.DeviceTupleTable(device, bk, br, bn); probe = hd.DeviceTupleTable(device, pk, pr, pn); sync(); t3 = time.time()
     result = device.join_hash(build.table, 0, probe.table, 0, capi.JOIN_INNER, 8); st = device.last_stats(); sync(); t4 = time.time()
     if rank == 0:
-        print(f"materialize {1e3*(t1-t0):.1f} exchange {1e3*(t2-t1):.1f} tables {1e3*(t3-t2):.1f} join wall {1e3*(t4-t3):.1f} "
+        print(f"partition {1e3*(t1-t0):.1f} exchange {1e3*(t2-t1):.1f} tables {1e3*(t3-t2):.1f} join wall {1e3*(t4-t3):.1f} "
               f"kernel {st.dominant_kernel_ms:.2f} op {st.device_ms:.2f} pairs {result.info()[0]} build {build.count} probe {probe.count}", flush=True)
     result.free(); build.drop(); probe.drop()
 dist.destroy_process_group()
