@@ -20,6 +20,7 @@
 // NULL group first and the LAST row as representative when the immediate-key shortcut applies (:781-804, :367).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <numeric>
@@ -524,6 +525,7 @@ struct FastPlan {
   unsigned long long* partial_raw_nulls;      // [cta][G][C]
   unsigned long long* partial_product_nulls;  // [cta][G][C]
   uint32_t* overflow;                    // set when a CTA sees more than G groups
+  uint32_t prefetch_distance;            // iterations ahead to prefetch into L2 (0 = off)
 };
 
 template <int W>
@@ -622,6 +624,22 @@ __device__ __forceinline__ T warp_reduce_add(T value) {
   return value;
 }
 
+// Element j of a register-resident 8-array for a run-time j. Indexing such an array directly (a[j]) in a rolled loop
+// makes the compiler place the WHOLE array in local memory for its entire lifetime — measured as LDL/STL round trips on
+// every access of the hot path — so the rare rolled loops go through these select chains instead.
+template <typename T>
+__device__ __forceinline__ T pick8(const T (&array)[8], int j) {
+  T result = array[0];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) result = (j == k) ? array[k] : result;
+  return result;
+}
+template <typename T>
+__device__ __forceinline__ void put8(T (&array)[8], int j, T value) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) array[k] = (j == k) ? value : array[k];
+}
+
 constexpr int kFastThreads = 128;
 constexpr int kFastWarps = kFastThreads / 32;
 constexpr int kFastRowsPerWarp = kAggTileRows / kFastWarps;   // 1024 contiguous rows per warp and tile
@@ -645,8 +663,8 @@ __device__ __forceinline__ void add_where(long long& accumulator, long long valu
       : "l"(value), "r"(group), "r"(g));
 }
 
-template <int W, int G, int C>
-__global__ void __launch_bounds__(kFastThreads, 3) aggregate_fast_kernel(const FastPlan* __restrict__ plan_ptr) {
+template <int W, int G, int C, int kMinBlocks>
+__global__ void __launch_bounds__(kFastThreads, kMinBlocks) aggregate_fast_kernel(const FastPlan* __restrict__ plan_ptr) {
   using Value = typename WorkType<W>::Value;
   using Accumulator = typename WorkType<W>::Accumulator;
   const FastPlan& plan = *plan_ptr;
@@ -779,6 +797,20 @@ __global__ void __launch_bounds__(kFastThreads, 3) aggregate_fast_kernel(const F
     for (int it = 0; it < kFastIterations; ++it) {
       const uint32_t row0 = tile_row0 + warp * kFastRowsPerWarp + it * 256 + lane * 8;
       if (row0 >= chunk_rows) continue;
+      if (plan.prefetch_distance) {
+        // Pull the rows this thread reads `prefetch_distance` iterations from now into L2 (hint only, no registers held).
+        const uint32_t ahead = row0 + plan.prefetch_distance * 256;
+        if (ahead + 8 <= chunk_rows) {
+          for (uint32_t p = 0; p < plan.predicate_count; ++p) prefetch_codes(plan.predicate_segments[p][chunk], ahead);
+          if constexpr (G > 1) {
+            for (uint32_t q = 0; q < groupby_count; ++q) prefetch_codes(s_group_segment[q], ahead);
+          }
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            if (plan.value_segments[c] != nullptr) prefetch_codes(s_value_segment[c], ahead);
+          }
+        }
+      }
       uint32_t mask = chunk_rows - row0 >= 8 ? 0xFFu : ((1u << (chunk_rows - row0)) - 1u);
       for (uint32_t p = 0; p < plan.predicate_count && mask; ++p) {
         const ChunkTest& test = plan.predicate_tests[p][chunk];
@@ -822,9 +854,11 @@ __global__ void __launch_bounds__(kFastThreads, 3) aggregate_fast_kernel(const F
 #pragma unroll 1
         for (int j = 0; j < 8; ++j) {
           if (!((mask >> j) & 1u)) continue;
-          if (use_combos && group_of[j] != kComboUnresolved) {
-            if (group_of[j] == kComboOverflow) {
-              group_of[j] = -1;
+          const int32_t known = pick8(group_of, j);
+          const uint32_t combination = pick8(combo, j);
+          if (use_combos && known != kComboUnresolved) {
+            if (known == kComboOverflow) {
+              put8(group_of, j, int32_t{-1});
               mask &= ~(1u << j);
             }
             continue;
@@ -855,11 +889,11 @@ __global__ void __launch_bounds__(kFastThreads, 3) aggregate_fast_kernel(const F
           if (found < 0) {
             *plan.overflow = 1;  // more than G groups: the host reruns with a bigger G or the general kernel
             mask &= ~(1u << j);
-            if (use_combos) s_combo_group[combo[j]] = kComboOverflow;
+            if (use_combos) s_combo_group[combination] = kComboOverflow;
           } else if (use_combos) {
-            s_combo_group[combo[j]] = static_cast<uint8_t>(found);
+            s_combo_group[combination] = static_cast<uint8_t>(found);
           }
-          group_of[j] = found;
+          put8(group_of, j, found);
         }
       }
 
@@ -962,9 +996,10 @@ __global__ void __launch_bounds__(kFastThreads, 3) aggregate_fast_kernel(const F
         if ((need_raw && (null_bits & mask)) || (need_product && (product_nulls & mask))) {
 #pragma unroll 1
           for (int j = 0; j < 8; ++j) {
-            if (!((mask >> j) & 1u) || group_of[j] < 0) continue;
-            if (need_raw && ((null_bits >> j) & 1u)) atomicAdd(&s_null_counts[0][group_of[j]][c], 1ull);
-            if (need_product && ((product_nulls >> j) & 1u)) atomicAdd(&s_null_counts[1][group_of[j]][c], 1ull);
+            const int32_t group = pick8(group_of, j);
+            if (!((mask >> j) & 1u) || group < 0) continue;
+            if (need_raw && ((null_bits >> j) & 1u)) atomicAdd(&s_null_counts[0][group][c], 1ull);
+            if (need_product && ((product_nulls >> j) & 1u)) atomicAdd(&s_null_counts[1][group][c], 1ull);
           }
         }
       }
@@ -1039,15 +1074,34 @@ __global__ void __launch_bounds__(kFastThreads, 3) aggregate_fast_kernel(const F
 
 using FastKernel = void (*)(const FastPlan*);
 
+// Experiment switch (HYB_AGG_MIN_BLOCKS=3|4|5): resident CTAs per SM the register allocation is capped for.
+static int fast_min_blocks() {
+  const char* text = std::getenv("HYB_AGG_MIN_BLOCKS");
+  const int value = text ? std::atoi(text) : 3;
+  return value == 4 || value == 5 ? value : 3;
+}
+
+template <int W, int G, int C>
+static FastKernel fast_kernel_for_min_blocks() {
+  switch (fast_min_blocks()) {
+    case 4:
+      return aggregate_fast_kernel<W, G, C, 4>;
+    case 5:
+      return aggregate_fast_kernel<W, G, C, 5>;
+    default:
+      return aggregate_fast_kernel<W, G, C, 3>;
+  }
+}
+
 template <int W, int G>
 static FastKernel fast_kernel_for_columns(int columns) {
   switch (columns) {
     case 1:
-      return aggregate_fast_kernel<W, G, 1>;
+      return fast_kernel_for_min_blocks<W, G, 1>();
     case 2:
-      return aggregate_fast_kernel<W, G, 2>;
+      return fast_kernel_for_min_blocks<W, G, 2>();
     default:
-      return aggregate_fast_kernel<W, G, 4>;
+      return fast_kernel_for_min_blocks<W, G, 4>();
   }
 }
 
@@ -1458,6 +1512,10 @@ int hyb_aggregate_hash(hyb_context* context, const hyb_aggregate_query* query, h
       host_plan.tile_map = tile_map;
       host_plan.chunk_row_start = reinterpret_cast<const unsigned long long*>(table->d_chunk_row_start);
       host_plan.tile_count = tile_count;
+      {
+        const char* text = std::getenv("HYB_AGG_PREFETCH");
+        host_plan.prefetch_distance = text ? static_cast<uint32_t>(std::atoi(text)) : 0;
+      }
       host_plan.predicate_count = query->predicate_count;
       for (uint32_t p = 0; p < query->predicate_count; ++p) {
         host_plan.predicate_segments[p] = table->d_segments + size_t{query->predicates[p].column_id} * chunk_count;

@@ -54,6 +54,35 @@ __device__ __forceinline__ void st_volatile_u64(unsigned long long* ptr, unsigne
   asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(ptr), "l"(value) : "memory");
 }
 
+// Bytes per row of the vector a scan streams (codes of compressed segments, values of unencoded ones); 0 = bit-packed.
+__device__ __forceinline__ uint32_t segment_stream(const DevSegment& segment, const char*& base) {
+  if (segment.encoding == HYB_ENC_UNENCODED) {
+    base = static_cast<const char*>(segment.values);
+    return (segment.data_type == HYB_TYPE_INT32 || segment.data_type == HYB_TYPE_FLOAT32) ? 4u : 8u;
+  }
+  base = static_cast<const char*>(segment.av);
+  switch (segment.vector_type) {
+    case HYB_VEC_FIXED_1B:
+      return 1u;
+    case HYB_VEC_FIXED_2B:
+      return 2u;
+    case HYB_VEC_FIXED_4B:
+      return 4u;
+    default:
+      return 0u;
+  }
+}
+
+// L2 prefetch hint for the line holding `row` of a segment's streamed vector (no registers held, no fault on misuse of
+// the hint: callers still keep `row` inside the segment).
+__device__ __forceinline__ void prefetch_codes(const DevSegment& segment, uint32_t row) {
+  const char* base;
+  const uint32_t bytes_per_row = segment_stream(segment, base);
+  if (bytes_per_row == 0) return;
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(base + static_cast<size_t>(row) * bytes_per_row));
+}
+
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Compressed-vector decode: 8 consecutive entries starting at `row0` (row0 % 8 == 0) of a FixedWidthIntegerVector
 // (fixed_width_integer_vector.hpp:29-33) or BitPackingVector (compact_iterator.hpp:218-252: entry i occupies bits
