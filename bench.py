@@ -154,6 +154,25 @@ def cpu_arm(tables: TpchTables, sample_lineitem_chunks: int, steps: int, warmup:
                       f"orders chunks of the same generated tables", "detail": detail}
 
 
+def ncu_traffic(kernels, sf, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant operator's kernels, from the committed
+    `ncu --set full` capture of this workload (profiles/traffic.json, written by tools/make_profiles.py). None when the
+    capture was taken on another workload."""
+    path = os.path.join(REPO, "profiles", "traffic.json")
+    if not os.path.exists(path) or world != 1:
+        return None
+    capture = json.load(open(path))
+    if abs(capture.get("sf", -1) - sf) > 1e-9:
+        return None
+    total = 0.0
+    for kernel in kernels:
+        matches = [value for name, value in capture["kernels"].items() if name.split("<")[0] == kernel]
+        if not matches:
+            return None
+        total += matches[0]["dram_bytes_per_launch"]
+    return total
+
+
 def main() -> None:
     parser = argparse.ArgumentParser()
     parser.add_argument("--gpus", type=int, default=1)
@@ -226,6 +245,7 @@ def main() -> None:
 
     operators = {"scan": [], "join": [], "aggregate": []}
     launches = [0]
+    peers = None
     torch_device = torch.device("cuda", local_rank)
     if distributed:
         from hyrise_b200 import distributed as hd
@@ -233,11 +253,23 @@ def main() -> None:
         orders_chunk_base = hd.chunk_bases(tables.orders.chunk_count, torch_device)[rank]
         lineitem_row_base = rank * 0  # positions only order groups; per-rank offsets keep them disjoint
         radix_bits = 8 if args.sf * world >= 4 else 4
+        # Receive arenas for the fused split + NVLink P2P exchange; NCCL all-to-all of a local send buffer otherwise.
+        peers = None
+        if os.environ.get("HYB_EXCHANGE", "p2p") == "p2p":
+            try:
+                peers = hd.PeerExchange(device, torch_device, capacity=2 * rows + 65_536)
+            except Exception as error:  # noqa: BLE001 - CUDA IPC can be unavailable (container / driver policy)
+                print(f"[bench] rank {rank}: peer exchange unavailable ({error}); using the NCCL all-to-all path", file=sys.stderr)
+            flags = [None] * world
+            dist.all_gather_object(flags, peers is not None)
+            if not all(flags):
+                peers = None
 
     def distributed_join():
         """materialise {key, RowID} of both sides -> one NCCL all-to-all per side -> local hyb_join_hash on what arrived"""
         pairs, offsets, build_rows, probe_rows, result = hd.device_distributed_join(
-            device, orders, O_ORDERKEY, lineitem, L_ORDERKEY, radix_bits, orders_chunk_base, lineitem_chunk_base, torch_device)
+            device, orders, O_ORDERKEY, lineitem, L_ORDERKEY, radix_bits, orders_chunk_base, lineitem_chunk_base, torch_device,
+            peers=peers)
         stats = device.last_stats()
         return pairs, result, stats
 
@@ -372,11 +404,13 @@ def main() -> None:
                            "achieved_gbs": algorithmic / kernel_ms / 1e6, "frac": algorithmic / kernel_ms / 1e6 / peak,
                            "output_rows": int(samples[-1][3])}
     dominant = max(breakdown, key=lambda name: breakdown[name]["kernel_ms"])
-    kernel_names = {"scan": "scan_kernel", "join": "join_probe_count_kernel + scan + join_probe_write_kernel",
-                    "aggregate": "aggregate_fast_kernel<f32, 4 groups, 4 columns>"}
-    roofline = {"bound": "hbm", "kernel": kernel_names[dominant], "achieved": breakdown[dominant]["achieved_gbs"],
+    kernels_of = {"scan": ["scan_kernel"],
+                  "join": ["join_build_kernel", "join_probe_count_kernel", "exclusive_scan_kernel", "join_probe_write_kernel"],
+                  "aggregate": ["aggregate_fast_kernel"]}
+    roofline = {"bound": "hbm", "kernel": " + ".join(kernels_of[dominant]), "achieved": breakdown[dominant]["achieved_gbs"],
                 "peak": peak, "peak_source": peak_source, "unit": "GB/s", "frac": breakdown[dominant]["frac"],
-                "traffic": None, "algorithmic_bytes_per_launch": breakdown[dominant]["algorithmic_bytes"],
+                "traffic": ncu_traffic(kernels_of[dominant], args.sf, world),
+                "algorithmic_bytes_per_launch": breakdown[dominant]["algorithmic_bytes"],
                 "kernel_ms": breakdown[dominant]["kernel_ms"]}
 
     cpu_baseline = None
@@ -392,9 +426,13 @@ def main() -> None:
             "dtype": "int32 keys / u16 value-IDs / f32 arithmetic, f64 sums", "data": "synthetic",
             "config": {"workload": workload, "lineitem_rows_per_gpu": rows, "orders_rows_per_gpu": tables.orders.row_count,
                        "chunk_size": capi.DEFAULT_CHUNK_SIZE, "l2": "256 MB memset before every operator, inside the timed region",
-                       "parallelism": (f"{world} ranks: chunk-partitioned scan (no collective); join = radix all-to-all of "
-                                       f"{{key, RowID}} tuples (one per side) + local join; aggregate = local pre-aggregation + "
-                                       f"all-to-all of partial groups") if world > 1 else "1 GPU",
+                       "parallelism": (f"{world} ranks: chunk-partitioned scan (no collective); join = radix exchange of "
+                                       f"{{key, RowID}} tuples, one per side ("
+                                       + ("split kernel storing straight into the owners' memory over NVLink P2P; collectives: "
+                                          "count all-gather + barrier" if peers is not None else
+                                          "device split + NCCL all-to-all") +
+                                       ") + local join; aggregate = local pre-aggregation + all-to-all of partial groups")
+                       if world > 1 else "1 GPU",
                        "outputs_per_step": {"scan_matches": int(outputs[0]), "join_pairs": int(outputs[1]), "groups": int(outputs[2])}},
             "roofline": roofline, "operators": breakdown, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": launches[0], "clocks": clocks.summary(),

@@ -156,6 +156,11 @@ SYMBOLS = {
     "hyb_join_side_positions": [_CTX, C.POINTER(JoinSide), C.POINTER(_U64)],
     "hyb_join_materialize": [_CTX, C.POINTER(JoinSide), _U32, _P, _P],
     "hyb_join_partition": [_CTX, C.POINTER(JoinSide), _U32, _U32, _P, _P, C.POINTER(_U64)],
+    "hyb_join_partition_push": [_CTX, C.POINTER(JoinSide), _U32, _U32, _P, _P],
+    "hyb_exchange_arena_create": [_CTX, _U64, C.POINTER(_P), _P],
+    "hyb_exchange_arena_open": [_CTX, _P, C.POINTER(_P)],
+    "hyb_exchange_arena_close": [_CTX, _P],
+    "hyb_exchange_arena_destroy": [_CTX, _P],
     "hyb_aggregate_hash": [_CTX, C.POINTER(AggregateQuery), C.POINTER(_U64)],
     "hyb_aggregate_result_info": [_CTX, _U64, C.POINTER(_U64), C.POINTER(_I32)],
     "hyb_aggregate_result_row_ids": [_CTX, _U64, _P],
@@ -166,6 +171,10 @@ SYMBOLS = {
     "hyb_join_result_device_ptrs": [_CTX, _U64, C.POINTER(_P), C.POINTER(_P)],
     "hyb_context_stream": [_CTX, C.POINTER(_P)],
 }
+
+
+IPC_HANDLE_BYTES = 64
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p))
 
 
 class HyriseB200Error(RuntimeError):

@@ -27,6 +27,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 #include "device_utils.cuh"
 #include "internal.hpp"
@@ -42,6 +43,7 @@ constexpr unsigned long long kEmptySlot = ~0ull;
 constexpr int kMaxPartitions = 256;
 constexpr long long kWideKeyUnset = static_cast<long long>(0x8080808080808080ull);  // memset(0x80) pattern
 constexpr uint32_t kEmitWithoutPartner = 0xFFFFFFFEu;  // output row with a NULL build partner / Semi-Anti output row
+constexpr int kMaxPeers = 16;            // ranks of one NVSwitch domain addressed by hyb_join_partition_push
 constexpr int32_t kModePartition = 100;  // not a JoinMode: hyb_join_partition's stable split of {key, RowID} tuples by owner
 
 struct KeySource {
@@ -500,6 +502,11 @@ struct ProbeParams {
   uint32_t* overflow;                     // set when the output does not fit out_capacity (optimistic sizing)
   uint32_t chunk_id_base;                 // kModePartition: added to chunk ids (RowIDs of the global table)
   uint32_t fast;                          // Inner join, int32 keys on both sides, direct-address table without shift
+  // kModePartition with peer destinations (hyb_join_partition_push): group p is written to peer_keys[p] / peer_rows[p]
+  // (device memory of rank p, mapped through CUDA IPC — NVLink P2P stores) at the group-relative index.
+  long long* peer_keys[kMaxPeers];
+  long long* peer_rows[kMaxPeers];
+  uint32_t push_to_peers;
 };
 
 // What one probe row contributes. Returns the match word: a build position (unique build side), a table slot
@@ -674,15 +681,19 @@ __device__ __forceinline__ void probe_chunk(const ProbeParams& params, const Til
 template <bool kRank, uint32_t kCodec, bool kFull>
 __device__ __forceinline__ void probe_chunk_fast(const ProbeParams& params, const TileRef& ref, const DevSegment& segment,
                                                  uint32_t chunk0, uint32_t lane, uint32_t* histogram, ChunkRows& rows) {
+  constexpr bool kWide = kCodec == kCodecPlain64;  // int64 keys (the tuples of a radix exchange): 64-bit index arithmetic
   const uint32_t lanes_below = (1u << lane) - 1u;
   const uint32_t partition_mask = params.partition_mask;
   const uint32_t* __restrict__ direct = params.table.direct;
   const uint32_t direct_min = static_cast<uint32_t>(params.table.direct_min);
   const uint32_t direct_range = static_cast<uint32_t>(params.table.direct_range);
+  const unsigned long long wide_min = static_cast<unsigned long long>(params.table.direct_min);
+  const uint32_t shift = params.table.direct_shift;
+  const unsigned long long low_bits = (1ull << shift) - 1ull;
   const uint32_t row_count = segment.row_count;
   const uint32_t row_base = ref.row0 + chunk0 + lane;
   uint32_t for_minimum = 0;
-  if constexpr (kCodec >= kCodecFor8) {
+  if constexpr (kCodec >= kCodecFor8 && kCodec != kCodecPlain64) {
     if (kFull || ref.row0 + chunk0 < row_count) {
       for_minimum = static_cast<uint32_t>(__ldg(static_cast<const int32_t*>(segment.values) + (ref.row0 + chunk0) / HYB_FOR_BLOCK_SIZE));
     }
@@ -694,20 +705,30 @@ __device__ __forceinline__ void probe_chunk_fast(const ProbeParams& params, cons
     const uint32_t row = row_base + step * 32;
     const bool valid = kFull || row < row_count;
     uint32_t key = 0;
-    if (valid) {
-      if constexpr (kCodec == kCodecPlain32) {
-        key = ld_stream_u32(static_cast<const uint32_t*>(segment.values) + row);
-      } else if constexpr (kCodec == kCodecFor8) {
-        key = for_minimum + __ldg(static_cast<const uint8_t*>(segment.av) + row);
-      } else if constexpr (kCodec == kCodecFor16) {
-        key = for_minimum + __ldg(static_cast<const uint16_t*>(segment.av) + row);
-      } else {
-        key = for_minimum + ld_stream_u32(static_cast<const uint32_t*>(segment.av) + row);
-      }
-    }
-    const uint32_t index = key - direct_min;  // wraps above the range for keys below the minimum
     uint32_t match = kNoMatch;
-    if (valid && index < direct_range) match = __ldg(direct + index);
+    if constexpr (kWide) {
+      if (valid) {
+        const uint2 bits = ld_stream_v2(static_cast<const long long*>(segment.values) + row);
+        key = bits.x;  // the partition only needs the low bits
+        const unsigned long long offset = ((static_cast<unsigned long long>(bits.y) << 32) | bits.x) - wide_min;
+        const unsigned long long index = offset >> shift;
+        if (index < direct_range && !(offset & low_bits)) match = __ldg(direct + index);
+      }
+    } else {
+      if (valid) {
+        if constexpr (kCodec == kCodecPlain32) {
+          key = ld_stream_u32(static_cast<const uint32_t*>(segment.values) + row);
+        } else if constexpr (kCodec == kCodecFor8) {
+          key = for_minimum + __ldg(static_cast<const uint8_t*>(segment.av) + row);
+        } else if constexpr (kCodec == kCodecFor16) {
+          key = for_minimum + __ldg(static_cast<const uint16_t*>(segment.av) + row);
+        } else {
+          key = for_minimum + ld_stream_u32(static_cast<const uint32_t*>(segment.av) + row);
+        }
+      }
+      const uint32_t index = key - direct_min;  // wraps above the range for keys below the minimum
+      if (valid && index < direct_range) match = __ldg(direct + index);
+    }
     const uint32_t partition = key & partition_mask;
     if constexpr (!kRank) {
       // Counting needs no order: one shared-memory reduction per emitting lane (measured 1.3 cycles per warp instruction
@@ -738,13 +759,18 @@ __device__ __forceinline__ void probe_chunk_fast_any_codec(const ProbeParams& pa
       return probe_chunk_fast<kRank, kCodecFor8, kFull>(params, ref, segment, chunk0, lane, histogram, rows);
     case kCodecFor16:
       return probe_chunk_fast<kRank, kCodecFor16, kFull>(params, ref, segment, chunk0, lane, histogram, rows);
+    case kCodecPlain64:
+      return probe_chunk_fast<kRank, kCodecPlain64, kFull>(params, ref, segment, chunk0, lane, histogram, rows);
     default:
       return probe_chunk_fast<kRank, kCodecFor32, kFull>(params, ref, segment, chunk0, lane, histogram, rows);
   }
 }
 
+// params.fast: 1 = int32 keys on both sides, unshifted direct table (32-bit arithmetic for every plain / FoR codec);
+// 2 = int64 probe keys against a (possibly shifted) direct table: plain int64 segments only.
 __device__ __forceinline__ bool fast_tile(const ProbeParams& params, uint32_t codec) {
-  return params.fast && params.unique_build && codec != kCodecGeneric && codec != kCodecPlain64;
+  if (!params.unique_build || codec == kCodecGeneric) return false;
+  return params.fast == 1 ? codec != kCodecPlain64 : (params.fast == 2 && codec == kCodecPlain64);
 }
 
 template <bool kRank, int kSource>
@@ -882,9 +908,17 @@ __global__ void __launch_bounds__(kJoinThreads, 3) join_probe_write_kernel(const
         long long key = 0;
         bool is_null = false;
         load_key1(params.probe, ref, segment, index, key, is_null);
-        st_stream_v2(params.out_build + at, static_cast<uint32_t>(static_cast<unsigned long long>(key)),
+        hyb_row_id* key_out = params.out_build + at;
+        hyb_row_id* row_out = params.out_probe + at;
+        if (params.push_to_peers) {
+          // index inside the group = position in the partition-major output minus the group's start
+          const unsigned long long inside = at - params.run_starts[static_cast<size_t>(partition) * params.probe.tile_count];
+          key_out = reinterpret_cast<hyb_row_id*>(params.peer_keys[partition] + inside);
+          row_out = reinterpret_cast<hyb_row_id*>(params.peer_rows[partition] + inside);
+        }
+        st_stream_v2(key_out, static_cast<uint32_t>(static_cast<unsigned long long>(key)),
                      static_cast<uint32_t>(static_cast<unsigned long long>(key) >> 32));
-        st_stream_v2(params.out_probe + at, probe_row.chunk_id + params.chunk_id_base, probe_row.chunk_offset);
+        st_stream_v2(row_out, probe_row.chunk_id + params.chunk_id_base, probe_row.chunk_offset);
       } else if (match == kEmitWithoutPartner) {
         if (emit_build) st_stream_v2(params.out_build + at, HYB_INVALID_CHUNK_ID, HYB_INVALID_CHUNK_OFFSET);
         st_stream_v2(params.out_probe + at, probe_row.chunk_id, probe_row.chunk_offset);
@@ -1194,7 +1228,7 @@ int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const h
     params.partition_mask = partition_count - 1;
     params.partition_count = partition_count;
     params.unique_build = 1;  // optimistic: a flag raised by the build kernel sends us to the position-list path below
-    params.fast = mode == HYB_JOIN_INNER && direct && direct_shift == 0 && !wide;
+    params.fast = (mode == HYB_JOIN_INNER && direct) ? ((direct_shift == 0 && !wide) ? 1u : (probe.data_type == HYB_TYPE_INT64 ? 2u : 0u)) : 0u;
     params.build_is_empty = build.positions == 0;
     params.flags = flags;
     params.matches = static_cast<uint32_t*>(matches);
@@ -1349,29 +1383,26 @@ int hyb_join_materialize(hyb_context* context, const hyb_join_side* side, uint32
   return HYB_OK;
 }
 
-int hyb_join_partition(hyb_context* context, const hyb_join_side* side, uint32_t partition_count, uint32_t chunk_id_base,
-                       void* out_keys_device, void* out_row_ids_device, uint64_t* out_partition_offsets) {
-  HYB_CHECK(context && side && out_partition_offsets, HYB_ERR_INVALID, "NULL argument");
+// Shared by hyb_join_partition (local output buffers) and hyb_join_partition_push (peer destinations chosen by `exchange`
+// after the counts are known).
+static int partition_side(hyb_context* context, const hyb_join_side* side, uint32_t partition_count, uint32_t chunk_id_base,
+                          void* out_keys_device, void* out_row_ids_device, uint64_t* out_partition_offsets,
+                          hyb_exchange_fn exchange, void* user) {
   HYB_CHECK(partition_count >= 1 && partition_count <= kMaxPartitions && (partition_count & (partition_count - 1)) == 0,
             HYB_ERR_INVALID, "partition_count must be a power of two <= 256");
+  HYB_CHECK(!exchange || partition_count <= kMaxPeers, HYB_ERR_INVALID, "at most 16 peers");
   DeviceGuard guard(context->device);
   std::lock_guard<std::mutex> lock(context->mutex);
   SideInfo info;
   HYB_TRY(prepare_side(context, side, &info));
-  HYB_CHECK(info.positions == 0 || (out_keys_device && out_row_ids_device), HYB_ERR_INVALID, "output buffers are NULL");
+  HYB_CHECK(exchange || info.positions == 0 || (out_keys_device && out_row_ids_device), HYB_ERR_INVALID, "output buffers are NULL");
   HYB_CHECK(info.positions < 0xFFFFFFF0ull, HYB_ERR_UNSUPPORTED, "more than 2^32 - 16 rows per join side");
   cudaStream_t stream = context->stream;
-  for (uint32_t p = 0; p <= partition_count; ++p) out_partition_offsets[p] = 0;
+  std::vector<uint64_t> offsets_host(size_t{partition_count} + 1, 0);
   timing_begin(context);
   const uint32_t tiles = info.source.tile_count;
-  if (tiles == 0) {
-    timing_kernel_begin(context);
-    timing_kernel_end(context);
-    timing_end(context, 0, 0, 0, 0);
-    return HYB_OK;
-  }
   // Same machinery as the probe: count per (partition, tile) -> exclusive scan -> ranked write. No table, no lookups.
-  const size_t histogram_entries = size_t{partition_count} * tiles;
+  const size_t histogram_entries = size_t{partition_count} * std::max<uint32_t>(tiles, 1);
   void* histogram = nullptr;
   void* run_starts = nullptr;
   void* control = nullptr;
@@ -1401,26 +1432,116 @@ int hyb_join_partition(hyb_context* context, const hyb_join_side* side, uint32_t
   int count_blocks = 1, write_blocks = 1;
   HYB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&count_blocks, join_probe_count_kernel<false>, kJoinThreads, 0));
   HYB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&write_blocks, join_probe_write_kernel<false>, kJoinThreads, 0));
+  uint32_t launches = 0;
   timing_kernel_begin(context);
-  join_probe_count_kernel<false><<<std::min<uint32_t>(tiles, context->sm_count * std::max(count_blocks, 1)), kJoinThreads, 0, stream>>>(params);
-  HYB_CUDA(cudaGetLastError());
-  HYB_TRY(run_exclusive_scan(context, static_cast<uint32_t*>(histogram), static_cast<unsigned long long*>(run_starts),
-                             histogram_entries, total_slot));
-  join_probe_write_kernel<false><<<std::min<uint32_t>(tiles, context->sm_count * std::max(write_blocks, 1)), kJoinThreads, 0, stream>>>(params);
-  HYB_CUDA(cudaGetLastError());
-  join_partition_offsets_kernel<<<(partition_count + 1 + 127) / 128, 128, 0, stream>>>(
-      static_cast<const unsigned long long*>(run_starts), total_slot, partition_count, tiles,
-      static_cast<unsigned long long*>(offsets));
-  HYB_CUDA(cudaGetLastError());
-  timing_kernel_end(context);
-  HYB_CUDA(cudaMemcpyAsync(out_partition_offsets, offsets, sizeof(uint64_t) * (size_t{partition_count} + 1),
-                           cudaMemcpyDeviceToHost, stream));
-  timing_end(context, 4, info.positions * 16, info.positions, 0);
-  HYB_CUDA(cudaStreamSynchronize(stream));  // the caller hands the buffers to NCCL on another stream
+  if (tiles) {
+    join_probe_count_kernel<false><<<std::min<uint32_t>(tiles, context->sm_count * std::max(count_blocks, 1)), kJoinThreads, 0, stream>>>(params);
+    HYB_CUDA(cudaGetLastError());
+    HYB_TRY(run_exclusive_scan(context, static_cast<uint32_t*>(histogram), static_cast<unsigned long long*>(run_starts),
+                               histogram_entries, total_slot));
+    join_partition_offsets_kernel<<<(partition_count + 1 + 127) / 128, 128, 0, stream>>>(
+        static_cast<const unsigned long long*>(run_starts), total_slot, partition_count, tiles,
+        static_cast<unsigned long long*>(offsets));
+    HYB_CUDA(cudaGetLastError());
+    launches += 3;
+    if (exchange) {
+      // The destinations depend on what every other rank sends: hand the counts to the host layer (one small
+      // all-gather) and get the peer pointers this rank's groups start at.
+      timing_kernel_end(context);
+      HYB_CUDA(cudaMemcpyAsync(offsets_host.data(), offsets, sizeof(uint64_t) * offsets_host.size(), cudaMemcpyDeviceToHost, stream));
+      HYB_CUDA(cudaStreamSynchronize(stream));
+    }
+  }
+  if (exchange) {
+    std::vector<uint64_t> counts(partition_count);
+    for (uint32_t p = 0; p < partition_count; ++p) counts[p] = offsets_host[p + 1] - offsets_host[p];
+    void* dest_keys[kMaxPeers] = {};
+    void* dest_rows[kMaxPeers] = {};
+    const int status = exchange(user, counts.data(), dest_keys, dest_rows);
+    HYB_CHECK(status == 0, HYB_ERR_INVALID, "the exchange callback failed");
+    for (uint32_t p = 0; p < partition_count; ++p) {
+      HYB_CHECK(counts[p] == 0 || (dest_keys[p] && dest_rows[p]), HYB_ERR_INVALID, "the exchange callback left a destination NULL");
+      params.peer_keys[p] = static_cast<long long*>(dest_keys[p]);
+      params.peer_rows[p] = static_cast<long long*>(dest_rows[p]);
+    }
+    params.push_to_peers = 1;
+    params.out_capacity = ~0ull;
+    if (tiles) timing_kernel_begin(context);
+  }
+  if (tiles) {
+    join_probe_write_kernel<false><<<std::min<uint32_t>(tiles, context->sm_count * std::max(write_blocks, 1)), kJoinThreads, 0, stream>>>(params);
+    HYB_CUDA(cudaGetLastError());
+    ++launches;
+    timing_kernel_end(context);
+    if (!exchange) {
+      HYB_CUDA(cudaMemcpyAsync(offsets_host.data(), offsets, sizeof(uint64_t) * offsets_host.size(), cudaMemcpyDeviceToHost, stream));
+    }
+  } else if (!exchange) {
+    timing_kernel_end(context);
+  }
+  timing_end(context, launches, info.positions * 16, info.positions, 0);
+  HYB_CUDA(cudaStreamSynchronize(stream));  // local: the caller hands the buffers to NCCL; push: stores to peers are done
   device_free(context, histogram);
   device_free(context, run_starts);
   device_free(context, control);
   device_free(context, offsets);
+  if (out_partition_offsets) {
+    for (uint32_t p = 0; p <= partition_count; ++p) out_partition_offsets[p] = offsets_host[p];
+  }
+  return HYB_OK;
+}
+
+int hyb_join_partition(hyb_context* context, const hyb_join_side* side, uint32_t partition_count, uint32_t chunk_id_base,
+                       void* out_keys_device, void* out_row_ids_device, uint64_t* out_partition_offsets) {
+  HYB_CHECK(context && side && out_partition_offsets, HYB_ERR_INVALID, "NULL argument");
+  return partition_side(context, side, partition_count, chunk_id_base, out_keys_device, out_row_ids_device,
+                        out_partition_offsets, nullptr, nullptr);
+}
+
+int hyb_join_partition_push(hyb_context* context, const hyb_join_side* side, uint32_t world_size, uint32_t chunk_id_base,
+                            hyb_exchange_fn exchange, void* user) {
+  HYB_CHECK(context && side && exchange, HYB_ERR_INVALID, "NULL argument");
+  return partition_side(context, side, world_size, chunk_id_base, nullptr, nullptr, nullptr, exchange, user);
+}
+
+// ---- peer-visible receive arenas (CUDA IPC) ----------------------------------------------------------------------------
+int hyb_exchange_arena_create(hyb_context* context, uint64_t bytes, void** out_device_ptr, void* out_ipc_handle) {
+  HYB_CHECK(context && out_device_ptr && out_ipc_handle && bytes, HYB_ERR_INVALID, "NULL argument");
+  DeviceGuard guard(context->device);
+  void* base = nullptr;
+  HYB_CUDA(cudaMalloc(&base, bytes));
+  cudaIpcMemHandle_t handle;
+  const cudaError_t error = cudaIpcGetMemHandle(&handle, base);
+  if (error != cudaSuccess) {
+    cudaFree(base);
+    HYB_CUDA(error);
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == HYB_IPC_HANDLE_BYTES, "IPC handle size");
+  std::memcpy(out_ipc_handle, &handle, sizeof(handle));
+  *out_device_ptr = base;
+  return HYB_OK;
+}
+
+int hyb_exchange_arena_open(hyb_context* context, const void* ipc_handle, void** out_peer_ptr) {
+  HYB_CHECK(context && ipc_handle && out_peer_ptr, HYB_ERR_INVALID, "NULL argument");
+  DeviceGuard guard(context->device);
+  cudaIpcMemHandle_t handle;
+  std::memcpy(&handle, ipc_handle, sizeof(handle));
+  HYB_CUDA(cudaIpcOpenMemHandle(out_peer_ptr, handle, cudaIpcMemLazyEnablePeerAccess));
+  return HYB_OK;
+}
+
+int hyb_exchange_arena_close(hyb_context* context, void* peer_ptr) {
+  HYB_CHECK(context, HYB_ERR_INVALID, "NULL argument");
+  DeviceGuard guard(context->device);
+  if (peer_ptr) HYB_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+  return HYB_OK;
+}
+
+int hyb_exchange_arena_destroy(hyb_context* context, void* device_ptr) {
+  HYB_CHECK(context, HYB_ERR_INVALID, "NULL argument");
+  DeviceGuard guard(context->device);
+  if (device_ptr) HYB_CUDA(cudaFree(device_ptr));
   return HYB_OK;
 }
 

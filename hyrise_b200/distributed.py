@@ -388,16 +388,127 @@ class DeviceTupleTable:
         self.table.drop()
 
 
+class _DeviceArray:
+    """Zero-copy torch view of library-owned device memory (torch.as_tensor reads __cuda_array_interface__)."""
+
+    def __init__(self, pointer: int, count: int):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<i8", "data": (pointer, False), "version": 2}
+
+
+class PeerExchange:
+    """The radix exchange without a send buffer: every rank owns a receive arena (plain device memory exported through
+    CUDA IPC and mapped by all peers); hyb_join_partition_push's ranked-write kernel stores each group straight into its
+    owner's arena over NVLink. Collectives left: one world^2-integer all-gather of counts per side and one barrier.
+    Arena layout: four regions of `capacity` int64 — build keys, build RowIDs, probe keys, probe RowIDs."""
+
+    REGIONS = 4
+
+    def __init__(self, device_context, torch_device: torch.device, capacity: int):
+        import ctypes as C
+
+        self.device_context = device_context
+        self.torch_device = torch_device
+        self.rank, self.world = _world()
+        assert self.world & (self.world - 1) == 0 and self.world <= 16
+        # every rank must lay its arena out identically: peers compute region addresses inside OUR arena with this value
+        agreed = torch.tensor([capacity], dtype=torch.int64, device=torch_device)
+        dist.all_reduce(agreed, op=dist.ReduceOp.MAX)
+        self.capacity = (int(agreed.item()) + 8 + 15) // 16 * 16
+        lib = device_context.lib
+        own = C.c_void_p()
+        handle = (C.c_ubyte * capi.IPC_HANDLE_BYTES)()
+        capi.check(lib.hyb_exchange_arena_create(device_context.ptr, self.REGIONS * self.capacity * 8, C.byref(own), handle))
+        self.own = own.value
+        handles: list = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle))
+        self.bases = []
+        for peer, raw in enumerate(handles):
+            if peer == self.rank:
+                self.bases.append(self.own)
+                continue
+            mapped = C.c_void_p()
+            buffer = (C.c_ubyte * capi.IPC_HANDLE_BYTES).from_buffer_copy(raw)
+            capi.check(lib.hyb_exchange_arena_open(device_context.ptr, buffer, C.byref(mapped)))
+            self.bases.append(mapped.value)
+        self._counts = torch.empty(self.world, dtype=torch.int64, device=torch_device)
+        self._matrix = torch.empty(self.world * self.world, dtype=torch.int64, device=torch_device)
+        self._error = None
+        self._received = 0
+
+    def region(self, peer: int, region: int) -> int:
+        return self.bases[peer] + region * self.capacity * 8
+
+    def push_side(self, table, column_id: int, chunk_id_base: int, first_region: int, filter_handle: int = 0) -> int:
+        """Split one join side and store it into the owners' arenas (regions first_region = keys, first_region + 1 =
+        RowIDs). Returns the number of tuples THIS rank receives for the side (complete after `barrier`)."""
+        import ctypes as C
+
+        def exchange(_user, counts, dest_keys, dest_rows):
+            try:
+                self._counts.copy_(torch.tensor([int(counts[d]) for d in range(self.world)], dtype=torch.int64))
+                dist.all_gather_into_tensor(self._matrix, self._counts)
+                matrix = self._matrix.view(self.world, self.world).tolist()  # [source][destination]
+                for d in range(self.world):
+                    before = sum(matrix[s][d] for s in range(self.rank))
+                    total = sum(matrix[s][d] for s in range(self.world))
+                    if total + 8 > self.capacity:
+                        raise RuntimeError(f"receive arena of rank {d} too small: {total} tuples > capacity {self.capacity - 8}")
+                    dest_keys[d] = self.region(d, first_region) + before * 8
+                    dest_rows[d] = self.region(d, first_region + 1) + before * 8
+                self._received = sum(matrix[s][self.rank] for s in range(self.world))
+                return 0
+            except BaseException as error:  # noqa: BLE001 - must not unwind through the C frame
+                self._error = error
+                return 1
+
+        callback = capi.EXCHANGE_FN(exchange)
+        side = capi.JoinSide(table.handle, column_id, filter_handle)
+        self._error = None
+        status = self.device_context.lib.hyb_join_partition_push(self.device_context.ptr, C.byref(side), self.world,
+                                                                 chunk_id_base, callback, None)
+        if self._error is not None:
+            raise self._error
+        capi.check(status)
+        return self._received
+
+    def barrier(self) -> None:
+        dist.barrier(device_ids=[self.torch_device.index])
+
+    def received(self, first_region: int, count: int) -> tuple[torch.Tensor, torch.Tensor]:
+        """(keys with 8 spare elements, RowIDs) of what this rank received, as zero-copy torch views of its arena."""
+        keys = torch.as_tensor(_DeviceArray(self.region(self.rank, first_region), count + 8), device=self.torch_device)
+        rows = torch.as_tensor(_DeviceArray(self.region(self.rank, first_region + 1), max(count, 1)), device=self.torch_device)
+        return keys, rows[:count]
+
+    def close(self) -> None:
+        lib = self.device_context.lib
+        for peer, base in enumerate(self.bases):
+            if peer != self.rank:
+                lib.hyb_exchange_arena_close(self.device_context.ptr, base)
+        dist.barrier(device_ids=[self.torch_device.index])  # nobody still maps the arena we are about to free
+        lib.hyb_exchange_arena_destroy(self.device_context.ptr, self.own)
+        self.bases = []
+
+
 def device_distributed_join(device_context, build_table, build_column: int, probe_table, probe_column: int,
-                            radix_bits: int, build_chunk_base: int, probe_chunk_base: int, torch_device: torch.device):
+                            radix_bits: int, build_chunk_base: int, probe_chunk_base: int, torch_device: torch.device,
+                            peers: "PeerExchange | None" = None):
     """Inner JoinHash across ranks: materialise both sides, ONE all-to-all per side, join the received tuples locally.
     Returns (pair count on this rank, partition offsets, build RowIDs, probe RowIDs) with GLOBAL RowIDs, the rank's part
     of the reference-ordered result (partitions p with p % world == rank)."""
     _, world = _world()
     assert world & (world - 1) == 0, "the radix exchange needs a power-of-two world size"
-    sides = [device_partition_side(device_context, build_table, build_column, build_chunk_base, world, torch_device),
-             device_partition_side(device_context, probe_table, probe_column, probe_chunk_base, world, torch_device)]
-    (build_keys, build_rows, build_count), (probe_keys, probe_rows, probe_count) = exchange_partitioned(sides)
+    if peers is not None and world > 1:
+        # fused split + NVLink stores into the owners' arenas; collectives: 2 count all-gathers + 1 barrier
+        build_count = peers.push_side(build_table, build_column, build_chunk_base, 0)
+        probe_count = peers.push_side(probe_table, probe_column, probe_chunk_base, 2)
+        peers.barrier()
+        build_keys, build_rows = peers.received(0, build_count)
+        probe_keys, probe_rows = peers.received(2, probe_count)
+    else:
+        sides = [device_partition_side(device_context, build_table, build_column, build_chunk_base, world, torch_device),
+                 device_partition_side(device_context, probe_table, probe_column, probe_chunk_base, world, torch_device)]
+        (build_keys, build_rows, build_count), (probe_keys, probe_rows, probe_count) = exchange_partitioned(sides)
     build = DeviceTupleTable(device_context, build_keys, build_rows, build_count)
     probe = DeviceTupleTable(device_context, probe_keys, probe_rows, probe_count)
     try:

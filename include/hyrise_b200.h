@@ -335,6 +335,25 @@ int hyb_join_materialize(hyb_context* context, const hyb_join_side* side, uint32
 int hyb_join_partition(hyb_context* context, const hyb_join_side* side, uint32_t partition_count, uint32_t chunk_id_base,
                        void* out_keys_device, void* out_row_ids_device, uint64_t* out_partition_offsets);
 
+/*
+ * The same split fused with the exchange: ONE ranked-write kernel stores every group straight into the memory of the rank
+ * that owns it (NVLink peer-to-peer stores through CUDA IPC mappings) — no send buffer, no NCCL payload transfer.
+ * Between the count pass and the write pass the library calls `exchange(user, counts, dest_keys, dest_row_ids)` with this
+ * rank's tuple count per destination rank; the host layer all-gathers the counts (the only collective of the exchange,
+ * world_size^2 integers) and answers with, for every destination rank d, the DEVICE addresses (valid in THIS process:
+ * hyb_exchange_arena_open) where this rank's group d starts inside rank d's receive arena. The call returns after this
+ * rank's stores have completed; a barrier across ranks then makes every arena complete. world_size: power of two <= 16.
+ */
+#define HYB_IPC_HANDLE_BYTES 64
+typedef int (*hyb_exchange_fn)(void* user, const uint64_t* counts, void** dest_keys, void** dest_row_ids);
+int hyb_join_partition_push(hyb_context* context, const hyb_join_side* side, uint32_t world_size, uint32_t chunk_id_base,
+                            hyb_exchange_fn exchange, void* user);
+/* Receive arenas: plain device memory of this rank exported to / imported from the other ranks of the node. */
+int hyb_exchange_arena_create(hyb_context* context, uint64_t bytes, void** out_device_ptr, void* out_ipc_handle);
+int hyb_exchange_arena_open(hyb_context* context, const void* ipc_handle, void** out_peer_ptr);
+int hyb_exchange_arena_close(hyb_context* context, void* peer_ptr);
+int hyb_exchange_arena_destroy(hyb_context* context, void* device_ptr);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * AggregateHash (with optionally fused scan predicates and Projection arithmetic)
  * ---------------------------------------------------------------------------------------------------------------- */

@@ -78,26 +78,30 @@ def main():
 
     # ---- join: radix all-to-all ----------------------------------------------------------------------------------------
     radix_bits = 4
-    pairs, offsets, build_rows, probe_rows, result = hd.device_distributed_join(
-        device, orders, O_ORDERKEY, lineitem, L_ORDERKEY, radix_bits, orders_base, lineitem_base, torch_device)
-    if result is not None:
-        got_build, got_probe = result.to_host()
-        out_build = hd.unpack_row_ids(build_rows.cpu().numpy()[got_build["chunk_offset"]])
-        out_probe = hd.unpack_row_ids(probe_rows.cpu().numpy()[got_probe["chunk_offset"]])
-        result.free()
-    else:
-        out_build = out_probe = hd.unpack_row_ids(np.zeros(0, dtype=np.int64))
-    gathered = [None] * world
-    dist.all_gather_object(gathered, (out_build, out_probe, offsets))
-    if rank == 0:
-        expected = orc.join_hash(global_orders, O_ORDERKEY, global_lineitem, L_ORDERKEY, capi.JOIN_INNER, radix_bits, threads=8)
-        build_parts, probe_parts = [], []
-        for partition in range(1 << radix_bits):
-            owner_build, owner_probe, owner_offsets = gathered[partition % world]
-            build_parts.append(owner_build[int(owner_offsets[partition]):int(owner_offsets[partition + 1])])
-            probe_parts.append(owner_probe[int(owner_offsets[partition]):int(owner_offsets[partition + 1])])
-        assert row_ids_equal(np.concatenate(probe_parts), expected.probe), "distributed join: probe RowIDs differ"
-        assert row_ids_equal(np.concatenate(build_parts), expected.build), "distributed join: build RowIDs differ"
+    expected = orc.join_hash(global_orders, O_ORDERKEY, global_lineitem, L_ORDERKEY, capi.JOIN_INNER, radix_bits, threads=8) \
+        if rank == 0 else None
+    peers = hd.PeerExchange(device, torch_device, capacity=2 * shard.lineitem.row_count + 65_536)
+    for exchange_kind, exchange in (("nccl all-to-all", None), ("fused split + NVLink P2P stores", peers)):
+        pairs, offsets, build_rows, probe_rows, result = hd.device_distributed_join(
+            device, orders, O_ORDERKEY, lineitem, L_ORDERKEY, radix_bits, orders_base, lineitem_base, torch_device, peers=exchange)
+        if result is not None:
+            got_build, got_probe = result.to_host()
+            out_build = hd.unpack_row_ids(build_rows.cpu().numpy()[got_build["chunk_offset"]])
+            out_probe = hd.unpack_row_ids(probe_rows.cpu().numpy()[got_probe["chunk_offset"]])
+            result.free()
+        else:
+            out_build = out_probe = hd.unpack_row_ids(np.zeros(0, dtype=np.int64))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (out_build, out_probe, offsets))
+        if rank == 0:
+            build_parts, probe_parts = [], []
+            for partition in range(1 << radix_bits):
+                owner_build, owner_probe, owner_offsets = gathered[partition % world]
+                build_parts.append(owner_build[int(owner_offsets[partition]):int(owner_offsets[partition + 1])])
+                probe_parts.append(owner_probe[int(owner_offsets[partition]):int(owner_offsets[partition + 1])])
+            assert row_ids_equal(np.concatenate(probe_parts), expected.probe), f"distributed join ({exchange_kind}): probe RowIDs differ"
+            assert row_ids_equal(np.concatenate(build_parts), expected.build), f"distributed join ({exchange_kind}): build RowIDs differ"
+    peers.close()
 
     # ---- aggregate: Q1 with one all-to-all of partial groups -----------------------------------------------------------
     q1_predicates = [Predicate(L_SHIPDATE, capi.PRED_LESS_THAN_EQUALS, "1998-09-02")]

@@ -212,3 +212,69 @@ def test_partition_for_exchange(device, partition_count):
         if scan:
             scan.free()
     device_table.drop()
+
+
+@pytest.mark.parametrize("shift_bits", [0, 2, 3])
+def test_int64_keys_with_common_low_bits(device, shift_bits):
+    """What one rank joins after a radix exchange: non-NULL int64 keys that agree in their low bits (direct table indexed
+    by (key - min) >> shift), unique and duplicated build sides, probe keys with other low bits mixed in."""
+    rng = np.random.default_rng(31 + shift_bits)
+    step = 1 << shift_bits
+    base = 5_000_000_000
+    unique_keys = base + 3 % step + step * rng.permutation(40_000)[:12_000].astype(np.int64)
+    for build_keys in (unique_keys, np.concatenate([unique_keys[:3_000], unique_keys[:1_000]])):
+        probe_keys = base + rng.integers(-500, 45_000 * step, 50_000).astype(np.int64)
+        build = Table.from_columns([ColumnDefinition("k", capi.TYPE_INT64)], [build_keys], chunk_size=5_000).encode("Unencoded")
+        probe = Table.from_columns([ColumnDefinition("k", capi.TYPE_INT64)], [probe_keys], chunk_size=8_191).encode("Unencoded")
+        build_dev, probe_dev = device.upload(build), device.upload(probe)
+        for mode in (capi.JOIN_INNER, capi.JOIN_SEMI, capi.JOIN_LEFT):
+            for radix_bits in (0, 4):
+                check_join(device, build, build_dev, 0, probe, probe_dev, 0, mode, radix_bits)
+        build_dev.drop()
+        probe_dev.drop()
+
+
+@pytest.mark.parametrize("partition_count", [1, 2, 8])
+def test_partition_push_addressing(device, partition_count):
+    """hyb_join_partition_push with all "peers" in local memory: every group must arrive, in order, at the destination the
+    exchange callback names — the same bytes hyb_join_partition writes into its grouped local buffers."""
+    import ctypes as C
+
+    import torch
+    rng = np.random.default_rng(12)
+    table = random_table(rng, 60_000, 8_191).encode("Automatic")
+    device_table = device.upload(table)
+    torch_device = torch.device("cuda", 0)
+    for column in (0, 1, 4):
+        side = capi.JoinSide(device_table.handle, column, 0)
+        positions = C.c_uint64()
+        capi.check(device.lib.hyb_join_side_positions(device.ptr, C.byref(side), C.byref(positions)))
+        keys = torch.zeros(positions.value + 8, dtype=torch.int64, device=torch_device)
+        row_ids = torch.zeros(positions.value + 8, dtype=torch.int64, device=torch_device)
+        torch.cuda.synchronize()
+        offsets = (C.c_uint64 * (partition_count + 1))()
+        capi.check(device.lib.hyb_join_partition(device.ptr, C.byref(side), partition_count, 77, keys.data_ptr(),
+                                                 row_ids.data_ptr(), offsets))
+        offsets = [int(v) for v in offsets]
+        received = {}
+
+        def exchange(_user, counts, dest_keys, dest_rows):
+            for p in range(partition_count):
+                assert int(counts[p]) == offsets[p + 1] - offsets[p]
+                # 1000 int64 of slack in front: a store at a wrong (smaller) index would land there and be caught
+                received[p] = (torch.full((int(counts[p]) + 2000,), -7, dtype=torch.int64, device=torch_device),
+                               torch.full((int(counts[p]) + 2000,), -7, dtype=torch.int64, device=torch_device))
+                dest_keys[p] = received[p][0].data_ptr() + 8000
+                dest_rows[p] = received[p][1].data_ptr() + 8000
+            torch.cuda.synchronize()
+            return 0
+
+        callback = capi.EXCHANGE_FN(exchange)
+        capi.check(device.lib.hyb_join_partition_push(device.ptr, C.byref(side), partition_count, 77, callback, None))
+        for p in range(partition_count):
+            count = offsets[p + 1] - offsets[p]
+            for got, want in ((received[p][0], keys), (received[p][1], row_ids)):
+                got = got.cpu().numpy()
+                assert np.all(got[:1000] == -7) and np.all(got[1000 + count:] == -7), (column, p)
+                assert np.array_equal(got[1000:1000 + count], want[offsets[p]:offsets[p + 1]].cpu().numpy()), (column, p)
+    device_table.drop()
