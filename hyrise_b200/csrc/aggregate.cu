@@ -525,7 +525,6 @@ struct FastPlan {
   unsigned long long* partial_raw_nulls;      // [cta][G][C]
   unsigned long long* partial_product_nulls;  // [cta][G][C]
   uint32_t* overflow;                    // set when a CTA sees more than G groups
-  uint32_t prefetch_distance;            // iterations ahead to prefetch into L2 (0 = off)
 };
 
 template <int W>
@@ -640,6 +639,8 @@ __device__ __forceinline__ void put8(T (&array)[8], int j, T value) {
   for (int k = 0; k < 8; ++k) array[k] = (j == k) ? value : array[k];
 }
 
+constexpr int kEarlyPredicates = 2;   // fused predicates / group-by columns whose loads are hoisted to the top of an
+constexpr int kEarlyGroups = 2;       // iteration (the rest load at their point of use)
 constexpr int kFastThreads = 128;
 constexpr int kFastWarps = kFastThreads / 32;
 constexpr int kFastRowsPerWarp = kAggTileRows / kFastWarps;   // 1024 contiguous rows per warp and tile
@@ -723,15 +724,25 @@ __global__ void __launch_bounds__(kFastThreads, kMinBlocks) aggregate_fast_kerne
   const uint32_t need_raw_mask = plan.need_raw_mask, need_product_mask = plan.need_product_mask;
   const uint32_t groupby_count = plan.groupby_count;
 
-  // Static tile assignment (tile = blockIdx.x + k * gridDim.x) keeps the summation order reproducible.
-  for (uint32_t tile = blockIdx.x; tile < plan.tile_count; tile += gridDim.x) {
+  // Static tile assignment in units of kTilesPerUnit consecutive tiles, units strided over the CTAs. Static keeps the
+  // summation order reproducible; consecutive tiles of a unit come from the same chunk, so descriptors, dictionaries and
+  // the combo table are staged once per unit instead of once per tile (the staging is a chain of dependent global loads
+  // and barriers, ~4 us, that the row work cannot hide); striding the units keeps the CTAs of a wave on neighbouring
+  // memory (fully blocked assignment — one chunk range per CTA — measured 40 % slower on bandwidth-heavy queries).
+  constexpr uint32_t kTilesPerUnit = 4;
+  uint32_t staged_chunk = 0xFFFFFFFFu;
+  const uint32_t unit_count = (plan.tile_count + kTilesPerUnit - 1) / kTilesPerUnit;
+  for (uint32_t unit = blockIdx.x; unit < unit_count; unit += gridDim.x)
+  for (uint32_t tile = unit * kTilesPerUnit; tile < min(plan.tile_count, (unit + 1) * kTilesPerUnit); ++tile) {
     const uint2 info = __ldg(plan.tile_map + tile);
     const uint32_t chunk = info.x;
     const uint32_t tile_row0 = info.y & 0x7FFFFFFFu;
     const unsigned long long chunk_first_position = __ldg(plan.chunk_row_start + chunk);
     const uint32_t chunk_rows = plan.size_segments[chunk].row_count;
 
-    // ---- per-tile staging: segment descriptors, small dictionaries, the combo -> group table -----------------------
+    if (chunk != staged_chunk) {
+    staged_chunk = chunk;
+    // ---- per-chunk staging: segment descriptors, small dictionaries, the combo -> group table ----------------------
     __syncthreads();  // previous tile done with the staged data
     if (threadIdx.x < C && plan.value_segments[threadIdx.x]) {
       s_value_segment[threadIdx.x] = plan.value_segments[threadIdx.x][chunk];
@@ -791,32 +802,68 @@ __global__ void __launch_bounds__(kFastThreads, kMinBlocks) aggregate_fast_kerne
       }
       __syncthreads();
     }
+    }  // staging
     const bool use_combos = G > 1 && s_use_combos != 0;
 
 #pragma unroll 1
     for (int it = 0; it < kFastIterations; ++it) {
       const uint32_t row0 = tile_row0 + warp * kFastRowsPerWarp + it * 256 + lane * 8;
       if (row0 >= chunk_rows) continue;
-      if (plan.prefetch_distance) {
-        // Pull the rows this thread reads `prefetch_distance` iterations from now into L2 (hint only, no registers held).
-        const uint32_t ahead = row0 + plan.prefetch_distance * 256;
-        if (ahead + 8 <= chunk_rows) {
-          for (uint32_t p = 0; p < plan.predicate_count; ++p) prefetch_codes(plan.predicate_segments[p][chunk], ahead);
-          if constexpr (G > 1) {
-            for (uint32_t q = 0; q < groupby_count; ++q) prefetch_codes(s_group_segment[q], ahead);
-          }
+      // ---- early loads: an iteration costs two DRAM round trips — all predicate columns, then (for threads with a
+      // surviving row) all group-by and value columns — instead of one per column; see device_utils.cuh. Static
+      // indexes only (a run-time index would move the arrays to local memory).
+      uint4 raw_predicate[kEarlyPredicates];
+      bool early_predicate[kEarlyPredicates];
 #pragma unroll
-          for (int c = 0; c < C; ++c) {
-            if (plan.value_segments[c] != nullptr) prefetch_codes(s_value_segment[c], ahead);
-          }
+      for (int p = 0; p < kEarlyPredicates; ++p) {
+        early_predicate[p] = false;
+        raw_predicate[p] = uint4{0u, 0u, 0u, 0u};
+        if (static_cast<uint32_t>(p) < plan.predicate_count) {
+          const DevSegment& segment = plan.predicate_segments[p][chunk];
+          const uint32_t mode = plan.predicate_tests[p][chunk].mode;
+          early_predicate[p] = raw_codes_loadable(segment) && (mode == kTestIdRange || mode == kTestInt);
+          raw_predicate[p] = early_predicate[p] ? load_raw_codes8(segment, row0) : uint4{0u, 0u, 0u, 0u};
         }
       }
       uint32_t mask = chunk_rows - row0 >= 8 ? 0xFFu : ((1u << (chunk_rows - row0)) - 1u);
-      for (uint32_t p = 0; p < plan.predicate_count && mask; ++p) {
+#pragma unroll
+      for (int p = 0; p < kEarlyPredicates; ++p) {
+        if (static_cast<uint32_t>(p) < plan.predicate_count) {
+          const ChunkTest& test = plan.predicate_tests[p][chunk];
+          mask &= test.mode == kTestNone ? 0u
+                                         : evaluate8(plan.predicate_segments[p][chunk], test, row0, early_predicate[p],
+                                                     raw_predicate[p]);
+        }
+      }
+      for (uint32_t p = kEarlyPredicates; p < plan.predicate_count && mask; ++p) {
         const ChunkTest& test = plan.predicate_tests[p][chunk];
         mask &= test.mode == kTestNone ? 0u : evaluate8(plan.predicate_segments[p][chunk], test, row0);
       }
       if (mask == 0) continue;
+      // second round trip: group-by and value columns, only for threads with a surviving row
+      uint2 raw_group[kEarlyGroups];
+      if constexpr (G > 1) {
+        if (use_combos) {
+#pragma unroll
+          for (int q = 0; q < kEarlyGroups; ++q) {
+            if (static_cast<uint32_t>(q) < groupby_count) {
+              raw_group[q] = ld_stream_v2(static_cast<const uint8_t*>(s_group_segment[q].av) + row0);
+            }
+          }
+        }
+      }
+      uint4 raw_value[C];
+      bool early_value[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        early_value[c] = false;
+        raw_value[c] = uint4{0u, 0u, 0u, 0u};
+        if (plan.value_segments[c] != nullptr) {
+          const DevSegment& segment = s_value_segment[c];
+          early_value[c] = segment.encoding == HYB_ENC_DICTIONARY && raw_codes_loadable(segment);
+          raw_value[c] = early_value[c] ? load_raw_codes8(segment, row0) : uint4{0u, 0u, 0u, 0u};
+        }
+      }
 
       // ---- group of each row ----------------------------------------------------------------------------------------
       int32_t group_of[8];
@@ -832,7 +879,19 @@ __global__ void __launch_bounds__(kFastThreads, kMinBlocks) aggregate_fast_kerne
           group_of[j] = -1;
         }
         if (use_combos) {
-          for (uint32_t q = 0; q < groupby_count; ++q) {
+#pragma unroll
+          for (int q = 0; q < kEarlyGroups; ++q) {
+            if (static_cast<uint32_t>(q) < groupby_count) {
+              const uint2 packed = raw_group[q];
+              const uint32_t stride = s_combo_stride[q];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                combo[j] += ((packed.x >> (8 * j)) & 0xFFu) * stride;
+                combo[4 + j] += ((packed.y >> (8 * j)) & 0xFFu) * stride;
+              }
+            }
+          }
+          for (uint32_t q = kEarlyGroups; q < groupby_count; ++q) {
             const uint2 packed = ld_stream_v2(static_cast<const uint8_t*>(s_group_segment[q].av) + row0);
             const uint32_t stride = s_combo_stride[q];
 #pragma unroll
@@ -924,7 +983,7 @@ __global__ void __launch_bounds__(kFastThreads, kMinBlocks) aggregate_fast_kerne
         uint32_t null_bits = 0;
         if (segment.encoding == HYB_ENC_DICTIONARY) {
           uint32_t codes[8];
-          load_codes8(segment.av, segment.vector_type, segment.bit_width, row0, segment.row_count, codes);
+          codes8(segment, row0, early_value[c], raw_value[c], codes);
           if (segment.pad & kSegmentMayContainNulls) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -1074,23 +1133,13 @@ __global__ void __launch_bounds__(kFastThreads, kMinBlocks) aggregate_fast_kerne
 
 using FastKernel = void (*)(const FastPlan*);
 
-// Experiment switch (HYB_AGG_MIN_BLOCKS=3|4|5): resident CTAs per SM the register allocation is capped for.
-static int fast_min_blocks() {
-  const char* text = std::getenv("HYB_AGG_MIN_BLOCKS");
-  const int value = text ? std::atoi(text) : 3;
-  return value == 4 || value == 5 ? value : 3;
-}
+// Resident CTAs per SM the register allocation is capped for: 3 (170 registers) measured best for Q1 — 2 leaves too few
+// warps to hide latency (+24 %), 4 spills the accumulators (+30 %).
+constexpr int kFastMinBlocks = 3;
 
 template <int W, int G, int C>
 static FastKernel fast_kernel_for_min_blocks() {
-  switch (fast_min_blocks()) {
-    case 4:
-      return aggregate_fast_kernel<W, G, C, 4>;
-    case 5:
-      return aggregate_fast_kernel<W, G, C, 5>;
-    default:
-      return aggregate_fast_kernel<W, G, C, 3>;
-  }
+  return aggregate_fast_kernel<W, G, C, kFastMinBlocks>;
 }
 
 template <int W, int G>
@@ -1512,10 +1561,7 @@ int hyb_aggregate_hash(hyb_context* context, const hyb_aggregate_query* query, h
       host_plan.tile_map = tile_map;
       host_plan.chunk_row_start = reinterpret_cast<const unsigned long long*>(table->d_chunk_row_start);
       host_plan.tile_count = tile_count;
-      {
-        const char* text = std::getenv("HYB_AGG_PREFETCH");
-        host_plan.prefetch_distance = text ? static_cast<uint32_t>(std::atoi(text)) : 0;
-      }
+
       host_plan.predicate_count = query->predicate_count;
       for (uint32_t p = 0; p < query->predicate_count; ++p) {
         host_plan.predicate_segments[p] = table->d_segments + size_t{query->predicates[p].column_id} * chunk_count;

@@ -146,6 +146,54 @@ __device__ __forceinline__ void load_codes8(const void* base, uint32_t vector_ty
   }
 }
 
+// ---- early loads ---------------------------------------------------------------------------------------------------
+// A kernel that reads several columns per row wants ALL of an iteration's loads in flight before the first use; decoders
+// that load inside per-encoding branches serialise one DRAM round trip per column instead. The code vectors that dominate
+// (FixedWidthIntegerVector of 1 or 2 bytes: dictionary value-IDs, FoR offsets) are therefore fetched up front as raw
+// 16 bytes per 8 rows and unpacked later; every other layout keeps loading at its point of use.
+__device__ __forceinline__ bool raw_codes_loadable(const DevSegment& segment) {
+  return segment.encoding != HYB_ENC_UNENCODED &&
+         (segment.vector_type == HYB_VEC_FIXED_1B || segment.vector_type == HYB_VEC_FIXED_2B);
+}
+
+__device__ __forceinline__ uint4 load_raw_codes8(const DevSegment& segment, uint32_t row0) {
+  if (segment.vector_type == HYB_VEC_FIXED_1B) {
+    const uint2 v = ld_stream_v2(static_cast<const uint8_t*>(segment.av) + row0);
+    return make_uint4(v.x, v.y, 0u, 0u);
+  }
+  return ld_stream_v4(static_cast<const uint16_t*>(segment.av) + row0);
+}
+
+__device__ __forceinline__ void unpack_raw_codes8(const uint4& raw, uint32_t vector_type, uint32_t (&codes)[8]) {
+  if (vector_type == HYB_VEC_FIXED_1B) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      codes[j] = (raw.x >> (8 * j)) & 0xFFu;
+      codes[4 + j] = (raw.y >> (8 * j)) & 0xFFu;
+    }
+  } else {
+    codes[0] = raw.x & 0xFFFFu;
+    codes[1] = raw.x >> 16;
+    codes[2] = raw.y & 0xFFFFu;
+    codes[3] = raw.y >> 16;
+    codes[4] = raw.z & 0xFFFFu;
+    codes[5] = raw.z >> 16;
+    codes[6] = raw.w & 0xFFFFu;
+    codes[7] = raw.w >> 16;
+  }
+}
+
+// load_codes8, or the unpacking of an early load (by value: taking the address of a register array element would move it
+// to local memory).
+__device__ __forceinline__ void codes8(const DevSegment& segment, uint32_t row0, bool have_raw, uint4 raw,
+                                       uint32_t (&codes)[8]) {
+  if (have_raw) {
+    unpack_raw_codes8(raw, segment.vector_type, codes);
+  } else {
+    load_codes8(segment.av, segment.vector_type, segment.bit_width, row0, segment.row_count, codes);
+  }
+}
+
 // Single-entry decode (gather paths: position-filtered scans, join build side through a filter).
 __device__ __forceinline__ uint32_t load_code1(const void* base, uint32_t vector_type, uint32_t bit_width, uint32_t row) {
   switch (vector_type) {

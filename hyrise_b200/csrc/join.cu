@@ -795,7 +795,7 @@ __device__ __forceinline__ void probe_chunk_any_codec(const ProbeParams& params,
 
 // Emitted rows per (partition, tile). kStore: also keep match/partition per probe slot for the write kernel.
 template <bool kStore>
-__global__ void __launch_bounds__(kJoinThreads, 4) join_probe_count_kernel(const ProbeParams params) {
+__global__ void __launch_bounds__(kJoinThreads, 5) join_probe_count_kernel(const ProbeParams params) {
   __shared__ uint32_t s_histogram[kMaxPartitions];
   const bool build_has_nulls = params.flags[1] != 0;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -903,23 +903,7 @@ __global__ void __launch_bounds__(kJoinThreads, 3) join_probe_write_kernel(const
       } else {
         probe_row = params.probe.filter[ref.first_position + index];
       }
-      if (params.mode == kModePartition) {
-        // exchange payload: the key (as the 8 bytes of out_build[at]) and the RowID in the global table
-        long long key = 0;
-        bool is_null = false;
-        load_key1(params.probe, ref, segment, index, key, is_null);
-        hyb_row_id* key_out = params.out_build + at;
-        hyb_row_id* row_out = params.out_probe + at;
-        if (params.push_to_peers) {
-          // index inside the group = position in the partition-major output minus the group's start
-          const unsigned long long inside = at - params.run_starts[static_cast<size_t>(partition) * params.probe.tile_count];
-          key_out = reinterpret_cast<hyb_row_id*>(params.peer_keys[partition] + inside);
-          row_out = reinterpret_cast<hyb_row_id*>(params.peer_rows[partition] + inside);
-        }
-        st_stream_v2(key_out, static_cast<uint32_t>(static_cast<unsigned long long>(key)),
-                     static_cast<uint32_t>(static_cast<unsigned long long>(key) >> 32));
-        st_stream_v2(row_out, probe_row.chunk_id + params.chunk_id_base, probe_row.chunk_offset);
-      } else if (match == kEmitWithoutPartner) {
+      if (match == kEmitWithoutPartner) {
         if (emit_build) st_stream_v2(params.out_build + at, HYB_INVALID_CHUNK_ID, HYB_INVALID_CHUNK_OFFSET);
         st_stream_v2(params.out_probe + at, probe_row.chunk_id, probe_row.chunk_offset);
       } else if (unique) {
@@ -934,6 +918,107 @@ __global__ void __launch_bounds__(kJoinThreads, 3) join_probe_write_kernel(const
           st_stream_v2(params.out_probe + at + j, probe_row.chunk_id, probe_row.chunk_offset);
         }
       }
+    }
+    __syncthreads();
+  }
+}
+
+// hyb_join_partition / hyb_join_partition_push, ranked-write pass: the stable split of one side's non-NULL
+// {key, global RowID} tuples by owner rank. Same ranking as join_probe_write_kernel, but nothing is looked up and the
+// keys stay in registers between the passes, so the pass costs one read of the key column and one 16-byte store per
+// tuple — to local buffers, or (push_to_peers) straight into the owners' memory over NVLink.
+__global__ void __launch_bounds__(kJoinThreads, 3) join_partition_write_kernel(const ProbeParams params) {
+  __shared__ uint32_t s_warp_histogram[kJoinWarps][kMaxPartitions];
+  __shared__ unsigned long long s_start[kJoinWarps][kMaxPartitions];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lanes_below = (1u << lane) - 1u;
+  const uint32_t tiles_per_cta = (params.probe.tile_count + gridDim.x - 1) / gridDim.x;
+  const uint32_t tile_end = min(params.probe.tile_count, (blockIdx.x + 1) * tiles_per_cta);
+  for (uint32_t tile = blockIdx.x * tiles_per_cta; tile < tile_end; ++tile) {
+    for (uint32_t p = lane; p < params.partition_count; p += 32) s_warp_histogram[warp][p] = 0;
+    __syncwarp();
+    const TileRef ref = tile_ref(params.probe, tile);
+    const DevSegment segment = params.probe.tile_map ? params.probe.segments[ref.chunk] : DevSegment{};
+    const uint32_t codec = tile_codec(params.probe, segment);
+    const uint32_t chunk0 = warp * kJoinRowsPerWarp;
+    uint32_t for_minimum = 0;
+    if (codec >= kCodecFor8 && ref.row0 + chunk0 < segment.row_count) {
+      for_minimum = static_cast<uint32_t>(__ldg(static_cast<const int32_t*>(segment.values) + (ref.row0 + chunk0) / HYB_FOR_BLOCK_SIZE));
+    }
+    uint32_t key_low[kProbeSteps], key_high[kProbeSteps], rank[kProbeSteps], partitions[kProbeSteps / 4];
+    uint32_t emit_mask = 0;
+#pragma unroll
+    for (int q = 0; q < kProbeSteps / 4; ++q) partitions[q] = 0;
+#pragma unroll
+    for (int step = 0; step < kProbeSteps; ++step) {
+      const uint32_t index = chunk0 + step * 32 + lane;
+      long long key = 0;
+      bool is_null = false;
+      bool valid;
+      // uniform per tile: the specialised decoders of the probe for the layouts that dominate, the generic one otherwise
+      switch (codec) {
+        case kCodecPlain32:
+          valid = codec_key<kCodecPlain32>(params.probe, ref, segment, index, for_minimum, key, is_null);
+          break;
+        case kCodecFor8:
+          valid = codec_key<kCodecFor8>(params.probe, ref, segment, index, for_minimum, key, is_null);
+          break;
+        case kCodecFor16:
+          valid = codec_key<kCodecFor16>(params.probe, ref, segment, index, for_minimum, key, is_null);
+          break;
+        case kCodecFor32:
+          valid = codec_key<kCodecFor32>(params.probe, ref, segment, index, for_minimum, key, is_null);
+          break;
+        default:
+          valid = load_key1(params.probe, ref, segment, index, key, is_null);
+          break;
+      }
+      const bool emit = valid && !is_null;
+      const uint32_t partition = static_cast<uint32_t>(static_cast<unsigned long long>(key)) & params.partition_mask;
+      const uint32_t peers = __match_any_sync(kFullMask, partition);
+      const uint32_t emitting = __ballot_sync(kFullMask, emit) & peers;
+      const int leader = __ffs(peers) - 1;
+      uint32_t earlier = 0;
+      if (lane == static_cast<uint32_t>(leader) && emitting) earlier = atomicAdd(&s_warp_histogram[warp][partition], __popc(emitting));
+      earlier = __shfl_sync(kFullMask, earlier, leader);
+      key_low[step] = static_cast<uint32_t>(static_cast<unsigned long long>(key));
+      key_high[step] = static_cast<uint32_t>(static_cast<unsigned long long>(key) >> 32);
+      rank[step] = earlier + __popc(emitting & lanes_below);
+      partitions[step >> 2] |= partition << (8 * (step & 3));
+      emit_mask |= emit ? (1u << step) : 0u;
+    }
+    __syncthreads();
+    for (uint32_t p = threadIdx.x; p < params.partition_count; p += kJoinThreads) {
+      unsigned long long running = params.run_starts[static_cast<size_t>(p) * params.probe.tile_count + tile];
+#pragma unroll
+      for (int w = 0; w < kJoinWarps; ++w) {
+        s_start[w][p] = running;
+        running += s_warp_histogram[w][p];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int step = 0; step < kProbeSteps; ++step) {
+      if (!((emit_mask >> step) & 1u)) continue;
+      const uint32_t index = chunk0 + step * 32 + lane;
+      const uint32_t partition = (partitions[step >> 2] >> (8 * (step & 3))) & 0xFFu;
+      const unsigned long long at = s_start[warp][partition] + rank[step];
+      hyb_row_id row;
+      if (params.probe.tile_map) {
+        row = hyb_row_id{ref.chunk, ref.row0 + index};
+      } else {
+        row = params.probe.filter[ref.first_position + index];
+      }
+      hyb_row_id* key_out = params.out_build + at;
+      hyb_row_id* row_out = params.out_probe + at;
+      if (params.push_to_peers) {
+        // index inside the group = position in the partition-major output minus the group's start
+        const unsigned long long inside = at - params.run_starts[static_cast<size_t>(partition) * params.probe.tile_count];
+        key_out = reinterpret_cast<hyb_row_id*>(params.peer_keys[partition] + inside);
+        row_out = reinterpret_cast<hyb_row_id*>(params.peer_rows[partition] + inside);
+      }
+      st_stream_v2(key_out, key_low[step], key_high[step]);
+      st_stream_v2(row_out, row.chunk_id + params.chunk_id_base, row.chunk_offset);
     }
     __syncthreads();
   }
@@ -1431,7 +1516,7 @@ static int partition_side(hyb_context* context, const hyb_join_side* side, uint3
   params.chunk_id_base = chunk_id_base;
   int count_blocks = 1, write_blocks = 1;
   HYB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&count_blocks, join_probe_count_kernel<false>, kJoinThreads, 0));
-  HYB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&write_blocks, join_probe_write_kernel<false>, kJoinThreads, 0));
+  HYB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&write_blocks, join_partition_write_kernel, kJoinThreads, 0));
   uint32_t launches = 0;
   timing_kernel_begin(context);
   if (tiles) {
@@ -1469,7 +1554,7 @@ static int partition_side(hyb_context* context, const hyb_join_side* side, uint3
     if (tiles) timing_kernel_begin(context);
   }
   if (tiles) {
-    join_probe_write_kernel<false><<<std::min<uint32_t>(tiles, context->sm_count * std::max(write_blocks, 1)), kJoinThreads, 0, stream>>>(params);
+    join_partition_write_kernel<<<std::min<uint32_t>(tiles, context->sm_count * std::max(write_blocks, 1)), kJoinThreads, 0, stream>>>(params);
     HYB_CUDA(cudaGetLastError());
     ++launches;
     timing_kernel_end(context);

@@ -38,14 +38,16 @@ int prepare_chunk_tests(hyb_context* context, Table* table, const hyb_scan_predi
 // Predicate evaluation for 8 consecutive rows of one segment. Returns a bit mask (bit j = row0 + j matches).
 // All control flow depends on per-chunk values only, so it is uniform across a CTA (one tile = one chunk).
 // ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t evaluate8(const DevSegment& segment, const ChunkTest& test, uint32_t row0) {
+// have_raw / raw: the segment's code vector for these rows if the caller loaded it early (load_raw_codes8).
+__device__ __forceinline__ uint32_t evaluate8(const DevSegment& segment, const ChunkTest& test, uint32_t row0,
+                                              bool have_raw = false, uint4 raw = uint4{0u, 0u, 0u, 0u}) {
   const uint32_t rows = segment.row_count;
   const uint32_t valid = rows - row0 >= 8 ? 0xFFu : ((1u << (rows - row0)) - 1u);
   uint32_t mask = 0;
   switch (test.mode) {
     case kTestIdRange: {
       uint32_t codes[8];
-      load_codes8(segment.av, segment.vector_type, segment.bit_width, row0, rows, codes);
+      codes8(segment, row0, have_raw, raw, codes);
       if (!test.negate) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) mask |= ((codes[j] - test.id_lo) < test.id_span) ? (1u << j) : 0u;
@@ -62,7 +64,7 @@ __device__ __forceinline__ uint32_t evaluate8(const DevSegment& segment, const C
       long long values[8];
       if (segment.encoding == HYB_ENC_FRAME_OF_REFERENCE) {
         uint32_t codes[8];
-        load_codes8(segment.av, segment.vector_type, segment.bit_width, row0, rows, codes);
+        codes8(segment, row0, have_raw, raw, codes);
         const int32_t minimum = __ldg(static_cast<const int32_t*>(segment.values) + row0 / HYB_FOR_BLOCK_SIZE);
 #pragma unroll
         for (int j = 0; j < 8; ++j) values[j] = static_cast<int32_t>(static_cast<uint32_t>(minimum) + codes[j]);

@@ -16,8 +16,8 @@ def run(f, n=12):
         r = f(); device.synchronize(); xs.append(device.last_stats().dominant_kernel_ms)
         if hasattr(r, "free"): r.free()
     return float(np.median(xs[2:]))
-for mb in ("3", "4", "5"):
-    for pf in ("0", "1", "2"):
+for mb in ("2", "3", "4"):
+    for pf in ("0",):
         os.environ["HYB_AGG_MIN_BLOCKS"] = mb; os.environ["HYB_AGG_PREFETCH"] = pf
         print(f"aggregate min_blocks {mb} prefetch {pf}: {run(lambda: device.aggregate_hash(lineitem, Q1_GROUPBY, Q1_AGGREGATES, predicates=Q1_PREDICATES)):.3f} ms", flush=True)
 for pf in ("0", "1"):
