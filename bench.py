@@ -358,26 +358,47 @@ def main() -> None:
         h2d = sum(block.bytes for block in host_blocks)
         d2h = 0
 
+        trace = os.environ.get("HYB_BENCH_E2E_TRACE") == "1"
+
         def e2e_step():
             nonlocal d2h
+            marks = [("start", time.perf_counter())]
+
+            def mark(name):
+                if trace:
+                    device.synchronize()
+                    marks.append((name, time.perf_counter()))
+
             # the generator's segment buffers live in a few pinned 256 MB blocks: one DMA per block, tables point into them
             block_set = device.upload_blocks(host_blocks)
+            mark("upload_blocks")
             table_l = device.upload_from_blocks(tables.lineitem, block_set)
             table_o = device.upload_from_blocks(tables.orders, block_set)
+            mark("tables")
             scan = device.table_scan(table_l, SCAN_PREDICATE)
+            mark("scan")
             matched = scan.to_host(scan_out)
+            mark("scan d2h")
             join = device.join_hash(table_o, O_ORDERKEY, table_l, L_ORDERKEY, capi.JOIN_INNER, -1)
+            mark("join")
             pairs = join.to_host(join_build_out, join_probe_out)
+            mark("join d2h")
             aggregate = device.aggregate_hash(table_l, Q1_GROUPBY, Q1_AGGREGATES, predicates=Q1_PREDICATES)
+            mark("aggregate")
             d2h = len(matched) * 8 + len(pairs[1]) * 16 + aggregate.group_count * (8 + 8 * len(Q1_AGGREGATES))
             scan.free()
             join.free()
             table_l.drop()
             table_o.drop()
             device.free_blocks(block_set)
+            mark("free")
+            if trace:
+                print("[e2e] " + " ".join(f"{name} {1e3 * (t - marks[i][1]):.1f}" for i, (name, t) in enumerate(marks[1:])),
+                      file=sys.stderr, flush=True)
 
         e2e_steps = max(2, min(args.steps, 5))
-        e2e_step()
+        for _ in range(max(3, warmup)):  # the first steps size the library's block cache (cudaMalloc on every miss)
+            e2e_step()
         device.synchronize()
         barrier()
         begin = time.perf_counter()
@@ -391,7 +412,7 @@ def main() -> None:
             dist.all_reduce(tensor, op=dist.ReduceOp.MAX)
             e2e_elapsed = float(tensor.item())
         e2e = {"value": rows_per_step * world / (e2e_elapsed / e2e_steps), "unit": "rows/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_elapsed / e2e_steps * 1e3, "steps": e2e_steps}
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_elapsed / e2e_steps * 1e3, "steps": e2e_steps, "warmup": max(3, warmup)}
 
     # ---- roofline of the dominant kernel + per-operator breakdown ---------------------------------------------------
     peak, peak_source = measured_peak_gbs()

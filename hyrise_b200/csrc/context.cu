@@ -52,7 +52,7 @@ void Arena::release() {
 }
 
 BlockSet::~BlockSet() {
-  for (auto& block : blocks) cudaFree(block.device_base);
+  for (auto& block : blocks) device_free(owner, block.device_base);
 }
 
 const void* BlockSet::translate(const void* host, size_t bytes) const {
@@ -626,11 +626,12 @@ int hyb_blocks_upload(hyb_context* context, const hyb_host_block* blocks, uint32
   DeviceGuard guard(context->device);
   std::lock_guard<std::mutex> lock(context->mutex);
   auto set = std::make_shared<BlockSet>();
+  set->owner = context;
   for (uint32_t index = 0; index < block_count; ++index) {
     HYB_CHECK(blocks[index].base, HYB_ERR_INVALID, "block base is NULL");
-    char* device = nullptr;
-    HYB_CUDA(cudaMalloc(&device, blocks[index].bytes + Arena::kTailPad));
-    set->blocks.push_back({static_cast<const char*>(blocks[index].base), blocks[index].bytes, device});
+    void* device = nullptr;
+    HYB_TRY(device_alloc(context, blocks[index].bytes + Arena::kTailPad, &device));
+    set->blocks.push_back({static_cast<const char*>(blocks[index].base), blocks[index].bytes, static_cast<char*>(device)});
     HYB_CUDA(cudaMemcpyAsync(device, blocks[index].base, blocks[index].bytes, cudaMemcpyHostToDevice, context->stream));
   }
   HYB_CUDA(cudaStreamSynchronize(context->stream));  // the blocks are borrowed for the duration of the call

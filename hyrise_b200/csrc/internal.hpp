@@ -14,6 +14,8 @@
 
 #include "../../include/hyrise_b200.h"
 
+struct hyb_context;
+
 namespace hyb {
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -66,6 +68,8 @@ struct BlockSet {
     char* device_base;
   };
   std::vector<Block> blocks;
+  hyb_context* owner = nullptr;  // device blocks come from / go back to owner's DeviceCache: re-uploading the same arena
+                                 // every step (an end-to-end pipeline) must not cost a cudaMalloc / cudaFree per block
   ~BlockSet();
   // Device address of a host buffer that lies inside one of the blocks, or nullptr.
   const void* translate(const void* host, size_t bytes) const;
