@@ -415,21 +415,35 @@ class PeerExchange:
         dist.all_reduce(agreed, op=dist.ReduceOp.MAX)
         self.capacity = (int(agreed.item()) + 8 + 15) // 16 * 16
         lib = device_context.lib
+        # Every rank takes part in every collective below even when a local step failed: a rank that raised early would
+        # leave the others waiting forever. Failures are agreed on first, then raised everywhere.
         own = C.c_void_p()
         handle = (C.c_ubyte * capi.IPC_HANDLE_BYTES)()
-        capi.check(lib.hyb_exchange_arena_create(device_context.ptr, self.REGIONS * self.capacity * 8, C.byref(own), handle))
-        self.own = own.value
-        handles: list = [None] * self.world
-        dist.all_gather_object(handles, bytes(handle))
+        status = lib.hyb_exchange_arena_create(device_context.ptr, self.REGIONS * self.capacity * 8, C.byref(own), handle)
+        self.own = own.value if status == capi.HYB_OK else None
+        exported: list = [None] * self.world
+        dist.all_gather_object(exported, bytes(handle) if status == capi.HYB_OK else None)
         self.bases = []
-        for peer, raw in enumerate(handles):
-            if peer == self.rank:
-                self.bases.append(self.own)
-                continue
-            mapped = C.c_void_p()
-            buffer = (C.c_ubyte * capi.IPC_HANDLE_BYTES).from_buffer_copy(raw)
-            capi.check(lib.hyb_exchange_arena_open(device_context.ptr, buffer, C.byref(mapped)))
-            self.bases.append(mapped.value)
+        opened = True
+        if all(raw is not None for raw in exported):
+            for peer, raw in enumerate(exported):
+                if peer == self.rank:
+                    self.bases.append(self.own)
+                    continue
+                mapped = C.c_void_p()
+                buffer = (C.c_ubyte * capi.IPC_HANDLE_BYTES).from_buffer_copy(raw)
+                if lib.hyb_exchange_arena_open(device_context.ptr, buffer, C.byref(mapped)) != capi.HYB_OK:
+                    opened = False
+                    break
+                self.bases.append(mapped.value)
+        else:
+            opened = False
+        agreed_open: list = [None] * self.world
+        dist.all_gather_object(agreed_open, opened)
+        if not all(agreed_open):
+            message = lib.hyb_last_error().decode("utf-8", "replace")
+            self._release()
+            raise RuntimeError(f"peer exchange unavailable on at least one rank (this rank: {message or 'ok'})")
         self._counts = torch.empty(self.world, dtype=torch.int64, device=torch_device)
         self._matrix = torch.empty(self.world * self.world, dtype=torch.int64, device=torch_device)
         self._error = None
@@ -480,14 +494,19 @@ class PeerExchange:
         rows = torch.as_tensor(_DeviceArray(self.region(self.rank, first_region + 1), max(count, 1)), device=self.torch_device)
         return keys, rows[:count]
 
-    def close(self) -> None:
+    def _release(self) -> None:
         lib = self.device_context.lib
         for peer, base in enumerate(self.bases):
-            if peer != self.rank:
+            if peer != self.rank and base:
                 lib.hyb_exchange_arena_close(self.device_context.ptr, base)
-        dist.barrier(device_ids=[self.torch_device.index])  # nobody still maps the arena we are about to free
-        lib.hyb_exchange_arena_destroy(self.device_context.ptr, self.own)
         self.bases = []
+        dist.barrier(device_ids=[self.torch_device.index])  # nobody still maps the arena we are about to free
+        if self.own:
+            lib.hyb_exchange_arena_destroy(self.device_context.ptr, self.own)
+            self.own = None
+
+    def close(self) -> None:
+        self._release()
 
 
 def device_distributed_join(device_context, build_table, build_column: int, probe_table, probe_column: int,
