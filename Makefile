@@ -29,8 +29,15 @@ $(TPCH_LIB): $(CSRC)/tpch_gen.cpp include/hyrise_b200_tpch.h include/hyrise_b200
 oracle:
 	$(MAKE) -C oracle
 
+# The C++ host-side mirror of the reference operator interface (include/hyrise_b200.hpp) driving the three operators.
+example: build/tpch_operators
+build/tpch_operators: examples/tpch_operators.cpp include/hyrise_b200.hpp include/hyrise_b200.h include/hyrise_b200_tpch.h $(LIB) $(TPCH_LIB)
+	@mkdir -p build
+	$(CXX) -O2 -std=c++17 -Wall -Wextra -Iinclude -o $@ examples/tpch_operators.cpp -Lhyrise_b200/lib -lhyrise_b200 -lhyb_tpch \
+		-Wl,-rpath,'$$ORIGIN/../hyrise_b200/lib'
+
 clean:
 	rm -rf build $(LIB) $(TPCH_LIB)
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle clean
+.PHONY: all oracle clean example
