@@ -144,6 +144,19 @@ def worker(rank: int, port: int, results):
             keep = ~nulls                                                # Inner join: NULL keys are discarded on both sides
             received_keys, received_rows = hd.exchange_tuples(torch.from_numpy(keys[keep].astype(np.int64)),
                                                               torch.from_numpy(hd.pack_row_ids(row_ids[keep])))
+            # the GPU path's exchange (hyb_join_partition's stable split, then exchange_partitioned) must deliver the same
+            # tuples in the same order; the split is emulated with numpy here
+            kept_keys, kept_rows = keys[keep].astype(np.int64), hd.pack_row_ids(row_ids[keep])
+            owner = kept_keys & (WORLD - 1)
+            order = np.argsort(owner, kind="stable")
+            offsets = [0] + np.cumsum(np.bincount(owner, minlength=WORLD)).tolist()
+            padding = np.zeros(8, dtype=np.int64)
+            (again_keys, again_rows, again_count), = hd.exchange_partitioned(
+                [(torch.from_numpy(np.concatenate([kept_keys[order], padding])),
+                  torch.from_numpy(np.concatenate([kept_rows[order], padding])), offsets)])
+            assert again_count == len(received_keys) and len(again_keys) == again_count + 8
+            assert np.array_equal(again_keys[:again_count].numpy(), received_keys.numpy())
+            assert np.array_equal(again_rows[:again_count].numpy(), received_rows.numpy())
             sides.append((received_keys.numpy(), hd.unpack_row_ids(received_rows.numpy())))
         (build_keys, build_rows), (probe_keys, probe_rows) = sides
         assert ((build_keys & (WORLD - 1)) == rank).all() and ((probe_keys & (WORLD - 1)) == rank).all()
