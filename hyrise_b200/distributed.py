@@ -299,19 +299,6 @@ def device_materialize_side(device_context, table, column_id: int, chunk_id_base
     return keys[keep], row_ids[keep]
 
 
-def exchange_tuples_masked(keys: torch.Tensor, row_ids: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
-    """exchange_tuples without a sort: one order-preserving boolean selection per destination rank."""
-    rank, world = _world()
-    if world == 1:
-        return keys, row_ids
-    assert world & (world - 1) == 0, "the radix exchange needs a power-of-two world size"
-    owner = partition_owner(keys, world)
-    payload = torch.stack([keys, row_ids], dim=1)
-    parts = [payload[owner == d] for d in range(world)]
-    received = torch.cat(all_to_all_variable(parts), dim=0)
-    return received[:, 0].contiguous(), received[:, 1].contiguous()
-
-
 def device_partition_side(device_context, table, column_id: int, chunk_id_base: int, world: int, torch_device: torch.device,
                           filter_handle: int = 0):
     """hyb_join_partition: the side's non-NULL {key, global RowID} tuples grouped by owner rank (key & (world - 1)), stable.
