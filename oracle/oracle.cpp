@@ -1533,17 +1533,22 @@ int orc_aggregate_hash(const hyb_table_view* table, const hyb_aggregate_query* q
     } else if (data_type == HYB_TYPE_STRING) {
       // (:852-925) strings of < 5 chars are packed; longer ones get ids from a map. Only value-IDs reach this code, so
       // the caller supplies the per-dictionary-entry codes it computed with exactly that scheme.
-      for (size_t c = 0; c < input_chunks.size(); ++c) {
+      // one job per chunk, as _partition_by_groupby_keys spawns them (:683-700, :927-940)
+      std::atomic<bool> missing_codes{false};
+      run_jobs(input_chunks.size(), threads, [&](size_t c) {
         const auto& rows = *input_chunks[c];
         for (size_t i = 0; i < rows.size(); ++i) {
           const auto& segment = segment_at(table, rows[i].chunk_id, column_id);
-          ORC_CHECK(segment.encoding == HYB_ENC_DICTIONARY && segment.dictionary_codes, HYB_ERR_INVALID,
-                    "string group-by columns need dictionary_codes");
+          if (!(segment.encoding == HYB_ENC_DICTIONARY && segment.dictionary_codes)) {
+            missing_codes = true;
+            return;
+          }
           const uint32_t value_id =
               vector_get(segment.attribute_vector, segment.vector_type, segment.bit_width, rows[i].chunk_offset);
           keys_per_chunk[c][i].entries[g] = value_id >= segment.dictionary_size ? 0 : segment.dictionary_codes[value_id];
         }
-      }
+      });
+      ORC_CHECK(!missing_codes, HYB_ERR_INVALID, "string group-by columns need dictionary_codes");
     } else {
       // (:818-925) dense ids in first-appearance order starting at 1; 0 = NULL
       with_type(data_type, [&](auto tag) {
@@ -1607,6 +1612,25 @@ int orc_aggregate_hash(const hyb_table_view* table, const hyb_aggregate_query* q
     return results[result_id];
   };
 
+  // The Projection below the aggregate (operators/projection.cpp:60-190: one ExpressionEvaluator job per chunk) hands
+  // AggregateHash materialised argument columns; the aggregation itself runs chunk after chunk on one thread.
+  // arguments[a][c][i] = value of aggregate a's argument for row i of input chunk c.
+  std::vector<std::vector<std::vector<Scalar>>> arguments(aggregate_count);
+  for (uint32_t a = 0; a < aggregate_count; ++a) {
+    if (query->aggregates[a].function == HYB_AGG_COUNT_STAR) continue;
+    arguments[a].resize(input_chunks.size());
+  }
+  run_jobs(input_chunks.size(), threads, [&](size_t c) {
+    const auto& rows = *input_chunks[c];
+    for (uint32_t a = 0; a < aggregate_count; ++a) {
+      const auto& def = query->aggregates[a];
+      if (def.function == HYB_AGG_COUNT_STAR) continue;
+      auto& column = arguments[a][c];
+      column.resize(rows.size());
+      for (size_t i = 0; i < rows.size(); ++i) column[i] = evaluate_expression(table, def, rows[i]);
+    }
+  });
+
   for (size_t c = 0; c < input_chunks.size(); ++c) {
     const auto& rows = *input_chunks[c];
     auto& keys = keys_per_chunk[c];
@@ -1632,7 +1656,7 @@ int orc_aggregate_hash(const hyb_table_view* table, const hyb_aggregate_query* q
       const bool integral = input_types[a] == HYB_TYPE_INT32 || input_types[a] == HYB_TYPE_INT64;
       for (size_t i = 0; i < rows.size(); ++i) {  // _aggregate_segment (:605-655)
         auto& result = get_or_add_result(context, keys[i], rows[i], cache_result_ids);
-        const Scalar value = evaluate_expression(table, def, rows[i]);
+        const Scalar value = arguments[a][c][i];
         if (value.is_null) continue;
         switch (def.function) {  // WindowFunctionBuilder (abstract_aggregate_operator.hpp:30-133)
           case HYB_AGG_MIN:
@@ -1717,7 +1741,6 @@ int orc_aggregate_hash(const hyb_table_view* table, const hyb_aggregate_query* q
       }
     }
   }
-  (void)threads;
   return HYB_OK;
 }
 

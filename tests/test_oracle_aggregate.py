@@ -142,3 +142,33 @@ def test_tpch_q6_against_sqlite():
         "select sum(l_extendedprice*l_discount) from lineitem where l_shipdate >= '1994-01-01' and "
         "l_shipdate < '1995-01-01' and l_discount between 0.05 and 0.07001 and l_quantity < 24").fetchall()
     assert_rows_match_unordered(aggregate_rows(table, [], output), want, rel=1e-4)
+
+
+def test_chunk_parallel_phases_do_not_change_the_result():
+    """The CPU arm runs the Projection and the group-key partitioning as one job per chunk (like the reference's JobTasks)
+    and the aggregation phase on one thread: the output must be identical to the fully sequential run, bit for bit."""
+    from helpers import random_table
+    from hyrise_b200.tpch import TpchTables, L_DISCOUNT, L_EXTENDEDPRICE, L_LINESTATUS, L_QUANTITY, L_RETURNFLAG, L_SHIPDATE, L_TAX
+    tables = TpchTables(0.05, seed=7)
+    one = ("lit", capi.TYPE_INT32, 1)
+    aggregates = [Aggregate(capi.AGG_SUM, Expression.column(L_QUANTITY)),
+                  Aggregate(capi.AGG_SUM, Expression([("col", L_EXTENDEDPRICE), one, ("col", L_DISCOUNT), "-", "*", one,
+                                                      ("col", L_TAX), "+", "*"])),
+                  Aggregate(capi.AGG_AVG, Expression.column(L_DISCOUNT)), Aggregate(capi.AGG_COUNT_STAR)]
+    predicates = [Predicate(L_SHIPDATE, capi.PRED_LESS_THAN_EQUALS, "1998-09-02")]
+    sequential = orc.aggregate_hash(tables.lineitem, [L_RETURNFLAG, L_LINESTATUS], aggregates, predicates=predicates, threads=1)
+    parallel = orc.aggregate_hash(tables.lineitem, [L_RETURNFLAG, L_LINESTATUS], aggregates, predicates=predicates, threads=6)
+    assert sequential.group_count == parallel.group_count == 4
+    assert np.array_equal(sequential.row_ids, parallel.row_ids)
+    for a, b in zip(sequential.values, parallel.values):
+        assert np.array_equal(a, b)
+    rng = np.random.default_rng(9)
+    table = random_table(rng, 30_000, 1_999).encode("Dictionary")
+    mixed = [Aggregate(capi.AGG_SUM, Expression.column(2)), Aggregate(capi.AGG_MIN, Expression.column(1)),
+             Aggregate(capi.AGG_AVG, Expression.column(3)), Aggregate(capi.AGG_COUNT, Expression.column(0))]
+    for groupby in ([4], [0, 4], []):
+        sequential = orc.aggregate_hash(table, groupby, mixed, threads=1)
+        parallel = orc.aggregate_hash(table, groupby, mixed, threads=5)
+        assert np.array_equal(sequential.row_ids, parallel.row_ids)
+        for a, b, na, nb in zip(sequential.values, parallel.values, sequential.nulls, parallel.nulls):
+            assert np.array_equal(na, nb) and np.array_equal(a[~na], b[~nb])
