@@ -132,6 +132,7 @@ SYMBOLS = {
     "hyb_context_destroy": [_CTX],
     "hyb_device_count": [C.POINTER(C.c_int)],
     "hyb_context_synchronize": [_CTX],
+    "hyb_context_set_option": [_CTX, C.c_char_p, C.c_char_p],
     "hyb_host_alloc": [C.c_size_t, C.POINTER(_P)],
     "hyb_host_free": [_P],
     "hyb_table_upload": [_CTX, C.POINTER(TableView), C.POINTER(_U64)],

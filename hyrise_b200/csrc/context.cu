@@ -4,6 +4,7 @@
 // ValueSegment (value_segment.hpp:84-85), DictionarySegment (dictionary_segment.hpp:88-90) and
 // FrameOfReferenceSegment (frame_of_reference_segment.hpp:94-97), addressed by (table, chunk, column).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "device_utils.cuh"
@@ -355,6 +356,42 @@ int hyb_device_count(int* out_count) {
   return HYB_OK;
 }
 
+static bool apply_option(hyb::ContextOptions& options, const std::string& name, const std::string& value) {
+  const auto as_flag = [&](bool* out) {
+    if (value == "0" || value == "1") {
+      *out = value == "1";
+      return true;
+    }
+    return false;
+  };
+  if (name == "join_table") {
+    if (value == "auto") options.join_table = hyb::ContextOptions::kAuto;
+    else if (value == "hash") options.join_table = hyb::ContextOptions::kHash;
+    else if (value == "direct") options.join_table = hyb::ContextOptions::kDirect;
+    else if (value == "rank") options.join_table = hyb::ContextOptions::kRank;
+    else return false;
+    return true;
+  }
+  if (name == "join_rank") {
+    if (value != "ballot" && value != "match") return false;
+    options.join_ballot_rank = value == "ballot";
+    return true;
+  }
+  if (name == "join_span") return as_flag(&options.join_span);
+  if (name == "scan_bulk") return as_flag(&options.scan_bulk);
+  if (name == "aggregate_stream") return as_flag(&options.aggregate_stream);
+  if (name == "aggregate_split") return as_flag(&options.aggregate_split);
+  return false;
+}
+
+int hyb_context_set_option(hyb_context* context, const char* name, const char* value) {
+  HYB_CHECK(context && name && value, HYB_ERR_INVALID, "NULL argument");
+  std::lock_guard<std::mutex> lock(context->mutex);
+  HYB_CHECK(apply_option(context->options, name, value), HYB_ERR_INVALID,
+            std::string("unknown option ") + name + " = " + value);
+  return HYB_OK;
+}
+
 int hyb_context_create(int device_index, hyb_context** out_context) {
   HYB_CHECK(out_context, HYB_ERR_INVALID, "out_context is NULL");
   *out_context = nullptr;
@@ -371,6 +408,16 @@ int hyb_context_create(int device_index, hyb_context** out_context) {
   auto context = std::make_unique<hyb_context>();
   context->device = device_index;
   context->sm_count = prop.multiProcessorCount;
+  // The environment is consulted here and nowhere else (operator calls never touch getenv).
+  const std::pair<const char*, const char*> knobs[] = {
+      {"HYB_JOIN_TABLE", "join_table"}, {"HYB_JOIN_SPAN", "join_span"},     {"HYB_JOIN_RANK", "join_rank"},
+      {"HYB_SCAN_BULK", "scan_bulk"},   {"HYB_AGG_STREAM", "aggregate_stream"}, {"HYB_AGG_SPLIT", "aggregate_split"}};
+  for (const auto& knob : knobs) {
+    const char* text = std::getenv(knob.first);
+    if (text && !apply_option(context->options, knob.second, text)) {
+      return fail(HYB_ERR_INVALID, std::string("bad value for ") + knob.first + ": " + text);
+    }
+  }
   HYB_CUDA(cudaStreamCreateWithFlags(&context->stream, cudaStreamNonBlocking));
   *out_context = context.release();
   return HYB_OK;

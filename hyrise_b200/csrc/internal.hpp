@@ -97,6 +97,7 @@ struct Table {
     long long min = 0, max = 0;
     bool has_values = false;
     uint32_t constant_low_bits = 0;  // every non-NULL key has the same value in these low bits (capped at 16)
+    bool strictly_increasing = false;  // no NULLs and key[i] > key[i - 1] for every row position i
   };
   std::map<uint32_t, KeyBounds> key_bounds;
 
@@ -116,6 +117,7 @@ struct PosList {
   uint64_t* d_chunk_end = nullptr;      // inclusive prefix per chunk (chunk_count entries) + total at [chunk_count]
   std::vector<uint64_t> h_chunk_offsets;  // chunk_count + 1, filled on first query
   bool host_valid = false;
+  bool ascending = true;                // RowIDs in table order (what every TableScan produces)
   cudaStream_t stream = nullptr;
   hyb_context* owner = nullptr;         // buffers go back to owner's DeviceCache
   ~PosList();
@@ -180,8 +182,23 @@ struct DeviceCache {
 };
 }  // namespace hyb
 
+namespace hyb {
+// Tuning / test knobs. Read from the environment ONCE, when the context is created (never on an operator's hot path);
+// hyb_context_set_option changes them afterwards (the parity tests force every join table kind that way).
+struct ContextOptions {
+  enum JoinTable : int { kAuto = 0, kHash, kDirect, kRank };
+  int join_table = kAuto;      // HYB_JOIN_TABLE = hash | direct | rank
+  bool join_span = true;       // HYB_JOIN_SPAN = 0: keep the 4096-row tile kernels for the Inner/unique fast path
+  bool join_ballot_rank = true;  // HYB_JOIN_RANK = match: rank with MATCH.ANY instead of one ballot per radix bit
+  bool scan_bulk = true;       // HYB_SCAN_BULK = 0: scan without the cp.async.bulk + mbarrier input pipeline
+  bool aggregate_stream = true;  // HYB_AGG_STREAM = 0: keep the register-tile fast kernel for low-cardinality group-bys
+  bool aggregate_split = true;   // HYB_AGG_SPLIT = 0: never split a big dictionary over a CTA pair
+};
+}  // namespace hyb
+
 struct hyb_context {
   int device = 0;
+  hyb::ContextOptions options;
   cudaStream_t stream = nullptr;
   int sm_count = 148;
   std::mutex mutex;  // serialises enqueue + registry access; device work itself is asynchronous
@@ -251,6 +268,44 @@ int get_tile_map(hyb_context* context, Table* table, uint32_t tile_rows, const u
 int device_alloc(hyb_context* context, size_t bytes, void** out);
 void device_free(hyb_context* context, void* ptr);
 void device_cache_destroy(hyb_context* context);
+
+// Scratch memory of one operator call: everything taken through it goes back to the context's block cache when the
+// call returns, on EVERY path (the HYB_TRY / HYB_CUDA / HYB_CHECK early returns included).
+class DeviceScratch {
+ public:
+  explicit DeviceScratch(hyb_context* context) : _context(context) {}
+  DeviceScratch(const DeviceScratch&) = delete;
+  DeviceScratch& operator=(const DeviceScratch&) = delete;
+  ~DeviceScratch() {
+    for (void* block : _blocks) device_free(_context, block);
+  }
+  int alloc(size_t bytes, void** out) {
+    const int status = device_alloc(_context, bytes, out);
+    if (status == HYB_OK) _blocks.push_back(*out);
+    return status;
+  }
+  template <typename T>
+  int alloc_array(size_t count, T** out) {
+    void* block = nullptr;
+    const int status = alloc(sizeof(T) * (count ? count : 1), &block);
+    *out = static_cast<T*>(block);
+    return status;
+  }
+  // Hand a block over to a result object (it is no longer released by this scope).
+  void* release(void* block) {
+    for (auto& entry : _blocks) {
+      if (entry == block) {
+        entry = nullptr;
+        break;
+      }
+    }
+    return block;
+  }
+
+ private:
+  hyb_context* _context;
+  std::vector<void*> _blocks;
+};
 
 void timing_begin(hyb_context* context);
 void timing_kernel_begin(hyb_context* context);

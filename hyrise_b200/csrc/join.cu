@@ -177,7 +177,17 @@ struct HashTable {
   long long direct_min;
   unsigned long long direct_range;
   uint32_t direct_shift;
+  // Rank mode (dense key domain AND a build side whose keys strictly increase with the build position — primary keys
+  // as dbgen and most loaders store them, also behind an order-preserving PosList): one {presence bits, ~(smallest
+  // position)} pair per block of 32 key values. position(key) = smallest position of the block + number of present
+  // keys below it in the block. 2 bits per key value instead of 32: the table of config 3 (60 M key values) shrinks
+  // from 240 MB to 15 MB and stays in L2 for both probe passes, whatever the probe order. Indexed by key - direct_min.
+  uint2* rank_blocks;
 };
+
+__device__ __forceinline__ uint32_t rank_block_position(const uint2 block, uint32_t bit) {
+  return ~block.y + __popc(block.x & ((1u << bit) - 1u));
+}
 
 __device__ __forceinline__ uint32_t mix32(uint32_t h) {
   h ^= h >> 16;
@@ -200,6 +210,15 @@ __device__ __forceinline__ unsigned long long pack_slot(uint32_t key_bits, uint3
 // Looks `key` up. Returns the slot index (kNoMatch if absent) and the slot's value. A bucket with a free slot ends the
 // search (there are no deletions). Written for few instructions: the probe kernel is issue-bound, not bandwidth-bound.
 __device__ __forceinline__ uint32_t table_find(const HashTable& table, long long key, uint32_t& value) {
+  if (table.rank_blocks) {
+    const unsigned long long offset = static_cast<unsigned long long>(key) - static_cast<unsigned long long>(table.direct_min);
+    if (offset >= table.direct_range) return kNoMatch;
+    const uint2 block = __ldg(table.rank_blocks + (offset >> 5));
+    const uint32_t bit = static_cast<uint32_t>(offset) & 31u;
+    if (!((block.x >> bit) & 1u)) return kNoMatch;
+    value = rank_block_position(block, bit);
+    return static_cast<uint32_t>(offset);
+  }
   if (table.direct) {
     const unsigned long long offset = static_cast<unsigned long long>(key) - static_cast<unsigned long long>(table.direct_min);
     const unsigned long long index = offset >> table.direct_shift;
@@ -242,6 +261,14 @@ struct BuildParams {
 };
 
 __device__ __forceinline__ void table_insert(const BuildParams& params, long long key, uint32_t value) {
+  if (params.table.rank_blocks) {
+    // keys are unique here (strictly increasing build side): no return value needed, both updates are fire-and-forget
+    const unsigned long long offset = static_cast<unsigned long long>(key) - static_cast<unsigned long long>(params.table.direct_min);
+    uint2* block = params.table.rank_blocks + (offset >> 5);
+    atomicOr(&block->x, 1u << (static_cast<uint32_t>(offset) & 31u));
+    atomicMax(&block->y, ~value);
+    return;
+  }
   if (params.table.direct) {
     // every key lies inside [direct_min, direct_min + direct_range): the bounds cover the whole column
     const unsigned long long index =
@@ -322,18 +349,35 @@ __global__ void __launch_bounds__(kJoinThreads) join_build_kernel(const BuildPar
   }
 }
 
-// Smallest / largest non-NULL key of a column: out = {min, max, count of non-NULL rows, AND of keys, OR of keys}. Decides
-// direct-address mode; bits where AND == OR are the same in every key.
+// Smallest / largest non-NULL key of a column: out = {min, max, count of non-NULL rows, AND of keys, OR of keys, order
+// violations}. Decides direct-address mode; bits where AND == OR are the same in every key; zero violations (no NULL, every
+// key greater than the key one position earlier) means the column strictly increases in row order (rank mode).
 __global__ void __launch_bounds__(kJoinThreads) join_key_bounds_kernel(const KeySource source, long long* __restrict__ out) {
   long long low = 0x7FFFFFFFFFFFFFFFll, high = -0x7FFFFFFFFFFFFFFFll - 1;
-  unsigned long long count = 0, all_and = ~0ull, all_or = 0ull;
+  unsigned long long count = 0, all_and = ~0ull, all_or = 0ull, violations = 0;
   for (uint32_t tile = blockIdx.x; tile < source.tile_count; tile += gridDim.x) {
     const TileRef ref = tile_ref(source, tile);
     const DevSegment segment = source.tile_map ? source.segments[ref.chunk] : DevSegment{};
     for (uint32_t index = threadIdx.x; index < kJoinTileRows; index += kJoinThreads) {
       long long key;
       bool is_null;
-      if (!load_key1(source, ref, segment, index, key, is_null) || is_null) continue;
+      if (!load_key1(source, ref, segment, index, key, is_null)) continue;
+      if (is_null) {
+        ++violations;
+        continue;
+      }
+      // the key one position earlier: same tile, or the last row of the previous tile (possibly another chunk)
+      long long previous = 0;
+      bool previous_null = false, has_previous = false;
+      if (index > 0) {
+        has_previous = load_key1(source, ref, segment, index - 1, previous, previous_null);
+      } else if (tile > 0 && source.tile_map) {
+        const TileRef before = tile_ref(source, tile - 1);
+        const DevSegment& before_segment = source.segments[before.chunk];
+        const uint32_t last = min(static_cast<uint32_t>(kJoinTileRows), before_segment.row_count - before.row0) - 1;
+        has_previous = load_key1(source, before, before_segment, last, previous, previous_null);
+      }
+      if (has_previous && !previous_null && previous >= key) ++violations;
       low = key < low ? key : low;
       high = key > high ? key : high;
       all_and &= static_cast<unsigned long long>(key);
@@ -348,15 +392,19 @@ __global__ void __launch_bounds__(kJoinThreads) join_key_bounds_kernel(const Key
     low = other_low < low ? other_low : low;
     high = other_high > high ? other_high : high;
     count += __shfl_xor_sync(kFullMask, count, delta);
+    violations += __shfl_xor_sync(kFullMask, violations, delta);
     all_and &= __shfl_xor_sync(kFullMask, all_and, delta);
     all_or |= __shfl_xor_sync(kFullMask, all_or, delta);
   }
-  if ((threadIdx.x & 31) == 0 && count) {
-    atomicMin(out, low);
-    atomicMax(out + 1, high);
-    atomicAdd(reinterpret_cast<unsigned long long*>(out + 2), count);
-    atomicAnd(reinterpret_cast<unsigned long long*>(out + 3), all_and);
-    atomicOr(reinterpret_cast<unsigned long long*>(out + 4), all_or);
+  if ((threadIdx.x & 31) == 0) {
+    if (count) {
+      atomicMin(out, low);
+      atomicMax(out + 1, high);
+      atomicAdd(reinterpret_cast<unsigned long long*>(out + 2), count);
+      atomicAnd(reinterpret_cast<unsigned long long*>(out + 3), all_and);
+      atomicOr(reinterpret_cast<unsigned long long*>(out + 4), all_or);
+    }
+    if (violations) atomicAdd(reinterpret_cast<unsigned long long*>(out + 5), violations);
   }
 }
 
@@ -923,6 +971,302 @@ __global__ void __launch_bounds__(kJoinThreads, 3) join_probe_write_kernel(const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Span kernels: the Inner / unique-build / direct-or-rank-table path (TPC-H's PK-FK joins) over 8192-row spans.
+//
+// What bounded the 4096-row tile kernels was not DRAM but the store path: every probe row wrote its two RowIDs with two
+// 8-byte stores into ~256-byte runs (a tile's 32 rows per partition), 32 different sectors per warp instruction. Here a
+// CTA owns 8192 consecutive probe rows, ranks them exactly as before (lane order = probe order), but scatters
+// {build position, row index | partition} into SHARED memory at the row's position inside the span's partition-ordered
+// output. The span's output then leaves in one flat loop: consecutive threads hold consecutive output rows of a run, so
+// every warp store is 256 contiguous bytes per PosList (runs average 8192 / partitions rows). The count pass uses the same
+// loader and only adds to a shared histogram. Loads are issued 8 steps at a time (keys, then table words, then use).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kSpanThreads = 512;
+constexpr int kSpanWarps = kSpanThreads / 32;
+constexpr int kSpanRows = kSpanWarps * kJoinRowsPerWarp;  // 8192
+constexpr int kCountGroup = 8;  // probe steps whose loads are in flight together: count pass
+constexpr int kRankGroup = 4;   //   ranking pass (the ranked rows of all 16 steps stay in registers as well)
+enum : int { kTableDirect = 0, kTableRank = 1 };
+
+// Keys and matches of kSpanGroup probe steps of one warp chunk: step s, lane l -> row row_base + 32 s.
+template <uint32_t kCodec, bool kFull, int kTable, int kSpanGroup>
+__device__ __forceinline__ void span_lookup(const ProbeParams& params, const DevSegment& segment, uint32_t row_base,
+                                            uint32_t for_minimum, uint32_t (&match)[kSpanGroup], uint32_t (&key_low)[kSpanGroup]) {
+  constexpr bool kWide = kCodec == kCodecPlain64;
+  static_assert(!(kWide && kTable == kTableRank), "rank tables are probed with int32 keys");
+  const uint32_t row_count = segment.row_count;
+  uint32_t key_high[kWide ? kSpanGroup : 1];
+  uint32_t valid_mask = 0;
+#pragma unroll
+  for (int s = 0; s < kSpanGroup; ++s) {
+    const uint32_t row = row_base + s * 32;
+    const bool valid = kFull || row < row_count;
+    valid_mask |= valid ? (1u << s) : 0u;
+    key_low[s] = 0;
+    if constexpr (kWide) key_high[s] = 0;
+    if (valid) {
+      if constexpr (kCodec == kCodecPlain32) {
+        key_low[s] = ld_stream_u32(static_cast<const uint32_t*>(segment.values) + row);
+      } else if constexpr (kCodec == kCodecPlain64) {
+        const uint2 bits = ld_stream_v2(static_cast<const long long*>(segment.values) + row);
+        key_low[s] = bits.x;
+        key_high[s] = bits.y;
+      } else if constexpr (kCodec == kCodecFor8) {
+        key_low[s] = for_minimum + __ldg(static_cast<const uint8_t*>(segment.av) + row);
+      } else if constexpr (kCodec == kCodecFor16) {
+        key_low[s] = for_minimum + __ldg(static_cast<const uint16_t*>(segment.av) + row);
+      } else {
+        key_low[s] = for_minimum + ld_stream_u32(static_cast<const uint32_t*>(segment.av) + row);
+      }
+    }
+  }
+  if constexpr (kTable == kTableRank) {
+    const uint2* __restrict__ blocks = params.table.rank_blocks;
+    const uint32_t minimum = static_cast<uint32_t>(params.table.direct_min);
+    const uint32_t range = static_cast<uint32_t>(params.table.direct_range);
+    uint2 block[kSpanGroup];
+#pragma unroll
+    for (int s = 0; s < kSpanGroup; ++s) {
+      const uint32_t offset = key_low[s] - minimum;  // wraps above the range for keys below the minimum
+      block[s] = make_uint2(0u, 0u);
+      if (((valid_mask >> s) & 1u) && offset < range) block[s] = __ldg(blocks + (offset >> 5));
+    }
+#pragma unroll
+    for (int s = 0; s < kSpanGroup; ++s) {
+      const uint32_t bit = (key_low[s] - minimum) & 31u;
+      match[s] = ((block[s].x >> bit) & 1u) ? rank_block_position(block[s], bit) : kNoMatch;
+    }
+  } else if constexpr (!kWide) {
+    const uint32_t* __restrict__ direct = params.table.direct;
+    const uint32_t minimum = static_cast<uint32_t>(params.table.direct_min);
+    const uint32_t range = static_cast<uint32_t>(params.table.direct_range);
+#pragma unroll
+    for (int s = 0; s < kSpanGroup; ++s) {
+      const uint32_t index = key_low[s] - minimum;
+      match[s] = kNoMatch;
+      if (((valid_mask >> s) & 1u) && index < range) match[s] = __ldg(direct + index);
+    }
+  } else {
+    const uint32_t* __restrict__ direct = params.table.direct;
+    const unsigned long long minimum = static_cast<unsigned long long>(params.table.direct_min);
+    const unsigned long long range = params.table.direct_range;
+    const uint32_t shift = params.table.direct_shift;
+    const unsigned long long low_bits = (1ull << shift) - 1ull;
+#pragma unroll
+    for (int s = 0; s < kSpanGroup; ++s) {
+      const unsigned long long offset = ((static_cast<unsigned long long>(key_high[s]) << 32) | key_low[s]) - minimum;
+      const unsigned long long index = offset >> shift;
+      match[s] = kNoMatch;
+      if (((valid_mask >> s) & 1u) && index < range && !(offset & low_bits)) match[s] = __ldg(direct + index);
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t span_for_minimum(const DevSegment& segment, uint32_t codec, uint32_t first_row) {
+  // first_row is a multiple of 512 and spans start at multiples of 8192: a warp chunk lies inside one 2048-row block
+  if (codec < kCodecFor8 || first_row >= segment.row_count) return 0;
+  return static_cast<uint32_t>(__ldg(static_cast<const int32_t*>(segment.values) + first_row / HYB_FOR_BLOCK_SIZE));
+}
+
+// Lanes of the warp whose row falls into the same radix partition. One ballot per radix bit (7 for config 3) keeps the
+// four schedulers of an SM busy in parallel; MATCH.ANY was measured at 16 cycles per warp instruction and SM.
+template <bool kBallot>
+__device__ __forceinline__ uint32_t partition_peers(uint32_t partition, uint32_t radix_bits) {
+  if constexpr (kBallot) {
+    uint32_t peers = kFullMask;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      if (static_cast<uint32_t>(b) < radix_bits) {  // uniform
+        const bool set = (partition >> b) & 1u;
+        const uint32_t vote = __ballot_sync(kFullMask, set);
+        peers &= set ? vote : ~vote;
+      }
+    }
+    return peers;
+  } else {
+    return __match_any_sync(kFullMask, partition);
+  }
+}
+
+template <uint32_t kCodec, bool kFull, int kTable>
+__device__ __forceinline__ void span_count_rows(const ProbeParams& params, const TileRef& ref, const DevSegment& segment,
+                                                uint32_t warp, uint32_t lane, uint32_t* histogram) {
+  const uint32_t chunk0 = warp * kJoinRowsPerWarp;
+  const uint32_t for_minimum = span_for_minimum(segment, kCodec, ref.row0 + chunk0);
+#pragma unroll 1
+  for (int group = 0; group < kProbeSteps / kCountGroup; ++group) {
+    uint32_t match[kCountGroup], key_low[kCountGroup];
+    span_lookup<kCodec, kFull, kTable, kCountGroup>(params, segment, ref.row0 + chunk0 + group * kCountGroup * 32 + lane,
+                                                    for_minimum, match, key_low);
+#pragma unroll
+    for (int s = 0; s < kCountGroup; ++s) {
+      if (match[s] != kNoMatch) atomicAdd(histogram + (key_low[s] & params.partition_mask), 1u);
+    }
+  }
+}
+
+struct SpanRows {
+  uint32_t match[kProbeSteps];
+  uint32_t rank_partition[kProbeSteps];  // rank inside the (warp chunk, partition) run | partition << 16
+};
+
+template <uint32_t kCodec, bool kFull, int kTable, bool kBallot>
+__device__ __forceinline__ void span_rank_rows(const ProbeParams& params, const TileRef& ref, const DevSegment& segment,
+                                               uint32_t warp, uint32_t lane, uint32_t* warp_histogram, SpanRows& rows) {
+  const uint32_t chunk0 = warp * kJoinRowsPerWarp;
+  const uint32_t for_minimum = span_for_minimum(segment, kCodec, ref.row0 + chunk0);
+  const uint32_t lanes_below = (1u << lane) - 1u;
+  const uint32_t radix_bits = __popc(params.partition_mask);
+#pragma unroll
+  for (int group = 0; group < kProbeSteps / kRankGroup; ++group) {
+    uint32_t match[kRankGroup], key_low[kRankGroup];
+    span_lookup<kCodec, kFull, kTable, kRankGroup>(params, segment, ref.row0 + chunk0 + group * kRankGroup * 32 + lane,
+                                                   for_minimum, match, key_low);
+#pragma unroll
+    for (int s = 0; s < kRankGroup; ++s) {
+      const uint32_t partition = key_low[s] & params.partition_mask;
+      const uint32_t peers = partition_peers<kBallot>(partition, radix_bits);
+      const uint32_t emitting = __ballot_sync(kFullMask, match[s] != kNoMatch) & peers;
+      const int leader = __ffs(peers) - 1;
+      uint32_t earlier = 0;
+      if (lane == static_cast<uint32_t>(leader) && emitting) earlier = atomicAdd(warp_histogram + partition, __popc(emitting));
+      earlier = __shfl_sync(kFullMask, earlier, leader);
+      rows.match[group * kRankGroup + s] = match[s];
+      rows.rank_partition[group * kRankGroup + s] = (earlier + __popc(emitting & lanes_below)) | (partition << 16);
+    }
+  }
+}
+
+// Codec and span fullness are uniform per span: one switch per CTA in front of fully specialised loops.
+#define HYB_SPAN_DISPATCH(CALL)                                                    \
+  do {                                                                             \
+    const bool span_full = ref.row0 + kSpanRows <= segment.row_count;              \
+    if constexpr (kTable == kTableRank) {                                          \
+      switch (codec) {                                                             \
+        case kCodecPlain32:                                                        \
+          if (span_full) CALL(kCodecPlain32, true) else CALL(kCodecPlain32, false) \
+          break;                                                                   \
+        case kCodecFor8:                                                           \
+          if (span_full) CALL(kCodecFor8, true) else CALL(kCodecFor8, false)       \
+          break;                                                                   \
+        case kCodecFor16:                                                          \
+          if (span_full) CALL(kCodecFor16, true) else CALL(kCodecFor16, false)     \
+          break;                                                                   \
+        default:                                                                   \
+          if (span_full) CALL(kCodecFor32, true) else CALL(kCodecFor32, false)     \
+          break;                                                                   \
+      }                                                                            \
+    } else {                                                                       \
+      switch (codec) {                                                             \
+        case kCodecPlain32:                                                        \
+          if (span_full) CALL(kCodecPlain32, true) else CALL(kCodecPlain32, false) \
+          break;                                                                   \
+        case kCodecPlain64:                                                        \
+          if (span_full) CALL(kCodecPlain64, true) else CALL(kCodecPlain64, false) \
+          break;                                                                   \
+        case kCodecFor8:                                                           \
+          if (span_full) CALL(kCodecFor8, true) else CALL(kCodecFor8, false)       \
+          break;                                                                   \
+        case kCodecFor16:                                                          \
+          if (span_full) CALL(kCodecFor16, true) else CALL(kCodecFor16, false)     \
+          break;                                                                   \
+        default:                                                                   \
+          if (span_full) CALL(kCodecFor32, true) else CALL(kCodecFor32, false)     \
+          break;                                                                   \
+      }                                                                            \
+    }                                                                              \
+  } while (0)
+
+// Matches per (partition, span). params.probe is the span-granular source (tile map of kSpanRows-row tiles).
+template <int kTable>
+__global__ void __launch_bounds__(kSpanThreads, 2) join_span_count_kernel(const ProbeParams params) {
+  __shared__ uint32_t s_histogram[kMaxPartitions];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t span = blockIdx.x;
+  if (threadIdx.x < params.partition_count) s_histogram[threadIdx.x] = 0;
+  __syncthreads();
+  const TileRef ref = tile_ref(params.probe, span);
+  const DevSegment segment = params.probe.segments[ref.chunk];
+  const uint32_t codec = tile_codec(params.probe, segment);
+#define HYB_SPAN_COUNT(CODEC, FULL) span_count_rows<CODEC, FULL, kTable>(params, ref, segment, warp, lane, s_histogram);
+  HYB_SPAN_DISPATCH(HYB_SPAN_COUNT);
+#undef HYB_SPAN_COUNT
+  __syncthreads();
+  if (threadIdx.x < params.partition_count) {
+    params.histogram[static_cast<size_t>(threadIdx.x) * params.probe.tile_count + span] = s_histogram[threadIdx.x];
+  }
+}
+
+template <int kTable, bool kBallot>
+__global__ void __launch_bounds__(kSpanThreads, 2) join_span_write_kernel(const ProbeParams params) {
+  extern __shared__ uint2 s_stage[];  // kSpanRows x {build position, row index in the span | partition << 16}
+  __shared__ uint32_t s_warp_histogram[kSpanWarps][kMaxPartitions];  // counts, then exclusive prefixes over the warps
+  __shared__ uint32_t s_local_start[kMaxPartitions];                 // first staged row of a partition
+  __shared__ unsigned long long s_destination[kMaxPartitions];       // output index of staged row i of partition p = this + i
+  __shared__ uint32_t s_scan[8];
+  __shared__ uint32_t s_total;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t span = blockIdx.x;
+  const uint32_t partition_count = params.partition_count;
+  for (uint32_t p = lane; p < partition_count; p += 32) s_warp_histogram[warp][p] = 0;
+  __syncwarp();
+  const TileRef ref = tile_ref(params.probe, span);
+  const DevSegment segment = params.probe.segments[ref.chunk];
+  const uint32_t codec = tile_codec(params.probe, segment);
+  // this span's run starts (exclusive scan of the count pass), in flight while the rows are ranked
+  unsigned long long run_start = 0;
+  if (threadIdx.x < partition_count) {
+    run_start = __ldg(params.run_starts + static_cast<size_t>(threadIdx.x) * params.probe.tile_count + span);
+  }
+  SpanRows rows;
+#define HYB_SPAN_RANK(CODEC, FULL) \
+  span_rank_rows<CODEC, FULL, kTable, kBallot>(params, ref, segment, warp, lane, s_warp_histogram[warp], rows);
+  HYB_SPAN_DISPATCH(HYB_SPAN_RANK);
+#undef HYB_SPAN_RANK
+  __syncthreads();
+  // per partition: exclusive prefix over the warp chunks, then over the partitions
+  uint32_t partition_total = 0;
+  if (threadIdx.x < partition_count) {
+#pragma unroll
+    for (int w = 0; w < kSpanWarps; ++w) {
+      const uint32_t count = s_warp_histogram[w][threadIdx.x];
+      s_warp_histogram[w][threadIdx.x] = partition_total;
+      partition_total += count;
+    }
+  }
+  const uint32_t inclusive = warp_inclusive_scan(partition_total, lane);
+  if (warp < 8 && lane == 31) s_scan[warp] = inclusive;
+  __syncthreads();
+  if (threadIdx.x < partition_count) {
+    uint32_t before = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) before += w < static_cast<int>(warp) ? s_scan[w] : 0u;
+    const uint32_t exclusive = before + inclusive - partition_total;
+    s_local_start[threadIdx.x] = exclusive;
+    s_destination[threadIdx.x] = run_start - exclusive;  // modulo 2^64: run_start + (i - exclusive) for staged row i
+    if (threadIdx.x + 1 == partition_count) s_total = exclusive + partition_total;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int step = 0; step < kProbeSteps; ++step) {
+    if (rows.match[step] == kNoMatch) continue;
+    const uint32_t partition = rows.rank_partition[step] >> 16;
+    const uint32_t at = s_local_start[partition] + s_warp_histogram[warp][partition] + (rows.rank_partition[step] & 0xFFFFu);
+    s_stage[at] = make_uint2(rows.match[step], (warp * kJoinRowsPerWarp + step * 32 + lane) | (partition << 16));
+  }
+  __syncthreads();
+  const uint32_t total = s_total;
+  for (uint32_t i = threadIdx.x; i < total; i += kSpanThreads) {
+    const uint2 staged = s_stage[i];
+    const unsigned long long at = s_destination[staged.y >> 16] + i;
+    const hyb_row_id build_row = position_to_row_id(params.build, staged.x);
+    st_stream_v2(params.out_build + at, build_row.chunk_id, build_row.chunk_offset);
+    st_stream_v2(params.out_probe + at, ref.chunk, ref.row0 + (staged.y & 0xFFFFu));
+  }
+}
+#undef HYB_SPAN_DISPATCH
+
 // hyb_join_partition / hyb_join_partition_push, ranked-write pass: the stable split of one side's non-NULL
 // {key, global RowID} tuples by owner rank. Same ranking as join_probe_write_kernel, but nothing is looked up and the
 // keys stay in registers between the passes, so the pass costs one read of the key column and one 16-byte store per
@@ -1136,20 +1480,21 @@ static int column_key_bounds(hyb_context* context, const SideInfo& side, uint32_
     HYB_TRY(get_tile_map(context, table, kJoinTileRows, &whole.tile_map, &whole.tile_count));
     whole.position_count = table->row_count();
     void* device_bounds = nullptr;
-    HYB_TRY(device_alloc(context, 5 * sizeof(long long), &device_bounds));
-    const long long initial[5] = {0x7FFFFFFFFFFFFFFFll, -0x7FFFFFFFFFFFFFFFll - 1, 0, -1ll, 0};
+    HYB_TRY(device_alloc(context, 6 * sizeof(long long), &device_bounds));
+    const long long initial[6] = {0x7FFFFFFFFFFFFFFFll, -0x7FFFFFFFFFFFFFFFll - 1, 0, -1ll, 0, 0};
     HYB_CUDA(cudaMemcpyAsync(device_bounds, initial, sizeof(initial), cudaMemcpyHostToDevice, context->stream));
     const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(whole.tile_count, context->sm_count * 8));
     join_key_bounds_kernel<<<grid, kJoinThreads, 0, context->stream>>>(whole, static_cast<long long*>(device_bounds));
     HYB_CUDA(cudaGetLastError());
     ++*launches;
-    long long host_bounds[5] = {};
+    long long host_bounds[6] = {};
     HYB_CUDA(cudaMemcpyAsync(host_bounds, device_bounds, sizeof(host_bounds), cudaMemcpyDeviceToHost, context->stream));
     HYB_CUDA(cudaStreamSynchronize(context->stream));
     device_free(context, device_bounds);
     bounds.has_values = host_bounds[2] != 0;
     bounds.min = host_bounds[0];
     bounds.max = host_bounds[1];
+    bounds.strictly_increasing = bounds.has_values && host_bounds[5] == 0;
     if (bounds.has_values) {
       const unsigned long long varying = static_cast<unsigned long long>(host_bounds[3]) ^ static_cast<unsigned long long>(host_bounds[4]);
       while (bounds.constant_low_bits < 16 && !((varying >> bounds.constant_low_bits) & 1ull)) ++bounds.constant_low_bits;
@@ -1205,47 +1550,58 @@ int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const h
   const bool wide = build.data_type == HYB_TYPE_INT64 || probe.data_type == HYB_TYPE_INT64;
   const bool semi_or_anti = mode == HYB_JOIN_SEMI || mode == HYB_JOIN_ANTI_NULL_AS_TRUE || mode == HYB_JOIN_ANTI_NULL_AS_FALSE;
   cudaStream_t stream = context->stream;
+  const ContextOptions options = context->options;
   uint32_t launches = 0;
+  DeviceScratch scratch(context);  // every scratch block of this call goes back to the cache on every exit path
 
   timing_begin(context);
 
   // ---- build -----------------------------------------------------------------------------------------------------
-  // Dense key domain (range of the build column <= 8x its rows): direct-address table, one uint32 per key value.
+  // Dense key domain (range of the build column <= 8x its rows): direct-address table, one uint32 per key value — or,
+  // when the build keys strictly increase with the build position, the 2-bits-per-key-value rank table.
   // Otherwise: bucketised open addressing at load factor <= 0.5.
   Table::KeyBounds bounds{};
   HYB_TRY(column_key_bounds(context, build, build_side->column_id, &bounds, &launches));
   const unsigned long long key_span = static_cast<unsigned long long>(bounds.max) - static_cast<unsigned long long>(bounds.min);
-  // HYB_JOIN_TABLE=hash|direct overrides the choice (the parity tests run every case in both modes).
-  const char* forced = std::getenv("HYB_JOIN_TABLE");
-  const bool force_hash = forced && forced[0] == 'h';
-  const bool force_direct = forced && forced[0] == 'd';
+  // options.join_table overrides the choice (the parity tests run every case with every table kind).
+  const bool force_hash = options.join_table == ContextOptions::kHash;
+  const bool force_direct = options.join_table == ContextOptions::kDirect;
   const uint32_t direct_shift = bounds.constant_low_bits;  // keys agree in these low bits (one rank's share of an exchange)
   const unsigned long long direct_span = key_span >> direct_shift;
   const bool direct = bounds.has_values && build.positions > 0 && direct_span < 0xFFFFFFE0ull && !force_hash &&
-                      (direct_span < 8 * build.positions + 65'536 || (force_direct && direct_span < (1ull << 28)));
+                      (direct_span < 8 * build.positions + 65'536 ||
+                       (options.join_table != ContextOptions::kAuto && direct_span < (1ull << 28)));
+  // Rank table: positions must grow with the keys — the column does (cached with the key bounds) and a PosList on top of
+  // it keeps the table order.
+  const bool rank = direct && !force_direct && bounds.strictly_increasing && key_span < 0xFFFFFFE0ull &&
+                    (!build.filter || build.filter->ascending);
   uint64_t bucket_count = 1;
   while (bucket_count * 2 < build.positions) bucket_count <<= 1;  // >= positions / 2 buckets -> load factor <= 0.5
   HYB_CHECK(bucket_count * 4 < 0xFFFFFFF0ull, HYB_ERR_UNSUPPORTED, "build side too large for 32-bit slot indexes");
-  const uint64_t slot_count = direct ? direct_span + 1 : bucket_count * 4;
-  const size_t slot_bytes = direct ? sizeof(uint32_t) : sizeof(uint64_t);
+  const uint64_t slot_count = rank ? (key_span >> 5) + 1 : direct ? direct_span + 1 : bucket_count * 4;
+  const size_t slot_bytes = direct && !rank ? sizeof(uint32_t) : sizeof(uint64_t);
   void* slots = nullptr;
   void* wide_keys = nullptr;
   void* control = nullptr;  // [0] duplicate keys, [1] NULL build keys, [2] output overflow, [4..5] total (u64)
-  HYB_TRY(device_alloc(context, slot_bytes * slot_count, &slots));
-  HYB_CUDA(cudaMemsetAsync(slots, 0xFF, slot_bytes * slot_count, stream));
-  HYB_TRY(device_alloc(context, 64, &control));
+  HYB_TRY(scratch.alloc(slot_bytes * slot_count, &slots));
+  HYB_CUDA(cudaMemsetAsync(slots, rank ? 0x00 : 0xFF, slot_bytes * slot_count, stream));
+  HYB_TRY(scratch.alloc(64, &control));
   HYB_CUDA(cudaMemsetAsync(control, 0, 64, stream));
   auto* flags = static_cast<uint32_t*>(control);
   auto* total_slot = reinterpret_cast<unsigned long long*>(flags + 4);
   if (wide && !direct) {
-    HYB_TRY(device_alloc(context, sizeof(long long) * std::max<uint64_t>(build.positions, 1), &wide_keys));
+    HYB_TRY(scratch.alloc(sizeof(long long) * std::max<uint64_t>(build.positions, 1), &wide_keys));
     HYB_CUDA(cudaMemsetAsync(wide_keys, 0x80, sizeof(long long) * std::max<uint64_t>(build.positions, 1), stream));
   }
   HashTable table{};
-  table.slots = static_cast<unsigned long long*>(slots);  // non-NULL also in direct mode: "a table exists"
+  table.slots = static_cast<unsigned long long*>(slots);  // non-NULL also in direct / rank mode: "a table exists"
   table.bucket_mask = static_cast<uint32_t>(bucket_count - 1);
   table.wide_keys = static_cast<const long long*>(wide_keys);
-  if (direct) {
+  if (rank) {
+    table.rank_blocks = static_cast<uint2*>(slots);
+    table.direct_min = bounds.min;
+    table.direct_range = key_span + 1;
+  } else if (direct) {
     table.direct = static_cast<uint32_t*>(slots);
     table.direct_min = bounds.min;
     table.direct_range = direct_span + 1;
@@ -1277,8 +1633,32 @@ int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const h
   HYB_CUDA(cudaMemsetAsync(partition_offsets, 0, sizeof(uint64_t) * (size_t{partition_count} + 2), stream));
 
   const uint32_t probe_tiles = probe.source.tile_count;
+  // Lean path of the case that dominates (Inner, dense unique build side): 1 = int32 keys on both sides, 2 = int64 probe
+  // keys against a (possibly shifted) direct table.
+  const uint32_t fast = (mode == HYB_JOIN_INNER && (direct || rank))
+                            ? ((direct_shift == 0 && !wide) ? 1u : ((!rank && probe.data_type == HYB_TYPE_INT64) ? 2u : 0u))
+                            : 0u;
+  // Span kernels: every probe segment must decode with a lean codec (plain values or FrameOfReference in a
+  // FixedWidthIntegerVector, no NULL vector); anything else keeps the tile kernels, which pick a decoder per tile.
+  bool use_span = options.join_span && fast != 0 && !probe.filter && probe_tiles > 0;
+  if (use_span) {
+    const Table* table_ptr = probe.table;
+    for (uint32_t chunk = 0; chunk < table_ptr->chunk_count() && use_span; ++chunk) {
+      const DevSegment& segment = table_ptr->segments[size_t{chunk} * table_ptr->column_count + probe_side->column_id];
+      if (segment.nulls) use_span = false;
+      if (segment.encoding == HYB_ENC_DICTIONARY) use_span = false;
+      if (segment.encoding == HYB_ENC_FRAME_OF_REFERENCE && segment.vector_type == HYB_VEC_BITPACKED) use_span = false;
+      const bool plain64 = segment.encoding == HYB_ENC_UNENCODED && segment.data_type == HYB_TYPE_INT64;
+      if ((fast == 2) != plain64) use_span = false;
+    }
+  }
+  KeySource span_source = probe.source;
+  if (use_span) HYB_TRY(get_tile_map(context, probe.table, kSpanRows, &span_source.tile_map, &span_source.tile_count));
+  const uint32_t histogram_tiles = use_span ? span_source.tile_count : probe_tiles;
+
   // Hash tables: the count kernel keeps match + partition per probe slot so that the write kernel does not repeat the
-  // random table accesses. Direct-address tables are probed sequentially; looking up twice is cheaper than 10 bytes/row.
+  // random table accesses. Direct-address / rank tables are probed sequentially or from L2; looking up twice is cheaper
+  // than 10 bytes/row.
   const bool store_matches = !direct;
   const auto count_kernel = store_matches ? join_probe_count_kernel<true> : join_probe_count_kernel<false>;
   const auto write_kernel = store_matches ? join_probe_write_kernel<true> : join_probe_write_kernel<false>;
@@ -1295,16 +1675,17 @@ int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const h
   void* dup_counts = nullptr;
   void* dup_offsets = nullptr;
   void* dup_positions = nullptr;
-  const size_t histogram_entries = size_t{partition_count} * probe_tiles;
+  size_t histogram_entries = size_t{partition_count} * histogram_tiles;
   ProbeParams params{};
   uint32_t host_control[8] = {};
   if (probe_tiles) {
     if (store_matches) {
-      HYB_TRY(device_alloc(context, sizeof(uint32_t) * probe_slots, &matches));
-      HYB_TRY(device_alloc(context, probe_slots, &partitions));
+      HYB_TRY(scratch.alloc(sizeof(uint32_t) * probe_slots, &matches));
+      HYB_TRY(scratch.alloc(probe_slots, &partitions));
     }
-    HYB_TRY(device_alloc(context, sizeof(uint32_t) * histogram_entries, &histogram));
-    HYB_TRY(device_alloc(context, sizeof(uint64_t) * histogram_entries, &run_starts));
+    // sized for the tile kernels as well: a duplicate build key sends a span-path call back to them
+    HYB_TRY(scratch.alloc(sizeof(uint32_t) * size_t{partition_count} * probe_tiles, &histogram));
+    HYB_TRY(scratch.alloc(sizeof(uint64_t) * size_t{partition_count} * probe_tiles, &run_starts));
     params.probe = probe.source;
     params.build = build.source;
     params.table = table;
@@ -1313,7 +1694,7 @@ int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const h
     params.partition_mask = partition_count - 1;
     params.partition_count = partition_count;
     params.unique_build = 1;  // optimistic: a flag raised by the build kernel sends us to the position-list path below
-    params.fast = (mode == HYB_JOIN_INNER && direct) ? ((direct_shift == 0 && !wide) ? 1u : (probe.data_type == HYB_TYPE_INT64 ? 2u : 0u)) : 0u;
+    params.fast = rank ? 0u : fast;  // the tile kernels' lean path knows the direct table only
     params.build_is_empty = build.positions == 0;
     params.flags = flags;
     params.matches = static_cast<uint32_t*>(matches);
@@ -1323,12 +1704,7 @@ int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const h
     params.overflow = flags + 2;
   }
 
-  const auto run_probe = [&](uint64_t capacity) -> int {
-    // count -> scan -> write, all queued without a host round trip; `capacity` output rows are pre-allocated
-    count_kernel<<<count_grid, kJoinThreads, 0, stream>>>(params);
-    HYB_CUDA(cudaGetLastError());
-    HYB_TRY(run_exclusive_scan(context, static_cast<uint32_t*>(histogram), static_cast<unsigned long long*>(run_starts),
-                               histogram_entries, total_slot));
+  const auto allocate_outputs = [&](uint64_t capacity) -> int {
     device_free(context, result->d_probe);
     device_free(context, result->d_build);
     result->d_probe = nullptr;
@@ -1336,13 +1712,25 @@ int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const h
     void* out_probe = nullptr;
     void* out_build = nullptr;
     HYB_TRY(device_alloc(context, sizeof(hyb_row_id) * std::max<uint64_t>(capacity, 1), &out_probe));
-    if (!semi_or_anti) HYB_TRY(device_alloc(context, sizeof(hyb_row_id) * std::max<uint64_t>(capacity, 1), &out_build));
     result->d_probe = static_cast<hyb_row_id*>(out_probe);
-    result->d_build = static_cast<hyb_row_id*>(out_build);
+    if (!semi_or_anti) {
+      HYB_TRY(device_alloc(context, sizeof(hyb_row_id) * std::max<uint64_t>(capacity, 1), &out_build));
+      result->d_build = static_cast<hyb_row_id*>(out_build);
+    }
     result->capacity = capacity;
     params.out_probe = result->d_probe;
     params.out_build = result->d_build;
     params.out_capacity = capacity;
+    return HYB_OK;
+  };
+
+  const auto run_probe = [&](uint64_t capacity) -> int {
+    // count -> scan -> write, all queued without a host round trip; `capacity` output rows are pre-allocated
+    count_kernel<<<count_grid, kJoinThreads, 0, stream>>>(params);
+    HYB_CUDA(cudaGetLastError());
+    HYB_TRY(run_exclusive_scan(context, static_cast<uint32_t*>(histogram), static_cast<unsigned long long*>(run_starts),
+                               histogram_entries, total_slot));
+    HYB_TRY(allocate_outputs(capacity));
     write_kernel<<<write_grid, kJoinThreads, 0, stream>>>(params);
     HYB_CUDA(cudaGetLastError());
     join_partition_offsets_kernel<<<(partition_count + 1 + 127) / 128, 128, 0, stream>>>(
@@ -1353,9 +1741,41 @@ int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const h
     return HYB_OK;
   };
 
+  const auto run_probe_spans = [&]() -> int {
+    ProbeParams span_params = params;
+    span_params.probe = span_source;
+    const uint32_t spans = span_source.tile_count;
+    const size_t stage_bytes = sizeof(uint2) * kSpanRows;
+    const auto count_spans = rank ? join_span_count_kernel<kTableRank> : join_span_count_kernel<kTableDirect>;
+    const auto write_spans =
+        rank ? (options.join_ballot_rank ? join_span_write_kernel<kTableRank, true> : join_span_write_kernel<kTableRank, false>)
+             : (options.join_ballot_rank ? join_span_write_kernel<kTableDirect, true> : join_span_write_kernel<kTableDirect, false>);
+    HYB_CUDA(cudaFuncSetAttribute(write_spans, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(stage_bytes)));
+    count_spans<<<spans, kSpanThreads, 0, stream>>>(span_params);
+    HYB_CUDA(cudaGetLastError());
+    HYB_TRY(run_exclusive_scan(context, static_cast<uint32_t*>(histogram), static_cast<unsigned long long*>(run_starts),
+                               histogram_entries, total_slot));
+    HYB_TRY(allocate_outputs(probe.positions));
+    span_params.out_probe = params.out_probe;
+    span_params.out_build = params.out_build;
+    span_params.out_capacity = params.out_capacity;
+    write_spans<<<spans, kSpanThreads, stage_bytes, stream>>>(span_params);
+    HYB_CUDA(cudaGetLastError());
+    join_partition_offsets_kernel<<<(partition_count + 1 + 127) / 128, 128, 0, stream>>>(
+        static_cast<const unsigned long long*>(run_starts), total_slot, partition_count, spans,
+        reinterpret_cast<unsigned long long*>(result->d_partition_offsets));
+    HYB_CUDA(cudaGetLastError());
+    launches += 4;
+    return HYB_OK;
+  };
+
   if (probe_tiles) {
     // With a unique build side every probe row emits at most one output row: probe.positions rows always suffice.
-    HYB_TRY(run_probe(probe.positions));
+    if (use_span) {
+      HYB_TRY(run_probe_spans());
+    } else {
+      HYB_TRY(run_probe(probe.positions));
+    }
   }
   timing_kernel_end(context);
   HYB_CUDA(cudaMemcpyAsync(host_control, control, sizeof(host_control), cudaMemcpyDeviceToHost, stream));
@@ -1363,11 +1783,13 @@ int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const h
   const bool has_duplicates = host_control[0] != 0;
 
   if (has_duplicates && !semi_or_anti && probe_tiles) {
-    // Duplicate build keys: build the position lists (PosHashTable::finalize, join_hash_steps.hpp:147-175) and probe again.
-    HYB_TRY(device_alloc(context, sizeof(uint32_t) * slot_count * 2, &dup_counts));  // counts | cursors
+    // Duplicate build keys: build the position lists (PosHashTable::finalize, join_hash_steps.hpp:147-175) and probe again
+    // (with the tile kernels: the span path is for unique build sides).
+    histogram_entries = size_t{partition_count} * probe_tiles;
+    HYB_TRY(scratch.alloc(sizeof(uint32_t) * slot_count * 2, &dup_counts));  // counts | cursors
     HYB_CUDA(cudaMemsetAsync(dup_counts, 0, sizeof(uint32_t) * slot_count * 2, stream));
-    HYB_TRY(device_alloc(context, sizeof(uint64_t) * slot_count, &dup_offsets));
-    HYB_TRY(device_alloc(context, sizeof(uint32_t) * std::max<uint64_t>(build.positions, 1), &dup_positions));
+    HYB_TRY(scratch.alloc(sizeof(uint64_t) * slot_count, &dup_offsets));
+    HYB_TRY(scratch.alloc(sizeof(uint32_t) * std::max<uint64_t>(build.positions, 1), &dup_positions));
     timing_kernel_begin(context);
     join_count_duplicates_kernel<<<build_grid, kJoinThreads, 0, stream>>>(build.source, table, static_cast<uint32_t*>(dup_counts));
     HYB_CUDA(cudaGetLastError());
@@ -1400,16 +1822,6 @@ int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const h
     HYB_CUDA(cudaStreamSynchronize(stream));
   }
 
-  device_free(context, matches);
-  device_free(context, partitions);
-  device_free(context, histogram);
-  device_free(context, run_starts);
-  device_free(context, slots);
-  device_free(context, wide_keys);
-  device_free(context, dup_counts);
-  device_free(context, dup_offsets);
-  device_free(context, dup_positions);
-
   // Compulsory traffic: each key once + each output RowID once.
   const auto key_bytes = [](const SideInfo& side) -> uint64_t {
     if (side.filter) return side.positions * (sizeof(hyb_row_id) + data_type_size(side.data_type));
@@ -1427,7 +1839,6 @@ int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const h
   };
   timing_end(context, launches, key_bytes(build) + key_bytes(probe), probe.positions, 0);
   timing_output_count(context, result->d_partition_offsets + partition_count, semi_or_anti ? 8 : 16);
-  device_free(context, control);
 
   const auto handle = context->next_handle++;
   context->join_results.emplace(handle, std::move(result));

@@ -215,6 +215,10 @@ class DeviceContext:
     def synchronize(self) -> None:
         check(self.lib.hyb_context_synchronize(self.ptr))
 
+    def set_option(self, name: str, value: str) -> None:
+        """hyb_context_set_option: tuning / test knobs (the HYB_* environment variables are read at context creation)."""
+        check(self.lib.hyb_context_set_option(self.ptr, name.encode(), str(value).encode()))
+
     # device column pool ------------------------------------------------------------------------------------------
     def upload(self, table) -> DeviceTable:
         """`table`: storage.Table or tpch.GeneratedTable (anything with view() / column_definitions)."""

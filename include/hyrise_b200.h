@@ -202,6 +202,17 @@ int hyb_device_count(int* out_count);
 /* Block until all work queued by this context has finished. */
 int hyb_context_synchronize(hyb_context* context);
 
+/* Tuning / test knobs (not needed for correctness). The HYB_* environment variables of the same meaning are read once,
+ * when the context is created; this call changes a knob afterwards. name/value pairs:
+ *   "join_table"       = "auto" | "hash" | "direct" | "rank"   hash-table kind of hyb_join_hash (parity tests force each)
+ *   "join_span"        = "0" | "1"   8192-row span kernels with shared-memory staged, coalesced PosList stores
+ *   "join_rank"        = "ballot" | "match"
+ *   "scan_bulk"        = "0" | "1"   cp.async.bulk + mbarrier input pipeline of the scan kernel
+ *   "aggregate_stream" = "0" | "1"   bulk-staged streaming kernel for low-cardinality group-bys
+ *   "aggregate_split"  = "0" | "1"   split a dictionary that exceeds shared memory over a CTA pair
+ * Unknown names / values return HYB_ERR_INVALID. */
+int hyb_context_set_option(hyb_context* context, const char* name, const char* value);
+
 /* Pinned host memory for upload sources / result destinations (a pinned MemoryResource in the reference's terms,
  * cf. src/lib/memory/default_memory_resource.cpp:29-35). */
 int hyb_host_alloc(size_t bytes, void** out_ptr);

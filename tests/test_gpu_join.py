@@ -12,15 +12,25 @@ pytestmark = pytest.mark.gpu
 
 
 
-@pytest.fixture(autouse=True, params=["auto", "hash", "direct"])
-def join_table_kind(request, monkeypatch):
-    """Every case runs with the library's own choice, with the open-addressing table forced and with the direct-address
-    table forced (HYB_JOIN_TABLE, read per call by hyb_join_hash): all three must reproduce the reference order."""
-    if request.param == "auto":
-        monkeypatch.delenv("HYB_JOIN_TABLE", raising=False)
-    else:
-        monkeypatch.setenv("HYB_JOIN_TABLE", request.param)
-    return request.param
+# Every case runs with the library's own choice (rank table + span kernels where they apply), with the open-addressing
+# table forced, with the direct-address table forced (span kernels, then the 4096-row tile kernels) and with MATCH.ANY
+# ranking instead of ballots (hyb_context_set_option): all must reproduce the reference order. The oracle result is
+# computed once per case.
+TABLE_KINDS = {"auto": ("auto", "1", "ballot"), "hash": ("hash", "1", "ballot"), "direct": ("direct", "1", "ballot"),
+               "direct-tiles": ("direct", "0", "ballot"), "rank-match": ("rank", "1", "match")}
+
+
+def select_table_kind(device, kind):
+    table, span, rank = TABLE_KINDS[kind]
+    device.set_option("join_table", table)
+    device.set_option("join_span", span)
+    device.set_option("join_rank", rank)
+
+
+@pytest.fixture(autouse=True)
+def restore_table_kind(device):
+    yield
+    select_table_kind(device, "auto")
 
 
 MODES = [capi.JOIN_INNER, capi.JOIN_LEFT, capi.JOIN_SEMI, capi.JOIN_ANTI_NULL_AS_TRUE, capi.JOIN_ANTI_NULL_AS_FALSE]
@@ -32,21 +42,24 @@ def check_join(device, build, build_dev, build_column, probe, probe_dev, probe_c
     expected = orc.join_hash(build, build_column, probe, probe_column, mode, radix_bits,
                              build_filter=build_filter[1] if build_filter else None,
                              probe_filter=probe_filter[1] if probe_filter else None)
-    result = device.join_hash(build_dev, build_column, probe_dev, probe_column, mode, radix_bits,
-                              build_filter=build_filter[0] if build_filter else None,
-                              probe_filter=probe_filter[0] if probe_filter else None)
-    try:
-        pairs, partitions, bits = result.info()
-        context = (mode, radix_bits, build_column, probe_column)
-        assert pairs == expected.pair_count, context
-        assert bits == expected.radix_bits, context
-        assert np.array_equal(result.partition_offsets(), expected.partition_offsets), context
-        got_build, got_probe = result.to_host()
-        assert row_ids_equal(got_probe, expected.probe), context
-        if expected.build is not None:
-            assert row_ids_equal(got_build, expected.build), context
-    finally:
-        result.free()
+    for kind in TABLE_KINDS:
+        select_table_kind(device, kind)
+        result = device.join_hash(build_dev, build_column, probe_dev, probe_column, mode, radix_bits,
+                                  build_filter=build_filter[0] if build_filter else None,
+                                  probe_filter=probe_filter[0] if probe_filter else None)
+        try:
+            pairs, partitions, bits = result.info()
+            context = (kind, mode, radix_bits, build_column, probe_column)
+            assert pairs == expected.pair_count, context
+            assert bits == expected.radix_bits, context
+            assert np.array_equal(result.partition_offsets(), expected.partition_offsets), context
+            got_build, got_probe = result.to_host()
+            assert row_ids_equal(got_probe, expected.probe), context
+            if expected.build is not None:
+                assert row_ids_equal(got_build, expected.build), context
+        finally:
+            result.free()
+    select_table_kind(device, "auto")
     return expected
 
 
@@ -278,3 +291,30 @@ def test_partition_push_addressing(device, partition_count):
                 assert np.all(got[:1000] == -7) and np.all(got[1000 + count:] == -7), (column, p)
                 assert np.array_equal(got[1000:1000 + count], want[offsets[p]:offsets[p + 1]].cpu().numpy()), (column, p)
     device_table.drop()
+
+
+@pytest.mark.parametrize("probe_encoding", ["Unencoded", "FrameOfReference"])
+@pytest.mark.parametrize("key_step", [1, 3, 200])
+def test_sorted_unique_build_span_path(device, probe_encoding, key_step):
+    """The PK-FK shape the span kernels and the rank table are built for: a strictly increasing build key column, probe
+    keys with hits and misses, FoR offsets of 1 / 2 / 4 bytes (key_step widens the blocks' value range), partial spans at
+    chunk ends, every radix width, plus a build side behind an (order-preserving) scan."""
+    rng = np.random.default_rng(77 + key_step)
+    build_keys = (1_000 + key_step * np.arange(30_000) + (np.arange(30_000) // 8) * 24 * key_step).astype(np.int32)
+    probe_keys = np.sort(rng.integers(900, int(build_keys[-1]) + 200, 70_000)).astype(np.int32)
+    if key_step == 3:
+        probe_keys = rng.permutation(probe_keys)  # unsorted probe side: ranks must still follow probe order
+    build = Table.from_columns([ColumnDefinition("k", capi.TYPE_INT32)], [build_keys], chunk_size=7_000).encode("Unencoded")
+    probe = Table.from_columns([ColumnDefinition("k", capi.TYPE_INT32)], [probe_keys], chunk_size=20_000).encode(probe_encoding)
+    build_dev, probe_dev = device.upload(build), device.upload(probe)
+    for radix_bits in (0, 1, 5, 8):
+        expected = check_join(device, build, build_dev, 0, probe, probe_dev, 0, capi.JOIN_INNER, radix_bits)
+        assert 0 < expected.pair_count < len(probe_keys)
+    check_join(device, build, build_dev, 0, probe, probe_dev, 0, capi.JOIN_SEMI, 4)
+    check_join(device, build, build_dev, 0, probe, probe_dev, 0, capi.JOIN_LEFT, 4)
+    predicate = Predicate(0, capi.PRED_GREATER_THAN, int(build_keys[9_000]))
+    build_filter = (device.table_scan(build_dev, predicate), orc.table_scan(build, predicate))
+    check_join(device, build, build_dev, 0, probe, probe_dev, 0, capi.JOIN_INNER, 3, build_filter=build_filter)
+    build_filter[0].free()
+    build_dev.drop()
+    probe_dev.drop()
