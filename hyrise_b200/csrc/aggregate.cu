@@ -25,6 +25,7 @@
 #include <limits>
 #include <numeric>
 
+#include "bulk_copy.cuh"
 #include "device_utils.cuh"
 #include "internal.hpp"
 #include "predicate.cuh"
@@ -1131,6 +1132,12 @@ __global__ void __launch_bounds__(kFastThreads, kMinBlocks) aggregate_fast_kerne
   }
 }
 
+}  // namespace hyb
+
+#include "aggregate_stream.cuh"
+
+namespace hyb {
+
 using FastKernel = void (*)(const FastPlan*);
 
 // Resident CTAs per SM the register allocation is capped for: 3 (170 registers) measured best for Q1 — 2 leaves too few
@@ -1238,6 +1245,7 @@ struct Factor {
   uint32_t column;
   int32_t kind;
   double literal;
+  int32_t literal_type = HYB_TYPE_INT32;
   bool operator==(const Factor& other) const {
     return column == other.column && kind == other.kind && (kind == kIdentity || literal == other.literal);
   }
@@ -1270,7 +1278,7 @@ static bool parse_product_chain(const hyb_aggregate_def& def, std::vector<Factor
     if (node.op == HYB_EXPR_COLUMN) {
       Item item;
       item.what = Item::kFactor;
-      item.factors.push_back(Factor{node.column_id, kIdentity, 0.0});
+      item.factors.push_back(Factor{node.column_id, kIdentity, 0.0, HYB_TYPE_INT32});
       stack.push_back(item);
     } else if (node.op == HYB_EXPR_LITERAL) {
       Item item;
@@ -1289,10 +1297,10 @@ static bool parse_product_chain(const hyb_aggregate_def& def, std::vector<Factor
         const bool plus = node.op == HYB_EXPR_ADD;
         if (a.what == Item::kLiteral && b.what == Item::kFactor && b.factors[0].kind == kIdentity) {
           result.what = Item::kFactor;
-          result.factors.push_back(Factor{b.factors[0].column, plus ? kLiteralPlusColumn : kLiteralMinusColumn, a.literal});
+          result.factors.push_back(Factor{b.factors[0].column, plus ? kLiteralPlusColumn : kLiteralMinusColumn, a.literal, a.literal_type});
         } else if (b.what == Item::kLiteral && a.what == Item::kFactor && a.factors[0].kind == kIdentity) {
           result.what = Item::kFactor;
-          result.factors.push_back(Factor{a.factors[0].column, plus ? kColumnPlusLiteral : kColumnMinusLiteral, b.literal});
+          result.factors.push_back(Factor{a.factors[0].column, plus ? kColumnPlusLiteral : kColumnMinusLiteral, b.literal, b.literal_type});
         } else {
           return false;
         }
@@ -1400,10 +1408,113 @@ static FastPlanHost plan_fast_path(const Table* table, const hyb_aggregate_query
     // int32 and int64 columns must not be mixed inside one FrameOfReference / value decode path: they are not (checked
     // per segment at decode time through data_type), nothing to do.
   }
-  // literals must be representable in the working type exactly as the reference converts them (int literal -> float)
+  // The fast kernels evaluate `literal (+|-) column` in the columns' type. The reference promotes per operation with
+  // std::common_type (expression_utils.cpp:172-205): a double literal next to a float column makes the factor — and every
+  // product after it — double, which only the general kernel's interpreter reproduces. Integer literals keep the
+  // column type (float o int -> float).
+  if (type == HYB_TYPE_FLOAT32) {
+    for (const auto& factor : plan.columns) {
+      if (factor.kind != kIdentity && factor.literal_type == HYB_TYPE_FLOAT64) return plan;
+    }
+  }
   plan.work_type = type == HYB_TYPE_FLOAT32 ? 0 : type == HYB_TYPE_FLOAT64 ? 1 : 2;
   plan.possible = true;
   return plan;
+}
+
+// ---- streaming kernel: host-side eligibility + shared-memory layout ----------------------------------------------------
+struct StreamLayout {
+  bool possible = false;
+  StreamPlan plan{};        // everything but plan.fast
+  size_t dynamic_bytes = 0;
+};
+
+template <int W>
+static void* stream_kernel_for(int groups, int columns) {
+  if (groups == 1) {
+    return columns == 1   ? reinterpret_cast<void*>(aggregate_stream_kernel<W, 1, 1>)
+           : columns == 2 ? reinterpret_cast<void*>(aggregate_stream_kernel<W, 1, 2>)
+                          : reinterpret_cast<void*>(aggregate_stream_kernel<W, 1, 4>);
+  }
+  return columns == 1   ? reinterpret_cast<void*>(aggregate_stream_kernel<W, 4, 1>)
+         : columns == 2 ? reinterpret_cast<void*>(aggregate_stream_kernel<W, 4, 2>)
+                        : reinterpret_cast<void*>(aggregate_stream_kernel<W, 4, 4>);
+}
+
+static StreamLayout stream_layout_for(const Table* table, const hyb_aggregate_query* query, const FastPlanHost& fast) {
+  StreamLayout layout;
+  if (fast.work_type == 2 || table->row_count() >= 0xFFFFFFF0ull) return layout;
+  const uint32_t chunk_count = table->chunk_count();
+  std::vector<uint32_t> staged;  // distinct referenced columns
+  const auto slot_of = [&](uint32_t column) -> uint32_t {
+    for (size_t i = 0; i < staged.size(); ++i) {
+      if (staged[i] == column) return static_cast<uint32_t>(i);
+    }
+    staged.push_back(column);
+    return static_cast<uint32_t>(staged.size() - 1);
+  };
+  StreamPlan& plan = layout.plan;
+  for (uint32_t p = 0; p < query->predicate_count; ++p) plan.predicate_slot[p] = slot_of(query->predicates[p].column_id);
+  for (uint32_t g = 0; g < query->groupby_count; ++g) plan.group_slot[g] = slot_of(query->groupby_column_ids[g]);
+  for (size_t c = 0; c < fast.columns.size(); ++c) plan.value_slot[c] = slot_of(fast.columns[c].column);
+  if (staged.size() > kStreamMaxColumns) return layout;
+
+  const size_t value_size = fast.work_type == 0 ? sizeof(float) : sizeof(double);
+  std::vector<uint32_t> max_width(staged.size(), 0);
+  for (uint32_t chunk = 0; chunk < chunk_count; ++chunk) {
+    const DevSegment* segments = &table->segments[size_t{chunk} * table->column_count];
+    for (size_t i = 0; i < staged.size(); ++i) {
+      const DevSegment& segment = segments[staged[i]];
+      uint32_t width = 0;
+      if (segment.encoding == HYB_ENC_UNENCODED) {
+        width = static_cast<uint32_t>(data_type_size(segment.data_type));
+      } else {
+        width = segment.vector_type == HYB_VEC_FIXED_1B ? 1u : segment.vector_type == HYB_VEC_FIXED_2B ? 2u
+                : segment.vector_type == HYB_VEC_FIXED_4B ? 4u : 0u;
+      }
+      if (width == 0 || width > 4 || segment.nulls || (segment.pad & kSegmentMayContainNulls)) return layout;
+      max_width[i] = std::max(max_width[i], width);
+    }
+    uint64_t combos = 1;
+    for (uint32_t g = 0; g < query->groupby_count; ++g) {
+      const DevSegment& segment = segments[query->groupby_column_ids[g]];
+      if (segment.encoding != HYB_ENC_DICTIONARY || segment.vector_type != HYB_VEC_FIXED_1B || segment.dict_size == 0) return layout;
+      if (!segment.dict_codes && segment.data_type == HYB_TYPE_STRING) return layout;
+      combos *= segment.dict_size;
+    }
+    if (combos > kMaxCombos) return layout;
+    for (const auto& factor : fast.columns) {
+      const DevSegment& segment = segments[factor.column];
+      const bool right_type = segment.data_type == (fast.work_type == 0 ? HYB_TYPE_FLOAT32 : HYB_TYPE_FLOAT64);
+      if (!right_type) return layout;
+      if (segment.encoding == HYB_ENC_FRAME_OF_REFERENCE) return layout;
+      if (segment.encoding == HYB_ENC_UNENCODED && fast.work_type != 0) return layout;
+    }
+  }
+  // stage = column slices | small dictionaries of the value columns | key data of the group-by dictionaries | header
+  uint32_t offset = 0;
+  plan.column_count = static_cast<uint32_t>(staged.size());
+  for (size_t i = 0; i < staged.size(); ++i) {
+    plan.columns[i].segments = table->d_segments + size_t{staged[i]} * chunk_count;
+    plan.columns[i].slot_offset = offset;
+    offset += kStreamTileRows * max_width[i];
+  }
+  for (size_t c = 0; c < fast.columns.size(); ++c) {
+    plan.dictionary_offset[c] = offset;
+    offset += static_cast<uint32_t>(kStagedDictionary * value_size);
+  }
+  for (uint32_t g = 0; g < query->groupby_count; ++g) {
+    plan.group_words_offset[g] = offset;
+    offset += kMaxCombos * 8 + 16;
+  }
+  offset = (offset + 127u) & ~127u;
+  plan.info_offset = offset;
+  offset += (static_cast<uint32_t>(sizeof(StreamStageInfo)) + 127u) & ~127u;
+  plan.stage_bytes = offset;
+  layout.dynamic_bytes = size_t{kStreamStages} * plan.stage_bytes;
+  if (layout.dynamic_bytes > 200 * 1024) return layout;
+  layout.possible = true;
+  return layout;
 }
 
 static hyb_row_id position_to_row_id_host(const Table* table, uint64_t position) {
@@ -1538,24 +1649,40 @@ int hyb_aggregate_hash(hyb_context* context, const hyb_aggregate_query* query, h
   const FastPlanHost fast = plan_fast_path(table, query);
   if (fast.possible && chunk_count > 0) {
     const int column_template = fast.columns.size() <= 1 ? 1 : fast.columns.size() <= 2 ? 2 : 4;
-    const int group_template = query->groupby_count == 0 ? 1 : 8;  // try 4 first when there are group-by columns
-    std::vector<int> attempts;
+    // Attempts in order: the TMA-staged streaming kernel when the layout allows it (<= 4 groups), then the register-tile
+    // kernel with 4 and 8 group slots; a kernel that meets more groups than it has slots raises `overflow`.
+    struct Attempt {
+      bool stream;
+      int groups;
+    };
+    std::vector<Attempt> attempts;
+    StreamLayout stream_layout;
+    if (context->options.aggregate_stream) stream_layout = stream_layout_for(table, query, fast);
+    if (stream_layout.possible) attempts.push_back({true, query->groupby_count == 0 ? 1 : 4});
     if (query->groupby_count == 0) {
-      attempts = {1};
+      attempts.push_back({false, 1});
     } else {
-      attempts = {4, 8};
+      attempts.push_back({false, 4});
+      attempts.push_back({false, 8});
     }
-    (void)group_template;
-    const uint2* tile_map = nullptr;
-    uint32_t tile_count = 0;
-    HYB_TRY(get_tile_map(context, table, kAggTileRows, &tile_map, &tile_count));
-    for (const int G : attempts) {
+    for (const Attempt attempt : attempts) {
+      const uint2* tile_map = nullptr;
+      uint32_t tile_count = 0;
+      HYB_TRY(get_tile_map(context, table, attempt.stream ? kStreamTileRows : kAggTileRows, &tile_map, &tile_count));
+      const int G = attempt.groups;
       const int C = column_template;
       const FastKernel kernel = fast_kernel(fast.work_type, G, C);
-      int blocks_per_sm = 1;
-      HYB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kFastThreads, 0));
-      // one wave of resident CTAs: the static tile striding must not queue CTAs behind each other
-      const uint32_t grid = std::max<uint32_t>(1, std::min<uint32_t>(tile_count, context->sm_count * std::max(blocks_per_sm, 1)));
+      uint32_t grid = 1;
+      if (attempt.stream) {
+        // one persistent CTA per SM (the stages take most of its shared memory), units strided over the CTAs
+        const uint32_t unit_count = (tile_count + kStreamUnitTiles - 1) / kStreamUnitTiles;
+        grid = std::max<uint32_t>(1, std::min<uint32_t>(unit_count, context->sm_count));
+      } else {
+        int blocks_per_sm = 1;
+        HYB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kFastThreads, 0));
+        // one wave of resident CTAs: the static tile striding must not queue CTAs behind each other
+        grid = std::max<uint32_t>(1, std::min<uint32_t>(tile_count, context->sm_count * std::max(blocks_per_sm, 1)));
+      }
       FastPlan host_plan{};
       host_plan.size_segments = table->d_segments;
       host_plan.tile_map = tile_map;
@@ -1607,10 +1734,22 @@ int hyb_aggregate_hash(hyb_context* context, const hyb_aggregate_query* query, h
       host_plan.overflow = reinterpret_cast<uint32_t*>(cursor);
       cursor += 1;
       auto* device_plan = reinterpret_cast<FastPlan*>(cursor);
+      if (attempt.stream) {
+        StreamPlan stream_plan = stream_layout.plan;
+        stream_plan.fast = host_plan;
+        void* stream_kernel = fast.work_type == 0 ? stream_kernel_for<0>(G, C) : stream_kernel_for<1>(G, C);
+        HYB_CUDA(cudaFuncSetAttribute(stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(stream_layout.dynamic_bytes)));
+        void* arguments[] = {&stream_plan};
+        timing_kernel_begin(context);
+        HYB_CUDA(cudaLaunchKernel(stream_kernel, dim3(grid), dim3(kStreamThreads), arguments, stream_layout.dynamic_bytes, stream));
+        timing_kernel_end(context);
+      } else {
       HYB_CUDA(cudaMemcpyAsync(device_plan, &host_plan, sizeof(FastPlan), cudaMemcpyHostToDevice, stream));
       timing_kernel_begin(context);
       kernel<<<grid, kFastThreads, 0, stream>>>(device_plan);
       timing_kernel_end(context);
+      }
       kernel_timed = true;
       HYB_CUDA(cudaGetLastError());
       ++launches;

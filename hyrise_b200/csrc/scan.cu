@@ -22,6 +22,7 @@
 #include <cmath>
 #include <limits>
 
+#include "bulk_copy.cuh"
 #include "device_utils.cuh"
 #include "internal.hpp"
 #include "predicate.cuh"
@@ -450,6 +451,254 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(const ScanParams par
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// scan_bulk_kernel: the same single-pass ordered compaction, restructured around the Blackwell asynchronous machinery.
+//
+//   producer warp   one lane claims tiles through the atomic ticket (so every predecessor of a claimed tile is owned by a
+//                   running CTA: the look-back cannot deadlock), reads the tile-map entry and the segment descriptor and
+//                   issues ONE cp.async.bulk per tile (the TMA unit moves the tile's 8192 codes, <= 32 KB, global ->
+//                   shared) that completes on the stage's `full` mbarrier; it runs kBulkStages - 1 tiles ahead of the
+//                   consumers and is throttled by the `empty` mbarriers. No load latency is left on the consumers' path.
+//   8 consumer warps  wait on `full`, evaluate their 1024 rows from shared memory (conflict-free 128-bit LDS), release
+//                   the stage, scan their match counts and publish the warp total. There is no CTA-wide barrier: the
+//                   warp that arrives LAST (shared-memory counter) owns the tile's decoupled look-back and publishes the
+//                   global offset through the `ready` mbarrier, while the other warps compact their matches into
+//                   warp-private staging; each warp then writes its own run of RowIDs (contiguous, 256 bytes per store).
+//
+// Eligible columns (checked on the host per call): every chunk streams a fixed-width vector of 1, 2 or 4 bytes per row
+// (dictionary value-IDs, FrameOfReference offsets, int32 / float values) and has no NULL vector; anything else takes
+// scan_kernel.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kBulkStages = 3;
+constexpr int kBulkConsumerWarps = kScanWarps;                   // 8 x 1024 rows = one 8192-row tile
+constexpr int kBulkThreads = (kBulkConsumerWarps + 1) * 32;      // + the producer warp
+constexpr uint32_t kBulkEndOfTiles = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t evaluate8_staged(const DevSegment& segment, const ChunkTest& test, uint32_t row0,
+                                                     const unsigned char* staged, uint32_t width) {
+  const uint32_t rows = segment.row_count;
+  const uint32_t valid = rows - row0 >= 8 ? 0xFFu : ((1u << (rows - row0)) - 1u);
+  uint32_t codes[8];
+  if (width == 2) {
+    const uint4 v = *reinterpret_cast<const uint4*>(staged);
+    codes[0] = v.x & 0xFFFFu;
+    codes[1] = v.x >> 16;
+    codes[2] = v.y & 0xFFFFu;
+    codes[3] = v.y >> 16;
+    codes[4] = v.z & 0xFFFFu;
+    codes[5] = v.z >> 16;
+    codes[6] = v.w & 0xFFFFu;
+    codes[7] = v.w >> 16;
+  } else if (width == 1) {
+    const uint2 v = *reinterpret_cast<const uint2*>(staged);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      codes[j] = (v.x >> (8 * j)) & 0xFFu;
+      codes[4 + j] = (v.y >> (8 * j)) & 0xFFu;
+    }
+  } else {
+    const uint4 a = *reinterpret_cast<const uint4*>(staged);
+    const uint4 b = *reinterpret_cast<const uint4*>(staged + 16);
+    codes[0] = a.x;
+    codes[1] = a.y;
+    codes[2] = a.z;
+    codes[3] = a.w;
+    codes[4] = b.x;
+    codes[5] = b.y;
+    codes[6] = b.z;
+    codes[7] = b.w;
+  }
+  uint32_t mask = 0;
+  switch (test.mode) {
+    case kTestIdRange:
+      if (!test.negate) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mask |= ((codes[j] - test.id_lo) < test.id_span) ? (1u << j) : 0u;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const bool inside = (codes[j] - test.id_lo) < test.id_span;
+          mask |= (!inside && codes[j] < segment.dict_size) ? (1u << j) : 0u;
+        }
+      }
+      break;
+    case kTestInt: {
+      uint32_t minimum = 0;
+      if (segment.encoding == HYB_ENC_FRAME_OF_REFERENCE) {
+        minimum = static_cast<uint32_t>(__ldg(static_cast<const int32_t*>(segment.values) + row0 / HYB_FOR_BLOCK_SIZE));
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const long long value = static_cast<int32_t>(minimum + codes[j]);
+        const bool inside = value >= test.int_lo && value <= test.int_hi;
+        mask |= (inside != static_cast<bool>(test.negate)) ? (1u << j) : 0u;
+      }
+      break;
+    }
+    case kTestFloat:
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const double value = __uint_as_float(codes[j]);
+        const bool above = test.float_lo_inclusive ? value >= test.float_lo : value > test.float_lo;
+        const bool below = test.float_hi_inclusive ? value <= test.float_hi : value < test.float_hi;
+        mask |= ((above && below) != static_cast<bool>(test.negate)) ? (1u << j) : 0u;
+      }
+      break;
+    case kTestNull:  // no NULL vector on this path: IS NOT NULL matches every row
+      mask = test.want_null ? 0u : 0xFFu;
+      break;
+    default:
+      break;
+  }
+  return mask & valid;
+}
+
+__global__ void __launch_bounds__(kBulkThreads) scan_bulk_kernel(const ScanParams params, const uint32_t stage_bytes) {
+  extern __shared__ __align__(128) unsigned char s_dynamic[];  // kBulkStages input stages, then the match staging
+  __shared__ __align__(8) unsigned long long s_full[kBulkStages], s_empty[kBulkStages], s_ready[2];
+  __shared__ uint4 s_info[kBulkStages];  // {tile, chunk, row0 | last-tile-of-chunk << 31, bytes per row}
+  __shared__ uint32_t s_totals[2][kBulkConsumerWarps];
+  __shared__ uint32_t s_arrived[2];
+  __shared__ unsigned long long s_base[2];
+
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int stage = 0; stage < kBulkStages; ++stage) {
+      mbarrier_init(&s_full[stage], 1);                    // the producer's arrive (+ the copy's bytes)
+      mbarrier_init(&s_empty[stage], kBulkConsumerWarps);  // one arrival per consumer warp
+    }
+    mbarrier_init(&s_ready[0], 1);
+    mbarrier_init(&s_ready[1], 1);
+    s_arrived[0] = 0;
+    s_arrived[1] = 0;
+    mbarrier_init_fence();
+  }
+  __syncthreads();  // the only CTA-wide barrier of the kernel
+
+  if (warp == kBulkConsumerWarps) {
+    // ---- producer -------------------------------------------------------------------------------------------------
+    if (lane != 0) return;
+    for (uint32_t fill = 0;; ++fill) {
+      const uint32_t stage = fill % kBulkStages;
+      mbarrier_wait(&s_empty[stage], ((fill / kBulkStages) & 1u) ^ 1u);  // passes at once for the first kBulkStages fills
+      const uint32_t tile = atomicAdd(params.ticket, 1u);
+      if (tile >= params.tile_count) {
+        s_info[stage] = make_uint4(kBulkEndOfTiles, 0u, 0u, 0u);
+        mbarrier_arrive(&s_full[stage]);
+        return;
+      }
+      const uint2 info = __ldg(params.tile_map + tile);
+      const DevSegment& segment = params.segments[info.x];
+      const uint32_t row0 = info.y & 0x7FFFFFFFu;
+      const char* base;
+      const uint32_t width = segment_stream(segment, base);
+      s_info[stage] = make_uint4(tile, info.x, info.y, width);
+      if (params.tests[info.x].mode != kTestNone) {
+        const uint32_t rows = min(static_cast<uint32_t>(kScanTileRows), segment.row_count - row0);
+        const uint32_t bytes = (rows * width + 15u) & ~15u;  // the readable tail pad covers the round-up
+        mbarrier_arrive_expect_tx(&s_full[stage], bytes);
+        bulk_copy_to_shared(s_dynamic + size_t{stage} * stage_bytes, base + size_t{row0} * width, bytes, &s_full[stage]);
+      } else {
+        mbarrier_arrive(&s_full[stage]);  // "no row can match": the chunk's bytes are never read
+      }
+    }
+  }
+
+  // ---- consumers ----------------------------------------------------------------------------------------------------
+  uint16_t* staging = reinterpret_cast<uint16_t*>(s_dynamic + size_t{kBulkStages} * stage_bytes) + warp * kScanWarpRows;
+  for (uint32_t iteration = 0;; ++iteration) {
+    const uint32_t stage = iteration % kBulkStages;
+    const uint32_t slot = iteration & 1u;
+    mbarrier_wait(&s_full[stage], (iteration / kBulkStages) & 1u);
+    const uint4 info = s_info[stage];
+    if (info.x == kBulkEndOfTiles) return;
+    const uint32_t tile = info.x, chunk = info.y, width = info.w;
+    const uint32_t tile_row0 = info.z & 0x7FFFFFFFu;
+    const bool last_tile_of_chunk = (info.z >> 31) != 0;
+    const DevSegment segment = params.segments[chunk];
+    const ChunkTest test = params.tests[chunk];
+    const unsigned char* staged = s_dynamic + size_t{stage} * stage_bytes;
+
+    // 1. predicate masks of this thread's kScanIterations x 8 rows, read from the staged tile
+    uint32_t masks[kScanIterations];
+    unsigned long long packed_counts = 0;  // iteration i's count in bits [16i, 16i+16)
+#pragma unroll
+    for (int it = 0; it < kScanIterations; ++it) {
+      const uint32_t relative = warp * kScanWarpRows + it * 256 + lane * 8;
+      const uint32_t row0 = tile_row0 + relative;
+      masks[it] = (test.mode != kTestNone && row0 < segment.row_count)
+                      ? evaluate8_staged(segment, test, row0, staged + size_t{relative} * width, width)
+                      : 0u;
+      packed_counts |= static_cast<unsigned long long>(__popc(masks[it])) << (16 * it);
+    }
+    __syncwarp();
+    if (lane == 0) mbarrier_arrive(&s_empty[stage]);  // the producer may refill the stage
+
+    // 2. warp scan of all iterations at once
+    unsigned long long inclusive = packed_counts;
+#pragma unroll
+    for (int delta = 1; delta < 32; delta <<= 1) {
+      const unsigned long long other = __shfl_up_sync(kFullMask, inclusive, delta);
+      if (lane >= static_cast<uint32_t>(delta)) inclusive += other;
+    }
+    const unsigned long long warp_sums = __shfl_sync(kFullMask, inclusive, 31);
+    const unsigned long long exclusive = inclusive - packed_counts;
+    uint32_t warp_total = 0;
+#pragma unroll
+    for (int it = 0; it < kScanIterations; ++it) warp_total += static_cast<uint32_t>((warp_sums >> (16 * it)) & 0xFFFFu);
+
+    // 3. publish the warp total; the last warp to arrive resolves the tile's global offset (decoupled look-back)
+    uint32_t arrived = 0;
+    if (lane == 0) {
+      s_totals[slot][warp] = warp_total;
+      __threadfence_block();
+      arrived = atomicAdd(&s_arrived[slot], 1u);
+    }
+    arrived = __shfl_sync(kFullMask, arrived, 0);
+    if (arrived == kBulkConsumerWarps - 1) {
+      __threadfence_block();
+      uint32_t tile_total = lane < kBulkConsumerWarps ? *reinterpret_cast<volatile uint32_t*>(&s_totals[slot][lane]) : 0u;
+#pragma unroll
+      for (int delta = 16; delta > 0; delta >>= 1) tile_total += __shfl_xor_sync(kFullMask, tile_total, delta);
+      const unsigned long long base = lookback_exclusive_prefix(params.tile_status, tile, tile_total, lane);
+      if (lane == 0) {
+        s_base[slot] = base;
+        if (last_tile_of_chunk) params.chunk_end[chunk] = base + tile_total;
+        if (tile + 1 == params.tile_count) params.chunk_end[params.chunk_count] = base + tile_total;
+        s_arrived[slot] = 0;  // next use: iteration + 2, after every warp has passed this tile's `ready`
+        mbarrier_arrive(&s_ready[slot]);
+      }
+    }
+
+    // 4. compact this warp's matches (tile-relative offsets, row order) into its private staging
+    {
+      uint32_t position = 0;
+#pragma unroll
+      for (int it = 0; it < kScanIterations; ++it) {
+        uint32_t at = position + static_cast<uint32_t>((exclusive >> (16 * it)) & 0xFFFFu);
+        const uint32_t relative = warp * kScanWarpRows + it * 256 + lane * 8;
+        const uint32_t mask = masks[it];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (mask & (1u << j)) staging[at++] = static_cast<uint16_t>(relative + j);
+        }
+        position += static_cast<uint32_t>((warp_sums >> (16 * it)) & 0xFFFFu);
+      }
+    }
+    __syncwarp();
+
+    // 5. this warp's run of RowIDs: contiguous in the output, 256 bytes per warp store
+    mbarrier_wait(&s_ready[slot], (iteration >> 1) & 1u);
+    unsigned long long at = s_base[slot];
+#pragma unroll
+    for (int w = 0; w < kBulkConsumerWarps; ++w) at += w < static_cast<int>(warp) ? s_totals[slot][w] : 0u;
+    hyb_row_id* out = params.out + at;
+    for (uint32_t i = lane; i < warp_total; i += 32) st_stream_v2(out + i, chunk, tile_row0 + staging[i]);
+    __syncwarp();  // staging is rewritten by the next tile
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Position-filtered scan (reference-table input whose pos lists reference a single chunk each — what a previous
 // TableScan on the same table produced; abstract_dereferenced_column_table_scan_impl.cpp:38-46 +
 // table_scan.cpp:150-197): gather the referenced rows, test, and emit the referenced RowIDs in input order.
@@ -682,15 +931,38 @@ int hyb_table_scan(hyb_context* context, hyb_table_t table_handle, const hyb_sca
       params.ticket = reinterpret_cast<uint32_t*>(static_cast<unsigned long long*>(status) + tile_count);
       params.out = result->d_row_ids;
       params.chunk_end = reinterpret_cast<unsigned long long*>(result->d_chunk_end);
-      {
-        const char* text = std::getenv("HYB_SCAN_PREFETCH");
-        params.prefetch = text ? static_cast<uint32_t>(std::atoi(text)) : 1;  // measured -8 % kernel time at SF 10
+      params.prefetch = 1;  // measured -8 % kernel time at SF 10
+      // Bulk (TMA-staged) path: every chunk streams a fixed-width vector of <= 4 bytes per row without a NULL vector.
+      uint32_t stream_width = 0;
+      bool bulk = context->options.scan_bulk;
+      for (uint32_t chunk = 0; chunk < chunk_count && bulk; ++chunk) {
+        const DevSegment& segment = table->segments[size_t{chunk} * table->column_count + predicate->column_id];
+        uint32_t width = 0;
+        if (segment.encoding == HYB_ENC_UNENCODED) {
+          width = static_cast<uint32_t>(data_type_size(segment.data_type));
+        } else {
+          width = segment.vector_type == HYB_VEC_FIXED_1B ? 1u : segment.vector_type == HYB_VEC_FIXED_2B ? 2u
+                  : segment.vector_type == HYB_VEC_FIXED_4B ? 4u : 0u;
+        }
+        if (width == 0 || width > 4 || segment.nulls) bulk = false;
+        stream_width = std::max(stream_width, width);
       }
-      int blocks_per_sm = 0;
-      HYB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, scan_kernel, kScanThreads, 0));
-      const uint32_t grid = std::min<uint32_t>(tile_count, context->sm_count * std::max(blocks_per_sm, 1));
       timing_kernel_begin(context);
-      scan_kernel<<<grid, kScanThreads, 0, context->stream>>>(params);
+      if (bulk) {
+        const uint32_t stage_bytes = kScanTileRows * stream_width;
+        const size_t dynamic_bytes = size_t{kBulkStages} * stage_bytes + sizeof(uint16_t) * kScanTileRows;
+        HYB_CUDA(cudaFuncSetAttribute(scan_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(dynamic_bytes)));
+        int blocks_per_sm = 0;
+        HYB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, scan_bulk_kernel, kBulkThreads, dynamic_bytes));
+        const uint32_t grid = std::min<uint32_t>(tile_count, context->sm_count * std::max(blocks_per_sm, 1));
+        scan_bulk_kernel<<<grid, kBulkThreads, dynamic_bytes, context->stream>>>(params, stage_bytes);
+      } else {
+        int blocks_per_sm = 0;
+        HYB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, scan_kernel, kScanThreads, 0));
+        const uint32_t grid = std::min<uint32_t>(tile_count, context->sm_count * std::max(blocks_per_sm, 1));
+        scan_kernel<<<grid, kScanThreads, 0, context->stream>>>(params);
+      }
       timing_kernel_end(context);
       HYB_CUDA(cudaGetLastError());
       device_free(context, status);
