@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """bench.py — the hot path of BASELINE.json on synthetic TPC-H-shaped tables.
 
-One *step* = one pass of the three operators over the resident lineitem / orders tables of scale factor --sf:
+One *step* = one pass of the three operators over the resident lineitem / orders tables of TPC-H scale factor --sf
+(default 100 = the configuration BASELINE.json's metric is quoted on; with N ranks every rank owns 1/N of it — strong
+scaling):
   1. TableScan   l_shipdate < '1995-01-01' on lineitem (DictionarySegment<string>, u16 value-IDs)  -> RowIDPosList
   2. JoinHash    orders (ValueSegment<int32>) x lineitem (FrameOfReference u16) on orderkey, Inner -> two PosLists
   3. AggregateHash  TPC-H Q1: l_shipdate <= '1998-09-02' fused, GROUP BY l_returnflag, l_linestatus, 4 SUM 3 AVG COUNT(*)
@@ -173,16 +175,125 @@ def ncu_traffic(kernels, sf, world):
     return total
 
 
+def verify_results(device, tables, lineitem, orders, outputs, distributed, rank, world) -> dict:
+    """Checks the timed operators' results on THIS rank's shard (outside the timed region):
+      scan    the match count against a numpy count over the host value-IDs (every row), a PosList sample bit-exact;
+      join    (1 GPU) pair count = lineitem rows (PK-FK), per-partition probe order, and on a sample of pairs the build
+              and probe keys decoded on the host are equal and fall into the pair's radix partition;
+      Q1      the CUDA aggregate of the first chunks against the CPU oracle on the same chunks (<= 1e-6 relative)."""
+    sys.path.insert(0, os.path.join(REPO, "tests"))
+    import ctypes as C
+
+    import oracle_lib as orc
+    from helpers import assert_aggregate_outputs_equal
+
+    report = {"ok": True, "checks": []}
+
+    def check(name, condition, detail=""):
+        report["checks"].append({"name": name, "ok": bool(condition), "detail": detail})
+        report["ok"] = report["ok"] and bool(condition)
+
+    host = tables.lineitem
+    # ---- scan: full count on the host (value-ID < per-chunk bound; u16 value-IDs)
+    bounds = host.string_value_id_bounds(SCAN_PREDICATE)
+    expected = 0
+    sample_chunk = min(3, host.chunk_count - 1)
+    sample_offsets = None
+    for chunk in range(host.chunk_count):
+        desc = host.segment_desc(chunk, L_SHIPDATE)
+        dtype = {capi.VEC_FIXED_1B: np.uint8, capi.VEC_FIXED_2B: np.uint16, capi.VEC_FIXED_4B: np.uint32}[desc.vector_type]
+        ids = np.ctypeslib.as_array(C.cast(desc.attribute_vector, C.POINTER(np.ctypeslib.as_ctypes_type(dtype))), shape=(desc.row_count,))
+        hits = ids < bounds[chunk, 0]
+        expected += int(hits.sum())
+        if chunk == sample_chunk:
+            sample_offsets = np.flatnonzero(hits).astype(np.uint32)
+    scan = device.table_scan(lineitem, SCAN_PREDICATE)
+    total, _ = scan.info()
+    check("scan count", total == expected, f"{total} vs {expected}")
+    offsets = scan.chunk_offsets()
+    begin, end = int(offsets[sample_chunk]), int(offsets[sample_chunk + 1])
+    got = np.empty(end - begin, dtype=ROW_ID_DTYPE)
+    capi.check(device.lib.hyb_pos_list_copy(device.ptr, scan.handle, begin, end - begin, got.ctypes.data))
+    check("scan PosList sample", len(got) == len(sample_offsets) and bool((got["chunk_id"] == sample_chunk).all())
+          and np.array_equal(got["chunk_offset"], sample_offsets), f"chunk {sample_chunk}: {len(got)} RowIDs")
+    scan.free()
+    check("timed scan count", distributed or int(outputs[0]) == expected, f"{outputs[0]}")
+
+    # ---- join (single GPU: the local join is the whole join)
+    if not distributed:
+        join = device.join_hash(orders, O_ORDERKEY, lineitem, L_ORDERKEY, capi.JOIN_INNER, -1)
+        pairs, partitions, bits = join.info()
+        check("join pair count", pairs == host.row_count == int(outputs[1]), f"{pairs} pairs, {host.row_count} lineitem rows")
+        part_offsets = join.partition_offsets().astype(np.int64)
+        rng = np.random.default_rng(7)
+        sample = 200_000
+        good = True
+        for partition in rng.choice(partitions, size=min(partitions, 6), replace=False):
+            begin, end = int(part_offsets[partition]), int(part_offsets[partition + 1])
+            count = min(sample, end - begin)
+            if count == 0:
+                continue
+            build_rows = np.empty(count, dtype=ROW_ID_DTYPE)
+            probe_rows = np.empty(count, dtype=ROW_ID_DTYPE)
+            capi.check(device.lib.hyb_join_result_copy(device.ptr, join.handle, begin, count, build_rows.ctypes.data,
+                                                       probe_rows.ctypes.data))
+            probe_position = probe_rows["chunk_id"].astype(np.int64) * capi.DEFAULT_CHUNK_SIZE + probe_rows["chunk_offset"]
+            good = good and bool((np.diff(probe_position) > 0).all())                    # probe order inside the partition
+            build_keys = host_keys(tables.orders, O_ORDERKEY, build_rows)
+            probe_keys = host_keys(host, L_ORDERKEY, probe_rows)
+            good = good and np.array_equal(build_keys, probe_keys)                        # the pair really joins
+            good = good and bool(((probe_keys & (partitions - 1)) == partition).all())    # and sits in its radix partition
+        check("join pairs sample (keys equal, radix partition, probe order)", good, f"radix_bits {bits}")
+        join.free()
+
+    # ---- Q1 on the first chunks against the oracle
+    chunks = min(host.chunk_count, 24)
+    sliced = SlicedTable(host, chunks)
+    device_slice = device.upload(sliced)
+    got = device.aggregate_hash(device_slice, Q1_GROUPBY, Q1_AGGREGATES, predicates=Q1_PREDICATES)
+    want = orc.aggregate_hash(sliced, Q1_GROUPBY, Q1_AGGREGATES, predicates=Q1_PREDICATES, threads=os.cpu_count() or 1)
+    try:
+        assert_aggregate_outputs_equal(got, want)
+        check("Q1 vs oracle on the first chunks", True, f"{chunks} chunks, {got.group_count} groups")
+    except AssertionError as error:
+        check("Q1 vs oracle on the first chunks", False, str(error)[:300])
+    device_slice.drop()
+    return report
+
+
+def host_keys(table, column_id: int, row_ids: np.ndarray) -> np.ndarray:
+    """int32 keys at the given RowIDs, decoded on the host from the generator's segments (ValueSegment / FoR)."""
+    import ctypes as C
+
+    keys = np.empty(len(row_ids), dtype=np.int64)
+    for chunk in np.unique(row_ids["chunk_id"]):
+        select = row_ids["chunk_id"] == chunk
+        offsets = row_ids["chunk_offset"][select].astype(np.int64)
+        desc = table.segment_desc(int(chunk), column_id)
+        if desc.encoding == capi.ENC_UNENCODED:
+            values = np.ctypeslib.as_array(C.cast(desc.values, C.POINTER(C.c_int32)), shape=(desc.row_count,))
+            keys[select] = values[offsets]
+        else:
+            dtype = {capi.VEC_FIXED_1B: C.c_uint8, capi.VEC_FIXED_2B: C.c_uint16, capi.VEC_FIXED_4B: C.c_uint32}[desc.vector_type]
+            codes = np.ctypeslib.as_array(C.cast(desc.attribute_vector, C.POINTER(dtype)), shape=(desc.row_count,))
+            blocks = (desc.row_count + capi.FOR_BLOCK_SIZE - 1) // capi.FOR_BLOCK_SIZE
+            minima = np.ctypeslib.as_array(C.cast(desc.values, C.POINTER(C.c_int32)), shape=(blocks,))
+            keys[select] = minima[offsets // capi.FOR_BLOCK_SIZE].astype(np.int64) + codes[offsets].astype(np.int64)
+    return keys
+
+
 def main() -> None:
     parser = argparse.ArgumentParser()
     parser.add_argument("--gpus", type=int, default=1)
     parser.add_argument("--steps", type=int, default=10)
     parser.add_argument("--warmup", type=int, default=3)
     parser.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    parser.add_argument("--sf", type=float, default=10.0, help="TPC-H scale factor per GPU")
-    parser.add_argument("--cpu-sample-chunks", type=int, default=92, help="lineitem chunks of the CPU sample (92 = SF 1)")
+    parser.add_argument("--sf", type=float, default=100.0, help="TPC-H scale factor of the WHOLE job (split over the ranks)")
+    parser.add_argument("--cpu-sample-chunks", type=int, default=184,
+                        help="lineitem chunks of the CPU arm's bounded sample (92 chunks = SF 1; default SF 2)")
     parser.add_argument("--no-cpu-baseline", action="store_true")
     parser.add_argument("--no-e2e", action="store_true")
+    parser.add_argument("--no-verify", action="store_true", help="skip the result self-check (outside the timed region)")
     args = parser.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -190,18 +301,24 @@ def main() -> None:
     world = int(os.environ.get("WORLD_SIZE", "1"))
     warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 0)
     metric = "TPC-H rows/sec scan+join+agg (TableScan l_shipdate + JoinHash orders x lineitem + Q1 AggregateHash)"
-    workload = f"tpch-sf{args.sf:g}-per-gpu scan(config 2)+join(config 3)+Q1 aggregate(config 4 query)"
+    workload = (f"tpch-sf{args.sf:g} TableScan l_shipdate<'1995-01-01' (config 2 query) + JoinHash orders x lineitem "
+                f"(config 3 query) + Q1 AggregateHash (config 4)")
+    # identical in both arms (the driver compares them); everything arm-specific lives under "detail" / "cpu_baseline"
+    config = {"workload": workload, "scale_factor": args.sf, "chunk_size": capi.DEFAULT_CHUNK_SIZE,
+              "tables": "seeded TPC-H-shaped lineitem / orders (dbgen distributions, Hyrise default encodings)"}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        tables = TpchTables(min(args.sf, 1.2), seed=42)  # only the sample is needed
+        # only the sample is generated: the same generator, seed and encodings, the first chunks of the same tables
+        sample_sf = min(args.sf, args.cpu_sample_chunks / 92.0 * 1.15 + 0.1)
+        tables = TpchTables(sample_sf, seed=42)
         result = cpu_arm(tables, args.cpu_sample_chunks, max(args.steps, 1), warmup)
         line = {
             "impl": "reference", "metric": metric, "value": result["value"], "unit": "rows/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": warmup, "ms_per_step": result["ms_per_step"], "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int32 keys / u16 value-IDs / f32->f64 sums", "data": "synthetic",
-            "config": {"workload": workload, "cpu_sample": result["sample"]},
+            "scaling": "strong", "vs_baseline": None, "dtype": "int32 keys / u16 value-IDs / f32 arithmetic, f64 sums",
+            "data": "synthetic", "config": config,
             "cpu_baseline": {"value": result["value"], "unit": "rows/s", "cores": result["cores"], "kind": "port",
                              "sample": result["sample"]},
             "e2e": {"value": result["value"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -222,10 +339,12 @@ def main() -> None:
         if distributed:
             dist.barrier()
 
-    # ---- data: every rank owns the shard [rank * orders, (rank + 1) * orders) of one global SF (sf x world) data set
-    #      (weak scaling: the per-GPU work is fixed; key ranges are disjoint, values depend on the global order index)
-    orders_per_rank = int(round(1_500_000 * args.sf))
-    tables = TpchTables(args.sf, seed=42, pinned=not args.no_e2e, first_order=rank * orders_per_rank)
+    # ---- data: every rank owns the shard [rank * orders, (rank + 1) * orders) of ONE global SF --sf data set (strong
+    #      scaling: the job is fixed, the per-GPU share shrinks; key ranges are disjoint, values depend on the global
+    #      order index)
+    sf_local = args.sf / world
+    orders_per_rank = int(round(1_500_000 * sf_local))
+    tables = TpchTables(sf_local, seed=42, pinned=not args.no_e2e, first_order=rank * orders_per_rank)
     device = DeviceContext(local_rank)
     lineitem = device.upload(tables.lineitem)
     orders = device.upload(tables.orders)
@@ -252,7 +371,7 @@ def main() -> None:
         lineitem_chunk_base = hd.chunk_bases(tables.lineitem.chunk_count, torch_device)[rank]
         orders_chunk_base = hd.chunk_bases(tables.orders.chunk_count, torch_device)[rank]
         lineitem_row_base = rank * 0  # positions only order groups; per-rank offsets keep them disjoint
-        radix_bits = 8 if args.sf * world >= 4 else 4
+        radix_bits = 8 if args.sf >= 4 else 4
         # Receive arenas for the fused split + NVLink P2P exchange; NCCL all-to-all of a local send buffer otherwise.
         peers = None
         if os.environ.get("HYB_EXCHANGE", "p2p") == "p2p":
@@ -425,14 +544,23 @@ def main() -> None:
                            "achieved_gbs": algorithmic / kernel_ms / 1e6, "frac": algorithmic / kernel_ms / 1e6 / peak,
                            "output_rows": int(samples[-1][3])}
     dominant = max(breakdown, key=lambda name: breakdown[name]["kernel_ms"])
-    kernels_of = {"scan": ["scan_kernel"],
-                  "join": ["join_build_kernel", "join_probe_count_kernel", "exclusive_scan_kernel", "join_probe_write_kernel"],
-                  "aggregate": ["aggregate_fast_kernel"]}
+    kernels_of = {"scan": ["scan_bulk_kernel"],
+                  "join": ["join_build_kernel", "join_span_count_kernel", "exclusive_scan_kernel", "join_span_write_kernel"],
+                  "aggregate": ["aggregate_stream_kernel"]}
     roofline = {"bound": "hbm", "kernel": " + ".join(kernels_of[dominant]), "achieved": breakdown[dominant]["achieved_gbs"],
                 "peak": peak, "peak_source": peak_source, "unit": "GB/s", "frac": breakdown[dominant]["frac"],
                 "traffic": ncu_traffic(kernels_of[dominant], args.sf, world),
                 "algorithmic_bytes_per_launch": breakdown[dominant]["algorithmic_bytes"],
                 "kernel_ms": breakdown[dominant]["kernel_ms"]}
+
+    # ---- self-check, outside the timed region: the numbers above are only worth something if the results are right ------
+    verification = None
+    if not args.no_verify:
+        verification = verify_results(device, tables, lineitem, orders, outputs, distributed, rank, world)
+        if distributed:
+            flags = [None] * world
+            dist.all_gather_object(flags, verification["ok"])
+            verification["all_ranks_ok"] = all(flags)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -443,25 +571,30 @@ def main() -> None:
     if rank == 0:
         line = {
             "metric": metric, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int32 keys / u16 value-IDs / f32 arithmetic, f64 sums", "data": "synthetic",
-            "config": {"workload": workload, "lineitem_rows_per_gpu": rows, "orders_rows_per_gpu": tables.orders.row_count,
-                       "chunk_size": capi.DEFAULT_CHUNK_SIZE, "l2": "256 MB memset before every operator, inside the timed region",
-                       "parallelism": (f"{world} ranks: chunk-partitioned scan (no collective); join = radix exchange of "
-                                       f"{{key, RowID}} tuples, one per side ("
+            "config": config,
+            "detail": {"lineitem_rows_per_gpu": rows, "orders_rows_per_gpu": tables.orders.row_count,
+                       "l2": "256 MB memset before every operator, inside the timed region; inputs exceed L2 anyway",
+                       "parallelism": (f"{world} ranks, each owning 1/{world} of the SF {args.sf:g} tables: chunk-partitioned "
+                                       f"scan (no collective); join = radix exchange of {{key, RowID}} tuples, one per side ("
                                        + ("split kernel storing straight into the owners' memory over NVLink P2P; collectives: "
                                           "count all-gather + barrier" if peers is not None else
                                           "device split + NCCL all-to-all") +
-                                       ") + local join; aggregate = local pre-aggregation + all-to-all of partial groups")
+                                       ") + local join; aggregate = local pre-aggregation + exchange of partial groups")
                        if world > 1 else "1 GPU",
                        "outputs_per_step": {"scan_matches": int(outputs[0]), "join_pairs": int(outputs[1]), "groups": int(outputs[2])}},
             "roofline": roofline, "operators": breakdown, "cpu_baseline": cpu_baseline, "e2e": e2e,
-            "gpu_launches": launches[0], "clocks": clocks.summary(),
+            "gpu_launches": launches[0], "clocks": clocks.summary(), "verify": verification,
         }
         print(json.dumps(line))
+    ok = verification is None or (verification["ok"] and verification.get("all_ranks_ok", True))
     device.close()
     if distributed:
         dist.destroy_process_group()
+    if not ok:
+        print(f"[bench] rank {rank}: result verification FAILED: {verification}", file=sys.stderr)
+        sys.exit(3)
 
 
 if __name__ == "__main__":

@@ -1444,6 +1444,8 @@ static void* stream_kernel_for(int groups, int columns) {
 static StreamLayout stream_layout_for(const Table* table, const hyb_aggregate_query* query, const FastPlanHost& fast) {
   StreamLayout layout;
   if (fast.work_type == 2 || table->row_count() >= 0xFFFFFFF0ull) return layout;
+  // a single int32 group-by column may take the immediate-key order, which needs the LAST row of every group
+  if (query->groupby_count == 1 && table->column_types[query->groupby_column_ids[0]] == HYB_TYPE_INT32) return layout;
   const uint32_t chunk_count = table->chunk_count();
   std::vector<uint32_t> staged;  // distinct referenced columns
   const auto slot_of = [&](uint32_t column) -> uint32_t {
@@ -1453,25 +1455,24 @@ static StreamLayout stream_layout_for(const Table* table, const hyb_aggregate_qu
     staged.push_back(column);
     return static_cast<uint32_t>(staged.size() - 1);
   };
-  StreamPlan& plan = layout.plan;
-  for (uint32_t p = 0; p < query->predicate_count; ++p) plan.predicate_slot[p] = slot_of(query->predicates[p].column_id);
-  for (uint32_t g = 0; g < query->groupby_count; ++g) plan.group_slot[g] = slot_of(query->groupby_column_ids[g]);
-  for (size_t c = 0; c < fast.columns.size(); ++c) plan.value_slot[c] = slot_of(fast.columns[c].column);
+  std::vector<uint32_t> predicate_slot(query->predicate_count), group_slot(query->groupby_count), value_slot(fast.columns.size());
+  for (uint32_t p = 0; p < query->predicate_count; ++p) predicate_slot[p] = slot_of(query->predicates[p].column_id);
+  for (uint32_t g = 0; g < query->groupby_count; ++g) group_slot[g] = slot_of(query->groupby_column_ids[g]);
+  for (size_t c = 0; c < fast.columns.size(); ++c) value_slot[c] = slot_of(fast.columns[c].column);
   if (staged.size() > kStreamMaxColumns) return layout;
 
+  const auto stream_width = [](const DevSegment& segment) -> uint32_t {
+    if (segment.encoding == HYB_ENC_UNENCODED) return static_cast<uint32_t>(data_type_size(segment.data_type));
+    return segment.vector_type == HYB_VEC_FIXED_1B ? 1u : segment.vector_type == HYB_VEC_FIXED_2B ? 2u
+           : segment.vector_type == HYB_VEC_FIXED_4B ? 4u : 0u;
+  };
   const size_t value_size = fast.work_type == 0 ? sizeof(float) : sizeof(double);
   std::vector<uint32_t> max_width(staged.size(), 0);
   for (uint32_t chunk = 0; chunk < chunk_count; ++chunk) {
     const DevSegment* segments = &table->segments[size_t{chunk} * table->column_count];
     for (size_t i = 0; i < staged.size(); ++i) {
       const DevSegment& segment = segments[staged[i]];
-      uint32_t width = 0;
-      if (segment.encoding == HYB_ENC_UNENCODED) {
-        width = static_cast<uint32_t>(data_type_size(segment.data_type));
-      } else {
-        width = segment.vector_type == HYB_VEC_FIXED_1B ? 1u : segment.vector_type == HYB_VEC_FIXED_2B ? 2u
-                : segment.vector_type == HYB_VEC_FIXED_4B ? 4u : 0u;
-      }
+      const uint32_t width = stream_width(segment);
       if (width == 0 || width > 4 || segment.nulls || (segment.pad & kSegmentMayContainNulls)) return layout;
       max_width[i] = std::max(max_width[i], width);
     }
@@ -1492,6 +1493,7 @@ static StreamLayout stream_layout_for(const Table* table, const hyb_aggregate_qu
     }
   }
   // stage = column slices | small dictionaries of the value columns | key data of the group-by dictionaries | header
+  StreamPlan& plan = layout.plan;
   uint32_t offset = 0;
   plan.column_count = static_cast<uint32_t>(staged.size());
   for (size_t i = 0; i < staged.size(); ++i) {
@@ -1499,7 +1501,28 @@ static StreamLayout stream_layout_for(const Table* table, const hyb_aggregate_qu
     plan.columns[i].slot_offset = offset;
     offset += kStreamTileRows * max_width[i];
   }
+  // launch constants: the common case, taken from the first chunk (tiles that deviate are flagged by the producer)
+  const DevSegment* first = &table->segments[0];
+  for (uint32_t p = 0; p < query->predicate_count; ++p) {
+    const DevSegment& segment = first[query->predicates[p].column_id];
+    const int32_t condition = query->predicates[p].condition;
+    const bool null_check = condition == HYB_PRED_IS_NULL || condition == HYB_PRED_IS_NOT_NULL;
+    plan.predicate_offset[p] = plan.columns[predicate_slot[p]].slot_offset;
+    plan.predicate_width[p] = stream_width(segment);
+    plan.predicate_encoding[p] = segment.encoding;
+    plan.predicate_mode[p] = segment.encoding == HYB_ENC_DICTIONARY ? kTestIdRange
+                             : null_check                            ? kTestNull
+                             : (segment.data_type == HYB_TYPE_FLOAT32 || segment.data_type == HYB_TYPE_FLOAT64) ? kTestFloat
+                                                                                                                 : kTestInt;
+  }
+  for (uint32_t g = 0; g < query->groupby_count; ++g) plan.group_offset[g] = plan.columns[group_slot[g]].slot_offset;
   for (size_t c = 0; c < fast.columns.size(); ++c) {
+    const DevSegment& segment = first[fast.columns[c].column];
+    plan.value_offset[c] = plan.columns[value_slot[c]].slot_offset;
+    plan.value_width[c] = stream_width(segment);
+    plan.value_kind[c] = segment.encoding != HYB_ENC_DICTIONARY       ? kValueBits
+                         : segment.dict_size <= kStagedDictionary ? kValueStagedDictionary
+                                                                  : kValueGlobalDictionary;
     plan.dictionary_offset[c] = offset;
     offset += static_cast<uint32_t>(kStagedDictionary * value_size);
   }

@@ -27,16 +27,13 @@ constexpr int kStreamConsumerWarps = 12;
 constexpr int kStreamConsumerThreads = kStreamConsumerWarps * 32;
 constexpr int kStreamThreads = kStreamConsumerThreads + 32;  // + the producer warp
 constexpr int kStreamRowsPerWarp = 256;
-constexpr int kStreamTileRows = kStreamConsumerWarps * kStreamRowsPerWarp;  // 4096
-constexpr int kStreamSteps = kStreamRowsPerWarp / 32;
+constexpr int kStreamTileRows = kStreamConsumerWarps * kStreamRowsPerWarp;  // 3072
+constexpr int kStreamLaneRows = 4;                                          // consecutive rows per lane and step
+constexpr int kStreamSteps = kStreamRowsPerWarp / (32 * kStreamLaneRows);   // 2
 constexpr int kStreamMaxColumns = 12;   // distinct staged columns (predicates + group-by + values)
 constexpr int kStreamUnitTiles = 4;
 constexpr uint32_t kStreamEnd = 0xFFFFFFFFu;
-
-struct StreamColumn {
-  const DevSegment* segments;  // descriptors of the column, one per chunk
-  uint32_t slot_offset;        // byte offset of the column's tile slice inside a stage
-};
+enum : uint32_t { kValueBits = 0, kValueStagedDictionary = 1, kValueGlobalDictionary = 2 };
 
 // Header of a stage: what the producer learned about the tile's chunk, handed to the consumers with the data.
 struct StreamStageInfo {
@@ -45,24 +42,39 @@ struct StreamStageInfo {
   uint32_t rows;   // valid rows of the tile (0: a predicate rules the whole chunk out, nothing was copied)
   uint32_t row0;   // first row of the tile inside its chunk
   uint32_t first_position;  // table position of the tile's first row
-  uint32_t pad;
-  uint32_t width[kStreamMaxColumns];       // bytes per row of a staged column in this chunk
-  uint32_t dict_size[kStreamMaxColumns];
-  const void* dictionary[kFastMaxColumns];       // value column: dictionary in global memory
-  uint32_t value_kind[kFastMaxColumns];          // 0 = unencoded value bits, 1 = dictionary in the stage, 2 = dictionary gathered from global
-  uint32_t group_entry_type[HYB_MAX_GROUPBY_COLUMNS];  // 0xFF = staged uint64 key words, else hyb_data_type of staged dictionary values
-  const int32_t* predicate_minima[HYB_MAX_FUSED_PREDICATES];  // FrameOfReference block minima
+  uint32_t regular;         // 1: widths / value kinds / test modes equal the launch constants of the plan
+  uint32_t predicate_width[HYB_MAX_FUSED_PREDICATES];
   uint32_t predicate_encoding[HYB_MAX_FUSED_PREDICATES];
+  const int32_t* predicate_minima[HYB_MAX_FUSED_PREDICATES];  // FrameOfReference block minima
   ChunkTest tests[HYB_MAX_FUSED_PREDICATES];
+  uint32_t group_dict_size[HYB_MAX_GROUPBY_COLUMNS];
+  uint32_t group_entry_type[HYB_MAX_GROUPBY_COLUMNS];  // 0xFF = staged uint64 key words, else hyb_data_type of staged dictionary values
+  uint32_t value_width[kFastMaxColumns];
+  uint32_t value_kind[kFastMaxColumns];
+  const void* dictionary[kFastMaxColumns];  // value column: dictionary in global memory
 };
 
+struct StreamColumn {
+  const DevSegment* segments;  // descriptors of the column, one per chunk
+  uint32_t slot_offset;        // byte offset of the column's tile slice inside a stage
+};
+
+// Passed as a kernel parameter: every field the row loop reads sits in the constant bank (uniform registers, uniform
+// branches). The launch constants describe the COMMON case (taken from the first chunk); a tile of a chunk that deviates —
+// another vector width because its dictionary is smaller, a dictionary that does not fit the stage — is flagged by the
+// producer and takes the same code with the values read from the stage header instead.
 struct StreamPlan {
   FastPlan fast;
   uint32_t column_count;
   StreamColumn columns[kStreamMaxColumns];
-  uint32_t predicate_slot[HYB_MAX_FUSED_PREDICATES];
-  uint32_t group_slot[HYB_MAX_GROUPBY_COLUMNS];
-  uint32_t value_slot[kFastMaxColumns];
+  uint32_t predicate_offset[HYB_MAX_FUSED_PREDICATES];   // stage offsets of the roles' column slices
+  uint32_t group_offset[HYB_MAX_GROUPBY_COLUMNS];
+  uint32_t value_offset[kFastMaxColumns];
+  uint32_t predicate_width[HYB_MAX_FUSED_PREDICATES];    // launch constants
+  uint32_t predicate_mode[HYB_MAX_FUSED_PREDICATES];
+  uint32_t predicate_encoding[HYB_MAX_FUSED_PREDICATES];
+  uint32_t value_width[kFastMaxColumns];
+  uint32_t value_kind[kFastMaxColumns];
   uint32_t dictionary_offset[kFastMaxColumns];           // stage offset of value column c's staged dictionary
   uint32_t group_words_offset[HYB_MAX_GROUPBY_COLUMNS];  // stage offset of group-by column q's per-entry key data
   uint32_t info_offset;
@@ -73,16 +85,33 @@ __device__ __forceinline__ void stream_consumer_barrier() {
   asm volatile("bar.sync 1, %0;" ::"n"(kStreamConsumerThreads) : "memory");
 }
 
-__device__ __forceinline__ uint32_t stream_code(const unsigned char* slot, uint32_t width, uint32_t local) {
-  if (width == 1) return slot[local];
-  if (width == 2) return reinterpret_cast<const uint16_t*>(slot)[local];
-  return reinterpret_cast<const uint32_t*>(slot)[local];
+// Entries local0 .. local0 + 3 (local0 % 4 == 0) of a staged vector of `width` bytes per entry: one 4 / 8 / 16-byte LDS.
+__device__ __forceinline__ void stream_codes4(const unsigned char* slot, uint32_t width, uint32_t local0, uint32_t (&codes)[4]) {
+  if (width == 1) {
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(slot + local0);
+    codes[0] = v & 0xFFu;
+    codes[1] = (v >> 8) & 0xFFu;
+    codes[2] = (v >> 16) & 0xFFu;
+    codes[3] = v >> 24;
+  } else if (width == 2) {
+    const uint2 v = *reinterpret_cast<const uint2*>(slot + size_t{local0} * 2);
+    codes[0] = v.x & 0xFFFFu;
+    codes[1] = v.x >> 16;
+    codes[2] = v.y & 0xFFFFu;
+    codes[3] = v.y >> 16;
+  } else {
+    const uint4 v = *reinterpret_cast<const uint4*>(slot + size_t{local0} * 4);
+    codes[0] = v.x;
+    codes[1] = v.y;
+    codes[2] = v.z;
+    codes[3] = v.w;
+  }
 }
 
 // One row against one predicate; `code` is the row's entry of the streamed vector. No NULLs on this path.
-__device__ __forceinline__ bool stream_test(const ChunkTest& test, uint32_t encoding, const int32_t* minima, uint32_t code,
-                                            uint32_t row) {
-  switch (test.mode) {
+__device__ __forceinline__ bool stream_test(uint32_t mode, const ChunkTest& test, uint32_t encoding, const int32_t* minima,
+                                            uint32_t code, uint32_t row) {
+  switch (mode) {
     case kTestIdRange: {
       const bool inside = (code - test.id_lo) < test.id_span;
       return inside != static_cast<bool>(test.negate);
@@ -128,10 +157,212 @@ __device__ __forceinline__ unsigned long long stream_key_entry(const unsigned ch
   }
 }
 
+// Per-thread aggregation state of a consumer (registers; static indexes only).
+template <int W, int G, int C>
+struct StreamState {
+  typename WorkType<W>::Accumulator raw_sum[G][C], product_sum[G][C];
+  uint32_t rows_seen[G];
+  uint32_t first_position[G];
+  uint32_t packed_rows;  // byte g = rows of group g since the last flush (< 256 by construction)
+  uint32_t seen_groups;  // bit g: this thread has recorded first_position[g]
+};
+
+// The rows of one warp in one tile. kRegular: vector widths, value kinds and test modes are the plan's launch constants.
+template <int W, int G, int C, bool kRegular>
+__device__ __forceinline__ void stream_warp_rows(const StreamPlan& plan, const StreamStageInfo* info, const unsigned char* stage_base,
+                                                 uint32_t warp, uint32_t lane, uint8_t* my_combos, unsigned long long* s_hash,
+                                                 unsigned long long (*s_keys)[kMaxKeyWords],
+                                                 const uint32_t (&combo_stride)[G == 1 ? 1 : HYB_MAX_GROUPBY_COLUMNS],
+                                                 const typename WorkType<W>::Value (&affine_a)[C],
+                                                 const typename WorkType<W>::Value (&affine_b)[C], StreamState<W, G, C>& state) {
+  using Value = typename WorkType<W>::Value;
+  using Accumulator = typename WorkType<W>::Accumulator;
+  const FastPlan& fast = plan.fast;
+  const uint32_t rows = info->rows;
+  const uint32_t groupby_count = fast.groupby_count;
+  const uint32_t predicate_count = fast.predicate_count;
+  const uint32_t need_raw_mask = fast.need_raw_mask, need_product_mask = fast.need_product_mask;
+#pragma unroll
+  for (int step = 0; step < kStreamSteps; ++step) {
+    const uint32_t local0 = warp * kStreamRowsPerWarp + step * (32 * kStreamLaneRows) + lane * kStreamLaneRows;
+    if (warp * kStreamRowsPerWarp + step * (32 * kStreamLaneRows) >= rows) break;  // uniform
+    const uint32_t valid = local0 >= rows ? 0u : (rows - local0 >= kStreamLaneRows ? 0xFu : ((1u << (rows - local0)) - 1u));
+    uint32_t pass = valid;
+    for (uint32_t p = 0; p < predicate_count; ++p) {
+      const uint32_t width = kRegular ? plan.predicate_width[p] : info->predicate_width[p];
+      const uint32_t mode = kRegular ? plan.predicate_mode[p] : info->tests[p].mode;
+      const uint32_t encoding = kRegular ? plan.predicate_encoding[p] : info->predicate_encoding[p];
+      uint32_t codes[kStreamLaneRows];
+      stream_codes4(stage_base + plan.predicate_offset[p], width, local0, codes);
+      uint32_t matches = 0;
+#pragma unroll
+      for (int j = 0; j < kStreamLaneRows; ++j) {
+        matches |= stream_test(mode, info->tests[p], encoding, info->predicate_minima[p], codes[j], info->row0 + local0 + j) ? (1u << j) : 0u;
+      }
+      pass &= matches;
+    }
+    if (!__any_sync(kFullMask, pass != 0)) continue;
+
+    // ---- group of every row (G == 1: the single group; else through the warp's combination table) -------------------
+    uint32_t group[kStreamLaneRows];
+    if constexpr (G == 1) {
+#pragma unroll
+      for (int j = 0; j < kStreamLaneRows; ++j) group[j] = ((pass >> j) & 1u) ? 0u : static_cast<uint32_t>(G);
+    } else {
+      uint32_t combination[kStreamLaneRows] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int q = 0; q < HYB_MAX_GROUPBY_COLUMNS; ++q) {
+        if (static_cast<uint32_t>(q) < groupby_count) {
+          uint32_t codes[kStreamLaneRows];
+          stream_codes4(stage_base + plan.group_offset[q], 1u, local0, codes);
+#pragma unroll
+          for (int j = 0; j < kStreamLaneRows; ++j) combination[j] += codes[j] * combo_stride[q];
+        }
+      }
+      bool unresolved = false;
+#pragma unroll
+      for (int j = 0; j < kStreamLaneRows; ++j) {
+        const bool row_passes = (pass >> j) & 1u;
+        combination[j] = row_passes ? combination[j] : 0u;  // rows past the tile's end carry stale codes
+        const uint32_t known = my_combos[combination[j]];
+        group[j] = row_passes ? known : static_cast<uint32_t>(G);
+        unresolved = unresolved || (row_passes && known >= kComboOverflow);
+      }
+      if (__any_sync(kFullMask, unresolved)) {
+        // first sighting of a combination in this warp and chunk (rare): resolve / insert into the CTA's group table
+#pragma unroll 1
+        for (int j = 0; j < kStreamLaneRows; ++j) {
+          uint32_t mine = j == 0 ? group[0] : j == 1 ? group[1] : j == 2 ? group[2] : group[3];
+          const uint32_t my_combination = j == 0 ? combination[0] : j == 1 ? combination[1] : j == 2 ? combination[2] : combination[3];
+          if (mine == kComboUnresolved) {
+            unsigned long long entries[kMaxKeyWords];
+            unsigned long long hash = 0x9E3779B97F4A7C15ull;
+            uint32_t rest = my_combination;
+            for (uint32_t q = 0; q < groupby_count; ++q) {
+              const uint32_t size = info->group_dict_size[q];
+              entries[q] = stream_key_entry(stage_base + plan.group_words_offset[q], info->group_entry_type[q], rest % size);
+              rest /= size;
+              hash = mix64(hash ^ entries[q]);
+            }
+            hash = mix64(hash) | 1ull;
+            int32_t found = -1;
+            for (int g = 0; g < G && found < 0; ++g) {
+              unsigned long long current = *reinterpret_cast<volatile unsigned long long*>(&s_hash[g]);
+              if (current == 0ull) {
+                current = atomicCAS(&s_hash[g], 0ull, hash);
+                if (current == 0ull) {
+                  for (uint32_t q = 0; q < groupby_count; ++q) s_keys[g][q] = entries[q];
+                  found = g;
+                }
+              }
+              if (current == hash) found = g;
+            }
+            if (found < 0) {
+              *fast.overflow = 1;  // more than G groups: the host falls back to a kernel with more group slots
+              my_combos[my_combination] = kComboOverflow;
+              mine = G;
+            } else {
+              my_combos[my_combination] = static_cast<uint8_t>(found);
+              mine = static_cast<uint32_t>(found);
+            }
+          } else if (mine == kComboOverflow) {
+            mine = G;
+          }
+          if (j == 0) group[0] = mine;
+          if (j == 1) group[1] = mine;
+          if (j == 2) group[2] = mine;
+          if (j == 3) group[3] = mine;
+        }
+      }
+    }
+
+    // ---- row counts (byte-packed, flushed by the caller) and the first position of every group ----------------------
+    {
+      uint32_t step_groups = 0;
+#pragma unroll
+      for (int j = 0; j < kStreamLaneRows; ++j) {
+        // group == G for rows that do not count: shifts of 32 and more yield 0 (shl.b32 clamps)
+        uint32_t increment, bit;
+        asm("shl.b32 %0, 1, %1;" : "=r"(increment) : "r"(group[j] * (G == 1 ? 32u : 8u)));
+        asm("shl.b32 %0, 1, %1;" : "=r"(bit) : "r"(group[j] + (group[j] >= static_cast<uint32_t>(G) ? 32u : 0u)));
+        state.packed_rows += increment;
+        step_groups |= bit;
+      }
+      if (step_groups & ~state.seen_groups) {  // rare after the first tiles: a lane meets a group for the first time
+#pragma unroll
+        for (int j = kStreamLaneRows - 1; j >= 0; --j) {
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            if (group[j] == static_cast<uint32_t>(g) && !((state.seen_groups >> g) & 1u)) {
+              state.first_position[g] = info->first_position + local0 + j;  // descending j: the smallest j wins
+            }
+          }
+        }
+        state.seen_groups |= step_groups;
+      }
+    }
+
+    // ---- value columns: raw sums and the running product ------------------------------------------------------------
+    Value product[kStreamLaneRows];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      if (fast.value_segments[c] == nullptr) continue;
+      const uint32_t width = kRegular ? plan.value_width[c] : info->value_width[c];
+      const uint32_t kind = kRegular ? plan.value_kind[c] : info->value_kind[c];
+      uint32_t codes[kStreamLaneRows];
+      stream_codes4(stage_base + plan.value_offset[c], width, local0, codes);
+      Value values[kStreamLaneRows];
+      if (kind == kValueStagedDictionary) {
+        const Value* dictionary = reinterpret_cast<const Value*>(stage_base + plan.dictionary_offset[c]);
+#pragma unroll
+        for (int j = 0; j < kStreamLaneRows; ++j) values[j] = dictionary[((valid >> j) & 1u) ? codes[j] : 0u];
+      } else if (kind == kValueGlobalDictionary) {
+        const void* dictionary = info->dictionary[c];
+#pragma unroll
+        for (int j = 0; j < kStreamLaneRows; ++j) values[j] = ((pass >> j) & 1u) ? typed_load<W>(dictionary, 0, codes[j]) : Value{};
+      } else {
+#pragma unroll
+        for (int j = 0; j < kStreamLaneRows; ++j) {
+          if constexpr (W == 0) {
+            values[j] = __uint_as_float(codes[j]);
+          } else {
+            values[j] = Value{};  // unencoded 8-byte values are not streamed (host eligibility)
+          }
+        }
+      }
+      const bool in_chain = (need_product_mask >> c) != 0;  // some product at or after this column
+      if (in_chain) {
+#pragma unroll
+        for (int j = 0; j < kStreamLaneRows; ++j) {
+          const Value factor = apply_affine<W>(affine_a[c], affine_b[c], values[j]);
+          product[j] = c == 0 ? factor : multiply<W>(product[j], factor);
+        }
+      }
+      if ((need_raw_mask >> c) & 1u) {
+#pragma unroll
+        for (int j = 0; j < kStreamLaneRows; ++j) {
+          const Accumulator widened = static_cast<Accumulator>(values[j]);
+#pragma unroll
+          for (int g = 0; g < G; ++g) add_where(state.raw_sum[g][c], widened, static_cast<int>(group[j]), g);
+        }
+      }
+      if ((need_product_mask >> c) & 1u) {
+#pragma unroll
+        for (int j = 0; j < kStreamLaneRows; ++j) {
+          const Accumulator widened = static_cast<Accumulator>(product[j]);
+#pragma unroll
+          for (int g = 0; g < G; ++g) add_where(state.product_sum[g][c], widened, static_cast<int>(group[j]), g);
+        }
+      }
+    }
+  }
+}
+
 template <int W, int G, int C>
 __global__ void __launch_bounds__(kStreamThreads, 1) aggregate_stream_kernel(const __grid_constant__ StreamPlan plan) {
   using Value = typename WorkType<W>::Value;
   using Accumulator = typename WorkType<W>::Accumulator;
+  static_assert(G == 1 || G == 4, "row counts are packed as one byte per group");
   const FastPlan& fast = plan.fast;  // kernel parameter: every plan field is a uniform constant-bank read
 
   extern __shared__ __align__(128) unsigned char s_stages[];  // kStreamStages x stage_bytes
@@ -152,7 +383,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) aggregate_stream_kernel(con
     mbarrier_init_fence();
   }
   if (threadIdx.x < G) {
-    s_hash[threadIdx.x] = 0;
+    s_hash[threadIdx.x] = G == 1 ? 1ull : 0ull;  // without group-by columns the single group always exists
     for (int w = 0; w < kMaxKeyWords; ++w) s_keys[threadIdx.x][w] = 0;
   }
   __syncthreads();
@@ -163,8 +394,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) aggregate_stream_kernel(con
 
   if (warp == kStreamConsumerWarps) {
     // ---- producer warp ----------------------------------------------------------------------------------------------
-    // Lane roles: [0, 12) one staged column each; [12, 16) small dictionary of value column lane - 12;
-    // [16, 24) key data of group-by column lane - 16; [24, 32) predicate lane - 24 (test + minima into the header).
+    // Lane roles: [0, 12) one staged column each; [12, 16) value column lane - 12 (header + small dictionary);
+    // [16, 24) group-by column lane - 16 (header + key data of its dictionary); [24, 32) predicate lane - 24 (header).
     uint32_t fill = 0;
     for (uint32_t unit = blockIdx.x; unit < unit_count; unit += gridDim.x) {
       for (uint32_t tile = unit * kStreamUnitTiles; tile < min(fast.tile_count, (unit + 1) * kStreamUnitTiles); ++tile, ++fill) {
@@ -181,13 +412,11 @@ __global__ void __launch_bounds__(kStreamThreads, 1) aggregate_stream_kernel(con
         const void* source = nullptr;
         void* destination = nullptr;
         uint32_t bytes = 0;
-        bool ruled_out = false;
+        bool ruled_out = false, regular = true;
         if (lane < plan.column_count) {
           const DevSegment& segment = plan.columns[lane].segments[chunk];
           const char* base;
           const uint32_t width = segment_stream(segment, base);
-          info->width[lane] = width;
-          info->dict_size[lane] = segment.dict_size;
           source = base + size_t{row0} * width;
           destination = stage_base + plan.columns[lane].slot_offset;
           bytes = (rows * width + 15u) & ~15u;
@@ -195,16 +424,20 @@ __global__ void __launch_bounds__(kStreamThreads, 1) aggregate_stream_kernel(con
           const int c = lane - 12;
           if (fast.value_segments[c] != nullptr) {
             const DevSegment& segment = fast.value_segments[c][chunk];
+            const char* base;
+            const uint32_t width = segment_stream(segment, base);
+            uint32_t kind = kValueBits;
+            if (segment.encoding == HYB_ENC_DICTIONARY) {
+              kind = segment.dict_size <= kStagedDictionary ? kValueStagedDictionary : kValueGlobalDictionary;
+            }
+            info->value_width[c] = width;
+            info->value_kind[c] = kind;
             info->dictionary[c] = segment.values;
-            if (segment.encoding != HYB_ENC_DICTIONARY) {
-              info->value_kind[c] = 0;
-            } else if (segment.dict_size <= kStagedDictionary) {
-              info->value_kind[c] = 1;
+            regular = width == plan.value_width[c] && kind == plan.value_kind[c];
+            if (kind == kValueStagedDictionary) {
               source = segment.values;
               destination = stage_base + plan.dictionary_offset[c];
               bytes = (segment.dict_size * static_cast<uint32_t>(sizeof(Value)) + 15u) & ~15u;
-            } else {
-              info->value_kind[c] = 2;
             }
           }
         } else if (lane >= 16 && lane < 16 + groupby_count) {
@@ -212,6 +445,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) aggregate_stream_kernel(con
           const DevSegment& segment = fast.group_segments[q][chunk];
           const uint32_t entry_bytes =
               (segment.dict_codes || segment.data_type == HYB_TYPE_INT64 || segment.data_type == HYB_TYPE_FLOAT64) ? 8u : 4u;
+          info->group_dict_size[q] = segment.dict_size;
           info->group_entry_type[q] = segment.dict_codes ? 0xFFu : segment.data_type;
           source = segment.dict_codes ? static_cast<const void*>(segment.dict_codes) : segment.values;
           destination = stage_base + plan.group_words_offset[q];
@@ -220,12 +454,18 @@ __global__ void __launch_bounds__(kStreamThreads, 1) aggregate_stream_kernel(con
           const int p = lane - 24;
           const ChunkTest test = fast.predicate_tests[p][chunk];
           const DevSegment& segment = fast.predicate_segments[p][chunk];
+          const char* base;
+          const uint32_t width = segment_stream(segment, base);
           info->tests[p] = test;
+          info->predicate_width[p] = width;
           info->predicate_minima[p] = static_cast<const int32_t*>(segment.values);
           info->predicate_encoding[p] = segment.encoding;
           ruled_out = test.mode == kTestNone;
+          regular = width == plan.predicate_width[p] && test.mode == plan.predicate_mode[p] &&
+                    segment.encoding == plan.predicate_encoding[p];
         }
         const bool skip = __any_sync(kFullMask, ruled_out);
+        const bool all_regular = __all_sync(kFullMask, regular);
         if (skip) bytes = 0;
         uint32_t total = bytes;
 #pragma unroll
@@ -236,6 +476,7 @@ __global__ void __launch_bounds__(kStreamThreads, 1) aggregate_stream_kernel(con
           info->rows = skip ? 0u : rows;
           info->row0 = row0;
           info->first_position = static_cast<uint32_t>(__ldg(fast.chunk_row_start + chunk)) + row0;
+          info->regular = all_regular ? 1u : 0u;
         }
         __syncwarp();  // header complete before the arrive publishes it
         if (lane == 0) {
@@ -259,19 +500,24 @@ __global__ void __launch_bounds__(kStreamThreads, 1) aggregate_stream_kernel(con
   }
 
   // ---- consumer warps ---------------------------------------------------------------------------------------------------
-  Accumulator raw_sum[G][C], product_sum[G][C];
-  uint32_t rows_seen[G], first_position[G], last_position[G];
+  StreamState<W, G, C> state;
+  state.packed_rows = 0;
+  state.seen_groups = 0;
 #pragma unroll
   for (int g = 0; g < G; ++g) {
-    rows_seen[g] = 0;
-    first_position[g] = 0xFFFFFFFFu;
-    last_position[g] = 0;
+    state.rows_seen[g] = 0;
+    state.first_position[g] = 0xFFFFFFFFu;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      raw_sum[g][c] = Accumulator{};
-      product_sum[g][c] = Accumulator{};
+      state.raw_sum[g][c] = Accumulator{};
+      state.product_sum[g][c] = Accumulator{};
     }
   }
+  const auto flush_row_counts = [&]() {
+#pragma unroll
+    for (int g = 0; g < G; ++g) state.rows_seen[g] += (state.packed_rows >> (8 * g)) & 0xFFu;
+    state.packed_rows = 0;
+  };
   Value affine_a[C], affine_b[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) {
@@ -282,12 +528,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) aggregate_stream_kernel(con
                                                                                                             : Value{};
     affine_b[c] = kind == kLiteralMinusColumn ? Value(-1) : Value(1);
   }
-  const uint32_t need_raw_mask = fast.need_raw_mask, need_product_mask = fast.need_product_mask;
   uint32_t combo_chunk = 0xFFFFFFFFu;   // chunk the warp's combination table was built for
-  uint32_t combo_stride[G == 1 ? 1 : HYB_MAX_GROUPBY_COLUMNS];
-  uint32_t combos = 0;
+  uint32_t combo_stride[G == 1 ? 1 : HYB_MAX_GROUPBY_COLUMNS] = {};
   uint8_t* my_combos = s_combo_group[G == 1 ? 0 : warp];
-  if (G == 1 && threadIdx.x == 0) s_hash[0] = 1;  // the single group always exists
 
   for (uint32_t iteration = 0;; ++iteration) {
     const uint32_t stage = iteration % kStreamStages;
@@ -295,28 +538,27 @@ __global__ void __launch_bounds__(kStreamThreads, 1) aggregate_stream_kernel(con
     const unsigned char* stage_base = s_stages + size_t{stage} * plan.stage_bytes;
     const auto* info = reinterpret_cast<const StreamStageInfo*>(stage_base + plan.info_offset);
     if (info->tile == kStreamEnd) break;
-    const uint32_t rows = info->rows;
-    if (rows != 0) {
+    if (info->rows != 0) {
       if constexpr (G > 1) {
         if (info->chunk != combo_chunk) {
           // New chunk, new dictionaries: rebuild this warp's value-ID combination -> group table from the staged key words
           // (lookup only: a combination that never occurs must not claim a group slot).
           combo_chunk = info->chunk;
-          combos = 1;
+          uint32_t combos = 1;
 #pragma unroll
           for (int q = 0; q < HYB_MAX_GROUPBY_COLUMNS; ++q) {
             combo_stride[q] = combos;
-            if (static_cast<uint32_t>(q) < groupby_count) combos *= info->dict_size[plan.group_slot[q]];
+            if (static_cast<uint32_t>(q) < groupby_count) combos *= info->group_dict_size[q];
           }
           __syncwarp();
           for (uint32_t combination = lane; combination < combos; combination += 32) {
             unsigned long long hash = 0x9E3779B97F4A7C15ull;
             uint32_t rest = combination;
             for (uint32_t q = 0; q < groupby_count; ++q) {
-              const uint32_t size = info->dict_size[plan.group_slot[q]];
-              const uint32_t value_id = rest % size;
+              const uint32_t size = info->group_dict_size[q];
+              const unsigned long long entry =
+                  stream_key_entry(stage_base + plan.group_words_offset[q], info->group_entry_type[q], rest % size);
               rest /= size;
-              const unsigned long long entry = stream_key_entry(stage_base + plan.group_words_offset[q], info->group_entry_type[q], value_id);
               hash = mix64(hash ^ entry);
             }
             hash = mix64(hash) | 1ull;
@@ -329,140 +571,29 @@ __global__ void __launch_bounds__(kStreamThreads, 1) aggregate_stream_kernel(con
           __syncwarp();
         }
       }
-      const uint32_t warp_row0 = warp * kStreamRowsPerWarp;
-#pragma unroll 1
-      for (int step = 0; step < kStreamSteps; ++step) {
-        const uint32_t local = warp_row0 + step * 32 + lane;
-        if (warp_row0 + step * 32 >= rows) break;  // uniform
-        const bool valid = local < rows;
-        bool pass = valid;
-        for (uint32_t p = 0; p < predicate_count; ++p) {
-          const uint32_t slot = plan.predicate_slot[p];
-          const uint32_t code = stream_code(stage_base + plan.columns[slot].slot_offset, info->width[slot], local);
-          pass = pass && stream_test(info->tests[p], info->predicate_encoding[p], info->predicate_minima[p], code,
-                                     info->row0 + local);
-        }
-        if (!__any_sync(kFullMask, pass)) continue;
-
-        // ---- group of the row ---------------------------------------------------------------------------------------
-        int32_t group = pass ? 0 : -1;
-        if constexpr (G > 1) {
-          uint32_t combination = 0;
-#pragma unroll
-          for (int q = 0; q < HYB_MAX_GROUPBY_COLUMNS; ++q) {
-            if (static_cast<uint32_t>(q) < groupby_count) {
-              const uint32_t slot = plan.group_slot[q];
-              combination += stage_base[plan.columns[slot].slot_offset + local] * combo_stride[q];
-            }
-          }
-          combination = valid ? combination : 0u;
-          group = pass ? static_cast<int32_t>(my_combos[combination]) : -1;
-          if (__any_sync(kFullMask, group >= static_cast<int32_t>(kComboOverflow))) {
-            // first sighting of a combination in this warp and chunk (rare): resolve / insert into the CTA's group table
-            if (group == kComboUnresolved) {
-              unsigned long long entries[kMaxKeyWords];
-              unsigned long long hash = 0x9E3779B97F4A7C15ull;
-              uint32_t rest = combination;
-              for (uint32_t q = 0; q < groupby_count; ++q) {
-                const uint32_t size = info->dict_size[plan.group_slot[q]];
-                entries[q] = stream_key_entry(stage_base + plan.group_words_offset[q], info->group_entry_type[q], rest % size);
-                rest /= size;
-                hash = mix64(hash ^ entries[q]);
-              }
-              hash = mix64(hash) | 1ull;
-              int32_t found = -1;
-              for (int g = 0; g < G && found < 0; ++g) {
-                unsigned long long current = *reinterpret_cast<volatile unsigned long long*>(&s_hash[g]);
-                if (current == 0ull) {
-                  current = atomicCAS(&s_hash[g], 0ull, hash);
-                  if (current == 0ull) {
-                    for (uint32_t q = 0; q < groupby_count; ++q) s_keys[g][q] = entries[q];
-                    found = g;
-                  }
-                }
-                if (current == hash) found = g;
-              }
-              if (found < 0) {
-                *fast.overflow = 1;  // more than G groups: the host falls back to a kernel with more group slots
-                my_combos[combination] = kComboOverflow;
-              } else {
-                my_combos[combination] = static_cast<uint8_t>(found);
-              }
-              group = found;
-            } else if (group == kComboOverflow) {
-              group = -1;
-            }
-          }
-        }
-
-        // ---- row count, first / last position per group ----------------------------------------------------------------
-        {
-          const uint32_t position = info->first_position + local;
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            if (group == g) {
-              ++rows_seen[g];
-              first_position[g] = min(first_position[g], position);
-              last_position[g] = position;
-            }
-          }
-        }
-
-        // ---- value columns: raw sums and the running product ------------------------------------------------------------
-        Value product = Value{};
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          if (fast.value_segments[c] == nullptr) continue;
-          const uint32_t slot = plan.value_slot[c];
-          uint32_t code = stream_code(stage_base + plan.columns[slot].slot_offset, info->width[slot], local);
-          code = valid ? code : 0u;
-          const uint32_t kind = info->value_kind[c];
-          Value value;
-          if (kind == 1) {
-            value = reinterpret_cast<const Value*>(stage_base + plan.dictionary_offset[c])[code];
-          } else if (kind == 2) {
-            value = pass ? typed_load<W>(info->dictionary[c], 0, code) : Value{};
-          } else {
-            if constexpr (W == 0) {
-              value = __uint_as_float(code);
-            } else {
-              value = Value{};  // unencoded 8-byte values are not streamed (host eligibility)
-            }
-          }
-          const bool in_chain = (need_product_mask >> c) != 0;  // some product at or after this column
-          if (in_chain) {
-            const Value factor = apply_affine<W>(affine_a[c], affine_b[c], value);
-            product = c == 0 ? factor : multiply<W>(product, factor);
-          }
-          if ((need_raw_mask >> c) & 1u) {
-            const Accumulator widened = static_cast<Accumulator>(value);
-#pragma unroll
-            for (int g = 0; g < G; ++g) add_where(raw_sum[g][c], widened, group, g);
-          }
-          if ((need_product_mask >> c) & 1u) {
-            const Accumulator widened = static_cast<Accumulator>(product);
-#pragma unroll
-            for (int g = 0; g < G; ++g) add_where(product_sum[g][c], widened, group, g);
-          }
-        }
+      if (info->regular) {
+        stream_warp_rows<W, G, C, true>(plan, info, stage_base, warp, lane, my_combos, s_hash, s_keys, combo_stride, affine_a,
+                                        affine_b, state);
+      } else {
+        stream_warp_rows<W, G, C, false>(plan, info, stage_base, warp, lane, my_combos, s_hash, s_keys, combo_stride, affine_a,
+                                         affine_b, state);
       }
+      if ((iteration & 15u) == 15u) flush_row_counts();  // <= 8 rows per lane and tile: the bytes stay below 256
     }
     __syncwarp();
     if (lane == 0) mbarrier_arrive(&s_empty[stage]);
   }
+  flush_row_counts();
 
   // ---- CTA reduction in a fixed order: lanes (butterfly), then warps; partials in the layout of aggregate_fast_kernel -------
   stream_consumer_barrier();
   const size_t cta = blockIdx.x;
 #pragma unroll
   for (int g = 0; g < G; ++g) {
-    const unsigned long long total_rows = warp_reduce_add(static_cast<unsigned long long>(rows_seen[g]));
-    uint32_t low = first_position[g], high = last_position[g];
+    const unsigned long long total_rows = warp_reduce_add(static_cast<unsigned long long>(state.rows_seen[g]));
+    uint32_t low = state.first_position[g];
 #pragma unroll
-    for (int delta = 16; delta > 0; delta >>= 1) {
-      low = min(low, __shfl_xor_sync(kFullMask, low, delta));
-      high = max(high, __shfl_xor_sync(kFullMask, high, delta));
-    }
+    for (int delta = 16; delta > 0; delta >>= 1) low = min(low, __shfl_xor_sync(kFullMask, low, delta));
     if (lane == 0) s_reduce_u64[warp] = total_rows;
     stream_consumer_barrier();
     if (threadIdx.x == 0) {
@@ -477,21 +608,14 @@ __global__ void __launch_bounds__(kStreamThreads, 1) aggregate_stream_kernel(con
       unsigned long long value = 0xFFFFFFFFull;
       for (int w = 0; w < kStreamConsumerWarps; ++w) value = min(value, s_reduce_u64[w]);
       fast.partial_min_position[cta * G + g] = value == 0xFFFFFFFFull ? ~0ull : value;
-    }
-    stream_consumer_barrier();
-    if (lane == 0) s_reduce_u64[warp] = high;
-    stream_consumer_barrier();
-    if (threadIdx.x == 0) {
-      unsigned long long value = 0;
-      for (int w = 0; w < kStreamConsumerWarps; ++w) value = max(value, s_reduce_u64[w]);
-      fast.partial_max_position[cta * G + g] = value;
+      fast.partial_max_position[cta * G + g] = 0;  // only the immediate-key order needs it; such queries are not streamed
     }
     stream_consumer_barrier();
 #pragma unroll
     for (int c = 0; c < C; ++c) {
 #pragma unroll
       for (int which = 0; which < 2; ++which) {
-        const Accumulator lane_sum = warp_reduce_add(which == 0 ? raw_sum[g][c] : product_sum[g][c]);
+        const Accumulator lane_sum = warp_reduce_add(which == 0 ? state.raw_sum[g][c] : state.product_sum[g][c]);
         if (lane == 0) s_reduce[warp] = lane_sum;
         stream_consumer_barrier();
         if (threadIdx.x == 0) {

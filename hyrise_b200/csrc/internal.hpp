@@ -189,7 +189,7 @@ struct ContextOptions {
   enum JoinTable : int { kAuto = 0, kHash, kDirect, kRank };
   int join_table = kAuto;      // HYB_JOIN_TABLE = hash | direct | rank
   bool join_span = true;       // HYB_JOIN_SPAN = 0: keep the 4096-row tile kernels for the Inner/unique fast path
-  bool join_ballot_rank = true;  // HYB_JOIN_RANK = match: rank with MATCH.ANY instead of one ballot per radix bit
+  bool join_ballot_rank = false;  // HYB_JOIN_RANK = ballot: one ballot per radix bit instead of MATCH.ANY (measured slower)
   bool scan_bulk = true;       // HYB_SCAN_BULK = 0: scan without the cp.async.bulk + mbarrier input pipeline
   bool aggregate_stream = true;  // HYB_AGG_STREAM = 0: keep the register-tile fast kernel for low-cardinality group-bys
   bool aggregate_split = true;   // HYB_AGG_SPLIT = 0: never split a big dictionary over a CTA pair

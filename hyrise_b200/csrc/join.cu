@@ -349,6 +349,53 @@ __global__ void __launch_bounds__(kJoinThreads) join_build_kernel(const BuildPar
   }
 }
 
+// Rank-table build. Keys arrive in rising order (that is what qualifies a build side for the rank table), so a warp's 32
+// consecutive rows fall into a handful of 32-key blocks: lanes of one run of equal block ids combine their presence bits
+// and smallest position with two warp reductions and the run's first lane issues ONE atomicOr + ONE atomicMax for all
+// of them (8 keys per block for dbgen's sparse order keys: 8x fewer atomics on the same 8 bytes). Runs are found by
+// comparing with the previous lane, so an input that is not sorted after all is still inserted correctly — just with more
+// atomics. All 16 key loads of a lane are in flight before the first use.
+__global__ void __launch_bounds__(kJoinThreads) join_build_rank_kernel(const BuildParams params) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned long long minimum = static_cast<unsigned long long>(params.table.direct_min);
+  for (uint32_t tile = blockIdx.x; tile < params.source.tile_count; tile += gridDim.x) {
+    const TileRef ref = tile_ref(params.source, tile);
+    const DevSegment segment = params.source.tile_map ? params.source.segments[ref.chunk] : DevSegment{};
+    constexpr int kSteps = kJoinRowsPerWarp / 32;
+    long long key[kSteps];
+    uint32_t usable = 0;
+#pragma unroll
+    for (int s = 0; s < kSteps; ++s) {
+      bool is_null = false;
+      key[s] = 0;
+      const bool valid = load_key1(params.source, ref, segment, warp * kJoinRowsPerWarp + s * 32 + lane, key[s], is_null);
+      if (valid && is_null) params.flags[1] = 1;
+      usable |= (valid && !is_null) ? (1u << s) : 0u;
+    }
+#pragma unroll
+    for (int s = 0; s < kSteps; ++s) {
+      const bool insert = (usable >> s) & 1u;
+      const unsigned long long offset = static_cast<unsigned long long>(key[s]) - minimum;
+      const uint32_t block = insert ? static_cast<uint32_t>(offset >> 5) : 0xFFFFFFFFu;
+      const uint32_t position = static_cast<uint32_t>(ref.first_position) + warp * kJoinRowsPerWarp + s * 32 + lane;
+      const uint32_t previous = __shfl_up_sync(kFullMask, block, 1);
+      const uint32_t heads = __ballot_sync(kFullMask, lane == 0 || block != previous);
+      // my run: from the last head at or below my lane to the lane before the next head
+      const uint32_t first = 31u - __clz(heads & (0xFFFFFFFFu >> (31u - lane)));
+      const uint32_t above = lane == 31 ? 0u : (heads >> (lane + 1));
+      const uint32_t last = above ? lane + __ffs(above) - 1 : 31u;
+      const uint32_t run = (0xFFFFFFFFu >> (31u - last)) & (0xFFFFFFFFu << first);
+      const uint32_t bits = __reduce_or_sync(run, insert ? (1u << (static_cast<uint32_t>(offset) & 31u)) : 0u);
+      const uint32_t smallest = __reduce_min_sync(run, insert ? position : 0xFFFFFFFFu);
+      if (lane == first && bits) {
+        uint2* entry = params.table.rank_blocks + block;
+        atomicOr(&entry->x, bits);
+        atomicMax(&entry->y, ~smallest);
+      }
+    }
+  }
+}
+
 // Smallest / largest non-NULL key of a column: out = {min, max, count of non-NULL rows, AND of keys, OR of keys, order
 // violations}. Decides direct-address mode; bits where AND == OR are the same in every key; zero violations (no NULL, every
 // key greater than the key one position earlier) means the column strictly increases in row order (rank mode).
@@ -976,51 +1023,68 @@ __global__ void __launch_bounds__(kJoinThreads, 3) join_probe_write_kernel(const
 //
 // What bounded the 4096-row tile kernels was not DRAM but the store path: every probe row wrote its two RowIDs with two
 // 8-byte stores into ~256-byte runs (a tile's 32 rows per partition), 32 different sectors per warp instruction. Here a
-// CTA owns 8192 consecutive probe rows, ranks them exactly as before (lane order = probe order), but scatters
-// {build position, row index | partition} into SHARED memory at the row's position inside the span's partition-ordered
-// output. The span's output then leaves in one flat loop: consecutive threads hold consecutive output rows of a run, so
-// every warp store is 256 contiguous bytes per PosList (runs average 8192 / partitions rows). The count pass uses the same
-// loader and only adds to a shared histogram. Loads are issued 8 steps at a time (keys, then table words, then use).
+// CTA owns 8192 consecutive probe rows and scatters {build position, row index | partition} into SHARED memory at the
+// row's position inside the span's partition-ordered output; the span's output then leaves in one flat loop in which
+// consecutive threads hold consecutive output rows of a run, so every warp store is 256 contiguous bytes per PosList.
+//
+//   join_span_count_kernel   matches per (span, 512-row warp chunk, partition) as uint16 + per (partition, span) totals.
+//                            The fine counts are what lets the write pass be a SINGLE sweep: a warp knows where its rows
+//                            of a partition start inside the staged span before it has ranked anything, so a row is
+//                            looked up, ranked (lane order = probe order) and scattered at once — no per-row state in
+//                            registers, no barrier between ranking and scattering.
+//   exclusive scan           over the (partition, span) totals: the run starts in the output.
+//   join_span_write_kernel   the sweep + the flat coalesced write-out.
+// All 16 key loads of a lane are issued before the first use; table lookups follow in groups of kSpanGroup.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kSpanThreads = 512;
 constexpr int kSpanWarps = kSpanThreads / 32;
 constexpr int kSpanRows = kSpanWarps * kJoinRowsPerWarp;  // 8192
-constexpr int kCountGroup = 8;  // probe steps whose loads are in flight together: count pass
-constexpr int kRankGroup = 4;   //   ranking pass (the ranked rows of all 16 steps stay in registers as well)
+constexpr int kSpanGroup = 4;                             // table lookups in flight together
 enum : int { kTableDirect = 0, kTableRank = 1 };
 
-// Keys and matches of kSpanGroup probe steps of one warp chunk: step s, lane l -> row row_base + 32 s.
-template <uint32_t kCodec, bool kFull, int kTable, int kSpanGroup>
-__device__ __forceinline__ void span_lookup(const ProbeParams& params, const DevSegment& segment, uint32_t row_base,
-                                            uint32_t for_minimum, uint32_t (&match)[kSpanGroup], uint32_t (&key_low)[kSpanGroup]) {
-  constexpr bool kWide = kCodec == kCodecPlain64;
-  static_assert(!(kWide && kTable == kTableRank), "rank tables are probed with int32 keys");
+struct SpanKeys {
+  uint32_t low[kProbeSteps];
+  uint32_t valid_mask;
+};
+
+// Keys of all 16 probe steps of a lane: step s, lane l -> row row_base + 32 s.
+template <uint32_t kCodec, bool kFull>
+__device__ __forceinline__ void span_load_keys(const DevSegment& segment, uint32_t row_base, uint32_t for_minimum, SpanKeys& keys,
+                                               uint32_t (&high)[kCodec == kCodecPlain64 ? kProbeSteps : 1]) {
   const uint32_t row_count = segment.row_count;
-  uint32_t key_high[kWide ? kSpanGroup : 1];
-  uint32_t valid_mask = 0;
+  keys.valid_mask = 0;
 #pragma unroll
-  for (int s = 0; s < kSpanGroup; ++s) {
+  for (int s = 0; s < kProbeSteps; ++s) {
     const uint32_t row = row_base + s * 32;
     const bool valid = kFull || row < row_count;
-    valid_mask |= valid ? (1u << s) : 0u;
-    key_low[s] = 0;
-    if constexpr (kWide) key_high[s] = 0;
+    keys.valid_mask |= valid ? (1u << s) : 0u;
+    keys.low[s] = 0;
+    if constexpr (kCodec == kCodecPlain64) high[s] = 0;
     if (valid) {
       if constexpr (kCodec == kCodecPlain32) {
-        key_low[s] = ld_stream_u32(static_cast<const uint32_t*>(segment.values) + row);
+        keys.low[s] = ld_stream_u32(static_cast<const uint32_t*>(segment.values) + row);
       } else if constexpr (kCodec == kCodecPlain64) {
         const uint2 bits = ld_stream_v2(static_cast<const long long*>(segment.values) + row);
-        key_low[s] = bits.x;
-        key_high[s] = bits.y;
+        keys.low[s] = bits.x;
+        high[s] = bits.y;
       } else if constexpr (kCodec == kCodecFor8) {
-        key_low[s] = for_minimum + __ldg(static_cast<const uint8_t*>(segment.av) + row);
+        keys.low[s] = for_minimum + __ldg(static_cast<const uint8_t*>(segment.av) + row);
       } else if constexpr (kCodec == kCodecFor16) {
-        key_low[s] = for_minimum + __ldg(static_cast<const uint16_t*>(segment.av) + row);
+        keys.low[s] = for_minimum + __ldg(static_cast<const uint16_t*>(segment.av) + row);
       } else {
-        key_low[s] = for_minimum + ld_stream_u32(static_cast<const uint32_t*>(segment.av) + row);
+        keys.low[s] = for_minimum + ld_stream_u32(static_cast<const uint32_t*>(segment.av) + row);
       }
     }
   }
+}
+
+// Matches (build position or kNoMatch) of steps first .. first + kSpanGroup - 1.
+template <uint32_t kCodec, int kTable>
+__device__ __forceinline__ void span_match(const ProbeParams& params, const SpanKeys& keys,
+                                           const uint32_t (&high)[kCodec == kCodecPlain64 ? kProbeSteps : 1], int first,
+                                           uint32_t (&match)[kSpanGroup]) {
+  constexpr bool kWide = kCodec == kCodecPlain64;
+  static_assert(!(kWide && kTable == kTableRank), "rank tables are probed with int32 keys");
   if constexpr (kTable == kTableRank) {
     const uint2* __restrict__ blocks = params.table.rank_blocks;
     const uint32_t minimum = static_cast<uint32_t>(params.table.direct_min);
@@ -1028,13 +1092,13 @@ __device__ __forceinline__ void span_lookup(const ProbeParams& params, const Dev
     uint2 block[kSpanGroup];
 #pragma unroll
     for (int s = 0; s < kSpanGroup; ++s) {
-      const uint32_t offset = key_low[s] - minimum;  // wraps above the range for keys below the minimum
+      const uint32_t offset = keys.low[first + s] - minimum;  // wraps above the range for keys below the minimum
       block[s] = make_uint2(0u, 0u);
-      if (((valid_mask >> s) & 1u) && offset < range) block[s] = __ldg(blocks + (offset >> 5));
+      if (((keys.valid_mask >> (first + s)) & 1u) && offset < range) block[s] = __ldg(blocks + (offset >> 5));
     }
 #pragma unroll
     for (int s = 0; s < kSpanGroup; ++s) {
-      const uint32_t bit = (key_low[s] - minimum) & 31u;
+      const uint32_t bit = (keys.low[first + s] - minimum) & 31u;
       match[s] = ((block[s].x >> bit) & 1u) ? rank_block_position(block[s], bit) : kNoMatch;
     }
   } else if constexpr (!kWide) {
@@ -1043,9 +1107,9 @@ __device__ __forceinline__ void span_lookup(const ProbeParams& params, const Dev
     const uint32_t range = static_cast<uint32_t>(params.table.direct_range);
 #pragma unroll
     for (int s = 0; s < kSpanGroup; ++s) {
-      const uint32_t index = key_low[s] - minimum;
+      const uint32_t index = keys.low[first + s] - minimum;
       match[s] = kNoMatch;
-      if (((valid_mask >> s) & 1u) && index < range) match[s] = __ldg(direct + index);
+      if (((keys.valid_mask >> (first + s)) & 1u) && index < range) match[s] = __ldg(direct + index);
     }
   } else {
     const uint32_t* __restrict__ direct = params.table.direct;
@@ -1055,10 +1119,10 @@ __device__ __forceinline__ void span_lookup(const ProbeParams& params, const Dev
     const unsigned long long low_bits = (1ull << shift) - 1ull;
 #pragma unroll
     for (int s = 0; s < kSpanGroup; ++s) {
-      const unsigned long long offset = ((static_cast<unsigned long long>(key_high[s]) << 32) | key_low[s]) - minimum;
+      const unsigned long long offset = ((static_cast<unsigned long long>(high[first + s]) << 32) | keys.low[first + s]) - minimum;
       const unsigned long long index = offset >> shift;
       match[s] = kNoMatch;
-      if (((valid_mask >> s) & 1u) && index < range && !(offset & low_bits)) match[s] = __ldg(direct + index);
+      if (((keys.valid_mask >> (first + s)) & 1u) && index < range && !(offset & low_bits)) match[s] = __ldg(direct + index);
     }
   }
 }
@@ -1069,8 +1133,8 @@ __device__ __forceinline__ uint32_t span_for_minimum(const DevSegment& segment, 
   return static_cast<uint32_t>(__ldg(static_cast<const int32_t*>(segment.values) + first_row / HYB_FOR_BLOCK_SIZE));
 }
 
-// Lanes of the warp whose row falls into the same radix partition. One ballot per radix bit (7 for config 3) keeps the
-// four schedulers of an SM busy in parallel; MATCH.ANY was measured at 16 cycles per warp instruction and SM.
+// Lanes of the warp whose row falls into the same radix partition: MATCH.ANY, or one ballot per radix bit (measured
+// slower on B200: 0.71 ms against 0.64 ms for config 3; kept selectable, option join_rank).
 template <bool kBallot>
 __device__ __forceinline__ uint32_t partition_peers(uint32_t partition, uint32_t radix_bits) {
   if constexpr (kBallot) {
@@ -1089,51 +1153,40 @@ __device__ __forceinline__ uint32_t partition_peers(uint32_t partition, uint32_t
   }
 }
 
-template <uint32_t kCodec, bool kFull, int kTable>
-__device__ __forceinline__ void span_count_rows(const ProbeParams& params, const TileRef& ref, const DevSegment& segment,
-                                                uint32_t warp, uint32_t lane, uint32_t* histogram) {
-  const uint32_t chunk0 = warp * kJoinRowsPerWarp;
-  const uint32_t for_minimum = span_for_minimum(segment, kCodec, ref.row0 + chunk0);
-#pragma unroll 1
-  for (int group = 0; group < kProbeSteps / kCountGroup; ++group) {
-    uint32_t match[kCountGroup], key_low[kCountGroup];
-    span_lookup<kCodec, kFull, kTable, kCountGroup>(params, segment, ref.row0 + chunk0 + group * kCountGroup * 32 + lane,
-                                                    for_minimum, match, key_low);
-#pragma unroll
-    for (int s = 0; s < kCountGroup; ++s) {
-      if (match[s] != kNoMatch) atomicAdd(histogram + (key_low[s] & params.partition_mask), 1u);
-    }
-  }
-}
-
-struct SpanRows {
-  uint32_t match[kProbeSteps];
-  uint32_t rank_partition[kProbeSteps];  // rank inside the (warp chunk, partition) run | partition << 16
-};
-
-template <uint32_t kCodec, bool kFull, int kTable, bool kBallot>
-__device__ __forceinline__ void span_rank_rows(const ProbeParams& params, const TileRef& ref, const DevSegment& segment,
-                                               uint32_t warp, uint32_t lane, uint32_t* warp_histogram, SpanRows& rows) {
+// One warp chunk (512 rows) of a span. kScatter == false: count matches per partition into `counters` (this warp's
+// histogram). kScatter == true: `counters[p]` holds the staged position of the chunk's next row of partition p; every
+// matching row is ranked in lane order and stored at once.
+template <uint32_t kCodec, bool kFull, int kTable, bool kScatter, bool kBallot>
+__device__ __forceinline__ void span_warp_chunk(const ProbeParams& params, const TileRef& ref, const DevSegment& segment,
+                                                uint32_t warp, uint32_t lane, uint32_t* counters, uint2* stage) {
   const uint32_t chunk0 = warp * kJoinRowsPerWarp;
   const uint32_t for_minimum = span_for_minimum(segment, kCodec, ref.row0 + chunk0);
   const uint32_t lanes_below = (1u << lane) - 1u;
   const uint32_t radix_bits = __popc(params.partition_mask);
+  SpanKeys keys;
+  uint32_t high[kCodec == kCodecPlain64 ? kProbeSteps : 1];
+  span_load_keys<kCodec, kFull>(segment, ref.row0 + chunk0 + lane, for_minimum, keys, high);
 #pragma unroll
-  for (int group = 0; group < kProbeSteps / kRankGroup; ++group) {
-    uint32_t match[kRankGroup], key_low[kRankGroup];
-    span_lookup<kCodec, kFull, kTable, kRankGroup>(params, segment, ref.row0 + chunk0 + group * kRankGroup * 32 + lane,
-                                                   for_minimum, match, key_low);
+  for (int group = 0; group < kProbeSteps / kSpanGroup; ++group) {
+    uint32_t match[kSpanGroup];
+    span_match<kCodec, kTable>(params, keys, high, group * kSpanGroup, match);
 #pragma unroll
-    for (int s = 0; s < kRankGroup; ++s) {
-      const uint32_t partition = key_low[s] & params.partition_mask;
-      const uint32_t peers = partition_peers<kBallot>(partition, radix_bits);
-      const uint32_t emitting = __ballot_sync(kFullMask, match[s] != kNoMatch) & peers;
-      const int leader = __ffs(peers) - 1;
-      uint32_t earlier = 0;
-      if (lane == static_cast<uint32_t>(leader) && emitting) earlier = atomicAdd(warp_histogram + partition, __popc(emitting));
-      earlier = __shfl_sync(kFullMask, earlier, leader);
-      rows.match[group * kRankGroup + s] = match[s];
-      rows.rank_partition[group * kRankGroup + s] = (earlier + __popc(emitting & lanes_below)) | (partition << 16);
+    for (int s = 0; s < kSpanGroup; ++s) {
+      const int step = group * kSpanGroup + s;
+      const uint32_t partition = keys.low[step] & params.partition_mask;
+      if constexpr (!kScatter) {
+        if (match[s] != kNoMatch) atomicAdd(counters + partition, 1u);  // counting needs no order
+      } else {
+        const uint32_t peers = partition_peers<kBallot>(partition, radix_bits);
+        const uint32_t emitting = __ballot_sync(kFullMask, match[s] != kNoMatch) & peers;
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (lane == static_cast<uint32_t>(leader) && emitting) base = atomicAdd(counters + partition, __popc(emitting));
+        base = __shfl_sync(kFullMask, base, leader);
+        if (match[s] != kNoMatch) {
+          stage[base + __popc(emitting & lanes_below)] = make_uint2(match[s], (chunk0 + step * 32 + lane) | (partition << 16));
+        }
+      }
     }
   }
 }
@@ -1178,61 +1231,65 @@ __device__ __forceinline__ void span_rank_rows(const ProbeParams& params, const 
     }                                                                              \
   } while (0)
 
-// Matches per (partition, span). params.probe is the span-granular source (tile map of kSpanRows-row tiles).
+// params.probe is the span-granular source (tile map of kSpanRows-row tiles). Dynamic shared memory (both kernels):
+// uint32 counters[kSpanWarps][partition_count] (the write kernel: behind its kSpanRows staged rows).
+// params.histogram[p * spans + span] = matches of partition p in the span; fine_counts[(span * kSpanWarps + w) *
+// partition_count + p] = those of warp chunk w.
 template <int kTable>
-__global__ void __launch_bounds__(kSpanThreads, 2) join_span_count_kernel(const ProbeParams params) {
-  __shared__ uint32_t s_histogram[kMaxPartitions];
+__global__ void __launch_bounds__(kSpanThreads, 2) join_span_count_kernel(const ProbeParams params, uint16_t* __restrict__ fine_counts) {
+  extern __shared__ uint32_t s_counters[];  // [kSpanWarps][partition_count]
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t span = blockIdx.x;
-  if (threadIdx.x < params.partition_count) s_histogram[threadIdx.x] = 0;
-  __syncthreads();
+  const uint32_t partition_count = params.partition_count;
+  uint32_t* mine = s_counters + warp * partition_count;
+  for (uint32_t p = lane; p < partition_count; p += 32) mine[p] = 0;
+  __syncwarp();
   const TileRef ref = tile_ref(params.probe, span);
   const DevSegment segment = params.probe.segments[ref.chunk];
   const uint32_t codec = tile_codec(params.probe, segment);
-#define HYB_SPAN_COUNT(CODEC, FULL) span_count_rows<CODEC, FULL, kTable>(params, ref, segment, warp, lane, s_histogram);
+#define HYB_SPAN_COUNT(CODEC, FULL) span_warp_chunk<CODEC, FULL, kTable, false, false>(params, ref, segment, warp, lane, mine, nullptr);
   HYB_SPAN_DISPATCH(HYB_SPAN_COUNT);
 #undef HYB_SPAN_COUNT
   __syncthreads();
-  if (threadIdx.x < params.partition_count) {
-    params.histogram[static_cast<size_t>(threadIdx.x) * params.probe.tile_count + span] = s_histogram[threadIdx.x];
+  uint16_t* out = fine_counts + static_cast<size_t>(span) * kSpanWarps * partition_count;
+  for (uint32_t i = threadIdx.x; i < kSpanWarps * partition_count; i += kSpanThreads) out[i] = static_cast<uint16_t>(s_counters[i]);
+  if (threadIdx.x < partition_count) {
+    uint32_t total = 0;
+#pragma unroll
+    for (int w = 0; w < kSpanWarps; ++w) total += s_counters[w * partition_count + threadIdx.x];
+    params.histogram[static_cast<size_t>(threadIdx.x) * params.probe.tile_count + span] = total;
   }
 }
 
 template <int kTable, bool kBallot>
-__global__ void __launch_bounds__(kSpanThreads, 2) join_span_write_kernel(const ProbeParams params) {
-  extern __shared__ uint2 s_stage[];  // kSpanRows x {build position, row index in the span | partition << 16}
-  __shared__ uint32_t s_warp_histogram[kSpanWarps][kMaxPartitions];  // counts, then exclusive prefixes over the warps
-  __shared__ uint32_t s_local_start[kMaxPartitions];                 // first staged row of a partition
-  __shared__ unsigned long long s_destination[kMaxPartitions];       // output index of staged row i of partition p = this + i
+__global__ void __launch_bounds__(kSpanThreads, 2) join_span_write_kernel(const ProbeParams params,
+                                                                          const uint16_t* __restrict__ fine_counts) {
+  extern __shared__ __align__(16) unsigned char s_dynamic[];
+  uint2* s_stage = reinterpret_cast<uint2*>(s_dynamic);  // kSpanRows x {build position, row index in the span | partition << 16}
+  uint32_t* s_position = reinterpret_cast<uint32_t*>(s_dynamic + sizeof(uint2) * kSpanRows);  // [kSpanWarps][partition_count]
+  __shared__ unsigned long long s_destination[kMaxPartitions];  // output index of staged row i of partition p = this + i
   __shared__ uint32_t s_scan[8];
   __shared__ uint32_t s_total;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t span = blockIdx.x;
   const uint32_t partition_count = params.partition_count;
-  for (uint32_t p = lane; p < partition_count; p += 32) s_warp_histogram[warp][p] = 0;
-  __syncwarp();
   const TileRef ref = tile_ref(params.probe, span);
   const DevSegment segment = params.probe.segments[ref.chunk];
   const uint32_t codec = tile_codec(params.probe, segment);
-  // this span's run starts (exclusive scan of the count pass), in flight while the rows are ranked
+
+  // ---- where every warp chunk's rows of every partition go inside the staged span (from the count pass) ----------------
+  uint32_t partition_total = 0;
   unsigned long long run_start = 0;
   if (threadIdx.x < partition_count) {
     run_start = __ldg(params.run_starts + static_cast<size_t>(threadIdx.x) * params.probe.tile_count + span);
-  }
-  SpanRows rows;
-#define HYB_SPAN_RANK(CODEC, FULL) \
-  span_rank_rows<CODEC, FULL, kTable, kBallot>(params, ref, segment, warp, lane, s_warp_histogram[warp], rows);
-  HYB_SPAN_DISPATCH(HYB_SPAN_RANK);
-#undef HYB_SPAN_RANK
-  __syncthreads();
-  // per partition: exclusive prefix over the warp chunks, then over the partitions
-  uint32_t partition_total = 0;
-  if (threadIdx.x < partition_count) {
+    const uint16_t* counts = fine_counts + static_cast<size_t>(span) * kSpanWarps * partition_count + threadIdx.x;
+    uint32_t count[kSpanWarps];
+#pragma unroll
+    for (int w = 0; w < kSpanWarps; ++w) count[w] = __ldg(counts + w * partition_count);
 #pragma unroll
     for (int w = 0; w < kSpanWarps; ++w) {
-      const uint32_t count = s_warp_histogram[w][threadIdx.x];
-      s_warp_histogram[w][threadIdx.x] = partition_total;
-      partition_total += count;
+      s_position[w * partition_count + threadIdx.x] = partition_total;  // relative to the partition's first staged row
+      partition_total += count[w];
     }
   }
   const uint32_t inclusive = warp_inclusive_scan(partition_total, lane);
@@ -1243,19 +1300,22 @@ __global__ void __launch_bounds__(kSpanThreads, 2) join_span_write_kernel(const 
 #pragma unroll
     for (int w = 0; w < 8; ++w) before += w < static_cast<int>(warp) ? s_scan[w] : 0u;
     const uint32_t exclusive = before + inclusive - partition_total;
-    s_local_start[threadIdx.x] = exclusive;
+#pragma unroll
+    for (int w = 0; w < kSpanWarps; ++w) s_position[w * partition_count + threadIdx.x] += exclusive;
     s_destination[threadIdx.x] = run_start - exclusive;  // modulo 2^64: run_start + (i - exclusive) for staged row i
     if (threadIdx.x + 1 == partition_count) s_total = exclusive + partition_total;
   }
   __syncthreads();
-#pragma unroll
-  for (int step = 0; step < kProbeSteps; ++step) {
-    if (rows.match[step] == kNoMatch) continue;
-    const uint32_t partition = rows.rank_partition[step] >> 16;
-    const uint32_t at = s_local_start[partition] + s_warp_histogram[warp][partition] + (rows.rank_partition[step] & 0xFFFFu);
-    s_stage[at] = make_uint2(rows.match[step], (warp * kJoinRowsPerWarp + step * 32 + lane) | (partition << 16));
-  }
+
+  // ---- one sweep: look up, rank, scatter --------------------------------------------------------------------------------
+  uint32_t* mine = s_position + warp * partition_count;
+#define HYB_SPAN_SCATTER(CODEC, FULL) \
+  span_warp_chunk<CODEC, FULL, kTable, true, kBallot>(params, ref, segment, warp, lane, mine, s_stage);
+  HYB_SPAN_DISPATCH(HYB_SPAN_SCATTER);
+#undef HYB_SPAN_SCATTER
   __syncthreads();
+
+  // ---- flat write-out: consecutive threads, consecutive output rows of a run ---------------------------------------------
   const uint32_t total = s_total;
   for (uint32_t i = threadIdx.x; i < total; i += kSpanThreads) {
     const uint2 staged = s_stage[i];
@@ -1615,7 +1675,11 @@ int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const h
     build_params.table = table;
     build_params.wide_keys_out = static_cast<long long*>(wide_keys);
     build_params.flags = flags;
-    join_build_kernel<<<build_grid, kJoinThreads, 0, stream>>>(build_params);
+    if (rank) {
+      join_build_rank_kernel<<<build_grid, kJoinThreads, 0, stream>>>(build_params);
+    } else {
+      join_build_kernel<<<build_grid, kJoinThreads, 0, stream>>>(build_params);
+    }
     HYB_CUDA(cudaGetLastError());
     ++launches;
   }
@@ -1745,13 +1809,16 @@ int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const h
     ProbeParams span_params = params;
     span_params.probe = span_source;
     const uint32_t spans = span_source.tile_count;
-    const size_t stage_bytes = sizeof(uint2) * kSpanRows;
+    const size_t counter_bytes = sizeof(uint32_t) * kSpanWarps * partition_count;
+    const size_t write_bytes = sizeof(uint2) * kSpanRows + counter_bytes;
     const auto count_spans = rank ? join_span_count_kernel<kTableRank> : join_span_count_kernel<kTableDirect>;
     const auto write_spans =
         rank ? (options.join_ballot_rank ? join_span_write_kernel<kTableRank, true> : join_span_write_kernel<kTableRank, false>)
              : (options.join_ballot_rank ? join_span_write_kernel<kTableDirect, true> : join_span_write_kernel<kTableDirect, false>);
-    HYB_CUDA(cudaFuncSetAttribute(write_spans, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(stage_bytes)));
-    count_spans<<<spans, kSpanThreads, 0, stream>>>(span_params);
+    HYB_CUDA(cudaFuncSetAttribute(write_spans, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(write_bytes)));
+    uint16_t* fine_counts = nullptr;
+    HYB_TRY(scratch.alloc_array(size_t{spans} * kSpanWarps * partition_count, &fine_counts));
+    count_spans<<<spans, kSpanThreads, counter_bytes, stream>>>(span_params, fine_counts);
     HYB_CUDA(cudaGetLastError());
     HYB_TRY(run_exclusive_scan(context, static_cast<uint32_t*>(histogram), static_cast<unsigned long long*>(run_starts),
                                histogram_entries, total_slot));
@@ -1759,7 +1826,7 @@ int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const h
     span_params.out_probe = params.out_probe;
     span_params.out_build = params.out_build;
     span_params.out_capacity = params.out_capacity;
-    write_spans<<<spans, kSpanThreads, stage_bytes, stream>>>(span_params);
+    write_spans<<<spans, kSpanThreads, write_bytes, stream>>>(span_params, fine_counts);
     HYB_CUDA(cudaGetLastError());
     join_partition_offsets_kernel<<<(partition_count + 1 + 127) / 128, 128, 0, stream>>>(
         static_cast<const unsigned long long*>(run_starts), total_slot, partition_count, spans,

@@ -556,6 +556,8 @@ __global__ void __launch_bounds__(kBulkThreads) scan_bulk_kernel(const ScanParam
   extern __shared__ __align__(128) unsigned char s_dynamic[];  // kBulkStages input stages, then the match staging
   __shared__ __align__(8) unsigned long long s_full[kBulkStages], s_empty[kBulkStages], s_ready[2];
   __shared__ uint4 s_info[kBulkStages];  // {tile, chunk, row0 | last-tile-of-chunk << 31, bytes per row}
+  __shared__ __align__(16) DevSegment s_segment[kBulkStages];  // the tile's chunk: descriptor and predicate test
+  __shared__ __align__(16) ChunkTest s_test[kBulkStages];
   __shared__ uint32_t s_totals[2][kBulkConsumerWarps];
   __shared__ uint32_t s_arrived[2];
   __shared__ unsigned long long s_base[2];
@@ -576,30 +578,45 @@ __global__ void __launch_bounds__(kBulkThreads) scan_bulk_kernel(const ScanParam
   __syncthreads();  // the only CTA-wide barrier of the kernel
 
   if (warp == kBulkConsumerWarps) {
-    // ---- producer -------------------------------------------------------------------------------------------------
-    if (lane != 0) return;
+    // ---- producer warp: lane 0 claims tiles and issues the copies; lanes 0-2 / 3-6 fetch the chunk's segment descriptor /
+    //      predicate test (16 bytes each, in parallel) and hand them to the consumers through the stage header ------------
     for (uint32_t fill = 0;; ++fill) {
       const uint32_t stage = fill % kBulkStages;
-      mbarrier_wait(&s_empty[stage], ((fill / kBulkStages) & 1u) ^ 1u);  // passes at once for the first kBulkStages fills
-      const uint32_t tile = atomicAdd(params.ticket, 1u);
+      uint32_t tile = 0;
+      if (lane == 0) {
+        mbarrier_wait(&s_empty[stage], ((fill / kBulkStages) & 1u) ^ 1u);  // passes at once for the first kBulkStages fills
+        tile = atomicAdd(params.ticket, 1u);
+      }
+      tile = __shfl_sync(kFullMask, tile, 0);
       if (tile >= params.tile_count) {
-        s_info[stage] = make_uint4(kBulkEndOfTiles, 0u, 0u, 0u);
-        mbarrier_arrive(&s_full[stage]);
+        if (lane == 0) {
+          s_info[stage] = make_uint4(kBulkEndOfTiles, 0u, 0u, 0u);
+          mbarrier_arrive(&s_full[stage]);
+        }
         return;
       }
       const uint2 info = __ldg(params.tile_map + tile);
-      const DevSegment& segment = params.segments[info.x];
-      const uint32_t row0 = info.y & 0x7FFFFFFFu;
-      const char* base;
-      const uint32_t width = segment_stream(segment, base);
-      s_info[stage] = make_uint4(tile, info.x, info.y, width);
-      if (params.tests[info.x].mode != kTestNone) {
-        const uint32_t rows = min(static_cast<uint32_t>(kScanTileRows), segment.row_count - row0);
-        const uint32_t bytes = (rows * width + 15u) & ~15u;  // the readable tail pad covers the round-up
-        mbarrier_arrive_expect_tx(&s_full[stage], bytes);
-        bulk_copy_to_shared(s_dynamic + size_t{stage} * stage_bytes, base + size_t{row0} * width, bytes, &s_full[stage]);
-      } else {
-        mbarrier_arrive(&s_full[stage]);  // "no row can match": the chunk's bytes are never read
+      static_assert(sizeof(DevSegment) == 48 && sizeof(ChunkTest) == 64, "copied as 3 + 4 uint4");
+      if (lane < 3) {
+        reinterpret_cast<uint4*>(&s_segment[stage])[lane] = __ldg(reinterpret_cast<const uint4*>(params.segments + info.x) + lane);
+      } else if (lane < 7) {
+        reinterpret_cast<uint4*>(&s_test[stage])[lane - 3] = __ldg(reinterpret_cast<const uint4*>(params.tests + info.x) + (lane - 3));
+      }
+      __syncwarp();
+      if (lane == 0) {
+        const DevSegment& segment = s_segment[stage];
+        const uint32_t row0 = info.y & 0x7FFFFFFFu;
+        const char* base;
+        const uint32_t width = segment_stream(segment, base);
+        s_info[stage] = make_uint4(tile, info.x, info.y, width);
+        if (s_test[stage].mode != kTestNone) {
+          const uint32_t rows = min(static_cast<uint32_t>(kScanTileRows), segment.row_count - row0);
+          const uint32_t bytes = (rows * width + 15u) & ~15u;  // the readable tail pad covers the round-up
+          mbarrier_arrive_expect_tx(&s_full[stage], bytes);
+          bulk_copy_to_shared(s_dynamic + size_t{stage} * stage_bytes, base + size_t{row0} * width, bytes, &s_full[stage]);
+        } else {
+          mbarrier_arrive(&s_full[stage]);  // "no row can match": the chunk's bytes are never read
+        }
       }
     }
   }
@@ -615,8 +632,8 @@ __global__ void __launch_bounds__(kBulkThreads) scan_bulk_kernel(const ScanParam
     const uint32_t tile = info.x, chunk = info.y, width = info.w;
     const uint32_t tile_row0 = info.z & 0x7FFFFFFFu;
     const bool last_tile_of_chunk = (info.z >> 31) != 0;
-    const DevSegment segment = params.segments[chunk];
-    const ChunkTest test = params.tests[chunk];
+    const DevSegment& segment = s_segment[stage];  // shared memory: no global access on the consumers' path
+    const ChunkTest& test = s_test[stage];
     const unsigned char* staged = s_dynamic + size_t{stage} * stage_bytes;
 
     // 1. predicate masks of this thread's kScanIterations x 8 rows, read from the staged tile
