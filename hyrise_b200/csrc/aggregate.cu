@@ -1468,13 +1468,17 @@ static StreamLayout stream_layout_for(const Table* table, const hyb_aggregate_qu
   };
   const size_t value_size = fast.work_type == 0 ? sizeof(float) : sizeof(double);
   std::vector<uint32_t> max_width(staged.size(), 0);
+  std::vector<uint32_t> max_dictionary(table->column_count, 0);
   for (uint32_t chunk = 0; chunk < chunk_count; ++chunk) {
     const DevSegment* segments = &table->segments[size_t{chunk} * table->column_count];
     for (size_t i = 0; i < staged.size(); ++i) {
       const DevSegment& segment = segments[staged[i]];
       const uint32_t width = stream_width(segment);
       if (width == 0 || width > 4 || segment.nulls || (segment.pad & kSegmentMayContainNulls)) return layout;
+      // one encoding per column: the row loop is compiled for the launch constants (narrower vectors are widened per tile)
+      if (segment.encoding != table->segments[staged[i]].encoding) return layout;
       max_width[i] = std::max(max_width[i], width);
+      max_dictionary[staged[i]] = std::max(max_dictionary[staged[i]], segment.dict_size);
     }
     uint64_t combos = 1;
     for (uint32_t g = 0; g < query->groupby_count; ++g) {
@@ -1499,16 +1503,17 @@ static StreamLayout stream_layout_for(const Table* table, const hyb_aggregate_qu
   for (size_t i = 0; i < staged.size(); ++i) {
     plan.columns[i].segments = table->d_segments + size_t{staged[i]} * chunk_count;
     plan.columns[i].slot_offset = offset;
+    plan.column_width[i] = max_width[i];
     offset += kStreamTileRows * max_width[i];
   }
-  // launch constants: the common case, taken from the first chunk (tiles that deviate are flagged by the producer)
+  // launch constants: widest vector / largest dictionary of a column over all chunks, the (uniform) encoding
   const DevSegment* first = &table->segments[0];
   for (uint32_t p = 0; p < query->predicate_count; ++p) {
     const DevSegment& segment = first[query->predicates[p].column_id];
     const int32_t condition = query->predicates[p].condition;
     const bool null_check = condition == HYB_PRED_IS_NULL || condition == HYB_PRED_IS_NOT_NULL;
     plan.predicate_offset[p] = plan.columns[predicate_slot[p]].slot_offset;
-    plan.predicate_width[p] = stream_width(segment);
+    plan.predicate_width[p] = max_width[predicate_slot[p]];
     plan.predicate_encoding[p] = segment.encoding;
     plan.predicate_mode[p] = segment.encoding == HYB_ENC_DICTIONARY ? kTestIdRange
                              : null_check                            ? kTestNull
@@ -1519,10 +1524,10 @@ static StreamLayout stream_layout_for(const Table* table, const hyb_aggregate_qu
   for (size_t c = 0; c < fast.columns.size(); ++c) {
     const DevSegment& segment = first[fast.columns[c].column];
     plan.value_offset[c] = plan.columns[value_slot[c]].slot_offset;
-    plan.value_width[c] = stream_width(segment);
-    plan.value_kind[c] = segment.encoding != HYB_ENC_DICTIONARY       ? kValueBits
-                         : segment.dict_size <= kStagedDictionary ? kValueStagedDictionary
-                                                                  : kValueGlobalDictionary;
+    plan.value_width[c] = max_width[value_slot[c]];
+    plan.value_kind[c] = segment.encoding != HYB_ENC_DICTIONARY                              ? kValueBits
+                         : max_dictionary[fast.columns[c].column] <= kStagedDictionary ? kValueStagedDictionary
+                                                                                       : kValueGlobalDictionary;
     plan.dictionary_offset[c] = offset;
     offset += static_cast<uint32_t>(kStagedDictionary * value_size);
   }
@@ -1535,7 +1540,7 @@ static StreamLayout stream_layout_for(const Table* table, const hyb_aggregate_qu
   offset += (static_cast<uint32_t>(sizeof(StreamStageInfo)) + 127u) & ~127u;
   plan.stage_bytes = offset;
   layout.dynamic_bytes = size_t{kStreamStages} * plan.stage_bytes;
-  if (layout.dynamic_bytes > 200 * 1024) return layout;
+  if (layout.dynamic_bytes > 110 * 1024) return layout;  // two CTAs per SM
   layout.possible = true;
   return layout;
 }
@@ -1697,9 +1702,9 @@ int hyb_aggregate_hash(hyb_context* context, const hyb_aggregate_query* query, h
       const FastKernel kernel = fast_kernel(fast.work_type, G, C);
       uint32_t grid = 1;
       if (attempt.stream) {
-        // one persistent CTA per SM (the stages take most of its shared memory), units strided over the CTAs
+        // two persistent CTAs per SM (three stages of 2048 rows each), units strided over the CTAs
         const uint32_t unit_count = (tile_count + kStreamUnitTiles - 1) / kStreamUnitTiles;
-        grid = std::max<uint32_t>(1, std::min<uint32_t>(unit_count, context->sm_count));
+        grid = std::max<uint32_t>(1, std::min<uint32_t>(unit_count, context->sm_count * 2));
       } else {
         int blocks_per_sm = 1;
         HYB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kFastThreads, 0));

@@ -23,7 +23,7 @@
 namespace hyb {
 
 constexpr int kStreamStages = 3;
-constexpr int kStreamConsumerWarps = 12;
+constexpr int kStreamConsumerWarps = 8;
 constexpr int kStreamConsumerThreads = kStreamConsumerWarps * 32;
 constexpr int kStreamThreads = kStreamConsumerThreads + 32;  // + the producer warp
 constexpr int kStreamRowsPerWarp = 256;
@@ -42,15 +42,12 @@ struct StreamStageInfo {
   uint32_t rows;   // valid rows of the tile (0: a predicate rules the whole chunk out, nothing was copied)
   uint32_t row0;   // first row of the tile inside its chunk
   uint32_t first_position;  // table position of the tile's first row
-  uint32_t regular;         // 1: widths / value kinds / test modes equal the launch constants of the plan
-  uint32_t predicate_width[HYB_MAX_FUSED_PREDICATES];
-  uint32_t predicate_encoding[HYB_MAX_FUSED_PREDICATES];
+  uint32_t regular;         // 1: every staged slice has the vector width the plan's launch constants name
+  uint32_t column_width[kStreamMaxColumns];  // bytes per row of the staged columns in this chunk
   const int32_t* predicate_minima[HYB_MAX_FUSED_PREDICATES];  // FrameOfReference block minima
   ChunkTest tests[HYB_MAX_FUSED_PREDICATES];
   uint32_t group_dict_size[HYB_MAX_GROUPBY_COLUMNS];
   uint32_t group_entry_type[HYB_MAX_GROUPBY_COLUMNS];  // 0xFF = staged uint64 key words, else hyb_data_type of staged dictionary values
-  uint32_t value_width[kFastMaxColumns];
-  uint32_t value_kind[kFastMaxColumns];
   const void* dictionary[kFastMaxColumns];  // value column: dictionary in global memory
 };
 
@@ -67,6 +64,7 @@ struct StreamPlan {
   FastPlan fast;
   uint32_t column_count;
   StreamColumn columns[kStreamMaxColumns];
+  uint32_t column_width[kStreamMaxColumns];              // launch constant: the widest vector of the column over all chunks
   uint32_t predicate_offset[HYB_MAX_FUSED_PREDICATES];   // stage offsets of the roles' column slices
   uint32_t group_offset[HYB_MAX_GROUPBY_COLUMNS];
   uint32_t value_offset[kFastMaxColumns];
@@ -157,6 +155,41 @@ __device__ __forceinline__ unsigned long long stream_key_entry(const unsigned ch
   }
 }
 
+// A tile whose chunk stores a column in a narrower vector than the launch constant (a dictionary that happens to be small,
+// typically in the table's last chunk): all consumer warps widen the staged slice in place — read into registers,
+// barrier, write — so that the row loop exists in one variant only. Rare; CTA-uniform (every consumer thread calls it).
+__device__ __noinline__ void stream_widen_slice(unsigned char* slot, uint32_t from, uint32_t to, uint32_t rows) {
+  constexpr int kPerThread = kStreamTileRows / kStreamConsumerThreads;  // 8
+  uint32_t held[kPerThread];
+#pragma unroll
+  for (int i = 0; i < kPerThread; ++i) {
+    const uint32_t row = threadIdx.x + i * kStreamConsumerThreads;
+    held[i] = 0;
+    if (row < rows) held[i] = from == 1 ? slot[row] : reinterpret_cast<const uint16_t*>(slot)[row];
+  }
+  stream_consumer_barrier();
+#pragma unroll
+  for (int i = 0; i < kPerThread; ++i) {
+    const uint32_t row = threadIdx.x + i * kStreamConsumerThreads;
+    if (row < rows) {
+      if (to == 2) {
+        reinterpret_cast<uint16_t*>(slot)[row] = static_cast<uint16_t>(held[i]);
+      } else {
+        reinterpret_cast<uint32_t*>(slot)[row] = held[i];
+      }
+    }
+  }
+  stream_consumer_barrier();
+}
+
+__device__ __forceinline__ void stream_widen_tile(const StreamPlan& plan, const StreamStageInfo* info, unsigned char* stage_base) {
+  // slices shared by several roles are widened once: the header records the width per staged column
+  for (uint32_t column = 0; column < plan.column_count; ++column) {
+    const uint32_t from = info->column_width[column], to = plan.column_width[column];
+    if (from < to) stream_widen_slice(stage_base + plan.columns[column].slot_offset, from, to, info->rows);
+  }
+}
+
 // Per-thread aggregation state of a consumer (registers; static indexes only).
 template <int W, int G, int C>
 struct StreamState {
@@ -167,8 +200,9 @@ struct StreamState {
   uint32_t seen_groups;  // bit g: this thread has recorded first_position[g]
 };
 
-// The rows of one warp in one tile. kRegular: vector widths, value kinds and test modes are the plan's launch constants.
-template <int W, int G, int C, bool kRegular>
+// The rows of one warp in one tile. Vector widths, value kinds and test modes are the plan's launch constants (tiles of a
+// chunk with narrower vectors have been widened in place by stream_widen_tile).
+template <int W, int G, int C>
 __device__ __forceinline__ void stream_warp_rows(const StreamPlan& plan, const StreamStageInfo* info, const unsigned char* stage_base,
                                                  uint32_t warp, uint32_t lane, uint8_t* my_combos, unsigned long long* s_hash,
                                                  unsigned long long (*s_keys)[kMaxKeyWords],
@@ -182,22 +216,31 @@ __device__ __forceinline__ void stream_warp_rows(const StreamPlan& plan, const S
   const uint32_t groupby_count = fast.groupby_count;
   const uint32_t predicate_count = fast.predicate_count;
   const uint32_t need_raw_mask = fast.need_raw_mask, need_product_mask = fast.need_product_mask;
-#pragma unroll
+#pragma unroll 1
   for (int step = 0; step < kStreamSteps; ++step) {
     const uint32_t local0 = warp * kStreamRowsPerWarp + step * (32 * kStreamLaneRows) + lane * kStreamLaneRows;
     if (warp * kStreamRowsPerWarp + step * (32 * kStreamLaneRows) >= rows) break;  // uniform
     const uint32_t valid = local0 >= rows ? 0u : (rows - local0 >= kStreamLaneRows ? 0xFu : ((1u << (rows - local0)) - 1u));
     uint32_t pass = valid;
     for (uint32_t p = 0; p < predicate_count; ++p) {
-      const uint32_t width = kRegular ? plan.predicate_width[p] : info->predicate_width[p];
-      const uint32_t mode = kRegular ? plan.predicate_mode[p] : info->tests[p].mode;
-      const uint32_t encoding = kRegular ? plan.predicate_encoding[p] : info->predicate_encoding[p];
+      const uint32_t width = plan.predicate_width[p];
+      const uint32_t mode = plan.predicate_mode[p];
       uint32_t codes[kStreamLaneRows];
       stream_codes4(stage_base + plan.predicate_offset[p], width, local0, codes);
       uint32_t matches = 0;
+      if (mode == kTestIdRange) {
+        // the common case (dictionary value-ID range): three broadcast reads, two instructions per row
+        const uint32_t id_lo = info->tests[p].id_lo, id_span = info->tests[p].id_span;
+        const uint32_t flip = info->tests[p].negate ? 0xFu : 0u;
 #pragma unroll
-      for (int j = 0; j < kStreamLaneRows; ++j) {
-        matches |= stream_test(mode, info->tests[p], encoding, info->predicate_minima[p], codes[j], info->row0 + local0 + j) ? (1u << j) : 0u;
+        for (int j = 0; j < kStreamLaneRows; ++j) matches |= ((codes[j] - id_lo) < id_span) ? (1u << j) : 0u;
+        matches ^= flip;
+      } else {
+        const uint32_t encoding = plan.predicate_encoding[p];
+#pragma unroll
+        for (int j = 0; j < kStreamLaneRows; ++j) {
+          matches |= stream_test(mode, info->tests[p], encoding, info->predicate_minima[p], codes[j], info->row0 + local0 + j) ? (1u << j) : 0u;
+        }
       }
       pass &= matches;
     }
@@ -223,7 +266,7 @@ __device__ __forceinline__ void stream_warp_rows(const StreamPlan& plan, const S
 #pragma unroll
       for (int j = 0; j < kStreamLaneRows; ++j) {
         const bool row_passes = (pass >> j) & 1u;
-        combination[j] = row_passes ? combination[j] : 0u;  // rows past the tile's end carry stale codes
+        combination[j] &= kMaxCombos - 1;  // identity for real rows; rows past the tile's end carry stale codes
         const uint32_t known = my_combos[combination[j]];
         group[j] = row_passes ? known : static_cast<uint32_t>(G);
         unresolved = unresolved || (row_passes && known >= kComboOverflow);
@@ -307,15 +350,21 @@ __device__ __forceinline__ void stream_warp_rows(const StreamPlan& plan, const S
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       if (fast.value_segments[c] == nullptr) continue;
-      const uint32_t width = kRegular ? plan.value_width[c] : info->value_width[c];
-      const uint32_t kind = kRegular ? plan.value_kind[c] : info->value_kind[c];
+      const uint32_t width = plan.value_width[c];
+      const uint32_t kind = plan.value_kind[c];
       uint32_t codes[kStreamLaneRows];
       stream_codes4(stage_base + plan.value_offset[c], width, local0, codes);
       Value values[kStreamLaneRows];
       if (kind == kValueStagedDictionary) {
+        // 1-byte codes cannot leave the 256-entry staged dictionary, whatever stale bytes sit past the tile's end
         const Value* dictionary = reinterpret_cast<const Value*>(stage_base + plan.dictionary_offset[c]);
+        if (width == 1) {
 #pragma unroll
-        for (int j = 0; j < kStreamLaneRows; ++j) values[j] = dictionary[((valid >> j) & 1u) ? codes[j] : 0u];
+          for (int j = 0; j < kStreamLaneRows; ++j) values[j] = dictionary[codes[j]];
+        } else {
+#pragma unroll
+          for (int j = 0; j < kStreamLaneRows; ++j) values[j] = dictionary[((valid >> j) & 1u) ? codes[j] : 0u];
+        }
       } else if (kind == kValueGlobalDictionary) {
         const void* dictionary = info->dictionary[c];
 #pragma unroll
@@ -359,7 +408,7 @@ __device__ __forceinline__ void stream_warp_rows(const StreamPlan& plan, const S
 }
 
 template <int W, int G, int C>
-__global__ void __launch_bounds__(kStreamThreads, 1) aggregate_stream_kernel(const __grid_constant__ StreamPlan plan) {
+__global__ void __launch_bounds__(kStreamThreads, 2) aggregate_stream_kernel(const __grid_constant__ StreamPlan plan) {
   using Value = typename WorkType<W>::Value;
   using Accumulator = typename WorkType<W>::Accumulator;
   static_assert(G == 1 || G == 4, "row counts are packed as one byte per group");
@@ -417,6 +466,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) aggregate_stream_kernel(con
           const DevSegment& segment = plan.columns[lane].segments[chunk];
           const char* base;
           const uint32_t width = segment_stream(segment, base);
+          info->column_width[lane] = width;
+          regular = width == plan.column_width[lane];  // narrower: the consumers widen the slice before the row loop
           source = base + size_t{row0} * width;
           destination = stage_base + plan.columns[lane].slot_offset;
           bytes = (rows * width + 15u) & ~15u;
@@ -424,17 +475,8 @@ __global__ void __launch_bounds__(kStreamThreads, 1) aggregate_stream_kernel(con
           const int c = lane - 12;
           if (fast.value_segments[c] != nullptr) {
             const DevSegment& segment = fast.value_segments[c][chunk];
-            const char* base;
-            const uint32_t width = segment_stream(segment, base);
-            uint32_t kind = kValueBits;
-            if (segment.encoding == HYB_ENC_DICTIONARY) {
-              kind = segment.dict_size <= kStagedDictionary ? kValueStagedDictionary : kValueGlobalDictionary;
-            }
-            info->value_width[c] = width;
-            info->value_kind[c] = kind;
             info->dictionary[c] = segment.values;
-            regular = width == plan.value_width[c] && kind == plan.value_kind[c];
-            if (kind == kValueStagedDictionary) {
+            if (plan.value_kind[c] == kValueStagedDictionary) {  // the host checked: <= kStagedDictionary entries in every chunk
               source = segment.values;
               destination = stage_base + plan.dictionary_offset[c];
               bytes = (segment.dict_size * static_cast<uint32_t>(sizeof(Value)) + 15u) & ~15u;
@@ -453,16 +495,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) aggregate_stream_kernel(con
         } else if (lane >= 24 && lane < 24 + predicate_count) {
           const int p = lane - 24;
           const ChunkTest test = fast.predicate_tests[p][chunk];
-          const DevSegment& segment = fast.predicate_segments[p][chunk];
-          const char* base;
-          const uint32_t width = segment_stream(segment, base);
           info->tests[p] = test;
-          info->predicate_width[p] = width;
-          info->predicate_minima[p] = static_cast<const int32_t*>(segment.values);
-          info->predicate_encoding[p] = segment.encoding;
+          info->predicate_minima[p] = static_cast<const int32_t*>(fast.predicate_segments[p][chunk].values);
           ruled_out = test.mode == kTestNone;
-          regular = width == plan.predicate_width[p] && test.mode == plan.predicate_mode[p] &&
-                    segment.encoding == plan.predicate_encoding[p];
         }
         const bool skip = __any_sync(kFullMask, ruled_out);
         const bool all_regular = __all_sync(kFullMask, regular);
@@ -571,13 +606,9 @@ __global__ void __launch_bounds__(kStreamThreads, 1) aggregate_stream_kernel(con
           __syncwarp();
         }
       }
-      if (info->regular) {
-        stream_warp_rows<W, G, C, true>(plan, info, stage_base, warp, lane, my_combos, s_hash, s_keys, combo_stride, affine_a,
-                                        affine_b, state);
-      } else {
-        stream_warp_rows<W, G, C, false>(plan, info, stage_base, warp, lane, my_combos, s_hash, s_keys, combo_stride, affine_a,
-                                         affine_b, state);
-      }
+      if (!info->regular) stream_widen_tile(plan, info, s_stages + size_t{stage} * plan.stage_bytes);  // rare, CTA-uniform
+      stream_warp_rows<W, G, C>(plan, info, stage_base, warp, lane, my_combos, s_hash, s_keys, combo_stride, affine_a, affine_b,
+                                state);
       if ((iteration & 15u) == 15u) flush_row_counts();  // <= 8 rows per lane and tile: the bytes stay below 256
     }
     __syncwarp();

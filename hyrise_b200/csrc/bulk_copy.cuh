@@ -43,7 +43,7 @@ __device__ __forceinline__ void mbarrier_wait(unsigned long long* barrier, uint3
       "{\n\t"
       ".reg .pred done;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 done, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 done, [%0], %1, 0x989680;\n\t"  // suspend-time hint: do not busy-poll
       "@done bra WAIT_DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t"

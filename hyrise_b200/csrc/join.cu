@@ -349,49 +349,84 @@ __global__ void __launch_bounds__(kJoinThreads) join_build_kernel(const BuildPar
   }
 }
 
-// Rank-table build. Keys arrive in rising order (that is what qualifies a build side for the rank table), so a warp's 32
-// consecutive rows fall into a handful of 32-key blocks: lanes of one run of equal block ids combine their presence bits
-// and smallest position with two warp reductions and the run's first lane issues ONE atomicOr + ONE atomicMax for all
-// of them (8 keys per block for dbgen's sparse order keys: 8x fewer atomics on the same 8 bytes). Runs are found by
-// comparing with the previous lane, so an input that is not sorted after all is still inserted correctly — just with more
-// atomics. All 16 key loads of a lane are in flight before the first use.
+// ---- per-tile key codecs ---------------------------------------------------------------------------------------------
+// The inner loops are specialised for the layouts that dominate (plain int32/int64 values, FrameOfReference offsets in a
+// FixedWidthIntegerVector, no NULL vector); everything else — dictionaries, bit-packed vectors, nullable segments, PosList
+// inputs — takes the generic decoder. The choice is uniform per tile (tiles never straddle chunks).
+enum : uint32_t { kCodecGeneric = 0, kCodecPlain32, kCodecPlain64, kCodecFor8, kCodecFor16, kCodecFor32 };
+
+__device__ __forceinline__ uint32_t tile_codec(const KeySource& source, const DevSegment& segment) {
+  if (!source.tile_map || segment.nulls) return kCodecGeneric;
+  if (segment.encoding == HYB_ENC_UNENCODED) return segment.data_type == HYB_TYPE_INT32 ? kCodecPlain32 : kCodecPlain64;
+  if (segment.encoding == HYB_ENC_FRAME_OF_REFERENCE) {
+    if (segment.vector_type == HYB_VEC_FIXED_1B) return kCodecFor8;
+    if (segment.vector_type == HYB_VEC_FIXED_2B) return kCodecFor16;
+    if (segment.vector_type == HYB_VEC_FIXED_4B) return kCodecFor32;
+  }
+  return kCodecGeneric;
+}
+
+// Rank-table build. Keys arrive in rising order (that is what qualifies a build side for the rank table), so neighbouring
+// rows fall into the same 32-key block: a thread combines the presence bits and the smallest position of its 4
+// consecutive keys (one 128-bit load) before it touches the table — ONE atomicOr + ONE atomicMax per run of equal block
+// ids instead of two atomics per key on the same 8 bytes (8 keys per block for dbgen's sparse order keys). Unique key
+// columns are stored as plain ValueSegment<int32> by the reference's encoder (benchmark_table_encoder.cpp:119-120), which
+// is the vectorised path; every other layout (FrameOfReference, dictionaries, int64, PosList inputs) inserts row by row.
+// An input that is not sorted after all is still inserted correctly, only with more atomics.
 __global__ void __launch_bounds__(kJoinThreads) join_build_rank_kernel(const BuildParams params) {
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned long long minimum = static_cast<unsigned long long>(params.table.direct_min);
+  uint2* __restrict__ blocks = params.table.rank_blocks;
   for (uint32_t tile = blockIdx.x; tile < params.source.tile_count; tile += gridDim.x) {
     const TileRef ref = tile_ref(params.source, tile);
     const DevSegment segment = params.source.tile_map ? params.source.segments[ref.chunk] : DevSegment{};
-    constexpr int kSteps = kJoinRowsPerWarp / 32;
+    const uint32_t codec = tile_codec(params.source, segment);
+    if (codec == kCodecPlain32 && ref.row0 + kJoinTileRows <= segment.row_count) {
+      constexpr int kVectors = kJoinTileRows / (4 * kJoinThreads);  // 4 x 128-bit loads per thread, all in flight
+      const uint4* keys4 = reinterpret_cast<const uint4*>(static_cast<const uint32_t*>(segment.values) + ref.row0);
+      uint4 loaded[kVectors];
+#pragma unroll
+      for (int v = 0; v < kVectors; ++v) loaded[v] = ld_stream_v4(keys4 + v * kJoinThreads + threadIdx.x);
+#pragma unroll
+      for (int v = 0; v < kVectors; ++v) {
+        const uint32_t first_position = static_cast<uint32_t>(ref.first_position) + (v * kJoinThreads + threadIdx.x) * 4;
+        const uint32_t keys[4] = {loaded[v].x, loaded[v].y, loaded[v].z, loaded[v].w};
+        uint32_t run_block = 0, run_bits = 0, run_position = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const unsigned long long offset = static_cast<unsigned long long>(static_cast<long long>(static_cast<int32_t>(keys[j]))) - minimum;
+          const uint32_t block = static_cast<uint32_t>(offset >> 5);
+          const uint32_t bit = 1u << (static_cast<uint32_t>(offset) & 31u);
+          if (j > 0 && block == run_block) {
+            run_bits |= bit;
+          } else {
+            if (j > 0) {
+              atomicOr(&blocks[run_block].x, run_bits);
+              atomicMax(&blocks[run_block].y, ~run_position);
+            }
+            run_block = block;
+            run_bits = bit;
+            run_position = first_position + j;
+          }
+        }
+        atomicOr(&blocks[run_block].x, run_bits);
+        atomicMax(&blocks[run_block].y, ~run_position);
+      }
+      continue;
+    }
+    constexpr int kSteps = kJoinTileRows / kJoinThreads;
     long long key[kSteps];
     uint32_t usable = 0;
 #pragma unroll
     for (int s = 0; s < kSteps; ++s) {
       bool is_null = false;
       key[s] = 0;
-      const bool valid = load_key1(params.source, ref, segment, warp * kJoinRowsPerWarp + s * 32 + lane, key[s], is_null);
+      const bool valid = load_key1(params.source, ref, segment, s * kJoinThreads + threadIdx.x, key[s], is_null);
       if (valid && is_null) params.flags[1] = 1;
       usable |= (valid && !is_null) ? (1u << s) : 0u;
     }
 #pragma unroll
     for (int s = 0; s < kSteps; ++s) {
-      const bool insert = (usable >> s) & 1u;
-      const unsigned long long offset = static_cast<unsigned long long>(key[s]) - minimum;
-      const uint32_t block = insert ? static_cast<uint32_t>(offset >> 5) : 0xFFFFFFFFu;
-      const uint32_t position = static_cast<uint32_t>(ref.first_position) + warp * kJoinRowsPerWarp + s * 32 + lane;
-      const uint32_t previous = __shfl_up_sync(kFullMask, block, 1);
-      const uint32_t heads = __ballot_sync(kFullMask, lane == 0 || block != previous);
-      // my run: from the last head at or below my lane to the lane before the next head
-      const uint32_t first = 31u - __clz(heads & (0xFFFFFFFFu >> (31u - lane)));
-      const uint32_t above = lane == 31 ? 0u : (heads >> (lane + 1));
-      const uint32_t last = above ? lane + __ffs(above) - 1 : 31u;
-      const uint32_t run = (0xFFFFFFFFu >> (31u - last)) & (0xFFFFFFFFu << first);
-      const uint32_t bits = __reduce_or_sync(run, insert ? (1u << (static_cast<uint32_t>(offset) & 31u)) : 0u);
-      const uint32_t smallest = __reduce_min_sync(run, insert ? position : 0xFFFFFFFFu);
-      if (lane == first && bits) {
-        uint2* entry = params.table.rank_blocks + block;
-        atomicOr(&entry->x, bits);
-        atomicMax(&entry->y, ~smallest);
-      }
+      if ((usable >> s) & 1u) table_insert(params, key[s], static_cast<uint32_t>(ref.first_position + s * kJoinThreads + threadIdx.x));
     }
   }
 }
@@ -640,23 +675,6 @@ __device__ __forceinline__ uint32_t emitted_rows(const ProbeParams& params, uint
   if (match == kNoMatch) return 0;
   if (match == kEmitWithoutPartner || params.unique_build) return 1;
   return params.dup_counts[match];
-}
-
-// ---- per-tile key codecs ---------------------------------------------------------------------------------------------
-// The inner loops are specialised for the layouts that dominate (plain int32/int64 values, FrameOfReference offsets in a
-// FixedWidthIntegerVector, no NULL vector); everything else — dictionaries, bit-packed vectors, nullable segments, PosList
-// inputs — takes the generic decoder. The choice is uniform per tile (tiles never straddle chunks).
-enum : uint32_t { kCodecGeneric = 0, kCodecPlain32, kCodecPlain64, kCodecFor8, kCodecFor16, kCodecFor32 };
-
-__device__ __forceinline__ uint32_t tile_codec(const KeySource& source, const DevSegment& segment) {
-  if (!source.tile_map || segment.nulls) return kCodecGeneric;
-  if (segment.encoding == HYB_ENC_UNENCODED) return segment.data_type == HYB_TYPE_INT32 ? kCodecPlain32 : kCodecPlain64;
-  if (segment.encoding == HYB_ENC_FRAME_OF_REFERENCE) {
-    if (segment.vector_type == HYB_VEC_FIXED_1B) return kCodecFor8;
-    if (segment.vector_type == HYB_VEC_FIXED_2B) return kCodecFor16;
-    if (segment.vector_type == HYB_VEC_FIXED_4B) return kCodecFor32;
-  }
-  return kCodecGeneric;
 }
 
 template <uint32_t kCodec>
@@ -1267,7 +1285,7 @@ __global__ void __launch_bounds__(kSpanThreads, 2) join_span_write_kernel(const 
   extern __shared__ __align__(16) unsigned char s_dynamic[];
   uint2* s_stage = reinterpret_cast<uint2*>(s_dynamic);  // kSpanRows x {build position, row index in the span | partition << 16}
   uint32_t* s_position = reinterpret_cast<uint32_t*>(s_dynamic + sizeof(uint2) * kSpanRows);  // [kSpanWarps][partition_count]
-  __shared__ unsigned long long s_destination[kMaxPartitions];  // output index of staged row i of partition p = this + i
+  __shared__ uint32_t s_destination[kMaxPartitions];  // output index of staged row i of partition p = this + i (mod 2^32)
   __shared__ uint32_t s_scan[8];
   __shared__ uint32_t s_total;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1302,7 +1320,7 @@ __global__ void __launch_bounds__(kSpanThreads, 2) join_span_write_kernel(const 
     const uint32_t exclusive = before + inclusive - partition_total;
 #pragma unroll
     for (int w = 0; w < kSpanWarps; ++w) s_position[w * partition_count + threadIdx.x] += exclusive;
-    s_destination[threadIdx.x] = run_start - exclusive;  // modulo 2^64: run_start + (i - exclusive) for staged row i
+    s_destination[threadIdx.x] = static_cast<uint32_t>(run_start) - exclusive;  // run_start + (i - exclusive) for staged row i
     if (threadIdx.x + 1 == partition_count) s_total = exclusive + partition_total;
   }
   __syncthreads();
@@ -1316,13 +1334,31 @@ __global__ void __launch_bounds__(kSpanThreads, 2) join_span_write_kernel(const 
   __syncthreads();
 
   // ---- flat write-out: consecutive threads, consecutive output rows of a run ---------------------------------------------
+  // (output positions fit 32 bits: the output holds at most one row per probe position, and those are < 2^32)
   const uint32_t total = s_total;
-  for (uint32_t i = threadIdx.x; i < total; i += kSpanThreads) {
-    const uint2 staged = s_stage[i];
-    const unsigned long long at = s_destination[staged.y >> 16] + i;
-    const hyb_row_id build_row = position_to_row_id(params.build, staged.x);
-    st_stream_v2(params.out_build + at, build_row.chunk_id, build_row.chunk_offset);
-    st_stream_v2(params.out_probe + at, ref.chunk, ref.row0 + (staged.y & 0xFFFFu));
+  hyb_row_id* __restrict__ out_build = params.out_build;
+  hyb_row_id* __restrict__ out_probe = params.out_probe;
+  if (!params.build.filter && params.build.uniform_chunk_rows) {
+    // build position -> RowID by an exact multiply-shift division (all chunks but the last have uniform_chunk_rows rows)
+    const uint32_t magic = params.build.uniform_magic, shift = params.build.uniform_shift;
+    const uint32_t chunk_rows = params.build.uniform_chunk_rows;
+    for (uint32_t i = threadIdx.x; i < total; i += kSpanThreads) {
+      const uint2 staged = s_stage[i];
+      const uint32_t at = s_destination[staged.y >> 16] + i;
+      const uint32_t n = staged.x;
+      const uint32_t t = __umulhi(n, magic);
+      const uint32_t chunk = shift == 0 ? n : (t + ((n - t) >> 1)) >> (shift - 1);
+      st_stream_v2(out_build + at, chunk, n - chunk * chunk_rows);
+      st_stream_v2(out_probe + at, ref.chunk, ref.row0 + (staged.y & 0xFFFFu));
+    }
+  } else {
+    for (uint32_t i = threadIdx.x; i < total; i += kSpanThreads) {
+      const uint2 staged = s_stage[i];
+      const uint32_t at = s_destination[staged.y >> 16] + i;
+      const hyb_row_id build_row = position_to_row_id(params.build, staged.x);
+      st_stream_v2(out_build + at, build_row.chunk_id, build_row.chunk_offset);
+      st_stream_v2(out_probe + at, ref.chunk, ref.row0 + (staged.y & 0xFFFFu));
+    }
   }
 }
 #undef HYB_SPAN_DISPATCH

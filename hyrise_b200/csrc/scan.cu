@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_kernel(const ScanParams par
 // (dictionary value-IDs, FrameOfReference offsets, int32 / float values) and has no NULL vector; anything else takes
 // scan_kernel.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kBulkStages = 3;
+constexpr int kBulkStages = 2;
 constexpr int kBulkConsumerWarps = kScanWarps;                   // 8 x 1024 rows = one 8192-row tile
 constexpr int kBulkThreads = (kBulkConsumerWarps + 1) * 32;      // + the producer warp
 constexpr uint32_t kBulkEndOfTiles = 0xFFFFFFFFu;
@@ -552,7 +552,7 @@ __device__ __forceinline__ uint32_t evaluate8_staged(const DevSegment& segment, 
   return mask & valid;
 }
 
-__global__ void __launch_bounds__(kBulkThreads) scan_bulk_kernel(const ScanParams params, const uint32_t stage_bytes) {
+__global__ void __launch_bounds__(kBulkThreads, 4) scan_bulk_kernel(const ScanParams params, const uint32_t stage_bytes) {
   extern __shared__ __align__(128) unsigned char s_dynamic[];  // kBulkStages input stages, then the match staging
   __shared__ __align__(8) unsigned long long s_full[kBulkStages], s_empty[kBulkStages], s_ready[2];
   __shared__ uint4 s_info[kBulkStages];  // {tile, chunk, row0 | last-tile-of-chunk << 31, bytes per row}
