@@ -82,6 +82,10 @@ class ScanPredicate(C.Structure):
     ]
 
 
+class Literal(C.Structure):
+    _fields_ = [("data_type", C.c_int32), ("value", Value)]
+
+
 class JoinSide(C.Structure):
     _fields_ = [("table", C.c_uint64), ("column_id", C.c_uint32), ("filter", C.c_uint64)]
 
@@ -144,6 +148,11 @@ SYMBOLS = {
     "hyb_table_upload_from_blocks": [_CTX, C.POINTER(TableView), _U64, C.POINTER(_U64)],
     "hyb_blocks_free": [_CTX, _U64],
     "hyb_table_info": [_CTX, _U64, C.POINTER(_U32), C.POINTER(_U32), C.POINTER(_U64), C.POINTER(_U64)],
+    "hyb_flip_predicate_condition": [_I32, C.POINTER(_I32)],
+    "hyb_next_float_towards": [C.c_double, C.c_double, C.POINTER(C.c_float), C.POINTER(_I32)],
+    "hyb_lossless_predicate_cast": [_I32, C.POINTER(Literal), _I32, _I32, C.POINTER(_I32), C.POINTER(Value)],
+    "hyb_lossless_between_cast": [_I32, C.POINTER(Literal), C.POINTER(Literal), _I32, C.POINTER(_I32), C.POINTER(Value),
+                                  C.POINTER(Value)],
     "hyb_table_scan": [_CTX, _U64, C.POINTER(ScanPredicate), _U64, C.POINTER(_U64)],
     "hyb_pos_list_info": [_CTX, _U64, C.POINTER(_U64), C.POINTER(_U32)],
     "hyb_pos_list_chunk_offsets": [_CTX, _U64, _P],

@@ -273,6 +273,27 @@ typedef struct hyb_scan_predicate {
 } hyb_scan_predicate;
 
 /*
+ * Predicate normalisation (host only): what TableScan::create_impl does to a literal before a scan implementation sees
+ * it (table_scan.cpp:340-366, :399-441) with lossless_predicate_variant_cast (utils/lossless_predicate_cast.hpp:20-66,
+ * .cpp:14-73), lossless_cast (lossless_cast.hpp:31-176) and flip_predicate_condition / between_to_conditions /
+ * conditions_to_between (types.cpp:51-153). A shim whose optimizer hands it a literal of another type than the column
+ * calls these and passes the results on in hyb_scan_predicate; HYB_ERR_UNSUPPORTED = "no lossless form": the reference
+ * falls back to the ExpressionEvaluator, i.e. the CPU operator runs.
+ *   `float_col < 3.1 (double)`  ->  `float_col <= 3.0999999f`        `int_col = 16.25`  ->  HYB_ERR_UNSUPPORTED
+ * value_on_left: the predicate reads `literal <condition> column`; the returned condition is for `column <cond'> value`.
+ */
+typedef struct hyb_literal {
+  int32_t data_type; /* hyb_data_type, numeric */
+  hyb_value value;
+} hyb_literal;
+int hyb_flip_predicate_condition(int32_t condition, int32_t* out_condition);
+int hyb_next_float_towards(double value, double towards, float* out_value, int32_t* out_possible);
+int hyb_lossless_predicate_cast(int32_t condition, const hyb_literal* literal, int32_t column_type, int32_t value_on_left,
+                                int32_t* out_condition, hyb_value* out_value);
+int hyb_lossless_between_cast(int32_t condition, const hyb_literal* lower, const hyb_literal* upper, int32_t column_type,
+                              int32_t* out_condition, hyb_value* out_lower, hyb_value* out_upper);
+
+/*
  * Scan `table` and produce, per input chunk, the ascending list of matching RowIDs — what
  * AbstractTableScanImpl::scan_chunk returns for every chunk (table_scan.cpp:131). `input_filter` (0 = none) restricts
  * the scan to the positions of a previous scan's result on the same table (reference-table input with single-chunk

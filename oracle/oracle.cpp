@@ -3,6 +3,7 @@
 #include "oracle.h"
 
 #include <algorithm>
+#include <optional>
 #include <array>
 #include <atomic>
 #include <cmath>
@@ -1171,9 +1172,214 @@ bool scalar_less(const Scalar& a, const Scalar& b) {
 // =====================================================================================================================
 // C interface
 // =====================================================================================================================
+// Predicate normalisation: lossless_cast (lossless_cast.hpp:31-176), next_float_towards / lossless_predicate_cast
+// (utils/lossless_predicate_cast.{hpp:20-62,cpp:14-38}), flip / between helpers (types.cpp:51-153) — restated with the
+// reference's template structure: one overload set per (Source, Target) pair, std::optional for "not lossless".
+// =====================================================================================================================
+namespace predicate_cast {
+
+template <typename Target, typename Source>
+std::optional<Target> lossless(const Source& source) {
+  if constexpr (std::is_same_v<Target, Source>) {
+    return source;                                                              // identity (:31-36)
+  } else if constexpr (std::is_same_v<Source, int64_t> && std::is_same_v<Target, int32_t>) {
+    if (source < std::numeric_limits<int32_t>::min() || source > std::numeric_limits<int32_t>::max()) return std::nullopt;
+    return static_cast<int32_t>(source);                                        // (:38-46)
+  } else if constexpr (std::is_same_v<Source, int32_t> && std::is_same_v<Target, int64_t>) {
+    return static_cast<int64_t>(source);                                        // (:48-53)
+  } else if constexpr (std::is_integral_v<Source> && std::is_floating_point_v<Target>) {
+    const auto floating_point = static_cast<Target>(source);                    // (:101-110), with the round trip done in
+    if (!(static_cast<long double>(floating_point) == static_cast<long double>(source))) return std::nullopt;  // long double
+    return floating_point;                                                      // to stay clear of UB at 2^31 / 2^63
+  } else if constexpr (std::is_floating_point_v<Source> && std::is_integral_v<Target>) {
+    Source integral_part{};                                                     // (:113-147)
+    if (std::modf(source, &integral_part) != Source{}) return std::nullopt;
+    if (!std::isfinite(source)) return std::nullopt;
+    if constexpr (std::is_same_v<Source, float> && std::is_same_v<Target, int32_t>) {
+      if (source >= 2'147'483'648.0f || source <= -2'147'483'904.0f) return std::nullopt;
+    } else if constexpr (std::is_same_v<Source, double> && std::is_same_v<Target, int32_t>) {
+      if (source >= 2'147'483'648.0 || source <= -2'147'483'649.0) return std::nullopt;
+    } else if constexpr (std::is_same_v<Source, float> && std::is_same_v<Target, int64_t>) {
+      if (source >= 9'223'372'036'854'775'808.0f || source <= -9'223'373'136'366'403'584.0f) return std::nullopt;
+    } else {
+      if (source >= 9'223'372'036'854'775'808.0 || source <= -9'223'372'036'854'777'856.0) return std::nullopt;
+    }
+    return static_cast<Target>(source);
+  } else if constexpr (std::is_same_v<Source, float> && std::is_same_v<Target, double>) {
+    return static_cast<double>(source);                                         // (:149-154)
+  } else {
+    static_assert(std::is_same_v<Source, double> && std::is_same_v<Target, float>);
+    if (source > 340282346638528859811704183484516925440.0 || source < -340282346638528859811704183484516925440.0) {
+      return std::nullopt;                                                      // (:156-170)
+    }
+    const auto casted_source = static_cast<float>(source);
+    if (static_cast<double>(casted_source) == source) return casted_source;
+    return std::nullopt;
+  }
+}
+
+std::optional<float> next_float_towards(const double value, const double towards) {  // lossless_predicate_cast.cpp:14-38
+  if (value > 340282346638528859811704183484516925440.0 || value < -340282346638528859811704183484516925440.0) return std::nullopt;
+  if (value == towards) return std::nullopt;
+  const auto casted_value = static_cast<float>(value);
+  if ((static_cast<double>(casted_value) < value && towards < value) || (static_cast<double>(casted_value) > value && towards > value)) {
+    return casted_value;
+  }
+  const float next = std::nexttowardf(casted_value, static_cast<long double>(towards));
+  if (!std::isfinite(next)) return std::nullopt;
+  return next;
+}
+
+template <typename Output, typename Input>
+std::optional<std::pair<int32_t, Output>> predicate(const int32_t condition, const Input& input) {  // .hpp:20-62
+  if (const auto casted = lossless<Output>(input)) return std::make_pair(condition, *casted);
+  if (condition < HYB_PRED_EQUALS || condition > HYB_PRED_GREATER_THAN_EQUALS) return std::nullopt;
+  if constexpr (std::is_same_v<Input, double> && std::is_same_v<Output, float>) {
+    if (condition == HYB_PRED_EQUALS) return std::nullopt;
+    if (condition == HYB_PRED_LESS_THAN || condition == HYB_PRED_LESS_THAN_EQUALS) {
+      const auto adjusted = next_float_towards(input, std::numeric_limits<double>::lowest());
+      if (!adjusted) return std::nullopt;
+      return std::make_pair(int32_t{HYB_PRED_LESS_THAN_EQUALS}, *adjusted);
+    }
+    if (condition == HYB_PRED_GREATER_THAN || condition == HYB_PRED_GREATER_THAN_EQUALS) {
+      const auto adjusted = next_float_towards(input, std::numeric_limits<double>::max());
+      if (!adjusted) return std::nullopt;
+      return std::make_pair(int32_t{HYB_PRED_GREATER_THAN_EQUALS}, *adjusted);
+    }
+  }
+  return std::nullopt;
+}
+
+template <typename Output>
+void store(hyb_value* out, Output value) {
+  if constexpr (std::is_same_v<Output, int32_t>) out->i32 = value;
+  if constexpr (std::is_same_v<Output, int64_t>) out->i64 = value;
+  if constexpr (std::is_same_v<Output, float>) out->f32 = value;
+  if constexpr (std::is_same_v<Output, double>) out->f64 = value;
+}
+
+// lossless_predicate_variant_cast (.cpp:40-73): resolve the variant's type and the target type
+template <typename Input>
+bool variant_to(const int32_t condition, const Input& input, const int32_t target_type, int32_t* out_condition, hyb_value* out_value) {
+  const auto finish = [&](const auto& result) {
+    if (!result) return false;
+    *out_condition = result->first;
+    store(out_value, result->second);
+    return true;
+  };
+  switch (target_type) {
+    case HYB_TYPE_INT32:
+      return finish(predicate<int32_t>(condition, input));
+    case HYB_TYPE_INT64:
+      return finish(predicate<int64_t>(condition, input));
+    case HYB_TYPE_FLOAT32:
+      return finish(predicate<float>(condition, input));
+    case HYB_TYPE_FLOAT64:
+      return finish(predicate<double>(condition, input));
+    default:
+      return false;
+  }
+}
+
+bool variant(const int32_t condition, const int32_t source_type, const hyb_value& value, const int32_t target_type,
+             int32_t* out_condition, hyb_value* out_value) {
+  switch (source_type) {
+    case HYB_TYPE_INT32:
+      return variant_to(condition, value.i32, target_type, out_condition, out_value);
+    case HYB_TYPE_INT64:
+      return variant_to(condition, value.i64, target_type, out_condition, out_value);
+    case HYB_TYPE_FLOAT32:
+      return variant_to(condition, value.f32, target_type, out_condition, out_value);
+    case HYB_TYPE_FLOAT64:
+      return variant_to(condition, value.f64, target_type, out_condition, out_value);
+    default:
+      return false;
+  }
+}
+
+int32_t flip(const int32_t condition) {  // types.cpp:51-82 (-1: Fail("Can't flip ..."))
+  switch (condition) {
+    case HYB_PRED_EQUALS:
+    case HYB_PRED_NOT_EQUALS:
+      return condition;
+    case HYB_PRED_LESS_THAN:
+      return HYB_PRED_GREATER_THAN;
+    case HYB_PRED_LESS_THAN_EQUALS:
+      return HYB_PRED_GREATER_THAN_EQUALS;
+    case HYB_PRED_GREATER_THAN:
+      return HYB_PRED_LESS_THAN;
+    case HYB_PRED_GREATER_THAN_EQUALS:
+      return HYB_PRED_LESS_THAN_EQUALS;
+    default:
+      return -1;
+  }
+}
+
+}  // namespace predicate_cast
+
+// =====================================================================================================================
 extern "C" {
 
 const char* orc_last_error(void) { return g_error.c_str(); }
+
+int orc_next_float_towards(double value, double towards, float* out_value) {
+  const auto result = predicate_cast::next_float_towards(value, towards);
+  if (result) *out_value = *result;
+  return result ? 1 : 0;
+}
+
+// `column <condition> literal` (value_on_left == 0) or `literal <condition> column` (table_scan.cpp:340-366, :388-390).
+// Returns 1 and the condition / value ColumnVsValueTableScanImpl receives, 0 for "ExpressionEvaluator fallback".
+int orc_normalize_predicate(int32_t condition, int32_t literal_type, hyb_value literal, int32_t column_type, int32_t value_on_left,
+                            int32_t* out_condition, hyb_value* out_value) {
+  if (value_on_left) {
+    const int32_t flipped = predicate_cast::flip(condition);
+    if (flipped < 0) return 0;
+    int32_t adjusted = 0;
+    if (!predicate_cast::variant(flipped, literal_type, literal, column_type, &adjusted, out_value)) return 0;
+    // predicate_condition = flip(adjusted) (:350), then ColumnVsValueTableScanImpl(..., flip(predicate_condition), ...) (:389)
+    *out_condition = predicate_cast::flip(predicate_cast::flip(adjusted));
+    return 1;
+  }
+  return predicate_cast::variant(condition, literal_type, literal, column_type, out_condition, out_value) ? 1 : 0;
+}
+
+// BetweenExpression (table_scan.cpp:399-441): split, cast both bounds, reassemble.
+int orc_normalize_between(int32_t condition, int32_t lower_type, hyb_value lower, int32_t upper_type, hyb_value upper,
+                          int32_t column_type, int32_t* out_condition, hyb_value* out_lower, hyb_value* out_upper) {
+  int32_t lower_condition, upper_condition;
+  switch (condition) {  // between_to_conditions (types.cpp:119-132)
+    case HYB_PRED_BETWEEN_INCLUSIVE:
+      lower_condition = HYB_PRED_GREATER_THAN_EQUALS, upper_condition = HYB_PRED_LESS_THAN_EQUALS;
+      break;
+    case HYB_PRED_BETWEEN_LOWER_EXCLUSIVE:
+      lower_condition = HYB_PRED_GREATER_THAN, upper_condition = HYB_PRED_LESS_THAN_EQUALS;
+      break;
+    case HYB_PRED_BETWEEN_UPPER_EXCLUSIVE:
+      lower_condition = HYB_PRED_GREATER_THAN_EQUALS, upper_condition = HYB_PRED_LESS_THAN;
+      break;
+    case HYB_PRED_BETWEEN_EXCLUSIVE:
+      lower_condition = HYB_PRED_GREATER_THAN, upper_condition = HYB_PRED_LESS_THAN;
+      break;
+    default:
+      return 0;
+  }
+  if (!predicate_cast::variant(lower_condition, lower_type, lower, column_type, &lower_condition, out_lower)) return 0;
+  if (!predicate_cast::variant(upper_condition, upper_type, upper, column_type, &upper_condition, out_upper)) return 0;
+  // conditions_to_between (types.cpp:134-153)
+  if (lower_condition == HYB_PRED_GREATER_THAN) {
+    if (upper_condition == HYB_PRED_LESS_THAN) *out_condition = HYB_PRED_BETWEEN_EXCLUSIVE;
+    else if (upper_condition == HYB_PRED_LESS_THAN_EQUALS) *out_condition = HYB_PRED_BETWEEN_LOWER_EXCLUSIVE;
+    else return 0;
+  } else if (lower_condition == HYB_PRED_GREATER_THAN_EQUALS) {
+    if (upper_condition == HYB_PRED_LESS_THAN) *out_condition = HYB_PRED_BETWEEN_UPPER_EXCLUSIVE;
+    else if (upper_condition == HYB_PRED_LESS_THAN_EQUALS) *out_condition = HYB_PRED_BETWEEN_INCLUSIVE;
+    else return 0;
+  } else {
+    return 0;
+  }
+  return 1;
+}
 
 // DictionaryEncoder::on_encode (dictionary_encoder.hpp:33-103)
 int orc_encode_dictionary(int32_t data_type, const void* values, const uint8_t* nulls, uint32_t n, void* out_dictionary,

@@ -100,6 +100,13 @@ int orc_aggregate_hash(const hyb_table_view* table, const hyb_aggregate_query* q
                        int32_t threads, int32_t parallel, orc_aggregate_result* out);
 void orc_aggregate_result_free(orc_aggregate_result* result);
 
+/* ---- predicate normalisation (lossless_predicate_cast.hpp/.cpp, lossless_cast.hpp, types.cpp, table_scan.cpp:340-441) -- */
+int orc_next_float_towards(double value, double towards, float* out_value); /* 1 = has a value */
+int orc_normalize_predicate(int32_t condition, int32_t literal_type, hyb_value literal, int32_t column_type,
+                            int32_t value_on_left, int32_t* out_condition, hyb_value* out_value);
+int orc_normalize_between(int32_t condition, int32_t lower_type, hyb_value lower, int32_t upper_type, hyb_value upper,
+                          int32_t column_type, int32_t* out_condition, hyb_value* out_lower, hyb_value* out_upper);
+
 const char* orc_last_error(void);
 
 #ifdef __cplusplus

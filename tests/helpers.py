@@ -229,3 +229,66 @@ def assert_aggregate_outputs_equal(device_output, oracle_output, rel=1e-6) -> No
             assert np.array_equal(got[valid], want[valid]), f"aggregate {index}: {got} != {want}"
         else:
             assert np.allclose(got[valid], want[valid], rtol=rel, atol=0.0), f"aggregate {index}: {got} != {want}"
+
+
+# ---- table_scan_between_test.cpp: the parameterised fixture (:43-96) and the literal expectations (:194-243) ------------
+BETWEEN_CASES = {
+    "BetweenInclusive": [
+        (12.25, 16.25, [1, 2, 3]), (12.0, 16.25, [1, 2, 3]), (12.25, 16.75, [1, 2, 3]), (12.0, 16.75, [1, 2, 3]),
+        (0.0, 16.75, [0, 1, 2, 3]), (16.0, 50.75, [3, 4, 5, 6, 7, 8, 9, 10]), (13.0, 16.25, [2, 3]), (12.25, 15.0, [1, 2]),
+        (0.25, 50.75, [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10]), (0.25, 0.75, []),
+    ],
+    "BetweenLowerExclusive": [(11.0, 16.25, [1, 2, 3]), (12.25, 16.25, [2, 3]), (13.0, 16.25, [2, 3])],
+    "BetweenUpperExclusive": [(12.25, 17.0, [1, 2, 3]), (12.25, 16.25, [1, 2]), (12.25, 15.0, [1, 2])],
+    "BetweenExclusive": [(12.25, 16.25, [2]), (11.0, 16.25, [1, 2]), (12.25, 17.0, [2, 3]), (11.0, 17.0, [1, 2, 3]),
+                         (13.0, 16.25, [2]), (12.25, 15.0, [2]), (13.0, 15.0, [2])],
+}
+BETWEEN_CONDITIONS = {"BetweenInclusive": capi.PRED_BETWEEN_INCLUSIVE, "BetweenLowerExclusive": capi.PRED_BETWEEN_LOWER_EXCLUSIVE,
+                      "BetweenUpperExclusive": capi.PRED_BETWEEN_UPPER_EXCLUSIVE, "BetweenExclusive": capi.PRED_BETWEEN_EXCLUSIVE}
+
+
+def between_fixture(data_type: int, encoding: str, sort_mode: str | None, nullable: bool) -> Table:
+    """SetUp (:43-96): column a = static_cast<Type>(10.25 + 2 i) (30.25 - 2 i when descending), column b = row index; with a
+    sort mode three NULL rows are prepended, without one every third value is NULL; chunk size 6, the two full chunks
+    encoded, the open one left unencoded."""
+    numpy_type = {capi.TYPE_INT32: np.int32, capi.TYPE_INT64: np.int64, capi.TYPE_FLOAT32: np.float32,
+                  capi.TYPE_FLOAT64: np.float64}[data_type]
+    number_of_nulls = 3 if (nullable and sort_mode) else 0
+    values, nulls, index = [], [], []
+    for i in range(number_of_nulls):
+        values.append(0)
+        nulls.append(True)
+        index.append(i)
+    for i in range(11):
+        double_value = 30.25 - i * 2.0 if sort_mode == "descending" else 10.25 + i * 2.0
+        is_null = nullable and not sort_mode and i % 3 == 2
+        values.append(0 if is_null else (int(double_value) if data_type in (capi.TYPE_INT32, capi.TYPE_INT64) else double_value))
+        nulls.append(is_null)
+        index.append(i + number_of_nulls)
+    definitions = [ColumnDefinition("a", data_type, nullable), ColumnDefinition("b", capi.TYPE_INT32, nullable)]
+    null_arrays = [np.array(nulls, dtype=bool), np.zeros(len(values), dtype=bool)] if nullable else None
+    table = Table.from_columns(definitions, [np.array(values, dtype=numpy_type), np.array(index, dtype=np.int32)], null_arrays,
+                               chunk_size=6)
+    full_chunks = [chunk for chunk in range(table.chunk_count) if table.get_chunk(chunk).size == 6][:2]
+    table.encode([encoding, "Unencoded"], full_chunks)
+    return table
+
+
+def between_expected(expected_with_null: list[int], sort_mode: str | None, nullable: bool) -> list[int]:
+    """The index transformation of _test_between_scan (:155-186)."""
+    number_of_nulls = 3 if (nullable and sort_mode) else 0
+    expected = list(expected_with_null)
+    if sort_mode == "descending":
+        expected = sorted((10 + number_of_nulls) - e for e in expected)
+    if sort_mode == "ascending":
+        expected = [e + number_of_nulls for e in expected]
+    if nullable and not sort_mode:
+        expected = [e for e in expected if e % 3 != 2]
+    return expected
+
+
+def between_bounds(data_type: int, left: float, right: float):
+    """static_cast<ColumnDataType>(double) of both bounds (:133-134)."""
+    if data_type in (capi.TYPE_INT32, capi.TYPE_INT64):
+        return int(left), int(right)
+    return left, right

@@ -171,3 +171,32 @@ def test_large_column_properties(device):
     complement = device.table_scan(device_table, Predicate(0, P.PRED_GREATER_THAN_EQUALS, 1095))
     assert complement.info()[0] + len(rows_out) == rows
     device_table.drop()
+
+
+@pytest.mark.parametrize("bulk", ["1", "0"])
+def test_between_reference_fixture(device, bulk):
+    """table_scan_between_test.cpp:194-243 on the fixture of :43-96 (types x encodings x sort modes x nullability), with and
+    without the cp.async.bulk staged kernel: the literal expectations of the reference, and the oracle's PosLists."""
+    from helpers import BETWEEN_CASES, BETWEEN_CONDITIONS, between_bounds, between_expected, between_fixture, column_values_at
+
+    device.set_option("scan_bulk", bulk)
+    try:
+        for data_type in (capi.TYPE_INT32, capi.TYPE_INT64, capi.TYPE_FLOAT32, capi.TYPE_FLOAT64):
+            for encoding in ENCODINGS:
+                if encoding == "FrameOfReference" and data_type != capi.TYPE_INT32:
+                    continue
+                for sort_mode in (None, "ascending", "descending"):
+                    for nullable in (False, True):
+                        table = between_fixture(data_type, encoding, sort_mode, nullable)
+                        device_table = device.upload(table)
+                        for name, cases in BETWEEN_CASES.items():
+                            for left, right, expected_with_null in cases:
+                                lower, upper = between_bounds(data_type, left, right)
+                                predicate = Predicate(0, BETWEEN_CONDITIONS[name], lower, upper)
+                                result, _ = check_scan(device, table, device_table, predicate)
+                                values = sorted(column_values_at(table, 1, result.to_host()))
+                                assert values == between_expected(expected_with_null, sort_mode, nullable), (name, left, right)
+                                result.free()
+                        device_table.drop()
+    finally:
+        device.set_option("scan_bulk", "1")
