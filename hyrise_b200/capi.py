@@ -111,6 +111,12 @@ class AggregateQuery(C.Structure):
     ]
 
 
+class DistributedStats(C.Structure):
+    _fields_ = [("split_count_ms", C.c_float), ("count_wait_ms", C.c_float), ("push_ms", C.c_float),
+                ("done_wait_ms", C.c_float), ("local_ms", C.c_float), ("finish_ms", C.c_float),
+                ("tuples_sent", C.c_uint64), ("tuples_received", C.c_uint64), ("nvlink_bytes", C.c_uint64)]
+
+
 class OperatorStats(C.Structure):
     _fields_ = [
         ("device_ms", C.c_float),
@@ -171,6 +177,12 @@ SYMBOLS = {
     "hyb_exchange_arena_open": [_CTX, _P, C.POINTER(_P)],
     "hyb_exchange_arena_close": [_CTX, _P],
     "hyb_exchange_arena_destroy": [_CTX, _P],
+    "hyb_peer_group_create": [_CTX, _U32, _U32, _U64, _P, C.POINTER(_U64)],
+    "hyb_peer_group_connect": [_CTX, _U64, _P],
+    "hyb_peer_group_destroy": [_CTX, _U64],
+    "hyb_join_hash_distributed": [_CTX, _U64, C.POINTER(JoinSide), C.POINTER(JoinSide), _U32, _U32, _I32, C.POINTER(_U64)],
+    "hyb_aggregate_hash_distributed": [_CTX, _U64, C.POINTER(AggregateQuery), _U32, _U64, C.POINTER(_U64)],
+    "hyb_peer_group_stats": [_CTX, _U64, C.POINTER(DistributedStats)],
     "hyb_aggregate_hash": [_CTX, C.POINTER(AggregateQuery), C.POINTER(_U64)],
     "hyb_aggregate_result_info": [_CTX, _U64, C.POINTER(_U64), C.POINTER(_I32)],
     "hyb_aggregate_result_row_ids": [_CTX, _U64, _P],

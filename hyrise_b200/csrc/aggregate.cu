@@ -28,6 +28,7 @@
 #include "bulk_copy.cuh"
 #include "device_utils.cuh"
 #include "internal.hpp"
+#include "peer.hpp"
 #include "predicate.cuh"
 
 namespace hyb {
@@ -1195,6 +1196,15 @@ struct HostGroup {
   uint64_t max_position = 0;
   std::vector<uint64_t> accumulators;  // per aggregate (bits)
   std::vector<uint64_t> counts;        // per aggregate
+  // distributed aggregation: positions are global and the rows behind them are named directly (they may live on another rank)
+  bool has_global_rows = false;
+  hyb_row_id row_min{}, row_max{};
+};
+
+struct AggregateExchange {
+  PeerGroup* group;
+  uint32_t chunk_id_base;
+  uint64_t position_base;
 };
 
 static int expression_type(const Table* table, const hyb_aggregate_def& def, int32_t* out_type) {
@@ -1565,17 +1575,16 @@ using namespace hyb;
 
 extern "C" {
 
-int hyb_aggregate_hash(hyb_context* context, const hyb_aggregate_query* query, hyb_aggregate_result_t* out_result) {
-  HYB_CHECK(context && query && out_result, HYB_ERR_INVALID, "NULL argument");
-  *out_result = 0;
-  HYB_CHECK(query->groupby_count <= HYB_MAX_GROUPBY_COLUMNS, HYB_ERR_UNSUPPORTED, "too many group-by columns");
-  HYB_CHECK(query->aggregate_count <= HYB_MAX_AGGREGATES, HYB_ERR_UNSUPPORTED, "too many aggregates");
-  HYB_CHECK(query->predicate_count <= HYB_MAX_FUSED_PREDICATES, HYB_ERR_UNSUPPORTED, "too many fused predicates");
-  HYB_CHECK(query->groupby_count == 0 || query->groupby_column_ids, HYB_ERR_INVALID, "groupby_column_ids is NULL");
-  HYB_CHECK(query->aggregate_count == 0 || query->aggregates, HYB_ERR_INVALID, "aggregates is NULL");
-  HYB_CHECK(query->predicate_count == 0 || query->predicates, HYB_ERR_INVALID, "predicates is NULL");
-  DeviceGuard guard(context->device);
-  std::lock_guard<std::mutex> lock(context->mutex);
+}  // extern "C"
+
+static int exchange_partial_groups(hyb_context* context, const AggregateExchange& exchange, const Table* table,
+                                   const hyb_aggregate_query* query, const std::vector<int32_t>& input_types,
+                                   std::vector<HostGroup>* groups);
+
+// hyb_aggregate_hash with context->mutex held. `exchange` != nullptr: the groups of this rank are partial; they are
+// exchanged with the peer group's ranks and merged before the result is ordered and materialised.
+static int aggregate_hash_locked(hyb_context* context, const hyb_aggregate_query* query, hyb_aggregate_result_t* out_result,
+                                 const AggregateExchange* exchange) {
   auto* table = find_table(context, query->table);
   HYB_CHECK(table, HYB_ERR_NOT_FOUND, "unknown table handle");
   PosList* filter = nullptr;
@@ -2042,6 +2051,11 @@ int hyb_aggregate_hash(hyb_context* context, const hyb_aggregate_query* query, h
   }
   release_tests();
 
+  if (exchange) {
+    HYB_CHECK(!filter, HYB_ERR_UNSUPPORTED, "distributed aggregation of position-filtered inputs is not on the GPU path");
+    HYB_TRY(exchange_partial_groups(context, *exchange, table, query, input_types, &groups));
+  }
+
   // ---- order the groups like the reference and materialise the result ---------------------------------------------
   uint64_t input_rows = 0;
   for (const auto& group : groups) input_rows += group.rows;
@@ -2096,6 +2110,8 @@ int hyb_aggregate_hash(hyb_context* context, const hyb_aggregate_query* query, h
       device_free(context, d_positions);
       device_free(context, d_rows);
       ++launches;
+    } else if (exchange) {
+      for (size_t g = 0; g < groups.size(); ++g) result->row_ids[g] = immediate ? groups[g].row_max : groups[g].row_min;
     } else {
       for (size_t g = 0; g < groups.size(); ++g) result->row_ids[g] = position_to_row_id_host(table, positions[g]);
     }
@@ -2170,6 +2186,218 @@ int hyb_aggregate_hash(hyb_context* context, const hyb_aggregate_query* query, h
   context->aggregate_results.emplace(handle, std::move(result));
   *out_result = handle;
   return HYB_OK;
+}
+
+// ---- distributed aggregation: partial groups through the peer arenas ------------------------------------------------------
+namespace {
+
+__global__ void peer_raise_flags_kernel(unsigned long long* const* flags, uint32_t world, unsigned long long epoch) {
+  __threadfence_system();
+  if (threadIdx.x < world) st_volatile_u64(flags[threadIdx.x], epoch);
+}
+
+struct PartialGroupRecord {  // fixed-size wire format of one partial group
+  uint64_t key[kMaxKeyWords];
+  uint64_t rows, min_position, max_position;
+  hyb_row_id row_min, row_max;
+  uint32_t null_mask, pad;
+  uint64_t accumulators[HYB_MAX_AGGREGATES];
+  uint64_t counts[HYB_MAX_AGGREGATES];
+};
+
+void merge_accumulator(int32_t function, bool integral, uint64_t* target, uint64_t* target_count, uint64_t source,
+                       uint64_t source_count) {
+  const auto as_double = [](uint64_t bits) {
+    double value;
+    std::memcpy(&value, &bits, sizeof(value));
+    return value;
+  };
+  const auto from_double = [](double value) {
+    uint64_t bits;
+    std::memcpy(&bits, &value, sizeof(bits));
+    return bits;
+  };
+  switch (function) {
+    case HYB_AGG_SUM:
+    case HYB_AGG_AVG:  // travels as SUM + COUNT
+      if (source_count) {
+        if (integral) {
+          *target = static_cast<uint64_t>(static_cast<int64_t>(*target) + static_cast<int64_t>(source));
+        } else {
+          *target = *target_count ? from_double(as_double(*target) + as_double(source)) : source;
+        }
+      }
+      break;
+    case HYB_AGG_MIN:
+    case HYB_AGG_MAX:
+      if (source_count) {
+        bool take = *target_count == 0;
+        if (!take) {
+          if (integral) {
+            take = function == HYB_AGG_MIN ? static_cast<int64_t>(source) < static_cast<int64_t>(*target)
+                                           : static_cast<int64_t>(source) > static_cast<int64_t>(*target);
+          } else {
+            take = function == HYB_AGG_MIN ? as_double(source) < as_double(*target) : as_double(source) > as_double(*target);
+          }
+        }
+        if (take) *target = source;
+      }
+      break;
+    default:  // COUNT, COUNT(*): the counts are the values
+      break;
+  }
+  *target_count += source_count;
+}
+
+}  // namespace
+
+static int exchange_partial_groups(hyb_context* context, const AggregateExchange& exchange, const Table* table,
+                                   const hyb_aggregate_query* query, const std::vector<int32_t>& input_types,
+                                   std::vector<HostGroup>* groups) {
+  PeerGroup* group = exchange.group;
+  const uint32_t world = group->world, rank = group->rank;
+  const uint32_t aggregate_count = query->aggregate_count;
+  cudaStream_t stream = context->stream;
+  const unsigned long long epoch = peer_next_epoch(group);
+  HYB_CUDA(cudaEventRecord(group->events[5], stream));  // local pre-aggregation ended (events[0..4] at the caller)
+
+  // ---- serialise this rank's partial groups (positions and representative rows made global) -----------------------------
+  const size_t capacity = (kPeerAggregateBlockBytes - 16) / sizeof(PartialGroupRecord);
+  HYB_CHECK(groups->size() <= capacity, HYB_ERR_UNSUPPORTED,
+            std::to_string(groups->size()) + " partial groups exceed the " + std::to_string(capacity) +
+                " the low-cardinality exchange carries per rank");
+  std::vector<unsigned char> block(kPeerAggregateBlockBytes, 0);
+  const uint64_t header[2] = {groups->size(), aggregate_count};
+  std::memcpy(block.data(), header, sizeof(header));
+  auto* records = reinterpret_cast<PartialGroupRecord*>(block.data() + 16);
+  for (size_t g = 0; g < groups->size(); ++g) {
+    const HostGroup& source = (*groups)[g];
+    PartialGroupRecord& record = records[g];
+    for (size_t w = 0; w < kMaxKeyWords; ++w) record.key[w] = w < source.key.size() ? source.key[w] : 0;
+    record.rows = source.rows;
+    record.null_mask = source.null_mask;
+    record.row_min = position_to_row_id_host(table, source.min_position);
+    record.row_max = position_to_row_id_host(table, source.max_position);
+    record.row_min.chunk_id += exchange.chunk_id_base;
+    record.row_max.chunk_id += exchange.chunk_id_base;
+    record.min_position = source.min_position + exchange.position_base;
+    record.max_position = source.max_position + exchange.position_base;
+    for (uint32_t a = 0; a < aggregate_count; ++a) {
+      record.accumulators[a] = source.accumulators[a];
+      record.counts[a] = source.counts[a];
+    }
+  }
+  const size_t used_bytes = 16 + groups->size() * sizeof(PartialGroupRecord);
+
+  // ---- store the block into every rank's arena, raise the flags, wait for everybody's ------------------------------------
+  DeviceScratch scratch(context);
+  void* staged = nullptr;
+  HYB_TRY(scratch.alloc(kPeerAggregateBlockBytes, &staged));
+  HYB_CUDA(cudaMemcpyAsync(staged, block.data(), used_bytes, cudaMemcpyHostToDevice, stream));
+  unsigned long long* host_flags[kPeerMax] = {};
+  for (uint32_t peer = 0; peer < world; ++peer) {
+    HYB_CUDA(cudaMemcpyAsync(group->control(peer)->aggregate_block[rank], staged, used_bytes, cudaMemcpyDefault, stream));
+    host_flags[peer] = &group->control(peer)->aggregate_flag[rank];
+  }
+  unsigned long long** flags = nullptr;
+  HYB_TRY(scratch.alloc_array(kPeerMax, &flags));
+  HYB_CUDA(cudaMemcpyAsync(flags, host_flags, sizeof(host_flags), cudaMemcpyHostToDevice, stream));
+  peer_raise_flags_kernel<<<1, 32, 0, stream>>>(flags, world, epoch);
+  HYB_CUDA(cudaGetLastError());
+  HYB_TRY(peer_wait(context, group->control(rank)->aggregate_flag, world, epoch));
+  std::vector<unsigned char> all(size_t{world} * kPeerAggregateBlockBytes);
+  HYB_CUDA(cudaMemcpyAsync(all.data(), group->control(rank)->aggregate_block, all.size(), cudaMemcpyDeviceToHost, stream));
+  HYB_CUDA(cudaEventRecord(group->events[6], stream));
+  HYB_CUDA(cudaStreamSynchronize(stream));
+  group->stats.nvlink_bytes = used_bytes * (world - 1);
+
+  // ---- merge in rank order (every rank computes the same complete result) ---------------------------------------------------
+  std::vector<HostGroup> merged;
+  for (uint32_t source_rank = 0; source_rank < world; ++source_rank) {
+    const unsigned char* base = all.data() + size_t{source_rank} * kPeerAggregateBlockBytes;
+    uint64_t source_header[2];
+    std::memcpy(source_header, base, sizeof(source_header));
+    HYB_CHECK(source_header[0] <= capacity && source_header[1] == aggregate_count, HYB_ERR_INVALID,
+              "rank " + std::to_string(source_rank) + " sent a partial-group block of another query");
+    const auto* source_records = reinterpret_cast<const PartialGroupRecord*>(base + 16);
+    for (uint64_t g = 0; g < source_header[0]; ++g) {
+      const PartialGroupRecord& record = source_records[g];
+      const size_t key_words = std::max<uint32_t>(query->groupby_count, 1);
+      HostGroup* target = nullptr;
+      for (auto& candidate : merged) {
+        if (candidate.null_mask == record.null_mask && std::equal(candidate.key.begin(), candidate.key.end(), record.key)) {
+          target = &candidate;
+          break;
+        }
+      }
+      if (!target) {
+        merged.emplace_back();
+        target = &merged.back();
+        target->key.assign(record.key, record.key + key_words);
+        target->null_mask = record.null_mask;
+        target->accumulators.assign(aggregate_count, 0);
+        target->counts.assign(aggregate_count, 0);
+        target->has_global_rows = true;
+        target->min_position = ~uint64_t{0};
+        target->max_position = 0;
+      }
+      if (record.rows) {
+        if (record.min_position < target->min_position || target->rows == 0) {
+          target->min_position = record.min_position;
+          target->row_min = record.row_min;
+        }
+        if (record.max_position >= target->max_position || target->rows == 0) {
+          target->max_position = record.max_position;
+          target->row_max = record.row_max;
+        }
+      }
+      target->rows += record.rows;
+      for (uint32_t a = 0; a < aggregate_count; ++a) {
+        const int32_t function = query->aggregates[a].function;
+        const bool integral = input_types[a] == HYB_TYPE_INT32 || input_types[a] == HYB_TYPE_INT64;
+        merge_accumulator(function, integral, &target->accumulators[a], &target->counts[a], record.accumulators[a], record.counts[a]);
+      }
+    }
+  }
+  *groups = std::move(merged);
+  return HYB_OK;
+}
+
+extern "C" {
+
+int hyb_aggregate_hash(hyb_context* context, const hyb_aggregate_query* query, hyb_aggregate_result_t* out_result) {
+  HYB_CHECK(context && query && out_result, HYB_ERR_INVALID, "NULL argument");
+  *out_result = 0;
+  HYB_CHECK(query->groupby_count <= HYB_MAX_GROUPBY_COLUMNS, HYB_ERR_UNSUPPORTED, "too many group-by columns");
+  HYB_CHECK(query->aggregate_count <= HYB_MAX_AGGREGATES, HYB_ERR_UNSUPPORTED, "too many aggregates");
+  HYB_CHECK(query->predicate_count <= HYB_MAX_FUSED_PREDICATES, HYB_ERR_UNSUPPORTED, "too many fused predicates");
+  HYB_CHECK(query->groupby_count == 0 || query->groupby_column_ids, HYB_ERR_INVALID, "groupby_column_ids is NULL");
+  HYB_CHECK(query->aggregate_count == 0 || query->aggregates, HYB_ERR_INVALID, "aggregates is NULL");
+  HYB_CHECK(query->predicate_count == 0 || query->predicates, HYB_ERR_INVALID, "predicates is NULL");
+  DeviceGuard guard(context->device);
+  std::lock_guard<std::mutex> lock(context->mutex);
+  return aggregate_hash_locked(context, query, out_result, nullptr);
+}
+
+int hyb_aggregate_hash_distributed(hyb_context* context, hyb_peer_group_t group_handle, const hyb_aggregate_query* query,
+                                   uint32_t chunk_id_base, uint64_t position_base, hyb_aggregate_result_t* out_result) {
+  HYB_CHECK(context && query && out_result, HYB_ERR_INVALID, "NULL argument");
+  *out_result = 0;
+  HYB_CHECK(query->groupby_count <= HYB_MAX_GROUPBY_COLUMNS, HYB_ERR_UNSUPPORTED, "too many group-by columns");
+  HYB_CHECK(query->aggregate_count <= HYB_MAX_AGGREGATES, HYB_ERR_UNSUPPORTED, "too many aggregates");
+  HYB_CHECK(query->predicate_count <= HYB_MAX_FUSED_PREDICATES, HYB_ERR_UNSUPPORTED, "too many fused predicates");
+  HYB_CHECK(query->groupby_count == 0 || query->groupby_column_ids, HYB_ERR_INVALID, "groupby_column_ids is NULL");
+  HYB_CHECK(query->aggregate_count == 0 || query->aggregates, HYB_ERR_INVALID, "aggregates is NULL");
+  HYB_CHECK(query->predicate_count == 0 || query->predicates, HYB_ERR_INVALID, "predicates is NULL");
+  DeviceGuard guard(context->device);
+  std::lock_guard<std::mutex> lock(context->mutex);
+  PeerGroup* group = find_peer_group(context, group_handle);
+  HYB_CHECK(group, HYB_ERR_NOT_FOUND, "unknown peer group handle");
+  HYB_CHECK(group->connected || group->world == 1, HYB_ERR_INVALID, "peer group is not connected");
+  group->stats = hyb_distributed_stats{};
+  for (int event = 0; event < 5; ++event) HYB_CUDA(cudaEventRecord(group->events[event], context->stream));
+  const AggregateExchange exchange{group, chunk_id_base, position_base};
+  return aggregate_hash_locked(context, query, out_result, &exchange);
 }
 
 static AggregateResult* find_aggregate_result(hyb_context* context, hyb_aggregate_result_t handle) {

@@ -160,6 +160,15 @@ void device_cache_destroy(hyb_context* context) {
 int sync_table_descriptors(hyb_context* context, Table* table) {
   if (!table->dirty) return HYB_OK;
   const uint32_t chunk_count = table->chunk_count();
+  if (table->fixed_single_chunk_capacity && table->d_segments) {
+    // only the row count changed: patch the descriptor (stream-ordered; the sources are members that outlive the copies'
+    // staging) and keep the tile maps
+    HYB_CUDA(cudaMemcpyAsync(table->d_segments, table->segments.data(), sizeof(DevSegment), cudaMemcpyHostToDevice, context->stream));
+    HYB_CUDA(cudaMemcpyAsync(table->d_chunk_row_start, table->chunk_row_start.data(), 2 * sizeof(uint64_t), cudaMemcpyHostToDevice,
+                             context->stream));
+    table->dirty = false;
+    return HYB_OK;
+  }
   if (table->d_chunk_capacity < chunk_count || !table->d_segments) {
     // Descriptor arrays are read by kernels already queued on the stream: wait before replacing them.
     HYB_CUDA(cudaStreamSynchronize(context->stream));
@@ -194,12 +203,17 @@ int sync_table_descriptors(hyb_context* context, Table* table) {
 int get_tile_map(hyb_context* context, Table* table, uint32_t tile_rows, const uint2** out_device,
                  uint32_t* out_tile_count) {
   auto it = table->d_tile_maps.find(tile_rows);
+  if (it != table->d_tile_maps.end() && table->fixed_single_chunk_capacity) {
+    *out_device = it->second.first;
+    *out_tile_count = (table->chunk_rows[0] + tile_rows - 1) / tile_rows;  // the map covers the whole capacity
+    return HYB_OK;
+  }
   if (it == table->d_tile_maps.end()) {
     // One entry per tile: {chunk, first row | last-tile-of-chunk flag in bit 31}. Tiles never straddle chunks.
     std::vector<uint2> map;
     const uint32_t chunk_count = table->chunk_count();
     for (uint32_t chunk = 0; chunk < chunk_count; ++chunk) {
-      const uint32_t rows = table->chunk_rows[chunk];
+      const uint32_t rows = table->fixed_single_chunk_capacity ? table->fixed_single_chunk_capacity : table->chunk_rows[chunk];
       for (uint32_t row0 = 0; row0 < rows; row0 += tile_rows) {
         const bool last = row0 + tile_rows >= rows;
         map.push_back(make_uint2(chunk, row0 | (last ? 0x80000000u : 0u)));
@@ -213,7 +227,7 @@ int get_tile_map(hyb_context* context, Table* table, uint32_t tile_rows, const u
     it = table->d_tile_maps.emplace(tile_rows, std::make_pair(device, static_cast<uint32_t>(map.size()))).first;
   }
   *out_device = it->second.first;
-  *out_tile_count = it->second.second;
+  *out_tile_count = table->fixed_single_chunk_capacity ? (table->chunk_rows[0] + tile_rows - 1) / tile_rows : it->second.second;
   return HYB_OK;
 }
 
@@ -428,6 +442,7 @@ int hyb_context_destroy(hyb_context* context) {
   {
     DeviceGuard guard(context->device);
     cudaStreamSynchronize(context->stream);
+    context->peer_groups.clear();
     context->pos_lists.clear();
     context->join_results.clear();
     context->aggregate_results.clear();

@@ -106,6 +106,9 @@ struct Table {
   // Largest chunk and whether all chunks but the last share one size (lets kernels divide instead of search).
   uint32_t max_chunk_rows = 0;
   bool uniform_chunks = true;
+  // > 0: a one-chunk table over a fixed device buffer whose row count changes between calls (the receive regions of a peer
+  // group): descriptors are patched in place and tile maps are built once, for this many rows.
+  uint32_t fixed_single_chunk_capacity = 0;
   ~Table();
 };
 
@@ -196,9 +199,14 @@ struct ContextOptions {
 };
 }  // namespace hyb
 
+namespace hyb {
+struct PeerGroup;
+}
+
 struct hyb_context {
   int device = 0;
   hyb::ContextOptions options;
+  std::unordered_map<uint64_t, std::shared_ptr<hyb::PeerGroup>> peer_groups;
   cudaStream_t stream = nullptr;
   int sm_count = 148;
   std::mutex mutex;  // serialises enqueue + registry access; device work itself is asynchronous

@@ -31,6 +31,7 @@
 
 #include "device_utils.cuh"
 #include "internal.hpp"
+#include "peer.hpp"
 
 namespace hyb {
 
@@ -637,7 +638,29 @@ struct ProbeParams {
   long long* peer_keys[kMaxPeers];
   long long* peer_rows[kMaxPeers];
   uint32_t push_to_peers;
+  // hyb_join_hash_distributed: the LAST CTA of the push kernels (both sides share the arrival counter) raises this rank's
+  // done flag in every peer's control block, after a system-scope fence that orders it behind all tuple stores.
+  unsigned int* signal_arrivals;
+  uint32_t signal_expected;
+  uint32_t signal_world;
+  unsigned long long signal_epoch;
+  unsigned long long* signal_flags[kMaxPeers];
 };
+
+__device__ __forceinline__ void peer_signal_when_last(const ProbeParams& params) {
+  if (!params.signal_arrivals) return;
+  __threadfence_system();  // this thread's peer stores are performed system-wide before the CTA counts itself in
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int ticket = atomicAdd(params.signal_arrivals, 1u);
+    if (ticket + 1 == params.signal_expected) {
+      __threadfence_system();
+      for (uint32_t peer = 0; peer < params.signal_world; ++peer) st_volatile_u64(params.signal_flags[peer], params.signal_epoch);
+    }
+  }
+}
+
+__global__ void peer_signal_kernel(const ProbeParams params) { peer_signal_when_last(params); }
 
 // What one probe row contributes. Returns the match word: a build position (unique build side), a table slot
 // (duplicate build keys), kEmitWithoutPartner (one output row without a build partner) or kNoMatch (no output row).
@@ -1462,6 +1485,7 @@ __global__ void __launch_bounds__(kJoinThreads, 3) join_partition_write_kernel(c
     }
     __syncthreads();
   }
+  peer_signal_when_last(params);
 }
 
 // Multi-GPU exchange payload: {key, packed global RowID} per position; NULL keys are marked with RowID -1.
@@ -1626,15 +1650,11 @@ using namespace hyb;
 
 extern "C" {
 
-int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const hyb_join_side* probe_side, int32_t mode,
-                  int32_t radix_bits, hyb_join_result_t* out_result) {
-  HYB_CHECK(context && build_side && probe_side && out_result, HYB_ERR_INVALID, "NULL argument");
-  *out_result = 0;
-  HYB_CHECK(mode == HYB_JOIN_INNER || mode == HYB_JOIN_LEFT || mode == HYB_JOIN_RIGHT || mode == HYB_JOIN_SEMI ||
-                mode == HYB_JOIN_ANTI_NULL_AS_TRUE || mode == HYB_JOIN_ANTI_NULL_AS_FALSE,
-            HYB_ERR_UNSUPPORTED, "JoinMode not supported by JoinHash");
-  DeviceGuard guard(context->device);
-  std::lock_guard<std::mutex> lock(context->mutex);
+}  // extern "C"
+
+// hyb_join_hash with context->mutex held (hyb_join_hash_distributed joins the received tuples through it).
+static int join_hash_locked(hyb_context* context, const hyb_join_side* build_side, const hyb_join_side* probe_side, int32_t mode,
+                            int32_t radix_bits, hyb_join_result_t* out_result) {
   SideInfo build, probe;
   HYB_TRY(prepare_side(context, build_side, &build));
   HYB_TRY(prepare_side(context, probe_side, &probe));
@@ -1949,6 +1969,20 @@ int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const h
   return HYB_OK;
 }
 
+extern "C" {
+
+int hyb_join_hash(hyb_context* context, const hyb_join_side* build_side, const hyb_join_side* probe_side, int32_t mode,
+                  int32_t radix_bits, hyb_join_result_t* out_result) {
+  HYB_CHECK(context && build_side && probe_side && out_result, HYB_ERR_INVALID, "NULL argument");
+  *out_result = 0;
+  HYB_CHECK(mode == HYB_JOIN_INNER || mode == HYB_JOIN_LEFT || mode == HYB_JOIN_RIGHT || mode == HYB_JOIN_SEMI ||
+                mode == HYB_JOIN_ANTI_NULL_AS_TRUE || mode == HYB_JOIN_ANTI_NULL_AS_FALSE,
+            HYB_ERR_UNSUPPORTED, "JoinMode not supported by JoinHash");
+  DeviceGuard guard(context->device);
+  std::lock_guard<std::mutex> lock(context->mutex);
+  return join_hash_locked(context, build_side, probe_side, mode, radix_bits, out_result);
+}
+
 int hyb_join_side_positions(hyb_context* context, const hyb_join_side* side, uint64_t* out_positions) {
   HYB_CHECK(context && side && out_positions, HYB_ERR_INVALID, "NULL argument");
   DeviceGuard guard(context->device);
@@ -2102,6 +2136,290 @@ int hyb_join_partition_push(hyb_context* context, const hyb_join_side* side, uin
   HYB_CHECK(context && side && exchange, HYB_ERR_INVALID, "NULL argument");
   return partition_side(context, side, world_size, chunk_id_base, nullptr, nullptr, nullptr, exchange, user);
 }
+
+}  // extern "C" (reopened below)
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Distributed Inner JoinHash over a peer group (peer.hpp). All of it is queued on the context stream; the host waits once,
+// for the world x world count matrix.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace hyb {
+
+// Writes this rank's per-destination tuple counts of both sides and its build-key statistics into EVERY rank's control
+// block (row `rank` of the count matrix), then — behind a system-scope fence — raises its count flag there.
+__global__ void peer_publish_counts_kernel(PeerControl* const* controls, uint32_t rank, uint32_t world, unsigned long long epoch,
+                                           const unsigned long long* build_offsets, const unsigned long long* probe_offsets,
+                                           long long key_min, long long key_max, long long key_count) {
+  const uint32_t peer = threadIdx.x / 32, lane = threadIdx.x & 31;
+  if (peer < world) {
+    PeerControl* control = controls[peer];
+    if (lane < world) {
+      control->counts[0][rank][lane] = build_offsets ? build_offsets[lane + 1] - build_offsets[lane] : 0ull;
+      control->counts[1][rank][lane] = probe_offsets ? probe_offsets[lane + 1] - probe_offsets[lane] : 0ull;
+    }
+    if (lane == 0) {
+      control->key_info[rank][0] = key_min;
+      control->key_info[rank][1] = key_max;
+      control->key_info[rank][2] = key_count;
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) st_volatile_u64(&control->count_flag[rank], epoch);
+  }
+}
+
+// Join result positions (RowIDs {0, index} into the received tuple tables) -> the global RowIDs that travelled with the keys.
+__global__ void peer_translate_kernel(hyb_row_id* __restrict__ rows, const hyb_row_id* __restrict__ received,
+                                      const unsigned long long* __restrict__ total) {
+  const unsigned long long count = *total;
+  for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; i < count;
+       i += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
+    const hyb_row_id position = rows[i];
+    const hyb_row_id global = received[position.chunk_offset];
+    st_stream_v2(rows + i, global.chunk_id, global.chunk_offset);
+  }
+}
+
+// The persistent one-chunk table over receive region `side` (ValueSegment<int64> of keys), resized to `rows`.
+static int received_table(hyb_context* context, PeerGroup* group, int side, uint64_t rows, hyb_table_t* out_handle) {
+  Table* table = nullptr;
+  if (!group->received[side]) {
+    auto created = std::make_unique<Table>();
+    created->column_count = 1;
+    created->column_types.assign(1, HYB_TYPE_INT64);
+    created->chunk_row_start = {0, 0};
+    created->chunk_rows = {0};
+    DevSegment segment{};
+    segment.values = group->region(group->rank, side == 0 ? 0 : 2);
+    segment.encoding = HYB_ENC_UNENCODED;
+    segment.data_type = HYB_TYPE_INT64;
+    segment.vector_type = HYB_VEC_NONE;
+    created->segments.push_back(segment);
+    created->fixed_single_chunk_capacity = static_cast<uint32_t>(std::min<uint64_t>(group->capacity, 0xFFFFFFF0ull));
+    table = created.get();
+    group->received[side] = context->next_handle++;
+    context->tables.emplace(group->received[side], std::move(created));
+  } else {
+    table = find_table(context, group->received[side]);
+  }
+  table->segments[0].row_count = static_cast<uint32_t>(rows);
+  table->chunk_rows[0] = static_cast<uint32_t>(rows);
+  table->chunk_row_start[1] = rows;
+  table->max_chunk_rows = static_cast<uint32_t>(rows);
+  table->uniform_chunks = true;
+  table->key_bounds.clear();
+  table->dirty = true;
+  *out_handle = group->received[side];
+  return HYB_OK;
+}
+
+// Per-destination counts of one side: count kernel -> scan -> offsets (device, world + 1 entries).
+static int peer_count_side(hyb_context* context, DeviceScratch& scratch, const SideInfo& info, uint32_t world, uint32_t chunk_id_base,
+                           ProbeParams* params, unsigned long long** out_offsets) {
+  const uint32_t tiles = info.source.tile_count;
+  const size_t histogram_entries = size_t{world} * std::max<uint32_t>(tiles, 1);
+  uint32_t* histogram = nullptr;
+  unsigned long long* run_starts = nullptr;
+  unsigned long long* offsets = nullptr;
+  uint32_t* control = nullptr;
+  HYB_TRY(scratch.alloc_array(histogram_entries, &histogram));
+  HYB_TRY(scratch.alloc_array(histogram_entries, &run_starts));
+  HYB_TRY(scratch.alloc_array(size_t{world} + 1, &offsets));
+  HYB_TRY(scratch.alloc_array(16, &control));
+  HYB_CUDA(cudaMemsetAsync(control, 0, 64, context->stream));
+  HYB_CUDA(cudaMemsetAsync(offsets, 0, sizeof(unsigned long long) * (size_t{world} + 1), context->stream));
+  *params = ProbeParams{};
+  params->probe = info.source;
+  params->build = info.source;
+  params->mode = kModePartition;
+  params->partition_mask = world - 1;
+  params->partition_count = world;
+  params->unique_build = 1;
+  params->flags = control;
+  params->histogram = histogram;
+  params->run_starts = run_starts;
+  params->overflow = control + 2;
+  params->out_capacity = ~0ull;
+  params->chunk_id_base = chunk_id_base;
+  params->push_to_peers = 1;
+  if (tiles) {
+    int count_blocks = 1;
+    HYB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&count_blocks, join_probe_count_kernel<false>, kJoinThreads, 0));
+    join_probe_count_kernel<false><<<std::min<uint32_t>(tiles, context->sm_count * std::max(count_blocks, 1)), kJoinThreads, 0,
+                                     context->stream>>>(*params);
+    HYB_CUDA(cudaGetLastError());
+    HYB_TRY(run_exclusive_scan(context, histogram, run_starts, histogram_entries, reinterpret_cast<unsigned long long*>(control + 4)));
+    join_partition_offsets_kernel<<<1, 128, 0, context->stream>>>(run_starts, reinterpret_cast<unsigned long long*>(control + 4),
+                                                                  world, tiles, offsets);
+    HYB_CUDA(cudaGetLastError());
+  }
+  *out_offsets = offsets;
+  return HYB_OK;
+}
+
+}  // namespace hyb
+
+extern "C" {
+
+int hyb_join_hash_distributed(hyb_context* context, hyb_peer_group_t group_handle, const hyb_join_side* build_side,
+                              const hyb_join_side* probe_side, uint32_t build_chunk_base, uint32_t probe_chunk_base,
+                              int32_t radix_bits, hyb_join_result_t* out_result) {
+  HYB_CHECK(context && build_side && probe_side && out_result, HYB_ERR_INVALID, "NULL argument");
+  *out_result = 0;
+  DeviceGuard guard(context->device);
+  std::lock_guard<std::mutex> lock(context->mutex);
+  PeerGroup* group = find_peer_group(context, group_handle);
+  HYB_CHECK(group, HYB_ERR_NOT_FOUND, "unknown peer group handle");
+  HYB_CHECK(group->connected || group->world == 1, HYB_ERR_INVALID, "peer group is not connected");
+  const uint32_t world = group->world, rank = group->rank;
+  HYB_CHECK(radix_bits < 0 || (1u << radix_bits) >= world, HYB_ERR_INVALID,
+            "radix_bits must give every rank a partition (2^radix_bits >= world)");
+  cudaStream_t stream = context->stream;
+  SideInfo sides[2];
+  HYB_TRY(prepare_side(context, build_side, &sides[0]));
+  HYB_TRY(prepare_side(context, probe_side, &sides[1]));
+  HYB_CHECK(sides[0].positions < 0xFFFFFFF0ull && sides[1].positions < 0xFFFFFFF0ull, HYB_ERR_UNSUPPORTED,
+            "more than 2^32 - 16 rows per join side");
+  const unsigned long long epoch = peer_next_epoch(group);
+  DeviceScratch scratch(context);
+  group->stats = hyb_distributed_stats{};
+  HYB_CUDA(cudaEventRecord(group->events[0], stream));
+
+  // ---- 1. per-destination counts of both sides; publish them (and the build-key bounds) to every rank -------------------
+  ProbeParams params[2];
+  unsigned long long* offsets[2] = {nullptr, nullptr};
+  HYB_TRY(peer_count_side(context, scratch, sides[0], world, build_chunk_base, &params[0], &offsets[0]));
+  HYB_TRY(peer_count_side(context, scratch, sides[1], world, probe_chunk_base, &params[1], &offsets[1]));
+  Table::KeyBounds local_bounds{};
+  uint32_t bounds_launches = 0;
+  HYB_TRY(column_key_bounds(context, sides[0], build_side->column_id, &local_bounds, &bounds_launches));
+  PeerControl** controls = nullptr;
+  HYB_TRY(scratch.alloc_array(kPeerMax, &controls));
+  PeerControl* host_controls[kPeerMax] = {};
+  for (uint32_t peer = 0; peer < world; ++peer) host_controls[peer] = group->control(peer);
+  HYB_CUDA(cudaMemcpyAsync(controls, host_controls, sizeof(host_controls), cudaMemcpyHostToDevice, stream));
+  peer_publish_counts_kernel<<<1, 32 * kPeerMax, 0, stream>>>(controls, rank, world, epoch, offsets[0], offsets[1], local_bounds.min,
+                                                              local_bounds.max, local_bounds.has_values ? 1 : 0);
+  HYB_CUDA(cudaGetLastError());
+  HYB_CUDA(cudaEventRecord(group->events[1], stream));
+
+  // ---- 2. wait (on the device) for every rank's counts; the one host round trip of the operator -------------------------
+  HYB_TRY(peer_wait(context, group->control(rank)->count_flag, world, epoch));
+  HYB_CUDA(cudaMemcpyAsync(group->h_counts, group->control(rank)->counts, sizeof(PeerControl::counts) + sizeof(PeerControl::key_info),
+                           cudaMemcpyDeviceToHost, stream));
+  HYB_CUDA(cudaEventRecord(group->events[2], stream));
+  HYB_CUDA(cudaStreamSynchronize(stream));
+  const auto count_at = [&](int side, uint32_t source, uint32_t destination) {
+    return group->h_counts[(size_t(side) * kPeerMax + source) * kPeerMax + destination];
+  };
+  const long long* key_info = reinterpret_cast<const long long*>(group->h_counts + 2 * kPeerMax * kPeerMax);
+  uint64_t received[2] = {0, 0}, sent_elsewhere = 0;
+  for (int side = 0; side < 2; ++side) {
+    for (uint32_t destination = 0; destination < world; ++destination) {
+      uint64_t before = 0, total = 0;
+      for (uint32_t source = 0; source < world; ++source) {
+        if (source < rank) before += count_at(side, source, destination);
+        total += count_at(side, source, destination);
+      }
+      HYB_CHECK(total <= group->capacity, HYB_ERR_OOM,
+                "receive region of rank " + std::to_string(destination) + " too small: " + std::to_string(total) + " tuples > " +
+                    std::to_string(group->capacity));
+      params[side].peer_keys[destination] = reinterpret_cast<long long*>(group->region(destination, side == 0 ? 0 : 2)) + before;
+      params[side].peer_rows[destination] = reinterpret_cast<long long*>(group->region(destination, side == 0 ? 1 : 3)) + before;
+      if (destination == rank) received[side] = total;
+      if (destination != rank) sent_elsewhere += count_at(side, rank, destination);
+    }
+  }
+  group->stats.tuples_sent = sent_elsewhere;
+  group->stats.tuples_received = received[0] + received[1];
+  group->stats.nvlink_bytes = sent_elsewhere * 16;
+
+  // ---- 3. fused split + NVLink stores of both sides; the last CTA raises this rank's done flag everywhere ------------------
+  int write_blocks = 1;
+  HYB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&write_blocks, join_partition_write_kernel, kJoinThreads, 0));
+  uint32_t grids[2];
+  uint32_t expected = 0;
+  for (int side = 0; side < 2; ++side) {
+    const uint32_t tiles = sides[side].source.tile_count;
+    grids[side] = tiles ? std::min<uint32_t>(tiles, context->sm_count * std::max(write_blocks, 1)) : 0;
+    expected += grids[side];
+  }
+  HYB_CUDA(cudaMemsetAsync(group->d_arrivals, 0, sizeof(unsigned int), stream));
+  for (int side = 0; side < 2; ++side) {
+    params[side].signal_arrivals = group->d_arrivals;
+    params[side].signal_expected = std::max<uint32_t>(expected, 1);
+    params[side].signal_world = world;
+    params[side].signal_epoch = epoch;
+    for (uint32_t peer = 0; peer < world; ++peer) params[side].signal_flags[peer] = &group->control(peer)->done_flag[rank];
+    if (grids[side]) {
+      join_partition_write_kernel<<<grids[side], kJoinThreads, 0, stream>>>(params[side]);
+      HYB_CUDA(cudaGetLastError());
+    }
+  }
+  if (expected == 0) {
+    peer_signal_kernel<<<1, 32, 0, stream>>>(params[0]);  // nothing to send: still tell the peers this rank is done
+    HYB_CUDA(cudaGetLastError());
+  }
+  HYB_CUDA(cudaEventRecord(group->events[3], stream));
+
+  // ---- 4. wait for every rank's stores, then join what arrived ------------------------------------------------------------
+  HYB_TRY(peer_wait(context, group->control(rank)->done_flag, world, epoch));
+  HYB_CUDA(cudaEventRecord(group->events[4], stream));
+  if (radix_bits < 0) {
+    uint64_t global_build = 0;
+    for (uint32_t source = 0; source < world; ++source) {
+      for (uint32_t destination = 0; destination < world; ++destination) global_build += count_at(0, source, destination);
+    }
+    radix_bits = std::max<int32_t>(calculate_radix_bits(global_build), 0);
+    while ((1u << radix_bits) < world) ++radix_bits;
+  }
+  hyb_table_t tables[2];
+  HYB_TRY(received_table(context, group, 0, received[0], &tables[0]));
+  HYB_TRY(received_table(context, group, 1, received[1], &tables[1]));
+  {
+    // Bounds of the received build keys without another pass: they lie inside the union of the ranks' column bounds and
+    // agree in their low log2(world) bits (that is what brought them here) -> direct table indexed by (key - min) >> shift.
+    Table::KeyBounds bounds{};
+    for (uint32_t source = 0; source < world; ++source) {
+      if (key_info[source * 4 + 2] == 0) continue;
+      bounds.min = bounds.has_values ? std::min<long long>(bounds.min, key_info[source * 4 + 0]) : key_info[source * 4 + 0];
+      bounds.max = bounds.has_values ? std::max<long long>(bounds.max, key_info[source * 4 + 1]) : key_info[source * 4 + 1];
+      bounds.has_values = true;
+    }
+    if (bounds.has_values && received[0] > 0) {
+      uint32_t shift = 0;
+      while ((1u << shift) < world) ++shift;
+      // smallest value >= min with the low bits of this rank (keeps (key - min) a multiple of 2^shift)
+      const long long mask = static_cast<long long>(world) - 1;
+      const long long aligned = bounds.min + ((static_cast<long long>(rank) - (bounds.min & mask)) & mask);
+      bounds.min = aligned;
+      bounds.max = std::max(bounds.max, aligned);
+      bounds.constant_low_bits = shift;
+      find_table(context, tables[0])->key_bounds.emplace(0u, bounds);
+    }
+  }
+  hyb_join_side local_build{tables[0], 0, 0}, local_probe{tables[1], 0, 0};
+  hyb_join_result_t result_handle = 0;
+  HYB_TRY(join_hash_locked(context, &local_build, &local_probe, HYB_JOIN_INNER, radix_bits, &result_handle));
+  HYB_CUDA(cudaEventRecord(group->events[5], stream));
+
+  // ---- 5. positions in the received tables -> global RowIDs ----------------------------------------------------------------
+  JoinResult* result = context->join_results.at(result_handle).get();
+  const unsigned long long* total = reinterpret_cast<const unsigned long long*>(result->d_partition_offsets + result->partition_count);
+  if (result->capacity) {
+    const uint32_t grid = context->sm_count * 8;
+    peer_translate_kernel<<<grid, 256, 0, stream>>>(result->d_build, reinterpret_cast<const hyb_row_id*>(group->region(rank, 1)), total);
+    peer_translate_kernel<<<grid, 256, 0, stream>>>(result->d_probe, reinterpret_cast<const hyb_row_id*>(group->region(rank, 3)), total);
+    HYB_CUDA(cudaGetLastError());
+  }
+  HYB_CUDA(cudaEventRecord(group->events[6], stream));
+  *out_result = result_handle;
+  return HYB_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
 
 // ---- peer-visible receive arenas (CUDA IPC) ----------------------------------------------------------------------------
 int hyb_exchange_arena_create(hyb_context* context, uint64_t bytes, void** out_device_ptr, void* out_ipc_handle) {

@@ -191,6 +191,52 @@ class AggregateOutput:
     value_types: list[int]
 
 
+class DevicePeerGroup:
+    """hyb_peer_group: this rank's exchange arena and its mappings of the peers' arenas. Distributed operators are one
+    C-ABI call per rank; the host layer only moves the IPC handles once (hyrise_b200.distributed.connect_peer_group)."""
+
+    def __init__(self, context: "DeviceContext", rank: int, world: int, tuple_capacity: int):
+        self.context = context
+        self.rank, self.world = rank, world
+        handle = (C.c_ubyte * capi.IPC_HANDLE_BYTES)()
+        group = C.c_uint64()
+        check(context.lib.hyb_peer_group_create(context.ptr, rank, world, tuple_capacity, handle, C.byref(group)))
+        self.handle = group.value
+        self.ipc_handle = bytes(handle)
+
+    def connect(self, all_ipc_handles: Sequence[bytes]) -> None:
+        packed = (C.c_ubyte * (capi.IPC_HANDLE_BYTES * self.world)).from_buffer_copy(b"".join(all_ipc_handles))
+        check(self.context.lib.hyb_peer_group_connect(self.context.ptr, self.handle, packed))
+
+    def join_hash(self, build: "DeviceTable", build_column: int, probe: "DeviceTable", probe_column: int,
+                  build_chunk_base: int, probe_chunk_base: int, radix_bits: int = -1) -> "DeviceJoinResult":
+        build_side = capi.JoinSide(build.handle, build_column, 0)
+        probe_side = capi.JoinSide(probe.handle, probe_column, 0)
+        handle = C.c_uint64()
+        check(self.context.lib.hyb_join_hash_distributed(self.context.ptr, self.handle, C.byref(build_side), C.byref(probe_side),
+                                                         build_chunk_base, probe_chunk_base, radix_bits, C.byref(handle)))
+        return DeviceJoinResult(self.context, handle.value, True)
+
+    def aggregate_hash(self, table: "DeviceTable", groupby_column_ids: Sequence[int], aggregates: Sequence["Aggregate"],
+                       predicates: Sequence["Predicate"] = (), chunk_id_base: int = 0, position_base: int = 0) -> "AggregateOutput":
+        query, keepalive = self.context._aggregate_query(table, groupby_column_ids, aggregates, predicates, None)
+        handle = C.c_uint64()
+        check(self.context.lib.hyb_aggregate_hash_distributed(self.context.ptr, self.handle, C.byref(query), chunk_id_base,
+                                                              position_base, C.byref(handle)))
+        del keepalive
+        return self.context._collect_aggregate(handle.value, len(aggregates))
+
+    def stats(self) -> capi.DistributedStats:
+        stats = capi.DistributedStats()
+        check(self.context.lib.hyb_peer_group_stats(self.context.ptr, self.handle, C.byref(stats)))
+        return stats
+
+    def destroy(self) -> None:
+        if self.handle:
+            check(self.context.lib.hyb_peer_group_destroy(self.context.ptr, self.handle))
+            self.handle = 0
+
+
 class DeviceContext:
     """hyb_context: one per process and GPU."""
 
@@ -264,9 +310,8 @@ class DeviceContext:
         semi_or_anti = mode in (capi.JOIN_SEMI, capi.JOIN_ANTI_NULL_AS_TRUE, capi.JOIN_ANTI_NULL_AS_FALSE)
         return DeviceJoinResult(self, handle.value, not semi_or_anti)
 
-    def aggregate_hash(self, table: DeviceTable, groupby_column_ids: Sequence[int], aggregates: Sequence[Aggregate],
-                       predicates: Sequence[Predicate] = (), input_filter: DevicePosList | None = None,
-                       ) -> AggregateOutput:
+    def _aggregate_query(self, table: DeviceTable, groupby_column_ids, aggregates, predicates, input_filter):
+        """AggregateQuery struct + the objects that must stay alive while it is in use."""
         query = capi.AggregateQuery()
         query.table = table.handle
         query.filter = input_filter.handle if input_filter else 0
@@ -284,28 +329,39 @@ class DeviceContext:
         defs = build_aggregate_defs(aggregates)
         query.aggregate_count = len(aggregates)
         query.aggregates = C.cast(defs, C.POINTER(capi.AggregateDef))
-        handle = C.c_uint64()
-        check(self.lib.hyb_aggregate_hash(self.ptr, C.byref(query), C.byref(handle)))
+        keepalive += [predicate_structs, groupby, defs]
+        return query, keepalive
+
+    def _collect_aggregate(self, handle: int, aggregate_count: int) -> AggregateOutput:
         try:
             groups, immediate = C.c_uint64(), C.c_int32()
-            check(self.lib.hyb_aggregate_result_info(self.ptr, handle.value, C.byref(groups), C.byref(immediate)))
+            check(self.lib.hyb_aggregate_result_info(self.ptr, handle, C.byref(groups), C.byref(immediate)))
             count = groups.value
             row_ids = np.empty(count, dtype=ROW_ID_DTYPE)
-            check(self.lib.hyb_aggregate_result_row_ids(self.ptr, handle.value, row_ids.ctypes.data))
+            check(self.lib.hyb_aggregate_result_row_ids(self.ptr, handle, row_ids.ctypes.data))
             values, nulls, types = [], [], []
-            for index in range(len(aggregates)):
+            for index in range(aggregate_count):
                 raw = np.zeros(max(count, 1), dtype=np.uint64)
                 null = np.zeros(max(count, 1), dtype=np.uint8)
                 value_type = C.c_int32()
-                check(self.lib.hyb_aggregate_result_values(self.ptr, handle.value, index, raw.ctypes.data,
-                                                           null.ctypes.data, C.byref(value_type)))
+                check(self.lib.hyb_aggregate_result_values(self.ptr, handle, index, raw.ctypes.data, null.ctypes.data,
+                                                           C.byref(value_type)))
                 dtype = NUMPY_TYPES[value_type.value]
                 values.append(raw.view(np.uint8)[: count * np.dtype(dtype).itemsize].view(dtype).copy())
                 nulls.append(null[:count].astype(bool))
                 types.append(value_type.value)
         finally:
-            check(self.lib.hyb_aggregate_result_free(self.ptr, handle.value))
+            check(self.lib.hyb_aggregate_result_free(self.ptr, handle))
         return AggregateOutput(count, bool(immediate.value), row_ids, values, nulls, types)
+
+    def aggregate_hash(self, table: DeviceTable, groupby_column_ids: Sequence[int], aggregates: Sequence[Aggregate],
+                       predicates: Sequence[Predicate] = (), input_filter: DevicePosList | None = None,
+                       ) -> AggregateOutput:
+        query, keepalive = self._aggregate_query(table, groupby_column_ids, aggregates, predicates, input_filter)
+        handle = C.c_uint64()
+        check(self.lib.hyb_aggregate_hash(self.ptr, C.byref(query), C.byref(handle)))
+        del keepalive
+        return self._collect_aggregate(handle.value, len(aggregates))
 
     def last_stats(self) -> capi.OperatorStats:
         stats = capi.OperatorStats()

@@ -496,6 +496,44 @@ class PeerExchange:
         self._release()
 
 
+def connect_peer_group(device_context, tuple_capacity: int):
+    """Creates this rank's hyb_peer_group, all-gathers the CUDA IPC handles (the one collective of the native multi-GPU
+    path) and maps every peer's arena. Every rank takes part in every collective even when a local step failed, so that
+    nobody hangs; the failure is agreed on and raised everywhere."""
+    from .device import DevicePeerGroup
+
+    rank, world = _world()
+    agreed = [None] * world
+    if world > 1:
+        dist.all_gather_object(agreed, int(tuple_capacity))
+        tuple_capacity = max(agreed)
+    group, error = None, None
+    try:
+        group = DevicePeerGroup(device_context, rank, world, tuple_capacity)
+    except Exception as exception:  # noqa: BLE001
+        error = exception
+    handles = [group.ipc_handle if group else None]
+    if world > 1:
+        handles = [None] * world
+        dist.all_gather_object(handles, group.ipc_handle if group else None)
+    if all(handle is not None for handle in handles):
+        try:
+            if world > 1:
+                group.connect(handles)
+        except Exception as exception:  # noqa: BLE001
+            error = exception
+    elif error is None:
+        error = RuntimeError("a peer could not create its exchange arena")
+    if world > 1:
+        states = [None] * world
+        dist.all_gather_object(states, error is None)
+        if not all(states) and error is None:
+            error = RuntimeError("a peer could not map the exchange arenas")
+    if error is not None:
+        raise error
+    return group
+
+
 def device_distributed_join(device_context, build_table, build_column: int, probe_table, probe_column: int,
                             radix_bits: int, build_chunk_base: int, probe_chunk_base: int, torch_device: torch.device,
                             peers: "PeerExchange | None" = None):

@@ -386,6 +386,58 @@ int hyb_exchange_arena_open(hyb_context* context, const void* ipc_handle, void**
 int hyb_exchange_arena_close(hyb_context* context, void* peer_ptr);
 int hyb_exchange_arena_destroy(hyb_context* context, void* device_ptr);
 
+/*
+ * Peer groups: the multi-GPU operators without host orchestration. One process per GPU; every rank creates its group
+ * (allocating its exchange arena: a control block plus four regions of tuple_capacity tuples), the host layer
+ * all-gathers the IPC handles once (the only use of torch.distributed / NCCL besides verification), every rank connects.
+ * After that a distributed operator is ONE C-ABI call per rank: counts, statistics and partial groups travel through the
+ * arenas with NVLink peer stores issued by the library's kernels, ranks order themselves with epoch flags polled on the
+ * device, and the only host round trip is the one that reads the world x world count matrix. Every rank must make the
+ * same distributed calls in the same order. world: power of two <= 16.
+ */
+typedef uint64_t hyb_peer_group_t;
+int hyb_peer_group_create(hyb_context* context, uint32_t rank, uint32_t world, uint64_t tuple_capacity, void* out_ipc_handle,
+                          hyb_peer_group_t* out_group);
+/* all_ipc_handles: world x HYB_IPC_HANDLE_BYTES, in rank order (the own entry is ignored). */
+int hyb_peer_group_connect(hyb_context* context, hyb_peer_group_t group, const void* all_ipc_handles);
+int hyb_peer_group_destroy(hyb_context* context, hyb_peer_group_t group);
+
+/*
+ * Inner JoinHash over ranks: both sides are split by the rank that owns the radix partition
+ * (key & (world - 1), the reference's hash(key) & mask with the identity hash) and pushed straight into the owners'
+ * arenas by the fused split + NVLink store kernel; every rank then joins what it received (hyb_join_hash on the received
+ * tuples) and translates the result to GLOBAL RowIDs (chunk ids shifted by build_chunk_base / probe_chunk_base of the
+ * rank the row came from). The result on this rank holds the partitions p with p % world == rank of the
+ * reference-ordered result, in the reference's order.
+ */
+int hyb_join_hash_distributed(hyb_context* context, hyb_peer_group_t group, const hyb_join_side* build,
+                              const hyb_join_side* probe, uint32_t build_chunk_base, uint32_t probe_chunk_base,
+                              int32_t radix_bits, hyb_join_result_t* out_result);
+
+/*
+ * AggregateHash over ranks, low-cardinality form (the partial groups of a rank must fit one 32 KB block, else
+ * HYB_ERR_UNSUPPORTED): every rank pre-aggregates its shard (AVG travels as SUM and COUNT), stores its partial groups
+ * into every peer's arena and merges all ranks' blocks in rank order — every rank ends up with the complete result.
+ * chunk_id_base / position_base: first global chunk id / row position of this rank's shard (group order and
+ * representative RowIDs refer to the global table).
+ */
+int hyb_aggregate_hash_distributed(hyb_context* context, hyb_peer_group_t group, const struct hyb_aggregate_query* query,
+                                   uint32_t chunk_id_base, uint64_t position_base, hyb_aggregate_result_t* out_result);
+
+/* Phases of the last distributed call on this rank (CUDA-event times on the context stream). */
+typedef struct hyb_distributed_stats {
+  float split_count_ms;      /* per-destination counts of both sides + publishing them to the peers */
+  float count_wait_ms;       /* waiting for every peer's counts (device-side flag wait) incl. the host read of the matrix */
+  float push_ms;             /* fused split + NVLink stores of both sides */
+  float done_wait_ms;        /* waiting for every peer's stores */
+  float local_ms;            /* local join (or pre-aggregation) */
+  float finish_ms;           /* RowID translation / merge */
+  uint64_t tuples_sent;      /* to other ranks */
+  uint64_t tuples_received;  /* from all ranks, own included */
+  uint64_t nvlink_bytes;     /* bytes this rank stored into peer memory */
+} hyb_distributed_stats;
+int hyb_peer_group_stats(hyb_context* context, hyb_peer_group_t group, hyb_distributed_stats* out_stats);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * AggregateHash (with optionally fused scan predicates and Projection arithmetic)
  * ---------------------------------------------------------------------------------------------------------------- */

@@ -51,20 +51,26 @@ class UnionTable:
         return np.concatenate([t.string_value_id_bounds(predicate) for t in self._tables], axis=0)
 
 
-def main():
-    rank, world, local_rank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local_rank)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    torch_device = torch.device("cuda", local_rank)
-    orders_per_rank = int(round(1_500_000 * SF))
-    shard = TpchTables(SF, seed=42, first_order=rank * orders_per_rank)
-    device = DeviceContext(local_rank)
+def run_distributed_checks(device, rank, world, torch_device, sf=SF, legacy_paths=True):
+    """Scan / JoinHash / Q1 AggregateHash over `world` ranks on shards of one SF-`sf` data set, checked on rank 0 against the
+    oracle run over the union of all shards (bit-exact RowIDs in reference order; sums within 1e-6). Returns a summary line on
+    rank 0; raises AssertionError on any rank that sees a mismatch (every rank takes part in every collective first)."""
+    orders_per_rank = int(round(1_500_000 * sf))
+    shard = TpchTables(sf, seed=42, first_order=rank * orders_per_rank)
     lineitem, orders = device.upload(shard.lineitem), device.upload(shard.orders)
     lineitem_base = hd.chunk_bases(shard.lineitem.chunk_count, torch_device)[rank]
     orders_base = hd.chunk_bases(shard.orders.chunk_count, torch_device)[rank]
+    rows_per_rank = [None] * world
+    dist.all_gather_object(rows_per_rank, shard.lineitem.row_count)
+    position_base = sum(rows_per_rank[:rank])
+    failures = []
+
+    def expect(condition, message):
+        if not condition:
+            failures.append(message)
 
     if rank == 0:
-        all_shards = [shard] + [TpchTables(SF, seed=42, first_order=r * orders_per_rank) for r in range(1, world)]
+        all_shards = [shard] + [TpchTables(sf, seed=42, first_order=r * orders_per_rank) for r in range(1, world)]
         global_lineitem, global_orders = UnionTable(all_shards, "lineitem"), UnionTable(all_shards, "orders")
 
     # ---- scan: no collective -----------------------------------------------------------------------------------------
@@ -72,69 +78,98 @@ def main():
     scan = device.table_scan(lineitem, predicate)
     gathered = [None] * world
     dist.all_gather_object(gathered, hd.globalize_row_ids(scan.to_host(), lineitem_base))
+    scan.free()
+    scan_rows = sum(len(g) for g in gathered)
     if rank == 0:
         expected = orc.table_scan(global_lineitem, predicate, threads=8)
-        assert row_ids_equal(np.concatenate(gathered), expected.row_ids), "distributed scan differs"
+        expect(row_ids_equal(np.concatenate(gathered), expected.row_ids), "distributed scan differs")
 
-    # ---- join: radix all-to-all ----------------------------------------------------------------------------------------
+    # ---- join: native peer-group path (fused split + NVLink stores, device-side flags), then the legacy host paths --------
     radix_bits = 4
     expected = orc.join_hash(global_orders, O_ORDERKEY, global_lineitem, L_ORDERKEY, capi.JOIN_INNER, radix_bits, threads=8) \
         if rank == 0 else None
-    peers = hd.PeerExchange(device, torch_device, capacity=2 * shard.lineitem.row_count + 65_536)
-    for exchange_kind, exchange in (("nccl all-to-all", None), ("fused split + NVLink P2P stores", peers)):
-        pairs, offsets, build_rows, probe_rows, result = hd.device_distributed_join(
-            device, orders, O_ORDERKEY, lineitem, L_ORDERKEY, radix_bits, orders_base, lineitem_base, torch_device, peers=exchange)
-        if result is not None:
-            got_build, got_probe = result.to_host()
-            out_build = hd.unpack_row_ids(build_rows.cpu().numpy()[got_build["chunk_offset"]])
-            out_probe = hd.unpack_row_ids(probe_rows.cpu().numpy()[got_probe["chunk_offset"]])
-            result.free()
-        else:
-            out_build = out_probe = hd.unpack_row_ids(np.zeros(0, dtype=np.int64))
+    group = hd.connect_peer_group(device, 2 * max(rows_per_rank) + 65_536)
+
+    def check_join(kind, out_build, out_probe, offsets):
         gathered = [None] * world
         dist.all_gather_object(gathered, (out_build, out_probe, offsets))
-        if rank == 0:
-            build_parts, probe_parts = [], []
-            for partition in range(1 << radix_bits):
-                owner_build, owner_probe, owner_offsets = gathered[partition % world]
-                build_parts.append(owner_build[int(owner_offsets[partition]):int(owner_offsets[partition + 1])])
-                probe_parts.append(owner_probe[int(owner_offsets[partition]):int(owner_offsets[partition + 1])])
-            assert row_ids_equal(np.concatenate(probe_parts), expected.probe), f"distributed join ({exchange_kind}): probe RowIDs differ"
-            assert row_ids_equal(np.concatenate(build_parts), expected.build), f"distributed join ({exchange_kind}): build RowIDs differ"
-    peers.close()
+        if rank != 0:
+            return 0
+        build_parts, probe_parts = [], []
+        for partition in range(1 << radix_bits):
+            owner_build, owner_probe, owner_offsets = gathered[partition % world]
+            build_parts.append(owner_build[int(owner_offsets[partition]):int(owner_offsets[partition + 1])])
+            probe_parts.append(owner_probe[int(owner_offsets[partition]):int(owner_offsets[partition + 1])])
+            for other in range(world):   # a partition lives on exactly one rank
+                if other != partition % world:
+                    expect(gathered[other][2][partition] == gathered[other][2][partition + 1], f"{kind}: partition on a foreign rank")
+        expect(row_ids_equal(np.concatenate(probe_parts), expected.probe), f"distributed join ({kind}): probe RowIDs differ")
+        expect(row_ids_equal(np.concatenate(build_parts), expected.build), f"distributed join ({kind}): build RowIDs differ")
+        return sum(len(p) for p in probe_parts)
 
-    # ---- aggregate: Q1 with one all-to-all of partial groups -----------------------------------------------------------
-    q1_predicates = [Predicate(L_SHIPDATE, capi.PRED_LESS_THAN_EQUALS, "1998-09-02")]
-    functions = [a.function for a in Q1_AGGREGATES]
+    join_pairs = 0
+    for repeat in range(2):   # twice: the arenas, the received tables and the epoch flags are reused
+        result = group.join_hash(orders, O_ORDERKEY, lineitem, L_ORDERKEY, orders_base, lineitem_base, radix_bits)
+        got_build, got_probe = result.to_host()
+        offsets = result.partition_offsets()
+        result.free()
+        join_pairs = check_join("peer group", got_build, got_probe, offsets)
+    stats = group.stats()
 
-    def local(decomposed):
-        aggregates = [Aggregate(function, None if function == capi.AGG_COUNT_STAR else Q1_AGGREGATES[original].expression)
-                      for function, original in decomposed]
-        output = device.aggregate_hash(lineitem, [L_RETURNFLAG, L_LINESTATUS], aggregates, predicates=q1_predicates)
-        keys = np.zeros((output.group_count, 2), dtype=np.int64)
-        for g, row in enumerate(output.row_ids):
-            keys[g, 0] = shard.lineitem.char_at(L_RETURNFLAG, int(row["chunk_id"]), int(row["chunk_offset"]))
-            keys[g, 1] = shard.lineitem.char_at(L_LINESTATUS, int(row["chunk_id"]), int(row["chunk_offset"]))
-        positions = (np.int64(rank) << 40) + output.row_ids["chunk_id"].astype(np.int64) * capi.DEFAULT_CHUNK_SIZE + \
-            output.row_ids["chunk_offset"].astype(np.int64)
-        values = [v.astype(np.float64) if v.dtype.kind == "f" else v.astype(np.int64) for v in output.values]
-        counts = [v.astype(np.int64) if f in (capi.AGG_COUNT, capi.AGG_COUNT_STAR) else (~n).astype(np.int64)
-                  for v, n, (f, _) in zip(output.values, output.nulls, decomposed)]
-        return hd.PartialGroups(keys, np.zeros_like(keys, dtype=bool), positions, [f for f, _ in decomposed], values, counts)
-
-    outcome = hd.distributed_aggregate(local, functions, torch_device)
-    if rank == 0:
-        merged, (values, nulls) = outcome
-        expected = orc.aggregate_hash(global_lineitem, [L_RETURNFLAG, L_LINESTATUS], Q1_AGGREGATES, predicates=q1_predicates)
-        assert len(merged.keys) == expected.group_count == 4
-        # same group order: first appearance in global row order
-        for index in range(len(functions)):
-            if expected.values[index].dtype.kind == "f":
-                assert np.allclose(values[index], expected.values[index], rtol=1e-6), index
+    if legacy_paths and world > 1:
+        peers = hd.PeerExchange(device, torch_device, capacity=2 * shard.lineitem.row_count + 65_536)
+        for exchange_kind, exchange in (("nccl all-to-all", None), ("host-orchestrated P2P stores", peers)):
+            pairs, offsets, build_rows, probe_rows, result = hd.device_distributed_join(
+                device, orders, O_ORDERKEY, lineitem, L_ORDERKEY, radix_bits, orders_base, lineitem_base, torch_device, peers=exchange)
+            if result is not None:
+                got_build, got_probe = result.to_host()
+                out_build = hd.unpack_row_ids(build_rows.cpu().numpy()[got_build["chunk_offset"]])
+                out_probe = hd.unpack_row_ids(probe_rows.cpu().numpy()[got_probe["chunk_offset"]])
+                result.free()
             else:
-                assert np.array_equal(values[index].astype(np.int64), expected.values[index].astype(np.int64)), index
-        print(f"distributed OK on {world} GPUs: scan {sum(len(g) for g in gathered)} tuples gathered, join pairs "
-              f"{sum(len(p) for p in probe_parts)}, Q1 groups {len(merged.keys)}")
+                out_build = out_probe = hd.unpack_row_ids(np.zeros(0, dtype=np.int64))
+            check_join(exchange_kind, out_build, out_probe, offsets)
+        peers.close()
+
+    # ---- aggregate: Q1, partial groups through the peer arenas, every rank ends up with the complete result -----------------
+    q1_predicates = [Predicate(L_SHIPDATE, capi.PRED_LESS_THAN_EQUALS, "1998-09-02")]
+    output = group.aggregate_hash(lineitem, [L_RETURNFLAG, L_LINESTATUS], Q1_AGGREGATES, q1_predicates, lineitem_base, position_base)
+    everyone = [None] * world
+    dist.all_gather_object(everyone, (output.row_ids, output.values))
+    if rank == 0:
+        expected = orc.aggregate_hash(global_lineitem, [L_RETURNFLAG, L_LINESTATUS], Q1_AGGREGATES, predicates=q1_predicates)
+        expect(output.group_count == expected.group_count == 4, f"Q1 groups {output.group_count}")
+        expect(row_ids_equal(output.row_ids, expected.row_ids), "Q1: group order / representative RowIDs differ")
+        for index in range(len(Q1_AGGREGATES)):
+            if expected.values[index].dtype.kind == "f":
+                expect(np.allclose(output.values[index], expected.values[index], rtol=1e-6, atol=0.0), f"Q1 aggregate {index}")
+            else:
+                expect(np.array_equal(output.values[index], expected.values[index]), f"Q1 aggregate {index}")
+        for other_rows, other_values in everyone[1:]:   # replicated result: bit-identical on every rank
+            expect(row_ids_equal(other_rows, output.row_ids), "Q1 result differs between ranks")
+            expect(all(np.array_equal(a, b) for a, b in zip(other_values, output.values)), "Q1 values differ between ranks")
+    dist.barrier()
+    group.destroy()
+    lineitem.drop()
+    orders.drop()
+    shard.close()
+    ok = [None] * world
+    dist.all_gather_object(ok, failures)
+    all_failures = [message for per_rank in ok for message in per_rank]
+    assert not all_failures, "; ".join(all_failures)
+    return (f"distributed OK on {world} GPUs: scan {scan_rows} RowIDs, join pairs {join_pairs} (push {stats.push_ms:.3f} ms, "
+            f"local join {stats.local_ms:.3f} ms, {stats.nvlink_bytes} bytes over NVLink from rank 0), Q1 groups {output.group_count}")
+
+
+def main():
+    rank, world, local_rank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch_device = torch.device("cuda", local_rank)
+    device = DeviceContext(local_rank)
+    summary = run_distributed_checks(device, rank, world, torch_device)
+    if rank == 0:
+        print(summary)
     dist.barrier()
     device.close()
     dist.destroy_process_group()

@@ -318,3 +318,36 @@ def test_sorted_unique_build_span_path(device, probe_encoding, key_step):
     build_filter[0].free()
     build_dev.drop()
     probe_dev.drop()
+
+
+def test_peer_group_single_rank(device):
+    """The native multi-GPU path with a world of one: counts published through the control block, device-side flag waits,
+    the fused split + push kernel storing into this rank's own arena, the local join over the received tuples and the
+    translation back to (global) RowIDs — and the partial-group exchange of the aggregate. (tests/gpu_distributed_worker.py
+    runs the same calls on >= 2 GPUs.)"""
+    from hyrise_b200 import distributed as hd
+    from hyrise_b200.tpch import L_LINESTATUS, L_ORDERKEY, L_RETURNFLAG, L_SHIPDATE, O_ORDERKEY, TpchTables
+    from test_oracle_aggregate import Q1_AGGREGATES
+
+    tables = TpchTables(0.05, seed=11)
+    lineitem, orders = device.upload(tables.lineitem), device.upload(tables.orders)
+    group = hd.connect_peer_group(device, tables.lineitem.row_count + 4096)
+    for radix_bits in (3, 0, 3):  # repeated calls reuse the arena, the received tables and the epoch flags
+        expected = orc.join_hash(tables.orders, O_ORDERKEY, tables.lineitem, L_ORDERKEY, capi.JOIN_INNER, radix_bits)
+        result = group.join_hash(orders, O_ORDERKEY, lineitem, L_ORDERKEY, 0, 0, radix_bits)
+        got_build, got_probe = result.to_host()
+        assert result.info()[0] == expected.pair_count
+        assert np.array_equal(result.partition_offsets(), expected.partition_offsets)
+        assert row_ids_equal(got_probe, expected.probe) and row_ids_equal(got_build, expected.build)
+        result.free()
+    stats = group.stats()
+    assert stats.tuples_received == tables.lineitem.row_count + tables.orders.row_count and stats.tuples_sent == 0
+    predicates = [Predicate(L_SHIPDATE, capi.PRED_LESS_THAN_EQUALS, "1998-09-02")]
+    got = group.aggregate_hash(lineitem, [L_RETURNFLAG, L_LINESTATUS], Q1_AGGREGATES, predicates, 0, 0)
+    want = orc.aggregate_hash(tables.lineitem, [L_RETURNFLAG, L_LINESTATUS], Q1_AGGREGATES, predicates=predicates)
+    from helpers import assert_aggregate_outputs_equal
+    assert_aggregate_outputs_equal(got, want)
+    group.destroy()
+    lineitem.drop()
+    orders.drop()
+    tables.close()
