@@ -364,58 +364,36 @@ def main() -> None:
 
     operators = {"scan": [], "join": [], "aggregate": []}
     launches = [0]
-    peers = None
+    group = None
+    phases = {"join": [], "aggregate": []}
     torch_device = torch.device("cuda", local_rank)
     if distributed:
         from hyrise_b200 import distributed as hd
         lineitem_chunk_base = hd.chunk_bases(tables.lineitem.chunk_count, torch_device)[rank]
         orders_chunk_base = hd.chunk_bases(tables.orders.chunk_count, torch_device)[rank]
-        lineitem_row_base = rank * 0  # positions only order groups; per-rank offsets keep them disjoint
+        rows_per_rank = [None] * world
+        dist.all_gather_object(rows_per_rank, rows)
+        position_base = sum(rows_per_rank[:rank])
         radix_bits = 8 if args.sf >= 4 else 4
-        # Receive arenas for the fused split + NVLink P2P exchange; NCCL all-to-all of a local send buffer otherwise.
-        peers = None
-        if os.environ.get("HYB_EXCHANGE", "p2p") == "p2p":
-            try:
-                peers = hd.PeerExchange(device, torch_device, capacity=2 * rows + 65_536)
-            except Exception as error:  # noqa: BLE001 - CUDA IPC can be unavailable (container / driver policy)
-                print(f"[bench] rank {rank}: peer exchange unavailable ({error}); using the NCCL all-to-all path", file=sys.stderr)
-            flags = [None] * world
-            dist.all_gather_object(flags, peers is not None)
-            if not all(flags):
-                peers = None
+        # every rank receives about 1 / world of all tuples, i.e. about its own share; 25 % head room for skew
+        group = hd.connect_peer_group(device, int(1.25 * max(rows_per_rank)) + 65_536)
 
-    def distributed_join():
-        """materialise {key, RowID} of both sides -> one NCCL all-to-all per side -> local hyb_join_hash on what arrived"""
-        pairs, offsets, build_rows, probe_rows, result = hd.device_distributed_join(
-            device, orders, O_ORDERKEY, lineitem, L_ORDERKEY, radix_bits, orders_chunk_base, lineitem_chunk_base, torch_device,
-            peers=peers)
-        stats = device.last_stats()
-        return pairs, result, stats
+    def phase_record(stats):
+        return {"split_count_ms": stats.split_count_ms, "count_wait_ms": stats.count_wait_ms, "push_ms": stats.push_ms,
+                "done_wait_ms": stats.done_wait_ms, "local_ms": stats.local_ms, "finish_ms": stats.finish_ms,
+                "tuples_sent": int(stats.tuples_sent), "tuples_received": int(stats.tuples_received),
+                "nvlink_bytes": int(stats.nvlink_bytes)}
 
-    def distributed_q1():
-        """local aggregate_fast_kernel, then the partial groups are exchanged by key hash (one all-to-all) and merged"""
-        functions = [a.function for a in Q1_AGGREGATES]
+    def distributed_join(table_o=None, table_l=None):
+        """hyb_join_hash_distributed: counts published by kernel, fused split + NVLink push of both sides, device-side flag
+        waits, local join of the received tuples, translation to global RowIDs — one C-ABI call per rank"""
+        result = group.join_hash(table_o or orders, O_ORDERKEY, table_l or lineitem, L_ORDERKEY, orders_chunk_base,
+                                 lineitem_chunk_base, radix_bits)
+        return result, device.last_stats()
 
-        def local(decomposed):
-            aggregates = [Aggregate(function, None if function == capi.AGG_COUNT_STAR else Q1_AGGREGATES[original].expression)
-                          for function, original in decomposed]
-            output = device.aggregate_hash(lineitem, Q1_GROUPBY, aggregates, predicates=Q1_PREDICATES)
-            keys = np.zeros((output.group_count, 2), dtype=np.int64)
-            for g, row in enumerate(output.row_ids):
-                keys[g, 0] = tables.lineitem.char_at(L_RETURNFLAG, int(row["chunk_id"]), int(row["chunk_offset"]))
-                keys[g, 1] = tables.lineitem.char_at(L_LINESTATUS, int(row["chunk_id"]), int(row["chunk_offset"]))
-            positions = (np.int64(rank) << 40) + output.row_ids["chunk_id"].astype(np.int64) * capi.DEFAULT_CHUNK_SIZE + \
-                output.row_ids["chunk_offset"].astype(np.int64)
-            values, counts = [], []
-            for index, (function, _) in enumerate(decomposed):
-                raw = output.values[index]
-                values.append(raw.astype(np.float64) if raw.dtype.kind == "f" else raw.astype(np.int64))
-                counts.append(raw.astype(np.int64) if function in (capi.AGG_COUNT, capi.AGG_COUNT_STAR)
-                              else (~output.nulls[index]).astype(np.int64))
-            return hd.PartialGroups(keys, np.zeros_like(keys, dtype=bool), positions, [f for f, _ in decomposed], values, counts)
-
-        outcome = hd.distributed_aggregate(local, functions, torch_device)
-        return outcome
+    def distributed_q1(table_l=None):
+        """hyb_aggregate_hash_distributed: local pre-aggregation, partial groups stored into every peer's arena, merged by all"""
+        return group.aggregate_hash(table_l or lineitem, Q1_GROUPBY, Q1_AGGREGATES, Q1_PREDICATES, lineitem_chunk_base, position_base)
 
     def run_step(record: bool):
         flush_l2()
@@ -423,14 +401,18 @@ def main() -> None:
         scan_stats = device.last_stats()
         flush_l2()
         if distributed:
-            join_pairs, join, join_stats = distributed_join()
+            join, join_stats = distributed_join()
+            if record:
+                phases["join"].append(phase_record(group.stats()))
         else:
             join = device.join_hash(orders, O_ORDERKEY, lineitem, L_ORDERKEY, capi.JOIN_INNER, -1)
             join_stats = device.last_stats()
         flush_l2()
         if distributed:
-            merged = distributed_q1()
+            aggregate = distributed_q1()
             aggregate_stats = device.last_stats()
+            if record:
+                phases["aggregate"].append(phase_record(group.stats()))
         else:
             aggregate = device.aggregate_hash(lineitem, Q1_GROUPBY, Q1_AGGREGATES, predicates=Q1_PREDICATES)
             aggregate_stats = device.last_stats()
@@ -438,13 +420,9 @@ def main() -> None:
             for name, stats in (("scan", scan_stats), ("join", join_stats), ("aggregate", aggregate_stats)):
                 operators[name].append((stats.dominant_kernel_ms, stats.device_ms, stats.algorithmic_bytes, stats.output_rows))
                 launches[0] += stats.kernel_launches
-        if distributed:
-            result = (scan.info()[0], join_pairs, len(merged[0].keys) if merged is not None else 0)
-        else:
-            result = (scan.info()[0], join.info()[0], aggregate.group_count)
+        result = (scan.info()[0], join.info()[0], aggregate.group_count)
         scan.free()
-        if join is not None:
-            join.free()
+        join.free()
         return result
 
     for _ in range(warmup):
@@ -470,9 +448,10 @@ def main() -> None:
     # ---- end to end: host buffers in, host buffers out, every step ---------------------------------------------------
     e2e = None
     if not args.no_e2e:
+        join_capacity = rows if not distributed else int(1.25 * max(rows_per_rank)) + 65_536
         scan_out = device.pinned_empty(rows, ROW_ID_DTYPE)
-        join_build_out = device.pinned_empty(rows, ROW_ID_DTYPE)
-        join_probe_out = device.pinned_empty(rows, ROW_ID_DTYPE)
+        join_build_out = device.pinned_empty(join_capacity, ROW_ID_DTYPE)
+        join_probe_out = device.pinned_empty(join_capacity, ROW_ID_DTYPE)
         host_blocks = tables.host_blocks()
         h2d = sum(block.bytes for block in host_blocks)
         d2h = 0
@@ -498,11 +477,17 @@ def main() -> None:
             mark("scan")
             matched = scan.to_host(scan_out)
             mark("scan d2h")
-            join = device.join_hash(table_o, O_ORDERKEY, table_l, L_ORDERKEY, capi.JOIN_INNER, -1)
+            if distributed:   # the partitioned path: exchange over NVLink, then this rank's partitions of the result
+                join, _ = distributed_join(table_o, table_l)
+            else:
+                join = device.join_hash(table_o, O_ORDERKEY, table_l, L_ORDERKEY, capi.JOIN_INNER, -1)
             mark("join")
             pairs = join.to_host(join_build_out, join_probe_out)
             mark("join d2h")
-            aggregate = device.aggregate_hash(table_l, Q1_GROUPBY, Q1_AGGREGATES, predicates=Q1_PREDICATES)
+            if distributed:
+                aggregate = distributed_q1(table_l)
+            else:
+                aggregate = device.aggregate_hash(table_l, Q1_GROUPBY, Q1_AGGREGATES, predicates=Q1_PREDICATES)
             mark("aggregate")
             d2h = len(matched) * 8 + len(pairs[1]) * 16 + aggregate.group_count * (8 + 8 * len(Q1_AGGREGATES))
             scan.free()
@@ -558,9 +543,37 @@ def main() -> None:
     if not args.no_verify:
         verification = verify_results(device, tables, lineitem, orders, outputs, distributed, rank, world)
         if distributed:
+            # the partitioned operators against the oracle over the union of all shards, at a size the oracle handles
+            # (bit-exact RowIDs in reference order, Q1 within 1e-6) — the same checks tests/gpu_distributed_worker.py makes
+            sys.path.insert(0, os.path.join(REPO, "tests"))
+            from gpu_distributed_worker import run_distributed_checks
+            try:
+                summary = run_distributed_checks(device, rank, world, torch_device, sf=0.1, legacy_paths=False)
+                verification["checks"].append({"name": "distributed scan/join/Q1 vs oracle (SF 0.1 per rank)", "ok": True,
+                                               "detail": summary or ""})
+            except AssertionError as error:
+                verification["checks"].append({"name": "distributed scan/join/Q1 vs oracle (SF 0.1 per rank)", "ok": False,
+                                               "detail": str(error)[:400]})
+                verification["ok"] = False
+            # the timed run itself: every lineitem row joins exactly once, across all ranks
+            totals = [None] * world
+            dist.all_gather_object(totals, (int(outputs[1]), rows))
+            pairs_ok = sum(t[0] for t in totals) == sum(t[1] for t in totals)
+            verification["checks"].append({"name": "timed distributed join: pairs over all ranks == lineitem rows", "ok": pairs_ok,
+                                           "detail": str(totals)})
+            verification["ok"] = verification["ok"] and pairs_ok
             flags = [None] * world
             dist.all_gather_object(flags, verification["ok"])
             verification["all_ranks_ok"] = all(flags)
+
+    phase_summary = None
+    if distributed:
+        phase_summary = {}
+        for name, samples in phases.items():
+            if samples:
+                phase_summary[name] = {key: float(np.mean([sample[key] for sample in samples])) for key in samples[0]}
+        accounted = sum(breakdown[name]["operator_ms"] for name in breakdown) + 3 * 0.035
+        phase_summary["host_gap_ms"] = max(0.0, ms_per_step - accounted)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -576,19 +589,23 @@ def main() -> None:
             "config": config,
             "detail": {"lineitem_rows_per_gpu": rows, "orders_rows_per_gpu": tables.orders.row_count,
                        "l2": "256 MB memset before every operator, inside the timed region; inputs exceed L2 anyway",
-                       "parallelism": (f"{world} ranks, each owning 1/{world} of the SF {args.sf:g} tables: chunk-partitioned "
-                                       f"scan (no collective); join = radix exchange of {{key, RowID}} tuples, one per side ("
-                                       + ("split kernel storing straight into the owners' memory over NVLink P2P; collectives: "
-                                          "count all-gather + barrier" if peers is not None else
-                                          "device split + NCCL all-to-all") +
-                                       ") + local join; aggregate = local pre-aggregation + exchange of partial groups")
+                       "parallelism": (f"{world} ranks, each owning 1/{world} of the SF {args.sf:g} tables: chunk-partitioned scan (no "
+                                       f"collective); join = radix exchange of {{key, RowID}} tuples by key & (world - 1): counts "
+                                       f"published into the peers' control blocks by kernel, fused split + NVLink P2P store "
+                                       f"kernel per side, epoch flags polled on the device, local join of the received tuples "
+                                       f"(hyb_join_hash_distributed); aggregate = local pre-aggregation, partial groups stored "
+                                       f"into every peer's arena and merged by all ranks (hyb_aggregate_hash_distributed); no "
+                                       f"NCCL collective inside the step")
                        if world > 1 else "1 GPU",
                        "outputs_per_step": {"scan_matches": int(outputs[0]), "join_pairs": int(outputs[1]), "groups": int(outputs[2])}},
-            "roofline": roofline, "operators": breakdown, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "roofline": roofline, "operators": breakdown, "phases_rank0": phase_summary, "cpu_baseline": cpu_baseline, "e2e": e2e,
             "gpu_launches": launches[0], "clocks": clocks.summary(), "verify": verification,
         }
         print(json.dumps(line))
     ok = verification is None or (verification["ok"] and verification.get("all_ranks_ok", True))
+    if group is not None:
+        barrier()
+        group.destroy()
     device.close()
     if distributed:
         dist.destroy_process_group()

@@ -109,6 +109,9 @@ struct Table {
   // > 0: a one-chunk table over a fixed device buffer whose row count changes between calls (the receive regions of a peer
   // group): descriptors are patched in place and tile maps are built once, for this many rows.
   uint32_t fixed_single_chunk_capacity = 0;
+  // != nullptr: operators that emit RowIDs of this table emit position_payload[row position] instead (JoinHash only; the
+  // tuples a rank received in a radix exchange stand for rows of the global table)
+  const hyb_row_id* position_payload = nullptr;
   ~Table();
 };
 

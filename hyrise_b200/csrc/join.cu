@@ -55,6 +55,8 @@ struct KeySource {
   unsigned long long position_count;
   uint32_t tile_count;
   uint32_t chunk_count;
+  const hyb_row_id* payload;         // != nullptr: position -> the RowID to emit (received tuples of a peer group carry the
+                                     // global RowIDs of the rows they came from); else RowIDs of this table are emitted
   uint32_t uniform_chunk_rows;       // > 0: all chunks but the last have this many rows
   uint32_t uniform_magic;            // ceil(2^(32 + shift) / uniform_chunk_rows) - 2^32  (position / rows by multiply-shift)
   uint32_t uniform_shift;
@@ -120,6 +122,7 @@ __device__ __forceinline__ KeyAt key_at(const KeySource& source, uint32_t tile, 
 }
 
 __device__ __forceinline__ hyb_row_id position_to_row_id(const KeySource& source, unsigned long long position) {
+  if (source.payload) return source.payload[position];
   if (source.filter) return source.filter[position];
   if (source.uniform_chunk_rows) {
     // positions are < 2^32 here (checked by the host): exact division by an invariant via multiply-high
@@ -1016,7 +1019,12 @@ __global__ void __launch_bounds__(kJoinThreads, 3) join_probe_write_kernel(const
         const unsigned long long at = s_start[warp][partition] + rows.rank[step];
         const hyb_row_id build_row = position_to_row_id(params.build, match);
         st_stream_v2(params.out_build + at, build_row.chunk_id, build_row.chunk_offset);
-        st_stream_v2(params.out_probe + at, ref.chunk, row_base + step * 32);
+        if (params.probe.payload) {
+          const hyb_row_id probe_row = params.probe.payload[ref.first_position + (row_base - ref.row0) + step * 32];
+          st_stream_v2(params.out_probe + at, probe_row.chunk_id, probe_row.chunk_offset);
+        } else {
+          st_stream_v2(params.out_probe + at, ref.chunk, row_base + step * 32);
+        }
       }
       __syncthreads();
       continue;
@@ -1035,7 +1043,7 @@ __global__ void __launch_bounds__(kJoinThreads, 3) join_probe_write_kernel(const
       }
       hyb_row_id probe_row;
       if (params.probe.tile_map) {
-        probe_row = hyb_row_id{ref.chunk, ref.row0 + index};
+        probe_row = params.probe.payload ? params.probe.payload[ref.first_position + index] : hyb_row_id{ref.chunk, ref.row0 + index};
       } else {
         probe_row = params.probe.filter[ref.first_position + index];
       }
@@ -1361,7 +1369,7 @@ __global__ void __launch_bounds__(kSpanThreads, 2) join_span_write_kernel(const 
   const uint32_t total = s_total;
   hyb_row_id* __restrict__ out_build = params.out_build;
   hyb_row_id* __restrict__ out_probe = params.out_probe;
-  if (!params.build.filter && params.build.uniform_chunk_rows) {
+  if (!params.build.filter && !params.build.payload && !params.probe.payload && params.build.uniform_chunk_rows) {
     // build position -> RowID by an exact multiply-shift division (all chunks but the last have uniform_chunk_rows rows)
     const uint32_t magic = params.build.uniform_magic, shift = params.build.uniform_shift;
     const uint32_t chunk_rows = params.build.uniform_chunk_rows;
@@ -1373,6 +1381,17 @@ __global__ void __launch_bounds__(kSpanThreads, 2) join_span_write_kernel(const 
       const uint32_t chunk = shift == 0 ? n : (t + ((n - t) >> 1)) >> (shift - 1);
       st_stream_v2(out_build + at, chunk, n - chunk * chunk_rows);
       st_stream_v2(out_probe + at, ref.chunk, ref.row0 + (staged.y & 0xFFFFu));
+    }
+  } else if (params.probe.payload) {
+    // received tuples: both sides emit the RowIDs that travelled with the keys; the probe side's lie in this span's slice
+    const hyb_row_id* __restrict__ probe_payload = params.probe.payload + ref.first_position;
+    for (uint32_t i = threadIdx.x; i < total; i += kSpanThreads) {
+      const uint2 staged = s_stage[i];
+      const uint32_t at = s_destination[staged.y >> 16] + i;
+      const hyb_row_id build_row = position_to_row_id(params.build, staged.x);
+      const hyb_row_id probe_row = probe_payload[staged.y & 0xFFFFu];
+      st_stream_v2(out_build + at, build_row.chunk_id, build_row.chunk_offset);
+      st_stream_v2(out_probe + at, probe_row.chunk_id, probe_row.chunk_offset);
     }
   } else {
     for (uint32_t i = threadIdx.x; i < total; i += kSpanThreads) {
@@ -1386,19 +1405,35 @@ __global__ void __launch_bounds__(kSpanThreads, 2) join_span_write_kernel(const 
 }
 #undef HYB_SPAN_DISPATCH
 
-// hyb_join_partition / hyb_join_partition_push, ranked-write pass: the stable split of one side's non-NULL
-// {key, global RowID} tuples by owner rank. Same ranking as join_probe_write_kernel, but nothing is looked up and the
-// keys stay in registers between the passes, so the pass costs one read of the key column and one 16-byte store per
-// tuple — to local buffers, or (push_to_peers) straight into the owners' memory over NVLink.
+// hyb_join_partition / hyb_join_partition_push / hyb_join_hash_distributed, ranked-write pass: the stable split of one
+// side's non-NULL {key, global RowID} tuples by owner rank. Same ranking as join_probe_write_kernel, nothing is looked up,
+// the keys stay in registers between the passes. The tile's tuples are first scattered into SHARED memory in destination
+// order and then leave in one flat loop, so every warp store is 256 contiguous bytes per array INSIDE ONE DESTINATION —
+// what NVLink wants (8-byte stores into 32-byte runs, as the direct scatter produced at world = 8, waste most of every
+// packet). Destinations are local buffers, or (push_to_peers) the owners' memory over NVLink.
+constexpr size_t kPartitionStageBytes = sizeof(uint4) * kJoinTileRows;  // dynamic shared memory of the kernel
+
 __global__ void __launch_bounds__(kJoinThreads, 3) join_partition_write_kernel(const ProbeParams params) {
-  __shared__ uint32_t s_warp_histogram[kJoinWarps][kMaxPartitions];
-  __shared__ unsigned long long s_start[kJoinWarps][kMaxPartitions];
+  extern __shared__ uint4 s_tuples[];  // kJoinTileRows x {key low, key high, RowID chunk, RowID offset}, destination-major
+  __shared__ uint32_t s_warp_histogram[kJoinWarps][kMaxPartitions];  // counts, then exclusive prefixes over the warps
+  __shared__ uint32_t s_local_start[kMaxPartitions];
+  __shared__ unsigned long long s_destination[kMaxPartitions];  // index in the destination array of staged tuple i = this + i
+  __shared__ long long* s_keys_out[kMaxPeers];
+  __shared__ long long* s_rows_out[kMaxPeers];
+  __shared__ uint32_t s_scan[kJoinWarps];
+  __shared__ uint32_t s_total;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lanes_below = (1u << lane) - 1u;
+  const uint32_t partition_count = params.partition_count;
+  const bool push = params.push_to_peers != 0;
+  if (threadIdx.x < kMaxPeers) {
+    s_keys_out[threadIdx.x] = push ? params.peer_keys[threadIdx.x] : reinterpret_cast<long long*>(params.out_build);
+    s_rows_out[threadIdx.x] = push ? params.peer_rows[threadIdx.x] : reinterpret_cast<long long*>(params.out_probe);
+  }
   const uint32_t tiles_per_cta = (params.probe.tile_count + gridDim.x - 1) / gridDim.x;
   const uint32_t tile_end = min(params.probe.tile_count, (blockIdx.x + 1) * tiles_per_cta);
   for (uint32_t tile = blockIdx.x * tiles_per_cta; tile < tile_end; ++tile) {
-    for (uint32_t p = lane; p < params.partition_count; p += 32) s_warp_histogram[warp][p] = 0;
+    for (uint32_t p = lane; p < partition_count; p += 32) s_warp_histogram[warp][p] = 0;
     __syncwarp();
     const TileRef ref = tile_ref(params.probe, tile);
     const DevSegment segment = params.probe.tile_map ? params.probe.segments[ref.chunk] : DevSegment{};
@@ -1408,10 +1443,15 @@ __global__ void __launch_bounds__(kJoinThreads, 3) join_partition_write_kernel(c
     if (codec >= kCodecFor8 && ref.row0 + chunk0 < segment.row_count) {
       for_minimum = static_cast<uint32_t>(__ldg(static_cast<const int32_t*>(segment.values) + (ref.row0 + chunk0) / HYB_FOR_BLOCK_SIZE));
     }
-    uint32_t key_low[kProbeSteps], key_high[kProbeSteps], rank[kProbeSteps], partitions[kProbeSteps / 4];
+    // this tile's run starts (exclusive scan of the count pass), in flight while the rows are ranked
+    unsigned long long run_start = 0;
+    if (threadIdx.x < partition_count) {
+      const size_t first = static_cast<size_t>(threadIdx.x) * params.probe.tile_count;
+      run_start = __ldg(params.run_starts + first + tile);
+      if (push) run_start -= __ldg(params.run_starts + first);  // peers receive a pointer to the start of their group
+    }
+    uint32_t key_low[kProbeSteps], key_high[kProbeSteps], rank[kProbeSteps];
     uint32_t emit_mask = 0;
-#pragma unroll
-    for (int q = 0; q < kProbeSteps / 4; ++q) partitions[q] = 0;
 #pragma unroll
     for (int step = 0; step < kProbeSteps; ++step) {
       const uint32_t index = chunk0 + step * 32 + lane;
@@ -1447,41 +1487,55 @@ __global__ void __launch_bounds__(kJoinThreads, 3) join_partition_write_kernel(c
       key_low[step] = static_cast<uint32_t>(static_cast<unsigned long long>(key));
       key_high[step] = static_cast<uint32_t>(static_cast<unsigned long long>(key) >> 32);
       rank[step] = earlier + __popc(emitting & lanes_below);
-      partitions[step >> 2] |= partition << (8 * (step & 3));
       emit_mask |= emit ? (1u << step) : 0u;
     }
     __syncthreads();
-    for (uint32_t p = threadIdx.x; p < params.partition_count; p += kJoinThreads) {
-      unsigned long long running = params.run_starts[static_cast<size_t>(p) * params.probe.tile_count + tile];
+    // per destination: exclusive prefix over the warp chunks, then over the destinations
+    uint32_t partition_total = 0;
+    if (threadIdx.x < partition_count) {
 #pragma unroll
       for (int w = 0; w < kJoinWarps; ++w) {
-        s_start[w][p] = running;
-        running += s_warp_histogram[w][p];
+        const uint32_t count = s_warp_histogram[w][threadIdx.x];
+        s_warp_histogram[w][threadIdx.x] = partition_total;
+        partition_total += count;
       }
+    }
+    const uint32_t inclusive = warp_inclusive_scan(partition_total, lane);
+    if (lane == 31) s_scan[warp] = inclusive;
+    __syncthreads();
+    if (threadIdx.x < partition_count) {
+      uint32_t before = 0;
+#pragma unroll
+      for (int w = 0; w < kJoinWarps; ++w) before += w < static_cast<int>(warp) ? s_scan[w] : 0u;
+      const uint32_t exclusive = before + inclusive - partition_total;
+      s_local_start[threadIdx.x] = exclusive;
+      s_destination[threadIdx.x] = run_start - exclusive;  // modulo 2^64
+      if (threadIdx.x + 1 == partition_count) s_total = exclusive + partition_total;
     }
     __syncthreads();
 #pragma unroll
     for (int step = 0; step < kProbeSteps; ++step) {
       if (!((emit_mask >> step) & 1u)) continue;
       const uint32_t index = chunk0 + step * 32 + lane;
-      const uint32_t partition = (partitions[step >> 2] >> (8 * (step & 3))) & 0xFFu;
-      const unsigned long long at = s_start[warp][partition] + rank[step];
+      const uint32_t partition = key_low[step] & params.partition_mask;
       hyb_row_id row;
       if (params.probe.tile_map) {
         row = hyb_row_id{ref.chunk, ref.row0 + index};
       } else {
         row = params.probe.filter[ref.first_position + index];
       }
-      hyb_row_id* key_out = params.out_build + at;
-      hyb_row_id* row_out = params.out_probe + at;
-      if (params.push_to_peers) {
-        // index inside the group = position in the partition-major output minus the group's start
-        const unsigned long long inside = at - params.run_starts[static_cast<size_t>(partition) * params.probe.tile_count];
-        key_out = reinterpret_cast<hyb_row_id*>(params.peer_keys[partition] + inside);
-        row_out = reinterpret_cast<hyb_row_id*>(params.peer_rows[partition] + inside);
-      }
-      st_stream_v2(key_out, key_low[step], key_high[step]);
-      st_stream_v2(row_out, row.chunk_id + params.chunk_id_base, row.chunk_offset);
+      s_tuples[s_local_start[partition] + s_warp_histogram[warp][partition] + rank[step]] =
+          make_uint4(key_low[step], key_high[step], row.chunk_id + params.chunk_id_base, row.chunk_offset);
+    }
+    __syncthreads();
+    const uint32_t total = s_total;
+    for (uint32_t i = threadIdx.x; i < total; i += kJoinThreads) {
+      const uint4 tuple = s_tuples[i];
+      const uint32_t partition = tuple.x & params.partition_mask;
+      const unsigned long long at = s_destination[partition] + i;
+      const uint32_t owner = push ? partition : 0u;
+      st_stream_v2(s_keys_out[owner] + at, tuple.x, tuple.y);
+      st_stream_v2(s_rows_out[owner] + at, tuple.z, tuple.w);
     }
     __syncthreads();
   }
@@ -1554,6 +1608,7 @@ static int prepare_side(hyb_context* context, const hyb_join_side* side, SideInf
   source.segments = out->table->d_segments + size_t{side->column_id} * chunk_count;
   source.chunk_row_start = reinterpret_cast<const unsigned long long*>(out->table->d_chunk_row_start);
   source.chunk_count = chunk_count;
+  source.payload = out->table->position_payload;
   source.uniform_chunk_rows = (out->table->uniform_chunks && chunk_count) ? out->table->chunk_rows[0] : 0;
   if (source.uniform_chunk_rows) {
     // d = rows: shift = ceil(log2 d); magic = floor(2^32 * (2^shift - d) / d) + 1
@@ -2064,7 +2119,9 @@ static int partition_side(hyb_context* context, const hyb_join_side* side, uint3
   params.chunk_id_base = chunk_id_base;
   int count_blocks = 1, write_blocks = 1;
   HYB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&count_blocks, join_probe_count_kernel<false>, kJoinThreads, 0));
-  HYB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&write_blocks, join_partition_write_kernel, kJoinThreads, 0));
+  HYB_CUDA(cudaFuncSetAttribute(join_partition_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(kPartitionStageBytes)));
+  HYB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&write_blocks, join_partition_write_kernel, kJoinThreads, kPartitionStageBytes));
   uint32_t launches = 0;
   timing_kernel_begin(context);
   if (tiles) {
@@ -2102,7 +2159,8 @@ static int partition_side(hyb_context* context, const hyb_join_side* side, uint3
     if (tiles) timing_kernel_begin(context);
   }
   if (tiles) {
-    join_partition_write_kernel<<<std::min<uint32_t>(tiles, context->sm_count * std::max(write_blocks, 1)), kJoinThreads, 0, stream>>>(params);
+    join_partition_write_kernel<<<std::min<uint32_t>(tiles, context->sm_count * std::max(write_blocks, 1)), kJoinThreads,
+                                  kPartitionStageBytes, stream>>>(params);
     HYB_CUDA(cudaGetLastError());
     ++launches;
     timing_kernel_end(context);
@@ -2168,18 +2226,6 @@ __global__ void peer_publish_counts_kernel(PeerControl* const* controls, uint32_
   }
 }
 
-// Join result positions (RowIDs {0, index} into the received tuple tables) -> the global RowIDs that travelled with the keys.
-__global__ void peer_translate_kernel(hyb_row_id* __restrict__ rows, const hyb_row_id* __restrict__ received,
-                                      const unsigned long long* __restrict__ total) {
-  const unsigned long long count = *total;
-  for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; i < count;
-       i += static_cast<unsigned long long>(gridDim.x) * blockDim.x) {
-    const hyb_row_id position = rows[i];
-    const hyb_row_id global = received[position.chunk_offset];
-    st_stream_v2(rows + i, global.chunk_id, global.chunk_offset);
-  }
-}
-
 // The persistent one-chunk table over receive region `side` (ValueSegment<int64> of keys), resized to `rows`.
 static int received_table(hyb_context* context, PeerGroup* group, int side, uint64_t rows, hyb_table_t* out_handle) {
   Table* table = nullptr;
@@ -2196,6 +2242,7 @@ static int received_table(hyb_context* context, PeerGroup* group, int side, uint
     segment.vector_type = HYB_VEC_NONE;
     created->segments.push_back(segment);
     created->fixed_single_chunk_capacity = static_cast<uint32_t>(std::min<uint64_t>(group->capacity, 0xFFFFFFF0ull));
+    created->position_payload = reinterpret_cast<const hyb_row_id*>(group->region(group->rank, side == 0 ? 1 : 3));
     table = created.get();
     group->received[side] = context->next_handle++;
     context->tables.emplace(group->received[side], std::move(created));
@@ -2336,7 +2383,9 @@ int hyb_join_hash_distributed(hyb_context* context, hyb_peer_group_t group_handl
 
   // ---- 3. fused split + NVLink stores of both sides; the last CTA raises this rank's done flag everywhere ------------------
   int write_blocks = 1;
-  HYB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&write_blocks, join_partition_write_kernel, kJoinThreads, 0));
+  HYB_CUDA(cudaFuncSetAttribute(join_partition_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(kPartitionStageBytes)));
+  HYB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&write_blocks, join_partition_write_kernel, kJoinThreads, kPartitionStageBytes));
   uint32_t grids[2];
   uint32_t expected = 0;
   for (int side = 0; side < 2; ++side) {
@@ -2352,7 +2401,7 @@ int hyb_join_hash_distributed(hyb_context* context, hyb_peer_group_t group_handl
     params[side].signal_epoch = epoch;
     for (uint32_t peer = 0; peer < world; ++peer) params[side].signal_flags[peer] = &group->control(peer)->done_flag[rank];
     if (grids[side]) {
-      join_partition_write_kernel<<<grids[side], kJoinThreads, 0, stream>>>(params[side]);
+      join_partition_write_kernel<<<grids[side], kJoinThreads, kPartitionStageBytes, stream>>>(params[side]);
       HYB_CUDA(cudaGetLastError());
     }
   }
@@ -2403,15 +2452,7 @@ int hyb_join_hash_distributed(hyb_context* context, hyb_peer_group_t group_handl
   HYB_TRY(join_hash_locked(context, &local_build, &local_probe, HYB_JOIN_INNER, radix_bits, &result_handle));
   HYB_CUDA(cudaEventRecord(group->events[5], stream));
 
-  // ---- 5. positions in the received tables -> global RowIDs ----------------------------------------------------------------
-  JoinResult* result = context->join_results.at(result_handle).get();
-  const unsigned long long* total = reinterpret_cast<const unsigned long long*>(result->d_partition_offsets + result->partition_count);
-  if (result->capacity) {
-    const uint32_t grid = context->sm_count * 8;
-    peer_translate_kernel<<<grid, 256, 0, stream>>>(result->d_build, reinterpret_cast<const hyb_row_id*>(group->region(rank, 1)), total);
-    peer_translate_kernel<<<grid, 256, 0, stream>>>(result->d_probe, reinterpret_cast<const hyb_row_id*>(group->region(rank, 3)), total);
-    HYB_CUDA(cudaGetLastError());
-  }
+  // ---- 5. nothing to translate: the received tables carry the global RowIDs as their payload and the join emitted them ----
   HYB_CUDA(cudaEventRecord(group->events[6], stream));
   *out_result = result_handle;
   return HYB_OK;
