@@ -169,6 +169,8 @@ SYMBOLS = {
     "hyb_join_result_partition_offsets": [_CTX, _U64, _P],
     "hyb_join_result_copy": [_CTX, _U64, _U64, _U64, _P, _P],
     "hyb_join_result_free": [_CTX, _U64],
+    "hyb_join_result_pos_list": [_CTX, _U64, _I32, C.POINTER(_U64)],
+    "hyb_join_result_output_chunks": [_CTX, _U64, _P, C.POINTER(_U32)],
     "hyb_join_side_positions": [_CTX, C.POINTER(JoinSide), C.POINTER(_U64)],
     "hyb_join_materialize": [_CTX, C.POINTER(JoinSide), _U32, _P, _P],
     "hyb_join_partition": [_CTX, C.POINTER(JoinSide), _U32, _U32, _P, _P, C.POINTER(_U64)],
@@ -188,6 +190,7 @@ SYMBOLS = {
     "hyb_aggregate_result_row_ids": [_CTX, _U64, _P],
     "hyb_aggregate_result_values": [_CTX, _U64, _U32, _P, _P, C.POINTER(_I32)],
     "hyb_aggregate_result_free": [_CTX, _U64],
+    "hyb_aggregate_result_top_k": [_CTX, _U64, _U32, _U32, _I32, _P, C.POINTER(_U32)],
     "hyb_last_operator_stats": [_CTX, C.POINTER(OperatorStats)],
     "hyb_pos_list_device_ptr": [_CTX, _U64, C.POINTER(_P)],
     "hyb_join_result_device_ptrs": [_CTX, _U64, C.POINTER(_P), C.POINTER(_P)],

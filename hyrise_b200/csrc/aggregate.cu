@@ -488,6 +488,39 @@ __global__ void __launch_bounds__(kAggThreads) aggregate_general_kernel(const Ag
   }
 }
 
+// The group table is sized for the worst case (2 slots per input row, at most 2^20 to start with); what leaves the
+// device is only the occupied slots: this kernel packs them (order irrelevant: the host orders groups by their first row
+// or, with immediate keys, by key) into arrays of `groups` entries with the layout of the table itself.
+__global__ void aggregate_compact_kernel(const GroupTable table, uint32_t aggregate_count, uint32_t groups,
+                                         unsigned long long* __restrict__ out_words, uint32_t* __restrict__ out_null_masks,
+                                         uint32_t* __restrict__ cursor) {
+  const uint32_t capacity = table.capacity_mask + 1;
+  const uint32_t key_words = table.key_words;
+  unsigned long long* out_hashes = out_words;
+  unsigned long long* out_keys = out_hashes + groups;
+  unsigned long long* out_rows = out_keys + static_cast<size_t>(groups) * key_words;
+  unsigned long long* out_min = out_rows + groups;
+  unsigned long long* out_max = out_min + groups;
+  unsigned long long* out_accumulators = out_max + groups;
+  unsigned long long* out_counts = out_accumulators + static_cast<size_t>(groups) * aggregate_count;
+  for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < capacity; slot += gridDim.x * blockDim.x) {
+    const unsigned long long hash = table.hashes[slot];
+    if (hash == 0) continue;
+    const uint32_t at = atomicAdd(cursor, 1u);
+    if (at >= groups) continue;  // cannot happen: `groups` is the table's own insert counter
+    out_hashes[at] = hash;
+    for (uint32_t w = 0; w < key_words; ++w) out_keys[static_cast<size_t>(at) * key_words + w] = table.keys[static_cast<size_t>(slot) * key_words + w];
+    out_rows[at] = table.rows[slot];
+    out_min[at] = table.min_position[slot];
+    out_max[at] = table.max_position[slot];
+    for (uint32_t a = 0; a < aggregate_count; ++a) {
+      out_accumulators[static_cast<size_t>(a) * groups + at] = table.accumulators[static_cast<size_t>(a) * capacity + slot];
+      out_counts[static_cast<size_t>(a) * groups + at] = table.counts[static_cast<size_t>(a) * capacity + slot];
+    }
+    out_null_masks[at] = table.null_masks[slot];
+  }
+}
+
 __global__ void gather_row_ids_kernel(const unsigned long long* __restrict__ positions, uint32_t count,
                                       const hyb_row_id* __restrict__ filter, hyb_row_id* __restrict__ out) {
   const uint32_t index = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1592,6 +1625,8 @@ static int aggregate_hash_locked(hyb_context* context, const hyb_aggregate_query
     filter = find_pos_list(context, query->filter);
     HYB_CHECK(filter, HYB_ERR_NOT_FOUND, "unknown filter handle");
     HYB_CHECK(filter->table == query->table, HYB_ERR_INVALID, "filter belongs to a different table");
+    HYB_CHECK(!filter->may_hold_null_rows, HYB_ERR_UNSUPPORTED,
+              "aggregating a PosList with NULL_ROW_IDs (an outer join's output) runs on the CPU operator");
   }
   HYB_TRY(sync_table_descriptors(context, table));
   cudaStream_t stream = context->stream;
@@ -1998,18 +2033,40 @@ static int aggregate_hash_locked(hyb_context* context, const hyb_aggregate_query
       }
       if (!kernel_timed) timing_kernel_end(context);
       kernel_timed = true;
-      std::vector<uint8_t> host(bytes);
-      HYB_CUDA(cudaMemcpyAsync(host.data(), scratch, bytes, cudaMemcpyDeviceToHost, stream));
+      // {groups inserted, overflow}: 8 bytes decide whether the table was big enough
+      uint32_t table_control[2] = {0, 0};
+      HYB_CUDA(cudaMemcpyAsync(table_control, group_table.control, sizeof(table_control), cudaMemcpyDeviceToHost, stream));
       HYB_CUDA(cudaStreamSynchronize(stream));
-      device_free(context, scratch);
-      const auto* words = reinterpret_cast<const uint64_t*>(host.data());
-      const size_t word_count = capacity * per_slot_words;
-      const auto* tail = reinterpret_cast<const uint32_t*>(words + word_count);
-      const uint32_t overflow = tail[2 * capacity + 1];
-      if (overflow) {
+      if (table_control[1]) {
+        device_free(context, scratch);
         capacity <<= 3;
         continue;
       }
+      // pack the occupied slots on the device; only they travel to the host
+      const uint64_t group_slots = table_control[0];
+      const size_t compact_words = std::max<uint64_t>(group_slots, 1) * per_slot_words;
+      const size_t compact_bytes = sizeof(uint64_t) * compact_words + sizeof(uint32_t) * std::max<uint64_t>(group_slots, 1) + 64;
+      void* compact = nullptr;
+      HYB_TRY(device_alloc(context, compact_bytes, &compact));
+      auto* compact_null_masks = reinterpret_cast<uint32_t*>(static_cast<unsigned long long*>(compact) + compact_words);
+      uint32_t* compact_cursor = compact_null_masks + std::max<uint64_t>(group_slots, 1);
+      HYB_CUDA(cudaMemsetAsync(compact_cursor, 0, sizeof(uint32_t), stream));
+      if (group_slots) {
+        const uint32_t compact_grid = static_cast<uint32_t>(std::min<uint64_t>((capacity + 255) / 256, uint64_t{context->sm_count} * 16));
+        aggregate_compact_kernel<<<compact_grid, 256, 0, stream>>>(group_table, aggregate_count, static_cast<uint32_t>(group_slots),
+                                                                   static_cast<unsigned long long*>(compact), compact_null_masks,
+                                                                   compact_cursor);
+        HYB_CUDA(cudaGetLastError());
+        ++launches;
+      }
+      std::vector<uint8_t> host(compact_bytes);
+      HYB_CUDA(cudaMemcpyAsync(host.data(), compact, compact_bytes, cudaMemcpyDeviceToHost, stream));
+      HYB_CUDA(cudaStreamSynchronize(stream));
+      device_free(context, compact);
+      device_free(context, scratch);
+      const auto* words = reinterpret_cast<const uint64_t*>(host.data());
+      const uint64_t table_capacity = capacity;
+      capacity = group_slots;  // the parsing below walks the packed arrays
       const uint64_t* h_hashes = words;
       const uint64_t* h_keys = h_hashes + capacity;
       const uint64_t* h_rows = h_keys + capacity * key_words;
@@ -2017,7 +2074,8 @@ static int aggregate_hash_locked(hyb_context* context, const hyb_aggregate_query
       const uint64_t* h_max = h_min + capacity;
       const uint64_t* h_acc = h_max + capacity;
       const uint64_t* h_counts = h_acc + capacity * aggregate_count;
-      const uint32_t* h_null_masks = tail + capacity;
+      const uint32_t* h_null_masks = reinterpret_cast<const uint32_t*>(words + compact_words);
+      (void)table_capacity;
       for (uint64_t slot = 0; slot < capacity; ++slot) {
         if (h_hashes[slot] == 0) continue;
         HostGroup group;
@@ -2437,6 +2495,172 @@ int hyb_aggregate_result_values(hyb_context* context, hyb_aggregate_result_t han
   if (out_values && !column.values.empty()) std::memcpy(out_values, column.values.data(), column.values.size());
   if (out_nulls && !column.nulls.empty()) std::memcpy(out_nulls, column.nulls.data(), column.nulls.size());
   if (out_value_type) *out_value_type = column.value_type;
+  return HYB_OK;
+}
+
+}  // extern "C"
+
+// ---- Sort + Limit over one aggregate column: top-k selection on the device -------------------------------------------------
+namespace {
+
+// Sort key of a candidate: the value mapped to an order-preserving uint64 (largest first after the mapping), ties broken by
+// the smaller group index (Sort is stable). 0 = "taken / not a candidate".
+struct TopKCandidate {
+  unsigned long long key;
+  uint32_t index;
+};
+
+__device__ __forceinline__ bool top_k_before(const TopKCandidate& a, const TopKCandidate& b) {
+  return a.key > b.key || (a.key == b.key && a.index < b.index);
+}
+
+// Every CTA selects the k best of its slice by k rounds of a block-wide arg-max (k is small: LIMIT 10 / 20 / 100);
+// candidates[cta * k + i] = i-th best of the slice. A second launch with one CTA merges the per-CTA candidates.
+__global__ void __launch_bounds__(256) top_k_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ indexes,
+                                                    uint32_t count, uint32_t k, TopKCandidate* __restrict__ candidates) {
+  __shared__ TopKCandidate s_best[8];
+  __shared__ TopKCandidate s_round;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t per_cta = (count + gridDim.x - 1) / gridDim.x;
+  const uint32_t begin = blockIdx.x * per_cta, end = min(count, begin + per_cta);
+  TopKCandidate previous{~0ull, 0u};  // everything at or before `previous` in the order has been emitted
+  bool first_round = true;
+  for (uint32_t round = 0; round < k; ++round) {
+    TopKCandidate best{0ull, 0xFFFFFFFFu};
+    for (uint32_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
+      const TopKCandidate candidate{keys[i], indexes ? indexes[i] : i};
+      if (candidate.key == 0) continue;
+      const bool emitted = !first_round && !top_k_before(previous, candidate);  // candidate <= previous in the order
+      if (!emitted && (best.index == 0xFFFFFFFFu || top_k_before(candidate, best))) best = candidate;
+    }
+#pragma unroll
+    for (int delta = 16; delta > 0; delta >>= 1) {
+      TopKCandidate other;
+      other.key = __shfl_xor_sync(0xFFFFFFFFu, best.key, delta);
+      other.index = __shfl_xor_sync(0xFFFFFFFFu, best.index, delta);
+      if (other.index != 0xFFFFFFFFu && (best.index == 0xFFFFFFFFu || top_k_before(other, best))) best = other;
+    }
+    if (lane == 0) s_best[warp] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      TopKCandidate winner = s_best[0];
+      for (int w = 1; w < 8; ++w) {
+        if (s_best[w].index != 0xFFFFFFFFu && (winner.index == 0xFFFFFFFFu || top_k_before(s_best[w], winner))) winner = s_best[w];
+      }
+      s_round = winner;
+      candidates[static_cast<size_t>(blockIdx.x) * k + round] = winner.index == 0xFFFFFFFFu ? TopKCandidate{0ull, 0xFFFFFFFFu} : winner;
+    }
+    __syncthreads();
+    if (s_round.index == 0xFFFFFFFFu) {
+      for (uint32_t rest = round + 1 + threadIdx.x; rest < k; rest += blockDim.x) {
+        candidates[static_cast<size_t>(blockIdx.x) * k + rest] = TopKCandidate{0ull, 0xFFFFFFFFu};
+      }
+      return;
+    }
+    previous = s_round;
+    first_round = false;
+    __syncthreads();
+  }
+}
+
+unsigned long long top_k_order_key(const hyb::AggregateColumn& column, uint64_t group, bool descending) {
+  // order-preserving uint64 of the value; NULLs get the smallest non-zero key (they sort last either way)
+  if (column.nulls[group]) return 1ull;
+  unsigned long long ordered = 0;
+  switch (column.value_type) {
+    case HYB_TYPE_INT32: {
+      int32_t v;
+      std::memcpy(&v, column.values.data() + group * 4, 4);
+      ordered = static_cast<unsigned long long>(static_cast<long long>(v)) ^ 0x8000000000000000ull;
+      break;
+    }
+    case HYB_TYPE_INT64: {
+      long long v;
+      std::memcpy(&v, column.values.data() + group * 8, 8);
+      ordered = static_cast<unsigned long long>(v) ^ 0x8000000000000000ull;
+      break;
+    }
+    default: {
+      double v;
+      if (column.value_type == HYB_TYPE_FLOAT32) {
+        float f;
+        std::memcpy(&f, column.values.data() + group * 4, 4);
+        v = f;
+      } else {
+        std::memcpy(&v, column.values.data() + group * 8, 8);
+      }
+      unsigned long long bits;
+      std::memcpy(&bits, &v, 8);
+      ordered = (bits >> 63) ? ~bits : (bits | 0x8000000000000000ull);
+      break;
+    }
+  }
+  if (!descending) ordered = ~ordered;
+  return std::max<unsigned long long>(ordered, 2ull);  // keep clear of the reserved 0 / 1
+}
+
+}  // namespace
+
+extern "C" {
+
+int hyb_aggregate_result_top_k(hyb_context* context, hyb_aggregate_result_t handle, uint32_t aggregate_index, uint32_t k,
+                               int32_t descending, uint32_t* out_group_indexes, uint32_t* out_count) {
+  HYB_CHECK(context && out_group_indexes && out_count, HYB_ERR_INVALID, "NULL argument");
+  HYB_CHECK(k >= 1 && k <= 1024, HYB_ERR_UNSUPPORTED, "LIMIT beyond 1024 rows is not a top-k selection: sort on the CPU operator");
+  DeviceGuard guard(context->device);
+  std::lock_guard<std::mutex> lock(context->mutex);
+  auto* result = find_aggregate_result(context, handle);
+  HYB_CHECK(result, HYB_ERR_NOT_FOUND, "unknown aggregate result handle");
+  HYB_CHECK(aggregate_index < result->columns.size(), HYB_ERR_INVALID, "aggregate_index out of range");
+  const uint64_t groups = result->group_count;
+  HYB_CHECK(groups < 0xFFFFFFF0ull, HYB_ERR_UNSUPPORTED, "too many groups");
+  *out_count = static_cast<uint32_t>(std::min<uint64_t>(k, groups));
+  if (groups == 0) return HYB_OK;
+  // the result columns live on the host (AggregateResult): stage the order keys, select on the device
+  const auto& column = result->columns[aggregate_index];
+  std::vector<unsigned long long> keys(groups);
+  for (uint64_t g = 0; g < groups; ++g) keys[g] = top_k_order_key(column, g, descending != 0);
+  cudaStream_t stream = context->stream;
+  DeviceScratch scratch(context);
+  unsigned long long* d_keys = nullptr;
+  HYB_TRY(scratch.alloc_array(groups, &d_keys));
+  HYB_CUDA(cudaMemcpyAsync(d_keys, keys.data(), sizeof(unsigned long long) * groups, cudaMemcpyHostToDevice, stream));
+  const uint32_t grid = static_cast<uint32_t>(std::min<uint64_t>((groups + 4095) / 4096, uint64_t{context->sm_count} * 2));
+  TopKCandidate* candidates = nullptr;
+  HYB_TRY(scratch.alloc_array(size_t{grid} * k + k, &candidates));
+  top_k_kernel<<<grid, 256, 0, stream>>>(d_keys, nullptr, static_cast<uint32_t>(groups), k, candidates);
+  HYB_CUDA(cudaGetLastError());
+  TopKCandidate* winners = candidates;
+  if (grid > 1) {
+    // merge: the per-CTA candidates as (key, index) arrays for one more selection by a single CTA
+    unsigned long long* merge_keys = nullptr;
+    uint32_t* merge_indexes = nullptr;
+    HYB_TRY(scratch.alloc_array(size_t{grid} * k, &merge_keys));
+    HYB_TRY(scratch.alloc_array(size_t{grid} * k, &merge_indexes));
+    std::vector<TopKCandidate> host(size_t{grid} * k);
+    HYB_CUDA(cudaMemcpyAsync(host.data(), candidates, sizeof(TopKCandidate) * host.size(), cudaMemcpyDeviceToHost, stream));
+    HYB_CUDA(cudaStreamSynchronize(stream));
+    std::vector<unsigned long long> host_keys(host.size());
+    std::vector<uint32_t> host_indexes(host.size());
+    for (size_t i = 0; i < host.size(); ++i) {
+      host_keys[i] = host[i].index == 0xFFFFFFFFu ? 0ull : host[i].key;
+      host_indexes[i] = host[i].index;
+    }
+    HYB_CUDA(cudaMemcpyAsync(merge_keys, host_keys.data(), sizeof(unsigned long long) * host_keys.size(), cudaMemcpyHostToDevice, stream));
+    HYB_CUDA(cudaMemcpyAsync(merge_indexes, host_indexes.data(), sizeof(uint32_t) * host_indexes.size(), cudaMemcpyHostToDevice, stream));
+    winners = candidates + size_t{grid} * k;
+    top_k_kernel<<<1, 256, 0, stream>>>(merge_keys, merge_indexes, static_cast<uint32_t>(host.size()), k, winners);
+    HYB_CUDA(cudaGetLastError());
+    std::vector<TopKCandidate> final_candidates(k);
+    HYB_CUDA(cudaMemcpyAsync(final_candidates.data(), winners, sizeof(TopKCandidate) * k, cudaMemcpyDeviceToHost, stream));
+    HYB_CUDA(cudaStreamSynchronize(stream));
+    for (uint32_t i = 0; i < *out_count; ++i) out_group_indexes[i] = final_candidates[i].index;
+    return HYB_OK;
+  }
+  std::vector<TopKCandidate> final_candidates(k);
+  HYB_CUDA(cudaMemcpyAsync(final_candidates.data(), winners, sizeof(TopKCandidate) * k, cudaMemcpyDeviceToHost, stream));
+  HYB_CUDA(cudaStreamSynchronize(stream));
+  for (uint32_t i = 0; i < *out_count; ++i) out_group_indexes[i] = final_candidates[i].index;
   return HYB_OK;
 }
 

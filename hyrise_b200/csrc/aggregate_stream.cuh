@@ -246,6 +246,42 @@ __device__ __forceinline__ void stream_warp_rows(const StreamPlan& plan, const S
     }
     if (!__any_sync(kFullMask, pass != 0)) continue;
 
+    // ---- values of all columns first: every dictionary lookup of the step (shared-memory reads and, for dictionaries too
+    //      large to stage, gathers through L1/L2) is in flight while the rows' groups are resolved and counted ----------
+    Value values[C][kStreamLaneRows];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      if (fast.value_segments[c] == nullptr) continue;
+      const uint32_t width = plan.value_width[c];
+      const uint32_t kind = plan.value_kind[c];
+      uint32_t codes[kStreamLaneRows];
+      stream_codes4(stage_base + plan.value_offset[c], width, local0, codes);
+      if (kind == kValueStagedDictionary) {
+        // 1-byte codes cannot leave the 256-entry staged dictionary, whatever stale bytes sit past the tile's end
+        const Value* dictionary = reinterpret_cast<const Value*>(stage_base + plan.dictionary_offset[c]);
+        if (width == 1) {
+#pragma unroll
+          for (int j = 0; j < kStreamLaneRows; ++j) values[c][j] = dictionary[codes[j]];
+        } else {
+#pragma unroll
+          for (int j = 0; j < kStreamLaneRows; ++j) values[c][j] = dictionary[((valid >> j) & 1u) ? codes[j] : 0u];
+        }
+      } else if (kind == kValueGlobalDictionary) {
+        const void* dictionary = info->dictionary[c];
+#pragma unroll
+        for (int j = 0; j < kStreamLaneRows; ++j) values[c][j] = ((pass >> j) & 1u) ? typed_load<W>(dictionary, 0, codes[j]) : Value{};
+      } else {
+#pragma unroll
+        for (int j = 0; j < kStreamLaneRows; ++j) {
+          if constexpr (W == 0) {
+            values[c][j] = __uint_as_float(codes[j]);
+          } else {
+            values[c][j] = Value{};  // unencoded 8-byte values are not streamed (host eligibility)
+          }
+        }
+      }
+    }
+
     // ---- group of every row (G == 1: the single group; else through the warp's combination table) -------------------
     uint32_t group[kStreamLaneRows];
     if constexpr (G == 1) {
@@ -350,47 +386,18 @@ __device__ __forceinline__ void stream_warp_rows(const StreamPlan& plan, const S
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       if (fast.value_segments[c] == nullptr) continue;
-      const uint32_t width = plan.value_width[c];
-      const uint32_t kind = plan.value_kind[c];
-      uint32_t codes[kStreamLaneRows];
-      stream_codes4(stage_base + plan.value_offset[c], width, local0, codes);
-      Value values[kStreamLaneRows];
-      if (kind == kValueStagedDictionary) {
-        // 1-byte codes cannot leave the 256-entry staged dictionary, whatever stale bytes sit past the tile's end
-        const Value* dictionary = reinterpret_cast<const Value*>(stage_base + plan.dictionary_offset[c]);
-        if (width == 1) {
-#pragma unroll
-          for (int j = 0; j < kStreamLaneRows; ++j) values[j] = dictionary[codes[j]];
-        } else {
-#pragma unroll
-          for (int j = 0; j < kStreamLaneRows; ++j) values[j] = dictionary[((valid >> j) & 1u) ? codes[j] : 0u];
-        }
-      } else if (kind == kValueGlobalDictionary) {
-        const void* dictionary = info->dictionary[c];
-#pragma unroll
-        for (int j = 0; j < kStreamLaneRows; ++j) values[j] = ((pass >> j) & 1u) ? typed_load<W>(dictionary, 0, codes[j]) : Value{};
-      } else {
-#pragma unroll
-        for (int j = 0; j < kStreamLaneRows; ++j) {
-          if constexpr (W == 0) {
-            values[j] = __uint_as_float(codes[j]);
-          } else {
-            values[j] = Value{};  // unencoded 8-byte values are not streamed (host eligibility)
-          }
-        }
-      }
       const bool in_chain = (need_product_mask >> c) != 0;  // some product at or after this column
       if (in_chain) {
 #pragma unroll
         for (int j = 0; j < kStreamLaneRows; ++j) {
-          const Value factor = apply_affine<W>(affine_a[c], affine_b[c], values[j]);
+          const Value factor = apply_affine<W>(affine_a[c], affine_b[c], values[c][j]);
           product[j] = c == 0 ? factor : multiply<W>(product[j], factor);
         }
       }
       if ((need_raw_mask >> c) & 1u) {
 #pragma unroll
         for (int j = 0; j < kStreamLaneRows; ++j) {
-          const Accumulator widened = static_cast<Accumulator>(values[j]);
+          const Accumulator widened = static_cast<Accumulator>(values[c][j]);
 #pragma unroll
           for (int g = 0; g < G; ++g) add_where(state.raw_sum[g][c], widened, static_cast<int>(group[j]), g);
         }

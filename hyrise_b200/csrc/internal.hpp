@@ -123,13 +123,15 @@ struct PosList {
   uint64_t* d_chunk_end = nullptr;      // inclusive prefix per chunk (chunk_count entries) + total at [chunk_count]
   std::vector<uint64_t> h_chunk_offsets;  // chunk_count + 1, filled on first query
   bool host_valid = false;
-  bool ascending = true;                // RowIDs in table order (what every TableScan produces)
+  bool ascending = true;                // RowIDs in table order (what every TableScan of a table or of an ascending list produces)
+  bool may_hold_null_rows = false;      // NULL_ROW_ID entries possible (one side of an outer join's result)
   cudaStream_t stream = nullptr;
   hyb_context* owner = nullptr;         // buffers go back to owner's DeviceCache
   ~PosList();
 };
 
 struct JoinResult {
+  hyb_table_t build_table = 0, probe_table = 0;
   int32_t mode = 0;
   int32_t radix_bits = 0;
   uint32_t partition_count = 1;
@@ -196,7 +198,7 @@ struct ContextOptions {
   int join_table = kAuto;      // HYB_JOIN_TABLE = hash | direct | rank
   bool join_span = true;       // HYB_JOIN_SPAN = 0: keep the 4096-row tile kernels for the Inner/unique fast path
   bool join_ballot_rank = false;  // HYB_JOIN_RANK = ballot: one ballot per radix bit instead of MATCH.ANY (measured slower)
-  bool scan_bulk = true;       // HYB_SCAN_BULK = 0: scan without the cp.async.bulk + mbarrier input pipeline
+  bool scan_bulk = false;      // HYB_SCAN_BULK = 0: scan without the cp.async.bulk + mbarrier input pipeline
   bool aggregate_stream = true;  // HYB_AGG_STREAM = 0: keep the register-tile fast kernel for low-cardinality group-bys
   bool aggregate_split = true;   // HYB_AGG_SPLIT = 0: never split a big dictionary over a CTA pair
 };

@@ -114,7 +114,11 @@ __device__ __forceinline__ KeyAt key_at(const KeySource& source, uint32_t tile, 
     result.valid = position < source.position_count;
     if (result.valid) {
       result.row_id = source.filter[position];
-      result.key = decode_int_key(source.segments[result.row_id.chunk_id], result.row_id.chunk_offset, result.is_null);
+      if (result.row_id.chunk_id == HYB_INVALID_CHUNK_ID) {
+        result.is_null = true;
+      } else {
+        result.key = decode_int_key(source.segments[result.row_id.chunk_id], result.row_id.chunk_offset, result.is_null);
+      }
       result.position = position;
     }
   }
@@ -332,6 +336,11 @@ __device__ __forceinline__ bool load_key1(const KeySource& source, const TileRef
   const unsigned long long position = ref.first_position + index;
   if (position >= source.position_count) return false;
   const hyb_row_id row_id = source.filter[position];
+  if (row_id.chunk_id == HYB_INVALID_CHUNK_ID) {  // NULL_ROW_ID (an outer join's unmatched side): a NULL key
+    key = 0;
+    is_null = true;
+    return true;
+  }
   key = decode_int_key(source.segments[row_id.chunk_id], row_id.chunk_offset, is_null);
   return true;
 }
@@ -1798,6 +1807,8 @@ static int join_hash_locked(hyb_context* context, const hyb_join_side* build_sid
   // ---- probe -----------------------------------------------------------------------------------------------------
   auto result = std::make_unique<JoinResult>();
   result->mode = mode;
+  result->build_table = build_side->table;
+  result->probe_table = probe_side->table;
   result->radix_bits = radix_bits;
   result->partition_count = partition_count;
   result->stream = stream;
@@ -2563,6 +2574,78 @@ int hyb_join_result_copy(hyb_context* context, hyb_join_result_t handle, uint64_
                              context->stream));
   }
   HYB_CUDA(cudaStreamSynchronize(context->stream));
+  return HYB_OK;
+}
+
+int hyb_join_result_pos_list(hyb_context* context, hyb_join_result_t handle, int32_t side, hyb_pos_list_t* out_pos_list) {
+  HYB_CHECK(context && out_pos_list && (side == 0 || side == 1), HYB_ERR_INVALID, "bad argument");
+  *out_pos_list = 0;
+  DeviceGuard guard(context->device);
+  std::lock_guard<std::mutex> lock(context->mutex);
+  auto* result = find_join_result(context, handle);
+  HYB_CHECK(result, HYB_ERR_NOT_FOUND, "unknown join result handle");
+  HYB_TRY(ensure_join_host(context, result));
+  const hyb_row_id* source = side == 0 ? result->d_build : result->d_probe;
+  HYB_CHECK(source, HYB_ERR_INVALID, "Semi/Anti joins have no build-side PosList");
+  const hyb_table_t table = side == 0 ? result->build_table : result->probe_table;
+  HYB_CHECK(table && find_table(context, table), HYB_ERR_INVALID, "the join's input table has been dropped");
+  const uint64_t total = result->h_partition_offsets.back();
+  auto list = std::make_unique<PosList>();
+  list->table = table;
+  list->chunk_count = 1;  // one list in result order (the rows of many chunks interleave)
+  list->capacity = total;
+  list->ascending = false;
+  list->may_hold_null_rows = result->mode == HYB_JOIN_LEFT || result->mode == HYB_JOIN_RIGHT;
+  list->stream = context->stream;
+  list->owner = context;
+  void* rows = nullptr;
+  void* ends = nullptr;
+  HYB_TRY(device_alloc(context, sizeof(hyb_row_id) * std::max<uint64_t>(total, 1), &rows));
+  list->d_row_ids = static_cast<hyb_row_id*>(rows);
+  HYB_TRY(device_alloc(context, sizeof(uint64_t) * 2, &ends));
+  list->d_chunk_end = static_cast<uint64_t*>(ends);
+  if (total) HYB_CUDA(cudaMemcpyAsync(rows, source, sizeof(hyb_row_id) * total, cudaMemcpyDeviceToDevice, context->stream));
+  const uint64_t host_ends[2] = {total, total};
+  HYB_CUDA(cudaMemcpyAsync(ends, host_ends, sizeof(host_ends), cudaMemcpyHostToDevice, context->stream));
+  HYB_CUDA(cudaStreamSynchronize(context->stream));
+  const auto id = context->next_handle++;
+  context->pos_lists.emplace(id, std::move(list));
+  *out_pos_list = id;
+  return HYB_OK;
+}
+
+int hyb_join_result_output_chunks(hyb_context* context, hyb_join_result_t handle, uint64_t* out_offsets, uint32_t* inout_count) {
+  HYB_CHECK(context && inout_count, HYB_ERR_INVALID, "NULL argument");
+  DeviceGuard guard(context->device);
+  std::lock_guard<std::mutex> lock(context->mutex);
+  auto* result = find_join_result(context, handle);
+  HYB_CHECK(result, HYB_ERR_NOT_FOUND, "unknown join result handle");
+  HYB_TRY(ensure_join_host(context, result));
+  // probe(): one PosList per non-empty partition and PROBE_SIZE_PER_CHUNK slice of it (join_hash_steps.hpp:47, :644-655)
+  constexpr uint64_t kProbeSizePerChunk = uint64_t{HYB_DEFAULT_CHUNK_SIZE} * 2;
+  std::vector<uint64_t> list_sizes;
+  for (uint32_t partition = 0; partition < result->partition_count; ++partition) {
+    const uint64_t rows = result->h_partition_offsets[partition + 1] - result->h_partition_offsets[partition];
+    for (uint64_t begin = 0; begin < rows; begin += kProbeSizePerChunk) list_sizes.push_back(std::min(kProbeSizePerChunk, rows - begin));
+  }
+  // write_output_chunks (join_output_writing.cpp:247-296): merge small lists
+  constexpr uint64_t kMinSize = 1000, kMaxSize = kMinSize * 4;
+  std::vector<uint64_t> offsets;
+  uint64_t position = 0;
+  for (size_t list = 0; list < list_sizes.size();) {
+    uint64_t size = list_sizes[list];
+    offsets.push_back(position);
+    while (list + 1 < list_sizes.size() && size < kMinSize && size + list_sizes[list + 1] < kMaxSize) size += list_sizes[++list];
+    position += size;
+    ++list;
+  }
+  offsets.push_back(position);
+  const uint32_t chunk_count = static_cast<uint32_t>(offsets.size() - 1);
+  if (out_offsets) {
+    HYB_CHECK(*inout_count >= chunk_count, HYB_ERR_INVALID, "out_offsets holds fewer than the " + std::to_string(chunk_count) + " chunks");
+    std::copy(offsets.begin(), offsets.end(), out_offsets);
+  }
+  *inout_count = chunk_count;
   return HYB_OK;
 }
 

@@ -29,7 +29,7 @@
 
 namespace hyb {
 
-constexpr int kScanThreads = 256;
+constexpr int kScanThreads = 512;  // 16 warps x 1024 rows: 16384-row tiles (see the look-back note at scan_kernel)
 constexpr int kScanWarps = kScanThreads / 32;
 constexpr int kScanIterations = 4;                       // 8 rows per thread per iteration
 constexpr int kScanWarpRows = 32 * 8 * kScanIterations;  // rows owned by one warp in a tile (contiguous)
@@ -552,7 +552,7 @@ __device__ __forceinline__ uint32_t evaluate8_staged(const DevSegment& segment, 
   return mask & valid;
 }
 
-__global__ void __launch_bounds__(kBulkThreads, 4) scan_bulk_kernel(const ScanParams params, const uint32_t stage_bytes) {
+__global__ void __launch_bounds__(kBulkThreads, 2) scan_bulk_kernel(const ScanParams params, const uint32_t stage_bytes) {
   extern __shared__ __align__(128) unsigned char s_dynamic[];  // kBulkStages input stages, then the match staging
   __shared__ __align__(8) unsigned long long s_full[kBulkStages], s_empty[kBulkStages], s_ready[2];
   __shared__ uint4 s_info[kBulkStages];  // {tile, chunk, row0 | last-tile-of-chunk << 31, bytes per row}
@@ -732,6 +732,7 @@ struct FilteredScanParams {
   uint32_t* ticket;
   hyb_row_id* out;
   unsigned long long* out_total;      // [0] = total matches
+  uint32_t null_row_matches;          // 1: the predicate is IS NULL — a NULL_ROW_ID (outer join) is a NULL value and matches
 };
 
 __global__ void __launch_bounds__(kScanThreads) filtered_scan_kernel(const FilteredScanParams params) {
@@ -757,9 +758,13 @@ __global__ void __launch_bounds__(kScanThreads) filtered_scan_kernel(const Filte
       const unsigned long long index = first + j;
       if (index < params.input_count) {
         rows[j] = params.input[index];
-        const DevSegment& segment = params.segments[rows[j].chunk_id];
-        const ChunkTest& test = params.tests[rows[j].chunk_id];
-        if (evaluate1(segment, test, rows[j].chunk_offset)) mask |= 1u << j;
+        if (rows[j].chunk_id != HYB_INVALID_CHUNK_ID) {
+          const DevSegment& segment = params.segments[rows[j].chunk_id];
+          const ChunkTest& test = params.tests[rows[j].chunk_id];
+          if (evaluate1(segment, test, rows[j].chunk_offset)) mask |= 1u << j;
+        } else if (params.null_row_matches) {  // NULL_ROW_ID (outer join): the value is NULL; only IS NULL holds
+          mask |= 1u << j;
+        }
       }
     }
     const uint32_t count = __popc(mask);
@@ -1019,6 +1024,7 @@ int hyb_table_scan(hyb_context* context, hyb_table_t table_handle, const hyb_sca
       params.ticket = reinterpret_cast<uint32_t*>(static_cast<unsigned long long*>(status) + tile_count);
       params.out = result->d_row_ids;
       params.out_total = total;
+      params.null_row_matches = predicate->condition == HYB_PRED_IS_NULL;
       int blocks_per_sm = 0;
       HYB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, filtered_scan_kernel, kScanThreads, 0));
       const uint32_t grid = std::min<uint32_t>(tile_count, context->sm_count * std::max(blocks_per_sm, 1));
@@ -1026,8 +1032,19 @@ int hyb_table_scan(hyb_context* context, hyb_table_t table_handle, const hyb_sca
       HYB_CUDA(cudaGetLastError());
     }
     timing_kernel_end(context);
-    pos_list_chunk_ends_kernel<<<(chunk_count + 1 + 127) / 128, 128, 0, context->stream>>>(
-        result->d_row_ids, total, chunk_count, reinterpret_cast<unsigned long long*>(result->d_chunk_end));
+    if (filter->ascending) {
+      pos_list_chunk_ends_kernel<<<(chunk_count + 1 + 127) / 128, 128, 0, context->stream>>>(
+          result->d_row_ids, total, chunk_count, reinterpret_cast<unsigned long long*>(result->d_chunk_end));
+    } else {
+      // input in another order than the table's (a join's output, abstract_dereferenced_column_table_scan_impl.cpp:49-86):
+      // the matches keep the input order and form ONE list
+      result->chunk_count = 1;
+      result->ascending = false;
+      result->may_hold_null_rows = filter->may_hold_null_rows && predicate->condition == HYB_PRED_IS_NULL;
+      pos_list_chunk_ends_kernel<<<1, 128, 0, context->stream>>>(result->d_row_ids, total, 0u,
+                                                                 reinterpret_cast<unsigned long long*>(result->d_chunk_end));
+      HYB_CUDA(cudaMemcpyAsync(result->d_chunk_end + 1, result->d_chunk_end, sizeof(uint64_t), cudaMemcpyDeviceToDevice, context->stream));
+    }
     HYB_CUDA(cudaGetLastError());
     device_free(context, status);
     launches = 3;

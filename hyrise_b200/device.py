@@ -175,6 +175,20 @@ class DeviceJoinResult:
                                                     None if build is None else build.ctypes.data, probe.ctypes.data))
         return (None if build is None else build[:pairs]), probe[:pairs]
 
+    def pos_list(self, side: int) -> "DevicePosList":
+        """hyb_join_result_pos_list: one side (0 = build, 1 = probe) as a PosList on that side's table, in result order."""
+        handle = C.c_uint64()
+        check(self.context.lib.hyb_join_result_pos_list(self.context.ptr, self.handle, side, C.byref(handle)))
+        return DevicePosList(self.context, handle.value)
+
+    def output_chunks(self) -> np.ndarray:
+        """hyb_join_result_output_chunks: offsets of the chunks write_output_chunks cuts the result into."""
+        count = C.c_uint32()
+        check(self.context.lib.hyb_join_result_output_chunks(self.context.ptr, self.handle, None, C.byref(count)))
+        offsets = np.zeros(count.value + 1, dtype=np.uint64)
+        check(self.context.lib.hyb_join_result_output_chunks(self.context.ptr, self.handle, offsets.ctypes.data, C.byref(count)))
+        return offsets
+
     def free(self) -> None:
         if self.handle:
             check(self.context.lib.hyb_join_result_free(self.context.ptr, self.handle))
@@ -189,6 +203,7 @@ class AggregateOutput:
     values: list[np.ndarray]
     nulls: list[np.ndarray]
     value_types: list[int]
+    result_handle: int = 0   # != 0: the device-side result is still alive (aggregate_hash(..., keep_result=True))
 
 
 class DevicePeerGroup:
@@ -332,7 +347,18 @@ class DeviceContext:
         keepalive += [predicate_structs, groupby, defs]
         return query, keepalive
 
-    def _collect_aggregate(self, handle: int, aggregate_count: int) -> AggregateOutput:
+    def aggregate_top_k(self, result_handle: int, aggregate_index: int, k: int, descending: bool = True) -> np.ndarray:
+        """hyb_aggregate_result_top_k on a result kept alive with aggregate_hash(..., keep_result=True)."""
+        indexes = np.zeros(k, dtype=np.uint32)
+        count = C.c_uint32()
+        check(self.lib.hyb_aggregate_result_top_k(self.ptr, result_handle, aggregate_index, k, int(descending),
+                                                  indexes.ctypes.data, C.byref(count)))
+        return indexes[: count.value]
+
+    def free_aggregate_result(self, result_handle: int) -> None:
+        check(self.lib.hyb_aggregate_result_free(self.ptr, result_handle))
+
+    def _collect_aggregate(self, handle: int, aggregate_count: int, keep_result: bool = False) -> AggregateOutput:
         try:
             groups, immediate = C.c_uint64(), C.c_int32()
             check(self.lib.hyb_aggregate_result_info(self.ptr, handle, C.byref(groups), C.byref(immediate)))
@@ -351,17 +377,20 @@ class DeviceContext:
                 nulls.append(null[:count].astype(bool))
                 types.append(value_type.value)
         finally:
-            check(self.lib.hyb_aggregate_result_free(self.ptr, handle))
-        return AggregateOutput(count, bool(immediate.value), row_ids, values, nulls, types)
+            if not keep_result:
+                check(self.lib.hyb_aggregate_result_free(self.ptr, handle))
+        output = AggregateOutput(count, bool(immediate.value), row_ids, values, nulls, types)
+        output.result_handle = handle if keep_result else 0
+        return output
 
     def aggregate_hash(self, table: DeviceTable, groupby_column_ids: Sequence[int], aggregates: Sequence[Aggregate],
                        predicates: Sequence[Predicate] = (), input_filter: DevicePosList | None = None,
-                       ) -> AggregateOutput:
+                       keep_result: bool = False) -> AggregateOutput:
         query, keepalive = self._aggregate_query(table, groupby_column_ids, aggregates, predicates, input_filter)
         handle = C.c_uint64()
         check(self.lib.hyb_aggregate_hash(self.ptr, C.byref(query), C.byref(handle)))
         del keepalive
-        return self._collect_aggregate(handle.value, len(aggregates))
+        return self._collect_aggregate(handle.value, len(aggregates), keep_result)
 
     def last_stats(self) -> capi.OperatorStats:
         stats = capi.OperatorStats()

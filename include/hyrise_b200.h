@@ -343,6 +343,27 @@ int hyb_join_result_copy(hyb_context* context, hyb_join_result_t result, uint64_
 int hyb_join_result_free(hyb_context* context, hyb_join_result_t result);
 
 /*
+ * Composing operators on the device: one side of a join result as a PosList on that side's table — the
+ * reference table a following operator of the plan consumes (join_output_writing.cpp:95-200: output ReferenceSegments always
+ * point at the ORIGINAL data table, which is what the RowIDs of a result already do). side: 0 = build, 1 = probe. The list
+ * is in result order (not table order: `hyb_pos_list_info` reports one chunk), may hold NULL_ROW_ID for outer joins, and is
+ * accepted as `filter` / `input_filter` by hyb_table_scan, hyb_join_hash and hyb_aggregate_hash like a scan's PosList:
+ * scans keep the input order (abstract_dereferenced_column_table_scan_impl.cpp:49-86: matches are positions of the input
+ * list, mapped back to the referenced RowIDs by table_scan.cpp:150-197), NULL rows never match / never join.
+ */
+int hyb_join_result_pos_list(hyb_context* context, hyb_join_result_t result, int32_t side, hyb_pos_list_t* out_pos_list);
+
+/*
+ * The chunks write_output_chunks would cut the result into (join_output_writing.cpp:205-340): the PosLists probe() emits —
+ * one per non-empty radix partition, cut every PROBE_SIZE_PER_CHUNK = 131 070 probe elements of the partition
+ * (join_hash_steps.hpp:47, :655) — merged while they hold fewer than MIN_SIZE = 1000 rows and the merge stays below
+ * MAX_SIZE = 4000 (:255-296). out_offsets receives *inout_count + 1 offsets into the flat pair list; call with
+ * out_offsets = NULL to get the count. (Slices are cut over the emitted rows of a partition: without secondary
+ * predicates and Bloom-filter false positives that is the reference's element count for PK-FK joins; see DESIGN.md.)
+ */
+int hyb_join_result_output_chunks(hyb_context* context, hyb_join_result_t result, uint64_t* out_offsets, uint32_t* inout_count);
+
+/*
  * Multi-GPU radix exchange, step 1 (materialize_input, join_hash_steps.hpp:274-420, without the Bloom filter): write one
  * join side as {key, RowID} tuples into caller-provided DEVICE buffers of hyb_join_side_positions() elements each:
  * out_keys[i] = key as int64, out_row_ids[i] = chunk_id + chunk_id_base | chunk_offset << 32, in row order. Rows with a
@@ -504,6 +525,15 @@ int hyb_aggregate_result_row_ids(hyb_context* context, hyb_aggregate_result_t re
 int hyb_aggregate_result_values(hyb_context* context, hyb_aggregate_result_t result, uint32_t aggregate_index,
                                 void* out_values, uint8_t* out_nulls, int32_t* out_value_type);
 int hyb_aggregate_result_free(hyb_context* context, hyb_aggregate_result_t result);
+
+/*
+ * Sort + Limit over an aggregate's output (operators/sort.cpp, operators/limit.cpp — `ORDER BY <aggregate> DESC LIMIT k`,
+ * the tail of TPC-H Q3 / Q10 / Q18): the k groups with the largest (descending != 0) or smallest values of aggregate
+ * `aggregate_index`, ties in group order (Sort is stable). The values are sorted on the device (top-k selection kernel);
+ * out_group_indexes receives min(k, group_count) indexes into the result's groups. NULL values sort last.
+ */
+int hyb_aggregate_result_top_k(hyb_context* context, hyb_aggregate_result_t result, uint32_t aggregate_index, uint32_t k,
+                               int32_t descending, uint32_t* out_group_indexes, uint32_t* out_count);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Instrumentation (fills the reference's performance_data, operators/operator_performance_data.hpp:46-97)

@@ -76,6 +76,9 @@ def main():
                    LINEITEM_COLUMNS)
         tbl_to_npz(os.path.join(REF, "tpch", scale, "orders.tbl"), os.path.join(tpch, f"{scale}_orders.npz"),
                    ORDERS_COLUMNS)
+    # Q3 (tpch_queries.cpp:92-109) additionally filters customer by c_mktsegment
+    tbl_to_npz(os.path.join(REF, "tpch", "sf-0.01", "customer.tbl"), os.path.join(tpch, "sf-0.01_customer.npz"),
+               ["c_custkey", "c_mktsegment"])
 
 
 if __name__ == "__main__":

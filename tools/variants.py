@@ -18,6 +18,7 @@ def main():
     parser = argparse.ArgumentParser()
     parser.add_argument("--sf", type=float, default=10.0)
     parser.add_argument("--repeat", type=int, default=5)
+    parser.add_argument("--only", default="scan,join,aggregate")
     args = parser.parse_args()
     import torch
     tables = TpchTables(args.sf, seed=42)
@@ -41,16 +42,17 @@ def main():
         print(f"{name:12s} {str(options):70s} kernel {kernel:.4f} ms  operator {np.median([s[1] for s in samples[1:]]):.4f} ms  "
               f"launches {samples[-1][2]}  {samples[-1][3] / kernel / 1e6:.0f} GB/s", flush=True)
 
-    for bulk in ("1", "0"):
+    only = args.only.split(",")
+    for bulk in ("1", "0") if "scan" in only else ():
         timed("scan", {"scan_bulk": bulk}, lambda: device.table_scan(lineitem, SCAN_PREDICATE))
     for options in ({"join_table": "auto", "join_span": "1", "join_rank": "ballot"},
                     {"join_table": "auto", "join_span": "1", "join_rank": "match"},
                     {"join_table": "direct", "join_span": "1", "join_rank": "ballot"},
                     {"join_table": "direct", "join_span": "0", "join_rank": "ballot"},
-                    {"join_table": "hash", "join_span": "1", "join_rank": "ballot"}):
+                    {"join_table": "hash", "join_span": "1", "join_rank": "ballot"}) if "join" in only else ():
         timed("join", options, lambda: device.join_hash(orders, O_ORDERKEY, lineitem, L_ORDERKEY, capi.JOIN_INNER, -1))
     device.set_option("join_table", "auto")
-    for stream in ("1", "0"):
+    for stream in ("1", "0") if "aggregate" in only else ():
         timed("aggregate", {"aggregate_stream": stream},
               lambda: device.aggregate_hash(lineitem, Q1_GROUPBY, Q1_AGGREGATES, predicates=Q1_PREDICATES))
     device.close()
