@@ -36,6 +36,12 @@ build/tpch_operators: examples/tpch_operators.cpp include/hyrise_b200.hpp includ
 	$(CXX) -O2 -std=c++17 -Wall -Wextra -Iinclude -o $@ examples/tpch_operators.cpp -Lhyrise_b200/lib -lhyrise_b200 -lhyb_tpch \
 		-Wl,-rpath,'$$ORIGIN/../hyrise_b200/lib'
 
+# Host-only check of the mirror's predicate normalisation against the reference's own test expectations.
+build/predicate_cast_check: tests/cpp/predicate_cast_check.cpp include/hyrise_b200.hpp include/hyrise_b200.h $(LIB)
+	@mkdir -p build
+	$(CXX) -O1 -std=c++17 -Wall -Wextra -Iinclude -o $@ tests/cpp/predicate_cast_check.cpp -Lhyrise_b200/lib -lhyrise_b200 \
+		-Wl,-rpath,'$$ORIGIN/../hyrise_b200/lib'
+
 clean:
 	rm -rf build $(LIB) $(TPCH_LIB)
 	$(MAKE) -C oracle clean

@@ -66,10 +66,26 @@ const void* BlockSet::translate(const void* host, size_t bytes) const {
   return nullptr;
 }
 
+// Descriptor arrays / tile maps: cached device blocks when the table knows its context (every table created through the
+// C-ABI does), driver allocations otherwise.
+static cudaError_t table_alloc(hyb_context* owner, size_t bytes, void** out) {
+  if (owner) return device_alloc(owner, bytes, out) == HYB_OK ? cudaSuccess : cudaErrorMemoryAllocation;
+  return cudaMalloc(out, bytes);
+}
+
+static void table_free(hyb_context* owner, void* ptr) {
+  if (!ptr) return;
+  if (owner) {
+    device_free(owner, ptr);
+  } else {
+    cudaFree(ptr);
+  }
+}
+
 Table::~Table() {
-  if (d_segments) cudaFree(d_segments);
-  if (d_chunk_row_start) cudaFree(d_chunk_row_start);
-  for (auto& entry : d_tile_maps) cudaFree(entry.second.first);
+  table_free(owner, d_segments);
+  table_free(owner, d_chunk_row_start);
+  for (auto& entry : d_tile_maps) table_free(owner, entry.second.first);
 }
 
 PosList::~PosList() {
@@ -172,11 +188,15 @@ int sync_table_descriptors(hyb_context* context, Table* table) {
   if (table->d_chunk_capacity < chunk_count || !table->d_segments) {
     // Descriptor arrays are read by kernels already queued on the stream: wait before replacing them.
     HYB_CUDA(cudaStreamSynchronize(context->stream));
-    if (table->d_segments) cudaFree(table->d_segments);
-    if (table->d_chunk_row_start) cudaFree(table->d_chunk_row_start);
+    table_free(table->owner, table->d_segments);
+    table_free(table->owner, table->d_chunk_row_start);
+    table->d_segments = nullptr;
+    table->d_chunk_row_start = nullptr;
     table->d_chunk_capacity = std::max<uint32_t>(chunk_count, 16);
-    HYB_CUDA(cudaMalloc(&table->d_segments, sizeof(DevSegment) * size_t{table->d_chunk_capacity} * table->column_count));
-    HYB_CUDA(cudaMalloc(&table->d_chunk_row_start, sizeof(uint64_t) * (size_t{table->d_chunk_capacity} + 1)));
+    HYB_CUDA(table_alloc(table->owner, sizeof(DevSegment) * size_t{table->d_chunk_capacity} * table->column_count,
+                         reinterpret_cast<void**>(&table->d_segments)));
+    HYB_CUDA(table_alloc(table->owner, sizeof(uint64_t) * (size_t{table->d_chunk_capacity} + 1),
+                         reinterpret_cast<void**>(&table->d_chunk_row_start)));
   }
   // Column-major staging so that one column's descriptors are contiguous for the kernels.
   std::vector<DevSegment> staged(size_t{chunk_count} * table->column_count);
@@ -193,7 +213,7 @@ int sync_table_descriptors(hyb_context* context, Table* table) {
                            table->chunk_row_start.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, context->stream));
   // `staged` is pageable, so the copies above have completed with respect to the host buffer on return.
   HYB_CUDA(cudaStreamSynchronize(context->stream));
-  for (auto& entry : table->d_tile_maps) cudaFree(entry.second.first);
+  for (auto& entry : table->d_tile_maps) table_free(table->owner, entry.second.first);
   table->d_tile_maps.clear();
   table->key_bounds.clear();
   table->dirty = false;
@@ -220,9 +240,10 @@ int get_tile_map(hyb_context* context, Table* table, uint32_t tile_rows, const u
       }
     }
     uint2* device = nullptr;
-    HYB_CUDA(cudaMalloc(&device, sizeof(uint2) * std::max<size_t>(map.size(), 1)));
+    HYB_CUDA(table_alloc(table->owner, sizeof(uint2) * std::max<size_t>(map.size(), 1), reinterpret_cast<void**>(&device)));
     if (!map.empty()) {
-      HYB_CUDA(cudaMemcpy(device, map.data(), sizeof(uint2) * map.size(), cudaMemcpyHostToDevice));
+      // stream-ordered behind whatever used the cached block before; `map` is pageable: staged before the call returns
+      HYB_CUDA(cudaMemcpyAsync(device, map.data(), sizeof(uint2) * map.size(), cudaMemcpyHostToDevice, context->stream));
     }
     it = table->d_tile_maps.emplace(tile_rows, std::make_pair(device, static_cast<uint32_t>(map.size()))).first;
   }
@@ -618,6 +639,7 @@ int hyb_table_create(hyb_context* context, uint32_t column_count, hyb_table_t* o
   HYB_CHECK(column_count > 0, HYB_ERR_INVALID, "a table needs at least one column");
   std::lock_guard<std::mutex> lock(context->mutex);
   auto table = std::make_unique<Table>();
+  table->owner = context;
   table->column_count = column_count;
   table->column_types.assign(column_count, -1);
   table->chunk_row_start.push_back(0);

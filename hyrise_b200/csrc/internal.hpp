@@ -76,6 +76,8 @@ struct BlockSet {
 };
 
 struct Table {
+  hyb_context* owner = nullptr;             // descriptor arrays and tile maps come from / go back to its DeviceCache: creating
+                                            // and dropping tables in a loop (an end-to-end pipeline) never calls the driver
   std::shared_ptr<BlockSet> block_set;      // set when the segment buffers live in uploaded arena blocks
   bool adopting_device_buffers = false;     // hyb_table_append_chunk_device in progress: pointers are device pointers
   uint32_t column_count = 0;

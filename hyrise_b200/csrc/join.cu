@@ -2242,6 +2242,7 @@ static int received_table(hyb_context* context, PeerGroup* group, int side, uint
   Table* table = nullptr;
   if (!group->received[side]) {
     auto created = std::make_unique<Table>();
+    created->owner = context;
     created->column_count = 1;
     created->column_types.assign(1, HYB_TYPE_INT64);
     created->chunk_row_start = {0, 0};

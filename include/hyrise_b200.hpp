@@ -217,14 +217,88 @@ inline hyb_value to_value(const AllTypeVariant& variant) {
 }
 }  // namespace detail
 
-// column <condition> value | column BETWEEN lower AND upper | column IS [NOT] NULL. Values must already have the column's
-// data type (the reference casts losslessly before choosing the scan implementation, table_scan.cpp:340-366).
+enum class DataType : int32_t {  // all_type_variant.hpp:34-39, the numeric types
+  Int = HYB_TYPE_INT32,
+  Long = HYB_TYPE_INT64,
+  Float = HYB_TYPE_FLOAT32,
+  Double = HYB_TYPE_FLOAT64
+};
+
+inline DataType data_type_from_all_type_variant(const AllTypeVariant& variant) {
+  return static_cast<DataType>(variant.index());  // the variant's alternatives are in DataType order
+}
+
+namespace detail {
+inline AllTypeVariant to_variant(DataType type, const hyb_value& value) {
+  switch (type) {
+    case DataType::Int:
+      return value.i32;
+    case DataType::Long:
+      return static_cast<int64_t>(value.i64);
+    case DataType::Float:
+      return value.f32;
+    default:
+      return value.f64;
+  }
+}
+}  // namespace detail
+
+// types.cpp:51-82. Throws std::logic_error (the reference's Fail) for conditions that cannot be flipped.
+inline PredicateCondition flip_predicate_condition(PredicateCondition condition) {
+  int32_t flipped = 0;
+  check(hyb_flip_predicate_condition(static_cast<int32_t>(condition), &flipped));
+  return static_cast<PredicateCondition>(flipped);
+}
+
+// lossless_predicate_variant_cast (utils/lossless_predicate_cast.hpp:64-66, .cpp:40-73): the literal in the column's type
+// and the possibly adjusted condition (`float_col < 3.1` -> `float_col <= 3.0999999f`), or nullopt when no lossless form
+// exists — the reference then falls back to the ExpressionEvaluator, i.e. the CPU operator runs.
+inline std::optional<std::pair<PredicateCondition, AllTypeVariant>> lossless_predicate_variant_cast(
+    PredicateCondition condition, const AllTypeVariant& variant, DataType target_data_type) {
+  const hyb_literal literal{static_cast<int32_t>(data_type_from_all_type_variant(variant)), detail::to_value(variant)};
+  int32_t adjusted = 0;
+  hyb_value value{};
+  const int status = hyb_lossless_predicate_cast(static_cast<int32_t>(condition), &literal, static_cast<int32_t>(target_data_type), 0,
+                                                 &adjusted, &value);
+  if (status == HYB_ERR_UNSUPPORTED) return std::nullopt;
+  check(status);
+  return std::make_pair(static_cast<PredicateCondition>(adjusted), detail::to_variant(target_data_type, value));
+}
+
+// column <condition> value | column BETWEEN lower AND upper | column IS [NOT] NULL. Values must have the column's data
+// type: ScanPredicate::normalized() does what TableScan::create_impl does with a literal of another type
+// (table_scan.cpp:340-366 and :399-441), through the library's hyb_lossless_predicate_cast / hyb_lossless_between_cast.
 struct ScanPredicate {
   ColumnID column_id;
   PredicateCondition condition;
   std::optional<AllTypeVariant> value;   // binary conditions and the lower bound of BETWEEN
   std::optional<AllTypeVariant> value2;  // upper bound of BETWEEN
   std::vector<uint32_t> string_value_id_bounds;  // string dictionaries: per-chunk bounds, see hyb_scan_predicate
+
+  // The predicate with its literal(s) cast to `column_type`; nullopt: no lossless form (run the CPU operator).
+  std::optional<ScanPredicate> normalized(DataType column_type) const {
+    ScanPredicate result = *this;
+    const bool between = condition >= PredicateCondition::BetweenInclusive && condition <= PredicateCondition::BetweenExclusive;
+    if (between && value && value2) {
+      const hyb_literal lower{static_cast<int32_t>(data_type_from_all_type_variant(*value)), detail::to_value(*value)};
+      const hyb_literal upper{static_cast<int32_t>(data_type_from_all_type_variant(*value2)), detail::to_value(*value2)};
+      int32_t adjusted = 0;
+      hyb_value low{}, high{};
+      const int status = hyb_lossless_between_cast(static_cast<int32_t>(condition), &lower, &upper, static_cast<int32_t>(column_type),
+                                                   &adjusted, &low, &high);
+      if (status == HYB_ERR_UNSUPPORTED) return std::nullopt;
+      check(status);
+      result.condition = static_cast<PredicateCondition>(adjusted);
+      result.value = detail::to_variant(column_type, low);
+      result.value2 = detail::to_variant(column_type, high);
+    } else if (value) {
+      const auto cast = lossless_predicate_variant_cast(condition, *value, column_type);
+      if (!cast) return std::nullopt;
+      result.condition = cast->first;
+      result.value = cast->second;
+    }
+    return result;
+  }
 
   hyb_scan_predicate to_abi() const {
     hyb_scan_predicate predicate{};
