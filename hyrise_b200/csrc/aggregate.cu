@@ -1472,8 +1472,56 @@ struct StreamLayout {
   size_t dynamic_bytes = 0;
 };
 
+// Registry of the compile-time row-loop shapes (aggregate_stream.cuh): W, G, C, shape word. The layout-generic instantiations
+// (shape 0) cover every eligible plan; these add the fixed-width layouts dbgen's lineitem yields for the TPC-H Q1 / Q6 plans
+// (the shapes of the reference's own headline queries) — anything else a deployment runs hot is one line here.
+//   Q1: l_shipdate (2-byte value-IDs) range test | 2 group-by columns | l_extendedprice (2-byte IDs, dictionary in global
+//       memory), 1 - l_discount, 1 + l_tax, l_quantity (1-byte IDs, staged dictionaries); sums: price, disc, qty raw + 2 products
+//   Q6: l_shipdate, l_discount, l_quantity range tests | no group-by | sum(l_extendedprice * l_discount)
+constexpr uint64_t kShapeTpchQ1 =
+    shape_counts(1, 2) | shape_predicate(0, 2, 0) | shape_value(0, 2, kValueGlobalDictionary, kIdentity, true) |
+    shape_value(1, 1, kValueStagedDictionary, kLiteralMinusColumn, true) |
+    shape_value(2, 1, kValueStagedDictionary, kLiteralPlusColumn, false) | shape_value(3, 1, kValueStagedDictionary, kIdentity, true) |
+    shape_products(0b0110);
+constexpr uint64_t kShapeTpchQ6 = shape_counts(3, 0) | shape_predicate(0, 2, 0) | shape_predicate(1, 1, 0) | shape_predicate(2, 1, 0) |
+                                  shape_value(0, 2, kValueGlobalDictionary, kIdentity, false) |
+                                  shape_value(1, 1, kValueStagedDictionary, kIdentity, false) | shape_products(0b0010);
+#define HYB_STREAM_SHAPES(X) \
+  X(0, 4, 4, kShapeTpchQ1)   \
+  X(0, 1, 2, kShapeTpchQ6)
+
+// The shape word of a plan, 0 if the word cannot express it (more predicates than it has room for, encoded int tests, ...).
+static uint64_t stream_shape_of(const StreamPlan& plan, const FastPlan& fast, uint32_t column_count) {
+  if (fast.predicate_count > kShapeMaxPredicates || fast.groupby_count > 7 || column_count > 4) return 0;
+  uint64_t shape = shape_counts(fast.predicate_count, fast.groupby_count) | shape_products(fast.need_product_mask);
+  for (uint32_t p = 0; p < fast.predicate_count; ++p) {
+    uint32_t mode_code;
+    if (plan.predicate_mode[p] == kTestIdRange) {
+      mode_code = 0;
+    } else if (plan.predicate_mode[p] == kTestInt && plan.predicate_encoding[p] == HYB_ENC_UNENCODED) {
+      mode_code = 1;
+    } else if (plan.predicate_mode[p] == kTestFloat) {
+      mode_code = 2;
+    } else {
+      return 0;
+    }
+    shape |= shape_predicate(static_cast<int>(p), plan.predicate_width[p], mode_code);
+  }
+  for (uint32_t c = 0; c < column_count; ++c) {
+    if (fast.value_segments[c] == nullptr) continue;
+    shape |= shape_value(static_cast<int>(c), plan.value_width[c], plan.value_kind[c], fast.affine_kind[c], (fast.need_raw_mask >> c) & 1u);
+  }
+  return shape;
+}
+
 template <int W>
-static void* stream_kernel_for(int groups, int columns) {
+static void* stream_kernel_for(int groups, int columns, uint64_t shape, bool* is_static) {
+  *is_static = true;
+#define HYB_STREAM_MATCH(SW, SG, SC, SHAPE) \
+  if (W == SW && groups == SG && columns == SC && shape == SHAPE) return reinterpret_cast<void*>(aggregate_stream_static_kernel<SW, SG, SC, SHAPE>);
+  HYB_STREAM_SHAPES(HYB_STREAM_MATCH)
+#undef HYB_STREAM_MATCH
+  *is_static = false;
   if (groups == 1) {
     return columns == 1   ? reinterpret_cast<void*>(aggregate_stream_kernel<W, 1, 1>)
            : columns == 2 ? reinterpret_cast<void*>(aggregate_stream_kernel<W, 1, 2>)
@@ -1484,7 +1532,8 @@ static void* stream_kernel_for(int groups, int columns) {
                         : reinterpret_cast<void*>(aggregate_stream_kernel<W, 4, 4>);
 }
 
-static StreamLayout stream_layout_for(const Table* table, const hyb_aggregate_query* query, const FastPlanHost& fast) {
+static StreamLayout stream_layout_for(const Table* table, const hyb_aggregate_query* query, const FastPlanHost& fast,
+                                      uint32_t stage_count) {
   StreamLayout layout;
   if (fast.work_type == 2 || table->row_count() >= 0xFFFFFFF0ull) return layout;
   // a single int32 group-by column may take the immediate-key order, which needs the LAST row of every group
@@ -1582,8 +1631,10 @@ static StreamLayout stream_layout_for(const Table* table, const hyb_aggregate_qu
   plan.info_offset = offset;
   offset += (static_cast<uint32_t>(sizeof(StreamStageInfo)) + 127u) & ~127u;
   plan.stage_bytes = offset;
-  layout.dynamic_bytes = size_t{kStreamStages} * plan.stage_bytes;
-  if (layout.dynamic_bytes > 110 * 1024) return layout;  // two CTAs per SM
+  plan.stage_count = std::min<uint32_t>(std::max<uint32_t>(stage_count, 2), kStreamMaxStages);
+  while (plan.stage_count > 2 && size_t{plan.stage_count} * plan.stage_bytes > kStreamMaxDynamicBytes) --plan.stage_count;
+  layout.dynamic_bytes = size_t{plan.stage_count} * plan.stage_bytes;
+  if (layout.dynamic_bytes > kStreamMaxDynamicBytes) return layout;
   layout.possible = true;
   return layout;
 }
@@ -1729,7 +1780,7 @@ static int aggregate_hash_locked(hyb_context* context, const hyb_aggregate_query
     };
     std::vector<Attempt> attempts;
     StreamLayout stream_layout;
-    if (context->options.aggregate_stream) stream_layout = stream_layout_for(table, query, fast);
+    if (context->options.aggregate_stream) stream_layout = stream_layout_for(table, query, fast, context->options.aggregate_stages);
     if (stream_layout.possible) attempts.push_back({true, query->groupby_count == 0 ? 1 : 4});
     if (query->groupby_count == 0) {
       attempts.push_back({false, 1});
@@ -1746,9 +1797,8 @@ static int aggregate_hash_locked(hyb_context* context, const hyb_aggregate_query
       const FastKernel kernel = fast_kernel(fast.work_type, G, C);
       uint32_t grid = 1;
       if (attempt.stream) {
-        // two persistent CTAs per SM (three stages of 2048 rows each), units strided over the CTAs
-        const uint32_t unit_count = (tile_count + kStreamUnitTiles - 1) / kStreamUnitTiles;
-        grid = std::max<uint32_t>(1, std::min<uint32_t>(unit_count, context->sm_count * 2));
+        // one persistent CTA per SM; its tiles are kStreamRounds contiguous runs, the runs strided over the CTAs
+        grid = std::max<uint32_t>(1, std::min<uint32_t>(tile_count, context->sm_count));
       } else {
         int blocks_per_sm = 1;
         HYB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, kFastThreads, 0));
@@ -1809,7 +1859,15 @@ static int aggregate_hash_locked(hyb_context* context, const hyb_aggregate_query
       if (attempt.stream) {
         StreamPlan stream_plan = stream_layout.plan;
         stream_plan.fast = host_plan;
-        void* stream_kernel = fast.work_type == 0 ? stream_kernel_for<0>(G, C) : stream_kernel_for<1>(G, C);
+        stream_plan.unit_tiles = std::max<uint32_t>(1, (tile_count + grid * kStreamRounds - 1) / (grid * kStreamRounds));
+        const uint64_t shape = context->options.aggregate_static_shapes ? stream_shape_of(stream_plan, host_plan, static_cast<uint32_t>(C)) : 0;
+        bool static_shape = false;
+        void* stream_kernel = fast.work_type == 0 ? stream_kernel_for<0>(G, C, shape, &static_shape)
+                                                  : stream_kernel_for<1>(G, C, shape, &static_shape);
+        if (context->options.trace) {
+          std::fprintf(stderr, "[hyb] aggregate_stream_kernel<%d, %d, %d> shape %#llx (%s)\n", fast.work_type, G, C,
+                       static_cast<unsigned long long>(shape), static_shape ? "static instantiation" : "layout-generic");
+        }
         HYB_CUDA(cudaFuncSetAttribute(stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(stream_layout.dynamic_bytes)));
         void* arguments[] = {&stream_plan};

@@ -203,6 +203,9 @@ struct ContextOptions {
   bool scan_bulk = false;      // HYB_SCAN_BULK = 0: scan without the cp.async.bulk + mbarrier input pipeline
   bool aggregate_stream = true;  // HYB_AGG_STREAM = 0: keep the register-tile fast kernel for low-cardinality group-bys
   bool aggregate_split = true;   // HYB_AGG_SPLIT = 0: never split a big dictionary over a CTA pair
+  uint32_t aggregate_stages = 3;        // HYB_AGG_STAGES: depth of the streaming kernel's shared-memory ring (2..4)
+  bool aggregate_static_shapes = true;  // HYB_AGG_SHAPES = 0: always the layout-generic row loop of the streaming kernel
+  bool trace = false;                   // HYB_TRACE = 1: one stderr line per kernel-variant decision
 };
 }  // namespace hyb
 

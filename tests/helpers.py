@@ -228,7 +228,7 @@ def assert_aggregate_outputs_equal(device_output, oracle_output, rel=1e-6) -> No
         if got.dtype.kind in "iu":
             assert np.array_equal(got[valid], want[valid]), f"aggregate {index}: {got} != {want}"
         else:
-            assert np.allclose(got[valid], want[valid], rtol=rel, atol=0.0), f"aggregate {index}: {got} != {want}"
+            assert np.allclose(got[valid], want[valid], rtol=rel, atol=0.0, equal_nan=True), f"aggregate {index}: {got} != {want}"
 
 
 # ---- table_scan_between_test.cpp: the parameterised fixture (:43-96) and the literal expectations (:194-243) ------------

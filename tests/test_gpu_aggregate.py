@@ -111,6 +111,41 @@ def test_tpch_q1_q6_real_data(device):
     device_table.drop()
 
 
+def test_q1_non_finite_values_stay_in_their_group(device):
+    """The streaming kernel adds every row to every group through a 0 / 1 mask (one DFMA instead of DADD + two selects); a
+    step that holds inf / NaN / an overflowing product must take the select form, or 0 * inf = NaN would leak into the other
+    groups. Poisoned rows sit in single groups; the others must still match the oracle to 1e-6."""
+    from hyrise_b200.storage import ColumnDefinition, Table
+
+    data = dict(np.load("tests/golden/tpch/sf-0.01_lineitem.npz"))
+    names = ["l_orderkey", "l_quantity", "l_extendedprice", "l_discount", "l_tax", "l_returnflag", "l_linestatus", "l_shipdate"]
+    types = [capi.TYPE_INT32] + [capi.TYPE_FLOAT32] * 4 + [capi.TYPE_STRING] * 3
+    definitions = [ColumnDefinition(name, data_type) for name, data_type in zip(names, types)]
+    flags, status = data["l_returnflag"], data["l_linestatus"]
+    group_rows = {key: np.flatnonzero((flags == key[0]) & (status == key[1])) for key in ((b"A", b"F"), (b"R", b"F"), (b"N", b"O"))}
+    overflowing = np.flatnonzero((flags == b"N") & (status == b"O") & (data["l_discount"] == 0) & (data["l_tax"] >= 0.02))[0]
+    cases = [
+        {"l_extendedprice": [(group_rows[(b"A", b"F")][5], np.inf)]},                       # +inf in one group
+        {"l_quantity": [(group_rows[(b"R", b"F")][77], np.nan)]},                            # NaN in a raw-only column
+        {"l_extendedprice": [(overflowing, 3.4e38)]},                                        # finite, price * 1 * (1 + tax) is not
+        {"l_extendedprice": [(group_rows[(b"A", b"F")][9], np.inf), (group_rows[(b"A", b"F")][20_000 % 5_000], -np.inf)]},
+    ]
+    for poison in cases:
+        columns = {name: np.array(data[name]) for name in names}
+        for name, edits in poison.items():
+            for row, value in edits:
+                columns[name][row] = value
+        table = Table.from_columns(definitions, [columns[name] for name in names], chunk_size=10_000).encode("Automatic")
+        device_table = device.upload(table)
+        got = check_aggregate(device, table, device_table, [5, 6], Q1_AGGREGATES, predicates=Q1_PREDICATES)
+        assert got.group_count == 4
+        poisoned = np.zeros(4, dtype=bool)
+        for values in got.values:
+            poisoned |= ~np.isfinite(values.astype(np.float64))
+        assert poisoned.sum() == 1, got.values  # exactly one group is poisoned
+        device_table.drop()
+
+
 def test_generated_q1_sf1(device):
     """Q1 on the generated SF 1 lineitem (6 M rows, 65 535-row chunks) against the oracle on the same segments."""
     from hyrise_b200.tpch import TpchTables

@@ -1,0 +1,7 @@
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+HYB_TRACE=1 timeout -k 10 900 python -m pytest tests/test_gpu_aggregate.py -x -q -m gpu > gpurun_out/test_aggregate.log 2>&1; echo "rc=$?" >> gpurun_out/test_aggregate.log
+grep -c "static instantiation" gpurun_out/test_aggregate.log; grep "shape" gpurun_out/test_aggregate.log | sort | uniq -c | sort -rn | head -8
+tail -n 6 gpurun_out/test_aggregate.log | cut -c1-400
+HYB_TRACE=1 timeout -k 10 600 python tools/variants.py --sf 10 --only aggregate > gpurun_out/variants.txt 2>&1
+grep -v "^\[hyb\]" gpurun_out/variants.txt | tail -n 8; grep "shape" gpurun_out/variants.txt | sort | uniq -c
