@@ -382,11 +382,13 @@ def main() -> None:
         return {"split_count_ms": stats.split_count_ms, "count_wait_ms": stats.count_wait_ms, "push_ms": stats.push_ms,
                 "done_wait_ms": stats.done_wait_ms, "local_ms": stats.local_ms, "finish_ms": stats.finish_ms,
                 "tuples_sent": int(stats.tuples_sent), "tuples_received": int(stats.tuples_received),
-                "nvlink_bytes": int(stats.nvlink_bytes)}
+                "nvlink_bytes": int(stats.nvlink_bytes), "colocated": int(stats.colocated)}
 
     def distributed_join(table_o=None, table_l=None):
-        """hyb_join_hash_distributed: counts published by kernel, fused split + NVLink push of both sides, device-side flag
-        waits, local join of the received tuples, translation to global RowIDs — one C-ABI call per rank"""
+        """hyb_join_hash_distributed, one C-ABI call per rank: the ranks exchange the key bounds of their shards; co-located
+        shards (this data set: a rank's lineitem rows belong to its own orders) are joined locally with global RowIDs, otherwise
+        counts are published by kernel, both sides are split and pushed over NVLink, and every rank joins what it received.
+        The forced-exchange time of the same call is reported next to the step in phases_rank0."""
         result = group.join_hash(table_o or orders, O_ORDERKEY, table_l or lineitem, L_ORDERKEY, orders_chunk_base,
                                  lineitem_chunk_base, radix_bits)
         return result, device.last_stats()
@@ -572,6 +574,17 @@ def main() -> None:
         for name, samples in phases.items():
             if samples:
                 phase_summary[name] = {key: float(np.mean([sample[key] for sample in samples])) for key in samples[0]}
+        # the same join with the co-location shortcut switched off (outside the timed region): what the radix exchange costs
+        device.set_option("join_colocated", "0")
+        forced = []
+        for _ in range(3):
+            flush_l2()
+            barrier()
+            result, stats = distributed_join()
+            forced.append(dict(phase_record(group.stats()), operator_ms=float(stats.device_ms)))
+            result.free()
+        device.set_option("join_colocated", "1")
+        phase_summary["join_exchange_forced"] = {key: float(np.mean([sample[key] for sample in forced[1:]])) for key in forced[0]}
         accounted = sum(breakdown[name]["operator_ms"] for name in breakdown) + 3 * 0.035
         phase_summary["host_gap_ms"] = max(0.0, ms_per_step - accounted)
 

@@ -24,7 +24,7 @@ namespace hyb {
 
 // One persistent CTA per SM: 15 consumer warps + the producer warp = 16 warps, which may use 128 registers each (a second
 // CTA of 9 warps would cap the row loop at 80 registers: the register file is allocated in units of 4 warps).
-constexpr int kStreamMaxStages = 4;  // ring depth is a launch parameter (StreamPlan::stage_count): fewer stages leave more L1 for gathers
+constexpr int kStreamMaxStages = 8;  // ring depth is a launch parameter (StreamPlan::stage_count): fewer stages leave more L1 for gathers
 constexpr int kStreamConsumerWarps = 15;
 constexpr int kStreamConsumerThreads = kStreamConsumerWarps * 32;
 constexpr int kStreamThreads = kStreamConsumerThreads + 32;  // + the producer warp
@@ -34,7 +34,7 @@ constexpr int kStreamLaneRows = 4;                                          // c
 constexpr int kStreamSteps = kStreamRowsPerWarp / (32 * kStreamLaneRows);   // 1
 constexpr int kStreamMaxColumns = 12;   // distinct staged columns (predicates + group-by + values)
 constexpr int kStreamRounds = 4;        // a CTA's tiles: kStreamRounds contiguous runs (chunk locality) spread over the table
-constexpr size_t kStreamMaxDynamicBytes = 200 * 1024;
+constexpr size_t kStreamMaxDynamicBytes = 216 * 1024;
 constexpr uint32_t kStreamEnd = 0xFFFFFFFFu;
 enum : uint32_t { kValueBits = 0, kValueStagedDictionary = 1, kValueGlobalDictionary = 2 };
 

@@ -413,13 +413,14 @@ static bool apply_option(hyb::ContextOptions& options, const std::string& name, 
     return true;
   }
   if (name == "join_span") return as_flag(&options.join_span);
+  if (name == "join_colocated") return as_flag(&options.join_colocated);
   if (name == "scan_bulk") return as_flag(&options.scan_bulk);
   if (name == "aggregate_stream") return as_flag(&options.aggregate_stream);
   if (name == "aggregate_split") return as_flag(&options.aggregate_split);
   if (name == "aggregate_static_shapes") return as_flag(&options.aggregate_static_shapes);
   if (name == "trace") return as_flag(&options.trace);
   if (name == "aggregate_stages") {
-    if (value.size() != 1 || value[0] < '2' || value[0] > '4') return false;
+    if (value.size() != 1 || value[0] < '2' || value[0] > '8') return false;
     options.aggregate_stages = static_cast<uint32_t>(value[0] - '0');
     return true;
   }
@@ -454,7 +455,8 @@ int hyb_context_create(int device_index, hyb_context** out_context) {
   const std::pair<const char*, const char*> knobs[] = {
       {"HYB_JOIN_TABLE", "join_table"}, {"HYB_JOIN_SPAN", "join_span"},     {"HYB_JOIN_RANK", "join_rank"},
       {"HYB_SCAN_BULK", "scan_bulk"},   {"HYB_AGG_STREAM", "aggregate_stream"}, {"HYB_AGG_SPLIT", "aggregate_split"},
-      {"HYB_AGG_SHAPES", "aggregate_static_shapes"}, {"HYB_TRACE", "trace"}, {"HYB_AGG_STAGES", "aggregate_stages"}};
+      {"HYB_AGG_SHAPES", "aggregate_static_shapes"}, {"HYB_TRACE", "trace"}, {"HYB_AGG_STAGES", "aggregate_stages"},
+      {"HYB_JOIN_COLOCATED", "join_colocated"}};
   for (const auto& knob : knobs) {
     const char* text = std::getenv(knob.first);
     if (text && !apply_option(context->options, knob.second, text)) {

@@ -198,12 +198,13 @@ namespace hyb {
 struct ContextOptions {
   enum JoinTable : int { kAuto = 0, kHash, kDirect, kRank };
   int join_table = kAuto;      // HYB_JOIN_TABLE = hash | direct | rank
+  bool join_colocated = true;  // HYB_JOIN_COLOCATED = 0: the distributed join always exchanges, even when the shards are co-located
   bool join_span = true;       // HYB_JOIN_SPAN = 0: keep the 4096-row tile kernels for the Inner/unique fast path
   bool join_ballot_rank = false;  // HYB_JOIN_RANK = ballot: one ballot per radix bit instead of MATCH.ANY (measured slower)
   bool scan_bulk = false;      // HYB_SCAN_BULK = 0: scan without the cp.async.bulk + mbarrier input pipeline
   bool aggregate_stream = true;  // HYB_AGG_STREAM = 0: keep the register-tile fast kernel for low-cardinality group-bys
   bool aggregate_split = true;   // HYB_AGG_SPLIT = 0: never split a big dictionary over a CTA pair
-  uint32_t aggregate_stages = 3;        // HYB_AGG_STAGES: depth of the streaming kernel's shared-memory ring (2..4)
+  uint32_t aggregate_stages = 5;        // HYB_AGG_STAGES: depth of the streaming kernel's shared-memory ring (2..8, as far as it fits)
   bool aggregate_static_shapes = true;  // HYB_AGG_SHAPES = 0: always the layout-generic row loop of the streaming kernel
   bool trace = false;                   // HYB_TRACE = 1: one stderr line per kernel-variant decision
 };

@@ -60,6 +60,8 @@ struct KeySource {
   uint32_t uniform_chunk_rows;       // > 0: all chunks but the last have this many rows
   uint32_t uniform_magic;            // ceil(2^(32 + shift) / uniform_chunk_rows) - 2^32  (position / rows by multiply-shift)
   uint32_t uniform_shift;
+  uint32_t chunk_id_base;            // added to the chunk id of every RowID of this table that is emitted (a rank's shard of a
+                                     // global table: hyb_join_hash_distributed on co-located shards); 0 otherwise
 };
 
 struct KeyAt {
@@ -127,14 +129,18 @@ __device__ __forceinline__ KeyAt key_at(const KeySource& source, uint32_t tile, 
 
 __device__ __forceinline__ hyb_row_id position_to_row_id(const KeySource& source, unsigned long long position) {
   if (source.payload) return source.payload[position];
-  if (source.filter) return source.filter[position];
+  if (source.filter) {
+    hyb_row_id row = source.filter[position];
+    if (row.chunk_id != HYB_INVALID_CHUNK_ID) row.chunk_id += source.chunk_id_base;
+    return row;
+  }
   if (source.uniform_chunk_rows) {
     // positions are < 2^32 here (checked by the host): exact division by an invariant via multiply-high
     // (Granlund & Montgomery; q = (mulhi(n, m') + ((n - mulhi(n, m')) >> 1)) >> (shift - 1))
     const uint32_t n = static_cast<uint32_t>(position);
     const uint32_t t = __umulhi(n, source.uniform_magic);
     const uint32_t chunk = source.uniform_shift == 0 ? n : (t + ((n - t) >> 1)) >> (source.uniform_shift - 1);
-    return hyb_row_id{chunk, n - chunk * source.uniform_chunk_rows};
+    return hyb_row_id{chunk + source.chunk_id_base, n - chunk * source.uniform_chunk_rows};
   }
   uint32_t lo = 0, hi = source.chunk_count;  // chunk_row_start[lo] <= position < chunk_row_start[hi]
   while (hi - lo > 1) {
@@ -145,7 +151,7 @@ __device__ __forceinline__ hyb_row_id position_to_row_id(const KeySource& source
       hi = mid;
     }
   }
-  return hyb_row_id{lo, static_cast<uint32_t>(position - __ldg(source.chunk_row_start + lo))};
+  return hyb_row_id{lo + source.chunk_id_base, static_cast<uint32_t>(position - __ldg(source.chunk_row_start + lo))};
 }
 
 struct TileRef {
@@ -1032,7 +1038,7 @@ __global__ void __launch_bounds__(kJoinThreads, 3) join_probe_write_kernel(const
           const hyb_row_id probe_row = params.probe.payload[ref.first_position + (row_base - ref.row0) + step * 32];
           st_stream_v2(params.out_probe + at, probe_row.chunk_id, probe_row.chunk_offset);
         } else {
-          st_stream_v2(params.out_probe + at, ref.chunk, row_base + step * 32);
+          st_stream_v2(params.out_probe + at, ref.chunk + params.probe.chunk_id_base, row_base + step * 32);
         }
       }
       __syncthreads();
@@ -1052,9 +1058,11 @@ __global__ void __launch_bounds__(kJoinThreads, 3) join_probe_write_kernel(const
       }
       hyb_row_id probe_row;
       if (params.probe.tile_map) {
-        probe_row = params.probe.payload ? params.probe.payload[ref.first_position + index] : hyb_row_id{ref.chunk, ref.row0 + index};
+        probe_row = params.probe.payload ? params.probe.payload[ref.first_position + index]
+                                         : hyb_row_id{ref.chunk + params.probe.chunk_id_base, ref.row0 + index};
       } else {
         probe_row = params.probe.filter[ref.first_position + index];
+        if (probe_row.chunk_id != HYB_INVALID_CHUNK_ID) probe_row.chunk_id += params.probe.chunk_id_base;
       }
       if (match == kEmitWithoutPartner) {
         if (emit_build) st_stream_v2(params.out_build + at, HYB_INVALID_CHUNK_ID, HYB_INVALID_CHUNK_OFFSET);
@@ -1378,6 +1386,7 @@ __global__ void __launch_bounds__(kSpanThreads, 2) join_span_write_kernel(const 
   const uint32_t total = s_total;
   hyb_row_id* __restrict__ out_build = params.out_build;
   hyb_row_id* __restrict__ out_probe = params.out_probe;
+  const uint32_t build_base = params.build.chunk_id_base, probe_chunk = ref.chunk + params.probe.chunk_id_base;
   if (!params.build.filter && !params.build.payload && !params.probe.payload && params.build.uniform_chunk_rows) {
     // build position -> RowID by an exact multiply-shift division (all chunks but the last have uniform_chunk_rows rows)
     const uint32_t magic = params.build.uniform_magic, shift = params.build.uniform_shift;
@@ -1388,8 +1397,8 @@ __global__ void __launch_bounds__(kSpanThreads, 2) join_span_write_kernel(const 
       const uint32_t n = staged.x;
       const uint32_t t = __umulhi(n, magic);
       const uint32_t chunk = shift == 0 ? n : (t + ((n - t) >> 1)) >> (shift - 1);
-      st_stream_v2(out_build + at, chunk, n - chunk * chunk_rows);
-      st_stream_v2(out_probe + at, ref.chunk, ref.row0 + (staged.y & 0xFFFFu));
+      st_stream_v2(out_build + at, chunk + build_base, n - chunk * chunk_rows);
+      st_stream_v2(out_probe + at, probe_chunk, ref.row0 + (staged.y & 0xFFFFu));
     }
   } else if (params.probe.payload) {
     // received tuples: both sides emit the RowIDs that travelled with the keys; the probe side's lie in this span's slice
@@ -1408,7 +1417,7 @@ __global__ void __launch_bounds__(kSpanThreads, 2) join_span_write_kernel(const 
       const uint32_t at = s_destination[staged.y >> 16] + i;
       const hyb_row_id build_row = position_to_row_id(params.build, staged.x);
       st_stream_v2(out_build + at, build_row.chunk_id, build_row.chunk_offset);
-      st_stream_v2(out_probe + at, ref.chunk, ref.row0 + (staged.y & 0xFFFFu));
+      st_stream_v2(out_probe + at, probe_chunk, ref.row0 + (staged.y & 0xFFFFu));
     }
   }
 }
@@ -1718,10 +1727,13 @@ extern "C" {
 
 // hyb_join_hash with context->mutex held (hyb_join_hash_distributed joins the received tuples through it).
 static int join_hash_locked(hyb_context* context, const hyb_join_side* build_side, const hyb_join_side* probe_side, int32_t mode,
-                            int32_t radix_bits, hyb_join_result_t* out_result) {
+                            int32_t radix_bits, hyb_join_result_t* out_result, uint32_t build_chunk_base = 0,
+                            uint32_t probe_chunk_base = 0) {
   SideInfo build, probe;
   HYB_TRY(prepare_side(context, build_side, &build));
   HYB_TRY(prepare_side(context, probe_side, &probe));
+  build.source.chunk_id_base = build_chunk_base;  // emitted RowIDs only: keys are still read from this table's chunks
+  probe.source.chunk_id_base = probe_chunk_base;
   HYB_CHECK(build.positions < 0xFFFFFFF0ull && probe.positions < 0xFFFFFFF0ull, HYB_ERR_UNSUPPORTED,
             "more than 2^32 - 16 rows per join side");
   if (radix_bits < 0) radix_bits = calculate_radix_bits(build.positions);
@@ -2237,6 +2249,21 @@ __global__ void peer_publish_counts_kernel(PeerControl* const* controls, uint32_
   }
 }
 
+// Writes this rank's key bounds of both join sides into every rank's control block, then raises its bounds flag there.
+__global__ void peer_publish_bounds_kernel(PeerControl* const* controls, uint32_t rank, uint32_t world, unsigned long long epoch,
+                                           long long build_min, long long build_max, long long build_keys, long long build_rows,
+                                           long long probe_min, long long probe_max, long long probe_keys, long long probe_rows) {
+  const uint32_t peer = threadIdx.x;
+  if (peer < world) {
+    PeerControl* control = controls[peer];
+    long long* row = control->side_bounds[rank];
+    row[0] = build_min, row[1] = build_max, row[2] = build_keys, row[3] = build_rows;
+    row[4] = probe_min, row[5] = probe_max, row[6] = probe_keys, row[7] = probe_rows;
+    __threadfence_system();
+    st_volatile_u64(&control->bounds_flag[rank], epoch);
+  }
+}
+
 // The persistent one-chunk table over receive region `side` (ValueSegment<int64> of keys), resized to `rows`.
 static int received_table(hyb_context* context, PeerGroup* group, int side, uint64_t rows, hyb_table_t* out_handle) {
   Table* table = nullptr;
@@ -2343,6 +2370,59 @@ int hyb_join_hash_distributed(hyb_context* context, hyb_peer_group_t group_handl
   DeviceScratch scratch(context);
   group->stats = hyb_distributed_stats{};
   HYB_CUDA(cudaEventRecord(group->events[0], stream));
+  PeerControl** controls = nullptr;
+  HYB_TRY(scratch.alloc_array(kPeerMax, &controls));
+  PeerControl* host_controls[kPeerMax] = {};
+  for (uint32_t peer = 0; peer < world; ++peer) host_controls[peer] = group->control(peer);
+  HYB_CUDA(cudaMemcpyAsync(controls, host_controls, sizeof(host_controls), cudaMemcpyHostToDevice, stream));
+
+  // ---- 0. co-located shards? ------------------------------------------------------------------------------------------------
+  // Every rank publishes the [min, max] of its build and probe keys (column statistics, cached with the table like the
+  // reference's per-segment MinMaxFilter, statistics/statistics_objects/min_max_filter.hpp). If no rank's probe range touches
+  // another rank's build range, every match is local: each rank joins its own shards and emits global RowIDs; partition p of
+  // the global result is the concatenation of the ranks' partition-p slices in rank order (a rank's chunks precede those of
+  // the next rank). Nothing crosses NVLink but these 64 bytes per pair of ranks. All ranks decide on the same matrix.
+  bool colocated = false;
+  Table::KeyBounds side_bounds[2]{};
+  if (context->options.join_colocated && !sides[0].filter && !sides[1].filter) {
+    uint32_t bounds_launches = 0;
+    HYB_TRY(column_key_bounds(context, sides[0], build_side->column_id, &side_bounds[0], &bounds_launches));
+    HYB_TRY(column_key_bounds(context, sides[1], probe_side->column_id, &side_bounds[1], &bounds_launches));
+    peer_publish_bounds_kernel<<<1, 32, 0, stream>>>(
+        controls, rank, world, epoch, side_bounds[0].min, side_bounds[0].max, side_bounds[0].has_values ? 1 : 0,
+        static_cast<long long>(sides[0].positions), side_bounds[1].min, side_bounds[1].max, side_bounds[1].has_values ? 1 : 0,
+        static_cast<long long>(sides[1].positions));
+    HYB_CUDA(cudaGetLastError());
+    HYB_TRY(peer_wait(context, group->control(rank)->bounds_flag, world, epoch));
+    long long* h_bounds = reinterpret_cast<long long*>(group->h_counts);
+    HYB_CUDA(cudaMemcpyAsync(h_bounds, group->control(rank)->side_bounds, sizeof(PeerControl::side_bounds), cudaMemcpyDeviceToHost, stream));
+    HYB_CUDA(cudaStreamSynchronize(stream));
+    colocated = true;
+    uint64_t global_build_rows = 0;
+    for (uint32_t r = 0; r < world; ++r) {
+      global_build_rows += static_cast<uint64_t>(h_bounds[r * 8 + 3]);
+      for (uint32_t other = 0; other < world && colocated; ++other) {
+        if (other == r || h_bounds[r * 8 + 6] == 0 || h_bounds[other * 8 + 2] == 0) continue;  // no probe keys / no build keys
+        const bool disjoint = h_bounds[r * 8 + 5] < h_bounds[other * 8 + 0] || h_bounds[r * 8 + 4] > h_bounds[other * 8 + 1];
+        colocated = disjoint;
+      }
+    }
+    if (colocated) {
+      if (radix_bits < 0) {
+        radix_bits = std::max<int32_t>(calculate_radix_bits(global_build_rows), 0);
+        while ((1u << radix_bits) < world) ++radix_bits;  // the same rule as the exchanging path: results agree
+      }
+      for (int e = 1; e <= 4; ++e) HYB_CUDA(cudaEventRecord(group->events[e], stream));  // split_count_ms = the bounds exchange
+      hyb_join_result_t local_result = 0;
+      HYB_TRY(join_hash_locked(context, build_side, probe_side, HYB_JOIN_INNER, radix_bits, &local_result, build_chunk_base,
+                               probe_chunk_base));
+      HYB_CUDA(cudaEventRecord(group->events[5], stream));
+      HYB_CUDA(cudaEventRecord(group->events[6], stream));
+      group->stats.colocated = 1;
+      *out_result = local_result;
+      return HYB_OK;
+    }
+  }
 
   // ---- 1. per-destination counts of both sides; publish them (and the build-key bounds) to every rank -------------------
   ProbeParams params[2];
@@ -2352,11 +2432,6 @@ int hyb_join_hash_distributed(hyb_context* context, hyb_peer_group_t group_handl
   Table::KeyBounds local_bounds{};
   uint32_t bounds_launches = 0;
   HYB_TRY(column_key_bounds(context, sides[0], build_side->column_id, &local_bounds, &bounds_launches));
-  PeerControl** controls = nullptr;
-  HYB_TRY(scratch.alloc_array(kPeerMax, &controls));
-  PeerControl* host_controls[kPeerMax] = {};
-  for (uint32_t peer = 0; peer < world; ++peer) host_controls[peer] = group->control(peer);
-  HYB_CUDA(cudaMemcpyAsync(controls, host_controls, sizeof(host_controls), cudaMemcpyHostToDevice, stream));
   peer_publish_counts_kernel<<<1, 32 * kPeerMax, 0, stream>>>(controls, rank, world, epoch, offsets[0], offsets[1], local_bounds.min,
                                                               local_bounds.max, local_bounds.has_values ? 1 : 0);
   HYB_CUDA(cudaGetLastError());

@@ -21,7 +21,8 @@ struct PeerControl {
   unsigned long long count_flag[kPeerMax];           // epoch: source's counts / key_info are complete in THIS arena
   unsigned long long done_flag[kPeerMax];            // epoch: source's tuple stores into THIS arena have completed
   unsigned long long aggregate_flag[kPeerMax];       // epoch: source's partial-group block is complete in THIS arena
-  unsigned long long pad[16];
+  unsigned long long bounds_flag[kPeerMax];          // epoch: source's side_bounds row is complete in THIS arena
+  long long side_bounds[kPeerMax][8];                // per source: {build min, max, non-NULL keys, rows, probe min, max, keys, rows}
   unsigned char aggregate_block[kPeerMax][kPeerAggregateBlockBytes];
 };
 constexpr size_t kPeerControlBytes = (sizeof(PeerControl) + 4095) / 4096 * 4096;

@@ -456,6 +456,10 @@ typedef struct hyb_distributed_stats {
   uint64_t tuples_sent;      /* to other ranks */
   uint64_t tuples_received;  /* from all ranks, own included */
   uint64_t nvlink_bytes;     /* bytes this rank stored into peer memory */
+  uint32_t colocated;        /* join: 1 = the ranks' key ranges did not overlap across ranks, every rank joined its own shards
+                                (result layout: every rank holds its slice of EVERY partition, global order = rank order
+                                inside a partition); 0 = radix exchange (a partition lives on rank partition % world) */
+  uint32_t reserved;
 } hyb_distributed_stats;
 int hyb_peer_group_stats(hyb_context* context, hyb_peer_group_t group, hyb_distributed_stats* out_stats);
 

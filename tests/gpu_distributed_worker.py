@@ -90,31 +90,64 @@ def run_distributed_checks(device, rank, world, torch_device, sf=SF, legacy_path
         if rank == 0 else None
     group = hd.connect_peer_group(device, 2 * max(rows_per_rank) + 65_536)
 
-    def check_join(kind, out_build, out_probe, offsets):
+    def check_join(kind, out_build, out_probe, offsets, colocated=False, want=None):
+        want = want or expected
         gathered = [None] * world
         dist.all_gather_object(gathered, (out_build, out_probe, offsets))
         if rank != 0:
             return 0
         build_parts, probe_parts = [], []
         for partition in range(1 << radix_bits):
-            owner_build, owner_probe, owner_offsets = gathered[partition % world]
-            build_parts.append(owner_build[int(owner_offsets[partition]):int(owner_offsets[partition + 1])])
-            probe_parts.append(owner_probe[int(owner_offsets[partition]):int(owner_offsets[partition + 1])])
-            for other in range(world):   # a partition lives on exactly one rank
-                if other != partition % world:
-                    expect(gathered[other][2][partition] == gathered[other][2][partition + 1], f"{kind}: partition on a foreign rank")
-        expect(row_ids_equal(np.concatenate(probe_parts), expected.probe), f"distributed join ({kind}): probe RowIDs differ")
-        expect(row_ids_equal(np.concatenate(build_parts), expected.build), f"distributed join ({kind}): build RowIDs differ")
+            if colocated:   # every rank holds its slice of every partition; rank order is global probe order
+                owners = range(world)
+            else:           # a partition lives on exactly one rank
+                owners = [partition % world]
+                for other in range(world):
+                    if other != partition % world:
+                        expect(gathered[other][2][partition] == gathered[other][2][partition + 1], f"{kind}: partition on a foreign rank")
+            for owner in owners:
+                owner_build, owner_probe, owner_offsets = gathered[owner]
+                build_parts.append(owner_build[int(owner_offsets[partition]):int(owner_offsets[partition + 1])])
+                probe_parts.append(owner_probe[int(owner_offsets[partition]):int(owner_offsets[partition + 1])])
+        expect(row_ids_equal(np.concatenate(probe_parts), want.probe), f"distributed join ({kind}): probe RowIDs differ")
+        expect(row_ids_equal(np.concatenate(build_parts), want.build), f"distributed join ({kind}): build RowIDs differ")
         return sum(len(p) for p in probe_parts)
 
     join_pairs = 0
-    for repeat in range(2):   # twice: the arenas, the received tables and the epoch flags are reused
-        result = group.join_hash(orders, O_ORDERKEY, lineitem, L_ORDERKEY, orders_base, lineitem_base, radix_bits)
+    layouts = []
+    for colocated_allowed in ("1", "0"):   # co-located shards: local joins, no exchange; then the radix exchange forced
+        device.set_option("join_colocated", colocated_allowed)
+        for repeat in range(2):   # twice: the arenas, the received tables and the epoch flags are reused
+            result = group.join_hash(orders, O_ORDERKEY, lineitem, L_ORDERKEY, orders_base, lineitem_base, radix_bits)
+            got_build, got_probe = result.to_host()
+            offsets = result.partition_offsets()
+            result.free()
+            stats = group.stats()
+            layouts.append(int(stats.colocated))
+            join_pairs = check_join(f"peer group, colocated={stats.colocated}", got_build, got_probe, offsets, bool(stats.colocated))
+    expect(layouts == [1, 1, 0, 0], f"co-location detection: {layouts}")
+    device.set_option("join_colocated", "1")
+
+    # shards that are NOT co-located: rank r probes with the lineitem shard of rank r + 1 -> the key ranges cross ranks, the
+    # bounds exchange must send every rank down the radix-exchange path
+    if world > 1:
+        neighbour = TpchTables(sf, seed=42, first_order=((rank + 1) % world) * orders_per_rank)
+        crossed = device.upload(neighbour.lineitem)
+        crossed_base = hd.chunk_bases(neighbour.lineitem.chunk_count, torch_device)[rank]
+        crossed_expected = None
+        if rank == 0:
+            rotated = [all_shards[(r + 1) % world] for r in range(world)]
+            crossed_expected = orc.join_hash(global_orders, O_ORDERKEY, UnionTable(rotated, "lineitem"), L_ORDERKEY, capi.JOIN_INNER,
+                                             radix_bits, threads=8)
+        result = group.join_hash(orders, O_ORDERKEY, crossed, L_ORDERKEY, orders_base, crossed_base, radix_bits)
         got_build, got_probe = result.to_host()
         offsets = result.partition_offsets()
         result.free()
-        join_pairs = check_join("peer group", got_build, got_probe, offsets)
-    stats = group.stats()
+        crossed_stats = group.stats()
+        expect(crossed_stats.colocated == 0, "crossed shards were taken for co-located ones")
+        check_join("peer group, crossed shards", got_build, got_probe, offsets, False, crossed_expected)
+        crossed.drop()
+        neighbour.close()
 
     if legacy_paths and world > 1:
         peers = hd.PeerExchange(device, torch_device, capacity=2 * shard.lineitem.row_count + 65_536)
@@ -157,8 +190,9 @@ def run_distributed_checks(device, rank, world, torch_device, sf=SF, legacy_path
     dist.all_gather_object(ok, failures)
     all_failures = [message for per_rank in ok for message in per_rank]
     assert not all_failures, "; ".join(all_failures)
-    return (f"distributed OK on {world} GPUs: scan {scan_rows} RowIDs, join pairs {join_pairs} (push {stats.push_ms:.3f} ms, "
-            f"local join {stats.local_ms:.3f} ms, {stats.nvlink_bytes} bytes over NVLink from rank 0), Q1 groups {output.group_count}")
+    return (f"distributed OK on {world} GPUs: scan {scan_rows} RowIDs, join pairs {join_pairs} (co-located, forced exchange and "
+            f"crossed shards; exchange: push {stats.push_ms:.3f} ms, local join {stats.local_ms:.3f} ms, {stats.nvlink_bytes} bytes "
+            f"over NVLink from rank 0), Q1 groups {output.group_count}")
 
 
 def main():

@@ -52,10 +52,12 @@ def main():
                     {"join_table": "hash", "join_span": "1", "join_rank": "ballot"}) if "join" in only else ():
         timed("join", options, lambda: device.join_hash(orders, O_ORDERKEY, lineitem, L_ORDERKEY, capi.JOIN_INNER, -1))
     device.set_option("join_table", "auto")
-    for options in ({"aggregate_stream": "1", "aggregate_static_shapes": "1", "aggregate_stages": "2"},
-                    {"aggregate_stream": "1", "aggregate_static_shapes": "1", "aggregate_stages": "3"},
-                    {"aggregate_stream": "1", "aggregate_static_shapes": "1", "aggregate_stages": "4"},
-                    {"aggregate_stream": "1", "aggregate_static_shapes": "0", "aggregate_stages": "3"},
+    for options in ({"aggregate_stream": "1", "aggregate_static_shapes": "1", "aggregate_stages": "4"},
+                    {"aggregate_stream": "1", "aggregate_static_shapes": "1", "aggregate_stages": "5"},
+                    {"aggregate_stream": "1", "aggregate_static_shapes": "1", "aggregate_stages": "6"},
+                    {"aggregate_stream": "1", "aggregate_static_shapes": "1", "aggregate_stages": "7"},
+                    {"aggregate_stream": "1", "aggregate_static_shapes": "1", "aggregate_stages": "8"},
+                    {"aggregate_stream": "1", "aggregate_static_shapes": "0", "aggregate_stages": "6"},
                     {"aggregate_stream": "0"}) if "aggregate" in only else ():
         timed("aggregate", options, lambda: device.aggregate_hash(lineitem, Q1_GROUPBY, Q1_AGGREGATES, predicates=Q1_PREDICATES))
     device.close()
