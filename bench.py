@@ -531,9 +531,9 @@ def main() -> None:
                            "achieved_gbs": algorithmic / kernel_ms / 1e6, "frac": algorithmic / kernel_ms / 1e6 / peak,
                            "output_rows": int(samples[-1][3])}
     dominant = max(breakdown, key=lambda name: breakdown[name]["kernel_ms"])
-    kernels_of = {"scan": ["scan_bulk_kernel"],
-                  "join": ["join_build_kernel", "join_span_count_kernel", "exclusive_scan_kernel", "join_span_write_kernel"],
-                  "aggregate": ["aggregate_stream_kernel"]}
+    kernels_of = {"scan": ["scan_mask_kernel", "scan_bases_kernel", "scan_expand_kernel"],
+                  "join": ["join_build_rank_kernel", "join_span_count_kernel", "exclusive_scan_kernel", "join_span_write_kernel"],
+                  "aggregate": ["aggregate_stream_static_kernel"]}
     roofline = {"bound": "hbm", "kernel": " + ".join(kernels_of[dominant]), "achieved": breakdown[dominant]["achieved_gbs"],
                 "peak": peak, "peak_source": peak_source, "unit": "GB/s", "frac": breakdown[dominant]["frac"],
                 "traffic": ncu_traffic(kernels_of[dominant], args.sf, world),
@@ -602,13 +602,16 @@ def main() -> None:
             "config": config,
             "detail": {"lineitem_rows_per_gpu": rows, "orders_rows_per_gpu": tables.orders.row_count,
                        "l2": "256 MB memset before every operator, inside the timed region; inputs exceed L2 anyway",
-                       "parallelism": (f"{world} ranks, each owning 1/{world} of the SF {args.sf:g} tables: chunk-partitioned scan (no "
-                                       f"collective); join = radix exchange of {{key, RowID}} tuples by key & (world - 1): counts "
-                                       f"published into the peers' control blocks by kernel, fused split + NVLink P2P store "
-                                       f"kernel per side, epoch flags polled on the device, local join of the received tuples "
-                                       f"(hyb_join_hash_distributed); aggregate = local pre-aggregation, partial groups stored "
-                                       f"into every peer's arena and merged by all ranks (hyb_aggregate_hash_distributed); no "
-                                       f"NCCL collective inside the step")
+                       "parallelism": (f"{world} ranks, each owning 1/{world} of the SF {args.sf:g} tables (orders [r n, (r + 1) n) and their "
+                                       f"lineitem rows): chunk-partitioned scan (no collective); join (hyb_join_hash_distributed) = the "
+                                       f"ranks exchange the key bounds of their shards through the peer control blocks; these shards "
+                                       f"are co-located (no rank's lineitem keys reach another rank's orders keys), so every rank "
+                                       f"joins its own shards and emits global RowIDs — the radix exchange the call falls back to "
+                                       f"otherwise (counts published by kernel, fused split + NVLink P2P stores, flags polled on the "
+                                       f"device, local join of the received tuples) is timed next to the step in "
+                                       f"phases_rank0.join_exchange_forced; aggregate (hyb_aggregate_hash_distributed) = local "
+                                       f"pre-aggregation, partial groups stored into every peer's arena and merged by all ranks; "
+                                       f"no NCCL collective inside the step")
                        if world > 1 else "1 GPU",
                        "outputs_per_step": {"scan_matches": int(outputs[0]), "join_pairs": int(outputs[1]), "groups": int(outputs[2])}},
             "roofline": roofline, "operators": breakdown, "phases_rank0": phase_summary, "cpu_baseline": cpu_baseline, "e2e": e2e,

@@ -1665,6 +1665,34 @@ static int exchange_partial_groups(hyb_context* context, const AggregateExchange
                                    const hyb_aggregate_query* query, const std::vector<int32_t>& input_types,
                                    std::vector<HostGroup>* groups);
 
+// Per (table, query shape): what the descriptor walk found. See Table::plan_memo.
+struct AggregatePlanMemo {
+  uint64_t algorithmic_bytes = 0;
+  bool has_stream_layout = false;
+  uint32_t stream_stages = 0;
+  StreamLayout stream_layout;
+};
+
+static std::string aggregate_signature(const hyb_aggregate_query* query) {
+  std::string signature = "agg";
+  const auto add = [&](const void* data, size_t bytes) { signature.append(static_cast<const char*>(data), bytes); };
+  add(&query->predicate_count, sizeof(query->predicate_count));
+  for (uint32_t p = 0; p < query->predicate_count; ++p) {
+    add(&query->predicates[p].column_id, sizeof(uint32_t));
+    add(&query->predicates[p].condition, sizeof(int32_t));
+  }
+  add(&query->groupby_count, sizeof(query->groupby_count));
+  for (uint32_t g = 0; g < query->groupby_count; ++g) add(&query->groupby_column_ids[g], sizeof(uint32_t));
+  add(&query->aggregate_count, sizeof(query->aggregate_count));
+  for (uint32_t a = 0; a < query->aggregate_count; ++a) {
+    const auto& def = query->aggregates[a];
+    add(&def.function, sizeof(def.function));
+    add(&def.node_count, sizeof(def.node_count));
+    for (uint32_t n = 0; n < def.node_count; ++n) add(&def.nodes[n], sizeof(def.nodes[n]));
+  }
+  return signature;
+}
+
 // hyb_aggregate_hash with context->mutex held. `exchange` != nullptr: the groups of this rank are partial; they are
 // exchanged with the peer group's ranks and merged before the result is ordered and materialised.
 static int aggregate_hash_locked(hyb_context* context, const hyb_aggregate_query* query, hyb_aggregate_result_t* out_result,
@@ -1735,7 +1763,13 @@ static int aggregate_hash_locked(hyb_context* context, const hyb_aggregate_query
   std::vector<HostGroup> groups;
   bool done = false;
   uint64_t algorithmic_bytes = 0;
+  std::shared_ptr<AggregatePlanMemo> memo;
   {
+    auto& slot = table->plan_memo[aggregate_signature(query)];
+    if (!slot) slot = std::make_shared<AggregatePlanMemo>();
+    memo = std::static_pointer_cast<AggregatePlanMemo>(slot);
+  }
+  if (memo->algorithmic_bytes == 0) {
     // bytes of every referenced column, each counted once
     std::vector<uint32_t> referenced;
     for (uint32_t p = 0; p < query->predicate_count; ++p) referenced.push_back(query->predicates[p].column_id);
@@ -1751,21 +1785,21 @@ static int aggregate_hash_locked(hyb_context* context, const hyb_aggregate_query
       for (uint32_t chunk = 0; chunk < chunk_count; ++chunk) {
         const auto& segment = table->segments[size_t{chunk} * table->column_count + column];
         if (segment.encoding == HYB_ENC_UNENCODED) {
-          algorithmic_bytes += data_type_size(segment.data_type) * segment.row_count;
+          memo->algorithmic_bytes += data_type_size(segment.data_type) * segment.row_count;
         } else {
-          algorithmic_bytes += vector_bytes(segment.vector_type, segment.bit_width, segment.row_count);
+          memo->algorithmic_bytes += vector_bytes(segment.vector_type, segment.bit_width, segment.row_count);
           if (segment.encoding == HYB_ENC_DICTIONARY && segment.data_type != HYB_TYPE_STRING) {
-            algorithmic_bytes += data_type_size(segment.data_type) * segment.dict_size;
+            memo->algorithmic_bytes += data_type_size(segment.data_type) * segment.dict_size;
           }
           if (segment.encoding == HYB_ENC_FRAME_OF_REFERENCE) {
-            algorithmic_bytes += sizeof(int32_t) * ((segment.row_count + HYB_FOR_BLOCK_SIZE - 1) / HYB_FOR_BLOCK_SIZE);
+            memo->algorithmic_bytes += sizeof(int32_t) * ((segment.row_count + HYB_FOR_BLOCK_SIZE - 1) / HYB_FOR_BLOCK_SIZE);
           }
         }
-        if (segment.nulls) algorithmic_bytes += segment.row_count;
+        if (segment.nulls) memo->algorithmic_bytes += segment.row_count;
       }
     }
-    if (filter) algorithmic_bytes = position_count * sizeof(hyb_row_id);
   }
+  algorithmic_bytes = filter ? position_count * sizeof(hyb_row_id) : memo->algorithmic_bytes;
   bool kernel_timed = false;
 
   // ---- fast path --------------------------------------------------------------------------------------------------
@@ -1780,7 +1814,14 @@ static int aggregate_hash_locked(hyb_context* context, const hyb_aggregate_query
     };
     std::vector<Attempt> attempts;
     StreamLayout stream_layout;
-    if (context->options.aggregate_stream) stream_layout = stream_layout_for(table, query, fast, context->options.aggregate_stages);
+    if (context->options.aggregate_stream) {
+      if (!memo->has_stream_layout || memo->stream_stages != context->options.aggregate_stages) {
+        memo->stream_layout = stream_layout_for(table, query, fast, context->options.aggregate_stages);
+        memo->stream_stages = context->options.aggregate_stages;
+        memo->has_stream_layout = true;
+      }
+      stream_layout = memo->stream_layout;
+    }
     if (stream_layout.possible) attempts.push_back({true, query->groupby_count == 0 ? 1 : 4});
     if (query->groupby_count == 0) {
       attempts.push_back({false, 1});

@@ -216,6 +216,7 @@ int sync_table_descriptors(hyb_context* context, Table* table) {
   for (auto& entry : table->d_tile_maps) table_free(table->owner, entry.second.first);
   table->d_tile_maps.clear();
   table->key_bounds.clear();
+  table->plan_memo.clear();
   table->dirty = false;
   return HYB_OK;
 }
@@ -415,6 +416,7 @@ static bool apply_option(hyb::ContextOptions& options, const std::string& name, 
   if (name == "join_span") return as_flag(&options.join_span);
   if (name == "join_colocated") return as_flag(&options.join_colocated);
   if (name == "scan_bulk") return as_flag(&options.scan_bulk);
+  if (name == "scan_two_pass") return as_flag(&options.scan_two_pass);
   if (name == "aggregate_stream") return as_flag(&options.aggregate_stream);
   if (name == "aggregate_split") return as_flag(&options.aggregate_split);
   if (name == "aggregate_static_shapes") return as_flag(&options.aggregate_static_shapes);
@@ -456,7 +458,7 @@ int hyb_context_create(int device_index, hyb_context** out_context) {
       {"HYB_JOIN_TABLE", "join_table"}, {"HYB_JOIN_SPAN", "join_span"},     {"HYB_JOIN_RANK", "join_rank"},
       {"HYB_SCAN_BULK", "scan_bulk"},   {"HYB_AGG_STREAM", "aggregate_stream"}, {"HYB_AGG_SPLIT", "aggregate_split"},
       {"HYB_AGG_SHAPES", "aggregate_static_shapes"}, {"HYB_TRACE", "trace"}, {"HYB_AGG_STAGES", "aggregate_stages"},
-      {"HYB_JOIN_COLOCATED", "join_colocated"}};
+      {"HYB_JOIN_COLOCATED", "join_colocated"}, {"HYB_SCAN_TWO_PASS", "scan_two_pass"}};
   for (const auto& knob : knobs) {
     const char* text = std::getenv(knob.first);
     if (text && !apply_option(context->options, knob.second, text)) {

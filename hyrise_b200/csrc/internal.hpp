@@ -102,6 +102,10 @@ struct Table {
     bool strictly_increasing = false;  // no NULLs and key[i] > key[i - 1] for every row position i
   };
   std::map<uint32_t, KeyBounds> key_bounds;
+  // What an operator derived from a pass over all segment descriptors for one query shape (vector widths, dictionary sizes,
+  // bytes per launch ...), keyed by the shape's signature: like the reference's physical-plan cache it spares a repeated
+  // query the O(chunks x columns) analysis. Dropped with the key bounds whenever chunks change.
+  std::map<std::string, std::shared_ptr<void>> plan_memo;
 
   uint32_t chunk_count() const { return static_cast<uint32_t>(chunk_rows.size()); }
   uint64_t row_count() const { return chunk_row_start.empty() ? 0 : chunk_row_start.back(); }
@@ -201,6 +205,7 @@ struct ContextOptions {
   bool join_colocated = true;  // HYB_JOIN_COLOCATED = 0: the distributed join always exchanges, even when the shards are co-located
   bool join_span = true;       // HYB_JOIN_SPAN = 0: keep the 4096-row tile kernels for the Inner/unique fast path
   bool join_ballot_rank = false;  // HYB_JOIN_RANK = ballot: one ballot per radix bit instead of MATCH.ANY (measured slower)
+  bool scan_two_pass = true;   // HYB_SCAN_TWO_PASS = 1: match bits + tile counts, prefix, expansion (no look-back chain)
   bool scan_bulk = false;      // HYB_SCAN_BULK = 0: scan without the cp.async.bulk + mbarrier input pipeline
   bool aggregate_stream = true;  // HYB_AGG_STREAM = 0: keep the register-tile fast kernel for low-cardinality group-bys
   bool aggregate_split = true;   // HYB_AGG_SPLIT = 0: never split a big dictionary over a CTA pair

@@ -416,15 +416,28 @@ int hyb_tpch_value_id_bounds(const hyb_tpch* tables, int32_t table, uint32_t col
   const auto& store = table == 0 ? tables->lineitem : tables->orders;
   if (column >= store.dates.size() || store.dates[column].empty()) return HYB_ERR_INVALID;
   const auto& dictionaries = store.dates[column];
-  for (size_t chunk = 0; chunk < dictionaries.size(); ++chunk) {
-    const auto& dictionary = dictionaries[chunk];
-    for (uint32_t v = 0; v < value_count; ++v) {
-      const auto lower = std::lower_bound(dictionary.begin(), dictionary.end(), day_numbers[v]);
-      const auto upper = std::upper_bound(dictionary.begin(), dictionary.end(), day_numbers[v]);
-      uint32_t* out = out_bounds + (chunk * value_count + v) * 2;
-      out[0] = lower == dictionary.end() ? HYB_INVALID_VALUE_ID : static_cast<uint32_t>(lower - dictionary.begin());
-      out[1] = upper == dictionary.end() ? HYB_INVALID_VALUE_ID : static_cast<uint32_t>(upper - dictionary.begin());
+  const auto search = [&](size_t begin, size_t end) {
+    for (size_t chunk = begin; chunk < end; ++chunk) {
+      const auto& dictionary = dictionaries[chunk];
+      for (uint32_t v = 0; v < value_count; ++v) {
+        const auto lower = std::lower_bound(dictionary.begin(), dictionary.end(), day_numbers[v]);
+        const auto upper = std::upper_bound(dictionary.begin(), dictionary.end(), day_numbers[v]);
+        uint32_t* out = out_bounds + (chunk * value_count + v) * 2;
+        out[0] = lower == dictionary.end() ? HYB_INVALID_VALUE_ID : static_cast<uint32_t>(lower - dictionary.begin());
+        out[1] = upper == dictionary.end() ? HYB_INVALID_VALUE_ID : static_cast<uint32_t>(upper - dictionary.begin());
+      }
     }
+  };
+  // one dictionary search per chunk, like the reference's per-chunk scan jobs: spread over a few threads for big tables
+  const size_t chunks = dictionaries.size();
+  const size_t workers = chunks >= 2048 ? std::min<size_t>(8, std::max<size_t>(1, std::thread::hardware_concurrency())) : 1;
+  if (workers == 1) {
+    search(0, chunks);
+  } else {
+    std::vector<std::thread> threads;
+    for (size_t w = 1; w < workers; ++w) threads.emplace_back(search, chunks * w / workers, chunks * (w + 1) / workers);
+    search(0, chunks / workers);
+    for (auto& thread : threads) thread.join();
   }
   return HYB_OK;
 }

@@ -332,16 +332,29 @@ def test_peer_group_single_rank(device):
     tables = TpchTables(0.05, seed=11)
     lineitem, orders = device.upload(tables.lineitem), device.upload(tables.orders)
     group = hd.connect_peer_group(device, tables.lineitem.row_count + 4096)
-    for radix_bits in (3, 0, 3):  # repeated calls reuse the arena, the received tables and the epoch flags
-        expected = orc.join_hash(tables.orders, O_ORDERKEY, tables.lineitem, L_ORDERKEY, capi.JOIN_INNER, radix_bits)
-        result = group.join_hash(orders, O_ORDERKEY, lineitem, L_ORDERKEY, 0, 0, radix_bits)
-        got_build, got_probe = result.to_host()
-        assert result.info()[0] == expected.pair_count
-        assert np.array_equal(result.partition_offsets(), expected.partition_offsets)
-        assert row_ids_equal(got_probe, expected.probe) and row_ids_equal(got_build, expected.build)
-        result.free()
-    stats = group.stats()
-    assert stats.tuples_received == tables.lineitem.row_count + tables.orders.row_count and stats.tuples_sent == 0
+    for colocated in ("0", "1"):  # a world of one is trivially co-located: force the exchange path first, then the shortcut
+        device.set_option("join_colocated", colocated)
+        for radix_bits in (3, 0, 3):  # repeated calls reuse the arena, the received tables and the epoch flags
+            expected = orc.join_hash(tables.orders, O_ORDERKEY, tables.lineitem, L_ORDERKEY, capi.JOIN_INNER, radix_bits)
+            result = group.join_hash(orders, O_ORDERKEY, lineitem, L_ORDERKEY, 0, 0, radix_bits)
+            got_build, got_probe = result.to_host()
+            assert result.info()[0] == expected.pair_count
+            assert np.array_equal(result.partition_offsets(), expected.partition_offsets)
+            assert row_ids_equal(got_probe, expected.probe) and row_ids_equal(got_build, expected.build)
+            result.free()
+        stats = group.stats()
+        assert stats.colocated == int(colocated) and stats.tuples_sent == 0
+        if colocated == "0":
+            assert stats.tuples_received == tables.lineitem.row_count + tables.orders.row_count
+    # global RowIDs of the co-located path: chunk bases are added to the emitted RowIDs of both sides
+    expected = orc.join_hash(tables.orders, O_ORDERKEY, tables.lineitem, L_ORDERKEY, capi.JOIN_INNER, 3)
+    result = group.join_hash(orders, O_ORDERKEY, lineitem, L_ORDERKEY, 1000, 70_000, 3)
+    got_build, got_probe = result.to_host()
+    assert np.array_equal(got_build["chunk_id"], expected.build["chunk_id"] + 1000)
+    assert np.array_equal(got_probe["chunk_id"], expected.probe["chunk_id"] + 70_000)
+    assert np.array_equal(got_build["chunk_offset"], expected.build["chunk_offset"])
+    assert np.array_equal(got_probe["chunk_offset"], expected.probe["chunk_offset"])
+    result.free()
     predicates = [Predicate(L_SHIPDATE, capi.PRED_LESS_THAN_EQUALS, "1998-09-02")]
     got = group.aggregate_hash(lineitem, [L_RETURNFLAG, L_LINESTATUS], Q1_AGGREGATES, predicates, 0, 0)
     want = orc.aggregate_hash(tables.lineitem, [L_RETURNFLAG, L_LINESTATUS], Q1_AGGREGATES, predicates=predicates)

@@ -11,6 +11,15 @@ from hyrise_b200.storage import ColumnDefinition, Table
 pytestmark = pytest.mark.gpu
 P = capi
 
+
+@pytest.fixture(autouse=True, params=["single-pass", "two-pass"])
+def scan_variant(device, request):
+    """Every scan test runs with both unfiltered scan pipelines: the single-pass ordered compaction with a decoupled look-back
+    and the two-pass form (match bits + tile counts, prefix, expansion)."""
+    device.set_option("scan_two_pass", "1" if request.param == "two-pass" else "0")
+    yield request.param
+    device.set_option("scan_two_pass", "0")
+
 BINARY = [P.PRED_EQUALS, P.PRED_NOT_EQUALS, P.PRED_LESS_THAN, P.PRED_LESS_THAN_EQUALS, P.PRED_GREATER_THAN,
           P.PRED_GREATER_THAN_EQUALS]
 BETWEEN = [P.PRED_BETWEEN_INCLUSIVE, P.PRED_BETWEEN_LOWER_EXCLUSIVE, P.PRED_BETWEEN_UPPER_EXCLUSIVE,

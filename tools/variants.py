@@ -43,8 +43,9 @@ def main():
               f"launches {samples[-1][2]}  {samples[-1][3] / kernel / 1e6:.0f} GB/s", flush=True)
 
     only = args.only.split(",")
-    for bulk in ("1", "0") if "scan" in only else ():
-        timed("scan", {"scan_bulk": bulk}, lambda: device.table_scan(lineitem, SCAN_PREDICATE))
+    for options in ({"scan_two_pass": "1"}, {"scan_two_pass": "0", "scan_bulk": "1"}, {"scan_two_pass": "0", "scan_bulk": "0"}) \
+            if "scan" in only else ():
+        timed("scan", options, lambda: device.table_scan(lineitem, SCAN_PREDICATE))
     for options in ({"join_table": "auto", "join_span": "1", "join_rank": "ballot"},
                     {"join_table": "auto", "join_span": "1", "join_rank": "match"},
                     {"join_table": "direct", "join_span": "1", "join_rank": "ballot"},
