@@ -21,6 +21,21 @@ int fail(int status, const std::string& message) {
   return status;
 }
 
+static void cache_release_free_blocks(hyb_context* context);
+
+// cudaMalloc outside the block cache (table slabs, exchange arenas): on out-of-memory the context's idle cache blocks — up to
+// 64 GiB after a big join — go back to the driver and the allocation is tried once more.
+cudaError_t device_malloc_retry(hyb_context* context, void** out, size_t bytes) {
+  cudaError_t error = cudaMalloc(out, bytes);
+  if (error == cudaErrorMemoryAllocation && context) {
+    cudaGetLastError();
+    cache_release_free_blocks(context);
+    error = cudaMalloc(out, bytes);
+  }
+  if (error != cudaSuccess) cudaGetLastError();
+  return error;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Arena
 // ---------------------------------------------------------------------------------------------------------------------
@@ -32,10 +47,7 @@ void* Arena::alloc(size_t bytes) {
                                                                                                    _reserved / 2)));
     slab_size = ((slab_size + kAlign - 1) / kAlign) * kAlign;
     char* base = nullptr;
-    if (cudaMalloc(&base, slab_size) != cudaSuccess) {
-      cudaGetLastError();
-      return nullptr;
-    }
+    if (device_malloc_retry(owner, reinterpret_cast<void**>(&base), slab_size) != cudaSuccess) return nullptr;
     _slabs.push_back({base, slab_size, 0});
     _reserved += slab_size;
   }
@@ -651,6 +663,7 @@ int hyb_table_create(hyb_context* context, uint32_t column_count, hyb_table_t* o
   HYB_CHECK(column_count > 0, HYB_ERR_INVALID, "a table needs at least one column");
   std::lock_guard<std::mutex> lock(context->mutex);
   auto table = std::make_unique<Table>();
+  table->arena.owner = context;
   table->owner = context;
   table->column_count = column_count;
   table->column_types.assign(column_count, -1);

@@ -45,6 +45,7 @@ class Arena {
   static constexpr size_t kTailPad = 64;  // kernels may read one 16-byte vector past the last row
   ~Arena() { release(); }
   void* alloc(size_t bytes);
+  hyb_context* owner = nullptr;  // set: a failed slab allocation releases the owner's idle cache blocks and retries once
   void release();
   size_t bytes_reserved() const { return _reserved; }
   size_t bytes_used() const { return _used; }
@@ -290,6 +291,7 @@ int get_tile_map(hyb_context* context, Table* table, uint32_t tile_rows, const u
                  uint32_t* out_tile_count);
 // Stream-ordered scratch/result memory.
 int device_alloc(hyb_context* context, size_t bytes, void** out);
+cudaError_t device_malloc_retry(hyb_context* context, void** out, size_t bytes);
 void device_free(hyb_context* context, void* ptr);
 void device_cache_destroy(hyb_context* context);
 

@@ -2554,7 +2554,7 @@ int hyb_exchange_arena_create(hyb_context* context, uint64_t bytes, void** out_d
   HYB_CHECK(context && out_device_ptr && out_ipc_handle && bytes, HYB_ERR_INVALID, "NULL argument");
   DeviceGuard guard(context->device);
   void* base = nullptr;
-  HYB_CUDA(cudaMalloc(&base, bytes));
+  HYB_CUDA(device_malloc_retry(context, &base, bytes));
   cudaIpcMemHandle_t handle;
   const cudaError_t error = cudaIpcGetMemHandle(&handle, base);
   if (error != cudaSuccess) {

@@ -61,7 +61,7 @@ int hyb_peer_group_create(hyb_context* context, uint32_t rank, uint32_t world, u
   group->world = world;
   group->capacity = (tuple_capacity + 15) / 16 * 16;
   void* base = nullptr;
-  HYB_CUDA(cudaMalloc(&base, group->arena_bytes()));
+  HYB_CUDA(device_malloc_retry(context, reinterpret_cast<void**>(&base), group->arena_bytes()));
   group->own = static_cast<char*>(base);
   group->peers[rank] = group->own;
   cudaError_t error = cudaMemset(base, 0, kPeerControlBytes);

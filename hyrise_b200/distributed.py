@@ -537,11 +537,15 @@ def connect_peer_group(device_context, tuple_capacity: int):
 def device_distributed_join(device_context, build_table, build_column: int, probe_table, probe_column: int,
                             radix_bits: int, build_chunk_base: int, probe_chunk_base: int, torch_device: torch.device,
                             peers: "PeerExchange | None" = None):
-    """Inner JoinHash across ranks: materialise both sides, ONE all-to-all per side, join the received tuples locally.
-    Returns (pair count on this rank, partition offsets, build RowIDs, probe RowIDs) with GLOBAL RowIDs, the rank's part
-    of the reference-ordered result (partitions p with p % world == rank)."""
+    """Inner JoinHash across ranks, host-orchestrated (the legacy paths next to DevicePeerGroup.join_hash): materialise both
+    sides, ONE all-to-all per side (or the P2P push of `peers`), join the received tuples locally.
+    Returns the 5-tuple (pair count on this rank, partition offsets, build RowIDs, probe RowIDs, join result or None): the
+    rank's part of the reference-ordered result — partitions p with p % world == rank, hence world <= 2^radix_bits. The
+    join result's RowIDs index the two GLOBAL-RowID arrays. With `peers` those arrays are zero-copy views of this rank's
+    receive arena: they are valid until the next push into the arena (clone them to keep them longer)."""
     _, world = _world()
     assert world & (world - 1) == 0, "the radix exchange needs a power-of-two world size"
+    assert world <= (1 << radix_bits), "every rank must own a partition: world <= 2^radix_bits"
     if peers is not None and world > 1:
         # fused split + NVLink stores into the owners' arenas; collectives: 2 count all-gathers + 1 barrier
         build_count = peers.push_side(build_table, build_column, build_chunk_base, 0)
