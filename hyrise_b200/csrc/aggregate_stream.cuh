@@ -598,66 +598,34 @@ __device__ __forceinline__ void stream_warp_rows(const StreamPlan& plan, const S
         }
       }
     } else {
-      // layout-generic: the same masked-FMA accumulation, with the set of sums read from the plan (uniform branches). The
-      // products are formed twice — once for the finiteness test of the step, once where they are consumed — which costs a
-      // few FFMA/FMUL per row and saves the registers that holding them would take next to 2 G C accumulators.
-      const auto absolute = [](Value value) {
-        if constexpr (W == 0) {
-          return fabsf(value);
-        } else {
-          return fabs(value);
-        }
-      };
-      bool finite = true;
+      // layout-generic: predicated adds (DADD + two selects each). The masked-FMA form of the static shapes was measured
+      // slower here (1.27 vs 0.97 ms for the Q1 plan): with all 2 G C accumulators live it spills.
+      Value product[kStreamLaneRows];
 #pragma unroll
-      for (int j = 0; j < kStreamLaneRows; ++j) {
-        Value product{}, magnitude{};
+      for (int c = 0; c < C; ++c) {
+        if (fast.value_segments[c] == nullptr) continue;
+        const bool in_chain = (need_product_mask >> c) != 0;  // some product at or after this column
+        if (in_chain) {
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          if (fast.value_segments[c] == nullptr) continue;
-          if ((need_product_mask >> c) != 0) {
+          for (int j = 0; j < kStreamLaneRows; ++j) {
             const Value factor = apply_affine<W>(affine_a[c], affine_b[c], values[c][j]);
-            product = c == 0 ? factor : multiply<W>(product, factor);
-          } else if ((need_raw_mask >> c) & 1u) {
-            magnitude += absolute(values[c][j]);
+            product[j] = c == 0 ? factor : multiply<W>(product[j], factor);
           }
         }
-        magnitude += absolute(product);  // the last product of the chain (0 without a chain)
-        finite = finite && magnitude <= (W == 0 ? Value(3.402823466e+38f) : Value(1.7976931348623157e+308));
-      }
-      const bool use_masks = __all_sync(kFullMask, finite);
+        if ((need_raw_mask >> c) & 1u) {
 #pragma unroll
-      for (int j = 0; j < kStreamLaneRows; ++j) {
-        Accumulator masks[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g) masks[g] = group[j] == static_cast<uint32_t>(g) ? Accumulator(1) : Accumulator(0);
-        Value product{};
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          if (fast.value_segments[c] == nullptr) continue;
-          if ((need_product_mask >> c) != 0) {  // some product at or after this column
-            const Value factor = apply_affine<W>(affine_a[c], affine_b[c], values[c][j]);
-            product = c == 0 ? factor : multiply<W>(product, factor);
-          }
-          if ((need_raw_mask >> c) & 1u) {
+          for (int j = 0; j < kStreamLaneRows; ++j) {
             const Accumulator widened = static_cast<Accumulator>(values[c][j]);
-            if (use_masks) {
 #pragma unroll
-              for (int g = 0; g < G; ++g) state.sums[g][2 * c] = __fma_rn(widened, masks[g], state.sums[g][2 * c]);
-            } else {
-#pragma unroll
-              for (int g = 0; g < G; ++g) add_where(state.sums[g][2 * c], widened, static_cast<int>(group[j]), g);
-            }
+            for (int g = 0; g < G; ++g) add_where(state.sums[g][2 * c], widened, static_cast<int>(group[j]), g);
           }
-          if ((need_product_mask >> c) & 1u) {
-            const Accumulator widened = static_cast<Accumulator>(product);
-            if (use_masks) {
+        }
+        if ((need_product_mask >> c) & 1u) {
 #pragma unroll
-              for (int g = 0; g < G; ++g) state.sums[g][2 * c + 1] = __fma_rn(widened, masks[g], state.sums[g][2 * c + 1]);
-            } else {
+          for (int j = 0; j < kStreamLaneRows; ++j) {
+            const Accumulator widened = static_cast<Accumulator>(product[j]);
 #pragma unroll
-              for (int g = 0; g < G; ++g) add_where(state.sums[g][2 * c + 1], widened, static_cast<int>(group[j]), g);
-            }
+            for (int g = 0; g < G; ++g) add_where(state.sums[g][2 * c + 1], widened, static_cast<int>(group[j]), g);
           }
         }
       }
