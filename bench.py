@@ -384,40 +384,43 @@ def main() -> None:
                 "tuples_sent": int(stats.tuples_sent), "tuples_received": int(stats.tuples_received),
                 "nvlink_bytes": int(stats.nvlink_bytes), "colocated": int(stats.colocated)}
 
-    def distributed_join(table_o=None, table_l=None):
+    def distributed_join(table_o=None, table_l=None, record=True):
         """hyb_join_hash_distributed, one C-ABI call per rank: the ranks exchange the key bounds of their shards; co-located
         shards (this data set: a rank's lineitem rows belong to its own orders) are joined locally with global RowIDs, otherwise
         counts are published by kernel, both sides are split and pushed over NVLink, and every rank joins what it received.
         The forced-exchange time of the same call is reported next to the step in phases_rank0."""
         result = group.join_hash(table_o or orders, O_ORDERKEY, table_l or lineitem, L_ORDERKEY, orders_chunk_base,
                                  lineitem_chunk_base, radix_bits)
-        return result, device.last_stats()
+        return result, (device.last_stats() if record else None)
 
     def distributed_q1(table_l=None):
         """hyb_aggregate_hash_distributed: local pre-aggregation, partial groups stored into every peer's arena, merged by all"""
         return group.aggregate_hash(table_l or lineitem, Q1_GROUPBY, Q1_AGGREGATES, Q1_PREDICATES, lineitem_chunk_base, position_base)
 
     def run_step(record: bool):
+        """One step. record=False (warm-up and the TIMED loop): nothing but the operator calls and the reads of their result
+        sizes; record=True (a second, untimed loop of the same steps): per-operator CUDA-event statistics are fetched after
+        every call, which synchronises the host with the device and therefore stays out of the timed region."""
         flush_l2()
         scan = device.table_scan(lineitem, SCAN_PREDICATE)
-        scan_stats = device.last_stats()
+        scan_stats = device.last_stats() if record else None
         flush_l2()
         if distributed:
-            join, join_stats = distributed_join()
+            join, join_stats = distributed_join(record=record)
             if record:
                 phases["join"].append(phase_record(group.stats()))
         else:
             join = device.join_hash(orders, O_ORDERKEY, lineitem, L_ORDERKEY, capi.JOIN_INNER, -1)
-            join_stats = device.last_stats()
+            join_stats = device.last_stats() if record else None
         flush_l2()
         if distributed:
             aggregate = distributed_q1()
-            aggregate_stats = device.last_stats()
             if record:
+                aggregate_stats = device.last_stats()
                 phases["aggregate"].append(phase_record(group.stats()))
         else:
             aggregate = device.aggregate_hash(lineitem, Q1_GROUPBY, Q1_AGGREGATES, predicates=Q1_PREDICATES)
-            aggregate_stats = device.last_stats()
+            aggregate_stats = device.last_stats() if record else None
         if record:
             for name, stats in (("scan", scan_stats), ("join", join_stats), ("aggregate", aggregate_stats)):
                 operators[name].append((stats.dominant_kernel_ms, stats.device_ms, stats.algorithmic_bytes, stats.output_rows))
@@ -435,10 +438,14 @@ def main() -> None:
     with ClockSampler(local_rank) as clocks:
         begin = time.perf_counter()
         for _ in range(args.steps):
-            outputs = run_step(True)
+            outputs = run_step(False)
         device.synchronize()
         torch.cuda.synchronize()
         elapsed = time.perf_counter() - begin
+    barrier()
+    for _ in range(args.steps):  # the same steps again, instrumented (untimed): per-operator kernel / device times, phases
+        run_step(True)
+    device.synchronize()
     barrier()
     if distributed:
         tensor = torch.tensor([elapsed], device=f"cuda:{local_rank}", dtype=torch.float64)

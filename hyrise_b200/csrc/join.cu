@@ -1243,6 +1243,8 @@ __device__ __forceinline__ void span_warp_chunk(const ProbeParams& params, const
       if constexpr (!kScatter) {
         if (match[s] != kNoMatch) atomicAdd(counters + partition, 1u);  // counting needs no order
       } else {
+        // (run detection for sorted probe keys — equal keys adjacent, one shuffle + two votes instead of MATCH.ANY — was
+        //  measured: 5.57 vs 5.65 ms at SF 100, within noise; the ranking primitive is not what bounds this kernel)
         const uint32_t peers = partition_peers<kBallot>(partition, radix_bits);
         const uint32_t emitting = __ballot_sync(kFullMask, match[s] != kNoMatch) & peers;
         const int leader = __ffs(peers) - 1;

@@ -463,28 +463,37 @@ __global__ void __launch_bounds__(kScanThreads) scan_mask_kernel(const ScanParam
                                                                  uint32_t* __restrict__ tile_counts) {
   __shared__ uint32_t s_warp_totals[kScanWarps];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (uint32_t tile = blockIdx.x; tile < params.tile_count; tile += gridDim.x) {
-    const uint2 info = __ldg(params.tile_map + tile);
-    const uint32_t chunk = info.x, tile_row0 = info.y & 0x7FFFFFFFu;
-    const DevSegment segment = params.segments[chunk];
-    const ChunkTest test = params.tests[chunk];
-    uint32_t packed = 0, count = 0;
+  // Two tiles per iteration: their 2 x 4 vector loads per thread are independent and all in flight before the first
+  // predicate is evaluated; the two match counts (<= 16 384 each) share one reduction as the halves of a 32-bit word.
+  for (uint32_t tile = blockIdx.x; tile < params.tile_count; tile += 2 * gridDim.x) {
+    uint32_t packed[2] = {0u, 0u}, counts = 0;
+    const uint32_t tiles[2] = {tile, tile + gridDim.x};
 #pragma unroll
-    for (int it = 0; it < kScanIterations; ++it) {
-      const uint32_t row0 = tile_row0 + warp * kScanWarpRows + it * 256 + lane * 8;
-      const uint32_t mask = (test.mode != kTestNone && row0 < segment.row_count) ? evaluate8(segment, test, row0) : 0u;
-      packed |= mask << (8 * it);
-      count += __popc(mask);
+    for (int t = 0; t < 2; ++t) {
+      if (tiles[t] >= params.tile_count) continue;  // uniform
+      const uint2 info = __ldg(params.tile_map + tiles[t]);
+      const uint32_t chunk = info.x, tile_row0 = info.y & 0x7FFFFFFFu;
+      const DevSegment segment = params.segments[chunk];
+      const ChunkTest test = params.tests[chunk];
+#pragma unroll
+      for (int it = 0; it < kScanIterations; ++it) {
+        const uint32_t row0 = tile_row0 + warp * kScanWarpRows + it * 256 + lane * 8;
+        const uint32_t mask = (test.mode != kTestNone && row0 < segment.row_count) ? evaluate8(segment, test, row0) : 0u;
+        packed[t] |= mask << (8 * it);
+        counts += static_cast<uint32_t>(__popc(mask)) << (16 * t);
+      }
     }
-    masks_out[static_cast<size_t>(tile) * kScanThreads + threadIdx.x] = packed;
-    count = __reduce_add_sync(kFullMask, count);
-    if (lane == 0) s_warp_totals[warp] = count;
+    masks_out[static_cast<size_t>(tiles[0]) * kScanThreads + threadIdx.x] = packed[0];
+    if (tiles[1] < params.tile_count) masks_out[static_cast<size_t>(tiles[1]) * kScanThreads + threadIdx.x] = packed[1];
+    counts = __reduce_add_sync(kFullMask, counts);  // no carry between the halves: a warp holds <= 1024 rows per tile
+    if (lane == 0) s_warp_totals[warp] = counts;
     __syncthreads();
     if (threadIdx.x == 0) {
       uint32_t total = 0;
 #pragma unroll
       for (int w = 0; w < kScanWarps; ++w) total += s_warp_totals[w];
-      tile_counts[tile] = total;
+      tile_counts[tiles[0]] = total & 0xFFFFu;
+      if (tiles[1] < params.tile_count) tile_counts[tiles[1]] = total >> 16;
     }
     __syncthreads();
   }

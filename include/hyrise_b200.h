@@ -424,12 +424,15 @@ int hyb_peer_group_connect(hyb_context* context, hyb_peer_group_t group, const v
 int hyb_peer_group_destroy(hyb_context* context, hyb_peer_group_t group);
 
 /*
- * Inner JoinHash over ranks: both sides are split by the rank that owns the radix partition
- * (key & (world - 1), the reference's hash(key) & mask with the identity hash) and pushed straight into the owners'
- * arenas by the fused split + NVLink store kernel; every rank then joins what it received (hyb_join_hash on the received
- * tuples) and translates the result to GLOBAL RowIDs (chunk ids shifted by build_chunk_base / probe_chunk_base of the
- * rank the row came from). The result on this rank holds the partitions p with p % world == rank of the
- * reference-ordered result, in the reference's order.
+ * Inner JoinHash over ranks. The ranks first exchange the [min, max] of their build and probe keys through
+ * the control blocks. Co-located shards (no rank's probe range touches another rank's build range) are joined locally and
+ * the RowIDs are globalised by adding build_chunk_base / probe_chunk_base to the chunk ids: every rank then holds its slice
+ * of EVERY radix partition, and partition p of the global result is the concatenation of the ranks' slices in rank order
+ * (hyb_distributed_stats.colocated == 1). Otherwise both sides are split by the rank that owns the radix partition
+ * (key & (world - 1), the reference's hash(key) & mask with the identity hash) and pushed straight into the owners' arenas
+ * by the fused split + NVLink store kernel; every rank joins what it received and emits the GLOBAL RowIDs that travelled
+ * with the keys: a rank ends up with the partitions p = rank (mod world) of the reference-ordered result, in the
+ * reference's order (colocated == 0). HYB_JOIN_COLOCATED=0 / option "join_colocated" forces the exchange.
  */
 int hyb_join_hash_distributed(hyb_context* context, hyb_peer_group_t group, const hyb_join_side* build,
                               const hyb_join_side* probe, uint32_t build_chunk_base, uint32_t probe_chunk_base,

@@ -77,8 +77,8 @@ for name, entries in kernels.items():
                  f"{int(first['grid'] or 0)} x {int(first['block'] or 0)} | {mean('warp_inst') / 1e6:.1f} | {first['stalls']} |")
 open(os.path.join(out_dir, f"{tag}_kernels.md"), "w").write("\n".join(lines) + "\n")
 json.dump(traffic, open(os.path.join(out_dir, f"{tag}_traffic.json"), "w"), indent=1, sort_keys=True)
-# bench.py reads the latest capture of its default workload (SF 10 per GPU) for roofline.traffic
-json.dump({"sf": 10.0, "tag": tag, "kernels": traffic}, open(os.path.join(out_dir, "traffic.json"), "w"), indent=1, sort_keys=True)
+# bench.py reads the latest capture of its default workload (SF 100, whole job on one GPU) for roofline.traffic
+json.dump({"sf": float(os.environ.get("HYB_CAPTURE_SF", "100")), "tag": tag, "kernels": traffic}, open(os.path.join(out_dir, "traffic.json"), "w"), indent=1, sort_keys=True)
 shutil.copy(launches, os.path.join(out_dir, f"{tag}_launches.csv"))
 for path in extra:
     shutil.copy(path, os.path.join(out_dir, f"{tag}_{os.path.basename(path)}"))
