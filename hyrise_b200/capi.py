@@ -115,7 +115,7 @@ class DistributedStats(C.Structure):
     _fields_ = [("split_count_ms", C.c_float), ("count_wait_ms", C.c_float), ("push_ms", C.c_float),
                 ("done_wait_ms", C.c_float), ("local_ms", C.c_float), ("finish_ms", C.c_float),
                 ("tuples_sent", C.c_uint64), ("tuples_received", C.c_uint64), ("nvlink_bytes", C.c_uint64),
-                ("colocated", C.c_uint32), ("reserved", C.c_uint32)]
+                ("colocated", C.c_uint32), ("aggregate_partitioned", C.c_uint32)]
 
 
 class OperatorStats(C.Structure):

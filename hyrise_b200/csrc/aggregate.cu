@@ -1663,7 +1663,11 @@ extern "C" {
 
 static int exchange_partial_groups(hyb_context* context, const AggregateExchange& exchange, const Table* table,
                                    const hyb_aggregate_query* query, const std::vector<int32_t>& input_types,
-                                   std::vector<HostGroup>* groups);
+                                   std::vector<HostGroup>* groups, bool* out_needs_partitioning);
+
+static int exchange_partial_groups_partitioned(hyb_context* context, const AggregateExchange& exchange, const Table* table,
+                                               const hyb_aggregate_query* query, const std::vector<int32_t>& input_types,
+                                               std::vector<HostGroup>* groups, int* out_immediate);
 
 // Per (table, query shape): what the descriptor walk found. See Table::plan_memo.
 struct AggregatePlanMemo {
@@ -1762,6 +1766,7 @@ static int aggregate_hash_locked(hyb_context* context, const hyb_aggregate_query
 
   std::vector<HostGroup> groups;
   bool done = false;
+  int forced_immediate = -1;
   uint64_t algorithmic_bytes = 0;
   std::shared_ptr<AggregatePlanMemo> memo;
   {
@@ -2210,14 +2215,22 @@ static int aggregate_hash_locked(hyb_context* context, const hyb_aggregate_query
 
   if (exchange) {
     HYB_CHECK(!filter, HYB_ERR_UNSUPPORTED, "distributed aggregation of position-filtered inputs is not on the GPU path");
-    HYB_TRY(exchange_partial_groups(context, *exchange, table, query, input_types, &groups));
+    // Low cardinality: one 32 KB block per rank, replicated result. A rank whose partial groups do not fit sends its block's
+    // header alone; every rank sees that in the same set of blocks and all of them switch to the partitioned exchange.
+    bool needs_partitioning = false;
+    HYB_TRY(exchange_partial_groups(context, *exchange, table, query, input_types, &groups, &needs_partitioning));
+    if (needs_partitioning) {
+      HYB_TRY(exchange_partial_groups_partitioned(context, *exchange, table, query, input_types, &groups, &forced_immediate));
+    }
   }
 
   // ---- order the groups like the reference and materialise the result ---------------------------------------------
   uint64_t input_rows = 0;
   for (const auto& group : groups) input_rows += group.rows;
   bool immediate = false;
-  if (query->groupby_count == 1 && table->column_types[query->groupby_column_ids[0]] == HYB_TYPE_INT32) {
+  if (forced_immediate >= 0) {
+    immediate = forced_immediate != 0;  // partitioned exchange: decided on the statistics of ALL ranks' groups
+  } else if (query->groupby_count == 1 && table->column_types[query->groupby_column_ids[0]] == HYB_TYPE_INT32) {
     // immediate key shortcut (aggregate_hash.cpp:781-804)
     uint64_t min_key = ~uint64_t{0}, max_key = 0;
     for (const auto& group : groups) {
@@ -2410,7 +2423,8 @@ void merge_accumulator(int32_t function, bool integral, uint64_t* target, uint64
 
 static int exchange_partial_groups(hyb_context* context, const AggregateExchange& exchange, const Table* table,
                                    const hyb_aggregate_query* query, const std::vector<int32_t>& input_types,
-                                   std::vector<HostGroup>* groups) {
+                                   std::vector<HostGroup>* groups, bool* out_needs_partitioning) {
+  *out_needs_partitioning = false;
   PeerGroup* group = exchange.group;
   const uint32_t world = group->world, rank = group->rank;
   const uint32_t aggregate_count = query->aggregate_count;
@@ -2420,14 +2434,12 @@ static int exchange_partial_groups(hyb_context* context, const AggregateExchange
 
   // ---- serialise this rank's partial groups (positions and representative rows made global) -----------------------------
   const size_t capacity = (kPeerAggregateBlockBytes - 16) / sizeof(PartialGroupRecord);
-  HYB_CHECK(groups->size() <= capacity, HYB_ERR_UNSUPPORTED,
-            std::to_string(groups->size()) + " partial groups exceed the " + std::to_string(capacity) +
-                " the low-cardinality exchange carries per rank");
+  const bool overflow = groups->size() > capacity;  // header only: tells every rank to switch to the partitioned exchange
   std::vector<unsigned char> block(kPeerAggregateBlockBytes, 0);
   const uint64_t header[2] = {groups->size(), aggregate_count};
   std::memcpy(block.data(), header, sizeof(header));
   auto* records = reinterpret_cast<PartialGroupRecord*>(block.data() + 16);
-  for (size_t g = 0; g < groups->size(); ++g) {
+  for (size_t g = 0; g < (overflow ? 0 : groups->size()); ++g) {
     const HostGroup& source = (*groups)[g];
     PartialGroupRecord& record = records[g];
     for (size_t w = 0; w < kMaxKeyWords; ++w) record.key[w] = w < source.key.size() ? source.key[w] : 0;
@@ -2444,7 +2456,7 @@ static int exchange_partial_groups(hyb_context* context, const AggregateExchange
       record.counts[a] = source.counts[a];
     }
   }
-  const size_t used_bytes = 16 + groups->size() * sizeof(PartialGroupRecord);
+  const size_t used_bytes = 16 + (overflow ? 0 : groups->size()) * sizeof(PartialGroupRecord);
 
   // ---- store the block into every rank's arena, raise the flags, wait for everybody's ------------------------------------
   DeviceScratch scratch(context);
@@ -2467,6 +2479,13 @@ static int exchange_partial_groups(hyb_context* context, const AggregateExchange
   HYB_CUDA(cudaEventRecord(group->events[6], stream));
   HYB_CUDA(cudaStreamSynchronize(stream));
   group->stats.nvlink_bytes = used_bytes * (world - 1);
+
+  for (uint32_t source_rank = 0; source_rank < world; ++source_rank) {
+    uint64_t source_header[2];
+    std::memcpy(source_header, all.data() + size_t{source_rank} * kPeerAggregateBlockBytes, sizeof(source_header));
+    if (source_header[0] > capacity) *out_needs_partitioning = true;
+  }
+  if (*out_needs_partitioning) return HYB_OK;  // `groups` untouched: the caller exchanges them partitioned
 
   // ---- merge in rank order (every rank computes the same complete result) ---------------------------------------------------
   std::vector<HostGroup> merged;
@@ -2514,6 +2533,234 @@ static int exchange_partial_groups(hyb_context* context, const AggregateExchange
         const bool integral = input_types[a] == HYB_TYPE_INT32 || input_types[a] == HYB_TYPE_INT64;
         merge_accumulator(function, integral, &target->accumulators[a], &target->counts[a], record.accumulators[a], record.counts[a]);
       }
+    }
+  }
+  *groups = std::move(merged);
+  return HYB_OK;
+}
+
+// ---- high-cardinality form: partial groups are partitioned by the hash of their key and every group is merged by ONE rank ----
+namespace {
+
+// Row `rank` of every rank's count matrix (side 0) and of its side_bounds: per-destination record counts and
+// {min key, max key, rows, groups} of this rank's partial groups; then the count flag.
+__global__ void peer_publish_group_counts_kernel(PeerControl* const* controls, uint32_t rank, uint32_t world, unsigned long long epoch,
+                                                 const unsigned long long* counts, long long min_key, long long max_key,
+                                                 long long rows, long long groups) {
+  const uint32_t peer = threadIdx.x / 32, lane = threadIdx.x & 31;
+  if (peer < world) {
+    PeerControl* control = controls[peer];
+    if (lane < world) control->counts[0][rank][lane] = counts[lane];
+    if (lane == 0) {
+      long long* row = control->side_bounds[rank];
+      row[0] = min_key, row[1] = max_key, row[2] = rows, row[3] = groups;
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) st_volatile_u64(&control->count_flag[rank], epoch);
+  }
+}
+
+uint64_t host_mix64(uint64_t x) {
+  x ^= x >> 33;
+  x *= 0xFF51AFD7ED558CCDull;
+  x ^= x >> 33;
+  x *= 0xC4CEB9FE1A85EC53ull;
+  x ^= x >> 33;
+  return x;
+}
+
+int upload_controls(hyb_context* context, PeerGroup* group, DeviceScratch& scratch, PeerControl*** out_controls) {
+  PeerControl** controls = nullptr;
+  HYB_TRY(scratch.alloc_array(kPeerMax, &controls));
+  PeerControl* host_controls[kPeerMax] = {};
+  for (uint32_t peer = 0; peer < group->world; ++peer) host_controls[peer] = group->control(peer);
+  HYB_CUDA(cudaMemcpyAsync(controls, host_controls, sizeof(host_controls), cudaMemcpyHostToDevice, context->stream));
+  *out_controls = controls;
+  return HYB_OK;
+}
+
+}  // namespace
+
+static int exchange_partial_groups_partitioned(hyb_context* context, const AggregateExchange& exchange, const Table* table,
+                                               const hyb_aggregate_query* query, const std::vector<int32_t>& input_types,
+                                               std::vector<HostGroup>* groups, int* out_immediate) {
+  PeerGroup* group = exchange.group;
+  const uint32_t world = group->world, rank = group->rank;
+  const uint32_t aggregate_count = query->aggregate_count;
+  const size_t key_words = std::max<uint32_t>(query->groupby_count, 1);
+  cudaStream_t stream = context->stream;
+  const unsigned long long epoch = peer_next_epoch(group);
+  HYB_CUDA(cudaEventRecord(group->events[5], stream));
+
+  // ---- 1. serialise, destination-major (owner = hash of the key words; the same group lands on the same rank from everywhere).
+  //         Wire format, in 64-bit words: key[key_words] | rows, min_position, max_position | row_min, row_max | null_mask |
+  //         accumulators[aggregate_count] | counts[aggregate_count]
+  const size_t record_words = key_words + 6 + 2 * size_t{aggregate_count};
+  const size_t record_bytes = record_words * sizeof(uint64_t);
+  std::vector<uint32_t> owner(groups->size());
+  std::vector<unsigned long long> counts(kPeerMax, 0);
+  long long min_key = std::numeric_limits<long long>::max(), max_key = 0, rows = 0;
+  for (size_t g = 0; g < groups->size(); ++g) {
+    const HostGroup& source = (*groups)[g];
+    uint64_t hash = 0x9E3779B97F4A7C15ull ^ source.null_mask;
+    for (size_t w = 0; w < key_words; ++w) hash = host_mix64(hash ^ (w < source.key.size() ? source.key[w] : 0));
+    owner[g] = static_cast<uint32_t>(hash % world);
+    ++counts[owner[g]];
+    rows += static_cast<long long>(source.rows);
+    if (!source.null_mask && !source.key.empty()) {
+      min_key = std::min<long long>(min_key, static_cast<long long>(source.key[0]));
+      max_key = std::max<long long>(max_key, static_cast<long long>(source.key[0]));
+    }
+  }
+  std::vector<size_t> start(world + 1, 0);
+  for (uint32_t d = 0; d < world; ++d) start[d + 1] = start[d] + counts[d];
+  std::vector<uint64_t> records(std::max<size_t>(groups->size(), 1) * record_words);
+  std::vector<size_t> cursor(start.begin(), start.end() - 1);
+  const auto pack_row_id = [](hyb_row_id row) { return (static_cast<uint64_t>(row.chunk_id) << 32) | row.chunk_offset; };
+  for (size_t g = 0; g < groups->size(); ++g) {
+    const HostGroup& source = (*groups)[g];
+    uint64_t* record = records.data() + (cursor[owner[g]]++) * record_words;
+    for (size_t w = 0; w < key_words; ++w) record[w] = w < source.key.size() ? source.key[w] : 0;
+    uint64_t* fields = record + key_words;
+    hyb_row_id row_min = position_to_row_id_host(table, source.min_position);
+    hyb_row_id row_max = position_to_row_id_host(table, source.max_position);
+    row_min.chunk_id += exchange.chunk_id_base;
+    row_max.chunk_id += exchange.chunk_id_base;
+    fields[0] = source.rows;
+    fields[1] = source.min_position + exchange.position_base;
+    fields[2] = source.max_position + exchange.position_base;
+    fields[3] = pack_row_id(row_min);
+    fields[4] = pack_row_id(row_max);
+    fields[5] = source.null_mask;
+    for (uint32_t a = 0; a < aggregate_count; ++a) {
+      fields[6 + a] = source.accumulators[a];
+      fields[6 + aggregate_count + a] = source.counts[a];
+    }
+  }
+
+  // ---- 2. publish the per-destination counts and the key statistics; read everybody's ----------------------------------------
+  DeviceScratch scratch(context);
+  PeerControl** controls = nullptr;
+  HYB_TRY(upload_controls(context, group, scratch, &controls));
+  unsigned long long* d_counts = nullptr;
+  HYB_TRY(scratch.alloc_array(kPeerMax, &d_counts));
+  HYB_CUDA(cudaMemcpyAsync(d_counts, counts.data(), sizeof(unsigned long long) * kPeerMax, cudaMemcpyHostToDevice, stream));
+  peer_publish_group_counts_kernel<<<1, 32 * kPeerMax, 0, stream>>>(controls, rank, world, epoch, d_counts, min_key, max_key, rows,
+                                                                    static_cast<long long>(groups->size()));
+  HYB_CUDA(cudaGetLastError());
+  HYB_TRY(peer_wait(context, group->control(rank)->count_flag, world, epoch));
+  HYB_CUDA(cudaMemcpyAsync(group->h_counts, group->control(rank)->counts, sizeof(PeerControl::counts), cudaMemcpyDeviceToHost, stream));
+  std::vector<long long> h_bounds(kPeerMax * 8);
+  HYB_CUDA(cudaMemcpyAsync(h_bounds.data(), group->control(rank)->side_bounds, sizeof(PeerControl::side_bounds), cudaMemcpyDeviceToHost,
+                           stream));
+  HYB_CUDA(cudaStreamSynchronize(stream));
+  const auto count_at = [&](uint32_t source, uint32_t destination) {
+    return group->h_counts[(size_t{0} * kPeerMax + source) * kPeerMax + destination];
+  };
+  const size_t receive_capacity = 4 * group->region_bytes();
+  uint64_t incoming = 0;
+  for (uint32_t destination = 0; destination < world; ++destination) {
+    uint64_t total = 0;
+    for (uint32_t source = 0; source < world; ++source) total += count_at(source, destination);
+    HYB_CHECK(total * record_bytes <= receive_capacity, HYB_ERR_OOM,
+              "receive arena of rank " + std::to_string(destination) + " too small for " + std::to_string(total) +
+                  " partial groups of " + std::to_string(record_bytes) + " bytes");
+    if (destination == rank) incoming = total;
+  }
+  // the immediate-key decision of aggregate_hash.cpp:781-804 on the statistics of the WHOLE input
+  {
+    long long global_min = std::numeric_limits<long long>::max(), global_max = 0, global_rows = 0;
+    for (uint32_t r = 0; r < world; ++r) {
+      if (h_bounds[r * 8 + 3] == 0) continue;
+      global_min = std::min(global_min, h_bounds[r * 8 + 0]);
+      global_max = std::max(global_max, h_bounds[r * 8 + 1]);
+      global_rows += h_bounds[r * 8 + 2];
+    }
+    const bool single_int = query->groupby_count == 1 && table->column_types[query->groupby_column_ids[0]] == HYB_TYPE_INT32;
+    *out_immediate = single_int && global_max > 0 && global_max >= global_min &&
+                             static_cast<double>(global_max - global_min) < static_cast<double>(global_rows) * 1.2
+                         ? 1
+                         : 0;
+  }
+
+  // ---- 3. stage the records on the device and store each destination's run into its arena (NVLink P2P copies) ----------------
+  void* staged = nullptr;
+  HYB_TRY(scratch.alloc(std::max<size_t>(records.size() * sizeof(uint64_t), 256), &staged));
+  if (!groups->empty()) {
+    HYB_CUDA(cudaMemcpyAsync(staged, records.data(), groups->size() * record_bytes, cudaMemcpyHostToDevice, stream));
+  }
+  uint64_t sent_elsewhere = 0;
+  unsigned long long* host_flags[kPeerMax] = {};
+  for (uint32_t destination = 0; destination < world; ++destination) {
+    uint64_t before = 0;
+    for (uint32_t source = 0; source < rank; ++source) before += count_at(source, destination);
+    if (counts[destination]) {
+      char* target = group->region(destination, 0) + before * record_bytes;
+      HYB_CUDA(cudaMemcpyAsync(target, static_cast<const char*>(staged) + start[destination] * record_bytes,
+                               counts[destination] * record_bytes, cudaMemcpyDefault, stream));
+      if (destination != rank) sent_elsewhere += counts[destination];
+    }
+    host_flags[destination] = &group->control(destination)->done_flag[rank];
+  }
+  unsigned long long** flags = nullptr;
+  HYB_TRY(scratch.alloc_array(kPeerMax, &flags));
+  HYB_CUDA(cudaMemcpyAsync(flags, host_flags, sizeof(host_flags), cudaMemcpyHostToDevice, stream));
+  peer_raise_flags_kernel<<<1, 32, 0, stream>>>(flags, world, epoch);
+  HYB_CUDA(cudaGetLastError());
+  HYB_TRY(peer_wait(context, group->control(rank)->done_flag, world, epoch));
+  std::vector<uint64_t> received(std::max<uint64_t>(incoming, 1) * record_words);
+  if (incoming) {
+    HYB_CUDA(cudaMemcpyAsync(received.data(), group->region(rank, 0), incoming * record_bytes, cudaMemcpyDeviceToHost, stream));
+  }
+  HYB_CUDA(cudaEventRecord(group->events[6], stream));
+  HYB_CUDA(cudaStreamSynchronize(stream));
+  group->stats.nvlink_bytes = sent_elsewhere * record_bytes;
+  group->stats.tuples_sent = sent_elsewhere;
+  group->stats.tuples_received = incoming;
+  group->stats.aggregate_partitioned = 1;
+
+  // ---- 4. merge what this rank owns (records arrive grouped by source rank, in rank order) ----------------------------------
+  const auto unpack_row_id = [](uint64_t packed) {
+    return hyb_row_id{static_cast<uint32_t>(packed >> 32), static_cast<uint32_t>(packed)};
+  };
+  std::vector<HostGroup> merged;
+  std::unordered_map<std::string, size_t> index;
+  index.reserve(incoming * 2 + 16);
+  std::string probe(key_words * sizeof(uint64_t) + sizeof(uint64_t), '\0');
+  for (uint64_t g = 0; g < incoming; ++g) {
+    const uint64_t* record = received.data() + g * record_words;
+    const uint64_t* fields = record + key_words;
+    std::memcpy(probe.data(), record, key_words * sizeof(uint64_t));
+    std::memcpy(probe.data() + key_words * sizeof(uint64_t), &fields[5], sizeof(uint64_t));
+    const auto [iter, inserted] = index.try_emplace(probe, merged.size());
+    if (inserted) {
+      merged.emplace_back();
+      HostGroup& created = merged.back();
+      created.key.assign(record, record + key_words);
+      created.null_mask = static_cast<uint32_t>(fields[5]);
+      created.accumulators.assign(aggregate_count, 0);
+      created.counts.assign(aggregate_count, 0);
+      created.has_global_rows = true;
+      created.min_position = ~uint64_t{0};
+      created.max_position = 0;
+    }
+    HostGroup& target = merged[iter->second];
+    if (fields[0]) {
+      if (fields[1] < target.min_position || target.rows == 0) {
+        target.min_position = fields[1];
+        target.row_min = unpack_row_id(fields[3]);
+      }
+      if (fields[2] >= target.max_position || target.rows == 0) {
+        target.max_position = fields[2];
+        target.row_max = unpack_row_id(fields[4]);
+      }
+    }
+    target.rows += fields[0];
+    for (uint32_t a = 0; a < aggregate_count; ++a) {
+      const int32_t function = query->aggregates[a].function;
+      const bool integral = input_types[a] == HYB_TYPE_INT32 || input_types[a] == HYB_TYPE_INT64;
+      merge_accumulator(function, integral, &target.accumulators[a], &target.counts[a], fields[6 + a], fields[6 + aggregate_count + a]);
     }
   }
   *groups = std::move(merged);

@@ -439,11 +439,13 @@ int hyb_join_hash_distributed(hyb_context* context, hyb_peer_group_t group, cons
                               int32_t radix_bits, hyb_join_result_t* out_result);
 
 /*
- * AggregateHash over ranks, low-cardinality form (the partial groups of a rank must fit one 32 KB block, else
- * HYB_ERR_UNSUPPORTED): every rank pre-aggregates its shard (AVG travels as SUM and COUNT), stores its partial groups
- * into every peer's arena and merges all ranks' blocks in rank order — every rank ends up with the complete result.
- * chunk_id_base / position_base: first global chunk id / row position of this rank's shard (group order and
- * representative RowIDs refer to the global table).
+ * AggregateHash over ranks: every rank pre-aggregates its shard (AVG travels as SUM and COUNT). The ranks agree on the form:
+ * low cardinality (every rank's partial groups fit one 32 KB block): the blocks are stored into every peer's arena and
+ * merged by all ranks in rank order — every rank returns the complete, bit-identical result; high cardinality (Q3 / Q18
+ * shapes): the partial groups are partitioned by the hash of their key, pushed into the owners' tuple regions over NVLink
+ * and merged by the owner — a rank returns the groups it owns (hyb_distributed_stats.aggregate_partitioned == 1).
+ * Representative RowIDs refer to the global table (chunk ids shifted by chunk_id_base); position_base = number of rows of
+ * the global table before this rank's shard (first-appearance order across ranks).
  */
 int hyb_aggregate_hash_distributed(hyb_context* context, hyb_peer_group_t group, const struct hyb_aggregate_query* query,
                                    uint32_t chunk_id_base, uint64_t position_base, hyb_aggregate_result_t* out_result);
@@ -462,7 +464,11 @@ typedef struct hyb_distributed_stats {
   uint32_t colocated;        /* join: 1 = the ranks' key ranges did not overlap across ranks, every rank joined its own shards
                                 (result layout: every rank holds its slice of EVERY partition, global order = rank order
                                 inside a partition); 0 = radix exchange (a partition lives on rank partition % world) */
-  uint32_t reserved;
+  uint32_t aggregate_partitioned; /* aggregate: 1 = high-cardinality form — the partial groups were partitioned by the hash of
+                                     their key and this rank's result holds the groups it owns (every group on exactly one
+                                     rank, in the reference's order among the rank's groups; the global order is the merge
+                                     of the ranks' results by representative RowID / key); 0 = every rank holds the complete
+                                     result */
 } hyb_distributed_stats;
 int hyb_peer_group_stats(hyb_context* context, hyb_peer_group_t group, hyb_distributed_stats* out_stats);
 

@@ -181,6 +181,36 @@ def run_distributed_checks(device, rank, world, torch_device, sf=SF, legacy_path
         for other_rows, other_values in everyone[1:]:   # replicated result: bit-identical on every rank
             expect(row_ids_equal(other_rows, output.row_ids), "Q1 result differs between ranks")
             expect(all(np.array_equal(a, b) for a, b in zip(other_values, output.values)), "Q1 values differ between ranks")
+    # ---- aggregate, high cardinality (Q3 / Q18 shape): partial groups partitioned by key hash, every group merged by one rank --
+    from hyrise_b200.device import Expression
+    wide = [Aggregate(capi.AGG_SUM, Expression.column(1)), Aggregate(capi.AGG_AVG, Expression.column(2)),
+            Aggregate(capi.AGG_MIN, Expression.column(2)), Aggregate(capi.AGG_MAX, Expression.column(3)),
+            Aggregate(capi.AGG_COUNT_STAR)]
+    owned = group.aggregate_hash(lineitem, [L_ORDERKEY, L_LINESTATUS], wide, [], lineitem_base, position_base)
+    wide_stats = group.stats()
+    parts = [None] * world
+    dist.all_gather_object(parts, (owned.row_ids, owned.values, owned.nulls, int(wide_stats.aggregate_partitioned)))
+    if rank == 0:
+        expected = orc.aggregate_hash(global_lineitem, [L_ORDERKEY, L_LINESTATUS], wide)
+        expect(all(part[3] == 1 for part in parts), "high-cardinality aggregate did not take the partitioned exchange")
+        rows = np.concatenate([part[0] for part in parts])
+        expect(len(rows) == expected.group_count, f"partitioned aggregate: {len(rows)} groups, expected {expected.group_count}")
+        if len(rows) == expected.group_count:
+            def ordered(row_ids):   # first-appearance order = ascending representative RowID
+                return np.lexsort((row_ids["chunk_offset"], row_ids["chunk_id"]))
+            got_order, want_order = ordered(rows), ordered(expected.row_ids)
+            expect(row_ids_equal(rows[got_order], expected.row_ids[want_order]), "partitioned aggregate: representative RowIDs differ")
+            expect(np.array_equal(want_order, np.arange(len(want_order))), "oracle groups are not in first-appearance order")
+            for index in range(len(wide)):
+                got = np.concatenate([part[1][index] for part in parts])[got_order]
+                want = expected.values[index][want_order]
+                if want.dtype.kind == "f":
+                    expect(np.allclose(got, want, rtol=1e-6, atol=0.0), f"partitioned aggregate {index}")
+                else:
+                    expect(np.array_equal(got, want), f"partitioned aggregate {index}")
+            # every group on exactly one rank, each rank's groups in first-appearance order
+            for part in parts:
+                expect(np.array_equal(ordered(part[0]), np.arange(len(part[0]))), "a rank's groups are not in first-appearance order")
     dist.barrier()
     group.destroy()
     lineitem.drop()

@@ -331,7 +331,7 @@ def test_peer_group_single_rank(device):
 
     tables = TpchTables(0.05, seed=11)
     lineitem, orders = device.upload(tables.lineitem), device.upload(tables.orders)
-    group = hd.connect_peer_group(device, tables.lineitem.row_count + 4096)
+    group = hd.connect_peer_group(device, 4 * tables.lineitem.row_count + 4096)   # room for the partitioned aggregate's records
     for colocated in ("0", "1"):  # a world of one is trivially co-located: force the exchange path first, then the shortcut
         device.set_option("join_colocated", colocated)
         for radix_bits in (3, 0, 3):  # repeated calls reuse the arena, the received tables and the epoch flags
@@ -359,6 +359,17 @@ def test_peer_group_single_rank(device):
     got = group.aggregate_hash(lineitem, [L_RETURNFLAG, L_LINESTATUS], Q1_AGGREGATES, predicates, 0, 0)
     want = orc.aggregate_hash(tables.lineitem, [L_RETURNFLAG, L_LINESTATUS], Q1_AGGREGATES, predicates=predicates)
     from helpers import assert_aggregate_outputs_equal
+    assert_aggregate_outputs_equal(got, want)
+    # high cardinality: the partial groups do not fit the 32 KB block -> partitioned exchange (with a world of one, through
+    # this rank's own tuple regions), result identical to the local operator's
+    from hyrise_b200.device import Aggregate, Expression
+    wide = [Aggregate(capi.AGG_SUM, Expression.column(1)), Aggregate(capi.AGG_MIN, Expression.column(2)), Aggregate(capi.AGG_COUNT_STAR)]
+    got = group.aggregate_hash(lineitem, [L_ORDERKEY, L_LINESTATUS], wide, [], 0, 0)
+    assert group.stats().aggregate_partitioned == 1
+    want = orc.aggregate_hash(tables.lineitem, [L_ORDERKEY, L_LINESTATUS], wide)
+    assert_aggregate_outputs_equal(got, want)
+    got = group.aggregate_hash(lineitem, [L_ORDERKEY], wide, [], 0, 0)   # single int32 column: immediate-key order
+    want = orc.aggregate_hash(tables.lineitem, [L_ORDERKEY], wide)
     assert_aggregate_outputs_equal(got, want)
     group.destroy()
     lineitem.drop()
