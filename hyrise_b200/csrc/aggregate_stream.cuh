@@ -1,23 +1,26 @@
-// aggregate_stream_kernel — the low-cardinality AggregateHash path (Q1 / Q6 shapes) rebuilt around the TMA unit.
+// aggregate_stream_kernel / aggregate_stream_static_kernel — the low-cardinality AggregateHash path (Q1 / Q6 shapes) built
+// around the TMA unit.
 //
-// Included by aggregate.cu (uses FastPlan, WorkType, apply_affine, multiply, add_where, key entries and the per-CTA
-// partials layout of aggregate_fast_kernel; the host merge of the partials is shared). What changed and why:
+// Included by aggregate.cu (uses FastPlan, WorkType, apply_affine, multiply, add_where, key entries and the per-CTA partials
+// layout of aggregate_fast_kernel; the host merge of the partials is shared). Design, with the measurement behind each point
+// (profiles/README.md):
 //
-//   * aggregate_fast_kernel was instruction-bound, not bandwidth-bound: 410 M warp instructions for 60 M rows (vector
-//     unpacking of 8 rows per thread, per-iteration hit masks, an instruction footprint that overflowed the I-cache).
-//     Here one row is handled per lane and step, with scalar code that is ~4x shorter per row.
-//   * no load latency on the compute warps: a producer warp walks the (static, reproducible) tile schedule ahead of the
-//     consumers and has the TMA unit copy — per tile, with one cp.async.bulk per array — the tile's slice of every
-//     referenced column, the small dictionaries of the value columns and the key words of the group-by dictionaries
-//     into a 3-stage shared-memory ring (mbarrier full/empty pairs). Segment descriptors and the chunk's predicate
-//     tests are fetched by the producer's lanes in parallel and handed over through the stage header, so consumers
-//     never wait on global memory except for dictionaries too large to stage (gathered through L1).
-//   * there is no CTA-wide barrier in the row loop: consumer warps run tile after tile on their own; the value-ID
-//     combination -> group table is private to a warp and rebuilt from the staged key words when the chunk changes.
+//   * aggregate_fast_kernel was instruction-bound, not bandwidth-bound (410 M warp instructions for 60 M rows). Here a lane
+//     handles 4 consecutive rows per step with scalar code; for the query shapes in HYB_STREAM_SHAPES the row loop is compiled
+//     with widths, kinds and the set of sums folded (~95 thread instructions per row for Q1).
+//   * one persistent CTA per SM, 15 consumer warps + 1 producer warp, up to 128 registers per thread.
+//   * no load latency on the compute warps: the producer walks a static tile schedule ahead of the consumers and has the TMA
+//     unit copy — per tile, one cp.async.bulk per array — the tile's slice of every referenced column into a shared-memory
+//     ring of StreamPlan::stage_count stages (mbarrier full/empty pairs). What it derives from segment descriptors is cached in
+//     registers per chunk; small dictionaries and group-key words are copied once per stage and chunk. Consumers touch global
+//     memory only for dictionaries too large to stage (gathered through L1).
+//   * no CTA-wide barrier in the row loop: consumer warps run tile after tile on their own; the value-ID combination -> group
+//     table is private to a warp and rebuilt from the staged key words when the chunk changes.
+//   * sums: one DFMA per (row, group, sum) with a 0/1 group mask; steps with non-finite operands take the select form.
 //
-// Eligibility is decided on the host per call (stream_plan_for): every referenced column streams a fixed-width vector
-// of <= 4 bytes per row, carries no NULLs, group-by columns are dictionary segments with 1-byte value-IDs whose
-// combinations fit kMaxCombos; everything else keeps aggregate_fast_kernel / aggregate_general_kernel.
+// Eligibility is decided on the host per call (stream_layout_for): every referenced column streams a fixed-width vector of
+// <= 4 bytes per row, carries no NULLs, group-by columns are dictionary segments with 1-byte value-IDs whose combinations fit
+// kMaxCombos; everything else keeps aggregate_fast_kernel / aggregate_general_kernel.
 #pragma once
 
 namespace hyb {
@@ -286,7 +289,7 @@ __device__ __forceinline__ unsigned long long stream_key_entry(const unsigned ch
 // typically in the table's last chunk): all consumer warps widen the staged slice in place — read into registers,
 // barrier, write — so that the row loop exists in one variant only. Rare; CTA-uniform (every consumer thread calls it).
 __device__ __noinline__ void stream_widen_slice(unsigned char* slot, uint32_t from, uint32_t to, uint32_t rows) {
-  constexpr int kPerThread = kStreamTileRows / kStreamConsumerThreads;  // 8
+  constexpr int kPerThread = kStreamTileRows / kStreamConsumerThreads;  // 4
   uint32_t held[kPerThread];
 #pragma unroll
   for (int i = 0; i < kPerThread; ++i) {
@@ -689,11 +692,11 @@ __device__ __forceinline__ void aggregate_stream_body(const StreamPlan& plan) {
       reinterpret_cast<StreamStageInfo*>(s_stages + size_t{stage} * plan.stage_bytes + plan.info_offset)->array_chunk = 0xFFFFFFFFu;
     }
     __syncwarp();
-    uint32_t fill = 0, stage = 0, empty_parity = 1;
+    uint32_t stage = 0, empty_parity = 1;
     for (uint32_t unit = blockIdx.x; unit < unit_count; unit += gridDim.x) {
       const uint32_t unit_end = min(fast.tile_count, (unit + 1) * plan.unit_tiles);
       uint2 where = __ldg(fast.tile_map + unit * plan.unit_tiles);
-      for (uint32_t tile = unit * plan.unit_tiles; tile < unit_end; ++tile, ++fill) {
+      for (uint32_t tile = unit * plan.unit_tiles; tile < unit_end; ++tile) {
         const uint32_t chunk = where.x;
         const uint32_t row0 = where.y & 0x7FFFFFFFu;
         if (tile + 1 < unit_end) where = __ldg(fast.tile_map + tile + 1);  // in flight while this tile is set up
@@ -881,7 +884,7 @@ __device__ __forceinline__ void aggregate_stream_body(const StreamPlan& plan) {
       if (!info->regular) stream_widen_tile(plan, info, s_stages + size_t{stage} * plan.stage_bytes);  // rare, CTA-uniform
       stream_warp_rows<W, G, C, S>(plan, info, stage_base, warp, lane, my_combos, s_hash, s_keys, combo_stride, affine_a,
                                    affine_b, state);
-      if (++since_flush == 16) {  // <= 8 rows per lane and tile: the bytes stay below 256
+      if (++since_flush == 16) {  // 4 rows per lane and tile: 64 per flush, the bytes stay below 256
         flush_row_counts();
         since_flush = 0;
       }
