@@ -54,7 +54,25 @@ def tbl_to_npz(source, destination, keep):
     np.savez_compressed(destination, **arrays)
 
 
+def copy_binary_fixtures():
+    """resources/test_data/bin: the reference's own binary-table fixtures (binary_parser_test.cpp), a few hundred bytes each.
+    LZ4MultipleBlocks.bin (49 KB) is left out: LZ4 segments are not on the device path."""
+    source_root = "/root/reference/resources/test_data/bin"
+    target_root = os.path.join(HERE, "bin")
+    os.makedirs(target_root, exist_ok=True)
+    for entry in sorted(os.listdir(source_root)):
+        source = os.path.join(source_root, entry)
+        if os.path.isdir(source):
+            os.makedirs(os.path.join(target_root, entry), exist_ok=True)
+            for name in sorted(os.listdir(source)):
+                if name.endswith(".bin"):
+                    shutil.copyfile(os.path.join(source, name), os.path.join(target_root, entry, name))
+        elif entry.endswith(".bin") and entry != "LZ4MultipleBlocks.bin":
+            shutil.copyfile(source, os.path.join(target_root, entry))
+
+
 def main():
+    copy_binary_fixtures()
     if not os.path.isdir(REF):
         sys.exit("reference test data not mounted; nothing to do")
     out_tbl = os.path.join(HERE, "tbl")
