@@ -17,6 +17,7 @@ UnsupportedOnDevice — the reference's default benchmark encoding does not prod
 """
 from __future__ import annotations
 
+import os
 import struct
 from dataclasses import dataclass, field
 
@@ -304,3 +305,100 @@ def write_binary_table(table: Table, path: str) -> None:
                 raise ValueError(f"cannot write encoding {segment.encoding}")
     with open(path, "wb") as file:
         file.write(b"".join(out))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The native loader (hyrise_b200/csrc/binary_loader.cu, hyb_binary_table_*): the same parse inside the C-ABI library, into
+# pinned host blocks, with a one-call upload. This wrapper exposes it as a storage.Table whose segment buffers are views
+# into the library's host blocks.
+# ---------------------------------------------------------------------------------------------------------------------
+import ctypes as C  # noqa: E402
+
+
+class NativeBinaryTable:
+    """hyb_binary_table: parse in C++ (no GPU needed), `upload(context)` = hyb_table_upload_binary."""
+
+    def __init__(self, path: str, pinned: bool = False):
+        self.lib = capi.load_library()
+        self.ptr = C.c_void_p()
+        capi.check(self.lib.hyb_binary_table_open(os.fsencode(path), 1 if pinned else 0, C.byref(self.ptr)))
+        chunk_size, chunk_count, column_count = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        capi.check(self.lib.hyb_binary_table_info(self.ptr, C.byref(chunk_size), C.byref(chunk_count), C.byref(column_count)))
+        definitions = []
+        for column in range(column_count.value):
+            name, data_type, nullable = C.c_char_p(), C.c_int32(), C.c_int32()
+            capi.check(self.lib.hyb_binary_table_column(self.ptr, column, C.byref(name), C.byref(data_type), C.byref(nullable)))
+            definitions.append(ColumnDefinition(name.value.decode(), data_type.value, bool(nullable.value)))
+        view = capi.TableView()
+        capi.check(self.lib.hyb_binary_table_view(self.ptr, C.byref(view)))
+        self.table = Table(definitions, target_chunk_size=chunk_size.value)
+        self.sorted_columns = []
+        for chunk in range(chunk_count.value):
+            segments = [self._segment(view.segments[chunk * column_count.value + column], chunk, column, definitions[column])
+                        for column in range(column_count.value)]
+            self.table.chunks.append(Chunk(segments))
+            ids, modes, count = (C.c_uint16 * 64)(), (C.c_uint8 * 64)(), C.c_uint32()
+            capi.check(self.lib.hyb_binary_table_sorted_columns(self.ptr, chunk, ids, modes, C.byref(count)))
+            self.sorted_columns.append([(ids[i], modes[i]) for i in range(count.value)])
+
+    @staticmethod
+    def _view(address, dtype, count) -> np.ndarray | None:
+        if not address:
+            return None
+        dtype = np.dtype(dtype)
+        if count == 0:
+            return np.zeros(0, dtype=dtype)
+        buffer = (C.c_uint8 * (count * dtype.itemsize)).from_address(address)
+        return np.frombuffer(buffer, dtype=dtype, count=count)
+
+    def _segment(self, desc, chunk: int, column: int, definition: ColumnDefinition) -> Segment:
+        rows = desc.row_count
+        segment = Segment(desc.encoding, desc.data_type, rows, vector_type=desc.vector_type, bit_width=desc.bit_width,
+                          dictionary_size=desc.dictionary_size)
+        if desc.encoding == capi.ENC_UNENCODED:
+            segment.values = self._view(desc.values, NUMPY_TYPES[desc.data_type], rows)
+        elif desc.encoding == capi.ENC_FRAME_OF_REFERENCE:
+            segment.values = self._view(desc.values, np.int32, (rows + capi.FOR_BLOCK_SIZE - 1) // capi.FOR_BLOCK_SIZE)
+        elif definition.data_type != capi.TYPE_STRING:
+            segment.values = self._view(desc.values, NUMPY_TYPES[desc.data_type], desc.dictionary_size)
+        segment.nulls = self._view(desc.nulls, np.uint8, rows)
+        if desc.encoding != capi.ENC_UNENCODED:
+            if desc.vector_type == capi.VEC_BITPACKED:
+                segment.attribute_vector = self._view(desc.attribute_vector, np.uint64, (rows * desc.bit_width + 63) // 64)
+            else:
+                width = {capi.VEC_FIXED_1B: np.uint8, capi.VEC_FIXED_2B: np.uint16, capi.VEC_FIXED_4B: np.uint32}[desc.vector_type]
+                segment.attribute_vector = self._view(desc.attribute_vector, width, rows)
+        if definition.data_type == capi.TYPE_STRING:
+            chars, offsets, count = C.c_void_p(), C.POINTER(C.c_uint64)(), C.c_uint32()
+            capi.check(self.lib.hyb_binary_table_string_dictionary(self.ptr, chunk, column, C.byref(chars), C.byref(offsets), C.byref(count)))
+            blob = C.string_at(chars, offsets[count.value]) if count.value else b""
+            segment.string_dictionary = _string_array([blob[offsets[i]:offsets[i + 1]] for i in range(count.value)]) \
+                if count.value else np.zeros(0, dtype="S1")
+            segment.dictionary_codes = self._view(desc.dictionary_codes, np.uint64, desc.dictionary_size)
+        return segment
+
+    def value_id_bounds(self, column: int, value: bytes, value2: bytes | None = None) -> np.ndarray:
+        width = 4 if value2 is not None else 2
+        bounds = np.empty((self.table.chunk_count, width), dtype=np.uint32)
+        capi.check(self.lib.hyb_binary_table_value_id_bounds(self.ptr, column, value, len(value), value2, len(value2) if value2 else 0,
+                                                             bounds.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return bounds
+
+    def host_blocks(self) -> list:
+        count = C.c_uint32()
+        capi.check(self.lib.hyb_binary_table_blocks(self.ptr, None, C.byref(count)))
+        blocks = (capi.HostBlock * max(count.value, 1))()
+        capi.check(self.lib.hyb_binary_table_blocks(self.ptr, blocks, C.byref(count)))
+        return list(blocks[: count.value])
+
+    def upload(self, context):
+        """hyb_table_upload_binary: one DMA per host block; returns a DeviceTable bound to this host table."""
+        from .device import DeviceTable
+        handle = C.c_uint64()
+        capi.check(self.lib.hyb_table_upload_binary(context.ptr, self.ptr, C.byref(handle)))
+        return DeviceTable(context, handle.value, self.table, self.table.view())
+
+    def close(self) -> None:
+        if self.ptr:
+            self.lib.hyb_binary_table_close(self.ptr)
+            self.ptr = None

@@ -154,6 +154,17 @@ SYMBOLS = {
     "hyb_blocks_upload": [_CTX, C.POINTER(HostBlock), _U32, C.POINTER(_U64)],
     "hyb_table_upload_from_blocks": [_CTX, C.POINTER(TableView), _U64, C.POINTER(_U64)],
     "hyb_blocks_free": [_CTX, _U64],
+    "hyb_binary_table_open": [C.c_char_p, _I32, C.POINTER(C.c_void_p)],
+    "hyb_binary_table_close": [C.c_void_p],
+    "hyb_binary_table_info": [C.c_void_p, C.POINTER(_U32), C.POINTER(_U32), C.POINTER(_U32)],
+    "hyb_binary_table_column": [C.c_void_p, _U32, C.POINTER(C.c_char_p), C.POINTER(_I32), C.POINTER(_I32)],
+    "hyb_binary_table_view": [C.c_void_p, C.POINTER(TableView)],
+    "hyb_binary_table_sorted_columns": [C.c_void_p, _U32, C.POINTER(C.c_uint16), C.POINTER(C.c_uint8), C.POINTER(_U32)],
+    "hyb_binary_table_string_dictionary": [C.c_void_p, _U32, _U32, C.POINTER(C.c_void_p), C.POINTER(C.POINTER(C.c_uint64)),
+                                           C.POINTER(_U32)],
+    "hyb_binary_table_value_id_bounds": [C.c_void_p, _U32, C.c_char_p, _U64, C.c_char_p, _U64, C.POINTER(_U32)],
+    "hyb_binary_table_blocks": [C.c_void_p, C.POINTER(HostBlock), C.POINTER(_U32)],
+    "hyb_table_upload_binary": [_CTX, C.c_void_p, C.POINTER(_U64)],
     "hyb_table_info": [_CTX, _U64, C.POINTER(_U32), C.POINTER(_U32), C.POINTER(_U64), C.POINTER(_U64)],
     "hyb_flip_predicate_condition": [_I32, C.POINTER(_I32)],
     "hyb_next_float_towards": [C.c_double, C.c_double, C.POINTER(C.c_float), C.POINTER(_I32)],
@@ -233,7 +244,7 @@ def load_library(path: str | None = None) -> C.CDLL:
     for name, argtypes in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
-        fn.restype = C.c_char_p if name == "hyb_last_error" else C.c_int
+        fn.restype = C.c_char_p if name == "hyb_last_error" else None if name == "hyb_binary_table_close" else C.c_int
     _lib = lib
     return lib
 

@@ -230,6 +230,35 @@ int hyb_table_append_chunk_device(hyb_context* context, hyb_table_t table, const
 int hyb_table_drop(hyb_context* context, hyb_table_t table);
 
 /*
+ * Loading path: Hyrise's binary table format (BinaryParser::parse, import_export/binary/binary_parser.cpp:40-344 — what
+ * hyriseBenchmarkTPCH caches under tpch_cached_tables/) -> host segments in this header's layout. Value / Dictionary /
+ * FrameOfReference segments keep the reference's encoding (FixedWidthInteger and BitPacking vectors as stored), RunLength
+ * segments are expanded, FixedStringDictionary and unencoded string segments become string dictionaries; every buffer sits
+ * in a 256-byte aligned slot of a few large host blocks — pinned (`pinned` != 0 and a CUDA device is usable) so that
+ * hyb_table_upload_binary moves the table with one DMA per block. HYB_ERR_NOT_FOUND: no such file; HYB_ERR_INVALID: what
+ * the reference reports with Fail() (invalid encoding / vector type, truncated file); HYB_ERR_UNSUPPORTED: LZ4 segments.
+ * The parse itself needs no GPU.
+ */
+typedef struct hyb_binary_table hyb_binary_table;
+int hyb_binary_table_open(const char* path, int32_t pinned, hyb_binary_table** out_table);
+void hyb_binary_table_close(hyb_binary_table* table);
+int hyb_binary_table_info(const hyb_binary_table* table, uint32_t* out_chunk_size, uint32_t* out_chunk_count, uint32_t* out_column_count);
+int hyb_binary_table_column(const hyb_binary_table* table, uint32_t column, const char** out_name, int32_t* out_data_type,
+                            int32_t* out_nullable);
+/* Segment descriptors (chunk-major) pointing into the table's host blocks; valid until hyb_binary_table_close. */
+int hyb_binary_table_view(const hyb_binary_table* table, hyb_table_view* out_view);
+/* Per chunk: the sorted-by information the file carries ({column id, SortMode} pairs, chunk.hpp). */
+int hyb_binary_table_sorted_columns(const hyb_binary_table* table, uint32_t chunk, uint16_t* out_column_ids, uint8_t* out_sort_modes,
+                                    uint32_t* out_count);
+/* Host-resident dictionary of a string segment: entry i = chars[offsets[i] .. offsets[i + 1]). */
+int hyb_binary_table_string_dictionary(const hyb_binary_table* table, uint32_t chunk, uint32_t column, const char** out_chars,
+                                       const uint64_t** out_offsets, uint32_t* out_count);
+/* hyb_scan_predicate.value_id_bounds for a string column of this table: per chunk DictionarySegment::lower_bound /
+ * upper_bound of `value` (and of `value2` for BETWEEN; pass NULL otherwise): chunk_count x (2 | 4) entries. */
+int hyb_binary_table_value_id_bounds(const hyb_binary_table* table, uint32_t column, const char* value, uint64_t value_length,
+                                     const char* value2, uint64_t value2_length, uint32_t* out_bounds);
+
+/*
  * Arena upload: when the segment buffers of one or more tables live inside a few large host blocks (a pinned
  * MemoryResource arena, cf. src/lib/memory/default_memory_resource.cpp:29-35 and Chunk::migrate, storage/chunk.hpp:119),
  * DMA each block ONCE and let tables point into the device copies instead of issuing one copy per segment buffer
@@ -247,6 +276,9 @@ int hyb_table_upload_from_blocks(hyb_context* context, const hyb_table_view* vie
                                  hyb_table_t* out_table);
 /* Releases the device copies once no table references them any more. */
 int hyb_blocks_free(hyb_context* context, hyb_block_set_t block_set);
+/* The host blocks of a parsed binary table (pointer to an array owned by the table) and the one-call upload. */
+int hyb_binary_table_blocks(const hyb_binary_table* table, hyb_host_block* out_blocks, uint32_t* out_count);
+int hyb_table_upload_binary(hyb_context* context, const hyb_binary_table* table, hyb_table_t* out_table);
 int hyb_table_info(hyb_context* context, hyb_table_t table, uint32_t* out_chunk_count, uint32_t* out_column_count,
                    uint64_t* out_row_count, uint64_t* out_device_bytes);
 

@@ -103,11 +103,51 @@ class DeviceContext {
   hyb_context* _context = nullptr;
 };
 
+// A table file in Hyrise's binary format (BinaryParser::parse, import_export/binary/binary_parser.cpp:40-344), parsed into
+// pinned host blocks in the device pool's layout. Parsing needs no GPU; DeviceTable(context, binary_table) uploads it with
+// one DMA per block.
+class BinaryTable {
+ public:
+  explicit BinaryTable(const std::string& path, bool pinned = true) { check(hyb_binary_table_open(path.c_str(), pinned ? 1 : 0, &_table)); }
+  ~BinaryTable() { hyb_binary_table_close(_table); }
+  BinaryTable(const BinaryTable&) = delete;
+  BinaryTable& operator=(const BinaryTable&) = delete;
+  const hyb_binary_table* get() const { return _table; }
+  uint32_t chunk_count() const {
+    uint32_t chunks = 0;
+    check(hyb_binary_table_info(_table, nullptr, &chunks, nullptr));
+    return chunks;
+  }
+  uint32_t column_count() const {
+    uint32_t columns = 0;
+    check(hyb_binary_table_info(_table, nullptr, nullptr, &columns));
+    return columns;
+  }
+  std::string column_name(uint32_t column) const {
+    const char* name = nullptr;
+    check(hyb_binary_table_column(_table, column, &name, nullptr, nullptr));
+    return name;
+  }
+  // hyb_scan_predicate.value_id_bounds of a string predicate: DictionarySegment::lower_bound / upper_bound per chunk
+  std::vector<uint32_t> value_id_bounds(uint32_t column, const std::string& value, const std::optional<std::string>& value2 = std::nullopt) const {
+    std::vector<uint32_t> bounds(size_t{chunk_count()} * (value2 ? 4 : 2));
+    check(hyb_binary_table_value_id_bounds(_table, column, value.data(), value.size(), value2 ? value2->data() : nullptr,
+                                           value2 ? value2->size() : 0, bounds.data()));
+    return bounds;
+  }
+
+ private:
+  hyb_binary_table* _table = nullptr;
+};
+
 // A stored table in the device column pool (StorageManager::add_table's device twin).
 class DeviceTable {
  public:
   DeviceTable(std::shared_ptr<DeviceContext> context, const hyb_table_view& view) : _context(std::move(context)) {
     check(hyb_table_upload(_context->get(), &view, &_handle));
+  }
+  DeviceTable(std::shared_ptr<DeviceContext> context, const BinaryTable& file) : _context(std::move(context)) {
+    check(hyb_table_upload_binary(_context->get(), file.get(), &_handle));
   }
   ~DeviceTable() { hyb_table_drop(_context->get(), _handle); }
   DeviceTable(const DeviceTable&) = delete;

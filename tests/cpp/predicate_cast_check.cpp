@@ -64,6 +64,22 @@ int main() {
   ScanPredicate fractional{0, PC::BetweenInclusive, AllTypeVariant{2.5}, AllTypeVariant{7.0}, {}};
   EXPECT(!fractional.normalized(DataType::Int));
 
+  // BinaryTable: the reference's fixture AllTypesNullValues/Dictionary.bin (binary_parser_test.cpp:165-188) parses on the host
+  if (const char* fixture = std::getenv("HYB_BINARY_FIXTURE")) {
+    BinaryTable file(fixture, /*pinned=*/false);
+    EXPECT(file.column_count() == 5 && file.chunk_count() == 1);
+    EXPECT(file.column_name(0) == "a" && file.column_name(3) == "d");
+    const auto bounds = file.value_id_bounds(3, "one");   // column d holds {"one","two","three",NULL,"five"}: sorted five, one, three, two
+    EXPECT(bounds.size() == 2 && bounds[0] == 1 && bounds[1] == 2);
+    bool threw_missing = false;
+    try {
+      BinaryTable missing("not_existing_file", false);
+    } catch (const std::exception&) {
+      threw_missing = true;
+    }
+    EXPECT(threw_missing);
+  }
+
   if (failures) return EXIT_FAILURE;
   std::puts("predicate casts OK");
   return EXIT_SUCCESS;

@@ -119,6 +119,79 @@ def test_empty_table_and_sort_definitions():   # binary_parser_test.cpp:401-446
     assert parsed.sorted_columns[1] == [(1, descending_nulls_first)] and parsed.sorted_columns[2] == []
 
 
+def all_fixture_files():
+    out = []
+    for root, _, files in os.walk(BIN):
+        out.extend(os.path.join(root, name) for name in sorted(files) if name.endswith(".bin"))
+    return sorted(out)
+
+
+def assert_same_tables(native, python):
+    assert [(d.name, d.data_type, d.nullable) for d in native.column_definitions] == \
+           [(d.name, d.data_type, d.nullable) for d in python.column_definitions]
+    assert native.target_chunk_size == python.target_chunk_size and native.chunk_count == python.chunk_count
+    for a_chunk, b_chunk in zip(native.chunks, python.chunks):
+        for a, b in zip(a_chunk.segments, b_chunk.segments):
+            assert (a.encoding, a.data_type, a.row_count, a.vector_type, a.bit_width, a.dictionary_size) == \
+                   (b.encoding, b.data_type, b.row_count, b.vector_type, b.bit_width, b.dictionary_size)
+            assert np.array_equal(a.null_mask(), b.null_mask())
+            mask = ~a.null_mask()
+            assert np.array_equal(a.decode()[mask], b.decode()[mask])
+            for x, y in ((a.attribute_vector, b.attribute_vector), (a.dictionary_codes, b.dictionary_codes)):
+                assert (x is None) == (y is None)
+                if x is not None:
+                    assert np.array_equal(np.asarray(x), np.asarray(y))
+            for buffer in (a.values, a.nulls, a.attribute_vector, a.dictionary_codes):
+                if buffer is not None and buffer.nbytes:
+                    assert buffer.ctypes.data % 256 == 0
+
+
+@pytest.mark.parametrize("path", all_fixture_files(), ids=lambda p: os.path.relpath(p, BIN))
+def test_native_loader_matches_the_python_loader(path):
+    """hyb_binary_table_open (csrc/binary_loader.cu) against binary_table.read_binary_table on every reference fixture: same
+    definitions, encodings, vectors, dictionaries, group-by codes and sort information — or the same kind of failure."""
+    from hyrise_b200.binary_table import NativeBinaryTable
+
+    try:
+        python = read_binary_table(path)
+    except capi.UnsupportedOnDevice:
+        with pytest.raises(capi.UnsupportedOnDevice):
+            NativeBinaryTable(path)
+        return
+    except BinaryFormatError:
+        with pytest.raises(capi.HyriseB200Error) as error:
+            NativeBinaryTable(path)
+        assert error.value.status == capi.HYB_ERR_INVALID
+        return
+    native = NativeBinaryTable(path)
+    assert_same_tables(native.table, python.table)
+    assert native.sorted_columns == python.sorted_columns
+    native.close()
+
+
+def test_native_loader_errors_and_string_bounds(tmp_path):
+    from hyrise_b200.binary_table import NativeBinaryTable
+    from hyrise_b200.device import Predicate
+    from test_oracle_aggregate import lineitem_table
+
+    with pytest.raises(capi.HyriseB200Error) as error:
+        NativeBinaryTable("not_existing_file")
+    assert error.value.status == capi.HYB_ERR_NOT_FOUND
+    source, _ = lineitem_table()   # dbgen sf-0.01 lineitem, reference default encodings, strings + FoR + dictionaries
+    path = str(tmp_path / "lineitem.bin")
+    write_binary_table(source, path)
+    native = NativeBinaryTable(path)
+    assert_same_tables(native.table, read_binary_table(path).table)
+    assert len(native.host_blocks()) >= 1
+    for predicate in (Predicate(7, capi.PRED_LESS_THAN, b"1995-01-01"),
+                      Predicate(7, capi.PRED_BETWEEN_INCLUSIVE, b"1994-01-01", b"1994-12-31"), Predicate(5, capi.PRED_EQUALS, b"R"),
+                      Predicate(7, capi.PRED_GREATER_THAN, b"2999-01-01"), Predicate(7, capi.PRED_GREATER_THAN, b"")):
+        between = predicate.upper is not None
+        got = native.value_id_bounds(predicate.column_id, predicate.lower, predicate.upper if between else None)
+        assert np.array_equal(got, source.string_value_id_bounds(predicate))
+    native.close()
+
+
 @pytest.mark.parametrize("bitpacking", [False, True])
 def test_write_then_read_keeps_segments_bit_identical(tmp_path, bitpacking):
     rng = np.random.default_rng(5)
@@ -171,3 +244,14 @@ def test_binary_table_to_device_through_pinned_blocks(device, tmp_path):
     assert_aggregate_outputs_equal(got, orc.aggregate_hash(source, [5, 6], Q1_AGGREGATES, predicates=Q1_PREDICATES))
     table.drop()
     device.free_blocks(block_set)
+    # the same file through the native loader: parse into pinned blocks and upload in one call (hyb_table_upload_binary)
+    from hyrise_b200.binary_table import NativeBinaryTable
+    native = NativeBinaryTable(path, pinned=True)
+    table = native.upload(device)
+    result = device.table_scan(table, predicate)
+    assert_pos_lists_equal(result.to_host(), result.chunk_offsets(), orc.table_scan(source, predicate))
+    result.free()
+    got = device.aggregate_hash(table, [5, 6], Q1_AGGREGATES, predicates=Q1_PREDICATES)
+    assert_aggregate_outputs_equal(got, orc.aggregate_hash(source, [5, 6], Q1_AGGREGATES, predicates=Q1_PREDICATES))
+    table.drop()
+    native.close()

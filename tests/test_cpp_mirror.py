@@ -23,7 +23,9 @@ def test_mirror_predicate_casts_match_reference_expectations():
     expectations of the reference's lossless_predicate_cast_test.cpp:49-91 (host logic, no GPU)."""
     build = subprocess.run(["make", "-C", REPO, "build/predicate_cast_check"], capture_output=True, text=True)
     assert build.returncode == 0, build.stdout + build.stderr
-    run = subprocess.run([os.path.join(REPO, "build", "predicate_cast_check")], capture_output=True, text=True, timeout=60)
+    environment = dict(os.environ, HYB_BINARY_FIXTURE=os.path.join(REPO, "tests", "golden", "bin", "AllTypesNullValues", "Dictionary.bin"))
+    run = subprocess.run([os.path.join(REPO, "build", "predicate_cast_check")], capture_output=True, text=True, timeout=60,
+                         env=environment)   # + the BinaryTable wrapper on one of the reference's binary fixtures
     assert run.returncode == 0, run.stdout + run.stderr
 
 
