@@ -455,6 +455,70 @@ class JoinHash : public Operator<JoinOutput> {
   std::optional<int32_t> _radix_bits;
 };
 
+// ---- multi-GPU (one process per GPU) --------------------------------------------------------------------------------------
+// hyb_peer_group: this rank's exchange arena plus the mappings of its peers' arenas. The host transport (MPI, torch.distributed,
+// sockets ...) is only needed once, to all-gather the HYB_IPC_HANDLE_BYTES-byte handles.
+class PeerGroup {
+ public:
+  PeerGroup(std::shared_ptr<DeviceContext> context, uint32_t rank, uint32_t world, uint64_t tuple_capacity)
+      : _context(std::move(context)), _rank(rank), _world(world), _ipc_handle(HYB_IPC_HANDLE_BYTES) {
+    check(hyb_peer_group_create(_context->get(), rank, world, tuple_capacity, _ipc_handle.data(), &_handle));
+  }
+  ~PeerGroup() { hyb_peer_group_destroy(_context->get(), _handle); }
+  PeerGroup(const PeerGroup&) = delete;
+  PeerGroup& operator=(const PeerGroup&) = delete;
+  const std::vector<unsigned char>& ipc_handle() const { return _ipc_handle; }  // all-gather these, in rank order ...
+  void connect(const std::vector<unsigned char>& all_ipc_handles) {             // ... and hand the concatenation back
+    if (all_ipc_handles.size() != size_t{_world} * HYB_IPC_HANDLE_BYTES) throw std::logic_error("world x HYB_IPC_HANDLE_BYTES bytes expected");
+    check(hyb_peer_group_connect(_context->get(), _handle, all_ipc_handles.data()));
+  }
+  hyb_peer_group_t handle() const { return _handle; }
+  uint32_t rank() const { return _rank; }
+  uint32_t world() const { return _world; }
+  const std::shared_ptr<DeviceContext>& context() const { return _context; }
+  hyb_distributed_stats stats() const {
+    hyb_distributed_stats stats{};
+    check(hyb_peer_group_stats(_context->get(), _handle, &stats));
+    return stats;
+  }
+
+ private:
+  std::shared_ptr<DeviceContext> _context;
+  uint32_t _rank, _world;
+  std::vector<unsigned char> _ipc_handle;
+  hyb_peer_group_t _handle = 0;
+};
+
+// Inner JoinHash over the shards of all ranks (hyb_join_hash_distributed): `build` / `probe` are this rank's shards, the chunk
+// bases the global ids of their first chunks. get_output() holds GLOBAL RowIDs; stats().colocated tells the layout (1: this
+// rank's slice of every partition, 0: the partitions p with p % world == rank).
+class DistributedJoinHash : public Operator<JoinOutput> {
+ public:
+  DistributedJoinHash(std::shared_ptr<PeerGroup> group, OperatorInput build, OperatorInput probe, OperatorJoinPredicate predicate,
+                      ChunkID build_chunk_base, ChunkID probe_chunk_base, std::optional<int32_t> radix_bits = std::nullopt)
+      : _group(std::move(group)), _build(std::move(build)), _probe(std::move(probe)), _predicate(predicate),
+        _build_chunk_base(build_chunk_base), _probe_chunk_base(probe_chunk_base), _radix_bits(radix_bits) {}
+
+ protected:
+  std::shared_ptr<const JoinOutput> _on_execute() override {
+    hyb_context* context = _group->context()->get();
+    const hyb_join_side build{_build.table->handle(), _predicate.column_ids.first, _build.filter_handle()};
+    const hyb_join_side probe{_probe.table->handle(), _predicate.column_ids.second, _probe.filter_handle()};
+    hyb_join_result_t handle = 0;
+    check(hyb_join_hash_distributed(context, _group->handle(), &build, &probe, _build_chunk_base, _probe_chunk_base,
+                                    _radix_bits.value_or(-1), &handle));
+    check(hyb_last_operator_stats(context, &performance_data));
+    return std::make_shared<JoinOutput>(_group->context(), handle, /*left_is_build=*/true, /*emits_build_side=*/true);
+  }
+
+ private:
+  std::shared_ptr<PeerGroup> _group;
+  OperatorInput _build, _probe;
+  OperatorJoinPredicate _predicate;
+  ChunkID _build_chunk_base, _probe_chunk_base;
+  std::optional<int32_t> _radix_bits;
+};
+
 // An aggregate over a column, or over arithmetic on columns the reference would evaluate in a Projection below the
 // aggregate (fused here). COUNT(*) has no argument (INVALID_COLUMN_ID in the reference).
 struct AggregateDefinition {
