@@ -622,9 +622,24 @@ class AggregateHash : public Operator<AggregateOutput> {
     query.aggregates = definitions.data();
     hyb_context* context = _input.table->context()->get();
     hyb_aggregate_result_t handle = 0;
-    check(hyb_aggregate_hash(context, &query, &handle));
+    if (_group) {
+      // every rank aggregates its shard; low cardinality: every rank gets the complete result, high cardinality: the groups
+      // this rank owns (PeerGroup::stats().aggregate_partitioned)
+      check(hyb_aggregate_hash_distributed(context, _group->handle(), &query, _chunk_id_base, _position_base, &handle));
+    } else {
+      check(hyb_aggregate_hash(context, &query, &handle));
+    }
     check(hyb_last_operator_stats(context, &performance_data));
     return std::make_shared<AggregateOutput>(_input.table->context(), handle);
+  }
+
+ public:
+  // Multi-GPU: `input` is this rank's shard; chunk_id_base = global id of its first chunk, position_base = rows of the global
+  // table before it (call before execute()).
+  void set_peer_group(std::shared_ptr<PeerGroup> group, ChunkID chunk_id_base, uint64_t position_base) {
+    _group = std::move(group);
+    _chunk_id_base = chunk_id_base;
+    _position_base = position_base;
   }
 
  private:
@@ -632,6 +647,9 @@ class AggregateHash : public Operator<AggregateOutput> {
   std::vector<AggregateDefinition> _aggregates;
   std::vector<ColumnID> _groupby_column_ids;
   std::vector<ScanPredicate> _fused_predicates;
+  std::shared_ptr<PeerGroup> _group;
+  ChunkID _chunk_id_base = 0;
+  uint64_t _position_base = 0;
 };
 
 }  // namespace hyrise_b200
